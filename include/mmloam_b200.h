@@ -1,0 +1,168 @@
+/*
+ * mmloam_b200 — C-ABI of the B200-native mm-loam scan-matching hot path.
+ *
+ * Drop-in boundary for TIERS/multi-modal-loam (reference paths relative to
+ * /root/reference/mm-loam). The reference has no FFI layer: the path sits behind the
+ * C++ member functions listed at each entry point below; the header-only adapters in
+ * multi-modal-loam_b200/host/ turn those calls into these.
+ *
+ * Conventions: every function returns 0 on success or a negative MML_ERR_* code and
+ * never throws. Pointers are caller-owned HOST buffers unless the name ends in `_dev`.
+ * Buffers are little-endian and tightly packed. A context is not re-entrant: use one
+ * context per host thread (the reference calls detectFeaturePoints from 6 threads,
+ * src/unionFeatureExtract.cpp:1008-1015 — the batched extractor takes all lines of a scan
+ * in one call instead). There is NO CPU fallback: without a CUDA device
+ * mml_ctx_create fails with MML_ERR_NO_DEVICE.
+ *
+ * Point layout: float4 (x, y, z, intensity) replaces pcl::PointXYZINormal (48 B);
+ * side arrays carry line id (u16), sweep fraction (f32) and label (u8).
+ */
+#ifndef MMLOAM_B200_H
+#define MMLOAM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MML_OK 0
+#define MML_ERR_INVALID (-1)    /* bad argument */
+#define MML_ERR_NO_DEVICE (-2)  /* no usable CUDA device */
+#define MML_ERR_CUDA (-3)       /* CUDA runtime error, see mml_last_error */
+#define MML_ERR_CAPACITY (-4)   /* input exceeds a documented limit */
+#define MML_ERR_STATE (-5)      /* call order (e.g. associate before map_set) */
+
+typedef struct mml_ctx mml_ctx;
+
+int mml_version(void);
+/* Opaque handle owning streams, scratch and the resident feature maps. */
+int mml_ctx_create(int device, int stream_count, mml_ctx** out);
+int mml_ctx_destroy(mml_ctx* ctx);
+const char* mml_last_error(const mml_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+long long mml_launch_count(const mml_ctx* ctx);
+int mml_sync(mml_ctx* ctx);
+
+/* ---- A1 (+ glue): feature_extraction::detectFeaturePoints, FE.cpp:341-844, called per
+ * line at FE.cpp:1010 / 1229; label write-back FE.cpp:1016-1023, 1233-1240.
+ * One call labels every line of a scan: label 0 none / 1 corner ("sharp") / 2 surf
+ * ("flat") in input order = the reference's normal_z. line_id[i] < n_lines.           */
+int mml_extract_features(mml_ctx* ctx, const float* xyzi, const uint16_t* line_id, int n, int n_lines,
+                         uint8_t* out_label, int* out_n_sharp, int* out_n_flat);
+/* Batched form: scans are concatenated, scan s = [scan_offsets[s], scan_offsets[s+1]). */
+int mml_extract_features_batch(mml_ctx* ctx, const float* xyzi, const uint16_t* line_id,
+                               const int* scan_offsets, int n_scans, int n_lines, uint8_t* out_label,
+                               int* out_n_sharp, int* out_n_flat);
+
+/* ---- A2: getVeloFeature ring + relative time, FE.cpp:1136-1195. line_out = -1 rejected. */
+int mml_velo_ring_time(mml_ctx* ctx, const float* xyzi, int n, int16_t* line_out, float* reltime_out);
+/* ---- A3: getHoriFeatureExtract filter, FE.cpp:985-998 (CustomPoint fields as arrays). */
+int mml_hori_filter(mml_ctx* ctx, const uint32_t* offset_time, const float* xyz3, const uint8_t* line, int n,
+                    uint8_t* keep, float* reltime_out);
+
+/* ---- A4: RemoveLidarDistortion, src/unionPoseEstimation.cpp:402-421. In place.      */
+int mml_undistort(mml_ctx* ctx, float* xyzi, const float* s, int n, const double* dR9, const double* dt3);
+
+/* ---- A6: pcl::VoxelGrid::filter as called at src/lio/Estimator.cpp:1015-1024.
+ * out has capacity n points; output ordered by voxel index.                           */
+int mml_voxel_downsample(mml_ctx* ctx, const float* xyzi, int n, float leaf, float* out, int* m_out);
+
+/* ---- map upload: replaces the kd-tree (re)builds at EST.cpp:1159-1179 and the cube
+ * binning of src/lio/Map_Manager.cpp:159-175. Builds the device spatial hash.
+ * kind: 0 corner-global, 1 surf-global, 2 corner-local, 3 surf-local.
+ * cube_centre3 = (laserCloudCenWidth, CenHeight, CenDepth), NULL = (10, 5, 10).       */
+#define MML_MAP_CORNER_GLOBAL 0
+#define MML_MAP_SURF_GLOBAL 1
+#define MML_MAP_CORNER_LOCAL 2
+#define MML_MAP_SURF_LOCAL 3
+int mml_map_set(mml_ctx* ctx, int kind, const float* xyzi, int m, const int* cube_centre3);
+/* Same with an explicit hash-cell edge in metres (0 = choose automatically).           */
+int mml_map_set_ex(mml_ctx* ctx, int kind, const float* xyzi, int m, const int* cube_centre3, float cell);
+/* info8 = [valid, points, cell edge, dim x, dim y, dim z, cells, cells per 50 m cube]  */
+int mml_map_info(mml_ctx* ctx, int kind, double* info8);
+
+/* ---- A7 / A8: Estimator::processPointToLine EST.cpp:148-365 and
+ * Estimator::processPointToPlanVec EST.cpp:573-777 (incl. A5 pointAssociateToMap +
+ * cube rule, MM.cpp:75-89, 583-629).
+ * kind 0: line features  [pointOri(3) lineP1(3) lineP2(3) error valid src]
+ * kind 1: plane features [pointOri(3) pointProj(3) normal(3) error valid src]
+ * out_feat: nq x 12 doubles, slot i belongs to query i; valid = -1 no feature,
+ * 0 feature with |error| <= 1e-5 (dropped by EST.cpp:1313/1385), 1 used.
+ * normal_moment9 / n_normals (kind 1, may be NULL): sum n n^T and count of accepted planes,
+ * the input of checkLocalizability (EST.cpp:536-565).                                  */
+int mml_associate(mml_ctx* ctx, int kind, const float* q_xyzi, int nq, const double* T_wl16, double thres_dist,
+                  double* out_feat, int* n_feat, double* normal_moment9, int* n_normals);
+
+/* ---- A9-A11: Cost_NavState_IMU_Line / _Plan_Vec evaluation + Huber + per-pose
+ * accumulation, include/utils/ceresfunc.h:412-440, 533-555, 33-63 (what ceres::Solve at
+ * EST.cpp:1425-1432 evaluates). x6 = [t_wb, phi_wb]; T_bl16 = exTlb^-1 row-major.
+ * Outputs H = sum J^T J (6x6 row-major), g = sum J^T r, cost = 1/2 sum rho.
+ * huber_a <= 0 disables the loss (window size 5, EST.cpp:1219).                        */
+int mml_accumulate(mml_ctx* ctx, const double* line_feat, int n_line, const double* plane_feat, int n_plane,
+                   const double* x6, const double* T_bl16, double plan_weight_tan, double huber_a, double* H36,
+                   double* g6, double* cost);
+
+/* ---- A12: Estimator::Estimate outer loop for one frame, EST.cpp:1143-1581 (window size
+ * 1, the branch the shipped launch file runs): <= max_outer x { associate ; dogleg solve
+ * <= max_inner iterations } entirely on the device (one CUDA-graph launch, no host round
+ * trip per iteration). P3 / q_wxyz4 = body pose, updated in place.                     */
+typedef struct {
+  int max_outer;          /* 5    EST.cpp:1210 */
+  int max_inner;          /* 10   EST.cpp:1428 */
+  double lidar_m;         /* 1.5e-3 include/IMUIntegrator/IMUIntegrator.h:83 */
+  double plan_weight_tan; /* 0.0  EST.cpp:1206 */
+  double thres0, thres1, thres2; /* 25, 10, 1  EST.cpp:1207, 1377-1381 */
+  int use_huber;          /* 1    EST.cpp:1221 */
+  int reserved;
+} mml_est_params;
+void mml_est_params_default(mml_est_params* p);
+/* stats (may be NULL, 16 doubles): [outer_iters, inner_iters, n_line, n_plane, final_cost,
+ * min_singular_value, is_degenerate, ...]                                              */
+int mml_estimate(mml_ctx* ctx, const float* corner_xyzi, int n_corner, const float* surf_xyzi, int n_surf,
+                 const double* exTlb16, double* P3, double* q_wxyz4, const mml_est_params* prm, double* stats);
+
+/* ---- whole per-scan path, device resident between stages:
+ * extract (A1) -> undistort (A4) -> label split + voxel filter (A6) -> estimate (A12).
+ * This is the loop body of process(), src/unionPoseEstimation.cpp:862-872, for one scan.
+ * s = per-point sweep fraction (normal_x). dR9/dt3 = predicted motion for undistortion.
+ * out_counts (may be NULL, 4 ints): n_sharp, n_flat, n_corner_ds, n_surf_ds.           */
+int mml_scan_to_pose(mml_ctx* ctx, const float* xyzi, const uint16_t* line_id, const float* s, int n, int n_lines,
+                     const double* dR9, const double* dt3, float leaf_corner, float leaf_surf,
+                     const double* exTlb16, double* P3, double* q_wxyz4, const mml_est_params* prm,
+                     double* stats, int* out_counts);
+/* Same with inputs already resident in device memory (bench.py's kernel-only `value`). */
+int mml_scan_to_pose_dev(mml_ctx* ctx, const void* xyzi_dev, const void* line_id_dev, const void* s_dev, int n,
+                         int n_lines, const double* dR9, const double* dt3, float leaf_corner, float leaf_surf,
+                         const double* exTlb16, double* P3, double* q_wxyz4, const mml_est_params* prm,
+                         double* stats, int* out_counts);
+
+/* ---- device-resident building blocks used by bench.py's roofline sweep (S4):
+ * queries and maps stay in HBM; one call = one association or one evaluation.          */
+int mml_frame_set(mml_ctx* ctx, const float* corner_xyzi, int n_corner, const float* surf_xyzi, int n_surf);
+int mml_frame_associate(mml_ctx* ctx, const double* T_wl16, double thres_dist, int* n_line, int* n_plane,
+                        double* normal_moment9, int* n_normals);
+int mml_frame_accumulate(mml_ctx* ctx, const double* x6, const double* T_bl16, double plan_weight_tan,
+                         double huber_a, double* H36, double* g6, double* cost);
+/* Features of the frame slot as host records (kind 0 line / 1 plane, n_query x 12).    */
+int mml_frame_get_features(mml_ctx* ctx, int kind, double* out_feat);
+/* Raw device buffers for callers that keep scans resident in HBM (bench.py).           */
+int mml_dev_alloc(mml_ctx* ctx, size_t bytes, void** out);
+int mml_dev_free(mml_ctx* ctx, void* p);
+int mml_dev_upload(mml_ctx* ctx, void* dst_dev, const void* src, size_t bytes);
+/* asynchronous variants for timing: enqueue `repeat` launches, no host read-back.      */
+int mml_frame_associate_async(mml_ctx* ctx, const double* T_wl16, double thres_dist, int repeat);
+int mml_frame_accumulate_async(mml_ctx* ctx, const double* x6, const double* T_bl16, double plan_weight_tan,
+                               double huber_a, int repeat);
+/* CUDA-event timing on the context's stream (bench.py cannot see it from torch).       */
+int mml_timer_start(mml_ctx* ctx);
+int mml_timer_stop_ms(mml_ctx* ctx, float* ms);
+/* Partial normal equations of this rank's map shard, left on the device for an NCCL
+ * all-reduce: returns the device pointer to 28 doubles [H upper triangle 21, g 6, cost]. */
+int mml_frame_accumulate_partial_dev(mml_ctx* ctx, const double* x6, const double* T_bl16, double plan_weight_tan,
+                                     double huber_a, void** partial28_dev);
+void* mml_stream_handle(mml_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,405 @@
+"""mmloam_b200 — B200-native scan-matching hot path of TIERS/multi-modal-loam.
+
+Python side of the C-ABI in include/mmloam_b200.h (ctypes; no torch types cross the
+boundary). The compute lives in libmmloam_b200.so (hand-written sm_100a CUDA, csrc/).
+There is no CPU fallback: importing works anywhere, creating a Context needs a GPU and
+the built library, and fails loudly otherwise.
+
+Host-side mirror of the reference call surface (names follow the reference):
+  feature_extraction.detectFeaturePoints   mm-loam/src/unionFeatureExtract.cpp:341
+  LidarFeatureExtractor.detectFeaturePoint  (LIO-Livox spelling of the same method)
+  Estimator.processPointToLine / processPointToPlanVec / EstimateLidarPose
+                                            mm-loam/include/Estimator/Estimator.h:159-214
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmloam_b200.so")
+_lib = None
+
+MAP_CORNER_GLOBAL, MAP_SURF_GLOBAL, MAP_CORNER_LOCAL, MAP_SURF_LOCAL = 0, 1, 2, 3
+
+ERRORS = {0: "ok", -1: "invalid argument", -2: "no CUDA device", -3: "CUDA error", -4: "capacity exceeded",
+          -5: "bad call order"}
+
+# every symbol include/mmloam_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "mml_version", "mml_ctx_create", "mml_ctx_destroy", "mml_last_error", "mml_launch_count", "mml_sync",
+    "mml_extract_features", "mml_extract_features_batch", "mml_velo_ring_time", "mml_hori_filter", "mml_undistort",
+    "mml_voxel_downsample", "mml_map_set", "mml_associate", "mml_accumulate", "mml_est_params_default",
+    "mml_estimate", "mml_scan_to_pose", "mml_scan_to_pose_dev", "mml_frame_set", "mml_frame_associate",
+    "mml_frame_accumulate", "mml_frame_associate_async", "mml_frame_accumulate_async", "mml_timer_start",
+    "mml_timer_stop_ms", "mml_frame_accumulate_partial_dev", "mml_stream_handle",
+]
+
+
+class MmlError(RuntimeError):
+    pass
+
+
+class EstParams(C.Structure):
+    _fields_ = [("max_outer", C.c_int), ("max_inner", C.c_int), ("lidar_m", C.c_double),
+                ("plan_weight_tan", C.c_double), ("thres0", C.c_double), ("thres1", C.c_double),
+                ("thres2", C.c_double), ("use_huber", C.c_int), ("reserved", C.c_int)]
+
+
+def load_library():
+    """dlopen libmmloam_b200.so. Raises MmlError if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MmlError(f"{LIB_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a). "
+                           "mmloam_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        lib.mml_last_error.restype = C.c_char_p
+        lib.mml_last_error.argtypes = [C.c_void_p]
+        lib.mml_launch_count.restype = C.c_longlong
+        lib.mml_launch_count.argtypes = [C.c_void_p]
+        lib.mml_stream_handle.restype = C.c_void_p
+        lib.mml_stream_handle.argtypes = [C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def est_params(**kw):
+    p = EstParams()
+    load_library().mml_est_params_default(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Context:
+    """Owns one mml_ctx (streams, scratch, resident maps). One per host thread."""
+
+    def __init__(self, device=0, streams=1):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.mml_ctx_create(int(device), int(streams), C.byref(h))
+        if rc != 0:
+            raise MmlError(f"mml_ctx_create failed: {ERRORS.get(rc, rc)} (a CUDA device is required; no CPU fallback)")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mml_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self.lib.mml_last_error(self.h)
+            raise MmlError(f"{ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    @property
+    def launches(self):
+        return int(self.lib.mml_launch_count(self.h))
+
+    def sync(self):
+        self._ck(self.lib.mml_sync(self.h))
+
+    # ---- A1
+    def extract_features(self, xyzi, line_id, n_lines):
+        xyzi = _f32(xyzi).reshape(-1, 4)
+        line_id = np.ascontiguousarray(line_id, np.uint16)
+        n = xyzi.shape[0]
+        label = np.zeros(max(n, 1), np.uint8)
+        ns, nf = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.mml_extract_features(self.h, _p(xyzi), _p(line_id), n, int(n_lines), _p(label), C.byref(ns),
+                                               C.byref(nf)))
+        return label[:n], ns.value, nf.value
+
+    def extract_features_batch(self, xyzi, line_id, scan_offsets, n_lines):
+        xyzi = _f32(xyzi).reshape(-1, 4)
+        line_id = np.ascontiguousarray(line_id, np.uint16)
+        off = np.ascontiguousarray(scan_offsets, np.int32)
+        ns = off.shape[0] - 1
+        n = xyzi.shape[0]
+        label = np.zeros(max(n, 1), np.uint8)
+        n_sharp = np.zeros(max(ns, 1), np.int32)
+        n_flat = np.zeros(max(ns, 1), np.int32)
+        self._ck(self.lib.mml_extract_features_batch(self.h, _p(xyzi), _p(line_id), _p(off), ns, int(n_lines), _p(label),
+                                                     _p(n_sharp), _p(n_flat)))
+        return label[:n], n_sharp[:ns], n_flat[:ns]
+
+    # ---- A2 / A3
+    def velo_ring_time(self, xyzi):
+        xyzi = _f32(xyzi).reshape(-1, 4)
+        n = xyzi.shape[0]
+        line = np.zeros(max(n, 1), np.int16)
+        rt = np.zeros(max(n, 1), np.float32)
+        self._ck(self.lib.mml_velo_ring_time(self.h, _p(xyzi), n, _p(line), _p(rt)))
+        return line[:n], rt[:n]
+
+    def hori_filter(self, offset_time, xyz, line):
+        offset_time = np.ascontiguousarray(offset_time, np.uint32)
+        xyz = _f32(xyz).reshape(-1, 3)
+        line = np.ascontiguousarray(line, np.uint8)
+        n = xyz.shape[0]
+        keep = np.zeros(max(n, 1), np.uint8)
+        rt = np.zeros(max(n, 1), np.float32)
+        self._ck(self.lib.mml_hori_filter(self.h, _p(offset_time), _p(xyz), _p(line), n, _p(keep), _p(rt)))
+        return keep[:n], rt[:n]
+
+    # ---- A4
+    def undistort(self, xyzi, s, dR, dt):
+        out = _f32(xyzi).reshape(-1, 4).copy()
+        s = _f32(s)
+        dR = _f64(dR).reshape(9)
+        dt = _f64(dt).reshape(3)
+        self._ck(self.lib.mml_undistort(self.h, _p(out), _p(s), out.shape[0], _p(dR), _p(dt)))
+        return out
+
+    # ---- A6
+    def voxel_downsample(self, xyzi, leaf):
+        xyzi = _f32(xyzi).reshape(-1, 4)
+        n = xyzi.shape[0]
+        out = np.zeros((max(n, 1), 4), np.float32)
+        m = C.c_int(0)
+        self._ck(self.lib.mml_voxel_downsample(self.h, _p(xyzi), n, C.c_float(leaf), _p(out), C.byref(m)))
+        return out[: m.value].copy()
+
+    # ---- maps
+    def map_set(self, kind, xyzi, cen=(10, 5, 10), cell=0.0):
+        xyzi = _f32(xyzi).reshape(-1, 4)
+        cen = np.asarray(cen, np.int32)
+        self._ck(self.lib.mml_map_set_ex(self.h, int(kind), _p(xyzi), xyzi.shape[0], _p(cen), C.c_float(cell)))
+
+    def map_info(self, kind):
+        info = np.zeros(8, np.float64)
+        self._ck(self.lib.mml_map_info(self.h, int(kind), _p(info)))
+        return dict(valid=bool(info[0]), m=int(info[1]), cell=float(info[2]), dim=tuple(int(v) for v in info[3:6]),
+                    ncell=int(info[6]), k_per_cube=int(info[7]))
+
+    # ---- A7 / A8
+    def associate(self, kind, q, T_wl, thres):
+        q = _f32(q).reshape(-1, 4)
+        T = _f64(T_wl).reshape(16)
+        nq = q.shape[0]
+        feat = np.zeros((max(nq, 1), 12), np.float64)
+        nf, nn = C.c_int(0), C.c_int(0)
+        M = np.zeros(9, np.float64)
+        self._ck(self.lib.mml_associate(self.h, int(kind), _p(q), nq, _p(T), C.c_double(thres), _p(feat), C.byref(nf), _p(M),
+                                        C.byref(nn)))
+        return feat[:nq], nf.value, M.reshape(3, 3), nn.value
+
+    # ---- A9-A11
+    def accumulate(self, line_feat, plane_feat, x6, T_bl, plan_weight_tan=0.0, huber_a=0.1 / 1.5e-3):
+        lf = _f64(line_feat).reshape(-1, 12)
+        pf = _f64(plane_feat).reshape(-1, 12)
+        x6 = _f64(x6)
+        T = _f64(T_bl).reshape(16)
+        H = np.zeros(36)
+        g = np.zeros(6)
+        cost = C.c_double(0)
+        self._ck(self.lib.mml_accumulate(self.h, _p(lf), lf.shape[0], _p(pf), pf.shape[0], _p(x6), _p(T),
+                                         C.c_double(plan_weight_tan), C.c_double(huber_a), _p(H), _p(g), C.byref(cost)))
+        return H.reshape(6, 6), g, cost.value
+
+    # ---- frame slot (device resident)
+    def frame_set(self, corner, surf):
+        corner = _f32(corner).reshape(-1, 4)
+        surf = _f32(surf).reshape(-1, 4)
+        self._ck(self.lib.mml_frame_set(self.h, _p(corner), corner.shape[0], _p(surf), surf.shape[0]))
+        self._nq = (corner.shape[0], surf.shape[0])
+
+    def frame_associate(self, T_wl, thres):
+        T = _f64(T_wl).reshape(16)
+        nl, np_, nn = C.c_int(0), C.c_int(0), C.c_int(0)
+        M = np.zeros(9)
+        self._ck(self.lib.mml_frame_associate(self.h, _p(T), C.c_double(thres), C.byref(nl), C.byref(np_), _p(M), C.byref(nn)))
+        return nl.value, np_.value, M.reshape(3, 3), nn.value
+
+    def frame_get_features(self, kind):
+        nq = self._nq[kind]
+        out = np.zeros((max(nq, 1), 12), np.float64)
+        self._ck(self.lib.mml_frame_get_features(self.h, int(kind), _p(out)))
+        return out[:nq]
+
+    def frame_accumulate(self, x6, T_bl, plan_weight_tan=0.0, huber_a=0.1 / 1.5e-3):
+        x6 = _f64(x6)
+        T = _f64(T_bl).reshape(16)
+        H = np.zeros(36)
+        g = np.zeros(6)
+        cost = C.c_double(0)
+        self._ck(self.lib.mml_frame_accumulate(self.h, _p(x6), _p(T), C.c_double(plan_weight_tan), C.c_double(huber_a),
+                                               _p(H), _p(g), C.byref(cost)))
+        return H.reshape(6, 6), g, cost.value
+
+    def frame_associate_async(self, T_wl, thres, repeat=1):
+        T = _f64(T_wl).reshape(16)
+        self._ck(self.lib.mml_frame_associate_async(self.h, _p(T), C.c_double(thres), int(repeat)))
+
+    def frame_accumulate_async(self, x6, T_bl, plan_weight_tan=0.0, huber_a=0.1 / 1.5e-3, repeat=1):
+        x6 = _f64(x6)
+        T = _f64(T_bl).reshape(16)
+        self._ck(self.lib.mml_frame_accumulate_async(self.h, _p(x6), _p(T), C.c_double(plan_weight_tan),
+                                                     C.c_double(huber_a), int(repeat)))
+
+    def timer_start(self):
+        self._ck(self.lib.mml_timer_start(self.h))
+
+    def timer_stop_ms(self):
+        ms = C.c_float(0)
+        self._ck(self.lib.mml_timer_stop_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    # ---- A12
+    def estimate(self, corner, surf, exTlb, P, q_wxyz, params=None):
+        corner = _f32(corner).reshape(-1, 4)
+        surf = _f32(surf).reshape(-1, 4)
+        ex = _f64(exTlb).reshape(16)
+        P = _f64(P).copy()
+        q = _f64(q_wxyz).copy()
+        stats = np.zeros(16)
+        prm = params if params is not None else est_params()
+        self._ck(self.lib.mml_estimate(self.h, _p(corner), corner.shape[0], _p(surf), surf.shape[0], _p(ex), _p(P), _p(q),
+                                       C.byref(prm), _p(stats)))
+        return P, q, stats
+
+    # ---- whole per-scan path
+    def scan_to_pose(self, xyzi, line_id, s, n_lines, dR, dt, exTlb, P, q_wxyz, leaf_corner=0.4, leaf_surf=0.2,
+                     params=None):
+        xyzi = _f32(xyzi).reshape(-1, 4)
+        line_id = np.ascontiguousarray(line_id, np.uint16)
+        s = _f32(s) if s is not None else None
+        dR = _f64(dR).reshape(9) if dR is not None else None
+        dt = _f64(dt).reshape(3) if dt is not None else None
+        ex = _f64(exTlb).reshape(16)
+        P = _f64(P).copy()
+        q = _f64(q_wxyz).copy()
+        stats = np.zeros(16)
+        counts = np.zeros(4, np.int32)
+        prm = params if params is not None else est_params()
+        self._ck(self.lib.mml_scan_to_pose(self.h, _p(xyzi), _p(line_id), _p(s), xyzi.shape[0], int(n_lines), _p(dR), _p(dt),
+                                           C.c_float(leaf_corner), C.c_float(leaf_surf), _p(ex), _p(P), _p(q),
+                                           C.byref(prm), _p(stats), _p(counts)))
+        return P, q, stats, counts
+
+    # ---- device-resident scans (bench.py)
+    def dev_upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        ptr = C.c_void_p()
+        self._ck(self.lib.mml_dev_alloc(self.h, C.c_size_t(arr.nbytes), C.byref(ptr)))
+        self._ck(self.lib.mml_dev_upload(self.h, ptr, _p(arr), C.c_size_t(arr.nbytes)))
+        return ptr
+
+    def dev_free(self, ptr):
+        self._ck(self.lib.mml_dev_free(self.h, ptr))
+
+    def scan_to_pose_dev(self, xyzi_dev, line_dev, s_dev, n, n_lines, dR, dt, exTlb, P, q_wxyz, leaf_corner=0.4,
+                         leaf_surf=0.2, params=None):
+        dR = _f64(dR).reshape(9) if dR is not None else None
+        dt = _f64(dt).reshape(3) if dt is not None else None
+        ex = _f64(exTlb).reshape(16)
+        P = _f64(P).copy()
+        q = _f64(q_wxyz).copy()
+        stats = np.zeros(16)
+        counts = np.zeros(4, np.int32)
+        prm = params if params is not None else est_params()
+        self._ck(self.lib.mml_scan_to_pose_dev(self.h, xyzi_dev, line_dev, s_dev, int(n), int(n_lines), _p(dR), _p(dt),
+                                               C.c_float(leaf_corner), C.c_float(leaf_surf), _p(ex), _p(P), _p(q),
+                                               C.byref(prm), _p(stats), _p(counts)))
+        return P, q, stats, counts
+
+
+# ---------------------------------------------------------------------------------------
+# Host-side mirror of the reference's call surface
+# ---------------------------------------------------------------------------------------
+class feature_extraction:
+    """Mirror of `class feature_extraction` (mm-loam/src/unionFeatureExtract.cpp:143)."""
+
+    def __init__(self, ctx: Context | None = None):
+        self.ctx = ctx or Context()
+
+    def detectFeaturePoints(self, cloud_xyzi):
+        """FE.cpp:341-343: one scan line in, (pointsLessSharp, pointsLessFlat) line-local indices out."""
+        cloud = _f32(cloud_xyzi).reshape(-1, 4)
+        n = cloud.shape[0]
+        label, _, _ = self.ctx.extract_features(cloud, np.zeros(n, np.uint16), 1)
+        return np.nonzero(label == 1)[0].astype(np.int32), np.nonzero(label == 2)[0].astype(np.int32)
+
+    def getFeatures(self, cloud_xyzi, line_id, n_lines):
+        """Split / detect / label glue of getHoriFeatureExtract (FE.cpp:952-1035) and getVeloFeature
+        (FE.cpp:1113-1317): returns normal_z-style labels (0 / 1 corner / 2 surf) in input order."""
+        return self.ctx.extract_features(cloud_xyzi, line_id, n_lines)[0]
+
+
+class LidarFeatureExtractor(feature_extraction):
+    """LIO-Livox spelling of the same class (SURVEY.md §0 naming caveat)."""
+
+    def detectFeaturePoint(self, cloud_xyzi):
+        return self.detectFeaturePoints(cloud_xyzi)
+
+
+class Estimator:
+    """Mirror of the hot-path members of `class Estimator` (include/Estimator/Estimator.h:26)."""
+
+    SLIDEWINDOWSIZE = 5  # EST.h:30
+
+    def __init__(self, filter_corner=0.4, filter_surf=0.2, ctx: Context | None = None):
+        self.ctx = ctx or Context()
+        self.filter_corner = float(filter_corner)
+        self.filter_surf = float(filter_surf)
+        self.thres_dist = 1.0  # EST.h:336
+        self._fail_detected = False
+
+    def setLocalMap(self, corner_xyzi, surf_xyzi):
+        """laserCloudCornerFromLocal / SurfFromLocal + kd-tree rebuild (EST.cpp:1159-1167)."""
+        self.ctx.map_set(MAP_CORNER_LOCAL, corner_xyzi)
+        self.ctx.map_set(MAP_SURF_LOCAL, surf_xyzi)
+
+    def setGlobalMap(self, corner_xyzi, surf_xyzi, cen=(10, 5, 10)):
+        """GlobalCornerMap / GlobalSurfMap copies (EST.cpp:1171-1182)."""
+        self.ctx.map_set(MAP_CORNER_GLOBAL, corner_xyzi, cen)
+        self.ctx.map_set(MAP_SURF_GLOBAL, surf_xyzi, cen)
+
+    def processPointToLine(self, laserCloudCorner, m4d):
+        """EST.h:159-165. Returns the FeatureLine records (12 doubles each, see mmloam_b200.h)."""
+        feat, n, _, _ = self.ctx.associate(0, laserCloudCorner, m4d, self.thres_dist)
+        return feat[feat[:, 10] >= 0]
+
+    def processPointToPlanVec(self, laserCloudSurf, m4d):
+        """EST.h:179-186. Returns (FeaturePlanVec records, is_degenerate)."""
+        feat, n, M, nn = self.ctx.associate(1, laserCloudSurf, m4d, self.thres_dist)
+        sv = -1.0
+        if nn > 10:  # checkLocalizability, EST.cpp:536-565
+            sv = float(np.sqrt(max(np.linalg.eigvalsh(M)[0], 0.0)))
+        if sv < 2.0:
+            self._fail_detected = True
+        return feat[feat[:, 10] >= 0], sv < 3.0
+
+    def EstimateLidarPose(self, cloud_xyzi_labelled, label, exTlb, P, q_wxyz, params=None):
+        """EST.h:211-214 for a one-frame list: label split + voxel filter (EST.cpp:992-1026), Estimate
+        (EST.cpp:1143-1581). Returns (P, q, stats)."""
+        cloud = _f32(cloud_xyzi_labelled).reshape(-1, 4)
+        corner = self.ctx.voxel_downsample(cloud[label == 1], self.filter_corner)
+        surf = self.ctx.voxel_downsample(cloud[label == 2], self.filter_surf)
+        P, q, stats = self.ctx.estimate(corner, surf, exTlb, P, q_wxyz, params)
+        self._fail_detected = bool(stats[6])
+        return P, q, stats
+
+    def failureDetected(self):
+        return self._fail_detected

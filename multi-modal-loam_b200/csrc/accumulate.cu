@@ -1,0 +1,650 @@
+// Residual + Jacobian evaluation, robust loss, per-pose normal-equation accumulation and the
+// device-side trust-region loop.
+//
+// Replaces what ceres::Solve (EST.cpp:1425-1432) evaluates for the LiDAR factors:
+//   Cost_NavState_IMU_Line::operator()      include/utils/ceresfunc.h:412-440
+//   Cost_NavState_IMU_Plan_Vec::operator()  include/utils/ceresfunc.h:533-555
+//   HuberLoss + Corrector (rho'' <= 0)      mirrored by ResidualBlockInfo::Evaluate, CF.h:33-63
+// and, for window size 1, Estimator::Estimate's outer loop (EST.cpp:1211-1579) with the
+// DOGLEG / DENSE_SCHUR trust-region iteration restated on the 6x6 normal equations.
+//
+// One launch of k_accumulate = one evaluation: each thread streams 48 B feature records
+// (3 x LDG.128, coalesced), evaluates residual and analytic Jacobian in float64, keeps
+// 28 partial sums (cost, g[6], upper H[21]) in registers, then warp-shuffle + shared-memory
+// block reduction; the last CTA to finish sums the per-CTA partials in a fixed order
+// (bit-reproducible) and - when the solver state is attached - performs the dogleg update,
+// so an inner iteration is exactly one kernel. The whole Estimate loop is captured in a CUDA
+// graph: no host round trip until the final pose is read back.
+#include "common.cuh"
+#include "smallmath.cuh"
+#include <float.h>
+#include <math.h>
+
+namespace mml {
+
+struct EstState {
+  // pose of the body frame (EST.h:33-56) and extrinsics
+  double P[3], Q[4];
+  double Rbl[9], Pbl[3];
+  double T_wl[16];
+  float thres;
+  int n_line, n_plane;
+  // control
+  int done_outer, done_inner, outer_it, inner_it, first, total_inner, is_degenerate;
+  int max_outer, max_inner;
+  double lidar_m, w_tan, huber_a, thres_sched[3];
+  // trust-region state (Ceres 2.1 TrustRegionMinimizer + DoglegStrategy)
+  double x[6], x_cand[6], x_best[6];
+  double cost, min_cost, H[36], g[6], scale[6];
+  double radius, mu, alpha, dogleg_norm, model_change, step_norm, x_norm;
+  double diag[6], grad[6], gn[6];
+  int reuse, num_invalid;
+  double q_before[4], t_before[3];
+  double min_sv, final_cost;
+};
+
+struct PoseLin {
+  double R[9], t[3], Jr[9], Rbl[9], Pbl[3];
+};
+
+__device__ inline void right_jacobian(const double* phi, double* Jr) {
+  const double th2 = (phi[0] * phi[0] + phi[1] * phi[1]) + phi[2] * phi[2];
+  double a, b;
+  if (th2 < 1e-12) {
+    a = 0.5 - th2 / 24.0;
+    b = 1.0 / 6.0 - th2 / 120.0;
+  } else {
+    const double th = sqrt(th2);
+    a = (1.0 - cos(th)) / th2;
+    b = (th - sin(th)) / (th2 * th);
+  }
+  const double K[9] = {0, -phi[2], phi[1], phi[2], 0, -phi[0], -phi[1], phi[0], 0};
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) {
+      double s = 0;
+      for (int k = 0; k < 3; k++) s += K[3 * r + k] * K[3 * k + c];
+      Jr[3 * r + c] = -a * K[3 * r + c] + b * s + (r == c ? 1.0 : 0.0);
+    }
+}
+
+__device__ inline void make_pose(const double* x6, const double* Rbl, const double* Pbl, PoseLin& L) {
+  const Quat q = so3_exp(x6 + 3);
+  quat_to_R(q, L.R);
+  L.t[0] = x6[0]; L.t[1] = x6[1]; L.t[2] = x6[2];
+  right_jacobian(x6 + 3, L.Jr);
+  for (int i = 0; i < 9; i++) L.Rbl[i] = Rbl[i];
+  for (int i = 0; i < 3; i++) L.Pbl[i] = Pbl[i];
+}
+
+// accumulate one scalar residual r with dr/dP = gr (3) at body-frame point u
+__device__ __forceinline__ void add_row(const PoseLin& L, const double* u, const double* gr, double r, double* acc) {
+  // J = [gr^T | (Jr^T (u x R^T gr))^T]
+  const double v0 = L.R[0] * gr[0] + L.R[3] * gr[1] + L.R[6] * gr[2];
+  const double v1 = L.R[1] * gr[0] + L.R[4] * gr[1] + L.R[7] * gr[2];
+  const double v2 = L.R[2] * gr[0] + L.R[5] * gr[1] + L.R[8] * gr[2];
+  const double w0 = u[1] * v2 - u[2] * v1, w1 = u[2] * v0 - u[0] * v2, w2 = u[0] * v1 - u[1] * v0;
+  double J[6];
+  J[0] = gr[0]; J[1] = gr[1]; J[2] = gr[2];
+  J[3] = L.Jr[0] * w0 + L.Jr[3] * w1 + L.Jr[6] * w2;
+  J[4] = L.Jr[1] * w0 + L.Jr[4] * w1 + L.Jr[7] * w2;
+  J[5] = L.Jr[2] * w0 + L.Jr[5] * w1 + L.Jr[8] * w2;
+  int k = 7;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    acc[1 + i] += J[i] * r;
+#pragma unroll
+    for (int j = i; j < 6; j++) acc[k++] += J[i] * J[j];
+  }
+}
+
+struct AccArgs {
+  const float4* f_line;
+  const float4* f_plane;
+  const double* w_line;  // WIDE form: host-layout records of 12 doubles (include/mmloam_b200.h)
+  const double* w_plane;
+  const int* n_dev;      // [n_corner, n_surf] (device) or null
+  int n_line, n_plane;   // host counts / capacities
+  double x6[6], Rbl[9], Pbl[3];
+  double lidar_m, w_tan, huber_a;
+  double* partials;      // [grid][28]
+  unsigned* ticket;
+  double* out28;
+  EstState* st;          // optional: evaluation point and parameters come from the solver state
+};
+
+__device__ void dogleg_update(EstState& S, const double* out28);
+
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_accumulate(AccArgs A) {
+  EstState* S = A.st;
+  if (S && (S->done_outer || S->done_inner)) return;
+  __shared__ PoseLin L;
+  __shared__ double s_par[3];
+  if (threadIdx.x == 0) {
+    if (S) {
+      make_pose(S->first ? S->x : S->x_cand, S->Rbl, S->Pbl, L);
+      s_par[0] = S->lidar_m; s_par[1] = S->w_tan; s_par[2] = S->huber_a;
+    } else {
+      make_pose(A.x6, A.Rbl, A.Pbl, L);
+      s_par[0] = A.lidar_m; s_par[1] = A.w_tan; s_par[2] = A.huber_a;
+    }
+  }
+  __syncthreads();
+  const double s_info = 1.0 / s_par[0], w_tan = s_par[1], ha = s_par[2];
+  const int n_line = A.n_dev ? A.n_dev[0] : A.n_line;
+  const int n_plane = A.n_dev ? A.n_dev[1] : A.n_plane;
+  double acc[28];
+#pragma unroll
+  for (int k = 0; k < 28; k++) acc[k] = 0.0;
+  const int stride = gridDim.x * 256;
+
+  // ---- point-to-line, CF.h:412-440
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n_line; i += stride) {
+    double p[3], a[3], b[3];
+    if (WIDE) {
+      const double* f = A.w_line + 12 * (size_t)i;
+      if (!(f[10] == 1.0)) continue;
+      for (int k = 0; k < 3; k++) { p[k] = f[k]; a[k] = f[3 + k]; b[k] = f[6 + k]; }
+    } else {
+      const float4 f0 = __ldg(A.f_line + 3 * (size_t)i);
+      if (!(f0.w == 1.f)) continue;
+      const float4 f1 = __ldg(A.f_line + 3 * (size_t)i + 1), f2 = __ldg(A.f_line + 3 * (size_t)i + 2);
+      p[0] = f0.x; p[1] = f0.y; p[2] = f0.z;
+      a[0] = f1.x; a[1] = f1.y; a[2] = f1.z;
+      b[0] = f1.w; b[1] = f2.x; b[2] = f2.y;
+    }
+    double u[3], P[3];
+    for (int r = 0; r < 3; r++) u[r] = L.Rbl[3 * r] * p[0] + L.Rbl[3 * r + 1] * p[1] + L.Rbl[3 * r + 2] * p[2] + L.Pbl[r];
+    for (int r = 0; r < 3; r++) P[r] = L.R[3 * r] * u[0] + L.R[3 * r + 1] * u[1] + L.R[3 * r + 2] * u[2] + L.t[r];
+    const double l12 = sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]));
+    const double c0 = (P[0] - a[0]) * (P[1] - b[1]) - (P[0] - b[0]) * (P[1] - a[1]);
+    const double c1 = (P[0] - a[0]) * (P[2] - b[2]) - (P[0] - b[0]) * (P[2] - a[2]);
+    const double c2 = (P[1] - a[1]) * (P[2] - b[2]) - (P[1] - b[1]) * (P[2] - a[2]);
+    const double a012 = sqrt(c0 * c0 + c1 * c1 + c2 * c2);
+    const double ld2 = a012 / l12;
+    const double PP = P[0] * P[0] + P[1] * P[1] + P[2] * P[2];
+    const double sq = sqrt(sqrt(PP));
+    const double w = 1.0 - 0.9 * fabs(ld2) / sq;
+    double r = s_info * w * ld2;
+    const double ch[3] = {c2 / a012, -c1 / a012, c0 / a012};
+    const double ab[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+    const double gd[3] = {(ab[1] * ch[2] - ab[2] * ch[1]) / l12, (ab[2] * ch[0] - ab[0] * ch[2]) / l12,
+                          (ab[0] * ch[1] - ab[1] * ch[0]) / l12};
+    const double k5 = 0.5 * ld2 / (PP * sq);
+    double gr[3];
+    for (int k = 0; k < 3; k++) gr[k] = s_info * (w * gd[k] + ld2 * (-0.9 * (gd[k] / sq - k5 * P[k])));
+    // Huber, CF.h:33-63 with rho'' <= 0
+    const double s = r * r;
+    double k1 = 1.0, rho = s;
+    if (ha > 0 && s > ha * ha) {
+      const double rr = sqrt(s);
+      k1 = sqrt(ha / rr);
+      rho = 2 * ha * rr - ha * ha;
+    }
+    acc[0] += 0.5 * rho;
+    r *= k1;
+    gr[0] *= k1; gr[1] *= k1; gr[2] *= k1;
+    add_row(L, u, gr, r, acc);
+  }
+
+  // ---- point-to-plane (vector form), CF.h:533-555
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n_plane; i += stride) {
+    double p[3], n[3], pp[3];
+    if (WIDE) {
+      const double* f = A.w_plane + 12 * (size_t)i;
+      if (!(f[10] == 1.0)) continue;
+      for (int k = 0; k < 3; k++) { p[k] = f[k]; pp[k] = f[3 + k]; n[k] = f[6 + k]; }
+    } else {
+      const float4 f0 = __ldg(A.f_plane + 3 * (size_t)i);
+      if (!(f0.w == 1.f)) continue;
+      const float4 f1 = __ldg(A.f_plane + 3 * (size_t)i + 1), f2 = __ldg(A.f_plane + 3 * (size_t)i + 2);
+      p[0] = f0.x; p[1] = f0.y; p[2] = f0.z;
+      n[0] = f2.x; n[1] = f2.y; n[2] = f2.z;
+      const double dist = (double)f1.w;
+      pp[0] = (double)f1.x - dist * n[0]; pp[1] = (double)f1.y - dist * n[1]; pp[2] = (double)f1.z - dist * n[2];
+    }
+    double u[3], P[3];
+    for (int r = 0; r < 3; r++) u[r] = L.Rbl[3 * r] * p[0] + L.Rbl[3 * r + 1] * p[1] + L.Rbl[3 * r + 2] * p[2] + L.Pbl[r];
+    for (int r = 0; r < 3; r++) P[r] = L.R[3 * r] * u[0] + L.R[3 * r + 1] * u[1] + L.R[3 * r + 2] * u[2] + L.t[r];
+    const double e[3] = {P[0] - pp[0], P[1] - pp[1], P[2] - pp[2]};
+    const double en = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+    const double PP = P[0] * P[0] + P[1] * P[1] + P[2] * P[2];
+    const double sq = sqrt(sqrt(PP));
+    const double w = 1.0 - 0.9 * en / sq;
+    const double k5 = 0.5 * en / (PP * sq);
+    double gw[3];
+    for (int k = 0; k < 3; k++) gw[k] = -0.9 * ((e[k] / en) / sq - k5 * P[k]);
+    // canonical basis [n t1 t2] (sqrt_info^T sqrt_info = (n n^T + w_t^2 (I - n n^T)) / lidar_m^2)
+    double B[3][3];
+    B[0][0] = n[0]; B[0][1] = n[1]; B[0][2] = n[2];
+    int nres = 1;
+    if (w_tan != 0.0) {
+      nres = 3;
+      int kk = 0;
+      if (fabs(n[1]) < fabs(n[kk])) kk = 1;
+      if (fabs(n[2]) < fabs(n[kk])) kk = 2;
+      double ex[3] = {0, 0, 0};
+      ex[kk] = 1.0;
+      double v[3] = {ex[1] * n[2] - ex[2] * n[1], ex[2] * n[0] - ex[0] * n[2], ex[0] * n[1] - ex[1] * n[0]};
+      const double nv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+      for (int k = 0; k < 3; k++) B[1][k] = v[k] / nv;
+      B[2][0] = n[1] * B[1][2] - n[2] * B[1][1];
+      B[2][1] = n[2] * B[1][0] - n[0] * B[1][2];
+      B[2][2] = n[0] * B[1][1] - n[1] * B[1][0];
+    }
+    double rv[3], grv[3][3];
+    double s = 0;
+    for (int k = 0; k < nres; k++) {
+      const double sc = k == 0 ? s_info : s_info * w_tan;
+      const double be = B[k][0] * e[0] + B[k][1] * e[1] + B[k][2] * e[2];
+      rv[k] = sc * w * be;
+      for (int c = 0; c < 3; c++) grv[k][c] = sc * (w * B[k][c] + be * gw[c]);
+      s += rv[k] * rv[k];
+    }
+    double k1 = 1.0, rho = s;
+    if (ha > 0 && s > ha * ha) {
+      const double rr = sqrt(s);
+      k1 = sqrt(ha / rr);
+      rho = 2 * ha * rr - ha * ha;
+    }
+    acc[0] += 0.5 * rho;
+    for (int k = 0; k < nres; k++) {
+      double gr[3] = {k1 * grv[k][0], k1 * grv[k][1], k1 * grv[k][2]};
+      add_row(L, u, gr, k1 * rv[k], acc);
+    }
+  }
+
+  // ---- CTA reduction: warp shuffles, then 8 warps through shared memory
+  __shared__ double sred[8][28];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 28; k++) {
+    double v = acc[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) sred[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 28) {
+    double v = 0;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; w8++) v += sred[w8][threadIdx.x];
+    A.partials[(size_t)blockIdx.x * 28 + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // last CTA: fixed-order sum over CTAs, 8 interleaved lanes per component
+  {
+    const int k = threadIdx.x & 31, part = threadIdx.x >> 5;
+    double v = 0;
+    if (k < 28)
+      for (unsigned b = part; b < gridDim.x; b += 8) v += __ldcg(A.partials + (size_t)b * 28 + k);
+    if (k < 28) sred[part][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 28) {
+    double v = 0;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; w8++) v += sred[w8][threadIdx.x];
+    A.out28[threadIdx.x] = v;
+    sred[0][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *A.ticket = 0;
+    if (S) dogleg_update(*S, sred[0]);
+  }
+}
+
+// ---------------------------------------------------------------- dogleg state machine
+__device__ inline void unpack28(const double* o, double* cost, double* g, double* H) {
+  *cost = o[0];
+  for (int i = 0; i < 6; i++) g[i] = o[1 + i];
+  int k = 7;
+  for (int i = 0; i < 6; i++)
+    for (int j = i; j < 6; j++) {
+      H[6 * i + j] = o[k];
+      H[6 * j + i] = o[k];
+      k++;
+    }
+}
+
+// One DoglegStrategy::ComputeStep + model evaluation. Returns false for an invalid step.
+__device__ bool dogleg_compute_step(EstState& S) {
+  const int n = 6;
+  double Hs[36], gs[6];
+  for (int i = 0; i < n; i++) {
+    gs[i] = S.g[i] * S.scale[i];
+    for (int j = 0; j < n; j++) Hs[i * n + j] = S.H[i * n + j] * S.scale[i] * S.scale[j];
+  }
+  if (!S.reuse) {
+    S.reuse = 1;
+    for (int i = 0; i < n; i++) S.diag[i] = sqrt(fmin(fmax(Hs[i * n + i], 1e-6), 1e32));
+    for (int i = 0; i < n; i++) S.grad[i] = gs[i] / S.diag[i];
+    double v[6], gg = 0, vHv = 0;
+    for (int i = 0; i < n; i++) { v[i] = S.grad[i] / S.diag[i]; gg += S.grad[i] * S.grad[i]; }
+    for (int i = 0; i < n; i++) {
+      double s = 0;
+      for (int j = 0; j < n; j++) s += Hs[i * n + j] * v[j];
+      vHv += v[i] * s;
+    }
+    S.alpha = gg / vHv;
+    bool ok = false;
+    while (S.mu < 1.0) {
+      double Amat[36], y[6];
+      for (int i = 0; i < 36; i++) Amat[i] = Hs[i];
+      for (int i = 0; i < n; i++) Amat[i * n + i] += S.mu * S.diag[i] * S.diag[i];
+      bool s_ok = chol_solve<6>(Amat, gs, y);
+      if (s_ok)
+        for (int i = 0; i < n; i++)
+          if (!isfinite(y[i])) s_ok = false;
+      if (!s_ok) { S.mu *= 10.0; continue; }
+      for (int i = 0; i < n; i++) S.gn[i] = -S.diag[i] * y[i];
+      ok = true;
+      break;
+    }
+    if (!ok) return false;
+  }
+  double gnorm = 0, gnn = 0;
+  for (int i = 0; i < n; i++) { gnorm += S.grad[i] * S.grad[i]; gnn += S.gn[i] * S.gn[i]; }
+  gnorm = sqrt(gnorm);
+  gnn = sqrt(gnn);
+  double step[6];
+  if (gnn <= S.radius) {
+    for (int i = 0; i < n; i++) step[i] = S.gn[i];
+    S.dogleg_norm = gnn;
+  } else if (gnorm * S.alpha >= S.radius) {
+    for (int i = 0; i < n; i++) step[i] = -(S.radius / gnorm) * S.grad[i];
+    S.dogleg_norm = S.radius;
+  } else {
+    double b_dot_a = 0;
+    for (int i = 0; i < n; i++) b_dot_a += S.grad[i] * S.gn[i];
+    b_dot_a *= -S.alpha;
+    const double a_sq = (S.alpha * gnorm) * (S.alpha * gnorm);
+    const double bma = a_sq - 2 * b_dot_a + gnn * gnn;
+    const double c = b_dot_a - a_sq;
+    const double d = sqrt(c * c + bma * (S.radius * S.radius - a_sq));
+    const double beta = (c <= 0) ? (d - c) / bma : (S.radius * S.radius - a_sq) / (d + c);
+    double sn = 0;
+    for (int i = 0; i < n; i++) {
+      step[i] = (-S.alpha * (1.0 - beta)) * S.grad[i] + beta * S.gn[i];
+      sn += step[i] * step[i];
+    }
+    S.dogleg_norm = sqrt(sn);
+  }
+  for (int i = 0; i < n; i++) step[i] /= S.diag[i];
+  double sg = 0, sHs = 0;
+  for (int i = 0; i < n; i++) {
+    double t = 0;
+    for (int j = 0; j < n; j++) t += Hs[i * n + j] * step[j];
+    sHs += step[i] * t;
+    sg += step[i] * gs[i];
+  }
+  S.model_change = -sg - 0.5 * sHs;
+  if (!(S.model_change > 0.0)) return false;
+  double sn = 0;
+  for (int i = 0; i < n; i++) {
+    const double dlt = step[i] * S.scale[i];
+    S.x_cand[i] = S.x[i] + dlt;
+    sn += dlt * dlt;
+  }
+  S.step_norm = sqrt(sn);
+  return true;
+}
+
+__device__ void dogleg_update(EstState& S, const double* out28) {
+  double cost, g[6], H[36];
+  unpack28(out28, &cost, g, H);
+  auto grad_max = [&](const double* gg) {
+    double m = 0;
+    for (int i = 0; i < 6; i++) m = fmax(m, fabs(gg[i]));
+    return m;
+  };
+  auto xnorm = [&]() {
+    double s = 0;
+    for (int i = 0; i < 6; i++) s += S.x[i] * S.x[i];
+    return sqrt(s);
+  };
+  if (S.first) {
+    S.first = 0;
+    S.cost = cost;
+    S.min_cost = cost;
+    for (int i = 0; i < 36; i++) S.H[i] = H[i];
+    for (int i = 0; i < 6; i++) { S.g[i] = g[i]; S.x_best[i] = S.x[i]; }
+    for (int i = 0; i < 6; i++) S.scale[i] = 1.0 / (1.0 + sqrt(H[6 * i + i]));
+    S.x_norm = xnorm();
+    S.radius = 1e4; S.mu = 1e-8; S.reuse = 0; S.num_invalid = 0; S.inner_it = 0;
+    if (!isfinite(cost) || grad_max(g) <= 1e-10) { S.done_inner = 1; return; }
+  } else {
+    const double cand_cost = isfinite(cost) ? cost : DBL_MAX;
+    if (S.step_norm <= 1e-8 * (S.x_norm + 1e-8)) { S.done_inner = 1; return; }
+    const double cost_change = S.cost - cand_cost;
+    if (fabs(cost_change) <= 1e-6 * S.cost) { S.done_inner = 1; return; }
+    const double rel = cost_change / S.model_change;
+    if (rel > 1e-3) {
+      for (int i = 0; i < 6; i++) { S.x[i] = S.x_cand[i]; S.g[i] = g[i]; }
+      for (int i = 0; i < 36; i++) S.H[i] = H[i];
+      S.cost = cand_cost;
+      S.x_norm = xnorm();
+      if (rel < 0.25) S.radius *= 0.5;
+      if (rel > 0.75) S.radius = fmax(S.radius, 3.0 * S.dogleg_norm);
+      S.mu = fmax(1e-8, 2.0 * S.mu / 10.0);
+      S.reuse = 0;
+      if (S.cost < S.min_cost) {
+        S.min_cost = S.cost;
+        for (int i = 0; i < 6; i++) S.x_best[i] = S.x[i];
+      }
+      if (grad_max(S.g) <= 1e-10) { S.done_inner = 1; return; }
+    } else {
+      S.radius *= 0.5;
+      S.reuse = 1;
+    }
+    if (S.radius < 1e-32) { S.done_inner = 1; return; }
+  }
+  for (;;) {
+    if (S.inner_it >= S.max_inner) { S.done_inner = 1; return; }
+    S.inner_it++;
+    S.total_inner++;
+    if (dogleg_compute_step(S)) { S.num_invalid = 0; return; }
+    if (++S.num_invalid >= 5) { S.done_inner = 1; return; }
+    S.mu *= 10.0;
+    S.reuse = 0;
+  }
+}
+
+// ---------------------------------------------------------------- outer loop bookkeeping
+// EST.cpp:1212 vector2double + EST.cpp:1268-1270 T_wl + thres_dist schedule (EST.cpp:1207, 1377-1381)
+__global__ void k_est_begin_outer(EstState* S, int it) {
+  if (threadIdx.x != 0 || S->done_outer) return;
+  S->outer_it = it;
+  const Quat Q = {S->Q[0], S->Q[1], S->Q[2], S->Q[3]};
+  S->x[0] = S->P[0]; S->x[1] = S->P[1]; S->x[2] = S->P[2];
+  so3_log(Q, S->x + 3);
+  for (int i = 0; i < 4; i++) S->q_before[i] = S->Q[i];
+  for (int i = 0; i < 3; i++) S->t_before[i] = S->P[i];
+  double Rq[9];
+  quat_to_R(Q, Rq);
+  // exRbl = Rbl, exPbl = Pbl
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++)
+      S->T_wl[4 * r + c] = Rq[3 * r] * S->Rbl[c] + Rq[3 * r + 1] * S->Rbl[3 + c] + Rq[3 * r + 2] * S->Rbl[6 + c];
+    S->T_wl[4 * r + 3] = Rq[3 * r] * S->Pbl[0] + Rq[3 * r + 1] * S->Pbl[1] + Rq[3 * r + 2] * S->Pbl[2] + S->P[r];
+  }
+  S->T_wl[12] = 0; S->T_wl[13] = 0; S->T_wl[14] = 0; S->T_wl[15] = 1;
+  S->thres = (float)S->thres_sched[it < 2 ? it : 2];
+  S->first = 1;
+  S->done_inner = 0;
+}
+
+// EST.cpp:771-775 localizability, EST.cpp:1439-1450 convergence test
+__global__ void k_est_end_outer(EstState* S, const double* assoc_stats) {
+  if (threadIdx.x != 0 || S->done_outer) return;
+  const int* ints = reinterpret_cast<const int*>(assoc_stats + 16);
+  S->n_line = ints[0];
+  S->n_plane = ints[1];
+  // checkLocalizability (EST.cpp:536-565): singular values of stacked normals
+  const double* mo = assoc_stats + 8;
+  double sv = -1.0;
+  if (ints[1] > 10) {
+    const double M[9] = {mo[0], mo[1], mo[2], mo[1], mo[3], mo[4], mo[2], mo[4], mo[5]};
+    double ev[3], V[9];
+    eig3_sym(M, ev, V);
+    sv = sqrt(fmax(ev[0], 0.0));
+  }
+  S->min_sv = sv;
+  if (sv < 3.0) S->is_degenerate = 1;
+  S->final_cost = S->min_cost;
+  S->P[0] = S->x_best[0]; S->P[1] = S->x_best[1]; S->P[2] = S->x_best[2];
+  const Quat Q = so3_exp(S->x_best + 3);
+  S->Q[0] = Q.w; S->Q[1] = Q.x; S->Q[2] = Q.y; S->Q[3] = Q.z;
+  const Quat qb = {S->q_before[0], S->q_before[1], S->q_before[2], S->q_before[3]};
+  const Quat dq = quat_mul(qb, Quat{Q.w, -Q.x, -Q.y, -Q.z});
+  const double deltaR = 2.0 * atan2(sqrt((dq.x * dq.x + dq.y * dq.y) + dq.z * dq.z), fabs(dq.w)) * 180.0 / 3.14159265358979323846;
+  const double d0 = S->t_before[0] - S->P[0], d1 = S->t_before[1] - S->P[1], d2 = S->t_before[2] - S->P[2];
+  const double deltaT = sqrt((d0 * d0 + d1 * d1) + d2 * d2);
+  if ((deltaR < 0.05 && deltaT < 0.05) || (S->outer_it + 1) == S->max_outer) S->done_outer = 1;
+}
+
+}  // namespace mml
+
+using namespace mml;
+
+extern int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres, const double* T_dev,
+                                const float* thres_dev, const int* gate, const int* nq_dev, int cap);
+
+static int acc_grid(int n) {
+  int g = div_up(n > 0 ? n : 1, 256);
+  const int cap = 4 * kNumSMs;
+  return g < cap ? g : cap;
+}
+
+// One evaluation at x6 (stateless form) -> out28 on device; optional copy to host.
+int mml_accumulate_launch(mml_ctx* ctx, const double* x6, const double* T_bl16, double lidar_m, double w_tan,
+                          double huber_a, EstState* st_dev, const int* n_dev, int cap_line, int cap_plane,
+                          const double* wide_line_dev, const double* wide_plane_dev) {
+  const int n = cap_line > cap_plane ? cap_line : cap_plane;
+  const int grid = acc_grid(n);
+  MML_CUDA(ctx, ctx->acc_partials.reserve(sizeof(double) * 28 * (size_t)(4 * kNumSMs) + 64));
+  MML_CUDA(ctx, ctx->acc_out.reserve(sizeof(double) * 32 + 64));
+  AccArgs A;
+  memset(&A, 0, sizeof(A));
+  A.f_line = ctx->f_line.as<float4>();
+  A.f_plane = ctx->f_plane.as<float4>();
+  A.w_line = wide_line_dev;
+  A.w_plane = wide_plane_dev;
+  A.n_dev = n_dev;
+  A.n_line = cap_line;
+  A.n_plane = cap_plane;
+  if (x6) for (int i = 0; i < 6; i++) A.x6[i] = x6[i];
+  if (T_bl16) {
+    // CF.h:405-408: rotation re-normalised through a quaternion
+    const double Rm[9] = {T_bl16[0], T_bl16[1], T_bl16[2], T_bl16[4], T_bl16[5], T_bl16[6], T_bl16[8], T_bl16[9], T_bl16[10]};
+    quat_to_R(quat_from_R9(Rm), A.Rbl);
+    A.Pbl[0] = T_bl16[3]; A.Pbl[1] = T_bl16[7]; A.Pbl[2] = T_bl16[11];
+  }
+  A.lidar_m = lidar_m; A.w_tan = w_tan; A.huber_a = huber_a;
+  A.partials = ctx->acc_partials.as<double>();
+  A.out28 = ctx->acc_out.as<double>();
+  A.ticket = reinterpret_cast<unsigned*>(ctx->acc_out.as<double>() + 30);
+  A.st = st_dev;
+  if (wide_line_dev || wide_plane_dev) k_accumulate<true><<<grid, 256, 0, ctx->stream>>>(A);
+  else k_accumulate<false><<<grid, 256, 0, ctx->stream>>>(A);
+  MML_LAUNCHED(ctx);
+  MML_CUDA(ctx, cudaGetLastError());
+  return MML_OK;
+}
+
+// Full Estimate loop for one frame on the device (window size 1). Queries must be in the
+// frame slot (q_corner / q_surf with device counts in `cnt_dev`, capacities cap_*).
+int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int cap_surf, const double* exTlb16,
+                        double* P3, double* q4, const mml_est_params* prm, double* stats) {
+  cudaStream_t st = ctx->stream;
+  MML_CUDA(ctx, ctx->est_state.reserve(sizeof(EstState) + 64));
+  MML_CUDA(ctx, ctx->acc_partials.reserve(sizeof(double) * 28 * (size_t)(4 * kNumSMs) + 64));
+  MML_CUDA(ctx, ctx->acc_out.reserve(sizeof(double) * 32 + 64));
+  MML_CUDA(ctx, ctx->assoc_stats.reserve(512));
+  MML_CUDA(ctx, ctx->f_line.reserve(sizeof(float4) * 3 * (size_t)(cap_corner > 0 ? cap_corner : 1)));
+  MML_CUDA(ctx, ctx->f_plane.reserve(sizeof(float4) * 3 * (size_t)(cap_surf > 0 ? cap_surf : 1)));
+  MML_CUDA(ctx, ctx->tmp_c.reserve(sizeof(double) * 8 * (size_t)(div_up((cap_corner > cap_surf ? cap_corner : cap_surf) + 1, 128) + 1) + 64));
+  EstState* S = ctx->est_state.as<EstState>();
+
+  // host-side initial state
+  MML_CUDA(ctx, ctx->pin_out.reserve(sizeof(EstState) + 64));
+  MML_CUDA(ctx, cudaStreamSynchronize(st));
+  EstState* h = ctx->pin_out.as<EstState>();
+  memset(h, 0, sizeof(EstState));
+  for (int i = 0; i < 3; i++) h->P[i] = P3[i];
+  for (int i = 0; i < 4; i++) h->Q[i] = q4[i];
+  // exRbl = R^T, exPbl = -R^T t (EST.cpp:1155-1156); CF.h:405-408 re-normalises R_bl via a quaternion
+  double Rbl[9];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) Rbl[3 * r + c] = exTlb16[4 * c + r];
+  for (int r = 0; r < 3; r++)
+    h->Pbl[r] = -1.0 * (Rbl[3 * r] * exTlb16[3] + Rbl[3 * r + 1] * exTlb16[7] + Rbl[3 * r + 2] * exTlb16[11]);
+  for (int i = 0; i < 9; i++) h->Rbl[i] = Rbl[i];
+  h->max_outer = prm->max_outer;
+  h->max_inner = prm->max_inner;
+  h->lidar_m = prm->lidar_m;
+  h->w_tan = prm->plan_weight_tan;
+  h->huber_a = prm->use_huber ? 0.1 / prm->lidar_m : 0.0;
+  h->thres_sched[0] = prm->thres0; h->thres_sched[1] = prm->thres1; h->thres_sched[2] = prm->thres2;
+  MML_CUDA(ctx, cudaMemcpyAsync(S, h, sizeof(EstState), cudaMemcpyHostToDevice, st));
+  MML_CUDA(ctx, cudaMemsetAsync(ctx->acc_out.p, 0, sizeof(double) * 32, st));
+  MML_CUDA(ctx, cudaMemsetAsync(ctx->assoc_stats.p, 0, 512, st));
+
+  // graph key: every pointer / capacity baked into the captured launches
+  long long key = 1469598103934665603ll;
+  auto mix = [&](long long v) { key = (key ^ v) * 1099511628211ll; };
+  mix((long long)(size_t)S); mix((long long)(size_t)ctx->f_line.p); mix((long long)(size_t)ctx->f_plane.p);
+  mix((long long)(size_t)ctx->q_corner.p); mix((long long)(size_t)ctx->q_surf.p); mix((long long)(size_t)cnt_dev);
+  mix((long long)(size_t)ctx->acc_partials.p); mix((long long)(size_t)ctx->acc_out.p); mix((long long)(size_t)ctx->tmp_c.p);
+  mix((long long)(size_t)ctx->assoc_stats.p); mix(cap_corner); mix(cap_surf); mix(prm->max_outer); mix(prm->max_inner);
+  for (int k = 0; k < 4; k++) {
+    const GridMap& M = ctx->maps[k];
+    mix(M.valid); mix((long long)(size_t)M.pts.p); mix((long long)(size_t)M.cell_start.p); mix(M.m); mix(M.ncell);
+    mix(M.dim[0]); mix(M.dim[1]); mix(M.dim[2]); mix((long long)(M.cell * 1e6f)); mix(M.cube_lo[0]); mix(M.cube_lo[1]); mix(M.cube_lo[2]);
+    mix((long long)(M.org_d[0] * 1e6)); mix((long long)(M.org_d[1] * 1e6)); mix((long long)(M.org_d[2] * 1e6));
+    mix(M.cen[0]); mix(M.cen[1]); mix(M.cen[2]);
+  }
+  if (!ctx->est_graph || ctx->est_graph_key != key) {
+    if (ctx->est_graph) { cudaGraphExecDestroy(ctx->est_graph); ctx->est_graph = nullptr; }
+    cudaGraph_t graph = nullptr;
+    const long long launches_before = ctx->launches;
+    MML_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = MML_OK;
+    for (int it = 0; it < prm->max_outer && rc == MML_OK; it++) {
+      k_est_begin_outer<<<1, 32, 0, st>>>(S, it);
+      MML_LAUNCHED(ctx);
+      rc = mml_associate_launch(ctx, 0, nullptr, 0.f, S->T_wl, &S->thres, &S->done_outer, cnt_dev, cap_corner);
+      if (rc == MML_OK) rc = mml_associate_launch(ctx, 1, nullptr, 0.f, S->T_wl, &S->thres, &S->done_outer, cnt_dev + 1, cap_surf);
+      for (int k = 0; k <= prm->max_inner && rc == MML_OK; k++)
+        rc = mml_accumulate_launch(ctx, nullptr, nullptr, 0, 0, 0, S, cnt_dev, cap_corner, cap_surf, nullptr, nullptr);
+      k_est_end_outer<<<1, 32, 0, st>>>(S, ctx->assoc_stats.as<double>());
+      MML_LAUNCHED(ctx);
+    }
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    ctx->est_launches_per_graph = ctx->launches - launches_before;
+    ctx->launches = launches_before;
+    if (rc != MML_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    MML_CUDA(ctx, ce);
+    MML_CUDA(ctx, cudaGraphInstantiate(&ctx->est_graph, graph, 0));
+    cudaGraphDestroy(graph);
+    ctx->est_graph_key = key;
+  }
+  MML_CUDA(ctx, cudaGraphLaunch(ctx->est_graph, st));
+  ctx->launches += ctx->est_launches_per_graph;
+  MML_CUDA(ctx, cudaMemcpyAsync(h, S, sizeof(EstState), cudaMemcpyDeviceToHost, st));
+  MML_CUDA(ctx, cudaStreamSynchronize(st));
+  for (int i = 0; i < 3; i++) P3[i] = h->P[i];
+  for (int i = 0; i < 4; i++) q4[i] = h->Q[i];
+  if (stats) {
+    stats[0] = h->outer_it + 1; stats[1] = h->total_inner; stats[2] = h->n_line; stats[3] = h->n_plane;
+    stats[4] = h->final_cost; stats[5] = h->min_sv; stats[6] = h->is_degenerate;
+  }
+  return MML_OK;
+}

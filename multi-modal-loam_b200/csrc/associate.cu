@@ -1,0 +1,602 @@
+// Spatial-hash feature map + correspondence search + local geometry fit on the device.
+//
+// Replaces, for the hot path:
+//   pcl::KdTreeFLANN::setInputCloud / nearestKSearch   EST.cpp:1159-1179, 199, 284, 630, 704
+//   MAP_MANAGER::pointAssociateToMap + cube rule       MM.cpp:75-89, 583-629
+//   Estimator::processPointToLine                      EST.cpp:148-365
+//   Estimator::processPointToPlanVec                   EST.cpp:573-777 (+ 536-565 moments)
+//
+// Map layout in HBM: points are counting-sorted into a dense grid of cubic cells
+// (float4 xyz + original index in .w, cell_start[ncell+1]); x is the fastest cell axis so a
+// row of neighbouring cells is ONE contiguous point range. Global maps keep the reference's
+// "own 50 m cube only" rule exactly: a point is binned by the reference's cube formula and
+// its cell is clamped into that cube's block of cells; a query only walks cells of its cube.
+//
+// Search: exact 5-NN inside radius sqrt(thres_dist) by growing Chebyshev shells; shell r is
+// final once the 5th best squared distance <= (r*cell - margin)^2. Distances are
+// ((dx*dx)+dy*dy)+dz*dz in float32 without FMA (FLANN L2_Simple<float>), ties broken by the
+// lower original index, so neighbour sets equal the CPU oracle's bit for bit.
+#include "common.cuh"
+#include "sort.cuh"
+#include "smallmath.cuh"
+#include <math.h>
+
+namespace mml {
+
+struct GridDev {
+  const float4* pts;
+  const int* cell_start;
+  const int* cube_count;  // global kinds only
+  double org[3];          // lower corner of cell (0,0,0)
+  double inv_cell;
+  float cell;
+  int dim[3];
+  int m;
+  int global;             // 1: cube rule
+  int k_per_cube;         // cells per cube edge (global)
+  int cube_lo[3];         // lowest cube index (I,J,K) covered by the grid
+  int cen[3];             // (CenWidth, CenHeight, CenDepth)
+  int min_cube_pts;       // > this many points in the cube (100 corner / 50 surf)  EST.cpp:198,627
+  int min_local_pts;      // > 20 for local maps                                    EST.cpp:283,702
+  int valid;
+};
+
+// reference cube rule, MM.cpp:583-605. Returns false when outside the 21x11x21 grid.
+__host__ __device__ inline bool cube_of(float x, float y, float z, const int* cen, int& cI, int& cJ, int& cK) {
+  cI = int(((double)x + 25.0) / 50.0) + cen[2];
+  cJ = int(((double)y + 25.0) / 50.0) + cen[0];
+  cK = int(((double)z + 25.0) / 50.0) + cen[1];
+  if ((double)x + 25.0 < 0) cI--;
+  if ((double)y + 25.0 < 0) cJ--;
+  if ((double)z + 25.0 < 0) cK--;
+  return cI >= 0 && cI < kCubeD && cJ >= 0 && cJ < kCubeW && cK >= 0 && cK < kCubeH;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// cell coordinates of a point + the inclusive cell range it may search / be binned in
+__device__ __forceinline__ bool locate(const GridDev& G, float x, float y, float z, int c[3], int lo[3], int hi[3],
+                                       int& cube_id) {
+  cube_id = -1;
+  if (G.global) {
+    int cI, cJ, cK;
+    if (!cube_of(x, y, z, G.cen, cI, cJ, cK)) return false;
+    cube_id = cI + kCubeD * cJ + kCubeD * kCubeW * cK;
+    const int rel[3] = {cI - G.cube_lo[0], cJ - G.cube_lo[1], cK - G.cube_lo[2]};
+    for (int a = 0; a < 3; a++) {
+      lo[a] = rel[a] * G.k_per_cube;
+      hi[a] = lo[a] + G.k_per_cube - 1;
+      if (lo[a] < 0 || hi[a] >= G.dim[a]) return false;  // cube not covered by the map
+    }
+  } else {
+    for (int a = 0; a < 3; a++) { lo[a] = 0; hi[a] = G.dim[a] - 1; }
+  }
+  const double p[3] = {(double)x, (double)y, (double)z};
+  for (int a = 0; a < 3; a++) {
+    double f = floor((p[a] - G.org[a]) * G.inv_cell);
+    int ci = f < -1e9 ? -1000000000 : (f > 1e9 ? 1000000000 : (int)f);
+    c[a] = clampi(ci, lo[a], hi[a]);
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------- map build
+__global__ void __launch_bounds__(256) k_map_count(const float4* __restrict__ pts, int m, GridDev G, int* __restrict__ cell_cnt,
+                                                   int* __restrict__ cell_of, int* __restrict__ cube_cnt) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= m) return;
+  const float4 p = pts[i];
+  int c[3], lo[3], hi[3], cube;
+  if (!locate(G, p.x, p.y, p.z, c, lo, hi, cube)) {  // outside the cube grid: dropped like MM.cpp:168-175
+    cell_of[i] = -1;
+    return;
+  }
+  const int cell = (c[2] * G.dim[1] + c[1]) * G.dim[0] + c[0];
+  cell_of[i] = cell;
+  atomicAdd(&cell_cnt[cell], 1);
+  if (G.global) atomicAdd(&cube_cnt[cube], 1);
+}
+
+__global__ void __launch_bounds__(256) k_map_scatter(const float4* __restrict__ pts, int m, const int* __restrict__ cell_of,
+                                                     const int* __restrict__ cell_start, int* __restrict__ cell_fill,
+                                                     float4* __restrict__ out) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= m) return;
+  const int cell = cell_of[i];
+  if (cell < 0) return;
+  const int pos = cell_start[cell] + atomicAdd(&cell_fill[cell], 1);
+  float4 p = pts[i];
+  p.w = __int_as_float(i);
+  out[pos] = p;
+}
+
+// occupied-cell count at a trial resolution (to pick the final cell size)
+__global__ void __launch_bounds__(256) k_count_nonzero(const int* __restrict__ a, long long n, unsigned long long* out) {
+  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  int v = 0;
+  for (; i < n; i += (long long)gridDim.x * 256) v += a[i] != 0;
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, (unsigned long long)v);
+}
+
+// ---------------------------------------------------------------- k-NN
+struct Knn5 {
+  float d[5];
+  int id[5];
+  int loc[5];  // position in the cell-sorted array
+  int cnt;
+};
+
+__device__ __forceinline__ void knn_init(Knn5& r) {
+#pragma unroll
+  for (int k = 0; k < 5; k++) { r.d[k] = INFINITY; r.id[k] = 0x7fffffff; r.loc[k] = -1; }
+  r.cnt = 0;
+}
+__device__ __forceinline__ bool knn_better(float d, int id, float d2, int id2) { return d < d2 || (d == d2 && id < id2); }
+__device__ __forceinline__ void knn_push(Knn5& r, float d, int id, int loc) {
+  if (!knn_better(d, id, r.d[4], r.id[4])) return;
+  // insertion into the sorted 5-list (fully unrolled, registers only)
+#pragma unroll
+  for (int k = 4; k >= 0; k--) {
+    const bool up = (k > 0) && knn_better(d, id, r.d[k - 1], r.id[k - 1]);
+    if (up) {
+      r.d[k] = r.d[k - 1]; r.id[k] = r.id[k - 1]; r.loc[k] = r.loc[k - 1];
+    } else {
+      r.d[k] = d; r.id[k] = id; r.loc[k] = loc;
+      break;
+    }
+  }
+  if (r.cnt < 5) r.cnt++;
+}
+
+__device__ __forceinline__ void scan_range(const GridDev& G, int c0, int c1, float qx, float qy, float qz, Knn5& r) {
+  const int s = __ldg(G.cell_start + c0), e = __ldg(G.cell_start + c1 + 1);
+  for (int k = s; k < e; k++) {
+    const float4 p = __ldg(G.pts + k);
+    const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+    const float d = (dx * dx + dy * dy) + dz * dz;
+    knn_push(r, d, __float_as_int(p.w), k);
+  }
+}
+
+// exact 5-NN within squared radius `thres`; true iff 5 neighbours found and d2[4] < thres
+__device__ bool knn5_grid(const GridDev& G, float qx, float qy, float qz, float thres, Knn5& r) {
+  knn_init(r);
+  int c[3], lo[3], hi[3], cube;
+  if (!locate(G, qx, qy, qz, c, lo, hi, cube)) return false;
+  if (G.global) {
+    if (!(__ldg(G.cube_count + cube) > G.min_cube_pts)) return false;
+  } else {
+    if (!(G.m > G.min_local_pts)) return false;
+  }
+  const float cellf = G.cell;
+  const int rmax = (int)ceilf(sqrtf(thres) / cellf) + 1;
+  for (int rr = 1; rr <= rmax; rr++) {
+    // shell rr (rr == 1 also covers the centre cell)
+    for (int dz = -rr; dz <= rr; dz++) {
+      const int z = c[2] + dz;
+      if (z < lo[2] || z > hi[2]) continue;
+      for (int dy = -rr; dy <= rr; dy++) {
+        const int y = c[1] + dy;
+        if (y < lo[1] || y > hi[1]) continue;
+        const int row = (z * G.dim[1] + y) * G.dim[0];
+        const bool full = (rr == 1) || dz == -rr || dz == rr || dy == -rr || dy == rr;
+        if (full) {
+          const int x0 = max(c[0] - rr, lo[0]), x1 = min(c[0] + rr, hi[0]);
+          if (x0 <= x1) scan_range(G, row + x0, row + x1, qx, qy, qz, r);
+        } else {
+          const int xa = c[0] - rr, xb = c[0] + rr;
+          if (xa >= lo[0]) scan_range(G, row + xa, row + xa, qx, qy, qz, r);
+          if (xb <= hi[0]) scan_range(G, row + xb, row + xb, qx, qy, qz, r);
+        }
+      }
+    }
+    // nothing left inside the searchable block of cells
+    if (c[0] - rr < lo[0] && c[0] + rr > hi[0] && c[1] - rr < lo[1] && c[1] + rr > hi[1] && c[2] - rr < lo[2] &&
+        c[2] + rr > hi[2])
+      break;
+    const float reach = fmaxf((float)rr * cellf - 1e-3f, 0.f);
+    const float reach2 = reach * reach;
+    if (r.cnt == 5 && r.d[4] <= reach2) break;
+    if (reach2 >= thres) break;
+  }
+  return r.cnt == 5 && r.d[4] < thres;
+}
+
+// ---------------------------------------------------------------- features
+// compact feature record: 3 x float4 per query slot
+//   line : f0 = (p.xyz, valid) f1 = (a.xyz, b.x) f2 = (b.y, b.z, 0, 0)
+//   plane: f0 = (p.xyz, valid) f1 = (sel.xyz, dist) f2 = (n.xyz, 0)       proj = sel - dist * n in double
+// valid: -1 none, 0 |error| <= 1e-5, 1 used.
+struct AssocArgs {
+  const float4* q;
+  int nq;
+  const int* nq_dev;        // optional: query count read from device memory (<= nq)
+  double T[16];
+  float thres;
+  GridDev G[2];  // [0] global, [1] local
+  float4* feat;
+  double* moment_partials;  // [grid][8]: 6 moments, count, pad  (plane only)
+  unsigned* ticket;
+  double* moment_out;       // [8]
+  int* n_feat_out;
+  const int* gate;          // device flag: nonzero -> skip (used by the estimate graph)
+  const double* T_dev;      // optional: T and thres read from device state
+  const float* thres_dev;
+};
+
+__device__ bool fit_line(const GridDev& G, const Knn5& r, float* a, float* b) {
+  float px[5], py[5], pz[5];
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const float4 p = __ldg(G.pts + r.loc[j]);
+    px[j] = p.x; py[j] = p.y; pz[j] = p.z;
+  }
+  float cx = 0, cy = 0, cz = 0;
+#pragma unroll
+  for (int j = 0; j < 5; j++) { cx += px[j]; cy += py[j]; cz += pz[j]; }
+  cx /= 5; cy /= 5; cz /= 5;
+  float a11 = 0, a12 = 0, a13 = 0, a22 = 0, a23 = 0, a33 = 0;
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const float ax = px[j] - cx, ay = py[j] - cy, az = pz[j] - cz;
+    a11 += ax * ax; a12 += ax * ay; a13 += ax * az;
+    a22 += ay * ay; a23 += ay * az; a33 += az * az;
+  }
+  a11 /= 5; a12 /= 5; a13 /= 5; a22 /= 5; a23 /= 5; a33 /= 5;
+  const double A[9] = {a11, a12, a13, a12, a22, a23, a13, a23, a33};
+  double ev[3], V[9];
+  eig3_sym(A, ev, V);
+  if (!(ev[2] > 3 * ev[1])) return false;
+  const double u0 = V[2], u1 = V[5], u2 = V[8];
+  a[0] = (float)((double)cx + 0.1 * u0); a[1] = (float)((double)cy + 0.1 * u1); a[2] = (float)((double)cz + 0.1 * u2);
+  b[0] = (float)((double)cx - 0.1 * u0); b[1] = (float)((double)cy - 0.1 * u1); b[2] = (float)((double)cz - 0.1 * u2);
+  return true;
+}
+
+__device__ bool fit_plane(const GridDev& G, const Knn5& r, float sx, float sy, float sz, float* nrm, float* dist_out) {
+  double A[5][3], bb[5];
+  float px[5], py[5], pz[5];
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const float4 p = __ldg(G.pts + r.loc[j]);
+    px[j] = p.x; py[j] = p.y; pz[j] = p.z;
+    A[j][0] = p.x; A[j][1] = p.y; A[j][2] = p.z;
+    bb[j] = -1.0;
+  }
+  double X[3];
+  qr5x3_solve(A, bb, X);
+  float pa = (float)X[0], pb = (float)X[1], pc = (float)X[2], pd = 1.f;
+  const float ps = sqrtf(pa * pa + pb * pb + pc * pc);
+  pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+#pragma unroll
+  for (int j = 0; j < 5; j++)
+    if ((double)fabsf(pa * px[j] + pb * py[j] + pc * pz[j] + pd) > 0.2) return false;
+  nrm[0] = pa; nrm[1] = pb; nrm[2] = pc;
+  *dist_out = pa * sx + pb * sy + pc * sz + pd;
+  return true;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128) k_associate(AssocArgs A) {
+  if (A.gate && *A.gate) return;
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  double T[16];
+  float thres = A.thres;
+  if (A.T_dev) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) T[k] = A.T_dev[k];
+    thres = *A.thres_dev;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; k++) T[k] = A.T[k];
+  }
+  double mom[7] = {0, 0, 0, 0, 0, 0, 0};
+  int found = 0;
+  const int nq = A.nq_dev ? *A.nq_dev : A.nq;
+  if (i < nq) {
+    const float4 q = A.q[i];
+    const double pin[3] = {(double)q.x, (double)q.y, (double)q.z};
+    float sel[3];
+#pragma unroll
+    for (int rr = 0; rr < 3; rr++)
+      sel[rr] = (float)(((T[4 * rr] * pin[0] + T[4 * rr + 1] * pin[1]) + T[4 * rr + 2] * pin[2]) + T[4 * rr + 3]);
+    float4 f0 = make_float4(q.x, q.y, q.z, -1.f), f1 = make_float4(0, 0, 0, 0), f2 = make_float4(0, 0, 0, 0);
+    // EST.cpp:192-196: out of the cube grid or NaN -> no feature at all
+    int cI, cJ, cK;
+    const bool in_grid = cube_of(sel[0], sel[1], sel[2], A.G[0].cen, cI, cJ, cK);
+    const bool finite = !(isnan(sel[0]) || isnan(sel[1]) || isnan(sel[2]));
+    if (in_grid && finite) {
+      Knn5 r;
+      for (int mp = 0; mp < 2 && !found; mp++) {
+        const GridDev& G = A.G[mp];
+        if (!G.valid) continue;
+        if (!knn5_grid(G, sel[0], sel[1], sel[2], thres, r)) continue;
+        if (KIND == 0) {
+          float a[3], b[3];
+          if (!fit_line(G, r, a, b)) continue;
+          f1 = make_float4(a[0], a[1], a[2], b[0]);
+          f2 = make_float4(b[1], b[2], 0.f, 0.f);
+          // Estimator.h:71-83 FeatureLine::ComputeError at the association pose
+          double P[3];
+#pragma unroll
+          for (int rr = 0; rr < 3; rr++)
+            P[rr] = ((T[4 * rr] * pin[0] + T[4 * rr + 1] * pin[1]) + T[4 * rr + 2] * pin[2]) + T[4 * rr + 3];
+          const double da[3] = {a[0], a[1], a[2]}, db[3] = {b[0], b[1], b[2]};
+          const double l12 = sqrt((da[0] - db[0]) * (da[0] - db[0]) + (da[1] - db[1]) * (da[1] - db[1]) +
+                                  (da[2] - db[2]) * (da[2] - db[2]));
+          const double c0 = (P[0] - da[0]) * (P[1] - db[1]) - (P[0] - db[0]) * (P[1] - da[1]);
+          const double c1 = (P[0] - da[0]) * (P[2] - db[2]) - (P[0] - db[0]) * (P[2] - da[2]);
+          const double c2 = (P[1] - da[1]) * (P[2] - db[2]) - (P[1] - db[1]) * (P[2] - da[2]);
+          const double err = sqrt(c0 * c0 + c1 * c1 + c2 * c2) / l12;
+          f0.w = (fabs(err) > 1e-5) ? 1.f : 0.f;
+          f2.z = (float)err;
+          found = 1;
+        } else {
+          float nrm[3], dist;
+          if (!fit_plane(G, r, sel[0], sel[1], sel[2], nrm, &dist)) continue;
+          f1 = make_float4(sel[0], sel[1], sel[2], dist);
+          f2 = make_float4(nrm[0], nrm[1], nrm[2], 0.f);
+          double e[3];
+#pragma unroll
+          for (int rr = 0; rr < 3; rr++) {
+            const double P = ((T[4 * rr] * pin[0] + T[4 * rr + 1] * pin[1]) + T[4 * rr + 2] * pin[2]) + T[4 * rr + 3];
+            const double proj = (double)sel[rr] - (double)dist * (double)nrm[rr];
+            e[rr] = P - proj;
+          }
+          const double err = sqrt((e[0] * e[0] + e[1] * e[1]) + e[2] * e[2]);
+          f0.w = (fabs(err) > 1e-5) ? 1.f : 0.f;
+          f2.w = (float)err;
+          const double n0 = nrm[0], n1 = nrm[1], n2 = nrm[2];
+          mom[0] = n0 * n0; mom[1] = n0 * n1; mom[2] = n0 * n2; mom[3] = n1 * n1; mom[4] = n1 * n2; mom[5] = n2 * n2;
+          found = 1;
+        }
+      }
+    }
+    A.feat[3 * (size_t)i] = f0;
+    A.feat[3 * (size_t)i + 1] = f1;
+    A.feat[3 * (size_t)i + 2] = f2;
+  }
+  // ---- block reduction of (moments, count); last block sums the partials in fixed order
+  mom[6] = (double)found;
+  __shared__ double sred[4][7];
+  __shared__ bool is_last;
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+    double v = mom[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    const double v = ((sred[0][threadIdx.x] + sred[1][threadIdx.x]) + sred[2][threadIdx.x]) + sred[3][threadIdx.x];
+    A.moment_partials[(size_t)blockIdx.x * 8 + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x < 7) {
+      double s = 0;
+      for (unsigned b = 0; b < gridDim.x; b++) s += __ldcg(A.moment_partials + (size_t)b * 8 + threadIdx.x);
+      A.moment_out[threadIdx.x] = s;
+      if (threadIdx.x == 6) *A.n_feat_out = (int)s;
+    }
+    if (threadIdx.x == 0) *A.ticket = 0;
+  }
+}
+
+// expand compact features to the host-visible 12-double records of include/mmloam_b200.h
+template <int KIND>
+__global__ void __launch_bounds__(256) k_export_features(const float4* __restrict__ feat, int nq, double* __restrict__ out) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= nq) return;
+  const float4 f0 = feat[3 * (size_t)i], f1 = feat[3 * (size_t)i + 1], f2 = feat[3 * (size_t)i + 2];
+  double* o = out + 12 * (size_t)i;
+  o[0] = f0.x; o[1] = f0.y; o[2] = f0.z;
+  if (f0.w < 0.f) {
+    for (int k = 3; k < 10; k++) o[k] = 0;
+  } else if (KIND == 0) {
+    o[3] = f1.x; o[4] = f1.y; o[5] = f1.z;
+    o[6] = f1.w; o[7] = f2.x; o[8] = f2.y;
+    o[9] = f2.z;
+  } else {
+    o[3] = (double)f1.x - (double)f1.w * (double)f2.x;
+    o[4] = (double)f1.y - (double)f1.w * (double)f2.y;
+    o[5] = (double)f1.z - (double)f1.w * (double)f2.z;
+    o[6] = f2.x; o[7] = f2.y; o[8] = f2.z;
+    o[9] = f2.w;
+  }
+  o[10] = (double)f0.w;
+  o[11] = (double)i;
+}
+
+}  // namespace mml
+
+using namespace mml;
+
+// ---------------------------------------------------------------- host side
+static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, float cell_hint);
+
+int mml_map_set_device(mml_ctx* ctx, int kind, const float4* pts_d, int m, const int* cen3, float cell_hint) {
+  if (kind < 0 || kind > 3) return mml_fail(ctx, MML_ERR_INVALID, "map kind must be 0..3");
+  GridMap& M = ctx->maps[kind];
+  M.global = (kind == MML_MAP_CORNER_GLOBAL || kind == MML_MAP_SURF_GLOBAL);
+  if (cen3) { M.cen[0] = cen3[0]; M.cen[1] = cen3[1]; M.cen[2] = cen3[2]; }
+  M.valid = false;
+  M.m = m;
+  if (m <= 0) return MML_OK;
+  return build_grid(ctx, M, pts_d, m, cell_hint);
+}
+
+extern int mml_bbox_device(mml_ctx* ctx, const float4* pts_d, int n, float* mn3, float* mx3);
+
+static GridDev grid_dev(const GridMap& M, int kind) {
+  GridDev G;
+  memset(&G, 0, sizeof(G));
+  G.valid = M.valid ? 1 : 0;
+  if (!M.valid) return G;
+  G.pts = M.pts.as<float4>();
+  G.cell_start = M.cell_start.as<int>();
+  G.cube_count = M.cube_count.as<int>();
+  for (int a = 0; a < 3; a++) { G.org[a] = M.org_d[a]; G.dim[a] = M.dim[a]; G.cen[a] = M.cen[a]; G.cube_lo[a] = M.cube_lo[a]; }
+  G.inv_cell = 1.0 / (double)M.cell;
+  G.cell = M.cell;
+  G.m = M.m;
+  G.global = M.global ? 1 : 0;
+  G.k_per_cube = M.k_per_cube;
+  G.min_cube_pts = (kind == MML_MAP_CORNER_GLOBAL) ? 100 : 50;
+  G.min_local_pts = 20;
+  return G;
+}
+
+static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, float cell_hint) {
+  cudaStream_t st = ctx->stream;
+  float mn[3], mx[3];
+  MML_CHECK(mml_bbox_device(ctx, pts_d, m, mn, mx));
+  const long long kMaxCells = 1ll << 28;
+
+  auto layout = [&](float cell) -> bool {  // fills M.{cell,org_d,dim,ncell,k_per_cube,cube_lo}
+    if (M.global) {
+      int k = (int)floor(50.0 / (double)cell + 0.5);
+      if (k < 1) k = 1;
+      M.k_per_cube = k;
+      M.cell = (float)(50.0 / k);
+      int lo[3], hi[3];
+      // cube range of the bounding box corners (cube_of is monotone per axis)
+      int a0, a1, a2, b0, b1, b2;
+      cube_of(mn[0], mn[1], mn[2], M.cen, a0, a1, a2);
+      cube_of(mx[0], mx[1], mx[2], M.cen, b0, b1, b2);
+      lo[0] = a0; lo[1] = a1; lo[2] = a2; hi[0] = b0; hi[1] = b1; hi[2] = b2;
+      const int lim[3] = {kCubeD, kCubeW, kCubeH};
+      for (int a = 0; a < 3; a++) {
+        if (lo[a] < 0) lo[a] = 0;
+        if (hi[a] > lim[a] - 1) hi[a] = lim[a] - 1;
+        if (hi[a] < lo[a]) hi[a] = lo[a];
+        M.cube_lo[a] = lo[a];
+        M.dim[a] = (hi[a] - lo[a] + 1) * k;
+      }
+      // lower corner of cube index c along x is -25 + 50*(c - cenDepth); y uses cenWidth, z cenHeight
+      M.org_d[0] = -25.0 + 50.0 * (lo[0] - M.cen[2]);
+      M.org_d[1] = -25.0 + 50.0 * (lo[1] - M.cen[0]);
+      M.org_d[2] = -25.0 + 50.0 * (lo[2] - M.cen[1]);
+    } else {
+      M.k_per_cube = 0;
+      M.cell = cell;
+      for (int a = 0; a < 3; a++) {
+        M.cube_lo[a] = 0;
+        M.org_d[a] = (double)mn[a];
+        M.dim[a] = (int)floor(((double)mx[a] - (double)mn[a]) / (double)cell) + 1;
+        if (M.dim[a] < 1) M.dim[a] = 1;
+      }
+    }
+    M.ncell = (long long)M.dim[0] * M.dim[1] * M.dim[2];
+    return M.ncell <= kMaxCells;
+  };
+
+  MML_CUDA(ctx, ctx->tmp_d.reserve(sizeof(int) * (size_t)m));        // cell_of
+  MML_CUDA(ctx, M.cube_count.reserve(sizeof(int) * kNumCubes));
+  int* cell_of = ctx->tmp_d.as<int>();
+
+  auto count_pass = [&](int* cnt) -> int {
+    MML_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)M.ncell + 1), st));
+    MML_CUDA(ctx, cudaMemsetAsync(M.cube_count.p, 0, sizeof(int) * kNumCubes, st));
+    GridDev G = grid_dev(M, 0);
+    G.valid = 1;
+    G.pts = nullptr; G.cell_start = nullptr; G.cube_count = nullptr;
+    for (int a = 0; a < 3; a++) { G.org[a] = M.org_d[a]; G.dim[a] = M.dim[a]; G.cen[a] = M.cen[a]; G.cube_lo[a] = M.cube_lo[a]; }
+    G.inv_cell = 1.0 / (double)M.cell; G.cell = M.cell; G.m = m; G.global = M.global; G.k_per_cube = M.k_per_cube;
+    k_map_count<<<div_up(m, 256), 256, 0, st>>>(pts_d, m, G, cnt, cell_of, M.cube_count.as<int>());
+    MML_LAUNCHED(ctx);
+    return MML_OK;
+  };
+
+  float cell = cell_hint;
+  if (!(cell > 0.f)) {
+    // trial resolution from the volume per point, then rescale so that an occupied cell
+    // holds ~3 points (feature maps are 1-D / 2-D manifolds: occupancy ~ cell^2)
+    double vol = 1.0;
+    for (int a = 0; a < 3; a++) vol *= fmax((double)mx[a] - (double)mn[a], 0.5);
+    cell = (float)fmin(fmax(cbrt(vol / (double)m) * 1.5, 0.1), 5.0);
+    while (!layout(cell)) cell *= 1.5f;
+    MML_CUDA(ctx, ctx->tmp_e.reserve(sizeof(int) * ((size_t)M.ncell + 1) + 64));
+    MML_CHECK(count_pass(ctx->tmp_e.as<int>()));
+    unsigned long long* nz_d = reinterpret_cast<unsigned long long*>(ctx->counters.p);
+    MML_CUDA(ctx, cudaMemsetAsync(nz_d, 0, 8, st));
+    k_count_nonzero<<<4 * kNumSMs, 256, 0, st>>>(ctx->tmp_e.as<int>(), M.ncell, nz_d);
+    MML_LAUNCHED(ctx);
+    unsigned long long nz = 0;
+    MML_CUDA(ctx, cudaMemcpyAsync(&nz, nz_d, 8, cudaMemcpyDeviceToHost, st));
+    MML_CUDA(ctx, cudaStreamSynchronize(st));
+    if (nz == 0) nz = 1;
+    const double occ = (double)m / (double)nz;
+    cell = (float)fmin(fmax((double)M.cell * sqrt(3.0 / occ), 0.05), 5.0);
+  }
+  while (!layout(cell)) cell *= 1.25f;
+
+  MML_CUDA(ctx, M.cell_start.reserve(sizeof(int) * ((size_t)M.ncell + 1)));
+  MML_CUDA(ctx, ctx->tmp_e.reserve(sizeof(int) * ((size_t)M.ncell + 1) + 64));
+  MML_CUDA(ctx, M.pts.reserve(sizeof(float4) * (size_t)m));
+  int* cell_start = M.cell_start.as<int>();
+  MML_CHECK(count_pass(cell_start));
+  k_exclusive_scan<<<1, kScanThreads, 0, st>>>(cell_start, nullptr, (int)(M.ncell + 1), nullptr);
+  MML_LAUNCHED(ctx);
+  MML_CUDA(ctx, cudaMemsetAsync(ctx->tmp_e.p, 0, sizeof(int) * (size_t)M.ncell, st));
+  k_map_scatter<<<div_up(m, 256), 256, 0, st>>>(pts_d, m, cell_of, cell_start, ctx->tmp_e.as<int>(), M.pts.as<float4>());
+  MML_LAUNCHED(ctx);
+  MML_CUDA(ctx, cudaGetLastError());
+  M.valid = true;
+  return MML_OK;
+}
+
+// Launch association of the frame slot's corner (kind 0) or surf (kind 1) queries.
+// T_dev / thres_dev / gate non-null: parameters come from the device-side solver state.
+int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres, const double* T_dev,
+                         const float* thres_dev, const int* gate, const int* nq_dev, int cap) {
+  const int nq = cap;
+  const int grid = div_up(nq > 0 ? nq : 1, 128);
+  mml::DevBuf& fb = kind == 0 ? ctx->f_line : ctx->f_plane;
+  MML_CUDA(ctx, fb.reserve(sizeof(float4) * 3 * (size_t)(nq > 0 ? nq : 1)));
+  // assoc_stats layout (doubles): [0..7] line moments/count, [8..15] plane moments/count,
+  // then ints: n_line, n_plane, tickets
+  MML_CUDA(ctx, ctx->assoc_stats.reserve(512));
+  MML_CUDA(ctx, ctx->tmp_c.reserve(sizeof(double) * 8 * (size_t)grid + 64));
+  AssocArgs A;
+  memset(&A, 0, sizeof(A));
+  A.q = (kind == 0 ? ctx->q_corner : ctx->q_surf).as<float4>();
+  A.nq = nq;
+  A.nq_dev = nq_dev;
+  if (T16) for (int k = 0; k < 16; k++) A.T[k] = T16[k];
+  A.thres = thres;
+  A.G[0] = grid_dev(ctx->maps[kind == 0 ? MML_MAP_CORNER_GLOBAL : MML_MAP_SURF_GLOBAL], kind == 0 ? 0 : 1);
+  A.G[1] = grid_dev(ctx->maps[kind == 0 ? MML_MAP_CORNER_LOCAL : MML_MAP_SURF_LOCAL], kind == 0 ? 2 : 3);
+  if (!A.G[0].valid) { A.G[0].cen[0] = ctx->maps[kind].cen[0]; A.G[0].cen[1] = ctx->maps[kind].cen[1]; A.G[0].cen[2] = ctx->maps[kind].cen[2]; }
+  A.feat = fb.as<float4>();
+  double* stats = ctx->assoc_stats.as<double>();
+  A.moment_out = stats + 8 * kind;
+  int* ints = reinterpret_cast<int*>(stats + 16);
+  A.n_feat_out = ints + kind;
+  A.ticket = reinterpret_cast<unsigned*>(ints + 4 + kind);
+  A.moment_partials = ctx->tmp_c.as<double>();
+  A.gate = gate;
+  A.T_dev = T_dev;
+  A.thres_dev = thres_dev;
+  if (kind == 0) k_associate<0><<<grid, 128, 0, ctx->stream>>>(A);
+  else k_associate<1><<<grid, 128, 0, ctx->stream>>>(A);
+  MML_LAUNCHED(ctx);
+  MML_CUDA(ctx, cudaGetLastError());
+  return MML_OK;
+}
+
+int mml_export_features(mml_ctx* ctx, int kind, int nq, double* out_dev) {
+  if (nq <= 0) return MML_OK;
+  const float4* f = (kind == 0 ? ctx->f_line : ctx->f_plane).as<float4>();
+  if (kind == 0) k_export_features<0><<<div_up(nq, 256), 256, 0, ctx->stream>>>(f, nq, out_dev);
+  else k_export_features<1><<<div_up(nq, 256), 256, 0, ctx->stream>>>(f, nq, out_dev);
+  MML_LAUNCHED(ctx);
+  MML_CUDA(ctx, cudaGetLastError());
+  return MML_OK;
+}

@@ -1,0 +1,474 @@
+// C-ABI of libmmloam_b200.so (include/mmloam_b200.h): host-buffer entry points stage through
+// pinned memory, run the device pipeline on the context's stream and copy results back.
+#include "common.cuh"
+#include <math.h>
+
+// device-resident stages (extract.cu, geometry.cu, associate.cu, accumulate.cu)
+namespace mml { struct EstState; }
+int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_d, const int* scan_off, int n_scans,
+                       int n_lines, uint8_t* label_d);
+int mml_undistort_device(mml_ctx* ctx, float4* pts_d, const float* s_d, int n, const double* dR9, const double* dt3);
+int mml_label_split_device(mml_ctx* ctx, const float4* pts_d, const uint8_t* label_d, int n, float4* corner_d,
+                           float4* surf_d, int* cnt_d);
+int mml_voxel_device(mml_ctx* ctx, const float4* pts_d, const int* n_dev, int n_max, float leaf, float4* out_d, int* m_dev);
+int mml_velo_ring_time_device(mml_ctx* ctx, const float4* pts_d, int n, const float* first_last_xy, int16_t* ring_d,
+                              float* reltime_d);
+int mml_hori_filter_device(mml_ctx* ctx, const uint32_t* off_d, const float* xyz_d, const uint8_t* line_d, int n,
+                           uint32_t last_offset, uint8_t* keep_d, float* reltime_d);
+int mml_map_set_device(mml_ctx* ctx, int kind, const float4* pts_d, int m, const int* cen3, float cell_hint);
+int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres, const double* T_dev,
+                         const float* thres_dev, const int* gate, const int* nq_dev, int cap);
+int mml_export_features(mml_ctx* ctx, int kind, int nq, double* out_dev);
+int mml_accumulate_launch(mml_ctx* ctx, const double* x6, const double* T_bl16, double lidar_m, double w_tan,
+                          double huber_a, mml::EstState* st_dev, const int* n_dev, int cap_line, int cap_plane,
+                          const double* wide_line_dev, const double* wide_plane_dev);
+int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int cap_surf, const double* exTlb16,
+                        double* P3, double* q4, const mml_est_params* prm, double* stats);
+
+using namespace mml;
+
+static int round_cap(int n) {  // capacity classes keep the captured graph reusable across scans
+  int c = 1024;
+  while (c < n) c += c / 2 > 4096 ? 4096 : c;
+  return c;
+}
+
+extern "C" {
+
+int mml_version(void) { return 100; }
+
+int mml_ctx_create(int device, int stream_count, mml_ctx** out) {
+  if (!out) return MML_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return MML_ERR_NO_DEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return MML_ERR_NO_DEVICE;
+  mml_ctx* c = new mml_ctx();
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return MML_ERR_CUDA;
+  }
+  for (int i = 1; i < stream_count; i++) {
+    cudaStream_t s;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess) c->extra_streams.push_back(s);
+  }
+  cudaEventCreate(&c->ev0);
+  cudaEventCreate(&c->ev1);
+  *out = c;
+  return MML_OK;
+}
+
+int mml_ctx_destroy(mml_ctx* c) {
+  if (!c) return MML_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->est_graph) cudaGraphExecDestroy(c->est_graph);
+  mml::DevBuf* bufs[] = {&c->in_xyzi, &c->in_line, &c->in_s, &c->in_label, &c->srt_xyzi, &c->srt_src, &c->srt_line,
+                         &c->chunk_tab, &c->chunk_hist, &c->line_start, &c->line_count, &c->curv, &c->refl, &c->attr,
+                         &c->sort_ind, &c->refl_ind, &c->counters, &c->tmp_a, &c->tmp_b, &c->tmp_c, &c->tmp_d, &c->tmp_e,
+                         &c->vox_keys[0], &c->vox_keys[1], &c->vox_vals[0], &c->vox_vals[1], &c->vox_hist, &c->vox_bbox,
+                         &c->corner_raw, &c->surf_raw, &c->q_corner, &c->q_surf, &c->f_line, &c->f_plane,
+                         &c->acc_partials, &c->acc_out, &c->est_state, &c->assoc_stats, &c->frame_cnt, &c->export_buf};
+  for (auto* b : bufs) b->release();
+  for (int k = 0; k < 4; k++) {
+    c->maps[k].pts.release();
+    c->maps[k].cell_start.release();
+    c->maps[k].cube_count.release();
+  }
+  c->pin_in.release();
+  c->pin_out.release();
+  c->pin_small.release();
+  for (auto s : c->extra_streams) cudaStreamDestroy(s);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return MML_OK;
+}
+
+const char* mml_last_error(const mml_ctx* c) { return c ? c->err.c_str() : "null context"; }
+long long mml_launch_count(const mml_ctx* c) { return c ? c->launches : 0; }
+void* mml_stream_handle(mml_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int mml_sync(mml_ctx* c) {
+  if (!c) return MML_ERR_INVALID;
+  MML_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MML_OK;
+}
+
+int mml_timer_start(mml_ctx* c) {
+  if (!c) return MML_ERR_INVALID;
+  MML_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  return MML_OK;
+}
+int mml_timer_stop_ms(mml_ctx* c, float* ms) {
+  if (!c || !ms) return MML_ERR_INVALID;
+  MML_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  MML_CUDA(c, cudaEventSynchronize(c->ev1));
+  MML_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return MML_OK;
+}
+
+void mml_est_params_default(mml_est_params* p) {
+  p->max_outer = 5;
+  p->max_inner = 10;
+  p->lidar_m = 1.5e-3;
+  p->plan_weight_tan = 0.0;
+  p->thres0 = 25.0;
+  p->thres1 = 10.0;
+  p->thres2 = 1.0;
+  p->use_huber = 1;
+  p->reserved = 0;
+}
+
+// ---- staging helpers -----------------------------------------------------------------
+static int upload(mml_ctx* c, mml::DevBuf& dst, const void* src, size_t bytes) {
+  MML_CUDA(c, dst.reserve(bytes ? bytes : 16));
+  if (bytes) MML_CUDA(c, cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  return MML_OK;
+}
+static int download(mml_ctx* c, void* dst, const void* src_d, size_t bytes) {
+  if (bytes) MML_CUDA(c, cudaMemcpyAsync(dst, src_d, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return MML_OK;
+}
+
+int mml_extract_features_batch(mml_ctx* c, const float* xyzi, const uint16_t* line_id, const int* scan_offsets,
+                               int n_scans, int n_lines, uint8_t* out_label, int* out_n_sharp, int* out_n_flat) {
+  if (!c || !scan_offsets || n_scans < 0) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  const int n = n_scans > 0 ? scan_offsets[n_scans] : 0;
+  if (n > 0 && (!xyzi || !line_id || !out_label)) return MML_ERR_INVALID;
+  MML_CHECK(upload(c, c->in_xyzi, xyzi, sizeof(float) * 4 * (size_t)n));
+  MML_CHECK(upload(c, c->in_line, line_id, sizeof(uint16_t) * (size_t)n));
+  MML_CUDA(c, c->in_label.reserve((size_t)n + 16));
+  MML_CHECK(mml_extract_device(c, c->in_xyzi.as<float4>(), c->in_line.as<uint16_t>(), scan_offsets, n_scans, n_lines,
+                               c->in_label.as<uint8_t>()));
+  MML_CHECK(download(c, out_label, c->in_label.p, (size_t)n));
+  std::vector<int> cnt(2 * (size_t)n_scans + 2, 0);
+  MML_CHECK(download(c, cnt.data(), c->counters.p, sizeof(int) * 2 * (size_t)n_scans));
+  MML_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int s = 0; s < n_scans; s++) {
+    if (out_n_sharp) out_n_sharp[s] = cnt[2 * s];
+    if (out_n_flat) out_n_flat[s] = cnt[2 * s + 1];
+  }
+  return MML_OK;
+}
+
+int mml_extract_features(mml_ctx* c, const float* xyzi, const uint16_t* line_id, int n, int n_lines,
+                         uint8_t* out_label, int* out_n_sharp, int* out_n_flat) {
+  if (n < 0) return MML_ERR_INVALID;
+  const int off[2] = {0, n};
+  return mml_extract_features_batch(c, xyzi, line_id, off, 1, n_lines, out_label, out_n_sharp, out_n_flat);
+}
+
+int mml_velo_ring_time(mml_ctx* c, const float* xyzi, int n, int16_t* line_out, float* reltime_out) {
+  if (!c || n < 0) return MML_ERR_INVALID;
+  if (n == 0) return MML_OK;
+  cudaSetDevice(c->device);
+  MML_CHECK(upload(c, c->in_xyzi, xyzi, sizeof(float) * 4 * (size_t)n));
+  MML_CUDA(c, c->tmp_a.reserve(sizeof(int16_t) * (size_t)n));
+  MML_CUDA(c, c->tmp_b.reserve(sizeof(float) * (size_t)n));
+  const float fl[4] = {xyzi[0], xyzi[1], xyzi[4 * (size_t)(n - 1)], xyzi[4 * (size_t)(n - 1) + 1]};
+  MML_CHECK(mml_velo_ring_time_device(c, c->in_xyzi.as<float4>(), n, fl, c->tmp_a.as<int16_t>(), c->tmp_b.as<float>()));
+  MML_CHECK(download(c, line_out, c->tmp_a.p, sizeof(int16_t) * (size_t)n));
+  MML_CHECK(download(c, reltime_out, c->tmp_b.p, sizeof(float) * (size_t)n));
+  MML_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MML_OK;
+}
+
+int mml_hori_filter(mml_ctx* c, const uint32_t* offset_time, const float* xyz3, const uint8_t* line, int n, uint8_t* keep,
+                    float* reltime_out) {
+  if (!c || n < 0) return MML_ERR_INVALID;
+  if (n == 0) return MML_OK;
+  cudaSetDevice(c->device);
+  MML_CHECK(upload(c, c->tmp_a, offset_time, sizeof(uint32_t) * (size_t)n));
+  MML_CHECK(upload(c, c->tmp_b, xyz3, sizeof(float) * 3 * (size_t)n));
+  MML_CHECK(upload(c, c->in_line, line, (size_t)n));
+  MML_CUDA(c, c->in_label.reserve((size_t)n + 16));
+  MML_CUDA(c, c->in_s.reserve(sizeof(float) * (size_t)n));
+  MML_CHECK(mml_hori_filter_device(c, c->tmp_a.as<uint32_t>(), c->tmp_b.as<float>(), c->in_line.as<uint8_t>(), n,
+                                   offset_time[n - 1], c->in_label.as<uint8_t>(), c->in_s.as<float>()));
+  MML_CHECK(download(c, keep, c->in_label.p, (size_t)n));
+  MML_CHECK(download(c, reltime_out, c->in_s.p, sizeof(float) * (size_t)n));
+  MML_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MML_OK;
+}
+
+int mml_undistort(mml_ctx* c, float* xyzi, const float* s, int n, const double* dR9, const double* dt3) {
+  if (!c || n < 0 || !dR9 || !dt3) return MML_ERR_INVALID;
+  if (n == 0) return MML_OK;
+  cudaSetDevice(c->device);
+  MML_CHECK(upload(c, c->in_xyzi, xyzi, sizeof(float) * 4 * (size_t)n));
+  MML_CHECK(upload(c, c->in_s, s, sizeof(float) * (size_t)n));
+  MML_CHECK(mml_undistort_device(c, c->in_xyzi.as<float4>(), c->in_s.as<float>(), n, dR9, dt3));
+  MML_CHECK(download(c, xyzi, c->in_xyzi.p, sizeof(float) * 4 * (size_t)n));
+  MML_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MML_OK;
+}
+
+int mml_voxel_downsample(mml_ctx* c, const float* xyzi, int n, float leaf, float* out, int* m_out) {
+  if (!c || n < 0 || !(leaf > 0.f) || !m_out) return MML_ERR_INVALID;
+  *m_out = 0;
+  if (n == 0) return MML_OK;
+  cudaSetDevice(c->device);
+  MML_CHECK(upload(c, c->corner_raw, xyzi, sizeof(float) * 4 * (size_t)n));
+  MML_CUDA(c, c->q_corner.reserve(sizeof(float4) * (size_t)n));
+  MML_CUDA(c, c->frame_cnt.reserve(64));
+  int* cnt = c->frame_cnt.as<int>();
+  MML_CUDA(c, cudaMemcpyAsync(cnt + 4, &n, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  MML_CHECK(mml_voxel_device(c, c->corner_raw.as<float4>(), cnt + 4, n, leaf, c->q_corner.as<float4>(), cnt + 5));
+  int m = 0;
+  MML_CHECK(download(c, &m, cnt + 5, sizeof(int)));
+  MML_CUDA(c, cudaStreamSynchronize(c->stream));
+  MML_CHECK(download(c, out, c->q_corner.p, sizeof(float) * 4 * (size_t)m));
+  MML_CUDA(c, cudaStreamSynchronize(c->stream));
+  *m_out = m;
+  return MML_OK;
+}
+
+int mml_map_set(mml_ctx* c, int kind, const float* xyzi, int m, const int* cube_centre3) {
+  if (!c || m < 0) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  MML_CHECK(upload(c, c->tmp_a, xyzi, sizeof(float) * 4 * (size_t)m));
+  return mml_map_set_device(c, kind, c->tmp_a.as<float4>(), m, cube_centre3, 0.f);
+}
+
+// like mml_map_set with an explicit cell edge (0 = automatic); used by the roofline sweep
+int mml_map_set_ex(mml_ctx* c, int kind, const float* xyzi, int m, const int* cube_centre3, float cell) {
+  if (!c || m < 0) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  MML_CHECK(upload(c, c->tmp_a, xyzi, sizeof(float) * 4 * (size_t)m));
+  return mml_map_set_device(c, kind, c->tmp_a.as<float4>(), m, cube_centre3, cell);
+}
+
+int mml_map_info(mml_ctx* c, int kind, double* info8) {
+  if (!c || kind < 0 || kind > 3 || !info8) return MML_ERR_INVALID;
+  const mml::GridMap& M = c->maps[kind];
+  info8[0] = M.valid; info8[1] = M.m; info8[2] = M.cell; info8[3] = M.dim[0]; info8[4] = M.dim[1]; info8[5] = M.dim[2];
+  info8[6] = (double)M.ncell; info8[7] = M.k_per_cube;
+  return MML_OK;
+}
+
+int mml_frame_set(mml_ctx* c, const float* corner_xyzi, int n_corner, const float* surf_xyzi, int n_surf) {
+  if (!c || n_corner < 0 || n_surf < 0) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  MML_CUDA(c, c->q_corner.reserve(sizeof(float4) * (size_t)round_cap(n_corner)));
+  MML_CUDA(c, c->q_surf.reserve(sizeof(float4) * (size_t)round_cap(n_surf)));
+  if (n_corner) MML_CUDA(c, cudaMemcpyAsync(c->q_corner.p, corner_xyzi, sizeof(float4) * (size_t)n_corner, cudaMemcpyHostToDevice, c->stream));
+  if (n_surf) MML_CUDA(c, cudaMemcpyAsync(c->q_surf.p, surf_xyzi, sizeof(float4) * (size_t)n_surf, cudaMemcpyHostToDevice, c->stream));
+  c->n_corner = n_corner;
+  c->n_surf = n_surf;
+  MML_CUDA(c, c->frame_cnt.reserve(64));
+  const int cnt[2] = {n_corner, n_surf};
+  MML_CUDA(c, cudaMemcpyAsync(c->frame_cnt.p, cnt, sizeof(cnt), cudaMemcpyHostToDevice, c->stream));
+  MML_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MML_OK;
+}
+
+static int read_assoc_stats(mml_ctx* c, int* n_line, int* n_plane, double* moment9, int* n_normals) {
+  double h[20];
+  MML_CHECK(download(c, h, c->assoc_stats.p, sizeof(h)));
+  MML_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int* ints = reinterpret_cast<const int*>(h + 16);
+  if (n_line) *n_line = ints[0];
+  if (n_plane) *n_plane = ints[1];
+  if (moment9) {
+    const double* m = h + 8;
+    const double M[9] = {m[0], m[1], m[2], m[1], m[3], m[4], m[2], m[4], m[5]};
+    for (int i = 0; i < 9; i++) moment9[i] = M[i];
+  }
+  if (n_normals) *n_normals = ints[1];
+  return MML_OK;
+}
+
+int mml_frame_associate_async(mml_ctx* c, const double* T_wl16, double thres_dist, int repeat) {
+  if (!c || !T_wl16) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  for (int r = 0; r < repeat; r++) {
+    MML_CHECK(mml_associate_launch(c, 0, T_wl16, (float)thres_dist, nullptr, nullptr, nullptr, nullptr, c->n_corner));
+    MML_CHECK(mml_associate_launch(c, 1, T_wl16, (float)thres_dist, nullptr, nullptr, nullptr, nullptr, c->n_surf));
+  }
+  return MML_OK;
+}
+
+int mml_frame_associate(mml_ctx* c, const double* T_wl16, double thres_dist, int* n_line, int* n_plane,
+                        double* normal_moment9, int* n_normals) {
+  MML_CHECK(mml_frame_associate_async(c, T_wl16, thres_dist, 1));
+  return read_assoc_stats(c, n_line, n_plane, normal_moment9, n_normals);
+}
+
+int mml_frame_accumulate_async(mml_ctx* c, const double* x6, const double* T_bl16, double plan_weight_tan,
+                               double huber_a, int repeat) {
+  if (!c || !x6 || !T_bl16) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  for (int r = 0; r < repeat; r++)
+    MML_CHECK(mml_accumulate_launch(c, x6, T_bl16, 1.5e-3, plan_weight_tan, huber_a, nullptr, nullptr, c->n_corner, c->n_surf,
+                                    nullptr, nullptr));
+  return MML_OK;
+}
+
+static void unpack28_host(const double* o, double* H36, double* g6, double* cost) {
+  if (cost) *cost = o[0];
+  if (g6) for (int i = 0; i < 6; i++) g6[i] = o[1 + i];
+  if (H36) {
+    int k = 7;
+    for (int i = 0; i < 6; i++)
+      for (int j = i; j < 6; j++) {
+        H36[6 * i + j] = o[k];
+        H36[6 * j + i] = o[k];
+        k++;
+      }
+  }
+}
+
+int mml_frame_accumulate(mml_ctx* c, const double* x6, const double* T_bl16, double plan_weight_tan, double huber_a,
+                         double* H36, double* g6, double* cost) {
+  MML_CHECK(mml_frame_accumulate_async(c, x6, T_bl16, plan_weight_tan, huber_a, 1));
+  double o[28];
+  MML_CHECK(download(c, o, c->acc_out.p, sizeof(o)));
+  MML_CUDA(c, cudaStreamSynchronize(c->stream));
+  unpack28_host(o, H36, g6, cost);
+  return MML_OK;
+}
+
+int mml_frame_accumulate_partial_dev(mml_ctx* c, const double* x6, const double* T_bl16, double plan_weight_tan,
+                                     double huber_a, void** partial28_dev) {
+  MML_CHECK(mml_frame_accumulate_async(c, x6, T_bl16, plan_weight_tan, huber_a, 1));
+  if (partial28_dev) *partial28_dev = c->acc_out.p;
+  return MML_OK;
+}
+
+int mml_frame_get_features(mml_ctx* c, int kind, double* out_feat) {
+  if (!c || (kind != 0 && kind != 1)) return MML_ERR_INVALID;
+  const int nq = kind == 0 ? c->n_corner : c->n_surf;
+  if (nq <= 0) return MML_OK;
+  MML_CUDA(c, c->export_buf.reserve(sizeof(double) * 12 * (size_t)nq));
+  MML_CHECK(mml_export_features(c, kind, nq, c->export_buf.as<double>()));
+  MML_CHECK(download(c, out_feat, c->export_buf.p, sizeof(double) * 12 * (size_t)nq));
+  MML_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MML_OK;
+}
+
+int mml_associate(mml_ctx* c, int kind, const float* q_xyzi, int nq, const double* T_wl16, double thres_dist,
+                  double* out_feat, int* n_feat, double* normal_moment9, int* n_normals) {
+  if (!c || (kind != 0 && kind != 1) || nq < 0 || !T_wl16) return MML_ERR_INVALID;
+  if (kind == 0) MML_CHECK(mml_frame_set(c, q_xyzi, nq, nullptr, 0));
+  else MML_CHECK(mml_frame_set(c, nullptr, 0, q_xyzi, nq));
+  MML_CHECK(mml_associate_launch(c, kind, T_wl16, (float)thres_dist, nullptr, nullptr, nullptr, nullptr, nq));
+  int nl = 0, np = 0;
+  MML_CHECK(read_assoc_stats(c, &nl, &np, kind == 1 ? normal_moment9 : nullptr, kind == 1 ? n_normals : nullptr));
+  if (n_feat) *n_feat = kind == 0 ? nl : np;
+  if (out_feat) MML_CHECK(mml_frame_get_features(c, kind, out_feat));
+  return MML_OK;
+}
+
+// stateless form: features arrive as host 12-double records and are evaluated as such
+int mml_accumulate(mml_ctx* c, const double* line_feat, int n_line, const double* plane_feat, int n_plane,
+                   const double* x6, const double* T_bl16, double plan_weight_tan, double huber_a, double* H36,
+                   double* g6, double* cost) {
+  if (!c || n_line < 0 || n_plane < 0 || !x6 || !T_bl16) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  MML_CHECK(upload(c, c->tmp_a, line_feat, sizeof(double) * 12 * (size_t)n_line));
+  MML_CHECK(upload(c, c->tmp_b, plane_feat, sizeof(double) * 12 * (size_t)n_plane));
+  MML_CHECK(mml_accumulate_launch(c, x6, T_bl16, 1.5e-3, plan_weight_tan, huber_a, nullptr, nullptr, n_line, n_plane,
+                                  c->tmp_a.as<double>(), c->tmp_b.as<double>()));
+  double o[28];
+  MML_CHECK(download(c, o, c->acc_out.p, sizeof(o)));
+  MML_CUDA(c, cudaStreamSynchronize(c->stream));
+  unpack28_host(o, H36, g6, cost);
+  return MML_OK;
+}
+
+int mml_estimate(mml_ctx* c, const float* corner_xyzi, int n_corner, const float* surf_xyzi, int n_surf,
+                 const double* exTlb16, double* P3, double* q_wxyz4, const mml_est_params* prm, double* stats) {
+  if (!c || !exTlb16 || !P3 || !q_wxyz4) return MML_ERR_INVALID;
+  mml_est_params def;
+  mml_est_params_default(&def);
+  if (!prm) prm = &def;
+  MML_CHECK(mml_frame_set(c, corner_xyzi, n_corner, surf_xyzi, n_surf));
+  return mml_estimate_device(c, c->frame_cnt.as<int>(), round_cap(n_corner), round_cap(n_surf), exTlb16, P3, q_wxyz4, prm,
+                             stats);
+}
+
+// extract -> undistort -> split + voxel -> estimate, everything resident between stages
+int mml_scan_to_pose_dev(mml_ctx* c, const void* xyzi_dev, const void* line_id_dev, const void* s_dev, int n, int n_lines,
+                         const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, const double* exTlb16,
+                         double* P3, double* q_wxyz4, const mml_est_params* prm, double* stats, int* out_counts) {
+  if (!c || n < 0 || !exTlb16 || !P3 || !q_wxyz4) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  mml_est_params def;
+  mml_est_params_default(&def);
+  if (!prm) prm = &def;
+  cudaStream_t st = c->stream;
+  MML_CUDA(c, c->in_label.reserve((size_t)n + 16));
+  MML_CUDA(c, c->tmp_e.reserve(sizeof(float4) * (size_t)(n > 0 ? n : 1)));
+  const int off[2] = {0, n};
+  MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, c->in_label.as<uint8_t>()));
+  // undistort a copy of the scan (the caller's buffer stays untouched)
+  mml::DevBuf& wbuf = c->srt_xyzi;  // the line-sorted copy is dead after extraction: reuse its storage
+  MML_CUDA(c, wbuf.reserve(sizeof(float4) * (size_t)(n > 0 ? n : 1)));
+  float4* work = wbuf.as<float4>();
+  if (n) MML_CUDA(c, cudaMemcpyAsync(work, xyzi_dev, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+  if (dR9 && dt3 && s_dev) MML_CHECK(mml_undistort_device(c, work, (const float*)s_dev, n, dR9, dt3));
+  // label split (EST.cpp:992-1011); capacities from the counts of the extractor
+  MML_CUDA(c, c->frame_cnt.reserve(64));
+  int* cnt = c->frame_cnt.as<int>();  // [0..1] voxel outputs, [2..3] raw split counts
+  int hc[2] = {0, 0};
+  MML_CHECK(download(c, hc, c->counters.p, sizeof(hc)));
+  MML_CUDA(c, cudaStreamSynchronize(st));
+  const int n_sharp = hc[0], n_flat = hc[1];
+  MML_CUDA(c, c->corner_raw.reserve(sizeof(float4) * (size_t)(n_sharp + 1)));
+  MML_CUDA(c, c->surf_raw.reserve(sizeof(float4) * (size_t)(n_flat + 1)));
+  const int cap_c = round_cap(n_sharp), cap_s = round_cap(n_flat);
+  MML_CUDA(c, c->q_corner.reserve(sizeof(float4) * (size_t)cap_c));
+  MML_CUDA(c, c->q_surf.reserve(sizeof(float4) * (size_t)cap_s));
+  MML_CHECK(mml_label_split_device(c, work, c->in_label.as<uint8_t>(), n, c->corner_raw.as<float4>(), c->surf_raw.as<float4>(), cnt + 2));
+  MML_CHECK(mml_voxel_device(c, c->corner_raw.as<float4>(), cnt + 2, n_sharp, leaf_corner, c->q_corner.as<float4>(), cnt));
+  MML_CHECK(mml_voxel_device(c, c->surf_raw.as<float4>(), cnt + 3, n_flat, leaf_surf, c->q_surf.as<float4>(), cnt + 1));
+  MML_CHECK(mml_estimate_device(c, cnt, cap_c, cap_s, exTlb16, P3, q_wxyz4, prm, stats));
+  if (out_counts) {
+    int hv[2];
+    MML_CHECK(download(c, hv, cnt, sizeof(hv)));
+    MML_CUDA(c, cudaStreamSynchronize(st));
+    out_counts[0] = n_sharp; out_counts[1] = n_flat; out_counts[2] = hv[0]; out_counts[3] = hv[1];
+    c->n_corner = hv[0];
+    c->n_surf = hv[1];
+  }
+  return MML_OK;
+}
+
+int mml_scan_to_pose(mml_ctx* c, const float* xyzi, const uint16_t* line_id, const float* s, int n, int n_lines,
+                     const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, const double* exTlb16,
+                     double* P3, double* q_wxyz4, const mml_est_params* prm, double* stats, int* out_counts) {
+  if (!c || n < 0) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  MML_CHECK(upload(c, c->in_xyzi, xyzi, sizeof(float) * 4 * (size_t)n));
+  MML_CHECK(upload(c, c->in_line, line_id, sizeof(uint16_t) * (size_t)n));
+  if (s) MML_CHECK(upload(c, c->in_s, s, sizeof(float) * (size_t)n));
+  return mml_scan_to_pose_dev(c, c->in_xyzi.p, c->in_line.p, s ? c->in_s.p : nullptr, n, n_lines, dR9, dt3, leaf_corner,
+                              leaf_surf, exTlb16, P3, q_wxyz4, prm, stats, out_counts);
+}
+
+// device allocation helpers for callers that keep scans resident (bench.py)
+int mml_dev_alloc(mml_ctx* c, size_t bytes, void** out) {
+  if (!c || !out) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  MML_CUDA(c, cudaMalloc(out, bytes ? bytes : 16));
+  return MML_OK;
+}
+int mml_dev_free(mml_ctx* c, void* p) {
+  if (!c) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  MML_CUDA(c, cudaFree(p));
+  return MML_OK;
+}
+int mml_dev_upload(mml_ctx* c, void* dst_dev, const void* src, size_t bytes) {
+  if (!c) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  MML_CUDA(c, cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  MML_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MML_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+// mmloam_b200 internal: context, device buffers, launch helpers. sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/mmloam_b200.h"
+
+namespace mml {
+
+constexpr int kNumSMs = 148;            // B200: 2 dies x 74 SMs
+constexpr int kParts = 50;              // thPartNum, FE.cpp:356
+constexpr int kCubeW = 21, kCubeH = 11, kCubeD = 21;  // MM.h:117-119
+constexpr int kNumCubes = kCubeW * kCubeH * kCubeD;
+constexpr int kCubeNone = 5000;         // MM.cpp:601
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// One spatial-hash map (a "kind" of mml_map_set): points sorted by cell.
+struct GridMap {
+  int m = 0;                 // points
+  float cell = 0.f;          // cell edge
+  float inv_cell = 0.f;
+  double org_d[3] = {0, 0, 0};  // lower corner of cell (0,0,0)
+  int dim[3] = {0, 0, 0};
+  int k_per_cube = 0;        // cells per 50 m cube edge (global kinds)
+  int cube_lo[3] = {0, 0, 0};
+  long long ncell = 0;
+  bool global = false;       // true: honour the 50 m cube rule
+  int cen[3] = {10, 5, 10};
+  DevBuf pts;                // float4[m] cell-sorted (w = original index bits)
+  DevBuf cell_start;         // int[ncell+1]
+  DevBuf cube_count;         // int[kNumCubes] points per 50 m cube (global kinds)
+  bool valid = false;
+};
+
+struct EstDev;  // device-side solver state (accumulate.cu)
+
+}  // namespace mml
+
+struct mml_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<cudaStream_t> extra_streams;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  long long launches = 0;
+
+  // scratch (grow-only)
+  mml::DevBuf in_xyzi, in_line, in_s, in_label;          // staged scan
+  mml::DevBuf srt_xyzi, srt_src, srt_line;               // line-sorted scan
+  mml::DevBuf chunk_tab, chunk_hist, line_start, line_count;
+  mml::DevBuf curv, refl, attr, sort_ind, refl_ind;      // per-point extraction state
+  mml::DevBuf counters;                                  // small int scratch
+  mml::DevBuf tmp_a, tmp_b, tmp_c, tmp_d, tmp_e;         // generic
+  mml::DevBuf vox_keys[2], vox_vals[2], vox_hist, vox_bbox;
+  mml::DevBuf corner_raw, surf_raw;                      // label-split clouds
+  mml::PinBuf pin_in, pin_out, pin_small;
+
+  // resident maps
+  mml::GridMap maps[4];
+
+  // frame slot (queries + features)
+  mml::DevBuf q_corner, q_surf;   // float4
+  int n_corner = 0, n_surf = 0;
+  mml::DevBuf f_line, f_plane;    // compact features (see associate.cu)
+  mml::DevBuf acc_partials, acc_out, est_state;
+  mml::DevBuf assoc_stats;        // ints + doubles
+  cudaGraphExec_t est_graph = nullptr;
+  long long est_graph_key = 0;
+  long long est_launches_per_graph = 0;
+  mml::DevBuf frame_cnt;          // int[2] device-side query counts
+  mml::DevBuf export_buf;
+};
+
+#define MML_CUDA(ctx, call)                                                         \
+  do {                                                                              \
+    cudaError_t _e = (call);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(_e);              \
+      return MML_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define MML_CHECK(expr)      \
+  do {                       \
+    int _r = (expr);         \
+    if (_r != MML_OK) return _r; \
+  } while (0)
+
+#define MML_LAUNCHED(ctx) ((ctx)->launches++)
+
+static inline int mml_fail(mml_ctx* ctx, int code, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }

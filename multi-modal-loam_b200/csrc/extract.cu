@@ -1,0 +1,560 @@
+// Feature extraction on the device: every line of every scan in one pass.
+//
+// Replaces feature_extraction::detectFeaturePoints (reference
+// mm-loam/src/unionFeatureExtract.cpp:341-844) and the split / label glue around it
+// (FE.cpp:1001-1023, 1209-1240). Results are bit-identical to the CPU oracle: all float32
+// and float64 expressions keep the reference's operand order and the file is compiled with
+// -fmad=false (the reference is built for baseline x86-64, no FMA contraction).
+//
+// Pipeline (all on ctx->stream, no host synchronisation inside):
+//   E1  k_line_hist / k_line_scan / k_line_scatter   stable split of each scan by line id
+//   E2  k_point_attr      per point: curvature, reflectivity difference and a 16-bit
+//                         attribute word holding every per-point test of FE.cpp:407-451,
+//                         543-806 (the parts of the algorithm with no sequential dependence)
+//   E3  k_part_sort       50 parts per line, stable rank-by-counting in shared memory
+//                         (replaces the O(m^2) insertion sorts of FE.cpp:458-479)
+//   E4  k_select          one CTA per line; the order-dependent flat selection
+//                         (FE.cpp:483-539) and the count_num stride walk (FE.cpp:543-650)
+//                         run on two lanes over shared-memory state; labels are scattered
+//                         back to input order.
+// HBM traffic per input point: 16 B xyzi + 2 B line read, 1 B label written (the
+// algorithmic 19 B of SURVEY.md §8 d) plus the line-sorted working copy.
+#include "common.cuh"
+
+namespace mml {
+
+// attribute bits written by k_point_attr
+enum : unsigned {
+  A_CAND = 1u << 0,   // curvature < (0.02*depth)^2          FE.cpp:488
+  A_FAR = 1u << 1,    // depth > 50                           FE.cpp:499
+  A_ANGLE = 1u << 2,  // both incidence cosines > 0.966       FE.cpp:430
+  A_GAP = 1u << 3,    // |p[i+1]-p[i]|^2 > 0.02               FE.cpp:499,512
+  A_C300 = 1u << 4,   // reflectivity pick test               FE.cpp:534-535
+  A_RF = 1u << 5,     // right side flat -> stride 4          FE.cpp:597-609
+  A_C150 = 1u << 6,   // two-plane corner test passes         FE.cpp:612-647
+  A_BRK100 = 1u << 7, // break point, flag 100                FE.cpp:677-753
+  A_BRK101 = 1u << 8, // break point demoted to 101           FE.cpp:756-804
+  A_NEAR = 1u << 9,   // range^2 < 1                          FE.cpp:824
+  A_W3 = 1u << 10,    // thNumCurvSize == 3 at this point     FE.cpp:424-428
+};
+
+struct Chunk { int scan, start, count, pad; };
+constexpr int kChunkPts = 1024;
+constexpr int kMaxLines = 64;
+
+struct V3d { double x, y, z; };
+__device__ __forceinline__ V3d vsub(const float4& a, const float4& b) {
+  return {(double)a.x - (double)b.x, (double)a.y - (double)b.y, (double)a.z - (double)b.z};
+}
+__device__ __forceinline__ double vdot(const V3d& a, const V3d& b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ double vnorm(const V3d& a) { return sqrt(vdot(a, a)); }
+__device__ __forceinline__ void vnormalize(V3d& a) {
+  double z = vdot(a, a);
+  if (z > 0) {
+    double s = sqrt(z);
+    a.x /= s; a.y /= s; a.z /= s;
+  }
+}
+__device__ __forceinline__ float range3(const float4& p) { return sqrtf(p.x * p.x + p.y * p.y + p.z * p.z); }
+
+// ---------------------------------------------------------------- E1: split by line
+__global__ void __launch_bounds__(256) k_line_hist(const uint16_t* __restrict__ line_id, const Chunk* __restrict__ chunks,
+                                                   int n_lines, int* __restrict__ hist) {
+  __shared__ int h[kMaxLines];
+  const Chunk c = chunks[blockIdx.x];
+  if (threadIdx.x < kMaxLines) h[threadIdx.x] = 0;
+  __syncthreads();
+  for (int r = threadIdx.x; r < c.count; r += 256) {
+    int l = line_id[c.start + r];
+    if (l < n_lines) atomicAdd(&h[l], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < n_lines) hist[(size_t)blockIdx.x * n_lines + threadIdx.x] = h[threadIdx.x];
+}
+
+// one CTA per scan: exclusive scan of the chunk histograms per line, then line offsets
+__global__ void __launch_bounds__(256) k_line_scan(int* __restrict__ hist, const int* __restrict__ scan_chunk0,
+                                                   const int* __restrict__ scan_off, int n_lines,
+                                                   int* __restrict__ line_start, int* __restrict__ line_count) {
+  __shared__ int cnt[kMaxLines];
+  const int s = blockIdx.x;
+  const int c0 = scan_chunk0[s], c1 = scan_chunk0[s + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int l = warp; l < n_lines; l += 8) {
+    int carry = 0;
+    for (int base = c0; base < c1; base += 32) {
+      int c = base + lane;
+      int v = (c < c1) ? hist[(size_t)c * n_lines + l] : 0;
+      int x = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+      }
+      if (c < c1) hist[(size_t)c * n_lines + l] = carry + x - v;
+      carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane == 0) cnt[l] = carry;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = scan_off[s];
+    for (int l = 0; l < n_lines; l++) {
+      line_start[s * n_lines + l] = run;
+      line_count[s * n_lines + l] = cnt[l];
+      run += cnt[l];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_line_scatter(const float4* __restrict__ xyzi, const uint16_t* __restrict__ line_id,
+                                                      const Chunk* __restrict__ chunks, const int* __restrict__ hist,
+                                                      const int* __restrict__ line_start, int n_lines,
+                                                      float4* __restrict__ srt_xyzi, int* __restrict__ srt_src,
+                                                      int* __restrict__ srt_line) {
+  __shared__ int wcnt[8][kMaxLines + 1];
+  __shared__ int base[kMaxLines + 1];
+  const Chunk c = chunks[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x <= kMaxLines) base[threadIdx.x] = 0;
+  for (int r0 = 0; r0 < c.count; r0 += 256) {
+    for (int k = threadIdx.x; k < 8 * (kMaxLines + 1); k += 256) (&wcnt[0][0])[k] = 0;
+    __syncthreads();
+    const int r = r0 + threadIdx.x;
+    const bool act = r < c.count;
+    int l = kMaxLines;
+    if (act) {
+      int li = line_id[c.start + r];
+      if (li < n_lines) l = li;
+    }
+    unsigned mask = __match_any_sync(0xffffffffu, l);
+    int rank = __popc(mask & ((1u << lane) - 1u));
+    if (rank == 0) wcnt[warp][l] = __popc(mask);
+    __syncthreads();
+    if (act && l < n_lines) {
+      int off = base[l] + rank;
+      for (int w = 0; w < warp; w++) off += wcnt[w][l];
+      int pos = line_start[c.scan * n_lines + l] + hist[(size_t)blockIdx.x * n_lines + l] + off;
+      srt_xyzi[pos] = xyzi[c.start + r];
+      srt_src[pos] = c.start + r;
+      srt_line[pos] = c.scan * n_lines + l;
+    }
+    __syncthreads();
+    if (threadIdx.x < n_lines) {
+      int t = 0;
+      for (int w = 0; w < 8; w++) t += wcnt[w][threadIdx.x];
+      base[threadIdx.x] += t;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- E2: per-point tests
+__global__ void __launch_bounds__(256) k_point_attr(const float4* __restrict__ P, const int* __restrict__ srt_line,
+                                                    const int* __restrict__ line_start, const int* __restrict__ line_count,
+                                                    int n_total, float* __restrict__ curv_out, float* __restrict__ refl_out,
+                                                    uint16_t* __restrict__ attr_out) {
+  const int g = blockIdx.x * 256 + threadIdx.x;
+  if (g >= n_total) return;
+  const int gl = srt_line[g];
+  if (gl < 0) { attr_out[g] = 0; curv_out[g] = 0.f; refl_out[g] = 0.f; return; }
+  const int ls = line_start[gl], n = line_count[gl];
+  const int i = g - ls;
+  const float4* p = P + ls;  // p[i] is the line-local point i
+  unsigned a = 0;
+  float curv = 0.f, refl = 0.f;
+  const float4 pi = p[i];
+  if (i + 1 < n) {
+    const float4 q = p[i + 1];
+    float dX = q.x - pi.x, dY = q.y - pi.y, dZ = q.z - pi.z;
+    if ((double)(dX * dX + dY * dY + dZ * dZ) > 0.02) a |= A_GAP;
+  }
+  if (i >= 5 && i < n - 5) {
+    const float4 pm1 = p[i - 1], pp1 = p[i + 1], pm2 = p[i - 2], pp2 = p[i + 2];
+    const float4 pm3 = p[i - 3], pp3 = p[i + 3], pm4 = p[i - 4], pp4 = p[i + 4];
+    // ---- FE.cpp:407-451
+    const float dis = range3(pi);
+    const V3d cur = {(double)pi.x, (double)pi.y, (double)pi.z};
+    const V3d dl = vsub(pm1, pi), dn = vsub(pp1, pi);
+    const double ncur = vnorm(cur);
+    const double angle_last = vdot(dl, cur) / (vnorm(dl) * ncur);
+    const double angle_next = vdot(dn, cur) / (vnorm(dn) * ncur);
+    const bool graze = fabs(angle_last) > 0.966 && fabs(angle_next) > 0.966;
+    const int w = (dis > 50.0f || graze) ? 2 : 3;
+    if (graze) a |= A_ANGLE;
+    if (w == 3) a |= A_W3;
+    float diffX = 0.f, diffY = 0.f, diffZ = 0.f;
+    float diffR = (float)(-2 * w) * pi.w;
+    diffX += pm1.x + pp1.x; diffY += pm1.y + pp1.y; diffZ += pm1.z + pp1.z; diffR += pm1.w + pp1.w;
+    diffX += pm2.x + pp2.x; diffY += pm2.y + pp2.y; diffZ += pm2.z + pp2.z; diffR += pm2.w + pp2.w;
+    if (w == 3) {
+      diffX += pm3.x + pp3.x; diffY += pm3.y + pp3.y; diffZ += pm3.z + pp3.z; diffR += pm3.w + pp3.w;
+    }
+    const float tw = (float)(2 * w);
+    diffX -= tw * pi.x; diffY -= tw * pi.y; diffZ -= tw * pi.z;
+    curv = diffX * diffX + diffY * diffY + diffZ * diffZ;
+    refl = diffR;
+    const float thF = 0.02f;
+    if (curv < thF * dis * thF * dis) a |= A_CAND;
+    if (dis > 50.0f) a |= A_FAR;
+    if ((double)curv < 0.7 * (double)thF * (double)dis * (double)thF * (double)dis && (double)refl > 20.0) a |= A_C300;
+    if (pi.x * pi.x + pi.y * pi.y + pi.z * pi.z < 1.0f) a |= A_NEAR;
+
+    // ---- FE.cpp:543-650 (tests only; which i are visited is decided in k_select)
+    {
+      float lX = pm4.x + pm3.x - 4 * pm2.x + pm1.x + pi.x;
+      float lY = pm4.y + pm3.y - 4 * pm2.y + pm1.y + pi.y;
+      float lZ = pm4.z + pm3.z - 4 * pm2.z + pm1.z + pi.z;
+      float left_curv = lX * lX + lY * lY + lZ * lZ;
+      float rX = pp4.x + pp3.x - 4 * pp2.x + pp1.x + pi.x;
+      float rY = pp4.y + pp3.y - 4 * pp2.y + pp1.y + pi.y;
+      float rZ = pp4.z + pp3.z - 4 * pp2.z + pp1.z + pi.z;
+      float right_curv = rX * rX + rY * rY + rZ * rZ;
+      const bool lf = left_curv < thF * dis, rf = right_curv < thF * dis;
+      if (rf) a |= A_RF;
+      if (lf && rf) {
+        V3d nl = {0, 0, 0}, nr = {0, 0, 0};
+        const float4 L[4] = {pm1, pm2, pm3, pm4};
+        const float4 R[4] = {pp1, pp2, pp3, pp4};
+#pragma unroll
+        for (int k = 1; k < 5; k++) {
+          V3d t = vsub(L[k - 1], pi);
+          vnormalize(t);
+          double wk = k / 10.0;
+          nl.x += wk * t.x; nl.y += wk * t.y; nl.z += wk * t.z;
+        }
+#pragma unroll
+        for (int k = 1; k < 5; k++) {
+          V3d t = vsub(R[k - 1], pi);
+          vnormalize(t);
+          double wk = k / 10.0;
+          nr.x += wk * t.x; nr.y += wk * t.y; nr.z += wk * t.z;
+        }
+        double cc = fabs(vdot(nl, nr) / (vnorm(nl) * vnorm(nr)));
+        double last_dis = vnorm(vsub(pm4, pi));
+        double current_dis = vnorm(vsub(pp4, pi));
+        if (cc < 0.5 && last_dis > 0.05 && current_dis > 0.05) a |= A_C150;
+      }
+    }
+    // ---- FE.cpp:651-806
+    {
+      float dX1 = pp1.x - pi.x, dY1 = pp1.y - pi.y, dZ1 = pp1.z - pi.z;
+      float diff_right = sqrtf(dX1 * dX1 + dY1 * dY1 + dZ1 * dZ1);
+      float dX2 = pm1.x - pi.x, dY2 = pm1.y - pi.y, dZ2 = pm1.z - pi.z;
+      float diff_left = sqrtf(dX2 * dX2 + dY2 * dY2 + dZ2 * dZ2);
+      float depth_right = range3(pp1), depth_left = range3(pm1);
+      bool f100 = false;
+      if (fabsf(diff_right - diff_left) > 1.0f) {
+        if (diff_right > diff_left) {
+          V3d sv = vsub(pm1, pi);
+          double cc = fabs(vdot(sv, cur) / (vnorm(sv) * ncur));
+          if (cc < 0.95) {
+            if (depth_right > depth_left) f100 = true;
+            else if (depth_right == 0.f) f100 = true;
+          }
+        } else {
+          V3d sv = vsub(pp1, pi);
+          double cc = fabs(vdot(sv, cur) / (vnorm(sv) * ncur));
+          if (cc < 0.95) {
+            if (depth_right < depth_left) f100 = true;
+            else if (depth_left == 0.f) f100 = true;
+          }
+        }
+      }
+      if (f100) {
+        V3d nf = {0, 0, 0}, nb = {0, 0, 0};
+        const float4 L[3] = {pm1, pm2, pm3};
+        const float4 R[3] = {pp1, pp2, pp3};
+#pragma unroll
+        for (int k = 1; k < 4; k++) {
+          if (range3(L[k - 1]) < 1.0f) continue;
+          V3d t = vsub(L[k - 1], pi);
+          vnormalize(t);
+          double wk = k / 6.0;
+          nf.x += wk * t.x; nf.y += wk * t.y; nf.z += wk * t.z;
+        }
+#pragma unroll
+        for (int k = 1; k < 4; k++) {
+          if (range3(L[k - 1]) < 1.0f) continue;  // sic, FE.cpp:782 tests i-k for the back side too
+          V3d t = vsub(R[k - 1], pi);
+          vnormalize(t);
+          double wk = k / 6.0;
+          nb.x += wk * t.x; nb.y += wk * t.y; nb.z += wk * t.z;
+        }
+        double cc = fabs(vdot(nf, nb) / (vnorm(nf) * vnorm(nb)));
+        a |= (cc < 0.95) ? A_BRK100 : A_BRK101;
+      }
+    }
+  }
+  curv_out[g] = curv;
+  refl_out[g] = refl;
+  attr_out[g] = (uint16_t)a;
+}
+
+// ---------------------------------------------------------------- E3: per-part stable sort
+__device__ __forceinline__ void part_bounds(int n, int j, int& sp, int& ep) {
+  // FE.cpp:454-455 with scanStartInd = 5, scanEndInd = n - 6
+  const int span = n - 11;
+  sp = 5 + (int)(((long long)span * j) / kParts);
+  ep = 5 + (int)(((long long)span * (j + 1)) / kParts) - 1;
+}
+
+__global__ void __launch_bounds__(128) k_part_sort(const float* __restrict__ curv, const float* __restrict__ refl,
+                                                   const int* __restrict__ line_start, const int* __restrict__ line_count,
+                                                   int* __restrict__ sort_ind, int* __restrict__ refl_ind, int max_m) {
+  extern __shared__ float sm[];
+  const int gl = blockIdx.x / kParts, j = blockIdx.x % kParts;
+  const int n = line_count[gl], ls = line_start[gl];
+  if (n < 11) return;
+  int sp, ep;
+  part_bounds(n, j, sp, ep);
+  const int m = ep - sp + 1;
+  if (m <= 0) return;
+  float* sc = sm;
+  float* sr = sm + max_m;
+  for (int e = threadIdx.x; e < m; e += 128) {
+    sc[e] = curv[ls + sp + e];
+    sr[e] = refl[ls + sp + e];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < m; e += 128) {
+    const float vc = sc[e], vr = sr[e];
+    int rc = 0, rr = 0;
+    for (int k = 0; k < m; k++) {
+      const float c = sc[k], r = sr[k];
+      rc += (c < vc) || (c == vc && k < e);
+      rr += (r < vr) || (r == vr && k < e);
+    }
+    sort_ind[ls + sp + rc] = sp + e;
+    refl_ind[ls + sp + rr] = sp + e;
+  }
+}
+
+// ---------------------------------------------------------------- E4: sequential selection
+// Dynamic shared memory: flags u8[n] | v150 bits u32[(n+31)/32] | part buffers int[2*max_m]
+// | (ATTR_SMEM) attr u16[n].
+template <bool ATTR_SMEM>
+__global__ void __launch_bounds__(64) k_select(const uint16_t* __restrict__ attr_g, const int* __restrict__ sort_ind,
+                                               const int* __restrict__ refl_ind, const int* __restrict__ srt_src,
+                                               const int* __restrict__ line_start, const int* __restrict__ line_count,
+                                               int n_lines, int max_n, int max_m, uint8_t* __restrict__ out_label,
+                                               int* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int gl = blockIdx.x;
+  const int n = line_count[gl], ls = line_start[gl];
+  const int nflag = (max_n + 15) & ~15;
+  const int nbits = ((max_n + 31) / 32 + 3) & ~3;
+  uint8_t* flags = smem_raw;
+  unsigned* v150 = reinterpret_cast<unsigned*>(smem_raw + nflag);
+  int* pbuf = reinterpret_cast<int*>(smem_raw + nflag + 4 * nbits);
+  uint16_t* attr_s = reinterpret_cast<uint16_t*>(smem_raw + nflag + 4 * nbits + 8 * (size_t)max_m);
+  const uint16_t* attr_line = attr_g + ls;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int i = tid; i < n; i += 64) {
+    flags[i] = 0;
+    if (ATTR_SMEM) attr_s[i] = attr_line[i];
+  }
+  for (int i = tid; i < (n + 31) / 32; i += 64) v150[i] = 0;
+  __syncthreads();
+  auto ATTR = [&](int i) -> unsigned { return ATTR_SMEM ? (unsigned)attr_s[i] : (unsigned)__ldg(attr_line + i); };
+
+  if (n >= 11) {
+    if (warp == 0) {
+      // ---- FE.cpp:453-541: parts in order; lane 0 runs the order-dependent logic
+      const int w = (ATTR(n - 6) & A_W3) ? 3 : 2;  // thNumCurvSize left by the last point (FE.cpp:424-428)
+      int* s_sort = pbuf;
+      int* s_refl = pbuf + max_m;
+      for (int j = 0; j < kParts; j++) {
+        int sp, ep;
+        part_bounds(n, j, sp, ep);
+        const int m = ep - sp + 1;
+        if (m <= 0) continue;
+        __syncwarp();
+        for (int e = lane; e < m; e += 32) {
+          s_sort[e] = sort_ind[ls + sp + e];
+          s_refl[e] = refl_ind[ls + sp + e];
+        }
+        __syncwarp();
+        if (lane == 0) {
+          for (int k = 0; k < m; k++) {  // FE.cpp:483-519
+            const int ind = s_sort[k];
+            if (flags[ind] != 0) continue;
+            const unsigned a = ATTR(ind);
+            if (a & A_CAND) {
+              flags[ind] = 3;
+              if (!(a & A_FAR)) {
+                for (int l = 1; l <= w; l++) {
+                  if (ATTR(ind + l - 1) & A_GAP) break;
+                  flags[ind + l] = 1;
+                }
+                for (int l = 1; l <= w; l++) {
+                  if (ATTR(ind - l) & A_GAP) break;
+                  flags[ind - l] = 1;
+                }
+              }
+            }
+          }
+          int smallest = 1, sharpest = 1;
+          for (int k = 0; k < m; k++) {  // FE.cpp:521-539
+            const int ind = s_sort[k];
+            const unsigned a = ATTR(ind);
+            const int f = flags[ind];
+            if ((f == 3 && smallest <= 1) || (f == 3 && (a & A_FAR)) || (a & A_ANGLE)) {
+              smallest++;
+              flags[ind] = 2;
+            }
+            const int idx = s_refl[k];
+            if (sharpest <= 3 && (ATTR(idx) & A_C300)) {
+              sharpest++;
+              flags[idx] = 4;  // 300
+            }
+          }
+        }
+      }
+    } else if (lane == 0) {
+      // ---- FE.cpp:543-650: visit i = 5, then i += 4 if the right side was flat else 1
+      int i = 5;
+      while (i < n - 5) {
+        const unsigned a = ATTR(i);
+        if (a & A_C150) v150[i >> 5] |= 1u << (i & 31);
+        i += (a & A_RF) ? 4 : 1;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- FE.cpp:818-842 + label write-back FE.cpp:1016-1023
+  const int scan = gl / n_lines;
+  int n_sharp = 0, n_flat = 0;
+  for (int i0 = 0; i0 < n; i0 += 64) {
+    const int i = i0 + tid;
+    int label = 0;
+    if (i < n && i >= 5 && i < n - 5) {
+      const unsigned a = ATTR(i);
+      if (!(a & A_NEAR)) {
+        const bool v = (v150[i >> 5] >> (i & 31)) & 1u;
+        if (a & A_BRK100) label = 1;
+        else if (a & A_BRK101) label = 0;
+        else if (v) label = 1;
+        else if (flags[i] == 2) label = 2;
+      }
+    }
+    if (i < n) out_label[srt_src[ls + i]] = (uint8_t)label;
+    n_sharp += __popc(__ballot_sync(0xffffffffu, label == 1));
+    n_flat += __popc(__ballot_sync(0xffffffffu, label == 2));
+  }
+  if (lane == 0) {
+    if (n_sharp) atomicAdd(&counters[2 * scan], n_sharp);
+    if (n_flat) atomicAdd(&counters[2 * scan + 1], n_flat);
+  }
+}
+
+}  // namespace mml
+
+using namespace mml;
+
+// Device-resident extraction. xyzi_d/line_d hold n_total points; labels go to label_d (u8),
+// per-scan (n_sharp, n_flat) to ctx->counters[2*s..]. scan_off is a HOST array.
+int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_d, const int* scan_off, int n_scans,
+                       int n_lines, uint8_t* label_d) {
+  if (n_lines <= 0 || n_lines > kMaxLines) return mml_fail(ctx, MML_ERR_INVALID, "n_lines must be in [1,64]");
+  const int n_total = scan_off[n_scans];
+  const int TL = n_scans * n_lines;
+  cudaStream_t st = ctx->stream;
+  MML_CUDA(ctx, ctx->counters.reserve(sizeof(int) * (2 * (size_t)n_scans + 64)));
+  MML_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * 2 * (size_t)n_scans, st));
+  if (n_total <= 0) return MML_OK;
+
+  // host-side chunk table (metadata only)
+  std::vector<Chunk> chunks;
+  std::vector<int> scan_chunk0(n_scans + 1);
+  int max_scan = 0;
+  for (int s = 0; s < n_scans; s++) {
+    scan_chunk0[s] = (int)chunks.size();
+    const int a = scan_off[s], b = scan_off[s + 1];
+    if (b < a) return mml_fail(ctx, MML_ERR_INVALID, "scan_offsets must be non-decreasing");
+    max_scan = b - a > max_scan ? b - a : max_scan;
+    for (int p = a; p < b; p += kChunkPts) chunks.push_back({s, p, (b - p < kChunkPts ? b - p : kChunkPts), 0});
+  }
+  scan_chunk0[n_scans] = (int)chunks.size();
+  const int n_chunks = (int)chunks.size();
+
+  const size_t meta_bytes = sizeof(Chunk) * n_chunks + sizeof(int) * (2 * (size_t)n_scans + 2);
+  MML_CUDA(ctx, ctx->pin_small.reserve(meta_bytes));
+  MML_CUDA(ctx, ctx->chunk_tab.reserve(meta_bytes));
+  // the pinned staging area may still be in flight from a previous call
+  MML_CUDA(ctx, cudaStreamSynchronize(st));
+  char* hp = ctx->pin_small.as<char>();
+  memcpy(hp, chunks.data(), sizeof(Chunk) * n_chunks);
+  memcpy(hp + sizeof(Chunk) * n_chunks, scan_chunk0.data(), sizeof(int) * (n_scans + 1));
+  memcpy(hp + sizeof(Chunk) * n_chunks + sizeof(int) * (n_scans + 1), scan_off, sizeof(int) * (n_scans + 1));
+  MML_CUDA(ctx, cudaMemcpyAsync(ctx->chunk_tab.p, hp, meta_bytes, cudaMemcpyHostToDevice, st));
+  const Chunk* chunks_d = ctx->chunk_tab.as<Chunk>();
+  const int* scan_chunk0_d = reinterpret_cast<const int*>(ctx->chunk_tab.as<char>() + sizeof(Chunk) * n_chunks);
+  const int* scan_off_d = scan_chunk0_d + (n_scans + 1);
+
+  MML_CUDA(ctx, ctx->chunk_hist.reserve(sizeof(int) * (size_t)n_chunks * n_lines));
+  MML_CUDA(ctx, ctx->line_start.reserve(sizeof(int) * ((size_t)TL + 1)));
+  MML_CUDA(ctx, ctx->line_count.reserve(sizeof(int) * ((size_t)TL + 1)));
+  MML_CUDA(ctx, ctx->srt_xyzi.reserve(sizeof(float4) * (size_t)n_total));
+  MML_CUDA(ctx, ctx->srt_src.reserve(sizeof(int) * (size_t)n_total));
+  MML_CUDA(ctx, ctx->srt_line.reserve(sizeof(int) * (size_t)n_total));
+  MML_CUDA(ctx, ctx->curv.reserve(sizeof(float) * (size_t)n_total));
+  MML_CUDA(ctx, ctx->refl.reserve(sizeof(float) * (size_t)n_total));
+  MML_CUDA(ctx, ctx->attr.reserve(sizeof(uint16_t) * (size_t)n_total));
+  MML_CUDA(ctx, ctx->sort_ind.reserve(sizeof(int) * (size_t)n_total));
+  MML_CUDA(ctx, ctx->refl_ind.reserve(sizeof(int) * (size_t)n_total));
+
+  int* hist = ctx->chunk_hist.as<int>();
+  int* line_start = ctx->line_start.as<int>();
+  int* line_count = ctx->line_count.as<int>();
+
+  MML_CUDA(ctx, cudaMemsetAsync(ctx->srt_line.p, 0xFF, sizeof(int) * (size_t)n_total, st));
+  MML_CUDA(ctx, cudaMemsetAsync(label_d, 0, (size_t)n_total, st));
+  k_line_hist<<<n_chunks, 256, 0, st>>>(line_d, chunks_d, n_lines, hist);
+  MML_LAUNCHED(ctx);
+  k_line_scan<<<n_scans, 256, 0, st>>>(hist, scan_chunk0_d, scan_off_d, n_lines, line_start, line_count);
+  MML_LAUNCHED(ctx);
+  k_line_scatter<<<n_chunks, 256, 0, st>>>(xyzi_d, line_d, chunks_d, hist, line_start, n_lines, ctx->srt_xyzi.as<float4>(),
+                                           ctx->srt_src.as<int>(), ctx->srt_line.as<int>());
+  MML_LAUNCHED(ctx);
+  k_point_attr<<<div_up(n_total, 256), 256, 0, st>>>(ctx->srt_xyzi.as<float4>(), ctx->srt_line.as<int>(), line_start,
+                                                     line_count, n_total, ctx->curv.as<float>(), ctx->refl.as<float>(),
+                                                     ctx->attr.as<uint16_t>());
+  MML_LAUNCHED(ctx);
+
+  // a line cannot be longer than its scan; a part holds at most ceil((n-11)/50)+1 points
+  const int max_n = max_scan;
+  const int max_m = max_n > 11 ? (max_n - 11) / kParts + 2 : 2;
+  const size_t sort_smem = sizeof(float) * 2 * (size_t)max_m;
+  if (sort_smem > 200 * 1024) return mml_fail(ctx, MML_ERR_CAPACITY, "scan line too long for k_part_sort shared memory");
+  if (sort_smem > 48 * 1024)
+    MML_CUDA(ctx, cudaFuncSetAttribute(k_part_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+  k_part_sort<<<TL * kParts, 128, sort_smem, st>>>(ctx->curv.as<float>(), ctx->refl.as<float>(), line_start, line_count,
+                                                   ctx->sort_ind.as<int>(), ctx->refl_ind.as<int>(), max_m);
+  MML_LAUNCHED(ctx);
+
+  const size_t nflag = ((size_t)max_n + 15) & ~(size_t)15;
+  const size_t nbits = (((size_t)max_n + 31) / 32 + 3) & ~(size_t)3;
+  const size_t base_smem = nflag + 4 * nbits + 8 * (size_t)max_m;
+  const size_t full_smem = base_smem + 2 * (size_t)max_n + 16;
+  const size_t kMaxSmem = 227 * 1024;
+  if (base_smem > kMaxSmem) return mml_fail(ctx, MML_ERR_CAPACITY, "scan line too long for k_select shared memory");
+  if (full_smem <= kMaxSmem) {
+    if (full_smem > 48 * 1024)
+      MML_CUDA(ctx, cudaFuncSetAttribute(k_select<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)full_smem));
+    k_select<true><<<TL, 64, full_smem, st>>>(ctx->attr.as<uint16_t>(), ctx->sort_ind.as<int>(), ctx->refl_ind.as<int>(),
+                                              ctx->srt_src.as<int>(), line_start, line_count, n_lines, max_n, max_m, label_d,
+                                              ctx->counters.as<int>());
+  } else {
+    if (base_smem > 48 * 1024)
+      MML_CUDA(ctx, cudaFuncSetAttribute(k_select<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base_smem));
+    k_select<false><<<TL, 64, base_smem, st>>>(ctx->attr.as<uint16_t>(), ctx->sort_ind.as<int>(), ctx->refl_ind.as<int>(),
+                                               ctx->srt_src.as<int>(), line_start, line_count, n_lines, max_n, max_m, label_d,
+                                               ctx->counters.as<int>());
+  }
+  MML_LAUNCHED(ctx);
+  MML_CUDA(ctx, cudaGetLastError());
+  return MML_OK;
+}

@@ -1,0 +1,261 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on identical
+seeded inputs. Integer / index work must be bit-exact; poses within 1e-4 m / 1e-4 rad."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL_M = 1e-4    # north_star: solved pose within 1e-4 m
+POSE_TOL_RAD = 1e-4  # and 1e-4 rad
+
+
+def test_extract_vlp16_bit_exact(ctx, orc, scene):
+    x, ring, _ = scene["vlp"]
+    label, ns, nf = ctx.extract_features(x, ring, 16)
+    ref = orc.extract_scan(x, ring, 16)
+    assert np.array_equal(label, ref)
+    assert ns == int((ref == 1).sum()) and nf == int((ref == 2).sum())
+    assert ns > 20 and nf > 500
+
+
+def test_extract_horizon_bit_exact(ctx, orc, scene):
+    x, line, _ = scene["hori"]
+    label, ns, nf = ctx.extract_features(x, line, 6)
+    ref = orc.extract_scan(x, line, 6)
+    assert np.array_equal(label, ref)
+    assert ns > 20 and nf > 100
+
+
+def test_extract_merged_scan_bit_exact(ctx, orc, scene):
+    vx, vr, _ = scene["vlp"]
+    hx, hl, _ = scene["hori"]
+    x = np.concatenate([vx, hx])
+    line = np.concatenate([vr, hl + 16]).astype(np.uint16)
+    label, _, _ = ctx.extract_features(x, line, 22)
+    assert np.array_equal(label, orc.extract_scan(x, line, 22))
+
+
+def test_extract_batch_matches_single(ctx, orc, synth):
+    xs, ls, offs = [], [], [0]
+    for k in range(3):
+        T = synth.make_T(synth.rot_z(0.1 * k), np.array([-2.0 + k, 0.5 * k, 0.1]))
+        x, r, _ = synth.vlp16_scan(T, seed=50 + k, n_az=900 + 100 * k)
+        xs.append(x); ls.append(r); offs.append(offs[-1] + x.shape[0])
+    X, L = np.concatenate(xs), np.concatenate(ls)
+    label, ns, nf = ctx.extract_features_batch(X, L, offs, 16)
+    for k in range(3):
+        ref = orc.extract_scan(xs[k], ls[k], 16)
+        assert np.array_equal(label[offs[k]:offs[k + 1]], ref)
+        assert ns[k] == int((ref == 1).sum()) and nf[k] == int((ref == 2).sum())
+
+
+@pytest.mark.parametrize("n", [0, 1, 10, 11, 12, 60, 61, 200])
+def test_extract_short_lines(ctx, orc, n):
+    rng = np.random.default_rng(n)
+    x = np.zeros((n, 4), np.float32)
+    if n:
+        ang = np.linspace(-0.5, 0.5, n)
+        r = 5.0 + rng.normal(0, 0.01, n)
+        x[:, 0] = r * np.cos(ang); x[:, 1] = r * np.sin(ang); x[:, 3] = rng.uniform(0, 255, n)
+    label, _, _ = ctx.extract_features(x, np.zeros(n, np.uint16), 1)
+    assert np.array_equal(label, orc.extract_scan(x, np.zeros(n, np.uint16), 1))
+
+
+def test_mirror_detectFeaturePoints(mm, ctx, orc, scene):
+    x, ring, _ = scene["vlp"]
+    fe = mm.LidarFeatureExtractor(ctx)
+    line = x[ring == 5]
+    sharp, flat = fe.detectFeaturePoint(line)
+    rs, rf = orc.detect_feature_points(line)
+    assert np.array_equal(sharp, np.sort(rs)) and np.array_equal(flat, np.sort(rf))
+
+
+def test_velo_ring_time(ctx, orc, scene):
+    x, ring, _ = scene["vlp"]
+    line, rt = ctx.velo_ring_time(x)
+    ol, ort = orc.velo_ring_time(x)
+    assert np.array_equal(line, ol) and np.array_equal(line, ring.astype(np.int16))
+    # CUDA atan2 vs glibc atan2: <= 2 float ulp on the relative time
+    assert np.abs(rt - ort).max() <= 3e-7
+
+
+def test_hori_filter(ctx, orc, synth, scene):
+    x, line, s = scene["hori"]
+    off, xyz, refl, ln = synth.horizon_custom_msg(x, line, s)
+    ln = ln.copy(); ln[::97] = 7           # lines > 5 are dropped
+    xyz = xyz.copy(); xyz[::101, 0] = 0.005  # x < 0.01 are dropped
+    keep, rt = ctx.hori_filter(off, xyz, ln)
+    ok, ort = orc.hori_filter(off, xyz, ln)
+    assert np.array_equal(keep, ok) and np.array_equal(rt, ort)
+
+
+def test_undistort(ctx, orc, synth, scene):
+    x, _, s = scene["vlp"]
+    dR = synth.rotvec_to_R([0.01, -0.02, 0.03])
+    dt = np.array([0.05, 0.02, -0.01])
+    out = ctx.undistort(x, s, dR, dt)
+    ref = orc.undistort(x, s, dR, dt)
+    # libm vs CUDA sin(): identical after float32 rounding except for rare 1-ulp cases
+    d = np.abs(out[:, :3] - ref[:, :3])
+    assert d.max() <= 4e-6
+    assert (d == 0).mean() > 0.99
+    assert np.array_equal(out[:, 3], ref[:, 3])
+
+
+@pytest.mark.parametrize("leaf", [0.2, 0.4])
+def test_voxel_downsample_bit_exact(ctx, orc, scene, leaf):
+    x, ring, _ = scene["vlp"]
+    out = ctx.voxel_downsample(x, leaf)
+    ref = orc.voxel_downsample(x, leaf)
+    assert out.shape == ref.shape and np.array_equal(out, ref)
+
+
+def test_voxel_small_and_empty(ctx, orc):
+    assert ctx.voxel_downsample(np.zeros((0, 4), np.float32), 0.2).shape[0] == 0
+    x = np.array([[0.1, 0.1, 0.1, 1], [0.15, 0.1, 0.1, 3], [5, 5, 5, 7], [-3.3, 2.2, 0.05, 9]], np.float32)
+    assert np.array_equal(ctx.voxel_downsample(x, 0.4), orc.voxel_downsample(x, 0.4))
+
+
+def _assoc_inputs(orc, scene):
+    x, ring, _ = scene["vlp"]
+    label = orc.extract_scan(x, ring, 16)
+    corner = orc.voxel_downsample(x[label == 1], 0.4)
+    surf = orc.voxel_downsample(x[label == 2], 0.2)
+    return corner, surf
+
+
+def _cmp_features(f, ref, kind):
+    assert np.array_equal(f[:, 10], ref[:, 10]), "accepted-feature sets differ"
+    ok = ref[:, 10] >= 0
+    assert np.array_equal(f[ok, :3], ref[ok, :3])
+    if kind == 0:
+        # end points are float32-rounded; eigenvector sign is arbitrary -> compare as unordered pair
+        a, b, ra, rb = f[ok, 3:6], f[ok, 6:9], ref[ok, 3:6], ref[ok, 6:9]
+        same = np.abs(a - ra).max(axis=1) + np.abs(b - rb).max(axis=1)
+        swap = np.abs(a - rb).max(axis=1) + np.abs(b - ra).max(axis=1)
+        assert np.minimum(same, swap).max() <= 2e-6
+    else:
+        assert np.abs(f[ok, 3:6] - ref[ok, 3:6]).max() <= 1e-9
+        assert np.array_equal(f[ok, 6:9], ref[ok, 6:9])
+    assert np.abs(f[ok, 9] - ref[ok, 9]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("thres", [25.0, 10.0, 1.0])
+def test_associate_local_map(ctx, mm, orc, synth, scene, thres):
+    corner, surf = _assoc_inputs(orc, scene)
+    ctx.map_set(mm.MAP_CORNER_GLOBAL, np.zeros((0, 4), np.float32))
+    ctx.map_set(mm.MAP_SURF_GLOBAL, np.zeros((0, 4), np.float32))
+    ctx.map_set(mm.MAP_SURF_LOCAL, scene["map_surf"])
+    ctx.map_set(mm.MAP_CORNER_LOCAL, scene["map_corner"])
+    om = orc.Map()
+    om.set(orc.SURF_LOCAL, scene["map_surf"])
+    om.set(orc.CORNER_LOCAL, scene["map_corner"])
+    T = scene["T_true"] @ synth.s1_offset_pose()
+    fl, nl, _, _ = ctx.associate(0, corner, T, thres)
+    rl, rnl = om.associate_line(corner, T, thres)
+    assert nl == rnl and nl > 10
+    _cmp_features(fl, rl, 0)
+    fp, np_, M, nn = ctx.associate(1, surf, T, thres)
+    rp, rnp, rM, rnn = om.associate_plane(surf, T, thres)
+    assert np_ == rnp and nn == rnn and np_ > 300
+    _cmp_features(fp, rp, 1)
+    assert np.abs(M - rM).max() <= 1e-9 * max(1.0, np.abs(rM).max())
+
+
+def test_associate_global_cube_rule(ctx, mm, orc, synth, scene):
+    """Global maps: a query only sees its own 50 m cube (MM.cpp:583-605). The scene is shifted so
+    that it straddles the cube boundary at x = 25 m."""
+    corner, surf = _assoc_inputs(orc, scene)
+    shift = np.array([27.0, 0.0, 0.0])
+    ms = scene["map_surf"].copy(); ms[:, :3] += shift.astype(np.float32)
+    mc = scene["map_corner"].copy(); mc[:, :3] += shift.astype(np.float32)
+    ctx.map_set(mm.MAP_SURF_GLOBAL, ms); ctx.map_set(mm.MAP_CORNER_GLOBAL, mc)
+    ctx.map_set(mm.MAP_SURF_LOCAL, np.zeros((0, 4), np.float32)); ctx.map_set(mm.MAP_CORNER_LOCAL, np.zeros((0, 4), np.float32))
+    om = orc.Map()
+    om.set(orc.SURF_GLOBAL, ms); om.set(orc.CORNER_GLOBAL, mc)
+    T = scene["T_true"] @ synth.s1_offset_pose()
+    T = T.copy(); T[:3, 3] += shift
+    for kind, q in ((0, corner), (1, surf)):
+        f, n, _, _ = ctx.associate(kind, q, T, 25.0)
+        r, rn = (om.associate_line(q, T, 25.0) if kind == 0 else om.associate_plane(q, T, 25.0)[:2])
+        assert n == rn and n > 5
+        _cmp_features(f, r, kind)
+
+
+def test_accumulate_matches_oracle(ctx, mm, orc, synth, scene):
+    corner, surf = _assoc_inputs(orc, scene)
+    om = orc.Map()
+    om.set(orc.SURF_LOCAL, scene["map_surf"]); om.set(orc.CORNER_LOCAL, scene["map_corner"])
+    T = scene["T_true"] @ synth.s1_offset_pose()
+    lf, _ = om.associate_line(corner, T, 25.0)
+    pf, _, _, _ = om.associate_plane(surf, T, 25.0)
+    x6 = np.concatenate([T[:3, 3], synth.R_to_rotvec(T[:3, :3])])
+    Tbl = np.eye(4)
+    for wt, ha in ((0.0, 0.1 / 1.5e-3), (0.0003, 0.0), (0.0, 0.0)):
+        H, g, c = ctx.accumulate(lf, pf, x6, Tbl, wt, ha)
+        Ho, go, co = orc.accumulate(lf, pf, x6, Tbl, wt, ha)
+        assert abs(c - co) <= 1e-9 * abs(co)
+        assert np.abs(H - Ho).max() <= 1e-9 * np.abs(Ho).max()
+        assert np.abs(g - go).max() <= 1e-9 * np.abs(go).max()
+
+
+def test_frame_path_matches_oracle(ctx, mm, orc, synth, scene):
+    """Device-resident path: compact features written by the association kernel, read by the
+    accumulation kernel."""
+    corner, surf = _assoc_inputs(orc, scene)
+    ctx.map_set(mm.MAP_CORNER_GLOBAL, np.zeros((0, 4), np.float32)); ctx.map_set(mm.MAP_SURF_GLOBAL, np.zeros((0, 4), np.float32))
+    ctx.map_set(mm.MAP_SURF_LOCAL, scene["map_surf"]); ctx.map_set(mm.MAP_CORNER_LOCAL, scene["map_corner"])
+    T = scene["T_true"] @ synth.s1_offset_pose()
+    ctx.frame_set(corner, surf)
+    nl, np_, M, nn = ctx.frame_associate(T, 10.0)
+    lf, pf = ctx.frame_get_features(0), ctx.frame_get_features(1)
+    x6 = np.concatenate([T[:3, 3], synth.R_to_rotvec(T[:3, :3])])
+    H, g, c = ctx.frame_accumulate(x6, np.eye(4))
+    Ho, go, co = orc.accumulate(lf, pf, x6, np.eye(4))
+    assert abs(c - co) <= 1e-9 * abs(co)
+    assert np.abs(H - Ho).max() <= 1e-9 * np.abs(Ho).max()
+    assert np.abs(g - go).max() <= 1e-9 * np.abs(go).max()
+
+
+def _pose_err(P, q, Po, qo):
+    dq = min(np.abs(q - qo).max(), np.abs(q + qo).max())
+    return float(np.abs(P - Po).max()), float(2 * dq)
+
+
+def test_estimate_pose_matches_oracle(ctx, mm, orc, synth, scene):
+    corner, surf = _assoc_inputs(orc, scene)
+    ctx.map_set(mm.MAP_CORNER_GLOBAL, np.zeros((0, 4), np.float32)); ctx.map_set(mm.MAP_SURF_GLOBAL, np.zeros((0, 4), np.float32))
+    ctx.map_set(mm.MAP_SURF_LOCAL, scene["map_surf"]); ctx.map_set(mm.MAP_CORNER_LOCAL, scene["map_corner"])
+    om = orc.Map()
+    om.set(orc.SURF_LOCAL, scene["map_surf"]); om.set(orc.CORNER_LOCAL, scene["map_corner"])
+    T = scene["T_true"] @ synth.s1_offset_pose()
+    q0, _ = orc.so3_exp(synth.R_to_rotvec(T[:3, :3]))
+    P, q, st = ctx.estimate(corner, surf, np.eye(4), T[:3, 3], q0)
+    Po, qo, so = om.estimate(corner, surf, np.eye(4), T[:3, 3], q0)
+    dP, dq = _pose_err(P, q, Po, qo)
+    assert dP <= POSE_TOL_M and dq <= POSE_TOL_RAD, (dP, dq, st[:7], so[:7])
+    assert st[0] == so[0] and st[2] == so[2] and st[3] == so[3]
+    # and the solve actually moved towards the truth
+    assert np.abs(P - scene["T_true"][:3, 3]).max() < 0.01
+
+
+def test_scan_to_pose_matches_oracle(ctx, mm, orc, synth, scene):
+    vx, vr, vs = scene["vlp"]
+    hx, hl, hs = scene["hori"]
+    x = np.concatenate([vx, hx]); line = np.concatenate([vr, hl + 16]).astype(np.uint16); s = np.concatenate([vs, hs])
+    ctx.map_set(mm.MAP_CORNER_GLOBAL, np.zeros((0, 4), np.float32)); ctx.map_set(mm.MAP_SURF_GLOBAL, np.zeros((0, 4), np.float32))
+    ctx.map_set(mm.MAP_SURF_LOCAL, scene["map_surf"]); ctx.map_set(mm.MAP_CORNER_LOCAL, scene["map_corner"])
+    T = scene["T_true"] @ synth.s1_offset_pose()
+    q0, _ = orc.so3_exp(synth.R_to_rotvec(T[:3, :3]))
+    dR, dt = np.eye(3), np.zeros(3)
+    P, q, st, cnt = ctx.scan_to_pose(x, line, s, 22, dR, dt, np.eye(4), T[:3, 3], q0)
+    label = orc.extract_scan(x, line, 22)
+    xu = orc.undistort(x, s, dR, dt)
+    corner = orc.voxel_downsample(xu[label == 1], 0.4); surf = orc.voxel_downsample(xu[label == 2], 0.2)
+    assert cnt[0] == (label == 1).sum() and cnt[1] == (label == 2).sum()
+    assert cnt[2] == corner.shape[0] and cnt[3] == surf.shape[0]
+    om = orc.Map()
+    om.set(orc.SURF_LOCAL, scene["map_surf"]); om.set(orc.CORNER_LOCAL, scene["map_corner"])
+    Po, qo, so = om.estimate(corner, surf, np.eye(4), T[:3, 3], q0)
+    dP, dq = _pose_err(P, q, Po, qo)
+    assert dP <= POSE_TOL_M and dq <= POSE_TOL_RAD, (dP, dq, st[:7], so[:7])

@@ -26,7 +26,11 @@ struct DevBuf {
     cap = 0;
     size_t want = bytes + bytes / 4 + 256;
     cudaError_t e = cudaMalloc(&p, want);
-    if (e == cudaSuccess) cap = want;
+    if (e != cudaSuccess) return e;
+    cap = want;
+    // fresh scratch is zero-filled (tickets and counters rely on it); growth is rare
+    e = cudaMemset(p, 0, want);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     return e;
   }
   void release() {

@@ -1,0 +1,454 @@
+#!/usr/bin/env python
+"""bench.py — mm-loam scan-matching hot path on B200: LiDAR scans/s through the odometry loop.
+
+Metric (BASELINE.json): "LiDAR scans/s through odometry loop (merged VLP16+Livox) at 1 GPU; pose RMSE".
+A step = one merged VLP-16 + Livox-Horizon scan through the whole hot path:
+  extract (A1) -> undistort (A4) -> label split + voxel filter (A6) -> Estimate (A7-A12)
+against a resident feature map (SURVEY.md §8 d, config S3). Scans come from a seeded synthetic
+constant-twist trajectory with motion distortion; every step is a different scan.
+
+Arms:
+  default            this repo's CUDA path (libmmloam_b200.so through the C-ABI)
+  --impl reference   the reference's CPU algorithm on the host cores. The reference binary
+                     (ROS + PCL + Eigen + Ceres) cannot be built in this image, so this arm runs
+                     the oracle port (oracle/, "kind": "port") with all host threads.
+Multi-GPU (torchrun, one rank per GPU): every rank runs its own independent scan stream
+(replicas, no data-path collective) -> "scaling": "weak"; value = all ranks' scans / max time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+LEAF_CORNER, LEAF_SURF = 0.4, 0.2  # launch/mm_lio_full.launch:43-44
+N_LINES = 22                       # 16 VLP-16 rings + 6 Horizon lines
+BYTES_PER_POINT_EXTRACT = 19       # SURVEY §8 d: 16 B xyzi + 2 B line + 1 B label
+BYTES_PER_QUERY_ASSOC = 96         # 16 B query + 5 x 16 B neighbours
+BYTES_PER_FEATURE_EVAL = 64        # 16 B query + 48 B feature record
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--livox-pts", type=int, default=24000)
+    ap.add_argument("--map-surf", type=int, default=100_000)
+    ap.add_argument("--map-corner", type=int, default=5_000)
+    ap.add_argument("--cpu-scans", type=int, default=12, help="bounded CPU-baseline sample (scans)")
+    ap.add_argument("--s4-queries", type=int, default=240_000)
+    ap.add_argument("--s4-map", type=int, default=1_000_000)
+    ap.add_argument("--no-s4", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+def make_workload(synth, n_frames, livox_pts, seed0):
+    """Merged scans along the S3 trajectory. Frame k sweeps from pose k to pose k+1."""
+    Ts = synth.trajectory(n_frames, v=0.5, yaw_rate=0.2, dt=0.1)
+    scans = []
+    for k in range(n_frames):
+        T0, T1 = Ts[k], Ts[k + 1]
+        vx, vr, vs = synth.vlp16_scan(T1, seed=seed0 + 2 * k, T_ws_start=T0)
+        hx, hl, hs = synth.horizon_scan(T1, livox_pts, seed=seed0 + 2 * k + 1, T_ws_start=T0)
+        x = np.ascontiguousarray(np.concatenate([vx, hx]))
+        line = np.ascontiguousarray(np.concatenate([vr, hl + 16]).astype(np.uint16))
+        s = np.ascontiguousarray(np.concatenate([vs, hs]).astype(np.float32))
+        scans.append((x, line, s))
+    return Ts, scans
+
+
+def pose_to_Pq(orc, synth, T):
+    q, _ = orc.so3_exp(synth.R_to_rotvec(T[:3, :3]))
+    return T[:3, 3].copy(), q
+
+
+def Pq_to_T(orc, synth, P, q):
+    _, R = orc.so3_exp(orc.so3_log(q))
+    return synth.make_T(R, P)
+
+
+class Odometry:
+    """Host-side loop state: constant-velocity prediction from the last two estimates (the
+    reference predicts from the previous inter-frame delta, unionPoseEstimation.cpp:847-852, 882-890)."""
+
+    def __init__(self, T_init, T_prev):
+        self.T_last = T_init.copy()
+        self.delta = np.linalg.inv(T_prev) @ T_init
+
+    def predict(self):
+        return self.T_last @ self.delta, self.delta
+
+    def update(self, T_new):
+        self.delta = np.linalg.inv(self.T_last) @ T_new
+        self.T_last = T_new
+
+
+def quat_to_R(q):
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def R_to_quat(R):
+    t = np.trace(R)
+    if t > 0:
+        s = np.sqrt(t + 1.0) * 2
+        q = np.array([0.25 * s, (R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s])
+    else:
+        i = int(np.argmax(np.diag(R)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0) * 2
+        v = np.zeros(3)
+        v[i] = 0.25 * s
+        v[j] = (R[j, i] + R[i, j]) / s
+        v[k] = (R[k, i] + R[i, k]) / s
+        q = np.array([(R[k, j] - R[j, k]) / s, v[0], v[1], v[2]])
+    return q / np.linalg.norm(q)
+
+
+def T_from(P, q):
+    T = np.eye(4)
+    T[:3, :3] = quat_to_R(q)
+    T[:3, 3] = P
+    return T
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [t.strip() for t in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_loop(orc, synth, scans, Ts, first, n, ms, mc, threads):
+    """The oracle through the same loop (extract -> undistort -> voxel -> estimate)."""
+    omap = orc.Map()
+    omap.set(orc.SURF_LOCAL, ms)
+    omap.set(orc.CORNER_LOCAL, mc)
+    prm = orc.est_params(threads=threads)
+    odo = Odometry(Ts[first], Ts[first - 1] if first > 0 else Ts[first])
+    poses = []
+    t0 = time.perf_counter()
+    for k in range(first, first + n):
+        x, line, s = scans[k]
+        Tp, delta = odo.predict()
+        label = orc.extract_scan(x, line, N_LINES, threads=threads)
+        xu = orc.undistort(x, s, delta[:3, :3], delta[:3, 3])
+        corner = orc.voxel_downsample(xu[label == 1], LEAF_CORNER)
+        surf = orc.voxel_downsample(xu[label == 2], LEAF_SURF)
+        P, q, st = omap.estimate(corner, surf, np.eye(4), Tp[:3, 3], R_to_quat(Tp[:3, :3]), prm)
+        T = T_from(P, q)
+        odo.update(T)
+        poses.append(T)
+    dt = time.perf_counter() - t0
+    return n / dt, poses
+
+
+def pose_rmse(poses, Ts, first):
+    e = [np.linalg.norm(p[:3, 3] - Ts[first + 1 + i][:3, 3]) for i, p in enumerate(poses)]
+    return float(np.sqrt(np.mean(np.square(e)))) if e else None
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    synth = ge.load_synth()
+    n_threads = len(os.sched_getaffinity(0))
+    workload = (f"S3-merged odometry loop: VLP-16 28800 + Horizon {a.livox_pts} pts/scan with motion distortion, "
+                f"extract -> undistort -> voxel {LEAF_CORNER}/{LEAF_SURF} -> Estimate window 1 "
+                f"(<=5 outer x <=10 dogleg) vs {a.map_surf}+{a.map_corner}-pt local feature map")
+    config = {"workload": workload, "points_per_scan": 28800 + a.livox_pts, "window": 1,
+              "l2": "flushed between timed steps (256 MiB memset)", "seed": 1003}
+
+    if a.impl == "reference":
+        # the oracle port timed on the host cores; rank 0 only
+        if rank != 0:
+            return 0
+        orc = ge.load_oracle()
+        orc.build()
+        n_total = a.warmup + a.steps
+        Ts, scans = make_workload(synth, n_total, a.livox_pts, 1003)
+        ms, mc = synth.feature_map(a.map_surf, a.map_corner, seed=1002)
+        cpu_loop(orc, synth, scans, Ts, 0, min(a.warmup, 2), ms, mc, n_threads)
+        v, poses = cpu_loop(orc, synth, scans, Ts, a.warmup, a.steps, ms, mc, n_threads)
+        line = {"impl": "reference", "metric": "LiDAR scans/s through odometry loop (merged VLP16+Livox)",
+                "value": v, "unit": "scans/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32/f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "scans/s", "cores": n_threads, "kind": "port",
+                                 "sample": f"{a.steps} scans of the same workload, oracle port (reference unbuildable here)"},
+                "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "pose_rmse_m": pose_rmse(poses, Ts, a.warmup), "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    mm = ge.load_package()
+    ctx = mm.Context(local_rank)
+
+    n_total = a.warmup + a.steps
+    Ts, scans = make_workload(synth, n_total, a.livox_pts, 1003 + 1000 * rank)
+    ms, mc = synth.feature_map(a.map_surf, a.map_corner, seed=1002)
+    ctx.map_set(mm.MAP_SURF_LOCAL, ms)
+    ctx.map_set(mm.MAP_CORNER_LOCAL, mc)
+    ex = np.eye(4)
+
+    # ---- device-resident scans for `value`
+    dev = [(ctx.dev_upload(x), ctx.dev_upload(l), ctx.dev_upload(s), x.shape[0]) for (x, l, s) in scans]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+
+    def run_dev(first, n, timed):
+        odo = Odometry(Ts[first], Ts[first - 1] if first > 0 else Ts[first])
+        total_ms, poses = 0.0, []
+        for k in range(first, first + n):
+            Tp, delta = odo.predict()
+            if timed:
+                flush.zero_()
+                torch.cuda.synchronize()
+                ctx.timer_start()
+            xd, ld, sd, npts = dev[k]
+            P, q, st, cnt = ctx.scan_to_pose_dev(xd, ld, sd, npts, N_LINES, delta[:3, :3], delta[:3, 3], ex, Tp[:3, 3],
+                                                 R_to_quat(Tp[:3, :3]), LEAF_CORNER, LEAF_SURF)
+            if timed:
+                total_ms += ctx.timer_stop_ms()
+            T = T_from(P, q)
+            odo.update(T)
+            poses.append(T)
+        return total_ms, poses
+
+    run_dev(0, a.warmup, False)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launches
+    t_ms, poses = run_dev(a.warmup, a.steps, True)
+    launches = ctx.launches - l0
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    t_all = torch.tensor([t_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    t_max_ms = float(t_all.item())
+    value = world * a.steps / (t_max_ms / 1000.0)
+
+    # ---- e2e: host (pinned) buffers in, pose out, wall clock
+    pinned = []
+    for (x, l, s) in scans:
+        tx = torch.from_numpy(x).pin_memory()
+        tl = torch.from_numpy(l.view(np.int16)).pin_memory()
+        ts = torch.from_numpy(s).pin_memory()
+        pinned.append((tx, tl, ts))
+
+    def run_e2e(first, n):
+        odo = Odometry(Ts[first], Ts[first - 1] if first > 0 else Ts[first])
+        t0 = time.perf_counter()
+        for k in range(first, first + n):
+            tx, tl, ts = pinned[k]
+            Tp, delta = odo.predict()
+            P, q, st, cnt = ctx.scan_to_pose(tx.numpy(), tl.numpy().view(np.uint16), ts.numpy(), N_LINES, delta[:3, :3],
+                                             delta[:3, 3], ex, Tp[:3, 3], R_to_quat(Tp[:3, :3]), LEAF_CORNER, LEAF_SURF)
+            odo.update(T_from(P, q))
+        return time.perf_counter() - t0
+
+    run_e2e(0, a.warmup)
+    if world > 1:
+        dist.barrier()
+    e2e_s = run_e2e(a.warmup, a.steps)
+    e_all = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(e_all, op=dist.ReduceOp.MAX)
+    e2e_value = world * a.steps / float(e_all.item())
+    npts = scans[0][0].shape[0]
+    h2d = npts * (16 + 2 + 4)
+    d2h = 7 * 8 + 16 * 8 + 4 * 4 + 8  # pose + stats + counts + extractor counters
+
+    if rank != 0:
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- stage shares of the step (CUDA events on the launching stream, separate pass)
+    ctx.profile_enable(True)
+    run_dev(a.warmup, min(a.steps, 20), False)
+    stage_ms, n_prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    stage_ms = (stage_ms / max(n_prof, 1)).tolist()
+
+    # ---- roofline of the dominant kernels, timed alone on the context's stream
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    roof = {}
+
+    def time_kernels(fn, reps):
+        fn(3)
+        ctx.sync()
+        ctx.timer_start()
+        fn(reps)
+        return ctx.timer_stop_ms() / reps
+
+    # S3 sizes: the frame left in the context by the last scan
+    x, line, s = scans[a.warmup]
+    orc = ge.load_oracle()
+    lab, _, _ = ctx.extract_features(x, line, N_LINES)
+    corner = ctx.voxel_downsample(x[lab == 1], LEAF_CORNER)
+    surf = ctx.voxel_downsample(x[lab == 2], LEAF_SURF)
+    T1 = Ts[a.warmup + 1]
+    x6 = np.concatenate([T1[:3, 3], synth.R_to_rotvec(T1[:3, :3])])
+    ctx.frame_set(corner, surf)
+    ms_assoc = time_kernels(lambda r: ctx.frame_associate_async(T1, 1.0, r), 50)
+    ms_acc = time_kernels(lambda r: ctx.frame_accumulate_async(x6, np.eye(4), repeat=r), 200)
+    nq = corner.shape[0] + surf.shape[0]
+    roof["s3_associate"] = {"queries": nq, "ms": ms_assoc, "gbs": nq * BYTES_PER_QUERY_ASSOC / ms_assoc / 1e6,
+                            "note": "latency-bound at one-scan size"}
+    roof["s3_accumulate"] = {"features": nq, "ms": ms_acc, "gbs": nq * BYTES_PER_FEATURE_EVAL / ms_acc / 1e6,
+                             "note": "latency-bound at one-scan size"}
+
+    s4 = None
+    if not a.no_s4:
+        # S4: 1M-pt map, Q queries perturbed by the S1 offset (SURVEY §8 d)
+        hs, hc = synth.feature_map(a.s4_map, a.s4_map // 20, seed=1004, box=synth.HALL, pillars=[])
+        ctx4 = mm.Context(local_rank)
+        ctx4.map_set(mm.MAP_SURF_LOCAL, hs)
+        ctx4.map_set(mm.MAP_CORNER_LOCAL, hc)
+        Tq = synth.s1_offset_pose()
+        qs = synth.queries_from_map(hs, a.s4_queries, np.eye(4), seed=1004)
+        qc = synth.queries_from_map(hc, max(a.s4_queries // 20, 64), np.eye(4), seed=1005)
+        ctx4.frame_set(qc, qs)
+        x6q = np.concatenate([Tq[:3, 3], synth.R_to_rotvec(Tq[:3, :3])])
+        nl, npl, _, _ = ctx4.frame_associate(Tq, 1.0)
+        ctx4.frame_associate_async(Tq, 1.0, 2)
+        ctx4.sync()
+        ctx4.timer_start()
+        ctx4.frame_associate_async(Tq, 1.0, 10)
+        ms_assoc4 = ctx4.timer_stop_ms() / 10
+        ctx4.frame_accumulate_async(x6q, np.eye(4), repeat=3)
+        ctx4.sync()
+        ctx4.timer_start()
+        ctx4.frame_accumulate_async(x6q, np.eye(4), repeat=20)
+        ms_acc4 = ctx4.timer_stop_ms() / 20
+        nq4 = qs.shape[0] + qc.shape[0]
+        s4 = {"map_points": int(hs.shape[0] + hc.shape[0]), "queries": int(nq4), "features": int(nl + npl),
+              "associate_ms": ms_assoc4, "associate_gbs": nq4 * BYTES_PER_QUERY_ASSOC / ms_assoc4 / 1e6,
+              "accumulate_ms": ms_acc4, "accumulate_gbs": nq4 * BYTES_PER_FEATURE_EVAL / ms_acc4 / 1e6,
+              "map_cell_m": ctx4.map_info(mm.MAP_SURF_LOCAL)["cell"]}
+        s4["associate_frac"] = s4["associate_gbs"] / peak
+        s4["accumulate_frac"] = s4["accumulate_gbs"] / peak
+        ctx4.close()
+
+    # the kernel that dominates the step: the estimate stage = associate + accumulate launches
+    dom_ms = ms_acc
+    achieved = nq * BYTES_PER_FEATURE_EVAL / dom_ms / 1e6
+    roofline = {"bound": "hbm", "kernel": "k_accumulate (residual+Jacobian+J^T J, one launch per dogleg iteration)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": nq * BYTES_PER_FEATURE_EVAL,
+                "launch_ms": dom_ms, "note": "one-scan working set (~0.1 MB): launch-latency-bound; see s4 for the HBM-sized sweep",
+                "stage_ms_per_scan": {"extract": stage_ms[0], "undistort_split_voxel": stage_ms[1], "estimate": stage_ms[2]},
+                "detail": roof, "s4": s4}
+
+    # ---- CPU baseline on a bounded sample of the same workload (rank 0, host cores)
+    orc.build()
+    n_cpu = min(a.cpu_scans, a.steps)
+    cpu_threads = min(6, n_threads)  # reference threading: 6 extraction / solver threads (FE.cpp:1008, EST.cpp:1430)
+    cpu_v, cpu_poses = cpu_loop(orc, synth, scans, Ts, a.warmup, n_cpu, ms, mc, cpu_threads)
+    # parity of the loop: GPU vs oracle poses on the sampled scans
+    dpos = max(float(np.abs(g[:3, 3] - c[:3, 3]).max()) for g, c in zip(poses[:n_cpu], cpu_poses))
+    drot = max(float(np.linalg.norm(synth.R_to_rotvec(g[:3, :3].T @ c[:3, :3]))) for g, c in zip(poses[:n_cpu], cpu_poses))
+
+    line = {"metric": "LiDAR scans/s through odometry loop (merged VLP16+Livox)", "value": value, "unit": "scans/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": t_max_ms / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+            "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": {"value": cpu_v, "unit": "scans/s", "cores": cpu_threads, "kind": "port",
+                             "sample": f"{n_cpu} scans of the same workload (oracle port, reference threading)"},
+            "pose_rmse_m": pose_rmse(poses, Ts, a.warmup),
+            "parity_vs_oracle": {"max_dpos_m": dpos, "max_drot_rad": drot, "scans": n_cpu}}
+    print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -149,6 +149,10 @@ int mml_frame_get_features(mml_ctx* ctx, int kind, double* out_feat);
 int mml_dev_alloc(mml_ctx* ctx, size_t bytes, void** out);
 int mml_dev_free(mml_ctx* ctx, void* p);
 int mml_dev_upload(mml_ctx* ctx, void* dst_dev, const void* src, size_t bytes);
+/* Per-stage CUDA-event timing of mml_scan_to_pose[_dev], summed over calls:
+ * stage_ms3 = [extract, undistort + split + voxel, estimate].                          */
+int mml_profile_enable(mml_ctx* ctx, int on);
+int mml_profile_read(mml_ctx* ctx, double* stage_ms3, long long* n_scans);
 /* asynchronous variants for timing: enqueue `repeat` launches, no host read-back.      */
 int mml_frame_associate_async(mml_ctx* ctx, const double* T_wl16, double thres_dist, int repeat);
 int mml_frame_accumulate_async(mml_ctx* ctx, const double* x6, const double* T_bl16, double plan_weight_tan,

@@ -258,6 +258,16 @@ class Context:
         self._ck(self.lib.mml_frame_accumulate_async(self.h, _p(x6), _p(T), C.c_double(plan_weight_tan),
                                                      C.c_double(huber_a), int(repeat)))
 
+    def profile_enable(self, on=True):
+        self._ck(self.lib.mml_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        """(ms per stage [extract, undistort+split+voxel, estimate] summed over scans, n_scans)"""
+        ms = np.zeros(3)
+        n = C.c_longlong(0)
+        self._ck(self.lib.mml_profile_read(self.h, _p(ms), C.byref(n)))
+        return ms, n.value
+
     def timer_start(self):
         self._ck(self.lib.mml_timer_start(self.h))
 

@@ -524,6 +524,7 @@ static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, floa
     while (!layout(cell)) cell *= 1.5f;
     MML_CUDA(ctx, ctx->tmp_e.reserve(sizeof(int) * ((size_t)M.ncell + 1) + 64));
     MML_CHECK(count_pass(ctx->tmp_e.as<int>()));
+    MML_CUDA(ctx, ctx->counters.reserve(256));
     unsigned long long* nz_d = reinterpret_cast<unsigned long long*>(ctx->counters.p);
     MML_CUDA(ctx, cudaMemsetAsync(nz_d, 0, 8, st));
     k_count_nonzero<<<4 * kNumSMs, 256, 0, st>>>(ctx->tmp_e.as<int>(), M.ncell, nz_d);

@@ -404,11 +404,13 @@ int mml_scan_to_pose_dev(mml_ctx* c, const void* xyzi_dev, const void* line_id_d
   MML_CUDA(c, c->in_label.reserve((size_t)n + 16));
   MML_CUDA(c, c->tmp_e.reserve(sizeof(float4) * (size_t)(n > 0 ? n : 1)));
   const int off[2] = {0, n};
+  if (c->profile) MML_CUDA(c, cudaEventRecord(c->pev[0], st));
   MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, c->in_label.as<uint8_t>()));
   // undistort a copy of the scan (the caller's buffer stays untouched)
   mml::DevBuf& wbuf = c->srt_xyzi;  // the line-sorted copy is dead after extraction: reuse its storage
   MML_CUDA(c, wbuf.reserve(sizeof(float4) * (size_t)(n > 0 ? n : 1)));
   float4* work = wbuf.as<float4>();
+  if (c->profile) MML_CUDA(c, cudaEventRecord(c->pev[1], st));
   if (n) MML_CUDA(c, cudaMemcpyAsync(work, xyzi_dev, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, st));
   if (dR9 && dt3 && s_dev) MML_CHECK(mml_undistort_device(c, work, (const float*)s_dev, n, dR9, dt3));
   // label split (EST.cpp:992-1011); capacities from the counts of the extractor
@@ -426,7 +428,18 @@ int mml_scan_to_pose_dev(mml_ctx* c, const void* xyzi_dev, const void* line_id_d
   MML_CHECK(mml_label_split_device(c, work, c->in_label.as<uint8_t>(), n, c->corner_raw.as<float4>(), c->surf_raw.as<float4>(), cnt + 2));
   MML_CHECK(mml_voxel_device(c, c->corner_raw.as<float4>(), cnt + 2, n_sharp, leaf_corner, c->q_corner.as<float4>(), cnt));
   MML_CHECK(mml_voxel_device(c, c->surf_raw.as<float4>(), cnt + 3, n_flat, leaf_surf, c->q_surf.as<float4>(), cnt + 1));
+  if (c->profile) MML_CUDA(c, cudaEventRecord(c->pev[2], st));
   MML_CHECK(mml_estimate_device(c, cnt, cap_c, cap_s, exTlb16, P3, q_wxyz4, prm, stats));
+  if (c->profile) {
+    MML_CUDA(c, cudaEventRecord(c->pev[3], st));
+    MML_CUDA(c, cudaEventSynchronize(c->pev[3]));
+    for (int k = 0; k < 3; k++) {
+      float ms = 0.f;
+      MML_CUDA(c, cudaEventElapsedTime(&ms, c->pev[k], c->pev[k + 1]));
+      c->stage_ms[k] += ms;
+    }
+    c->stage_n++;
+  }
   if (out_counts) {
     int hv[2];
     MML_CHECK(download(c, hv, cnt, sizeof(hv)));
@@ -448,6 +461,24 @@ int mml_scan_to_pose(mml_ctx* c, const float* xyzi, const uint16_t* line_id, con
   if (s) MML_CHECK(upload(c, c->in_s, s, sizeof(float) * (size_t)n));
   return mml_scan_to_pose_dev(c, c->in_xyzi.p, c->in_line.p, s ? c->in_s.p : nullptr, n, n_lines, dR9, dt3, leaf_corner,
                               leaf_surf, exTlb16, P3, q_wxyz4, prm, stats, out_counts);
+}
+
+// per-stage CUDA-event timing of mml_scan_to_pose[_dev]: [extract, undistort+split+voxel, estimate] in ms
+int mml_profile_enable(mml_ctx* c, int on) {
+  if (!c) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  if (on && !c->pev[0])
+    for (int k = 0; k < 4; k++) MML_CUDA(c, cudaEventCreate(&c->pev[k]));
+  c->profile = on != 0;
+  for (int k = 0; k < 4; k++) c->stage_ms[k] = 0.0;
+  c->stage_n = 0;
+  return MML_OK;
+}
+int mml_profile_read(mml_ctx* c, double* stage_ms3, long long* n_scans) {
+  if (!c || !stage_ms3) return MML_ERR_INVALID;
+  for (int k = 0; k < 3; k++) stage_ms3[k] = c->stage_ms[k];
+  if (n_scans) *n_scans = c->stage_n;
+  return MML_OK;
 }
 
 // device allocation helpers for callers that keep scans resident (bench.py)

@@ -115,6 +115,10 @@ struct mml_ctx {
   cudaGraphExec_t est_graph = nullptr;
   long long est_graph_key = 0;
   long long est_launches_per_graph = 0;
+  bool profile = false;
+  cudaEvent_t pev[4] = {nullptr, nullptr, nullptr, nullptr};
+  double stage_ms[4] = {0, 0, 0, 0};
+  long long stage_n = 0;
   mml::DevBuf frame_cnt;          // int[2] device-side query counts
   mml::DevBuf export_buf;
 };

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <memory>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 using namespace orc;
@@ -264,11 +265,10 @@ inline void write_feat(double* f, const P4& ori, const double* a, const double* 
 
 extern "C" {
 
-int orc_associate_line(const orc_map* m, const float* q_xyzi, int nq, const double* T,
-                       double thres_dist, double* feat, int* n_feat) {
-  const P4* q = reinterpret_cast<const P4*>(q_xyzi);
+static int assoc_line_range(const orc_map* m, const P4* q, int i0, int i1, const double* T, double thres_dist,
+                            double* feat) {
   int nf = 0;
-  for (int i = 0; i < nq; i++) {
+  for (int i = i0; i < i1; i++) {
     double* f = feat + 12 * i;
     for (int k = 0; k < 12; k++) f[k] = 0;
     f[10] = -1.0;
@@ -301,16 +301,41 @@ int orc_associate_line(const orc_map* m, const float* q_xyzi, int nq, const doub
       }
     }
   }
+  return nf;
+}
+
+// threads > 1: queries are split into contiguous ranges (the reference runs line and plane
+// association on two threads, EST.cpp:1271-1297; the "all cores" baseline splits the queries)
+int orc_associate_line_mt(const orc_map* m, const float* q_xyzi, int nq, const double* T, double thres_dist,
+                          double* feat, int* n_feat, int threads) {
+  const P4* q = reinterpret_cast<const P4*>(q_xyzi);
+  if (threads <= 1 || nq < 64) {
+    *n_feat = assoc_line_range(m, q, 0, nq, T, thres_dist, feat);
+    return 0;
+  }
+  std::vector<int> part(threads, 0);
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; t++)
+    th.emplace_back([&, t]() {
+      part[t] = assoc_line_range(m, q, (int)((long)nq * t / threads), (int)((long)nq * (t + 1) / threads), T, thres_dist, feat);
+    });
+  for (auto& t : th) t.join();
+  int nf = 0;
+  for (int v : part) nf += v;
   *n_feat = nf;
   return 0;
 }
 
-int orc_associate_plane(const orc_map* m, const float* q_xyzi, int nq, const double* T,
-                        double thres_dist, double* feat, int* n_feat, double* M9, int* n_normals) {
-  const P4* q = reinterpret_cast<const P4*>(q_xyzi);
+int orc_associate_line(const orc_map* m, const float* q_xyzi, int nq, const double* T,
+                       double thres_dist, double* feat, int* n_feat) {
+  return orc_associate_line_mt(m, q_xyzi, nq, T, thres_dist, feat, n_feat, 1);
+}
+
+static int assoc_plane_range(const orc_map* m, const P4* q, int i0, int i1, const double* T, double thres_dist,
+                             double* feat, double* M) {
   int nf = 0;
-  double M[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  for (int i = 0; i < nq; i++) {
+  for (int k = 0; k < 9; k++) M[k] = 0;
+  for (int i = i0; i < i1; i++) {
     double* f = feat + 12 * i;
     for (int k = 0; k < 12; k++) f[k] = 0;
     f[10] = -1.0;
@@ -343,10 +368,40 @@ int orc_associate_plane(const orc_map* m, const float* q_xyzi, int nq, const dou
       for (int c = 0; c < 3; c++) M[3 * r + c] += nrm[r] * nrm[c];
     nf++;
   }
+  return nf;
+}
+
+int orc_associate_plane_mt(const orc_map* m, const float* q_xyzi, int nq, const double* T, double thres_dist,
+                           double* feat, int* n_feat, double* M9, int* n_normals, int threads) {
+  const P4* q = reinterpret_cast<const P4*>(q_xyzi);
+  double M[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int nf = 0;
+  if (threads <= 1 || nq < 64) {
+    nf = assoc_plane_range(m, q, 0, nq, T, thres_dist, feat, M);
+  } else {
+    std::vector<int> part(threads, 0);
+    std::vector<double> Mp(9 * (size_t)threads, 0.0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++)
+      th.emplace_back([&, t]() {
+        part[t] = assoc_plane_range(m, q, (int)((long)nq * t / threads), (int)((long)nq * (t + 1) / threads), T, thres_dist,
+                                    feat, &Mp[9 * (size_t)t]);
+      });
+    for (auto& t : th) t.join();
+    for (int t = 0; t < threads; t++) {
+      nf += part[t];
+      for (int k = 0; k < 9; k++) M[k] += Mp[9 * (size_t)t + k];
+    }
+  }
   *n_feat = nf;
   if (M9) std::memcpy(M9, M, sizeof(M));
   if (n_normals) *n_normals = nf;
   return 0;
+}
+
+int orc_associate_plane(const orc_map* m, const float* q_xyzi, int nq, const double* T,
+                        double thres_dist, double* feat, int* n_feat, double* M9, int* n_normals) {
+  return orc_associate_plane_mt(m, q_xyzi, nq, T, thres_dist, feat, n_feat, M9, n_normals, 1);
 }
 
 // EST.cpp:536-565. Singular values of the stacked normals = sqrt(eig(sum n n^T)).

@@ -199,6 +199,11 @@ DoglegSummary dogleg_minimize(int n, double* x_io, const EvalFn& eval, int max_n
 
 using namespace orc;
 
+extern "C" int orc_associate_line_mt(const orc_map* m, const float* q_xyzi, int nq, const double* T, double thres_dist,
+                                     double* feat, int* n_feat, int threads);
+extern "C" int orc_associate_plane_mt(const orc_map* m, const float* q_xyzi, int nq, const double* T, double thres_dist,
+                                      double* feat, int* n_feat, double* M9, int* n_normals, int threads);
+
 extern "C" {
 
 void orc_est_params_default(orc_est_params* p) {
@@ -250,8 +255,8 @@ int orc_estimate(const orc_map* map, const float* corner, int n_corner, const fl
     }
     T[15] = 1;
     double M9[9];
-    orc_associate_line(map, corner, n_corner, T, thres, lf.data(), &nl);
-    orc_associate_plane(map, surf, n_surf, T, thres, pf.data(), &np, M9, &n_normals);
+    orc_associate_line_mt(map, corner, n_corner, T, thres, lf.data(), &nl, prm->threads);
+    orc_associate_plane_mt(map, surf, n_surf, T, thres, pf.data(), &np, M9, &n_normals, prm->threads);
     min_sv = orc_localizability(M9, n_normals);  // EST.cpp:771-775
     if (min_sv < 3.0) is_degenerate = 1;
     thres = (it == 0) ? prm->thres1 : prm->thres2;  // EST.cpp:1377-1381

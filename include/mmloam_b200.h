@@ -166,6 +166,17 @@ int mml_frame_accumulate_partial_dev(mml_ctx* ctx, const double* x6, const doubl
                                      double huber_a, void** partial28_dev);
 void* mml_stream_handle(mml_ctx* ctx);
 
+/* ---- host-side trust-region state machine (the same code the device loop runs) for callers
+ * that reduce the normal equations themselves, e.g. after an NCCL all-reduce of per-shard
+ * partial sums (SURVEY.md §8 e). Restates ceres::Solve's DOGLEG iteration (EST.cpp:1425-1432)
+ * on [cost, g(6), upper-triangular H(21)]. Needs no GPU.                                  */
+typedef struct mml_solver mml_solver;
+int mml_solver_create(mml_solver** out);
+int mml_solver_destroy(mml_solver* s);
+int mml_solver_begin(mml_solver* s, const double* x6, int max_inner);
+int mml_solver_feed(mml_solver* s, const double* out28, double* x_next6, int* done);
+int mml_solver_result(mml_solver* s, double* x_best6, double* min_cost, int* iterations);
+
 #ifdef __cplusplus
 }
 #endif

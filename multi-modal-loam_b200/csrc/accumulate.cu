@@ -112,7 +112,7 @@ struct AccArgs {
   EstState* st;          // optional: evaluation point and parameters come from the solver state
 };
 
-__device__ void dogleg_update(EstState& S, const double* out28);
+__host__ __device__ void dogleg_update(EstState& S, const double* out28);
 
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_accumulate(AccArgs A) {
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(256) k_accumulate(AccArgs A) {
 }
 
 // ---------------------------------------------------------------- dogleg state machine
-__device__ inline void unpack28(const double* o, double* cost, double* g, double* H) {
+__host__ __device__ inline void unpack28(const double* o, double* cost, double* g, double* H) {
   *cost = o[0];
   for (int i = 0; i < 6; i++) g[i] = o[1 + i];
   int k = 7;
@@ -315,7 +315,7 @@ __device__ inline void unpack28(const double* o, double* cost, double* g, double
 }
 
 // One DoglegStrategy::ComputeStep + model evaluation. Returns false for an invalid step.
-__device__ bool dogleg_compute_step(EstState& S) {
+__host__ __device__ bool dogleg_compute_step(EstState& S) {
   const int n = 6;
   double Hs[36], gs[6];
   for (int i = 0; i < n; i++) {
@@ -397,7 +397,7 @@ __device__ bool dogleg_compute_step(EstState& S) {
   return true;
 }
 
-__device__ void dogleg_update(EstState& S, const double* out28) {
+__host__ __device__ void dogleg_update(EstState& S, const double* out28) {
   double cost, g[6], H[36];
   unpack28(out28, &cost, g, H);
   auto grad_max = [&](const double* gg) {
@@ -648,3 +648,52 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
   }
   return MML_OK;
 }
+
+// ---------------------------------------------------------------- host-side dogleg
+// The same trust-region state machine for callers that reduce the normal equations themselves
+// (multi-GPU: per-shard partial sums are all-reduced over NCCL, then every rank takes the same step).
+struct mml_solver {
+  mml::EstState S;
+};
+
+extern "C" {
+
+int mml_solver_create(mml_solver** out) {
+  if (!out) return MML_ERR_INVALID;
+  *out = new mml_solver();
+  memset(&(*out)->S, 0, sizeof(mml::EstState));
+  return MML_OK;
+}
+int mml_solver_destroy(mml_solver* s) {
+  delete s;
+  return MML_OK;
+}
+// start a solve at x6 (<= max_inner dogleg iterations); the first evaluation point is x6
+int mml_solver_begin(mml_solver* s, const double* x6, int max_inner) {
+  if (!s || !x6) return MML_ERR_INVALID;
+  memset(&s->S, 0, sizeof(mml::EstState));
+  for (int i = 0; i < 6; i++) s->S.x[i] = x6[i];
+  s->S.first = 1;
+  s->S.max_inner = max_inner;
+  return MML_OK;
+}
+// feed [cost, g(6), upper H(21)] evaluated at the current evaluation point; returns the next
+// evaluation point in x_next6, or *done = 1 when the solve has terminated
+int mml_solver_feed(mml_solver* s, const double* out28, double* x_next6, int* done) {
+  if (!s || !out28 || !done) return MML_ERR_INVALID;
+  mml::dogleg_update(s->S, out28);
+  *done = s->S.done_inner;
+  if (x_next6)
+    for (int i = 0; i < 6; i++) x_next6[i] = s->S.x_cand[i];
+  return MML_OK;
+}
+int mml_solver_result(mml_solver* s, double* x_best6, double* min_cost, int* iterations) {
+  if (!s) return MML_ERR_INVALID;
+  if (x_best6)
+    for (int i = 0; i < 6; i++) x_best6[i] = s->S.x_best[i];
+  if (min_cost) *min_cost = s->S.min_cost;
+  if (iterations) *iterations = s->S.total_inner;
+  return MML_OK;
+}
+
+}  // extern "C"

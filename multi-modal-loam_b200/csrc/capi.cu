@@ -6,7 +6,7 @@
 // device-resident stages (extract.cu, geometry.cu, associate.cu, accumulate.cu)
 namespace mml { struct EstState; }
 int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_d, const int* scan_off, int n_scans,
-                       int n_lines, uint8_t* label_d);
+                       int n_lines, uint8_t* label_d, bool force_sequential);
 int mml_undistort_device(mml_ctx* ctx, float4* pts_d, const float* s_d, int n, const double* dR9, const double* dt3);
 int mml_label_split_device(mml_ctx* ctx, const float4* pts_d, const uint8_t* label_d, int n, float4* corner_d,
                            float4* surf_d, int* cnt_d);
@@ -142,11 +142,15 @@ int mml_extract_features_batch(mml_ctx* c, const float* xyzi, const uint16_t* li
   MML_CHECK(upload(c, c->in_xyzi, xyzi, sizeof(float) * 4 * (size_t)n));
   MML_CHECK(upload(c, c->in_line, line_id, sizeof(uint16_t) * (size_t)n));
   MML_CUDA(c, c->in_label.reserve((size_t)n + 16));
-  MML_CHECK(mml_extract_device(c, c->in_xyzi.as<float4>(), c->in_line.as<uint16_t>(), scan_offsets, n_scans, n_lines,
-                               c->in_label.as<uint8_t>()));
-  MML_CHECK(download(c, out_label, c->in_label.p, (size_t)n));
   std::vector<int> cnt(2 * (size_t)n_scans + 2, 0);
-  MML_CHECK(download(c, cnt.data(), c->counters.p, sizeof(int) * 2 * (size_t)n_scans));
+  for (int attempt = 0; attempt < 2; attempt++) {
+    MML_CHECK(mml_extract_device(c, c->in_xyzi.as<float4>(), c->in_line.as<uint16_t>(), scan_offsets, n_scans, n_lines,
+                                 c->in_label.as<uint8_t>(), attempt == 1));
+    MML_CHECK(download(c, cnt.data(), c->counters.p, sizeof(int) * (2 * (size_t)n_scans + 1)));
+    MML_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!cnt[2 * (size_t)n_scans]) break;  // no line overflowed the part-parallel kernel's shared memory
+  }
+  MML_CHECK(download(c, out_label, c->in_label.p, (size_t)n));
   MML_CUDA(c, cudaStreamSynchronize(c->stream));
   for (int s = 0; s < n_scans; s++) {
     if (out_n_sharp) out_n_sharp[s] = cnt[2 * s];
@@ -405,7 +409,7 @@ int mml_scan_to_pose_dev(mml_ctx* c, const void* xyzi_dev, const void* line_id_d
   MML_CUDA(c, c->tmp_e.reserve(sizeof(float4) * (size_t)(n > 0 ? n : 1)));
   const int off[2] = {0, n};
   if (c->profile) MML_CUDA(c, cudaEventRecord(c->pev[0], st));
-  MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, c->in_label.as<uint8_t>()));
+  MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, c->in_label.as<uint8_t>(), false));
   // undistort a copy of the scan (the caller's buffer stays untouched)
   mml::DevBuf& wbuf = c->srt_xyzi;  // the line-sorted copy is dead after extraction: reuse its storage
   MML_CUDA(c, wbuf.reserve(sizeof(float4) * (size_t)(n > 0 ? n : 1)));
@@ -416,9 +420,14 @@ int mml_scan_to_pose_dev(mml_ctx* c, const void* xyzi_dev, const void* line_id_d
   // label split (EST.cpp:992-1011); capacities from the counts of the extractor
   MML_CUDA(c, c->frame_cnt.reserve(64));
   int* cnt = c->frame_cnt.as<int>();  // [0..1] voxel outputs, [2..3] raw split counts
-  int hc[2] = {0, 0};
+  int hc[3] = {0, 0, 0};
   MML_CHECK(download(c, hc, c->counters.p, sizeof(hc)));
   MML_CUDA(c, cudaStreamSynchronize(st));
+  if (hc[2]) {  // a line overflowed the part-parallel kernel: sequential fallback
+    MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, c->in_label.as<uint8_t>(), true));
+    MML_CHECK(download(c, hc, c->counters.p, sizeof(hc)));
+    MML_CUDA(c, cudaStreamSynchronize(st));
+  }
   const int n_sharp = hc[0], n_flat = hc[1];
   MML_CUDA(c, c->corner_raw.reserve(sizeof(float4) * (size_t)(n_sharp + 1)));
   MML_CUDA(c, c->surf_raw.reserve(sizeof(float4) * (size_t)(n_flat + 1)));

@@ -115,6 +115,7 @@ struct mml_ctx {
   cudaGraphExec_t est_graph = nullptr;
   long long est_graph_key = 0;
   long long est_launches_per_graph = 0;
+  std::vector<int> last_scan_off;  // scan offsets the resident chunk table was built for
   bool profile = false;
   cudaEvent_t pev[4] = {nullptr, nullptr, nullptr, nullptr};
   double stage_ms[4] = {0, 0, 0, 0};

@@ -450,6 +450,217 @@ __global__ void __launch_bounds__(64) k_select(const uint16_t* __restrict__ attr
   }
 }
 
+// ---------------------------------------------------------------- E4': part-parallel selection
+// The flat selection of FE.cpp:453-541 is sequential across the 50 parts of a line only through
+// neighbour suppression spilling over a part boundary: processing part j marks up to 3 points at
+// the head of part j+1 (before j+1 runs) and up to 3 at the tail of part j-1 (after j-1 finished).
+// Both spills are contiguous from the boundary, so part j's behaviour depends on its predecessor
+// only through h_j in {0,1,2,3} = how many of its head points arrive pre-marked. Every part is
+// therefore simulated for all four values of h_j in parallel (4 x 50 lanes), a 50-step chain
+// picks the h_j that actually occurs, and the tail spills are applied last — the result is
+// identical to the sequential order. The count_num stride walk (FE.cpp:543-650) is a 4-state
+// automaton (distance to the next visited index), evaluated with a parallel scan of composed
+// transition functions.
+// Dynamic shared memory: flags u8[4][NF] | attr8 u8[NF] | v150 u32[nbits]
+constexpr int kSelThreads = 256;
+constexpr int kMinParallelN = 11 + 4 * kParts;  // every part holds >= 4 points: spills reach adjacent parts only
+
+__device__ __forceinline__ unsigned compose4(unsigned f, unsigned g) {  // (g o f)[s] = g[f[s]], 2 bits per state
+  unsigned r = 0;
+#pragma unroll
+  for (int s = 0; s < 4; s++) r |= ((g >> (2 * ((f >> (2 * s)) & 3u))) & 3u) << (2 * s);
+  return r;
+}
+
+__global__ void __launch_bounds__(kSelThreads) k_select_par(const uint16_t* __restrict__ attr_g, const int* __restrict__ sort_ind,
+                                                            const int* __restrict__ refl_ind, const int* __restrict__ srt_src,
+                                                            const int* __restrict__ line_start, const int* __restrict__ line_count,
+                                                            int n_lines, int max_n, uint8_t* __restrict__ out_label,
+                                                            int* __restrict__ counters, int* __restrict__ overflow_flag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned char s_out_h[kParts][4], s_lsp[kParts][4], s_hsel[kParts + 1];
+  __shared__ unsigned s_fn[kSelThreads];
+  __shared__ unsigned s_warp_fn[kSelThreads / 32];
+  const int gl = blockIdx.x;
+  const int n = line_count[gl], ls = line_start[gl];
+  const int NF = (max_n + 15) & ~15;
+  if (n > NF) {  // does not fit: the host re-runs the sequential kernel
+    if (threadIdx.x == 0) atomicExch(overflow_flag, 1);
+    return;
+  }
+  uint8_t* flags4 = smem_raw;
+  uint8_t* attr8 = smem_raw + 4 * (size_t)NF;
+  unsigned* v150 = reinterpret_cast<unsigned*>(smem_raw + 5 * (size_t)NF);
+  const uint16_t* attr_line = attr_g + ls;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int i = tid; i < n; i += kSelThreads) {
+    attr8[i] = (uint8_t)(attr_line[i] & 0xFFu);
+    flags4[i] = 0; flags4[NF + i] = 0; flags4[2 * NF + i] = 0; flags4[3 * NF + i] = 0;
+  }
+  for (int i = tid; i < (n + 31) / 32; i += kSelThreads) v150[i] = 0;
+  if (tid < kParts * 4) { (&s_out_h[0][0])[tid] = 0; (&s_lsp[0][0])[tid] = 0; }
+  if (tid <= kParts) s_hsel[tid] = 0;
+  __syncthreads();
+
+  if (n >= 11) {
+    const int w = (attr_line[n - 6] & A_W3) ? 3 : 2;  // thNumCurvSize left by the last point (FE.cpp:424-428)
+    const bool par = n >= kMinParallelN;
+    // ---- phase 1: flat selection. parallel: lane (j,h) simulates part j with h pre-marked head points;
+    //      short lines: lane 0 runs all parts in order on copy 0 (spills written directly)
+    const int n_sim = par ? kParts * 4 : 1;
+    if (tid < n_sim) {
+      const int j0 = par ? (tid >> 2) : 0, j1 = par ? j0 + 1 : kParts;
+      const int h = par ? (tid & 3) : 0;
+      uint8_t* F = flags4 + (size_t)h * NF;
+      for (int j = j0; j < j1; j++) {
+        int sp, ep;
+        part_bounds(n, j, sp, ep);
+        const int m = ep - sp + 1;
+        if (m <= 0) continue;
+        const int lo = par ? sp : 0, hi = par ? ep : n - 1;  // indices this lane may write
+        if (par)
+          for (int t = 0; t < h; t++) F[sp + t] = 1;
+        int rs = 0, lsp = 0;
+        const int* so = sort_ind + ls + sp;
+        const int* ro = refl_ind + ls + sp;
+        for (int k = 0; k < m; k++) {  // FE.cpp:483-519
+          const int ind = __ldg(so + k);
+          if (F[ind] != 0) continue;
+          const unsigned a = attr8[ind];
+          if (a & A_CAND) {
+            F[ind] = 3;
+            if (!(a & A_FAR)) {
+              for (int l = 1; l <= w; l++) {
+                if (attr8[ind + l - 1] & A_GAP) break;
+                const int idx = ind + l;
+                if (idx <= hi) F[idx] = 1;
+                else rs = max(rs, idx - hi);
+              }
+              for (int l = 1; l <= w; l++) {
+                if (attr8[ind - l] & A_GAP) break;
+                const int idx = ind - l;
+                if (idx >= lo) F[idx] = 1;
+                else lsp = max(lsp, lo - idx);
+              }
+            }
+          }
+        }
+        int smallest = 1, sharpest = 1;
+        for (int k = 0; k < m; k++) {  // FE.cpp:521-539
+          const int ind = __ldg(so + k);
+          const unsigned a = attr8[ind];
+          const int f = F[ind];
+          if ((f == 3 && smallest <= 1) || (f == 3 && (a & A_FAR)) || (a & A_ANGLE)) {
+            smallest++;
+            F[ind] = 2;
+          }
+          const int idx = __ldg(ro + k);
+          if (sharpest <= 3 && (attr8[idx] & A_C300)) {
+            sharpest++;
+            F[idx] = 4;  // 300
+          }
+        }
+        if (par) {
+          s_out_h[j][h] = (unsigned char)min(rs, 3);
+          s_lsp[j][h] = (unsigned char)min(lsp, 3);
+        }
+      }
+    }
+    // ---- phase C: stride walk as a scan of transition functions over 256 contiguous chunks
+    const int span = n - 10;  // indices 5 .. n-6
+    const int chunk = (span + kSelThreads - 1) / kSelThreads;
+    const int a0 = 5 + tid * chunk, a1 = min(a0 + chunk, n - 5);
+    unsigned fn = 0xE4u;  // identity: state s -> s
+    {
+      int st0 = 0, st1 = 1, st2 = 2, st3 = 3;
+      for (int i = a0; i < a1; i++) {
+        const int jump = (attr8[i] & A_RF) ? 3 : 0;
+        st0 = st0 ? st0 - 1 : jump;
+        st1 = st1 ? st1 - 1 : jump;
+        st2 = st2 ? st2 - 1 : jump;
+        st3 = st3 ? st3 - 1 : jump;
+      }
+      if (a0 < a1) fn = (unsigned)st0 | ((unsigned)st1 << 2) | ((unsigned)st2 << 4) | ((unsigned)st3 << 6);
+    }
+    // inclusive scan of composition within the warp, then across the 8 warps
+    unsigned inc = fn;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned prev = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc = compose4(prev, inc);
+    }
+    if (lane == 31) s_warp_fn[warp] = inc;
+    s_fn[tid] = inc;
+    __syncthreads();
+    unsigned pre = 0xE4u;  // composition of all chunks before this thread's
+    for (int wv = 0; wv < warp; wv++) pre = compose4(pre, s_warp_fn[wv]);
+    if (lane > 0) pre = compose4(pre, s_fn[tid - 1]);
+    int s = (int)(pre & 3u);  // state entering index 5 is 0 (index 5 is visited)
+    for (int i = a0; i < a1; i++) {
+      if (s == 0) {
+        const unsigned a = attr8[i];
+        if (a & A_C150) atomicOr(&v150[i >> 5], 1u << (i & 31));
+        s = (a & A_RF) ? 3 : 0;
+      } else {
+        s--;
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: which h_j actually occurs
+    if (tid == 0 && par) {
+      int h = 0;
+      for (int j = 0; j < kParts; j++) {
+        s_hsel[j] = (unsigned char)h;
+        h = s_out_h[j][h];
+      }
+      s_hsel[kParts] = 0;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3: FE.cpp:818-842 + label write-back FE.cpp:1016-1023
+  const int scan = gl / n_lines;
+  const bool par = n >= kMinParallelN;
+  int n_sharp = 0, n_flat = 0;
+  for (int i0 = 0; i0 < n; i0 += kSelThreads) {
+    const int i = i0 + tid;
+    int label = 0;
+    if (i < n && i >= 5 && i < n - 5) {
+      const unsigned a = attr_line[i];
+      if (!(a & A_NEAR)) {
+        const bool v = (v150[i >> 5] >> (i & 31)) & 1u;
+        if (a & A_BRK100) label = 1;
+        else if (a & A_BRK101) label = 0;
+        else if (v) label = 1;
+        else {
+          int f;
+          if (par) {
+            int j = (int)(((long long)(i - 5) * kParts) / (n - 11));
+            j = j > kParts - 1 ? kParts - 1 : j;
+            int sp, ep;
+            part_bounds(n, j, sp, ep);
+            while (i < sp) { j--; part_bounds(n, j, sp, ep); }
+            while (i > ep) { j++; part_bounds(n, j, sp, ep); }
+            f = flags4[(size_t)s_hsel[j] * NF + i];
+            if (j + 1 < kParts && i > ep - (int)s_lsp[j + 1][s_hsel[j + 1]]) f = 1;  // tail spill of part j+1
+          } else {
+            f = flags4[i];
+          }
+          if (f == 2) label = 2;
+        }
+      }
+    }
+    if (i < n) out_label[srt_src[ls + i]] = (uint8_t)label;
+    n_sharp += __popc(__ballot_sync(0xffffffffu, label == 1));
+    n_flat += __popc(__ballot_sync(0xffffffffu, label == 2));
+  }
+  if (lane == 0) {
+    if (n_sharp) atomicAdd(&counters[2 * scan], n_sharp);
+    if (n_flat) atomicAdd(&counters[2 * scan + 1], n_flat);
+  }
+}
+
 }  // namespace mml
 
 using namespace mml;
@@ -457,13 +668,13 @@ using namespace mml;
 // Device-resident extraction. xyzi_d/line_d hold n_total points; labels go to label_d (u8),
 // per-scan (n_sharp, n_flat) to ctx->counters[2*s..]. scan_off is a HOST array.
 int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_d, const int* scan_off, int n_scans,
-                       int n_lines, uint8_t* label_d) {
+                       int n_lines, uint8_t* label_d, bool force_sequential) {
   if (n_lines <= 0 || n_lines > kMaxLines) return mml_fail(ctx, MML_ERR_INVALID, "n_lines must be in [1,64]");
   const int n_total = scan_off[n_scans];
   const int TL = n_scans * n_lines;
   cudaStream_t st = ctx->stream;
   MML_CUDA(ctx, ctx->counters.reserve(sizeof(int) * (2 * (size_t)n_scans + 64)));
-  MML_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * 2 * (size_t)n_scans, st));
+  MML_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * (2 * (size_t)n_scans + 1), st));
   if (n_total <= 0) return MML_OK;
 
   // host-side chunk table (metadata only)
@@ -481,15 +692,21 @@ int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_
   const int n_chunks = (int)chunks.size();
 
   const size_t meta_bytes = sizeof(Chunk) * n_chunks + sizeof(int) * (2 * (size_t)n_scans + 2);
-  MML_CUDA(ctx, ctx->pin_small.reserve(meta_bytes));
-  MML_CUDA(ctx, ctx->chunk_tab.reserve(meta_bytes));
-  // the pinned staging area may still be in flight from a previous call
-  MML_CUDA(ctx, cudaStreamSynchronize(st));
-  char* hp = ctx->pin_small.as<char>();
-  memcpy(hp, chunks.data(), sizeof(Chunk) * n_chunks);
-  memcpy(hp + sizeof(Chunk) * n_chunks, scan_chunk0.data(), sizeof(int) * (n_scans + 1));
-  memcpy(hp + sizeof(Chunk) * n_chunks + sizeof(int) * (n_scans + 1), scan_off, sizeof(int) * (n_scans + 1));
-  MML_CUDA(ctx, cudaMemcpyAsync(ctx->chunk_tab.p, hp, meta_bytes, cudaMemcpyHostToDevice, st));
+  // the chunk table only depends on the scan offsets: re-upload only when they change
+  const bool cached = ctx->chunk_tab.p && (int)ctx->last_scan_off.size() == n_scans + 1 &&
+                      memcmp(ctx->last_scan_off.data(), scan_off, sizeof(int) * (n_scans + 1)) == 0;
+  if (!cached) {
+    MML_CUDA(ctx, ctx->pin_small.reserve(meta_bytes));
+    MML_CUDA(ctx, ctx->chunk_tab.reserve(meta_bytes));
+    // the pinned staging area may still be in flight from a previous call
+    MML_CUDA(ctx, cudaStreamSynchronize(st));
+    char* hp = ctx->pin_small.as<char>();
+    memcpy(hp, chunks.data(), sizeof(Chunk) * n_chunks);
+    memcpy(hp + sizeof(Chunk) * n_chunks, scan_chunk0.data(), sizeof(int) * (n_scans + 1));
+    memcpy(hp + sizeof(Chunk) * n_chunks + sizeof(int) * (n_scans + 1), scan_off, sizeof(int) * (n_scans + 1));
+    MML_CUDA(ctx, cudaMemcpyAsync(ctx->chunk_tab.p, hp, meta_bytes, cudaMemcpyHostToDevice, st));
+    ctx->last_scan_off.assign(scan_off, scan_off + n_scans + 1);
+  }
   const Chunk* chunks_d = ctx->chunk_tab.as<Chunk>();
   const int* scan_chunk0_d = reinterpret_cast<const int*>(ctx->chunk_tab.as<char>() + sizeof(Chunk) * n_chunks);
   const int* scan_off_d = scan_chunk0_d + (n_scans + 1);
@@ -535,23 +752,33 @@ int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_
                                                    ctx->sort_ind.as<int>(), ctx->refl_ind.as<int>(), max_m);
   MML_LAUNCHED(ctx);
 
-  const size_t nflag = ((size_t)max_n + 15) & ~(size_t)15;
-  const size_t nbits = (((size_t)max_n + 31) / 32 + 3) & ~(size_t)3;
-  const size_t base_smem = nflag + 4 * nbits + 8 * (size_t)max_m;
-  const size_t full_smem = base_smem + 2 * (size_t)max_n + 16;
+  int* overflow_flag = ctx->counters.as<int>() + 2 * (size_t)n_scans;
   const size_t kMaxSmem = 227 * 1024;
-  if (base_smem > kMaxSmem) return mml_fail(ctx, MML_ERR_CAPACITY, "scan line too long for k_select shared memory");
-  if (full_smem <= kMaxSmem) {
-    if (full_smem > 48 * 1024)
-      MML_CUDA(ctx, cudaFuncSetAttribute(k_select<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)full_smem));
-    k_select<true><<<TL, 64, full_smem, st>>>(ctx->attr.as<uint16_t>(), ctx->sort_ind.as<int>(), ctx->refl_ind.as<int>(),
-                                              ctx->srt_src.as<int>(), line_start, line_count, n_lines, max_n, max_m, label_d,
-                                              ctx->counters.as<int>());
+  if (!force_sequential) {
+    // part-parallel selection; lines longer than the shared-memory capacity raise the overflow flag and the
+    // caller re-runs the sequential kernel (mml_extract_overflowed)
+    const int cap_n = max_n < 44032 ? ((max_n + 15) & ~15) : 44032;
+    const size_t par_smem = 5 * (size_t)cap_n + 4 * ((((size_t)cap_n + 31) / 32 + 3) & ~(size_t)3);
+    if (par_smem > 48 * 1024)
+      MML_CUDA(ctx, cudaFuncSetAttribute(k_select_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)par_smem));
+    k_select_par<<<TL, kSelThreads, par_smem, st>>>(ctx->attr.as<uint16_t>(), ctx->sort_ind.as<int>(), ctx->refl_ind.as<int>(),
+                                                    ctx->srt_src.as<int>(), line_start, line_count, n_lines, cap_n, label_d,
+                                                    ctx->counters.as<int>(), overflow_flag);
   } else {
+    // sequential fallback: size shared memory for the longest line actually present
+    std::vector<int> lc(TL);
+    MML_CUDA(ctx, cudaMemcpyAsync(lc.data(), line_count, sizeof(int) * TL, cudaMemcpyDeviceToHost, st));
+    MML_CUDA(ctx, cudaStreamSynchronize(st));
+    int longest = 0;
+    for (int v : lc) longest = v > longest ? v : longest;
+    const size_t nflag = ((size_t)longest + 15) & ~(size_t)15;
+    const size_t nbits = (((size_t)longest + 31) / 32 + 3) & ~(size_t)3;
+    const size_t base_smem = nflag + 4 * nbits + 8 * (size_t)max_m;
+    if (base_smem > kMaxSmem) return mml_fail(ctx, MML_ERR_CAPACITY, "scan line too long for k_select shared memory");
     if (base_smem > 48 * 1024)
       MML_CUDA(ctx, cudaFuncSetAttribute(k_select<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base_smem));
     k_select<false><<<TL, 64, base_smem, st>>>(ctx->attr.as<uint16_t>(), ctx->sort_ind.as<int>(), ctx->refl_ind.as<int>(),
-                                               ctx->srt_src.as<int>(), line_start, line_count, n_lines, max_n, max_m, label_d,
+                                               ctx->srt_src.as<int>(), line_start, line_count, n_lines, longest, max_m, label_d,
                                                ctx->counters.as<int>());
   }
   MML_LAUNCHED(ctx);

@@ -570,7 +570,7 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
   MML_CUDA(ctx, ctx->assoc_stats.reserve(512));
   MML_CUDA(ctx, ctx->f_line.reserve(sizeof(float4) * 3 * (size_t)(cap_corner > 0 ? cap_corner : 1)));
   MML_CUDA(ctx, ctx->f_plane.reserve(sizeof(float4) * 3 * (size_t)(cap_surf > 0 ? cap_surf : 1)));
-  MML_CUDA(ctx, ctx->tmp_c.reserve(sizeof(double) * 8 * (size_t)(div_up((cap_corner > cap_surf ? cap_corner : cap_surf) + 1, 128) + 1) + 64));
+  MML_CUDA(ctx, ctx->tmp_c.reserve(sizeof(double) * 8 * (size_t)(div_up((cap_corner > cap_surf ? cap_corner : cap_surf) + 1, 4) + 1) + 64));
   EstState* S = ctx->est_state.as<EstState>();
 
   // host-side initial state

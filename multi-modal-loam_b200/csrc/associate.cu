@@ -20,6 +20,7 @@
 #include "sort.cuh"
 #include "smallmath.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace mml {
 
@@ -212,6 +213,7 @@ struct AssocArgs {
   const float4* q;
   int nq;
   const int* nq_dev;        // optional: query count read from device memory (<= nq)
+  int* overflow;            // set to 1 when *nq_dev exceeds the launch capacity nq
   double T[16];
   float thres;
   GridDev G[2];  // [0] global, [1] local
@@ -389,6 +391,228 @@ __global__ void __launch_bounds__(128) k_associate(AssocArgs A) {
   }
 }
 
+// ---------------------------------------------------------------- group-per-query search
+// G lanes cooperate on one query: the cells of a shell are dealt out to the lanes (ring 1: the 27
+// cells individually, outer shells: x-rows / end cells), every lane keeps its own sorted 5-list, and
+// after each shell the lists are merged with shuffle arg-min rounds into the exact global 5-list
+// (same (d2, index) order as the one-thread search, so results are identical). This removes the
+// serial chain of dependent L2 loads that bounds the latency of the thread-per-query kernel.
+template <int G>
+__device__ __forceinline__ unsigned group_mask() {
+  if (G == 32) return 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  return ((1u << G) - 1u) << (lane & ~(unsigned)(G - 1));
+}
+
+template <int G>
+__device__ __forceinline__ void group_merge(const Knn5& r, Knn5& m, unsigned mask, int lg) {
+  int ptr = 0;
+  m.cnt = 0;
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    float d = ptr == 0 ? r.d[0] : ptr == 1 ? r.d[1] : ptr == 2 ? r.d[2] : ptr == 3 ? r.d[3] : ptr == 4 ? r.d[4] : INFINITY;
+    int id = ptr == 0 ? r.id[0] : ptr == 1 ? r.id[1] : ptr == 2 ? r.id[2] : ptr == 3 ? r.id[3] : ptr == 4 ? r.id[4] : 0x7fffffff;
+    int loc = ptr == 0 ? r.loc[0] : ptr == 1 ? r.loc[1] : ptr == 2 ? r.loc[2] : ptr == 3 ? r.loc[3] : ptr == 4 ? r.loc[4] : -1;
+    int src = lg;
+#pragma unroll
+    for (int s = G / 2; s > 0; s >>= 1) {
+      const float od = __shfl_xor_sync(mask, d, s, G);
+      const int oid = __shfl_xor_sync(mask, id, s, G);
+      const int oloc = __shfl_xor_sync(mask, loc, s, G);
+      const int osrc = __shfl_xor_sync(mask, src, s, G);
+      // total order on (d, id, src): identical on both sides of the exchange
+      const bool take = od < d || (od == d && (oid < id || (oid == id && osrc < src)));
+      if (take) { d = od; id = oid; loc = oloc; src = osrc; }
+    }
+    m.d[k] = d; m.id[k] = id; m.loc[k] = loc;
+    if (d < INFINITY) m.cnt++;
+    if (src == lg) ptr++;
+  }
+}
+
+template <int G>
+__device__ bool knn5_grid_group(const GridDev& Gd, float qx, float qy, float qz, float thres, Knn5& m, unsigned mask, int lg) {
+  Knn5 r;
+  knn_init(r);
+  knn_init(m);
+  int c[3], lo[3], hi[3], cube;
+  if (!locate(Gd, qx, qy, qz, c, lo, hi, cube)) return false;
+  if (Gd.global) {
+    if (!(__ldg(Gd.cube_count + cube) > Gd.min_cube_pts)) return false;
+  } else {
+    if (!(Gd.m > Gd.min_local_pts)) return false;
+  }
+  const float cellf = Gd.cell;
+  const int rmax = (int)ceilf(sqrtf(thres) / cellf) + 1;
+  for (int rr = 1; rr <= rmax; rr++) {
+    const int side = 2 * rr + 1;
+    const int nseg = rr == 1 ? 27 : 2 * side * side;
+    for (int s = lg; s < nseg; s += G) {
+      int y, z, x0, x1;
+      if (rr == 1) {
+        const int dz = s / 9 - 1, dy = (s / 3) % 3 - 1, dx = s % 3 - 1;
+        z = c[2] + dz; y = c[1] + dy; x0 = x1 = c[0] + dx;
+        if (x0 < lo[0] || x0 > hi[0]) continue;
+      } else {
+        const int row = s >> 1, which = s & 1;
+        const int dz = row / side - rr, dy = row % side - rr;
+        z = c[2] + dz; y = c[1] + dy;
+        const bool full = dz == -rr || dz == rr || dy == -rr || dy == rr;
+        if (full) {
+          if (which) continue;
+          x0 = max(c[0] - rr, lo[0]); x1 = min(c[0] + rr, hi[0]);
+          if (x0 > x1) continue;
+        } else {
+          x0 = x1 = which ? c[0] + rr : c[0] - rr;
+          if (x0 < lo[0] || x0 > hi[0]) continue;
+        }
+      }
+      if (z < lo[2] || z > hi[2] || y < lo[1] || y > hi[1]) continue;
+      const int rowb = (z * Gd.dim[1] + y) * Gd.dim[0];
+      scan_range(Gd, rowb + x0, rowb + x1, qx, qy, qz, r);
+    }
+    group_merge<G>(r, m, mask, lg);
+    // lane 0 carries the merged list forward, the others start the next shell empty (no duplicates)
+    if (lg == 0) r = m;
+    else knn_init(r);
+    if (c[0] - rr < lo[0] && c[0] + rr > hi[0] && c[1] - rr < lo[1] && c[1] + rr > hi[1] && c[2] - rr < lo[2] &&
+        c[2] + rr > hi[2])
+      break;
+    const float reach = fmaxf((float)rr * cellf - 1e-3f, 0.f);
+    const float reach2 = reach * reach;
+    if (m.cnt == 5 && m.d[4] <= reach2) break;
+    if (reach2 >= thres) break;
+  }
+  return m.cnt == 5 && m.d[4] < thres;
+}
+
+template <int KIND, int G>
+__global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
+  if (A.gate && *A.gate) return;
+  constexpr int QPB = 128 / G;  // queries per block
+  const int lg = threadIdx.x % G;
+  const int i = blockIdx.x * QPB + threadIdx.x / G;
+  const unsigned mask = group_mask<G>();
+  double T[16];
+  float thres = A.thres;
+  if (A.T_dev) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) T[k] = A.T_dev[k];
+    thres = *A.thres_dev;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; k++) T[k] = A.T[k];
+  }
+  double mom[7] = {0, 0, 0, 0, 0, 0, 0};
+  int found = 0;
+  int nq = A.nq_dev ? *A.nq_dev : A.nq;
+  if (nq > A.nq) {  // more queries than this launch was sized for: flag it, the host re-launches
+    if (blockIdx.x == 0 && threadIdx.x == 0 && A.overflow) atomicExch(A.overflow, 1);
+    nq = A.nq;
+  }
+  // CTAs beyond the last query leave at once; the reduction below only spans the active ones
+  const unsigned n_active = nq > 0 ? (unsigned)((nq + QPB - 1) / QPB) : 1u;
+  if (blockIdx.x >= n_active) return;
+  if (i < nq) {
+    const float4 q = A.q[i];
+    const double pin[3] = {(double)q.x, (double)q.y, (double)q.z};
+    float sel[3];
+#pragma unroll
+    for (int rr = 0; rr < 3; rr++)
+      sel[rr] = (float)(((T[4 * rr] * pin[0] + T[4 * rr + 1] * pin[1]) + T[4 * rr + 2] * pin[2]) + T[4 * rr + 3]);
+    float4 f0 = make_float4(q.x, q.y, q.z, -1.f), f1 = make_float4(0, 0, 0, 0), f2 = make_float4(0, 0, 0, 0);
+    int cI, cJ, cK;
+    const bool in_grid = cube_of(sel[0], sel[1], sel[2], A.G[0].cen, cI, cJ, cK);
+    const bool finite = !(isnan(sel[0]) || isnan(sel[1]) || isnan(sel[2]));
+    if (in_grid && finite) {
+      Knn5 r;
+      for (int mp = 0; mp < 2 && !found; mp++) {
+        const GridDev& Gd = A.G[mp];
+        if (!Gd.valid) continue;
+        if (!knn5_grid_group<G>(Gd, sel[0], sel[1], sel[2], thres, r, mask, lg)) continue;  // group-uniform
+        int ok = 0;
+        if (lg == 0) {
+          if (KIND == 0) {
+            float a[3], b[3];
+            if (fit_line(Gd, r, a, b)) {
+              f1 = make_float4(a[0], a[1], a[2], b[0]);
+              f2 = make_float4(b[1], b[2], 0.f, 0.f);
+              double P[3];
+#pragma unroll
+              for (int rr = 0; rr < 3; rr++)
+                P[rr] = ((T[4 * rr] * pin[0] + T[4 * rr + 1] * pin[1]) + T[4 * rr + 2] * pin[2]) + T[4 * rr + 3];
+              const double da[3] = {a[0], a[1], a[2]}, db[3] = {b[0], b[1], b[2]};
+              const double l12 = sqrt((da[0] - db[0]) * (da[0] - db[0]) + (da[1] - db[1]) * (da[1] - db[1]) +
+                                      (da[2] - db[2]) * (da[2] - db[2]));
+              const double c0 = (P[0] - da[0]) * (P[1] - db[1]) - (P[0] - db[0]) * (P[1] - da[1]);
+              const double c1 = (P[0] - da[0]) * (P[2] - db[2]) - (P[0] - db[0]) * (P[2] - da[2]);
+              const double c2 = (P[1] - da[1]) * (P[2] - db[2]) - (P[1] - db[1]) * (P[2] - da[2]);
+              const double err = sqrt(c0 * c0 + c1 * c1 + c2 * c2) / l12;
+              f0.w = (fabs(err) > 1e-5) ? 1.f : 0.f;
+              f2.z = (float)err;
+              ok = 1;
+            }
+          } else {
+            float nrm[3], dist;
+            if (fit_plane(Gd, r, sel[0], sel[1], sel[2], nrm, &dist)) {
+              f1 = make_float4(sel[0], sel[1], sel[2], dist);
+              f2 = make_float4(nrm[0], nrm[1], nrm[2], 0.f);
+              double e[3];
+#pragma unroll
+              for (int rr = 0; rr < 3; rr++) {
+                const double P = ((T[4 * rr] * pin[0] + T[4 * rr + 1] * pin[1]) + T[4 * rr + 2] * pin[2]) + T[4 * rr + 3];
+                const double proj = (double)sel[rr] - (double)dist * (double)nrm[rr];
+                e[rr] = P - proj;
+              }
+              const double err = sqrt((e[0] * e[0] + e[1] * e[1]) + e[2] * e[2]);
+              f0.w = (fabs(err) > 1e-5) ? 1.f : 0.f;
+              f2.w = (float)err;
+              const double n0 = nrm[0], n1 = nrm[1], n2 = nrm[2];
+              mom[0] = n0 * n0; mom[1] = n0 * n1; mom[2] = n0 * n2; mom[3] = n1 * n1; mom[4] = n1 * n2; mom[5] = n2 * n2;
+              ok = 1;
+            }
+          }
+        }
+        found = __shfl_sync(mask, ok, 0, G);
+      }
+    }
+    if (lg == 0) {
+      A.feat[3 * (size_t)i] = f0;
+      A.feat[3 * (size_t)i + 1] = f1;
+      A.feat[3 * (size_t)i + 2] = f2;
+    }
+  }
+  mom[6] = (lg == 0) ? (double)found : 0.0;
+  __shared__ double sred[4][7];
+  __shared__ bool is_last;
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+    double v = mom[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    const double v = ((sred[0][threadIdx.x] + sred[1][threadIdx.x]) + sred[2][threadIdx.x]) + sred[3][threadIdx.x];
+    A.moment_partials[(size_t)blockIdx.x * 8 + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(A.ticket, 1u) == n_active - 1);
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x < 7) {
+      double s = 0;
+      for (unsigned b = 0; b < n_active; b++) s += __ldcg(A.moment_partials + (size_t)b * 8 + threadIdx.x);
+      A.moment_out[threadIdx.x] = s;
+      if (threadIdx.x == 6) *A.n_feat_out = (int)s;
+    }
+    if (threadIdx.x == 0) *A.ticket = 0;
+  }
+}
+
 // expand compact features to the host-visible 12-double records of include/mmloam_b200.h
 template <int KIND>
 __global__ void __launch_bounds__(256) k_export_features(const float4* __restrict__ feat, int nq, double* __restrict__ out) {
@@ -558,7 +782,10 @@ static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, floa
 int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres, const double* T_dev,
                          const float* thres_dev, const int* gate, const int* nq_dev, int cap) {
   const int nq = cap;
-  const int grid = div_up(nq > 0 ? nq : 1, 128);
+  // lanes per query: a whole warp for scan-sized query sets (latency), 8 lanes for map-sized sweeps
+  static const int g_env = getenv("MML_ASSOC_G") ? atoi(getenv("MML_ASSOC_G")) : 0;
+  const int G = g_env ? g_env : (cap <= 32768 ? 32 : 8);
+  const int grid = G == 1 ? div_up(nq > 0 ? nq : 1, 128) : div_up(nq > 0 ? nq : 1, 128 / G);
   mml::DevBuf& fb = kind == 0 ? ctx->f_line : ctx->f_plane;
   MML_CUDA(ctx, fb.reserve(sizeof(float4) * 3 * (size_t)(nq > 0 ? nq : 1)));
   // assoc_stats layout (doubles): [0..7] line moments/count, [8..15] plane moments/count,
@@ -585,8 +812,23 @@ int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres,
   A.gate = gate;
   A.T_dev = T_dev;
   A.thres_dev = thres_dev;
-  if (kind == 0) k_associate<0><<<grid, 128, 0, ctx->stream>>>(A);
-  else k_associate<1><<<grid, 128, 0, ctx->stream>>>(A);
+  A.overflow = ints + 6;
+  if (G == 32) {
+    if (kind == 0) k_associate_g<0, 32><<<grid, 128, 0, ctx->stream>>>(A);
+    else k_associate_g<1, 32><<<grid, 128, 0, ctx->stream>>>(A);
+  } else if (G == 8) {
+    if (kind == 0) k_associate_g<0, 8><<<grid, 128, 0, ctx->stream>>>(A);
+    else k_associate_g<1, 8><<<grid, 128, 0, ctx->stream>>>(A);
+  } else if (G == 16) {
+    if (kind == 0) k_associate_g<0, 16><<<grid, 128, 0, ctx->stream>>>(A);
+    else k_associate_g<1, 16><<<grid, 128, 0, ctx->stream>>>(A);
+  } else if (G == 4) {
+    if (kind == 0) k_associate_g<0, 4><<<grid, 128, 0, ctx->stream>>>(A);
+    else k_associate_g<1, 4><<<grid, 128, 0, ctx->stream>>>(A);
+  } else {
+    if (kind == 0) k_associate<0><<<grid, 128, 0, ctx->stream>>>(A);
+    else k_associate<1><<<grid, 128, 0, ctx->stream>>>(A);
+  }
   MML_LAUNCHED(ctx);
   MML_CUDA(ctx, cudaGetLastError());
   return MML_OK;

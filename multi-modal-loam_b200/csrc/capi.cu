@@ -22,6 +22,10 @@ int mml_export_features(mml_ctx* ctx, int kind, int nq, double* out_dev);
 int mml_accumulate_launch(mml_ctx* ctx, const double* x6, const double* T_bl16, double lidar_m, double w_tan,
                           double huber_a, mml::EstState* st_dev, const int* n_dev, int cap_line, int cap_plane,
                           const double* wide_line_dev, const double* wide_plane_dev);
+int mml_split_voxel_capacity();
+int mml_split_voxel_device(mml_ctx* ctx, const float4* pts_d, const float* s_d, const uint8_t* label_d, int n,
+                           const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, float4* corner_out,
+                           float4* surf_out, int* counts_d);
 int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int cap_surf, const double* exTlb16,
                         double* P3, double* q4, const mml_est_params* prm, double* stats);
 
@@ -79,6 +83,7 @@ int mml_ctx_destroy(mml_ctx* c) {
   c->pin_in.release();
   c->pin_out.release();
   c->pin_small.release();
+  c->pin_flags.release();
   for (auto s : c->extra_streams) cudaStreamDestroy(s);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
@@ -395,8 +400,8 @@ int mml_estimate(mml_ctx* c, const float* corner_xyzi, int n_corner, const float
                              stats);
 }
 
-// extract -> undistort -> split + voxel -> estimate, everything resident between stages
-int mml_scan_to_pose_dev(mml_ctx* c, const void* xyzi_dev, const void* line_id_dev, const void* s_dev, int n, int n_lines,
+// general path: any number of labelled points (multi-kernel split + radix-sort voxel filter)
+static int scan_to_pose_general(mml_ctx* c, const void* xyzi_dev, const void* line_id_dev, const void* s_dev, int n, int n_lines,
                          const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, const double* exTlb16,
                          double* P3, double* q_wxyz4, const mml_est_params* prm, double* stats, int* out_counts) {
   if (!c || n < 0 || !exTlb16 || !P3 || !q_wxyz4) return MML_ERR_INVALID;
@@ -456,6 +461,63 @@ int mml_scan_to_pose_dev(mml_ctx* c, const void* xyzi_dev, const void* line_id_d
     out_counts[0] = n_sharp; out_counts[1] = n_flat; out_counts[2] = hv[0]; out_counts[3] = hv[1];
     c->n_corner = hv[0];
     c->n_surf = hv[1];
+  }
+  return MML_OK;
+}
+
+// extract -> fused (split + undistort + voxel) -> estimate, everything resident between stages and ONE host
+// synchronisation per scan. Falls back to the general path when a line or a label class exceeds the
+// shared-memory capacities of the fused kernels.
+int mml_scan_to_pose_dev(mml_ctx* c, const void* xyzi_dev, const void* line_id_dev, const void* s_dev, int n, int n_lines,
+                         const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, const double* exTlb16,
+                         double* P3, double* q_wxyz4, const mml_est_params* prm, double* stats, int* out_counts) {
+  if (!c || n < 0 || !exTlb16 || !P3 || !q_wxyz4) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  mml_est_params def;
+  mml_est_params_default(&def);
+  if (!prm) prm = &def;
+  cudaStream_t st = c->stream;
+  const int cap = mml_split_voxel_capacity();
+  MML_CUDA(c, c->in_label.reserve((size_t)n + 16));
+  MML_CUDA(c, c->frame_cnt.reserve(64));
+  MML_CUDA(c, c->q_corner.reserve(sizeof(float4) * (size_t)cap));
+  MML_CUDA(c, c->q_surf.reserve(sizeof(float4) * (size_t)cap));
+  MML_CUDA(c, c->pin_flags.reserve(64));
+  const double P_in[3] = {P3[0], P3[1], P3[2]}, q_in[4] = {q_wxyz4[0], q_wxyz4[1], q_wxyz4[2], q_wxyz4[3]};
+  const int off[2] = {0, n};
+  if (c->profile) MML_CUDA(c, cudaEventRecord(c->pev[0], st));
+  MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, c->in_label.as<uint8_t>(), false));
+  if (c->profile) MML_CUDA(c, cudaEventRecord(c->pev[1], st));
+  int* cnt = c->frame_cnt.as<int>();  // [0..1] voxel outputs, [2..3] raw split counts, [4] overflow
+  const bool undist = dR9 && dt3 && s_dev;
+  MML_CHECK(mml_split_voxel_device(c, (const float4*)xyzi_dev, undist ? (const float*)s_dev : nullptr, c->in_label.as<uint8_t>(), n,
+                                   dR9, dt3, leaf_corner, leaf_surf, c->q_corner.as<float4>(), c->q_surf.as<float4>(), cnt));
+  int* hf = c->pin_flags.as<int>();  // [0..2] extractor counters (+ overflow), [4..8] split/voxel counts
+  MML_CUDA(c, cudaMemcpyAsync(hf, c->counters.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  MML_CUDA(c, cudaMemcpyAsync(hf + 4, cnt, 5 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (c->profile) MML_CUDA(c, cudaEventRecord(c->pev[2], st));
+  MML_CHECK(mml_estimate_device(c, cnt, cap, cap, exTlb16, P3, q_wxyz4, prm, stats));  // synchronises the stream
+  if (hf[2] || hf[8]) {
+    // a scan line or a label class did not fit the fused kernels: redo on the general path
+    for (int i = 0; i < 3; i++) P3[i] = P_in[i];
+    for (int i = 0; i < 4; i++) q_wxyz4[i] = q_in[i];
+    return scan_to_pose_general(c, xyzi_dev, line_id_dev, s_dev, n, n_lines, dR9, dt3, leaf_corner, leaf_surf, exTlb16, P3,
+                                q_wxyz4, prm, stats, out_counts);
+  }
+  if (c->profile) {
+    MML_CUDA(c, cudaEventRecord(c->pev[3], st));
+    MML_CUDA(c, cudaEventSynchronize(c->pev[3]));
+    for (int k = 0; k < 3; k++) {
+      float ms = 0.f;
+      MML_CUDA(c, cudaEventElapsedTime(&ms, c->pev[k], c->pev[k + 1]));
+      c->stage_ms[k] += ms;
+    }
+    c->stage_n++;
+  }
+  c->n_corner = hf[4];
+  c->n_surf = hf[5];
+  if (out_counts) {
+    out_counts[0] = hf[0]; out_counts[1] = hf[1]; out_counts[2] = hf[4]; out_counts[3] = hf[5];
   }
   return MML_OK;
 }

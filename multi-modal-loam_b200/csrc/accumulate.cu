@@ -606,7 +606,7 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
   mix((long long)(size_t)ctx->assoc_stats.p); mix(cap_corner); mix(cap_surf); mix(prm->max_outer); mix(prm->max_inner);
   for (int k = 0; k < 4; k++) {
     const GridMap& M = ctx->maps[k];
-    mix(M.valid); mix((long long)(size_t)M.pts.p); mix((long long)(size_t)M.cell_start.p); mix(M.m); mix(M.ncell);
+    mix(M.valid); mix(M.coarse); mix((long long)(size_t)M.pts2.p); mix((long long)(size_t)M.cell_start2.p); mix((long long)(size_t)M.pts.p); mix((long long)(size_t)M.cell_start.p); mix(M.m); mix(M.ncell);
     mix(M.dim[0]); mix(M.dim[1]); mix(M.dim[2]); mix((long long)(M.cell * 1e6f)); mix(M.cube_lo[0]); mix(M.cube_lo[1]); mix(M.cube_lo[2]);
     mix((long long)(M.org_d[0] * 1e6)); mix((long long)(M.org_d[1] * 1e6)); mix((long long)(M.org_d[2] * 1e6));
     mix(M.cen[0]); mix(M.cen[1]); mix(M.cen[2]);

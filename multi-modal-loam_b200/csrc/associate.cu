@@ -28,6 +28,10 @@ struct GridDev {
   const float4* pts;
   const int* cell_start;
   const int* cube_count;  // global kinds only
+  const float4* pts2;     // coarse level (cells `coarse` times larger), null when absent
+  const int* cell_start2;
+  int dim2[3];
+  int coarse;
   double org[3];          // lower corner of cell (0,0,0)
   double inv_cell;
   float cell;
@@ -109,6 +113,20 @@ __global__ void __launch_bounds__(256) k_map_scatter(const float4* __restrict__ 
   float4 p = pts[i];
   p.w = __int_as_float(i);
   out[pos] = p;
+}
+
+// coarse level: cell of every point from its fine cell (integer division keeps cube blocks aligned)
+__global__ void __launch_bounds__(256) k_map_coarse_count(const int* __restrict__ cell_of, int m, int dx, int dy, int f,
+                                                          int dx2, int dy2, int* __restrict__ cell_of2,
+                                                          int* __restrict__ cell_cnt2) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= m) return;
+  const int cell = cell_of[i];
+  if (cell < 0) { cell_of2[i] = -1; return; }
+  const int x = cell % dx, y = (cell / dx) % dy, z = cell / (dx * dy);
+  const int c2 = ((z / f) * dy2 + (y / f)) * dx2 + (x / f);
+  cell_of2[i] = c2;
+  atomicAdd(&cell_cnt2[c2], 1);
 }
 
 // occupied-cell count at a trial resolution (to pick the final cell size)
@@ -227,11 +245,11 @@ struct AssocArgs {
   const float* thres_dev;
 };
 
-__device__ bool fit_line(const GridDev& G, const Knn5& r, float* a, float* b) {
+__device__ bool fit_line(const float4* __restrict__ pts, const Knn5& r, float* a, float* b) {
   float px[5], py[5], pz[5];
 #pragma unroll
   for (int j = 0; j < 5; j++) {
-    const float4 p = __ldg(G.pts + r.loc[j]);
+    const float4 p = __ldg(pts + r.loc[j]);
     px[j] = p.x; py[j] = p.y; pz[j] = p.z;
   }
   float cx = 0, cy = 0, cz = 0;
@@ -256,12 +274,12 @@ __device__ bool fit_line(const GridDev& G, const Knn5& r, float* a, float* b) {
   return true;
 }
 
-__device__ bool fit_plane(const GridDev& G, const Knn5& r, float sx, float sy, float sz, float* nrm, float* dist_out) {
+__device__ bool fit_plane(const float4* __restrict__ pts, const Knn5& r, float sx, float sy, float sz, float* nrm, float* dist_out) {
   double A[5][3], bb[5];
   float px[5], py[5], pz[5];
 #pragma unroll
   for (int j = 0; j < 5; j++) {
-    const float4 p = __ldg(G.pts + r.loc[j]);
+    const float4 p = __ldg(pts + r.loc[j]);
     px[j] = p.x; py[j] = p.y; pz[j] = p.z;
     A[j][0] = p.x; A[j][1] = p.y; A[j][2] = p.z;
     bb[j] = -1.0;
@@ -316,7 +334,7 @@ __global__ void __launch_bounds__(128) k_associate(AssocArgs A) {
         if (!knn5_grid(G, sel[0], sel[1], sel[2], thres, r)) continue;
         if (KIND == 0) {
           float a[3], b[3];
-          if (!fit_line(G, r, a, b)) continue;
+          if (!fit_line(G.pts, r, a, b)) continue;
           f1 = make_float4(a[0], a[1], a[2], b[0]);
           f2 = make_float4(b[1], b[2], 0.f, 0.f);
           // Estimator.h:71-83 FeatureLine::ComputeError at the association pose
@@ -336,7 +354,7 @@ __global__ void __launch_bounds__(128) k_associate(AssocArgs A) {
           found = 1;
         } else {
           float nrm[3], dist;
-          if (!fit_plane(G, r, sel[0], sel[1], sel[2], nrm, &dist)) continue;
+          if (!fit_plane(G.pts, r, sel[0], sel[1], sel[2], nrm, &dist)) continue;
           f1 = make_float4(sel[0], sel[1], sel[2], dist);
           f2 = make_float4(nrm[0], nrm[1], nrm[2], 0.f);
           double e[3];
@@ -430,21 +448,30 @@ __device__ __forceinline__ void group_merge(const Knn5& r, Knn5& m, unsigned mas
   }
 }
 
-template <int G>
-__device__ bool knn5_grid_group(const GridDev& Gd, float qx, float qy, float qz, float thres, Knn5& m, unsigned mask, int lg) {
-  Knn5 r;
-  knn_init(r);
-  knn_init(m);
-  int c[3], lo[3], hi[3], cube;
-  if (!locate(Gd, qx, qy, qz, c, lo, hi, cube)) return false;
-  if (Gd.global) {
-    if (!(__ldg(Gd.cube_count + cube) > Gd.min_cube_pts)) return false;
-  } else {
-    if (!(Gd.m > Gd.min_local_pts)) return false;
+// one level of the hash (fine or coarse): its sorted points, cell table and geometry
+struct GridLevel {
+  const float4* pts;
+  const int* cell_start;
+  int dim[3];
+  float cell;
+};
+
+__device__ __forceinline__ void scan_cells(const GridLevel& L, int c0, int c1, float qx, float qy, float qz, Knn5& r) {
+  const int s = __ldg(L.cell_start + c0), e = __ldg(L.cell_start + c1 + 1);
+  for (int k = s; k < e; k++) {
+    const float4 p = __ldg(L.pts + k);
+    const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+    const float d = (dx * dx + dy * dy) + dz * dz;
+    knn_push(r, d, __float_as_int(p.w), k);
   }
-  const float cellf = Gd.cell;
-  const int rmax = (int)ceilf(sqrtf(thres) / cellf) + 1;
-  for (int rr = 1; rr <= rmax; rr++) {
+}
+
+// shells rr0..rr1 of one level. Returns true when the search is finished (5-list final, or proven that no
+// acceptable 5-list exists); false when rr1 was exhausted without a verdict.
+template <int G>
+__device__ bool search_shells(const GridLevel& L, const int* c, const int* lo, const int* hi, float qx, float qy, float qz,
+                              float thres, int rr0, int rr1, Knn5& r, Knn5& m, unsigned mask, int lg) {
+  for (int rr = rr0; rr <= rr1; rr++) {
     const int side = 2 * rr + 1;
     const int nseg = rr == 1 ? 27 : 2 * side * side;
     for (int s = lg; s < nseg; s += G) {
@@ -468,8 +495,8 @@ __device__ bool knn5_grid_group(const GridDev& Gd, float qx, float qy, float qz,
         }
       }
       if (z < lo[2] || z > hi[2] || y < lo[1] || y > hi[1]) continue;
-      const int rowb = (z * Gd.dim[1] + y) * Gd.dim[0];
-      scan_range(Gd, rowb + x0, rowb + x1, qx, qy, qz, r);
+      const int rowb = (z * L.dim[1] + y) * L.dim[0];
+      scan_cells(L, rowb + x0, rowb + x1, qx, qy, qz, r);
     }
     group_merge<G>(r, m, mask, lg);
     // lane 0 carries the merged list forward, the others start the next shell empty (no duplicates)
@@ -477,11 +504,54 @@ __device__ bool knn5_grid_group(const GridDev& Gd, float qx, float qy, float qz,
     else knn_init(r);
     if (c[0] - rr < lo[0] && c[0] + rr > hi[0] && c[1] - rr < lo[1] && c[1] + rr > hi[1] && c[2] - rr < lo[2] &&
         c[2] + rr > hi[2])
-      break;
-    const float reach = fmaxf((float)rr * cellf - 1e-3f, 0.f);
+      return true;  // nothing left inside the searchable block of cells
+    const float reach = fmaxf((float)rr * L.cell - 1e-3f, 0.f);
     const float reach2 = reach * reach;
-    if (m.cnt == 5 && m.d[4] <= reach2) break;
-    if (reach2 >= thres) break;
+    if (m.cnt == 5 && m.d[4] <= reach2) return true;
+    if (reach2 >= thres) return true;
+  }
+  return false;
+}
+
+// Two-level search: the first kFineShells shells on the fine cells (where almost every query ends); queries
+// that are still open restart on the coarse level (cells kCoarse times larger), which bounds the number of
+// cell rows a far or hopeless query has to walk by kCoarse^2 per shell and kCoarse fewer shells.
+__device__ int g_fine_shells = 2;
+#define kFineShells g_fine_shells
+
+template <int G>
+__device__ bool knn5_grid_group(const GridDev& Gd, float qx, float qy, float qz, float thres, Knn5& m, unsigned mask, int lg,
+                                const float4*& base) {
+  base = Gd.pts;
+  Knn5 r;
+  knn_init(r);
+  knn_init(m);
+  int c[3], lo[3], hi[3], cube;
+  if (!locate(Gd, qx, qy, qz, c, lo, hi, cube)) return false;
+  if (Gd.global) {
+    if (!(__ldg(Gd.cube_count + cube) > Gd.min_cube_pts)) return false;
+  } else {
+    if (!(Gd.m > Gd.min_local_pts)) return false;
+  }
+  GridLevel L0;
+  L0.pts = Gd.pts; L0.cell_start = Gd.cell_start; L0.cell = Gd.cell;
+  L0.dim[0] = Gd.dim[0]; L0.dim[1] = Gd.dim[1]; L0.dim[2] = Gd.dim[2];
+  const int rmax = (int)ceilf(sqrtf(thres) / Gd.cell) + 1;
+  const bool two_level = Gd.pts2 != nullptr && rmax > kFineShells;
+  bool done = search_shells<G>(L0, c, lo, hi, qx, qy, qz, thres, 1, two_level ? kFineShells : rmax, r, m, mask, lg);
+  if (!done && two_level) {
+    GridLevel L1;
+    L1.pts = Gd.pts2; L1.cell_start = Gd.cell_start2; L1.cell = Gd.cell * (float)Gd.coarse;
+    int c2[3], lo2[3], hi2[3];
+    for (int a = 0; a < 3; a++) {
+      L1.dim[a] = Gd.dim2[a];
+      c2[a] = c[a] / Gd.coarse; lo2[a] = lo[a] / Gd.coarse; hi2[a] = hi[a] / Gd.coarse;
+    }
+    knn_init(r);
+    knn_init(m);
+    const int rmax2 = (int)ceilf(sqrtf(thres) / L1.cell) + 1;
+    search_shells<G>(L1, c2, lo2, hi2, qx, qy, qz, thres, 1, rmax2, r, m, mask, lg);
+    base = Gd.pts2;  // the 5-list now indexes the coarse-sorted copy
   }
   return m.cnt == 5 && m.d[4] < thres;
 }
@@ -529,12 +599,13 @@ __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
       for (int mp = 0; mp < 2 && !found; mp++) {
         const GridDev& Gd = A.G[mp];
         if (!Gd.valid) continue;
-        if (!knn5_grid_group<G>(Gd, sel[0], sel[1], sel[2], thres, r, mask, lg)) continue;  // group-uniform
+        const float4* base;
+        if (!knn5_grid_group<G>(Gd, sel[0], sel[1], sel[2], thres, r, mask, lg, base)) continue;  // group-uniform
         int ok = 0;
         if (lg == 0) {
           if (KIND == 0) {
             float a[3], b[3];
-            if (fit_line(Gd, r, a, b)) {
+            if (fit_line(base, r, a, b)) {
               f1 = make_float4(a[0], a[1], a[2], b[0]);
               f2 = make_float4(b[1], b[2], 0.f, 0.f);
               double P[3];
@@ -554,7 +625,7 @@ __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
             }
           } else {
             float nrm[3], dist;
-            if (fit_plane(Gd, r, sel[0], sel[1], sel[2], nrm, &dist)) {
+            if (fit_plane(base, r, sel[0], sel[1], sel[2], nrm, &dist)) {
               f1 = make_float4(sel[0], sel[1], sel[2], dist);
               f2 = make_float4(nrm[0], nrm[1], nrm[2], 0.f);
               double e[3];
@@ -643,6 +714,7 @@ __global__ void __launch_bounds__(256) k_export_features(const float4* __restric
 using namespace mml;
 
 // ---------------------------------------------------------------- host side
+constexpr int kCoarseFactor = 4;
 static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, float cell_hint);
 
 int mml_map_set_device(mml_ctx* ctx, int kind, const float4* pts_d, int m, const int* cen3, float cell_hint) {
@@ -666,7 +738,10 @@ static GridDev grid_dev(const GridMap& M, int kind) {
   G.pts = M.pts.as<float4>();
   G.cell_start = M.cell_start.as<int>();
   G.cube_count = M.cube_count.as<int>();
-  for (int a = 0; a < 3; a++) { G.org[a] = M.org_d[a]; G.dim[a] = M.dim[a]; G.cen[a] = M.cen[a]; G.cube_lo[a] = M.cube_lo[a]; }
+  G.pts2 = M.coarse > 1 ? M.pts2.as<float4>() : nullptr;
+  G.cell_start2 = M.cell_start2.as<int>();
+  G.coarse = M.coarse;
+  for (int a = 0; a < 3; a++) { G.org[a] = M.org_d[a]; G.dim[a] = M.dim[a]; G.cen[a] = M.cen[a]; G.cube_lo[a] = M.cube_lo[a]; G.dim2[a] = M.dim2[a]; }
   G.inv_cell = 1.0 / (double)M.cell;
   G.cell = M.cell;
   G.m = M.m;
@@ -687,6 +762,7 @@ static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, floa
     if (M.global) {
       int k = (int)floor(50.0 / (double)cell + 0.5);
       if (k < 1) k = 1;
+      if (k >= 2 * kCoarseFactor) k = (k / kCoarseFactor) * kCoarseFactor;  // cube blocks stay aligned on the coarse level
       M.k_per_cube = k;
       M.cell = (float)(50.0 / k);
       int lo[3], hi[3];
@@ -772,6 +848,28 @@ static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, floa
   MML_CUDA(ctx, cudaMemsetAsync(ctx->tmp_e.p, 0, sizeof(int) * (size_t)M.ncell, st));
   k_map_scatter<<<div_up(m, 256), 256, 0, st>>>(pts_d, m, cell_of, cell_start, ctx->tmp_e.as<int>(), M.pts.as<float4>());
   MML_LAUNCHED(ctx);
+  // ---- coarse level
+  M.coarse = 1;
+  const bool aligned = (!M.global || (M.k_per_cube % kCoarseFactor == 0)) && !getenv("MML_NO_COARSE");
+  if (aligned && (M.dim[0] > kCoarseFactor || M.dim[1] > kCoarseFactor || M.dim[2] > kCoarseFactor)) {
+    M.coarse = kCoarseFactor;
+    for (int a = 0; a < 3; a++) M.dim2[a] = (M.dim[a] + kCoarseFactor - 1) / kCoarseFactor;
+    const long long ncell2 = (long long)M.dim2[0] * M.dim2[1] * M.dim2[2];
+    MML_CUDA(ctx, M.cell_start2.reserve(sizeof(int) * ((size_t)ncell2 + 1)));
+    MML_CUDA(ctx, M.pts2.reserve(sizeof(float4) * (size_t)m));
+    MML_CUDA(ctx, ctx->tmp_b.reserve(sizeof(int) * (size_t)m));
+    int* cell_of2 = ctx->tmp_b.as<int>();
+    int* cs2 = M.cell_start2.as<int>();
+    MML_CUDA(ctx, cudaMemsetAsync(cs2, 0, sizeof(int) * ((size_t)ncell2 + 1), st));
+    k_map_coarse_count<<<div_up(m, 256), 256, 0, st>>>(cell_of, m, M.dim[0], M.dim[1], kCoarseFactor, M.dim2[0], M.dim2[1],
+                                                       cell_of2, cs2);
+    MML_LAUNCHED(ctx);
+    k_exclusive_scan<<<1, kScanThreads, 0, st>>>(cs2, nullptr, (int)(ncell2 + 1), nullptr);
+    MML_LAUNCHED(ctx);
+    MML_CUDA(ctx, cudaMemsetAsync(ctx->tmp_e.p, 0, sizeof(int) * (size_t)ncell2, st));
+    k_map_scatter<<<div_up(m, 256), 256, 0, st>>>(pts_d, m, cell_of2, cs2, ctx->tmp_e.as<int>(), M.pts2.as<float4>());
+    MML_LAUNCHED(ctx);
+  }
   MML_CUDA(ctx, cudaGetLastError());
   M.valid = true;
   return MML_OK;
@@ -842,4 +940,8 @@ int mml_export_features(mml_ctx* ctx, int kind, int nq, double* out_dev) {
   MML_LAUNCHED(ctx);
   MML_CUDA(ctx, cudaGetLastError());
   return MML_OK;
+}
+
+extern "C" int mml_debug_set_fine_shells(int v) {
+  return cudaMemcpyToSymbol(mml::g_fine_shells, &v, sizeof(int)) == cudaSuccess ? 0 : -3;
 }

@@ -79,6 +79,8 @@ int mml_ctx_destroy(mml_ctx* c) {
     c->maps[k].pts.release();
     c->maps[k].cell_start.release();
     c->maps[k].cube_count.release();
+    c->maps[k].pts2.release();
+    c->maps[k].cell_start2.release();
   }
   c->pin_in.release();
   c->pin_out.release();
@@ -574,3 +576,26 @@ int mml_dev_upload(mml_ctx* c, void* dst_dev, const void* src, size_t bytes) {
 }
 
 }  // extern "C"
+
+// test / debug view of a built map level: cell-sorted points (xyz + original index) and the cell table
+extern "C" int mml_map_dump(mml_ctx* c, int kind, int level, float* pts_out /*m x 4*/, int* cell_start_out /*ncell+1*/) {
+  if (!c || kind < 0 || kind > 3) return MML_ERR_INVALID;
+  const mml::GridMap& M = c->maps[kind];
+  if (!M.valid) return MML_ERR_STATE;
+  cudaSetDevice(c->device);
+  const long long ncell = level == 0 ? M.ncell : (long long)M.dim2[0] * M.dim2[1] * M.dim2[2];
+  const void* p = level == 0 ? M.pts.p : M.pts2.p;
+  const void* cs = level == 0 ? M.cell_start.p : M.cell_start2.p;
+  if (level == 1 && M.coarse <= 1) return MML_ERR_STATE;
+  MML_CUDA(c, cudaMemcpyAsync(pts_out, p, sizeof(float) * 4 * (size_t)M.m, cudaMemcpyDeviceToHost, c->stream));
+  MML_CUDA(c, cudaMemcpyAsync(cell_start_out, cs, sizeof(int) * ((size_t)ncell + 1), cudaMemcpyDeviceToHost, c->stream));
+  MML_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MML_OK;
+}
+extern "C" int mml_map_dims(mml_ctx* c, int kind, int* dims7 /*dim xyz, dim2 xyz, coarse*/, double* org3) {
+  if (!c || kind < 0 || kind > 3) return MML_ERR_INVALID;
+  const mml::GridMap& M = c->maps[kind];
+  for (int a = 0; a < 3; a++) { dims7[a] = M.dim[a]; dims7[3 + a] = M.dim2[a]; org3[a] = M.org_d[a]; }
+  dims7[6] = M.coarse;
+  return MML_OK;
+}

@@ -77,6 +77,9 @@ struct GridMap {
   DevBuf pts;                // float4[m] cell-sorted (w = original index bits)
   DevBuf cell_start;         // int[ncell+1]
   DevBuf cube_count;         // int[kNumCubes] points per 50 m cube (global kinds)
+  int coarse = 1;            // coarse level: cells `coarse` times larger (1 = none)
+  int dim2[3] = {0, 0, 0};
+  DevBuf pts2, cell_start2;
   bool valid = false;
 };
 

@@ -94,18 +94,12 @@ __global__ void __launch_bounds__(kSvThreads) k_split_voxel(SplitVoxelArgs A) {
       if (lane == 31) s_base = xs;
     }
     __syncthreads();
+    // compact source indices first (they live in the key buffer until the keys are built) ...
     int pos = s_warp[warp] + (x - mine);
     if (mine) {
       for (int i = b0; i < b1; i++) {
         if (A.label[i] != want) continue;
-        if (pos < kSvCap) {
-          float4 p = A.pts[i];
-          if (A.U.enabled) p = undistort_point(p, (double)A.s[i], A.U);
-          scratch[pos] = p;
-          const unsigned e[3] = {sv_f2ord(p.x), sv_f2ord(p.y), sv_f2ord(p.z)};
-#pragma unroll
-          for (int c = 0; c < 3; c++) { mn[c] = min(mn[c], e[c]); mx[c] = max(mx[c], e[c]); }
-        }
+        if (pos < kSvCap) keys[pos] = (unsigned long long)(unsigned)i;
         pos++;
       }
     }
@@ -113,6 +107,17 @@ __global__ void __launch_bounds__(kSvThreads) k_split_voxel(SplitVoxelArgs A) {
   }
   int cnt = s_base;
   if (cnt > kSvCap) { overflow = true; cnt = kSvCap; }
+  // ... then undistort with the points dealt out evenly over the CTA (the labelled points cluster, so
+  // doing this inside the slice loop would leave the whole CTA waiting for a few busy lanes)
+  for (int k = tid; k < cnt; k += kSvThreads) {
+    const int i = (int)keys[k];
+    float4 p = A.pts[i];
+    if (A.U.enabled) p = undistort_point(p, (double)A.s[i], A.U);
+    scratch[k] = p;
+    const unsigned e[3] = {sv_f2ord(p.x), sv_f2ord(p.y), sv_f2ord(p.z)};
+#pragma unroll
+    for (int c = 0; c < 3; c++) { mn[c] = min(mn[c], e[c]); mx[c] = max(mx[c], e[c]); }
+  }
 #pragma unroll
   for (int c = 0; c < 3; c++) {
 #pragma unroll

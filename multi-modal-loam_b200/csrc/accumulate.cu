@@ -30,7 +30,7 @@ struct EstState {
   float thres;
   int n_line, n_plane;
   // control
-  int done_outer, done_inner, outer_it, inner_it, first, total_inner, is_degenerate;
+  int done_outer, done_inner, outer_it, inner_it, first, total_inner, is_degenerate, outer_next;
   int max_outer, max_inner;
   double lidar_m, w_tan, huber_a, thres_sched[3];
   // trust-region state (Ceres 2.1 TrustRegionMinimizer + DoglegStrategy)
@@ -459,8 +459,9 @@ __host__ __device__ void dogleg_update(EstState& S, const double* out28) {
 
 // ---------------------------------------------------------------- outer loop bookkeeping
 // EST.cpp:1212 vector2double + EST.cpp:1268-1270 T_wl + thres_dist schedule (EST.cpp:1207, 1377-1381)
-__global__ void k_est_begin_outer(EstState* S, int it) {
+__global__ void k_est_begin_outer(EstState* S) {
   if (threadIdx.x != 0 || S->done_outer) return;
+  const int it = S->outer_next;
   S->outer_it = it;
   const Quat Q = {S->Q[0], S->Q[1], S->Q[2], S->Q[3]};
   S->x[0] = S->P[0]; S->x[1] = S->P[1]; S->x[2] = S->P[2];
@@ -508,6 +509,7 @@ __global__ void k_est_end_outer(EstState* S, const double* assoc_stats) {
   const double d0 = S->t_before[0] - S->P[0], d1 = S->t_before[1] - S->P[1], d2 = S->t_before[2] - S->P[2];
   const double deltaT = sqrt((d0 * d0 + d1 * d1) + d2 * d2);
   if ((deltaR < 0.05 && deltaT < 0.05) || (S->outer_it + 1) == S->max_outer) S->done_outer = 1;
+  S->outer_next = S->outer_it + 1;
 }
 
 }  // namespace mml
@@ -570,7 +572,8 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
   MML_CUDA(ctx, ctx->assoc_stats.reserve(512));
   MML_CUDA(ctx, ctx->f_line.reserve(sizeof(float4) * 3 * (size_t)(cap_corner > 0 ? cap_corner : 1)));
   MML_CUDA(ctx, ctx->f_plane.reserve(sizeof(float4) * 3 * (size_t)(cap_surf > 0 ? cap_surf : 1)));
-  MML_CUDA(ctx, ctx->tmp_c.reserve(sizeof(double) * 8 * (size_t)(div_up((cap_corner > cap_surf ? cap_corner : cap_surf) + 1, 4) + 1) + 64));
+  MML_CUDA(ctx, ctx->assoc_part[0].reserve(sizeof(double) * 8 * (size_t)(div_up(cap_corner + 1, 4) + 1) + 64));
+  MML_CUDA(ctx, ctx->assoc_part[1].reserve(sizeof(double) * 8 * (size_t)(div_up(cap_surf + 1, 4) + 1) + 64));
   EstState* S = ctx->est_state.as<EstState>();
 
   // host-side initial state
@@ -603,7 +606,7 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
   mix((long long)(size_t)S); mix((long long)(size_t)ctx->f_line.p); mix((long long)(size_t)ctx->f_plane.p);
   mix((long long)(size_t)ctx->q_corner.p); mix((long long)(size_t)ctx->q_surf.p); mix((long long)(size_t)cnt_dev);
   mix((long long)(size_t)ctx->acc_partials.p); mix((long long)(size_t)ctx->acc_out.p); mix((long long)(size_t)ctx->tmp_c.p);
-  mix((long long)(size_t)ctx->assoc_stats.p); mix(cap_corner); mix(cap_surf); mix(prm->max_outer); mix(prm->max_inner);
+  mix((long long)(size_t)ctx->assoc_stats.p); mix((long long)(size_t)ctx->assoc_part[0].p); mix((long long)(size_t)ctx->assoc_part[1].p); mix(cap_corner); mix(cap_surf); mix(prm->max_outer); mix(prm->max_inner);
   for (int k = 0; k < 4; k++) {
     const GridMap& M = ctx->maps[k];
     mix(M.valid); mix(M.coarse); mix((long long)(size_t)M.pts2.p); mix((long long)(size_t)M.cell_start2.p); mix((long long)(size_t)M.pts.p); mix((long long)(size_t)M.cell_start.p); mix(M.m); mix(M.ncell);
@@ -611,22 +614,31 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
     mix((long long)(M.org_d[0] * 1e6)); mix((long long)(M.org_d[1] * 1e6)); mix((long long)(M.org_d[2] * 1e6));
     mix(M.cen[0]); mix(M.cen[1]); mix(M.cen[2]);
   }
+  // One outer iteration = one graph: begin | line association || plane association (two captured streams) |
+  // 1 + max_inner evaluations, each fused with its dogleg update | end. The host replays it until the device
+  // reports convergence; the first two iterations are enqueued back to back (nearly every scan needs both), so
+  // a typical scan costs two short synchronisations and no idle no-op launches for iterations 3-5.
   if (!ctx->est_graph || ctx->est_graph_key != key) {
     if (ctx->est_graph) { cudaGraphExecDestroy(ctx->est_graph); ctx->est_graph = nullptr; }
     cudaGraph_t graph = nullptr;
     const long long launches_before = ctx->launches;
+    cudaStream_t st2 = ctx->stream2;
     MML_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     int rc = MML_OK;
-    for (int it = 0; it < prm->max_outer && rc == MML_OK; it++) {
-      k_est_begin_outer<<<1, 32, 0, st>>>(S, it);
-      MML_LAUNCHED(ctx);
-      rc = mml_associate_launch(ctx, 0, nullptr, 0.f, S->T_wl, &S->thres, &S->done_outer, cnt_dev, cap_corner);
-      if (rc == MML_OK) rc = mml_associate_launch(ctx, 1, nullptr, 0.f, S->T_wl, &S->thres, &S->done_outer, cnt_dev + 1, cap_surf);
-      for (int k = 0; k <= prm->max_inner && rc == MML_OK; k++)
-        rc = mml_accumulate_launch(ctx, nullptr, nullptr, 0, 0, 0, S, cnt_dev, cap_corner, cap_surf, nullptr, nullptr);
-      k_est_end_outer<<<1, 32, 0, st>>>(S, ctx->assoc_stats.as<double>());
-      MML_LAUNCHED(ctx);
-    }
+    k_est_begin_outer<<<1, 32, 0, st>>>(S);
+    MML_LAUNCHED(ctx);
+    cudaEventRecord(ctx->ev_fork, st);
+    cudaStreamWaitEvent(st2, ctx->ev_fork, 0);
+    ctx->stream = st2;
+    rc = mml_associate_launch(ctx, 1, nullptr, 0.f, S->T_wl, &S->thres, &S->done_outer, cnt_dev + 1, cap_surf);
+    ctx->stream = st;
+    if (rc == MML_OK) rc = mml_associate_launch(ctx, 0, nullptr, 0.f, S->T_wl, &S->thres, &S->done_outer, cnt_dev, cap_corner);
+    cudaEventRecord(ctx->ev_join, st2);
+    cudaStreamWaitEvent(st, ctx->ev_join, 0);
+    for (int k = 0; k <= prm->max_inner && rc == MML_OK; k++)
+      rc = mml_accumulate_launch(ctx, nullptr, nullptr, 0, 0, 0, S, cnt_dev, cap_corner, cap_surf, nullptr, nullptr);
+    k_est_end_outer<<<1, 32, 0, st>>>(S, ctx->assoc_stats.as<double>());
+    MML_LAUNCHED(ctx);
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
     ctx->est_launches_per_graph = ctx->launches - launches_before;
     ctx->launches = launches_before;
@@ -636,10 +648,18 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
     cudaGraphDestroy(graph);
     ctx->est_graph_key = key;
   }
-  MML_CUDA(ctx, cudaGraphLaunch(ctx->est_graph, st));
-  ctx->launches += ctx->est_launches_per_graph;
-  MML_CUDA(ctx, cudaMemcpyAsync(h, S, sizeof(EstState), cudaMemcpyDeviceToHost, st));
-  MML_CUDA(ctx, cudaStreamSynchronize(st));
+  int launched = 0;
+  while (launched < prm->max_outer) {
+    const int burst = launched == 0 && prm->max_outer > 1 ? 2 : 1;
+    for (int b = 0; b < burst; b++) {
+      MML_CUDA(ctx, cudaGraphLaunch(ctx->est_graph, st));
+      ctx->launches += ctx->est_launches_per_graph;
+      launched++;
+    }
+    MML_CUDA(ctx, cudaMemcpyAsync(h, S, sizeof(EstState), cudaMemcpyDeviceToHost, st));
+    MML_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h->done_outer) break;
+  }
   for (int i = 0; i < 3; i++) P3[i] = h->P[i];
   for (int i = 0; i < 4; i++) q4[i] = h->Q[i];
   if (stats) {

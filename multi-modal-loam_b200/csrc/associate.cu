@@ -424,27 +424,27 @@ __device__ __forceinline__ unsigned group_mask() {
 
 template <int G>
 __device__ __forceinline__ void group_merge(const Knn5& r, Knn5& m, unsigned mask, int lg) {
+  // five arg-min rounds over the heads of the lanes' sorted lists. Squared distances are >= +0, so their
+  // bit patterns order like unsigned integers: one redux for the distance, one for the index tie-break.
   int ptr = 0;
   m.cnt = 0;
+  const int my_lane = threadIdx.x & 31;
 #pragma unroll
   for (int k = 0; k < 5; k++) {
-    float d = ptr == 0 ? r.d[0] : ptr == 1 ? r.d[1] : ptr == 2 ? r.d[2] : ptr == 3 ? r.d[3] : ptr == 4 ? r.d[4] : INFINITY;
-    int id = ptr == 0 ? r.id[0] : ptr == 1 ? r.id[1] : ptr == 2 ? r.id[2] : ptr == 3 ? r.id[3] : ptr == 4 ? r.id[4] : 0x7fffffff;
-    int loc = ptr == 0 ? r.loc[0] : ptr == 1 ? r.loc[1] : ptr == 2 ? r.loc[2] : ptr == 3 ? r.loc[3] : ptr == 4 ? r.loc[4] : -1;
-    int src = lg;
-#pragma unroll
-    for (int s = G / 2; s > 0; s >>= 1) {
-      const float od = __shfl_xor_sync(mask, d, s, G);
-      const int oid = __shfl_xor_sync(mask, id, s, G);
-      const int oloc = __shfl_xor_sync(mask, loc, s, G);
-      const int osrc = __shfl_xor_sync(mask, src, s, G);
-      // total order on (d, id, src): identical on both sides of the exchange
-      const bool take = od < d || (od == d && (oid < id || (oid == id && osrc < src)));
-      if (take) { d = od; id = oid; loc = oloc; src = osrc; }
-    }
-    m.d[k] = d; m.id[k] = id; m.loc[k] = loc;
-    if (d < INFINITY) m.cnt++;
-    if (src == lg) ptr++;
+    const float d = ptr == 0 ? r.d[0] : ptr == 1 ? r.d[1] : ptr == 2 ? r.d[2] : ptr == 3 ? r.d[3] : ptr == 4 ? r.d[4] : INFINITY;
+    const int id = ptr == 0 ? r.id[0] : ptr == 1 ? r.id[1] : ptr == 2 ? r.id[2] : ptr == 3 ? r.id[3] : ptr == 4 ? r.id[4] : 0x7fffffff;
+    const int loc = ptr == 0 ? r.loc[0] : ptr == 1 ? r.loc[1] : ptr == 2 ? r.loc[2] : ptr == 3 ? r.loc[3] : ptr == 4 ? r.loc[4] : -1;
+    const unsigned db = __float_as_uint(d);
+    const unsigned dmin = __reduce_min_sync(mask, db);
+    const unsigned idc = db == dmin ? (unsigned)id : 0xffffffffu;
+    const unsigned idmin = __reduce_min_sync(mask, idc);
+    const unsigned win = __ballot_sync(mask, db == dmin && (unsigned)id == idmin);
+    const int src = __ffs(win) - 1;  // lowest winning lane (several only for the INF padding entries)
+    m.d[k] = __uint_as_float(dmin);
+    m.id[k] = (int)idmin;
+    m.loc[k] = __shfl_sync(mask, loc, src);
+    if (dmin < 0x7f800000u) m.cnt++;
+    if (my_lane == src) ptr++;
   }
 }
 
@@ -834,7 +834,8 @@ static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, floa
     MML_CUDA(ctx, cudaStreamSynchronize(st));
     if (nz == 0) nz = 1;
     const double occ = (double)m / (double)nz;
-    cell = (float)fmin(fmax((double)M.cell * sqrt(3.0 / occ), 0.05), 5.0);
+    static const double target_occ = getenv("MML_CELL_OCC") ? atof(getenv("MML_CELL_OCC")) : 3.0;
+    cell = (float)fmin(fmax((double)M.cell * sqrt(target_occ / occ), 0.05), 5.0);
   }
   while (!layout(cell)) cell *= 1.25f;
 
@@ -889,7 +890,7 @@ int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres,
   // assoc_stats layout (doubles): [0..7] line moments/count, [8..15] plane moments/count,
   // then ints: n_line, n_plane, tickets
   MML_CUDA(ctx, ctx->assoc_stats.reserve(512));
-  MML_CUDA(ctx, ctx->tmp_c.reserve(sizeof(double) * 8 * (size_t)grid + 64));
+  MML_CUDA(ctx, ctx->assoc_part[kind].reserve(sizeof(double) * 8 * (size_t)grid + 64));
   AssocArgs A;
   memset(&A, 0, sizeof(A));
   A.q = (kind == 0 ? ctx->q_corner : ctx->q_surf).as<float4>();
@@ -906,7 +907,7 @@ int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres,
   int* ints = reinterpret_cast<int*>(stats + 16);
   A.n_feat_out = ints + kind;
   A.ticket = reinterpret_cast<unsigned*>(ints + 4 + kind);
-  A.moment_partials = ctx->tmp_c.as<double>();
+  A.moment_partials = ctx->assoc_part[kind].as<double>();
   A.gate = gate;
   A.T_dev = T_dev;
   A.thres_dev = thres_dev;

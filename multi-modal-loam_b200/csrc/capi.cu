@@ -57,6 +57,9 @@ int mml_ctx_create(int device, int stream_count, mml_ctx** out) {
     cudaStream_t s;
     if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess) c->extra_streams.push_back(s);
   }
+  cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
   *out = c;
@@ -87,6 +90,11 @@ int mml_ctx_destroy(mml_ctx* c) {
   c->pin_small.release();
   c->pin_flags.release();
   for (auto s : c->extra_streams) cudaStreamDestroy(s);
+  c->assoc_part[0].release();
+  c->assoc_part[1].release();
+  cudaEventDestroy(c->ev_fork);
+  cudaEventDestroy(c->ev_join);
+  cudaStreamDestroy(c->stream2);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->stream);

@@ -90,6 +90,8 @@ struct EstDev;  // device-side solver state (accumulate.cu)
 struct mml_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;       // second captured stream (plane association runs beside line association)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<cudaStream_t> extra_streams;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
@@ -115,6 +117,7 @@ struct mml_ctx {
   mml::DevBuf f_line, f_plane;    // compact features (see associate.cu)
   mml::DevBuf acc_partials, acc_out, est_state;
   mml::DevBuf assoc_stats;        // ints + doubles
+  mml::DevBuf assoc_part[2];      // per-CTA moment partials of the line / plane association
   cudaGraphExec_t est_graph = nullptr;
   long long est_graph_key = 0;
   long long est_launches_per_graph = 0;

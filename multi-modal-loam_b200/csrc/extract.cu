@@ -506,6 +506,76 @@ __global__ void __launch_bounds__(kSelThreads) k_select_par(const uint16_t* __re
   if (n >= 11) {
     const int w = (attr_line[n - 6] & A_W3) ? 3 : 2;  // thNumCurvSize left by the last point (FE.cpp:424-428)
     const bool par = n >= kMinParallelN;
+    // ---- phase C: stride walk (FE.cpp:543-650) as a scan of transition functions over 256 contiguous chunks
+    {
+      const int span = n - 10;  // indices 5 .. n-6
+      const int chunk = (span + kSelThreads - 1) / kSelThreads;
+      const int a0 = 5 + tid * chunk, a1 = min(a0 + chunk, n - 5);
+      unsigned fn = 0xE4u;  // identity: state s -> s
+      {
+        int st0 = 0, st1 = 1, st2 = 2, st3 = 3;
+        for (int i = a0; i < a1; i++) {
+          const int jump = (attr8[i] & A_RF) ? 3 : 0;
+          st0 = st0 ? st0 - 1 : jump;
+          st1 = st1 ? st1 - 1 : jump;
+          st2 = st2 ? st2 - 1 : jump;
+          st3 = st3 ? st3 - 1 : jump;
+        }
+        if (a0 < a1) fn = (unsigned)st0 | ((unsigned)st1 << 2) | ((unsigned)st2 << 4) | ((unsigned)st3 << 6);
+      }
+      // inclusive scan of composition within the warp, then across the 8 warps
+      unsigned inc = fn;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned prev = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc = compose4(prev, inc);
+      }
+      if (lane == 31) s_warp_fn[warp] = inc;
+      s_fn[tid] = inc;
+      __syncthreads();
+      unsigned pre = 0xE4u;  // composition of all chunks before this thread's
+      for (int wv = 0; wv < warp; wv++) pre = compose4(pre, s_warp_fn[wv]);
+      if (lane > 0) pre = compose4(pre, s_fn[tid - 1]);
+      int sst = (int)(pre & 3u);  // state entering index 5 is 0 (index 5 is visited)
+      for (int i = a0; i < a1; i++) {
+        if (sst == 0) {
+          const unsigned a = attr8[i];
+          if (a & A_C150) atomicOr(&v150[i >> 5], 1u << (i & 31));
+          sst = (a & A_RF) ? 3 : 0;
+        } else {
+          sst--;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- repack the attribute byte for the selection loops: bits 0-2 CAND/FAR/ANGLE, bit 3 C300, bits 4-5 /
+    //      6-7 = how many right / left neighbours a pick at this index suppresses (the walks of FE.cpp:492-517
+    //      with thNumCurvSize, the 0.02 gap test and the far test folded in). Copy 3 of the flags is the scratch.
+    {
+      uint8_t* tmp = flags4 + 3 * (size_t)NF;
+      for (int i = tid; i < n; i += kSelThreads) {
+        const unsigned a = attr8[i];
+        int rr = 0, ll = 0;
+        if (i >= 5 && i < n - 5 && !(a & A_FAR)) {
+          for (int l = 1; l <= w; l++) {
+            if (attr8[i + l - 1] & A_GAP) break;
+            rr = l;
+          }
+          for (int l = 1; l <= w; l++) {
+            if (attr8[i - l] & A_GAP) break;
+            ll = l;
+          }
+        }
+        tmp[i] = (uint8_t)((a & 7u) | (((a >> 4) & 1u) << 3) | ((unsigned)rr << 4) | ((unsigned)ll << 6));
+      }
+      __syncthreads();
+      for (int i = tid; i < n; i += kSelThreads) {
+        attr8[i] = tmp[i];
+        tmp[i] = 0;
+      }
+      __syncthreads();
+    }
+    constexpr unsigned B_CAND = 1u, B_FAR = 2u, B_ANGLE = 4u, B_C300 = 8u;
     // ---- phase 1: flat selection. parallel: lane (j,h) simulates part j with h pre-marked head points;
     //      short lines: lane 0 runs all parts in order on copy 0 (spills written directly)
     const int n_sim = par ? kParts * 4 : 1;
@@ -524,21 +594,22 @@ __global__ void __launch_bounds__(kSelThreads) k_select_par(const uint16_t* __re
         int rs = 0, lsp = 0;
         const int* so = sort_ind + ls + sp;
         const int* ro = refl_ind + ls + sp;
+        int ind_next = __ldg(so);
         for (int k = 0; k < m; k++) {  // FE.cpp:483-519
-          const int ind = __ldg(so + k);
-          if (F[ind] != 0) continue;
+          const int ind = ind_next;
+          if (k + 1 < m) ind_next = __ldg(so + k + 1);
           const unsigned a = attr8[ind];
-          if (a & A_CAND) {
+          if (F[ind] == 0 && (a & B_CAND)) {
             F[ind] = 3;
-            if (!(a & A_FAR)) {
-              for (int l = 1; l <= w; l++) {
-                if (attr8[ind + l - 1] & A_GAP) break;
+            const int rr = (a >> 4) & 3, ll = (a >> 6) & 3;
+#pragma unroll
+            for (int l = 1; l <= 3; l++) {
+              if (l <= rr) {
                 const int idx = ind + l;
                 if (idx <= hi) F[idx] = 1;
                 else rs = max(rs, idx - hi);
               }
-              for (int l = 1; l <= w; l++) {
-                if (attr8[ind - l] & A_GAP) break;
+              if (l <= ll) {
                 const int idx = ind - l;
                 if (idx >= lo) F[idx] = 1;
                 else lsp = max(lsp, lo - idx);
@@ -549,14 +620,14 @@ __global__ void __launch_bounds__(kSelThreads) k_select_par(const uint16_t* __re
         int smallest = 1, sharpest = 1;
         for (int k = 0; k < m; k++) {  // FE.cpp:521-539
           const int ind = __ldg(so + k);
+          const int idx = __ldg(ro + k);
           const unsigned a = attr8[ind];
           const int f = F[ind];
-          if ((f == 3 && smallest <= 1) || (f == 3 && (a & A_FAR)) || (a & A_ANGLE)) {
+          if ((f == 3 && (smallest <= 1 || (a & B_FAR))) || (a & B_ANGLE)) {
             smallest++;
             F[ind] = 2;
           }
-          const int idx = __ldg(ro + k);
-          if (sharpest <= 3 && (attr8[idx] & A_C300)) {
+          if (sharpest <= 3 && (attr8[idx] & B_C300)) {
             sharpest++;
             F[idx] = 4;  // 300
           }
@@ -565,45 +636,6 @@ __global__ void __launch_bounds__(kSelThreads) k_select_par(const uint16_t* __re
           s_out_h[j][h] = (unsigned char)min(rs, 3);
           s_lsp[j][h] = (unsigned char)min(lsp, 3);
         }
-      }
-    }
-    // ---- phase C: stride walk as a scan of transition functions over 256 contiguous chunks
-    const int span = n - 10;  // indices 5 .. n-6
-    const int chunk = (span + kSelThreads - 1) / kSelThreads;
-    const int a0 = 5 + tid * chunk, a1 = min(a0 + chunk, n - 5);
-    unsigned fn = 0xE4u;  // identity: state s -> s
-    {
-      int st0 = 0, st1 = 1, st2 = 2, st3 = 3;
-      for (int i = a0; i < a1; i++) {
-        const int jump = (attr8[i] & A_RF) ? 3 : 0;
-        st0 = st0 ? st0 - 1 : jump;
-        st1 = st1 ? st1 - 1 : jump;
-        st2 = st2 ? st2 - 1 : jump;
-        st3 = st3 ? st3 - 1 : jump;
-      }
-      if (a0 < a1) fn = (unsigned)st0 | ((unsigned)st1 << 2) | ((unsigned)st2 << 4) | ((unsigned)st3 << 6);
-    }
-    // inclusive scan of composition within the warp, then across the 8 warps
-    unsigned inc = fn;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned prev = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc = compose4(prev, inc);
-    }
-    if (lane == 31) s_warp_fn[warp] = inc;
-    s_fn[tid] = inc;
-    __syncthreads();
-    unsigned pre = 0xE4u;  // composition of all chunks before this thread's
-    for (int wv = 0; wv < warp; wv++) pre = compose4(pre, s_warp_fn[wv]);
-    if (lane > 0) pre = compose4(pre, s_fn[tid - 1]);
-    int s = (int)(pre & 3u);  // state entering index 5 is 0 (index 5 is visited)
-    for (int i = a0; i < a1; i++) {
-      if (s == 0) {
-        const unsigned a = attr8[i];
-        if (a & A_C150) atomicOr(&v150[i >> 5], 1u << (i & 31));
-        s = (a & A_RF) ? 3 : 0;
-      } else {
-        s--;
       }
     }
     __syncthreads();

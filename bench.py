@@ -41,7 +41,7 @@ BYTES_PER_FEATURE_EVAL = 64        # 16 B query + 48 B feature record
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=150)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--livox-pts", type=int, default=24000)
@@ -142,7 +142,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -189,11 +189,14 @@ def cpu_loop(orc, synth, scans, Ts, first, n, ms, mc, threads):
     prm = orc.est_params(threads=threads)
     odo = Odometry(Ts[first], Ts[first - 1] if first > 0 else Ts[first])
     poses = []
+    t_fe = 0.0
     t0 = time.perf_counter()
     for k in range(first, first + n):
         x, line, s = scans[k]
         Tp, delta = odo.predict()
+        t1 = time.perf_counter()
         label = orc.extract_scan(x, line, N_LINES, threads=threads)
+        t_fe += time.perf_counter() - t1
         xu = orc.undistort(x, s, delta[:3, :3], delta[:3, 3])
         corner = orc.voxel_downsample(xu[label == 1], LEAF_CORNER)
         surf = orc.voxel_downsample(xu[label == 2], LEAF_SURF)
@@ -202,6 +205,9 @@ def cpu_loop(orc, synth, scans, Ts, first, n, ms, mc, threads):
         odo.update(T)
         poses.append(T)
     dt = time.perf_counter() - t0
+    # the reference runs extraction and estimation as two pipelined ROS nodes: throughput of the slower stage
+    cpu_loop.pipelined = n / max(t_fe, dt - t_fe)
+    cpu_loop.stage_ms = {"extract": 1e3 * t_fe / n, "rest": 1e3 * (dt - t_fe) / n}
     return n / dt, poses
 
 
@@ -221,8 +227,12 @@ def main():
     workload = (f"S3-merged odometry loop: VLP-16 28800 + Horizon {a.livox_pts} pts/scan with motion distortion, "
                 f"extract -> undistort -> voxel {LEAF_CORNER}/{LEAF_SURF} -> Estimate window 1 "
                 f"(<=5 outer x <=10 dogleg) vs {a.map_surf}+{a.map_corner}-pt local feature map")
+    scan_mb = (28800 + a.livox_pts) * 22 / 1e6
     config = {"workload": workload, "points_per_scan": 28800 + a.livox_pts, "window": 1,
-              "l2": "flushed between timed steps (256 MiB memset)", "seed": 1003}
+              "l2": f"inputs larger than L2: {a.steps} distinct scans ({a.steps * scan_mb:.0f} MB) streamed once through the "
+                    "timed region; the 1.7 MB feature map is reused by design (resident map)",
+              "pipeline": "extraction of scan k+1 overlaps the matching of scan k (the reference's two-node pipeline)",
+              "seed": 1003}
 
     if a.impl == "reference":
         # the oracle port timed on the host cores; rank 0 only
@@ -234,13 +244,15 @@ def main():
         Ts, scans = make_workload(synth, n_total, a.livox_pts, 1003)
         ms, mc = synth.feature_map(a.map_surf, a.map_corner, seed=1002)
         cpu_loop(orc, synth, scans, Ts, 0, min(a.warmup, 2), ms, mc, n_threads)
-        v, poses = cpu_loop(orc, synth, scans, Ts, a.warmup, a.steps, ms, mc, n_threads)
+        v_seq, poses = cpu_loop(orc, synth, scans, Ts, a.warmup, a.steps, ms, mc, n_threads)
+        v = cpu_loop.pipelined  # two-node pipeline like the reference (and like this repo's arm)
         line = {"impl": "reference", "metric": "LiDAR scans/s through odometry loop (merged VLP16+Livox)",
                 "value": v, "unit": "scans/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32/f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "scans/s", "cores": n_threads, "kind": "port",
-                                 "sample": f"{a.steps} scans of the same workload, oracle port (reference unbuildable here)"},
+                                 "sample": f"{a.steps} scans of the same workload, oracle port (reference unbuildable here)",
+                                 "sequential_value": v_seq, "stage_ms": cpu_loop.stage_ms},
                 "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "pose_rmse_m": pose_rmse(poses, Ts, a.warmup), "gpu_launches": 0}
         print(json.dumps(line))
@@ -264,35 +276,49 @@ def main():
 
     # ---- device-resident scans for `value`
     dev = [(ctx.dev_upload(x), ctx.dev_upload(l), ctx.dev_upload(s), x.shape[0]) for (x, l, s) in scans]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
 
     def run_dev(first, n, timed):
+        """per-scan API (mml_scan_to_pose_dev), no pipelining: used for the stage profile"""
         odo = Odometry(Ts[first], Ts[first - 1] if first > 0 else Ts[first])
         total_ms, poses = 0.0, []
         for k in range(first, first + n):
             Tp, delta = odo.predict()
-            if timed:
-                flush.zero_()
-                torch.cuda.synchronize()
-                ctx.timer_start()
             xd, ld, sd, npts = dev[k]
             P, q, st, cnt = ctx.scan_to_pose_dev(xd, ld, sd, npts, N_LINES, delta[:3, :3], delta[:3, 3], ex, Tp[:3, 3],
                                                  R_to_quat(Tp[:3, :3]), LEAF_CORNER, LEAF_SURF)
-            if timed:
-                total_ms += ctx.timer_stop_ms()
             T = T_from(P, q)
             odo.update(T)
             poses.append(T)
+            iters.append((st[0], st[1], cnt[2], cnt[3]))
         return total_ms, poses
 
-    run_dev(0, a.warmup, False)
+    iters = []
+
+    def run_native(first, n, host):
+        """the native loop (mml_odom_run): constant-velocity prediction + pipelined extraction in C++"""
+        src = pinned_np if host else dev
+        t0 = time.perf_counter()
+        poses, ms, cnt = ctx.odom_run(src[first:first + n], N_LINES, Ts[first], Ts[first - 1] if first > 0 else Ts[first], ex,
+                                      host_buffers=host, leaf_corner=LEAF_CORNER, leaf_surf=LEAF_SURF)
+        return ms, time.perf_counter() - t0, [p for p in poses]
+
+    # pinned host copies for the e2e arm
+    pinned, pinned_np = [], []
+    for (x, l, s) in scans:
+        tx = torch.from_numpy(x).pin_memory()
+        tl = torch.from_numpy(l.view(np.int16)).pin_memory()
+        ts = torch.from_numpy(s).pin_memory()
+        pinned.append((tx, tl, ts))
+        pinned_np.append((tx.numpy(), tl.numpy().view(np.uint16), ts.numpy(), x.shape[0]))
+
+    run_native(0, a.warmup, False)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = ctx.launches
-    t_ms, poses = run_dev(a.warmup, a.steps, True)
+    t_ms, _, poses = run_native(a.warmup, a.steps, False)
     launches = ctx.launches - l0
     torch.cuda.synchronize()
     if world > 1:
@@ -304,29 +330,11 @@ def main():
     t_max_ms = float(t_all.item())
     value = world * a.steps / (t_max_ms / 1000.0)
 
-    # ---- e2e: host (pinned) buffers in, pose out, wall clock
-    pinned = []
-    for (x, l, s) in scans:
-        tx = torch.from_numpy(x).pin_memory()
-        tl = torch.from_numpy(l.view(np.int16)).pin_memory()
-        ts = torch.from_numpy(s).pin_memory()
-        pinned.append((tx, tl, ts))
-
-    def run_e2e(first, n):
-        odo = Odometry(Ts[first], Ts[first - 1] if first > 0 else Ts[first])
-        t0 = time.perf_counter()
-        for k in range(first, first + n):
-            tx, tl, ts = pinned[k]
-            Tp, delta = odo.predict()
-            P, q, st, cnt = ctx.scan_to_pose(tx.numpy(), tl.numpy().view(np.uint16), ts.numpy(), N_LINES, delta[:3, :3],
-                                             delta[:3, 3], ex, Tp[:3, 3], R_to_quat(Tp[:3, :3]), LEAF_CORNER, LEAF_SURF)
-            odo.update(T_from(P, q))
-        return time.perf_counter() - t0
-
-    run_e2e(0, a.warmup)
+    # ---- e2e: host (pinned) buffers in, poses out, wall clock around the public API call
+    run_native(0, a.warmup, True)
     if world > 1:
         dist.barrier()
-    e2e_s = run_e2e(a.warmup, a.steps)
+    _, e2e_s, poses_e2e = run_native(a.warmup, a.steps, True)
     e_all = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         dist.all_reduce(e_all, op=dist.ReduceOp.MAX)
@@ -422,13 +430,16 @@ def main():
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": nq * BYTES_PER_FEATURE_EVAL,
                 "launch_ms": dom_ms, "note": "one-scan working set (~0.1 MB): launch-latency-bound; see s4 for the HBM-sized sweep",
                 "stage_ms_per_scan": {"extract": stage_ms[0], "undistort_split_voxel": stage_ms[1], "estimate": stage_ms[2]},
+                "per_scan_avg": {"outer_iters": float(np.mean([i[0] for i in iters])), "dogleg_iters": float(np.mean([i[1] for i in iters])),
+                                 "corner_queries": float(np.mean([i[2] for i in iters])), "surf_queries": float(np.mean([i[3] for i in iters]))},
                 "detail": roof, "s4": s4}
 
     # ---- CPU baseline on a bounded sample of the same workload (rank 0, host cores)
     orc.build()
     n_cpu = min(a.cpu_scans, a.steps)
     cpu_threads = min(6, n_threads)  # reference threading: 6 extraction / solver threads (FE.cpp:1008, EST.cpp:1430)
-    cpu_v, cpu_poses = cpu_loop(orc, synth, scans, Ts, a.warmup, n_cpu, ms, mc, cpu_threads)
+    cpu_seq, cpu_poses = cpu_loop(orc, synth, scans, Ts, a.warmup, n_cpu, ms, mc, cpu_threads)
+    cpu_v = cpu_loop.pipelined
     # parity of the loop: GPU vs oracle poses on the sampled scans
     dpos = max(float(np.abs(g[:3, 3] - c[:3, 3]).max()) for g, c in zip(poses[:n_cpu], cpu_poses))
     drot = max(float(np.linalg.norm(synth.R_to_rotvec(g[:3, :3].T @ c[:3, :3]))) for g, c in zip(poses[:n_cpu], cpu_poses))
@@ -440,7 +451,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": {"value": cpu_v, "unit": "scans/s", "cores": cpu_threads, "kind": "port",
-                             "sample": f"{n_cpu} scans of the same workload (oracle port, reference threading)"},
+                             "sample": f"{n_cpu} scans of the same workload (oracle port, reference threading, "
+                                       "extraction and estimation pipelined like the reference's two nodes)",
+                             "sequential_value": cpu_seq, "stage_ms": cpu_loop.stage_ms},
             "pose_rmse_m": pose_rmse(poses, Ts, a.warmup),
             "parity_vs_oracle": {"max_dpos_m": dpos, "max_drot_rad": drot, "scans": n_cpu}}
     print(json.dumps(line))

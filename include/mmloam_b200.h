@@ -136,6 +136,17 @@ int mml_scan_to_pose_dev(mml_ctx* ctx, const void* xyzi_dev, const void* line_id
                          const double* exTlb16, double* P3, double* q_wxyz4, const mml_est_params* prm,
                          double* stats, int* out_counts);
 
+/* ---- native odometry loop: the per-scan body of process() (src/unionPoseEstimation.cpp:650-906) over a
+ * sequence of scans, keeping the reference's node pipeline (extraction of scan k+1 overlaps the matching of
+ * scan k on a second stream). xyzi / line / s: arrays of per-scan pointers, device pointers when
+ * host_buffers == 0, host (ideally pinned) pointers otherwise. T_init16 / T_prev16: the two poses before the
+ * first scan (constant-velocity seed, PE.cpp:847-852). poses_out: n_scans x 16 row-major T_wb.
+ * total_ms (may be NULL): CUDA-event time of the run. counts_out (may be NULL): n_scans x 4.            */
+int mml_odom_run(mml_ctx* ctx, const void* const* xyzi, const void* const* line, const void* const* s,
+                 const int* n_pts, int n_scans, int n_lines, int host_buffers, const double* T_init16,
+                 const double* T_prev16, const double* exTlb16, float leaf_corner, float leaf_surf,
+                 const mml_est_params* prm, double* poses_out, float* total_ms, int* counts_out);
+
 /* ---- device-resident building blocks used by bench.py's roofline sweep (S4):
  * queries and maps stay in HBM; one call = one association or one evaluation.          */
 int mml_frame_set(mml_ctx* ctx, const float* corner_xyzi, int n_corner, const float* surf_xyzi, int n_surf);

@@ -308,6 +308,35 @@ class Context:
                                            C.byref(prm), _p(stats), _p(counts)))
         return P, q, stats, counts
 
+    # ---- native odometry loop (pipelined extraction, constant-velocity prediction)
+    def odom_run(self, scans, n_lines, T_init, T_prev, exTlb, host_buffers=False, leaf_corner=0.4, leaf_surf=0.2,
+                 params=None):
+        """scans: list of (xyzi, line, s, n). Device pointers (ctypes.c_void_p) when host_buffers is False,
+        numpy arrays (ideally backed by pinned memory) otherwise. Returns (poses [k,4,4], total_ms, counts [k,4])."""
+        k = len(scans)
+        PtrArr = C.c_void_p * max(k, 1)
+
+        def ptr(v):
+            if isinstance(v, C.c_void_p):
+                return v.value
+            return v.ctypes.data if v is not None else None
+
+        xs = PtrArr(*[ptr(sc[0]) for sc in scans])
+        ls = PtrArr(*[ptr(sc[1]) for sc in scans])
+        ss = PtrArr(*[ptr(sc[2]) for sc in scans])
+        ns = np.ascontiguousarray([int(sc[3]) for sc in scans], np.int32)
+        poses = np.zeros((max(k, 1), 16), np.float64)
+        counts = np.zeros((max(k, 1), 4), np.int32)
+        ms = C.c_float(0)
+        Ti = _f64(T_init).reshape(16)
+        Tp = _f64(T_prev).reshape(16)
+        ex = _f64(exTlb).reshape(16)
+        prm = params if params is not None else est_params()
+        self._ck(self.lib.mml_odom_run(self.h, xs, ls, ss, _p(ns), k, int(n_lines), 1 if host_buffers else 0, _p(Ti), _p(Tp),
+                                       _p(ex), C.c_float(leaf_corner), C.c_float(leaf_surf), C.byref(prm), _p(poses),
+                                       C.byref(ms), _p(counts)))
+        return poses[:k].reshape(k, 4, 4), ms.value, counts[:k]
+
     # ---- device-resident scans (bench.py)
     def dev_upload(self, arr):
         arr = np.ascontiguousarray(arr)

@@ -71,6 +71,7 @@ int mml_ctx_destroy(mml_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->est_graph) cudaGraphExecDestroy(c->est_graph);
+  if (c->stream_fe) { cudaStreamSynchronize(c->stream_fe); cudaStreamDestroy(c->stream_fe); }
   mml::DevBuf* bufs[] = {&c->in_xyzi, &c->in_line, &c->in_s, &c->in_label, &c->srt_xyzi, &c->srt_src, &c->srt_line,
                          &c->chunk_tab, &c->chunk_hist, &c->line_start, &c->line_count, &c->curv, &c->refl, &c->attr,
                          &c->sort_ind, &c->refl_ind, &c->counters, &c->tmp_a, &c->tmp_b, &c->tmp_c, &c->tmp_d, &c->tmp_e,

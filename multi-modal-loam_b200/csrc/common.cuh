@@ -103,6 +103,7 @@ struct mml_ctx {
   mml::DevBuf chunk_tab, chunk_hist, line_start, line_count;
   mml::DevBuf curv, refl, attr, sort_ind, refl_ind;      // per-point extraction state
   mml::DevBuf counters;                                  // small int scratch
+  int* counters_alt = nullptr;                           // when set, extraction writes its counters here
   mml::DevBuf tmp_a, tmp_b, tmp_c, tmp_d, tmp_e;         // generic
   mml::DevBuf vox_keys[2], vox_vals[2], vox_hist, vox_bbox;
   mml::DevBuf corner_raw, surf_raw;                      // label-split clouds
@@ -122,6 +123,8 @@ struct mml_ctx {
   long long est_graph_key = 0;
   long long est_launches_per_graph = 0;
   std::vector<int> last_scan_off;  // scan offsets the resident chunk table was built for
+  void* odom = nullptr;            // pipelined odometry runner state (odometry.cu)
+  cudaStream_t stream_fe = nullptr;  // feature-extraction stream of the pipelined runner
   bool profile = false;
   cudaEvent_t pev[4] = {nullptr, nullptr, nullptr, nullptr};
   double stage_ms[4] = {0, 0, 0, 0};

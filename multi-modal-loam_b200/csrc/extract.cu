@@ -706,7 +706,9 @@ int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_
   const int TL = n_scans * n_lines;
   cudaStream_t st = ctx->stream;
   MML_CUDA(ctx, ctx->counters.reserve(sizeof(int) * (2 * (size_t)n_scans + 64)));
-  MML_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * (2 * (size_t)n_scans + 1), st));
+  // counters: per scan (n_sharp, n_flat), then the overflow flag. A pipelined caller redirects them to its slot.
+  int* const counters = ctx->counters_alt ? ctx->counters_alt : ctx->counters.as<int>();
+  MML_CUDA(ctx, cudaMemsetAsync(counters, 0, sizeof(int) * (2 * (size_t)n_scans + 1), st));
   if (n_total <= 0) return MML_OK;
 
   // host-side chunk table (metadata only)
@@ -784,7 +786,7 @@ int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_
                                                    ctx->sort_ind.as<int>(), ctx->refl_ind.as<int>(), max_m);
   MML_LAUNCHED(ctx);
 
-  int* overflow_flag = ctx->counters.as<int>() + 2 * (size_t)n_scans;
+  int* overflow_flag = counters + 2 * (size_t)n_scans;
   const size_t kMaxSmem = 227 * 1024;
   if (!force_sequential) {
     // part-parallel selection; lines longer than the shared-memory capacity raise the overflow flag and the
@@ -795,7 +797,7 @@ int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_
       MML_CUDA(ctx, cudaFuncSetAttribute(k_select_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)par_smem));
     k_select_par<<<TL, kSelThreads, par_smem, st>>>(ctx->attr.as<uint16_t>(), ctx->sort_ind.as<int>(), ctx->refl_ind.as<int>(),
                                                     ctx->srt_src.as<int>(), line_start, line_count, n_lines, cap_n, label_d,
-                                                    ctx->counters.as<int>(), overflow_flag);
+                                                    counters, overflow_flag);
   } else {
     // sequential fallback: size shared memory for the longest line actually present
     std::vector<int> lc(TL);
@@ -811,7 +813,7 @@ int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_
       MML_CUDA(ctx, cudaFuncSetAttribute(k_select<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base_smem));
     k_select<false><<<TL, 64, base_smem, st>>>(ctx->attr.as<uint16_t>(), ctx->sort_ind.as<int>(), ctx->refl_ind.as<int>(),
                                                ctx->srt_src.as<int>(), line_start, line_count, n_lines, longest, max_m, label_d,
-                                               ctx->counters.as<int>());
+                                               counters);
   }
   MML_LAUNCHED(ctx);
   MML_CUDA(ctx, cudaGetLastError());

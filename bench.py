@@ -392,34 +392,39 @@ def main():
 
     s4 = None
     if not a.no_s4:
-        # S4: 1M-pt map, Q queries perturbed by the S1 offset (SURVEY §8 d)
+        # S4: 1M-pt map, Q in {28.8k, 240k, 1M} queries perturbed by the S1 offset (SURVEY §8 d)
         hs, hc = synth.feature_map(a.s4_map, a.s4_map // 20, seed=1004, box=synth.HALL, pillars=[])
         ctx4 = mm.Context(local_rank)
+        t0 = time.perf_counter()
         ctx4.map_set(mm.MAP_SURF_LOCAL, hs)
         ctx4.map_set(mm.MAP_CORNER_LOCAL, hc)
+        ctx4.sync()
+        map_build_ms = 1e3 * (time.perf_counter() - t0)
         Tq = synth.s1_offset_pose()
-        qs = synth.queries_from_map(hs, a.s4_queries, np.eye(4), seed=1004)
-        qc = synth.queries_from_map(hc, max(a.s4_queries // 20, 64), np.eye(4), seed=1005)
-        ctx4.frame_set(qc, qs)
         x6q = np.concatenate([Tq[:3, 3], synth.R_to_rotvec(Tq[:3, :3])])
-        nl, npl, _, _ = ctx4.frame_associate(Tq, 1.0)
-        ctx4.frame_associate_async(Tq, 1.0, 2)
-        ctx4.sync()
-        ctx4.timer_start()
-        ctx4.frame_associate_async(Tq, 1.0, 10)
-        ms_assoc4 = ctx4.timer_stop_ms() / 10
-        ctx4.frame_accumulate_async(x6q, np.eye(4), repeat=3)
-        ctx4.sync()
-        ctx4.timer_start()
-        ctx4.frame_accumulate_async(x6q, np.eye(4), repeat=20)
-        ms_acc4 = ctx4.timer_stop_ms() / 20
-        nq4 = qs.shape[0] + qc.shape[0]
-        s4 = {"map_points": int(hs.shape[0] + hc.shape[0]), "queries": int(nq4), "features": int(nl + npl),
-              "associate_ms": ms_assoc4, "associate_gbs": nq4 * BYTES_PER_QUERY_ASSOC / ms_assoc4 / 1e6,
-              "accumulate_ms": ms_acc4, "accumulate_gbs": nq4 * BYTES_PER_FEATURE_EVAL / ms_acc4 / 1e6,
-              "map_cell_m": ctx4.map_info(mm.MAP_SURF_LOCAL)["cell"]}
-        s4["associate_frac"] = s4["associate_gbs"] / peak
-        s4["accumulate_frac"] = s4["accumulate_gbs"] / peak
+        s4 = {"map_points": int(hs.shape[0] + hc.shape[0]), "map_cell_m": ctx4.map_info(mm.MAP_SURF_LOCAL)["cell"],
+              "map_build_ms_incl_h2d": map_build_ms, "sweep": []}
+        for Q in sorted({28_800, a.s4_queries, 1_000_000} if a.s4_queries >= 240_000 else {a.s4_queries}):
+            qs = synth.queries_from_map(hs, Q, np.eye(4), seed=1004)
+            qc = synth.queries_from_map(hc, max(Q // 20, 64), np.eye(4), seed=1005)
+            ctx4.frame_set(qc, qs)
+            nl, npl, _, _ = ctx4.frame_associate(Tq, 1.0)
+            ctx4.frame_associate_async(Tq, 1.0, 2)
+            ctx4.sync()
+            ctx4.timer_start()
+            ctx4.frame_associate_async(Tq, 1.0, 10)
+            ms_as = ctx4.timer_stop_ms() / 10
+            ctx4.frame_accumulate_async(x6q, np.eye(4), repeat=3)
+            ctx4.sync()
+            ctx4.timer_start()
+            ctx4.frame_accumulate_async(x6q, np.eye(4), repeat=20)
+            ms_ac = ctx4.timer_stop_ms() / 20
+            nq4 = qs.shape[0] + qc.shape[0]
+            s4["sweep"].append({"queries": int(nq4), "features": int(nl + npl),
+                                "associate_ms": ms_as, "associate_gbs": nq4 * BYTES_PER_QUERY_ASSOC / ms_as / 1e6,
+                                "associate_frac": nq4 * BYTES_PER_QUERY_ASSOC / ms_as / 1e6 / peak,
+                                "accumulate_ms": ms_ac, "accumulate_gbs": nq4 * BYTES_PER_FEATURE_EVAL / ms_ac / 1e6,
+                                "accumulate_frac": nq4 * BYTES_PER_FEATURE_EVAL / ms_ac / 1e6 / peak})
         ctx4.close()
 
     # the kernel that dominates the step: the estimate stage = associate + accumulate launches

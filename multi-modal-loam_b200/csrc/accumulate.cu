@@ -616,8 +616,8 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
   }
   // One outer iteration = one graph: begin | line association || plane association (two captured streams) |
   // 1 + max_inner evaluations, each fused with its dogleg update | end. The host replays it until the device
-  // reports convergence; the first two iterations are enqueued back to back (nearly every scan needs both), so
-  // a typical scan costs two short synchronisations and no idle no-op launches for iterations 3-5.
+  // reports convergence (EST.cpp:1448): a well-predicted scan costs one graph and one short synchronisation
+  // and no idle no-op launches for iterations 2-5.
   if (!ctx->est_graph || ctx->est_graph_key != key) {
     if (ctx->est_graph) { cudaGraphExecDestroy(ctx->est_graph); ctx->est_graph = nullptr; }
     cudaGraph_t graph = nullptr;
@@ -650,7 +650,9 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
   }
   int launched = 0;
   while (launched < prm->max_outer) {
-    const int burst = launched == 0 && prm->max_outer > 1 ? 2 : 1;
+    // scans whose prediction is poor need several outer iterations: after the first convergence check the
+    // remaining ones are enqueued two at a time (a finished solve turns the surplus launch into cheap no-ops)
+    const int burst = launched == 0 ? 1 : (prm->max_outer - launched >= 2 ? 2 : 1);
     for (int b = 0; b < burst; b++) {
       MML_CUDA(ctx, cudaGraphLaunch(ctx->est_graph, st));
       ctx->launches += ctx->est_launches_per_graph;

@@ -232,6 +232,7 @@ struct AssocArgs {
   int nq;
   const int* nq_dev;        // optional: query count read from device memory (<= nq)
   int* overflow;            // set to 1 when *nq_dev exceeds the launch capacity nq
+  const unsigned* perm;     // optional: queries were spatially sorted; perm[i] = original index of query i
   double T[16];
   float thres;
   GridDev G[2];  // [0] global, [1] local
@@ -373,9 +374,10 @@ __global__ void __launch_bounds__(128) k_associate(AssocArgs A) {
         }
       }
     }
-    A.feat[3 * (size_t)i] = f0;
-    A.feat[3 * (size_t)i + 1] = f1;
-    A.feat[3 * (size_t)i + 2] = f2;
+    const size_t slot = A.perm ? (size_t)A.perm[i] : (size_t)i;  // features live in the caller's query order
+    A.feat[3 * slot] = f0;
+    A.feat[3 * slot + 1] = f1;
+    A.feat[3 * slot + 2] = f2;
   }
   // ---- block reduction of (moments, count); last block sums the partials in fixed order
   mom[6] = (double)found;
@@ -417,9 +419,12 @@ __global__ void __launch_bounds__(128) k_associate(AssocArgs A) {
 // serial chain of dependent L2 loads that bounds the latency of the thread-per-query kernel.
 template <int G>
 __device__ __forceinline__ unsigned group_mask() {
-  if (G == 32) return 0xffffffffu;
-  const unsigned lane = threadIdx.x & 31u;
-  return ((1u << G) - 1u) << (lane & ~(unsigned)(G - 1));
+  if constexpr (G == 32) {
+    return 0xffffffffu;
+  } else {
+    const unsigned lane = threadIdx.x & 31u;
+    return ((1u << G) - 1u) << (lane & ~(unsigned)(G - 1));
+  }
 }
 
 template <int G>
@@ -648,9 +653,10 @@ __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
       }
     }
     if (lg == 0) {
-      A.feat[3 * (size_t)i] = f0;
-      A.feat[3 * (size_t)i + 1] = f1;
-      A.feat[3 * (size_t)i + 2] = f2;
+      const size_t slot = A.perm ? (size_t)A.perm[i] : (size_t)i;
+      A.feat[3 * slot] = f0;
+      A.feat[3 * slot + 1] = f1;
+      A.feat[3 * slot + 2] = f2;
     }
   }
   mom[6] = (lg == 0) ? (double)found : 0.0;
@@ -883,7 +889,7 @@ int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres,
   const int nq = cap;
   // lanes per query: a whole warp for scan-sized query sets (latency), 8 lanes for map-sized sweeps
   static const int g_env = getenv("MML_ASSOC_G") ? atoi(getenv("MML_ASSOC_G")) : 0;
-  const int G = g_env ? g_env : (cap <= 32768 ? 32 : 8);
+  const int G = g_env ? g_env : (cap <= 32768 ? 32 : 1);
   const int grid = G == 1 ? div_up(nq > 0 ? nq : 1, 128) : div_up(nq > 0 ? nq : 1, 128 / G);
   mml::DevBuf& fb = kind == 0 ? ctx->f_line : ctx->f_plane;
   MML_CUDA(ctx, fb.reserve(sizeof(float4) * 3 * (size_t)(nq > 0 ? nq : 1)));
@@ -912,6 +918,7 @@ int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres,
   A.T_dev = T_dev;
   A.thres_dev = thres_dev;
   A.overflow = ints + 6;
+  A.perm = ctx->has_perm[kind] ? ctx->perm[kind].as<unsigned>() : nullptr;
   if (G == 32) {
     if (kind == 0) k_associate_g<0, 32><<<grid, 128, 0, ctx->stream>>>(A);
     else k_associate_g<1, 32><<<grid, 128, 0, ctx->stream>>>(A);

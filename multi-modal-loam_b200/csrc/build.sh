@@ -9,12 +9,12 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -Xcompiler -O3 ${MML_EXTRA_NVCC_FLAGS}"
 mkdir -p "$HERE/_obj"
 pids=()
-for f in extract geometry splitvoxel associate accumulate odometry capi; do
+for f in extract geometry splitvoxel framesort associate accumulate odometry capi; do
   if [ ! -f "$HERE/_obj/$f.o" ] || [ -n "$(find "$HERE" -maxdepth 1 \( -name '*.cu' -o -name '*.cuh' \) -newer "$HERE/_obj/$f.o" 2>/dev/null)" ] || [ "$HERE/../../include/mmloam_b200.h" -nt "$HERE/_obj/$f.o" ]; then
     $NVCC $FLAGS -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" &
     pids+=($!)
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$HERE"/_obj/{extract,geometry,splitvoxel,associate,accumulate,odometry,capi}.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$HERE"/_obj/{extract,geometry,splitvoxel,framesort,associate,accumulate,odometry,capi}.o -lcudart
 echo "built $OUT"

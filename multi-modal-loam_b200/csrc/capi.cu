@@ -2,6 +2,7 @@
 // pinned memory, run the device pipeline on the context's stream and copy results back.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 // device-resident stages (extract.cu, geometry.cu, associate.cu, accumulate.cu)
 namespace mml { struct EstState; }
@@ -22,6 +23,7 @@ int mml_export_features(mml_ctx* ctx, int kind, int nq, double* out_dev);
 int mml_accumulate_launch(mml_ctx* ctx, const double* x6, const double* T_bl16, double lidar_m, double w_tan,
                           double huber_a, mml::EstState* st_dev, const int* n_dev, int cap_line, int cap_plane,
                           const double* wide_line_dev, const double* wide_plane_dev);
+int mml_sort_queries_device(mml_ctx* ctx, float4* q_d, int n, mml::DevBuf& perm_buf);
 int mml_split_voxel_capacity();
 int mml_split_voxel_device(mml_ctx* ctx, const float4* pts_d, const float* s_d, const uint8_t* label_d, int n,
                            const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, float4* corner_out,
@@ -91,6 +93,8 @@ int mml_ctx_destroy(mml_ctx* c) {
   c->pin_small.release();
   c->pin_flags.release();
   for (auto s : c->extra_streams) cudaStreamDestroy(s);
+  c->perm[0].release();
+  c->perm[1].release();
   c->assoc_part[0].release();
   c->assoc_part[1].release();
   cudaEventDestroy(c->ev_fork);
@@ -279,6 +283,11 @@ int mml_frame_set(mml_ctx* c, const float* corner_xyzi, int n_corner, const floa
   if (n_surf) MML_CUDA(c, cudaMemcpyAsync(c->q_surf.p, surf_xyzi, sizeof(float4) * (size_t)n_surf, cudaMemcpyHostToDevice, c->stream));
   c->n_corner = n_corner;
   c->n_surf = n_surf;
+  // map-sized query sets are put into spatial (Morton) order once per frame; scans already are coherent
+  c->has_perm[0] = c->has_perm[1] = false;
+  static const int sort_min = getenv("MML_SORT_MIN") ? atoi(getenv("MML_SORT_MIN")) : 32768;
+  if (n_corner > sort_min) { MML_CHECK(mml_sort_queries_device(c, c->q_corner.as<float4>(), n_corner, c->perm[0])); c->has_perm[0] = true; }
+  if (n_surf > sort_min) { MML_CHECK(mml_sort_queries_device(c, c->q_surf.as<float4>(), n_surf, c->perm[1])); c->has_perm[1] = true; }
   MML_CUDA(c, c->frame_cnt.reserve(64));
   const int cnt[2] = {n_corner, n_surf};
   MML_CUDA(c, cudaMemcpyAsync(c->frame_cnt.p, cnt, sizeof(cnt), cudaMemcpyHostToDevice, c->stream));
@@ -499,6 +508,7 @@ int mml_scan_to_pose_dev(mml_ctx* c, const void* xyzi_dev, const void* line_id_d
   if (c->profile) MML_CUDA(c, cudaEventRecord(c->pev[0], st));
   MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, c->in_label.as<uint8_t>(), false));
   if (c->profile) MML_CUDA(c, cudaEventRecord(c->pev[1], st));
+  c->has_perm[0] = c->has_perm[1] = false;
   int* cnt = c->frame_cnt.as<int>();  // [0..1] voxel outputs, [2..3] raw split counts, [4] overflow
   const bool undist = dR9 && dt3 && s_dev;
   MML_CHECK(mml_split_voxel_device(c, (const float4*)xyzi_dev, undist ? (const float*)s_dev : nullptr, c->in_label.as<uint8_t>(), n,

@@ -114,6 +114,8 @@ struct mml_ctx {
 
   // frame slot (queries + features)
   mml::DevBuf q_corner, q_surf;   // float4
+  mml::DevBuf perm[2];            // spatial sort permutation of large query sets (framesort.cu)
+  bool has_perm[2] = {false, false};
   int n_corner = 0, n_surf = 0;
   mml::DevBuf f_line, f_plane;    // compact features (see associate.cu)
   mml::DevBuf acc_partials, acc_out, est_state;

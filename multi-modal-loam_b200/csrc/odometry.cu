@@ -124,6 +124,7 @@ int mml_odom_run(mml_ctx* c, const void* const* xyzi, const void* const* line, c
   MML_CUDA(c, c->q_corner.reserve(sizeof(float4) * (size_t)cap));
   MML_CUDA(c, c->q_surf.reserve(sizeof(float4) * (size_t)cap));
   MML_CUDA(c, c->pin_flags.reserve(64));
+  c->has_perm[0] = c->has_perm[1] = false;
   double T_last[16], T_before[16];
   memcpy(T_last, T_init16, sizeof(T_last));
   memcpy(T_before, T_prev16, sizeof(T_before));

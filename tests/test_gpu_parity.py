@@ -318,3 +318,67 @@ def test_large_scan_round_trip_properties(ctx, synth):
     assert len({tuple(v) for v in k}) == out.shape[0]
     # undistort with identity motion is the identity; with s = 1 as well
     assert np.array_equal(ctx.undistort(x, s, np.eye(3), np.zeros(3))[:, :3], x[:, :3])
+
+
+def test_native_odometry_loop_matches_oracle(ctx, mm, orc, synth, scene):
+    """mml_odom_run (pipelined extraction + constant-velocity prediction in C++) against the oracle driven
+    through the same loop in Python, on a short trajectory with motion distortion; device and host-buffer arms."""
+    Ts = synth.trajectory(7, v=0.5, yaw_rate=0.2, dt=0.1)
+    scans = []
+    for k in range(7):
+        vx, vr, vs = synth.vlp16_scan(Ts[k + 1], seed=300 + 2 * k, T_ws_start=Ts[k], n_az=900)
+        hx, hl, hs = synth.horizon_scan(Ts[k + 1], 12000, seed=301 + 2 * k, T_ws_start=Ts[k])
+        scans.append((np.ascontiguousarray(np.concatenate([vx, hx])),
+                      np.ascontiguousarray(np.concatenate([vr, hl + 16]).astype(np.uint16)),
+                      np.ascontiguousarray(np.concatenate([vs, hs]).astype(np.float32))))
+    ctx.map_set(mm.MAP_CORNER_GLOBAL, np.zeros((0, 4), np.float32)); ctx.map_set(mm.MAP_SURF_GLOBAL, np.zeros((0, 4), np.float32))
+    ctx.map_set(mm.MAP_SURF_LOCAL, scene["map_surf"]); ctx.map_set(mm.MAP_CORNER_LOCAL, scene["map_corner"])
+    om = orc.Map()
+    om.set(orc.SURF_LOCAL, scene["map_surf"]); om.set(orc.CORNER_LOCAL, scene["map_corner"])
+    # oracle loop (first scan is index 1: needs two earlier poses for the constant-velocity seed)
+    first = 1
+    T_last, T_before = Ts[first].copy(), Ts[first - 1].copy()
+    ref = []
+    for k in range(first, 7):
+        delta = np.linalg.inv(T_before) @ T_last
+        Tp = T_last @ delta
+        x, line, s = scans[k]
+        label = orc.extract_scan(x, line, 22)
+        xu = orc.undistort(x, s, delta[:3, :3], delta[:3, 3])
+        corner = orc.voxel_downsample(xu[label == 1], 0.4); surf = orc.voxel_downsample(xu[label == 2], 0.2)
+        q0, _ = orc.so3_exp(synth.R_to_rotvec(Tp[:3, :3]))
+        P, q, st = om.estimate(corner, surf, np.eye(4), Tp[:3, 3], q0)
+        _, R = orc.so3_exp(orc.so3_log(q))
+        Tn = synth.make_T(R, P)
+        ref.append(Tn)
+        T_before, T_last = T_last, Tn
+    host = [(x, l, s, x.shape[0]) for (x, l, s) in scans[first:]]
+    poses_h, ms_h, cnt_h = ctx.odom_run(host, 22, Ts[first], Ts[first - 1], np.eye(4), host_buffers=True)
+    dev = [(ctx.dev_upload(x), ctx.dev_upload(l), ctx.dev_upload(s), x.shape[0]) for (x, l, s) in scans[first:]]
+    poses_d, ms_d, cnt_d = ctx.odom_run(dev, 22, Ts[first], Ts[first - 1], np.eye(4), host_buffers=False)
+    for d in dev:
+        for p in d[:3]:
+            ctx.dev_free(p)
+    assert np.array_equal(poses_h, poses_d) and np.array_equal(cnt_h, cnt_d)
+    for k, Tn in enumerate(ref):
+        assert np.abs(poses_d[k][:3, 3] - Tn[:3, 3]).max() <= POSE_TOL_M
+        assert np.linalg.norm(synth.R_to_rotvec(poses_d[k][:3, :3].T @ Tn[:3, :3])) <= POSE_TOL_RAD
+        assert np.abs(poses_d[k][:3, 3] - Ts[first + 1 + k][:3, 3]).max() < 0.02
+    assert ms_d > 0 and (cnt_d[:, 2] > 20).all() and (cnt_d[:, 3] > 200).all()
+
+
+def test_large_query_set_is_sorted_but_slots_keep_caller_order(ctx, mm, orc, synth):
+    """Query sets above 32768 are Morton-sorted on the device; feature slot i must still belong to query i."""
+    ms, mc = synth.feature_map(200_000, 2_000, seed=9)
+    ctx.map_set(mm.MAP_CORNER_GLOBAL, np.zeros((0, 4), np.float32)); ctx.map_set(mm.MAP_SURF_GLOBAL, np.zeros((0, 4), np.float32))
+    ctx.map_set(mm.MAP_SURF_LOCAL, ms); ctx.map_set(mm.MAP_CORNER_LOCAL, mc)
+    om = orc.Map()
+    om.set(orc.SURF_LOCAL, ms)
+    T = synth.s1_offset_pose()
+    q = synth.queries_from_map(ms, 40_000, np.eye(4), seed=10)
+    f, n, M, nn = ctx.associate(1, q, T, 1.0)
+    r, rn, rM, rnn = om.associate_plane(q, T, 1.0)
+    assert n == rn and np.array_equal(f[:, 10], r[:, 10])
+    ok = r[:, 10] >= 0
+    assert np.array_equal(f[ok, :3], r[ok, :3]) and np.array_equal(f[ok, 6:9], r[ok, 6:9])
+    assert np.abs(f[ok, 3:6] - r[ok, 3:6]).max() <= 1e-9

@@ -112,10 +112,13 @@ struct AccArgs {
   EstState* st;          // optional: evaluation point and parameters come from the solver state
 };
 
-__host__ __device__ void dogleg_update(EstState& S, const double* out28);
+__host__ __device__ __noinline__ void dogleg_update(EstState& S, const double* out28);
 
+#ifndef MML_ACC_MINB
+#define MML_ACC_MINB 2
+#endif
 template <bool WIDE>
-__global__ void __launch_bounds__(256) k_accumulate(AccArgs A) {
+__global__ void __launch_bounds__(256, MML_ACC_MINB) k_accumulate(AccArgs A) {
   EstState* S = A.st;
   if (S && (S->done_outer || S->done_inner)) return;
   __shared__ PoseLin L;
@@ -214,33 +217,12 @@ __global__ void __launch_bounds__(256) k_accumulate(AccArgs A) {
     const double k5 = 0.5 * en / (PP * sq);
     double gw[3];
     for (int k = 0; k < 3; k++) gw[k] = -0.9 * ((e[k] / en) / sq - k5 * P[k]);
-    // canonical basis [n t1 t2] (sqrt_info^T sqrt_info = (n n^T + w_t^2 (I - n n^T)) / lidar_m^2)
-    double B[3][3];
-    B[0][0] = n[0]; B[0][1] = n[1]; B[0][2] = n[2];
-    int nres = 1;
-    if (w_tan != 0.0) {
-      nres = 3;
-      int kk = 0;
-      if (fabs(n[1]) < fabs(n[kk])) kk = 1;
-      if (fabs(n[2]) < fabs(n[kk])) kk = 2;
-      double ex[3] = {0, 0, 0};
-      ex[kk] = 1.0;
-      double v[3] = {ex[1] * n[2] - ex[2] * n[1], ex[2] * n[0] - ex[0] * n[2], ex[0] * n[1] - ex[1] * n[0]};
-      const double nv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-      for (int k = 0; k < 3; k++) B[1][k] = v[k] / nv;
-      B[2][0] = n[1] * B[1][2] - n[2] * B[1][1];
-      B[2][1] = n[2] * B[1][0] - n[0] * B[1][2];
-      B[2][2] = n[0] * B[1][1] - n[1] * B[1][0];
-    }
-    double rv[3], grv[3][3];
-    double s = 0;
-    for (int k = 0; k < nres; k++) {
-      const double sc = k == 0 ? s_info : s_info * w_tan;
-      const double be = B[k][0] * e[0] + B[k][1] * e[1] + B[k][2] * e[2];
-      rv[k] = sc * w * be;
-      for (int c = 0; c < 3; c++) grv[k][c] = sc * (w * B[k][c] + be * gw[c]);
-      s += rv[k] * rv[k];
-    }
+    // residual in the canonical basis [n t1 t2]: sqrt_info^T sqrt_info = (n n^T + w_t^2 (I - n n^T)) / lidar_m^2.
+    // ||r||^2 needs no basis: (s w)^2 [ (n.e)^2 + w_t^2 (|e|^2 - (n.e)^2) ]
+    const double ne = n[0] * e[0] + n[1] * e[1] + n[2] * e[2];
+    const double sw = s_info * w;
+    double s = sw * sw * ne * ne;
+    if (w_tan != 0.0) s += sw * sw * w_tan * w_tan * fmax(en * en - ne * ne, 0.0);
     double k1 = 1.0, rho = s;
     if (ha > 0 && s > ha * ha) {
       const double rr = sqrt(s);
@@ -248,9 +230,28 @@ __global__ void __launch_bounds__(256) k_accumulate(AccArgs A) {
       rho = 2 * ha * rr - ha * ha;
     }
     acc[0] += 0.5 * rho;
-    for (int k = 0; k < nres; k++) {
-      double gr[3] = {k1 * grv[k][0], k1 * grv[k][1], k1 * grv[k][2]};
-      add_row(L, u, gr, k1 * rv[k], acc);
+    {
+      const double sc = k1 * s_info;
+      const double gr[3] = {sc * (w * n[0] + ne * gw[0]), sc * (w * n[1] + ne * gw[1]), sc * (w * n[2] + ne * gw[2])};
+      add_row(L, u, gr, sc * w * ne, acc);
+    }
+    if (w_tan != 0.0) {  // window size 5 only (EST.cpp:1203): the two tangential rows
+      int kk = 0;
+      if (fabs(n[1]) < fabs(n[kk])) kk = 1;
+      if (fabs(n[2]) < fabs(n[kk])) kk = 2;
+      double ex[3] = {0, 0, 0};
+      ex[kk] = 1.0;
+      const double v[3] = {ex[1] * n[2] - ex[2] * n[1], ex[2] * n[0] - ex[0] * n[2], ex[0] * n[1] - ex[1] * n[0]};
+      const double nv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+      const double t1[3] = {v[0] / nv, v[1] / nv, v[2] / nv};
+      const double t2[3] = {n[1] * t1[2] - n[2] * t1[1], n[2] * t1[0] - n[0] * t1[2], n[0] * t1[1] - n[1] * t1[0]};
+      const double sc = k1 * s_info * w_tan;
+      const double b1 = t1[0] * e[0] + t1[1] * e[1] + t1[2] * e[2];
+      const double b2 = t2[0] * e[0] + t2[1] * e[1] + t2[2] * e[2];
+      const double g1[3] = {sc * (w * t1[0] + b1 * gw[0]), sc * (w * t1[1] + b1 * gw[1]), sc * (w * t1[2] + b1 * gw[2])};
+      const double g2[3] = {sc * (w * t2[0] + b2 * gw[0]), sc * (w * t2[1] + b2 * gw[1]), sc * (w * t2[2] + b2 * gw[2])};
+      add_row(L, u, g1, sc * w * b1, acc);
+      add_row(L, u, g2, sc * w * b2, acc);
     }
   }
 
@@ -397,7 +398,7 @@ __host__ __device__ bool dogleg_compute_step(EstState& S) {
   return true;
 }
 
-__host__ __device__ void dogleg_update(EstState& S, const double* out28) {
+__host__ __device__ __noinline__ void dogleg_update(EstState& S, const double* out28) {
   double cost, g[6], H[36];
   unpack28(out28, &cost, g, H);
   auto grad_max = [&](const double* gg) {
@@ -521,7 +522,7 @@ extern int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float
 
 static int acc_grid(int n) {
   int g = div_up(n > 0 ? n : 1, 256);
-  const int cap = 4 * kNumSMs;
+  const int cap = MML_ACC_MINB * kNumSMs;  // one resident wave
   return g < cap ? g : cap;
 }
 

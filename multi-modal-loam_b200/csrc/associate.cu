@@ -484,29 +484,52 @@ __device__ bool search_shells(const GridLevel& L, const int* c, const int* lo, c
   for (int rr = rr0; rr <= rr1; rr++) {
     const int side = 2 * rr + 1;
     const int nseg = rr == 1 ? 27 : 2 * side * side;
-    for (int s = lg; s < nseg; s += G) {
-      int y, z, x0, x1;
-      if (rr == 1) {
-        const int dz = s / 9 - 1, dy = (s / 3) % 3 - 1, dx = s % 3 - 1;
-        z = c[2] + dz; y = c[1] + dy; x0 = x1 = c[0] + dx;
-        if (x0 < lo[0] || x0 > hi[0]) continue;
-      } else {
-        const int row = s >> 1, which = s & 1;
-        const int dz = row / side - rr, dy = row % side - rr;
-        z = c[2] + dz; y = c[1] + dy;
-        const bool full = dz == -rr || dz == rr || dy == -rr || dy == rr;
-        if (full) {
-          if (which) continue;
-          x0 = max(c[0] - rr, lo[0]); x1 = min(c[0] + rr, hi[0]);
-          if (x0 > x1) continue;
+    // every lane resolves one segment (cell or x-row) to its point range; the non-empty ranges are then scanned
+    // by the whole group together (lane-strided, coalesced), so a long row - e.g. along a map edge - is not
+    // left to a single lane
+    for (int base = 0; base < nseg; base += G) {
+      const int s = base + lg;
+      int p0 = 0, p1 = 0;
+      if (s < nseg) {
+        int y, z, x0, x1;
+        bool ok = true;
+        if (rr == 1) {
+          const int dz = s / 9 - 1, dy = (s / 3) % 3 - 1, dx = s % 3 - 1;
+          z = c[2] + dz; y = c[1] + dy; x0 = x1 = c[0] + dx;
+          ok = !(x0 < lo[0] || x0 > hi[0]);
         } else {
-          x0 = x1 = which ? c[0] + rr : c[0] - rr;
-          if (x0 < lo[0] || x0 > hi[0]) continue;
+          const int row = s >> 1, which = s & 1;
+          const int dz = row / side - rr, dy = row % side - rr;
+          z = c[2] + dz; y = c[1] + dy;
+          const bool full = dz == -rr || dz == rr || dy == -rr || dy == rr;
+          if (full) {
+            x0 = max(c[0] - rr, lo[0]); x1 = min(c[0] + rr, hi[0]);
+            ok = !which && x0 <= x1;
+          } else {
+            x0 = x1 = which ? c[0] + rr : c[0] - rr;
+            ok = !(x0 < lo[0] || x0 > hi[0]);
+          }
+        }
+        ok = ok && !(z < lo[2] || z > hi[2] || y < lo[1] || y > hi[1]);
+        if (ok) {
+          const int rowb = (z * L.dim[1] + y) * L.dim[0];
+          p0 = __ldg(L.cell_start + rowb + x0);
+          p1 = __ldg(L.cell_start + rowb + x1 + 1);
         }
       }
-      if (z < lo[2] || z > hi[2] || y < lo[1] || y > hi[1]) continue;
-      const int rowb = (z * L.dim[1] + y) * L.dim[0];
-      scan_cells(L, rowb + x0, rowb + x1, qx, qy, qz, r);
+      unsigned live = __ballot_sync(mask, p1 > p0);
+      if (G < 32) live = (live >> ((threadIdx.x & 31u) & ~(unsigned)(G - 1))) & ((1u << (G & 31)) - 1u);
+      while (live) {
+        const int src = __ffs(live) - 1;  // lane within the group
+        live &= live - 1;
+        const int b0 = __shfl_sync(mask, p0, src, G), b1 = __shfl_sync(mask, p1, src, G);
+        for (int k = b0 + lg; k < b1; k += G) {
+          const float4 p = __ldg(L.pts + k);
+          const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+          const float d = (dx * dx + dy * dy) + dz * dz;
+          knn_push(r, d, __float_as_int(p.w), k);
+        }
+      }
     }
     group_merge<G>(r, m, mask, lg);
     // lane 0 carries the merged list forward, the others start the next shell empty (no duplicates)

@@ -442,6 +442,26 @@ def main():
     roof["s3_accumulate"] = {"features": nq, "ms": ms_acc, "gbs": nq * BYTES_PER_FEATURE_EVAL / ms_acc / 1e6,
                              "note": "latency-bound at one-scan size"}
 
+    # batched extraction (SURVEY §8 d: >= 256 scans per launch), device resident, kernels only
+    nb = 256
+    bx = np.concatenate([scans[k % len(scans)][0] for k in range(nb)])
+    bl = np.concatenate([scans[k % len(scans)][1] for k in range(nb)])
+    boff = np.concatenate([[0], np.cumsum([scans[k % len(scans)][0].shape[0] for k in range(nb)])]).astype(np.int32)
+    bxd, bld = ctx.dev_upload(bx), ctx.dev_upload(bl)
+    blab = ctx.dev_upload(np.zeros(bx.shape[0], np.uint8))
+    ctx.extract_batch_dev_async(bxd, bld, boff, N_LINES, blab)
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(3):
+        ctx.extract_batch_dev_async(bxd, bld, boff, N_LINES, blab)
+    ms_ext = ctx.timer_stop_ms() / 3
+    roof["extract_batched"] = {"scans_per_launch_set": nb, "points": int(bx.shape[0]), "ms": ms_ext,
+                               "gbs": bx.shape[0] * BYTES_PER_POINT_EXTRACT / ms_ext / 1e6,
+                               "frac": bx.shape[0] * BYTES_PER_POINT_EXTRACT / ms_ext / 1e6 / peak,
+                               "scans_per_s": nb / (ms_ext / 1e3)}
+    for ptr in (bxd, bld, blab):
+        ctx.dev_free(ptr)
+
     s4 = None
     if not a.no_s4:
         # S4: 1M-pt map, Q in {28.8k, 240k, 1M} queries perturbed by the S1 offset (SURVEY §8 d)

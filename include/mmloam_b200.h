@@ -54,6 +54,10 @@ int mml_extract_features_batch(mml_ctx* ctx, const float* xyzi, const uint16_t* 
                                const int* scan_offsets, int n_scans, int n_lines, uint8_t* out_label,
                                int* out_n_sharp, int* out_n_flat);
 
+/* Device-resident, asynchronous form (kernels only; labels stay in HBM): used for batched throughput runs. */
+int mml_extract_features_batch_dev(mml_ctx* ctx, const void* xyzi_dev, const void* line_id_dev, const int* scan_offsets,
+                                   int n_scans, int n_lines, void* label_dev);
+
 /* ---- A2: getVeloFeature ring + relative time, FE.cpp:1136-1195. line_out = -1 rejected. */
 int mml_velo_ring_time(mml_ctx* ctx, const float* xyzi, int n, int16_t* line_out, float* reltime_out);
 /* ---- A3: getHoriFeatureExtract filter, FE.cpp:985-998 (CustomPoint fields as arrays). */
@@ -80,6 +84,10 @@ int mml_map_set(mml_ctx* ctx, int kind, const float* xyzi, int m, const int* cub
 int mml_map_set_ex(mml_ctx* ctx, int kind, const float* xyzi, int m, const int* cube_centre3, float cell);
 /* info8 = [valid, points, cell edge, dim x, dim y, dim z, cells, cells per 50 m cube]  */
 int mml_map_info(mml_ctx* ctx, int kind, double* info8);
+/* Test view of a built map level (0 fine, 1 coarse): cell-sorted points (xyz + original index bits) and the
+ * cell table; mml_map_dims: dims7 = [dim xyz, coarse dim xyz, coarse factor], org3 = grid origin.     */
+int mml_map_dump(mml_ctx* ctx, int kind, int level, float* pts_out, int* cell_start_out);
+int mml_map_dims(mml_ctx* ctx, int kind, int* dims7, double* org3);
 
 /* ---- A7 / A8: Estimator::processPointToLine EST.cpp:148-365 and
  * Estimator::processPointToPlanVec EST.cpp:573-777 (incl. A5 pointAssociateToMap +

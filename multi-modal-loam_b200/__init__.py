@@ -144,6 +144,11 @@ class Context:
                                                      _p(n_sharp), _p(n_flat)))
         return label[:n], n_sharp[:ns], n_flat[:ns]
 
+    def extract_batch_dev_async(self, xyzi_dev, line_dev, scan_offsets, n_lines, label_dev):
+        off = np.ascontiguousarray(scan_offsets, np.int32)
+        self._ck(self.lib.mml_extract_features_batch_dev(self.h, xyzi_dev, line_dev, _p(off), off.shape[0] - 1, int(n_lines),
+                                                         label_dev))
+
     # ---- A2 / A3
     def velo_ring_time(self, xyzi):
         xyzi = _f32(xyzi).reshape(-1, 4)

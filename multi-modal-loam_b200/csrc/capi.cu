@@ -165,12 +165,13 @@ int mml_extract_features_batch(mml_ctx* c, const float* xyzi, const uint16_t* li
   MML_CHECK(upload(c, c->in_line, line_id, sizeof(uint16_t) * (size_t)n));
   MML_CUDA(c, c->in_label.reserve((size_t)n + 16));
   std::vector<int> cnt(2 * (size_t)n_scans + 2, 0);
-  for (int attempt = 0; attempt < 2; attempt++) {
+  for (int attempt = 0; attempt < 3; attempt++) {
     MML_CHECK(mml_extract_device(c, c->in_xyzi.as<float4>(), c->in_line.as<uint16_t>(), scan_offsets, n_scans, n_lines,
-                                 c->in_label.as<uint8_t>(), attempt == 1));
+                                 c->in_label.as<uint8_t>(), c->sel_tier >= 2));
     MML_CHECK(download(c, cnt.data(), c->counters.p, sizeof(int) * (2 * (size_t)n_scans + 1)));
     MML_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (!cnt[2 * (size_t)n_scans]) break;  // no line overflowed the part-parallel kernel's shared memory
+    if (!cnt[2 * (size_t)n_scans]) break;  // no line overflowed the selection kernel's shared-memory tier
+    if (c->sel_tier < 2) c->sel_tier++;
   }
   MML_CHECK(download(c, out_label, c->in_label.p, (size_t)n));
   MML_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -436,7 +437,8 @@ static int scan_to_pose_general(mml_ctx* c, const void* xyzi_dev, const void* li
   MML_CUDA(c, c->tmp_e.reserve(sizeof(float4) * (size_t)(n > 0 ? n : 1)));
   const int off[2] = {0, n};
   if (c->profile) MML_CUDA(c, cudaEventRecord(c->pev[0], st));
-  MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, c->in_label.as<uint8_t>(), false));
+  MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, c->in_label.as<uint8_t>(),
+                               c->sel_tier >= 2));
   // undistort a copy of the scan (the caller's buffer stays untouched)
   mml::DevBuf& wbuf = c->srt_xyzi;  // the line-sorted copy is dead after extraction: reuse its storage
   MML_CUDA(c, wbuf.reserve(sizeof(float4) * (size_t)(n > 0 ? n : 1)));
@@ -450,8 +452,10 @@ static int scan_to_pose_general(mml_ctx* c, const void* xyzi_dev, const void* li
   int hc[3] = {0, 0, 0};
   MML_CHECK(download(c, hc, c->counters.p, sizeof(hc)));
   MML_CUDA(c, cudaStreamSynchronize(st));
-  if (hc[2]) {  // a line overflowed the part-parallel kernel: sequential fallback
-    MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, c->in_label.as<uint8_t>(), true));
+  while (hc[2] && c->sel_tier < 2) {  // a line overflowed the selection kernel's tier: next tier (2 = sequential)
+    c->sel_tier++;
+    MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, c->in_label.as<uint8_t>(),
+                                 c->sel_tier >= 2));
     MML_CHECK(download(c, hc, c->counters.p, sizeof(hc)));
     MML_CUDA(c, cudaStreamSynchronize(st));
   }
@@ -619,4 +623,14 @@ extern "C" int mml_map_dims(mml_ctx* c, int kind, int* dims7 /*dim xyz, dim2 xyz
   for (int a = 0; a < 3; a++) { dims7[a] = M.dim[a]; dims7[3 + a] = M.dim2[a]; org3[a] = M.org_d[a]; }
   dims7[6] = M.coarse;
   return MML_OK;
+}
+
+// Device-resident batched extraction (kernels only, asynchronous): scans concatenated in xyzi_dev / line_dev,
+// scan_offsets on the host. Labels go to label_dev. Used for the batched roofline figure (SURVEY.md §8 d).
+extern "C" int mml_extract_features_batch_dev(mml_ctx* c, const void* xyzi_dev, const void* line_dev, const int* scan_offsets,
+                                              int n_scans, int n_lines, void* label_dev) {
+  if (!c || !scan_offsets || n_scans < 0) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  return mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_dev, scan_offsets, n_scans, n_lines,
+                            (uint8_t*)label_dev, false);
 }

@@ -103,6 +103,7 @@ struct mml_ctx {
   mml::DevBuf chunk_tab, chunk_hist, line_start, line_count;
   mml::DevBuf curv, refl, attr, sort_ind, refl_ind;      // per-point extraction state
   mml::DevBuf counters;                                  // small int scratch
+  int sel_tier = 0;                                      // shared-memory tier of the selection kernel (extract.cu)
   int* counters_alt = nullptr;                           // when set, extraction writes its counters here
   mml::DevBuf tmp_a, tmp_b, tmp_c, tmp_d, tmp_e;         // generic
   mml::DevBuf vox_keys[2], vox_vals[2], vox_hist, vox_bbox;

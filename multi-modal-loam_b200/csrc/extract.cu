@@ -788,10 +788,13 @@ int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_
 
   int* overflow_flag = counters + 2 * (size_t)n_scans;
   const size_t kMaxSmem = 227 * 1024;
-  if (!force_sequential) {
-    // part-parallel selection; lines longer than the shared-memory capacity raise the overflow flag and the
-    // caller re-runs the sequential kernel (mml_extract_overflowed)
-    const int cap_n = max_n < 44032 ? ((max_n + 15) & ~15) : 44032;
+  if (!force_sequential && ctx->sel_tier < 2) {
+    // part-parallel selection. Shared memory is sized by a sticky per-context tier: tier 0 holds lines of up to
+    // 8192 points (41 KB: 5 CTAs per SM, what VLP-16 / Horizon frames need), tier 1 up to 44032 points (one CTA
+    // per SM, 240k-point Horizon clouds). A longer line raises the overflow flag; the caller bumps the tier and
+    // re-runs (tier 2 = the sequential kernel).
+    const int tier_cap = ctx->sel_tier == 0 ? 8192 : 44032;
+    const int cap_n = max_n < tier_cap ? ((max_n + 15) & ~15) : tier_cap;
     const size_t par_smem = 5 * (size_t)cap_n + 4 * ((((size_t)cap_n + 31) / 32 + 3) & ~(size_t)3);
     if (par_smem > 48 * 1024)
       MML_CUDA(ctx, cudaFuncSetAttribute(k_select_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)par_smem));

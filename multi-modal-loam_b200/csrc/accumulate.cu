@@ -97,6 +97,116 @@ __device__ __forceinline__ void add_row(const PoseLin& L, const double* u, const
   }
 }
 
+// compact 48 B records (csrc/associate.cu k_export / fit writers); false = empty slot
+__device__ __forceinline__ bool load_line(const float4* __restrict__ f, int i, double* p, double* a, double* b) {
+  const float4 f0 = __ldg(f + 3 * (size_t)i);
+  if (!(f0.w == 1.f)) return false;
+  const float4 f1 = __ldg(f + 3 * (size_t)i + 1), f2 = __ldg(f + 3 * (size_t)i + 2);
+  p[0] = f0.x; p[1] = f0.y; p[2] = f0.z;
+  a[0] = f1.x; a[1] = f1.y; a[2] = f1.z;
+  b[0] = f1.w; b[1] = f2.x; b[2] = f2.y;
+  return true;
+}
+__device__ __forceinline__ bool load_plane(const float4* __restrict__ f, int i, double* p, double* pp, double* n) {
+  const float4 f0 = __ldg(f + 3 * (size_t)i);
+  if (!(f0.w == 1.f)) return false;
+  const float4 f1 = __ldg(f + 3 * (size_t)i + 1), f2 = __ldg(f + 3 * (size_t)i + 2);
+  p[0] = f0.x; p[1] = f0.y; p[2] = f0.z;
+  n[0] = f2.x; n[1] = f2.y; n[2] = f2.z;
+  const double dist = (double)f1.w;
+  pp[0] = (double)f1.x - dist * n[0]; pp[1] = (double)f1.y - dist * n[1]; pp[2] = (double)f1.z - dist * n[2];
+  return true;
+}
+
+// point-to-line residual + Jacobian + Huber, CF.h:412-440, accumulated into acc[28]
+__device__ __forceinline__ void eval_line(const PoseLin& L, const double* p, const double* a, const double* b, double s_info,
+                                          double ha, double* acc) {
+  double u[3], P[3];
+  for (int r = 0; r < 3; r++) u[r] = L.Rbl[3 * r] * p[0] + L.Rbl[3 * r + 1] * p[1] + L.Rbl[3 * r + 2] * p[2] + L.Pbl[r];
+  for (int r = 0; r < 3; r++) P[r] = L.R[3 * r] * u[0] + L.R[3 * r + 1] * u[1] + L.R[3 * r + 2] * u[2] + L.t[r];
+  const double l12 = sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]));
+  const double c0 = (P[0] - a[0]) * (P[1] - b[1]) - (P[0] - b[0]) * (P[1] - a[1]);
+  const double c1 = (P[0] - a[0]) * (P[2] - b[2]) - (P[0] - b[0]) * (P[2] - a[2]);
+  const double c2 = (P[1] - a[1]) * (P[2] - b[2]) - (P[1] - b[1]) * (P[2] - a[2]);
+  const double a012 = sqrt(c0 * c0 + c1 * c1 + c2 * c2);
+  const double ld2 = a012 / l12;
+  const double PP = P[0] * P[0] + P[1] * P[1] + P[2] * P[2];
+  const double sq = sqrt(sqrt(PP));
+  const double w = 1.0 - 0.9 * fabs(ld2) / sq;
+  double r = s_info * w * ld2;
+  const double ch[3] = {c2 / a012, -c1 / a012, c0 / a012};
+  const double ab[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+  const double gd[3] = {(ab[1] * ch[2] - ab[2] * ch[1]) / l12, (ab[2] * ch[0] - ab[0] * ch[2]) / l12,
+                        (ab[0] * ch[1] - ab[1] * ch[0]) / l12};
+  const double k5 = 0.5 * ld2 / (PP * sq);
+  double gr[3];
+  for (int k = 0; k < 3; k++) gr[k] = s_info * (w * gd[k] + ld2 * (-0.9 * (gd[k] / sq - k5 * P[k])));
+  // Huber, CF.h:33-63 with rho'' <= 0
+  const double s = r * r;
+  double k1 = 1.0, rho = s;
+  if (ha > 0 && s > ha * ha) {
+    const double rr = sqrt(s);
+    k1 = sqrt(ha / rr);
+    rho = 2 * ha * rr - ha * ha;
+  }
+  acc[0] += 0.5 * rho;
+  r *= k1;
+  gr[0] *= k1; gr[1] *= k1; gr[2] *= k1;
+  add_row(L, u, gr, r, acc);
+}
+
+// point-to-plane (vector form) residual + Jacobian + Huber, CF.h:533-555
+__device__ __forceinline__ void eval_plane(const PoseLin& L, const double* p, const double* pp, const double* n, double s_info,
+                                           double w_tan, double ha, double* acc) {
+  double u[3], P[3];
+  for (int r = 0; r < 3; r++) u[r] = L.Rbl[3 * r] * p[0] + L.Rbl[3 * r + 1] * p[1] + L.Rbl[3 * r + 2] * p[2] + L.Pbl[r];
+  for (int r = 0; r < 3; r++) P[r] = L.R[3 * r] * u[0] + L.R[3 * r + 1] * u[1] + L.R[3 * r + 2] * u[2] + L.t[r];
+  const double e[3] = {P[0] - pp[0], P[1] - pp[1], P[2] - pp[2]};
+  const double en = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+  const double PP = P[0] * P[0] + P[1] * P[1] + P[2] * P[2];
+  const double sq = sqrt(sqrt(PP));
+  const double w = 1.0 - 0.9 * en / sq;
+  const double k5 = 0.5 * en / (PP * sq);
+  double gw[3];
+  for (int k = 0; k < 3; k++) gw[k] = -0.9 * ((e[k] / en) / sq - k5 * P[k]);
+  // residual in the canonical basis [n t1 t2]: sqrt_info^T sqrt_info = (n n^T + w_t^2 (I - n n^T)) / lidar_m^2.
+  // ||r||^2 needs no basis: (s w)^2 [ (n.e)^2 + w_t^2 (|e|^2 - (n.e)^2) ]
+  const double ne = n[0] * e[0] + n[1] * e[1] + n[2] * e[2];
+  const double sw = s_info * w;
+  double s = sw * sw * ne * ne;
+  if (w_tan != 0.0) s += sw * sw * w_tan * w_tan * fmax(en * en - ne * ne, 0.0);
+  double k1 = 1.0, rho = s;
+  if (ha > 0 && s > ha * ha) {
+    const double rr = sqrt(s);
+    k1 = sqrt(ha / rr);
+    rho = 2 * ha * rr - ha * ha;
+  }
+  acc[0] += 0.5 * rho;
+  {
+    const double sc = k1 * s_info;
+    const double gr[3] = {sc * (w * n[0] + ne * gw[0]), sc * (w * n[1] + ne * gw[1]), sc * (w * n[2] + ne * gw[2])};
+    add_row(L, u, gr, sc * w * ne, acc);
+  }
+  if (w_tan != 0.0) {  // window size 5 only (EST.cpp:1203): the two tangential rows
+    int kk = 0;
+    if (fabs(n[1]) < fabs(n[kk])) kk = 1;
+    if (fabs(n[2]) < fabs(n[kk])) kk = 2;
+    double ex[3] = {0, 0, 0};
+    ex[kk] = 1.0;
+    const double v[3] = {ex[1] * n[2] - ex[2] * n[1], ex[2] * n[0] - ex[0] * n[2], ex[0] * n[1] - ex[1] * n[0]};
+    const double nv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    const double t1[3] = {v[0] / nv, v[1] / nv, v[2] / nv};
+    const double t2[3] = {n[1] * t1[2] - n[2] * t1[1], n[2] * t1[0] - n[0] * t1[2], n[0] * t1[1] - n[1] * t1[0]};
+    const double sc = k1 * s_info * w_tan;
+    const double b1 = t1[0] * e[0] + t1[1] * e[1] + t1[2] * e[2];
+    const double b2 = t2[0] * e[0] + t2[1] * e[1] + t2[2] * e[2];
+    const double g1[3] = {sc * (w * t1[0] + b1 * gw[0]), sc * (w * t1[1] + b1 * gw[1]), sc * (w * t1[2] + b1 * gw[2])};
+    const double g2[3] = {sc * (w * t2[0] + b2 * gw[0]), sc * (w * t2[1] + b2 * gw[1]), sc * (w * t2[2] + b2 * gw[2])};
+    add_row(L, u, g1, sc * w * b1, acc);
+    add_row(L, u, g2, sc * w * b2, acc);
+  }
+}
+
 struct AccArgs {
   const float4* f_line;
   const float4* f_plane;
@@ -149,45 +259,9 @@ __global__ void __launch_bounds__(256, MML_ACC_MINB) k_accumulate(AccArgs A) {
       if (!(f[10] == 1.0)) continue;
       for (int k = 0; k < 3; k++) { p[k] = f[k]; a[k] = f[3 + k]; b[k] = f[6 + k]; }
     } else {
-      const float4 f0 = __ldg(A.f_line + 3 * (size_t)i);
-      if (!(f0.w == 1.f)) continue;
-      const float4 f1 = __ldg(A.f_line + 3 * (size_t)i + 1), f2 = __ldg(A.f_line + 3 * (size_t)i + 2);
-      p[0] = f0.x; p[1] = f0.y; p[2] = f0.z;
-      a[0] = f1.x; a[1] = f1.y; a[2] = f1.z;
-      b[0] = f1.w; b[1] = f2.x; b[2] = f2.y;
+      if (!load_line(A.f_line, i, p, a, b)) continue;
     }
-    double u[3], P[3];
-    for (int r = 0; r < 3; r++) u[r] = L.Rbl[3 * r] * p[0] + L.Rbl[3 * r + 1] * p[1] + L.Rbl[3 * r + 2] * p[2] + L.Pbl[r];
-    for (int r = 0; r < 3; r++) P[r] = L.R[3 * r] * u[0] + L.R[3 * r + 1] * u[1] + L.R[3 * r + 2] * u[2] + L.t[r];
-    const double l12 = sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]));
-    const double c0 = (P[0] - a[0]) * (P[1] - b[1]) - (P[0] - b[0]) * (P[1] - a[1]);
-    const double c1 = (P[0] - a[0]) * (P[2] - b[2]) - (P[0] - b[0]) * (P[2] - a[2]);
-    const double c2 = (P[1] - a[1]) * (P[2] - b[2]) - (P[1] - b[1]) * (P[2] - a[2]);
-    const double a012 = sqrt(c0 * c0 + c1 * c1 + c2 * c2);
-    const double ld2 = a012 / l12;
-    const double PP = P[0] * P[0] + P[1] * P[1] + P[2] * P[2];
-    const double sq = sqrt(sqrt(PP));
-    const double w = 1.0 - 0.9 * fabs(ld2) / sq;
-    double r = s_info * w * ld2;
-    const double ch[3] = {c2 / a012, -c1 / a012, c0 / a012};
-    const double ab[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
-    const double gd[3] = {(ab[1] * ch[2] - ab[2] * ch[1]) / l12, (ab[2] * ch[0] - ab[0] * ch[2]) / l12,
-                          (ab[0] * ch[1] - ab[1] * ch[0]) / l12};
-    const double k5 = 0.5 * ld2 / (PP * sq);
-    double gr[3];
-    for (int k = 0; k < 3; k++) gr[k] = s_info * (w * gd[k] + ld2 * (-0.9 * (gd[k] / sq - k5 * P[k])));
-    // Huber, CF.h:33-63 with rho'' <= 0
-    const double s = r * r;
-    double k1 = 1.0, rho = s;
-    if (ha > 0 && s > ha * ha) {
-      const double rr = sqrt(s);
-      k1 = sqrt(ha / rr);
-      rho = 2 * ha * rr - ha * ha;
-    }
-    acc[0] += 0.5 * rho;
-    r *= k1;
-    gr[0] *= k1; gr[1] *= k1; gr[2] *= k1;
-    add_row(L, u, gr, r, acc);
+    eval_line(L, p, a, b, s_info, ha, acc);
   }
 
   // ---- point-to-plane (vector form), CF.h:533-555
@@ -198,61 +272,9 @@ __global__ void __launch_bounds__(256, MML_ACC_MINB) k_accumulate(AccArgs A) {
       if (!(f[10] == 1.0)) continue;
       for (int k = 0; k < 3; k++) { p[k] = f[k]; pp[k] = f[3 + k]; n[k] = f[6 + k]; }
     } else {
-      const float4 f0 = __ldg(A.f_plane + 3 * (size_t)i);
-      if (!(f0.w == 1.f)) continue;
-      const float4 f1 = __ldg(A.f_plane + 3 * (size_t)i + 1), f2 = __ldg(A.f_plane + 3 * (size_t)i + 2);
-      p[0] = f0.x; p[1] = f0.y; p[2] = f0.z;
-      n[0] = f2.x; n[1] = f2.y; n[2] = f2.z;
-      const double dist = (double)f1.w;
-      pp[0] = (double)f1.x - dist * n[0]; pp[1] = (double)f1.y - dist * n[1]; pp[2] = (double)f1.z - dist * n[2];
+      if (!load_plane(A.f_plane, i, p, pp, n)) continue;
     }
-    double u[3], P[3];
-    for (int r = 0; r < 3; r++) u[r] = L.Rbl[3 * r] * p[0] + L.Rbl[3 * r + 1] * p[1] + L.Rbl[3 * r + 2] * p[2] + L.Pbl[r];
-    for (int r = 0; r < 3; r++) P[r] = L.R[3 * r] * u[0] + L.R[3 * r + 1] * u[1] + L.R[3 * r + 2] * u[2] + L.t[r];
-    const double e[3] = {P[0] - pp[0], P[1] - pp[1], P[2] - pp[2]};
-    const double en = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
-    const double PP = P[0] * P[0] + P[1] * P[1] + P[2] * P[2];
-    const double sq = sqrt(sqrt(PP));
-    const double w = 1.0 - 0.9 * en / sq;
-    const double k5 = 0.5 * en / (PP * sq);
-    double gw[3];
-    for (int k = 0; k < 3; k++) gw[k] = -0.9 * ((e[k] / en) / sq - k5 * P[k]);
-    // residual in the canonical basis [n t1 t2]: sqrt_info^T sqrt_info = (n n^T + w_t^2 (I - n n^T)) / lidar_m^2.
-    // ||r||^2 needs no basis: (s w)^2 [ (n.e)^2 + w_t^2 (|e|^2 - (n.e)^2) ]
-    const double ne = n[0] * e[0] + n[1] * e[1] + n[2] * e[2];
-    const double sw = s_info * w;
-    double s = sw * sw * ne * ne;
-    if (w_tan != 0.0) s += sw * sw * w_tan * w_tan * fmax(en * en - ne * ne, 0.0);
-    double k1 = 1.0, rho = s;
-    if (ha > 0 && s > ha * ha) {
-      const double rr = sqrt(s);
-      k1 = sqrt(ha / rr);
-      rho = 2 * ha * rr - ha * ha;
-    }
-    acc[0] += 0.5 * rho;
-    {
-      const double sc = k1 * s_info;
-      const double gr[3] = {sc * (w * n[0] + ne * gw[0]), sc * (w * n[1] + ne * gw[1]), sc * (w * n[2] + ne * gw[2])};
-      add_row(L, u, gr, sc * w * ne, acc);
-    }
-    if (w_tan != 0.0) {  // window size 5 only (EST.cpp:1203): the two tangential rows
-      int kk = 0;
-      if (fabs(n[1]) < fabs(n[kk])) kk = 1;
-      if (fabs(n[2]) < fabs(n[kk])) kk = 2;
-      double ex[3] = {0, 0, 0};
-      ex[kk] = 1.0;
-      const double v[3] = {ex[1] * n[2] - ex[2] * n[1], ex[2] * n[0] - ex[0] * n[2], ex[0] * n[1] - ex[1] * n[0]};
-      const double nv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-      const double t1[3] = {v[0] / nv, v[1] / nv, v[2] / nv};
-      const double t2[3] = {n[1] * t1[2] - n[2] * t1[1], n[2] * t1[0] - n[0] * t1[2], n[0] * t1[1] - n[1] * t1[0]};
-      const double sc = k1 * s_info * w_tan;
-      const double b1 = t1[0] * e[0] + t1[1] * e[1] + t1[2] * e[2];
-      const double b2 = t2[0] * e[0] + t2[1] * e[1] + t2[2] * e[2];
-      const double g1[3] = {sc * (w * t1[0] + b1 * gw[0]), sc * (w * t1[1] + b1 * gw[1]), sc * (w * t1[2] + b1 * gw[2])};
-      const double g2[3] = {sc * (w * t2[0] + b2 * gw[0]), sc * (w * t2[1] + b2 * gw[1]), sc * (w * t2[2] + b2 * gw[2])};
-      add_row(L, u, g1, sc * w * b1, acc);
-      add_row(L, u, g2, sc * w * b2, acc);
-    }
+    eval_plane(L, p, pp, n, s_info, w_tan, ha, acc);
   }
 
   // ---- CTA reduction: warp shuffles, then 8 warps through shared memory
@@ -459,16 +481,11 @@ __host__ __device__ __noinline__ void dogleg_update(EstState& S, const double* o
 }
 
 // ---------------------------------------------------------------- outer loop bookkeeping
-// EST.cpp:1212 vector2double + EST.cpp:1268-1270 T_wl + thres_dist schedule (EST.cpp:1207, 1377-1381)
-__global__ void k_est_begin_outer(EstState* S) {
-  if (threadIdx.x != 0 || S->done_outer) return;
+// EST.cpp:1268-1270 T_wl + thres_dist schedule (EST.cpp:1207, 1377-1381): what the association needs
+__device__ inline void est_begin_assoc(EstState* S) {
   const int it = S->outer_next;
   S->outer_it = it;
   const Quat Q = {S->Q[0], S->Q[1], S->Q[2], S->Q[3]};
-  S->x[0] = S->P[0]; S->x[1] = S->P[1]; S->x[2] = S->P[2];
-  so3_log(Q, S->x + 3);
-  for (int i = 0; i < 4; i++) S->q_before[i] = S->Q[i];
-  for (int i = 0; i < 3; i++) S->t_before[i] = S->P[i];
   double Rq[9];
   quat_to_R(Q, Rq);
   // exRbl = Rbl, exPbl = Pbl
@@ -479,13 +496,20 @@ __global__ void k_est_begin_outer(EstState* S) {
   }
   S->T_wl[12] = 0; S->T_wl[13] = 0; S->T_wl[14] = 0; S->T_wl[15] = 1;
   S->thres = (float)S->thres_sched[it < 2 ? it : 2];
+}
+// EST.cpp:1212 vector2double: what the solve needs (idempotent)
+__device__ inline void est_begin_solve(EstState* S) {
+  const Quat Q = {S->Q[0], S->Q[1], S->Q[2], S->Q[3]};
+  S->x[0] = S->P[0]; S->x[1] = S->P[1]; S->x[2] = S->P[2];
+  so3_log(Q, S->x + 3);
+  for (int i = 0; i < 4; i++) S->q_before[i] = S->Q[i];
+  for (int i = 0; i < 3; i++) S->t_before[i] = S->P[i];
   S->first = 1;
   S->done_inner = 0;
 }
 
 // EST.cpp:771-775 localizability, EST.cpp:1439-1450 convergence test
-__global__ void k_est_end_outer(EstState* S, const double* assoc_stats) {
-  if (threadIdx.x != 0 || S->done_outer) return;
+__device__ inline void est_end(EstState* S, const double* assoc_stats) {
   const int* ints = reinterpret_cast<const int*>(assoc_stats + 16);
   S->n_line = ints[0];
   S->n_plane = ints[1];
@@ -511,6 +535,140 @@ __global__ void k_est_end_outer(EstState* S, const double* assoc_stats) {
   const double deltaT = sqrt((d0 * d0 + d1 * d1) + d2 * d2);
   if ((deltaR < 0.05 && deltaT < 0.05) || (S->outer_it + 1) == S->max_outer) S->done_outer = 1;
   S->outer_next = S->outer_it + 1;
+}
+
+// Start of a solve: the state upload, the zeroing of the association statistics and the first
+// begin-of-outer-iteration in one launch (parameters travel as kernel arguments).
+struct EstInit {
+  double P[3], Q[4], Rbl[9], Pbl[3];
+  double lidar_m, w_tan, huber_a, thres_sched[3];
+  int max_outer, max_inner;
+};
+__global__ void __launch_bounds__(128) k_est_init(EstState* S, EstInit I, unsigned* assoc_stats_words, unsigned* acc_out_words) {
+  unsigned* w = reinterpret_cast<unsigned*>(S);
+  for (int i = threadIdx.x; i < (int)(sizeof(EstState) / 4); i += 128) w[i] = 0u;
+  assoc_stats_words[threadIdx.x] = 0u;  // 512 B
+  if (threadIdx.x < 64) acc_out_words[threadIdx.x] = 0u;  // 32 doubles
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int i = 0; i < 3; i++) { S->P[i] = I.P[i]; S->Pbl[i] = I.Pbl[i]; S->thres_sched[i] = I.thres_sched[i]; }
+  for (int i = 0; i < 4; i++) S->Q[i] = I.Q[i];
+  for (int i = 0; i < 9; i++) S->Rbl[i] = I.Rbl[i];
+  S->max_outer = I.max_outer; S->max_inner = I.max_inner;
+  S->lidar_m = I.lidar_m; S->w_tan = I.w_tan; S->huber_a = I.huber_a;
+  est_begin_assoc(S);
+  est_begin_solve(S);
+}
+
+__global__ void k_est_begin_outer(EstState* S) {
+  if (threadIdx.x != 0 || S->done_outer) return;
+  est_begin_assoc(S);
+  est_begin_solve(S);
+}
+__global__ void k_est_end_outer(EstState* S, const double* assoc_stats) {
+  if (threadIdx.x != 0 || S->done_outer) return;
+  est_end(S, assoc_stats);
+}
+
+// ---------------------------------------------------------------- one-CTA solve of a scan-sized frame
+// For a scan's worth of features (a few thousand) a dogleg iteration is a dependent chain of ~5 us, and a
+// kernel launch per evaluation doubles it. k_solve_frame keeps the whole trust-region loop of one outer
+// iteration in one CTA: solver state and linearisation in shared memory, features re-read through L1
+// (<= 8192 x 48 B), fixed-order reduction (warp shuffles, then warps in index order), thread 0 runs the
+// dogleg update, and the tail does the convergence test and prepares T_wl / thres_dist for the next
+// association - so an outer iteration is association || association -> this kernel.
+#ifndef MML_SOLVE_THREADS
+#define MML_SOLVE_THREADS 512
+#endif
+constexpr int kSolveThreads = MML_SOLVE_THREADS;
+constexpr int kSolveWarps = kSolveThreads / 32;
+constexpr int kSolveFrameMax = 6144;  // feature slots (corner + surf queries) above which k_accumulate's grid wins
+
+struct SolveArgs {
+  const float4* f_line;
+  const float4* f_plane;
+  const int* n_dev;  // [n_corner, n_surf]
+  EstState* st;
+  const double* assoc_stats;
+};
+
+__global__ void __launch_bounds__(kSolveThreads, 1) k_solve_frame(SolveArgs A) {
+  if (A.st->done_outer) return;
+  __shared__ EstState S;
+  __shared__ PoseLin L;
+  __shared__ double sred[kSolveWarps][28];
+  __shared__ double tot[28];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {
+    const unsigned* src = reinterpret_cast<const unsigned*>(A.st);
+    unsigned* dst = reinterpret_cast<unsigned*>(&S);
+    for (int i = tid; i < (int)(sizeof(EstState) / 4); i += kSolveThreads) dst[i] = src[i];
+  }
+  __syncthreads();
+  if (tid == 0) est_begin_solve(&S);
+  const int n_line = A.n_dev[0], n_all = n_line + A.n_dev[1];
+  __syncthreads();
+  const double s_info = 1.0 / S.lidar_m, w_tan = S.w_tan, ha = S.huber_a;
+#ifdef MML_SOLVE_PROF
+  long long tp[5] = {0, 0, 0, 0, 0}, t0 = clock64(), t1;
+  int n_it = 0;
+#define TICK(k) { t1 = clock64(); tp[k] += t1 - t0; t0 = t1; }
+#else
+#define TICK(k)
+#endif
+  for (;;) {
+    if (tid == 0) make_pose(S.first ? S.x : S.x_cand, S.Rbl, S.Pbl, L);
+    __syncthreads();
+    TICK(0)
+    double acc[28];
+#pragma unroll
+    for (int k = 0; k < 28; k++) acc[k] = 0.0;
+    for (int i = tid; i < n_all; i += kSolveThreads) {
+      double p[3], a[3], b[3];
+      if (i < n_line) {
+        if (load_line(A.f_line, i, p, a, b)) eval_line(L, p, a, b, s_info, ha, acc);
+      } else {
+        if (load_plane(A.f_plane, i - n_line, p, a, b)) eval_plane(L, p, a, b, s_info, w_tan, ha, acc);
+      }
+    }
+    TICK(1)
+#pragma unroll
+    for (int k = 0; k < 28; k++) {
+      double v = acc[k];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if (lane == 0) sred[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid < 28) {
+      double v = 0;
+#pragma unroll
+      for (int w = 0; w < kSolveWarps; w++) v += sred[w][tid];
+      tot[tid] = v;
+    }
+    __syncthreads();
+    TICK(2)
+    if (tid == 0) dogleg_update(S, tot);
+    __syncthreads();
+    TICK(3)
+#ifdef MML_SOLVE_PROF
+    n_it++;
+#endif
+    if (S.done_inner) break;
+  }
+#ifdef MML_SOLVE_PROF
+  if (tid == 0) printf("solve: n=%d evals=%d pose=%lld eval=%lld reduce=%lld update=%lld cycles\n", n_all, n_it, tp[0], tp[1], tp[2], tp[3]);
+#endif
+  if (tid == 0) {
+    est_end(&S, A.assoc_stats);
+    if (!S.done_outer) est_begin_assoc(&S);
+  }
+  __syncthreads();
+  {
+    const unsigned* src = reinterpret_cast<const unsigned*>(&S);
+    unsigned* dst = reinterpret_cast<unsigned*>(A.st);
+    for (int i = tid; i < (int)(sizeof(EstState) / 4); i += kSolveThreads) dst[i] = src[i];
+  }
 }
 
 }  // namespace mml
@@ -565,7 +723,8 @@ int mml_accumulate_launch(mml_ctx* ctx, const double* x6, const double* T_bl16, 
 // Full Estimate loop for one frame on the device (window size 1). Queries must be in the
 // frame slot (q_corner / q_surf with device counts in `cnt_dev`, capacities cap_*).
 int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int cap_surf, const double* exTlb16,
-                        double* P3, double* q4, const mml_est_params* prm, double* stats) {
+                        double* P3, double* q4, const mml_est_params* prm, double* stats, int (*after_first_launch)(void*),
+                        void* hook_arg) {
   cudaStream_t st = ctx->stream;
   MML_CUDA(ctx, ctx->est_state.reserve(sizeof(EstState) + 64));
   MML_CUDA(ctx, ctx->acc_partials.reserve(sizeof(double) * 28 * (size_t)(4 * kNumSMs) + 64));
@@ -577,29 +736,25 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
   MML_CUDA(ctx, ctx->assoc_part[1].reserve(sizeof(double) * 8 * (size_t)(div_up(cap_surf + 1, 4) + 1) + 64));
   EstState* S = ctx->est_state.as<EstState>();
 
-  // host-side initial state
+  // initial state: one launch (k_est_init), parameters as kernel arguments
   MML_CUDA(ctx, ctx->pin_out.reserve(sizeof(EstState) + 64));
-  MML_CUDA(ctx, cudaStreamSynchronize(st));
   EstState* h = ctx->pin_out.as<EstState>();
-  memset(h, 0, sizeof(EstState));
-  for (int i = 0; i < 3; i++) h->P[i] = P3[i];
-  for (int i = 0; i < 4; i++) h->Q[i] = q4[i];
+  EstInit I;
+  for (int i = 0; i < 3; i++) I.P[i] = P3[i];
+  for (int i = 0; i < 4; i++) I.Q[i] = q4[i];
   // exRbl = R^T, exPbl = -R^T t (EST.cpp:1155-1156); CF.h:405-408 re-normalises R_bl via a quaternion
-  double Rbl[9];
   for (int r = 0; r < 3; r++)
-    for (int c = 0; c < 3; c++) Rbl[3 * r + c] = exTlb16[4 * c + r];
+    for (int c = 0; c < 3; c++) I.Rbl[3 * r + c] = exTlb16[4 * c + r];
   for (int r = 0; r < 3; r++)
-    h->Pbl[r] = -1.0 * (Rbl[3 * r] * exTlb16[3] + Rbl[3 * r + 1] * exTlb16[7] + Rbl[3 * r + 2] * exTlb16[11]);
-  for (int i = 0; i < 9; i++) h->Rbl[i] = Rbl[i];
-  h->max_outer = prm->max_outer;
-  h->max_inner = prm->max_inner;
-  h->lidar_m = prm->lidar_m;
-  h->w_tan = prm->plan_weight_tan;
-  h->huber_a = prm->use_huber ? 0.1 / prm->lidar_m : 0.0;
-  h->thres_sched[0] = prm->thres0; h->thres_sched[1] = prm->thres1; h->thres_sched[2] = prm->thres2;
-  MML_CUDA(ctx, cudaMemcpyAsync(S, h, sizeof(EstState), cudaMemcpyHostToDevice, st));
-  MML_CUDA(ctx, cudaMemsetAsync(ctx->acc_out.p, 0, sizeof(double) * 32, st));
-  MML_CUDA(ctx, cudaMemsetAsync(ctx->assoc_stats.p, 0, 512, st));
+    I.Pbl[r] = -1.0 * (I.Rbl[3 * r] * exTlb16[3] + I.Rbl[3 * r + 1] * exTlb16[7] + I.Rbl[3 * r + 2] * exTlb16[11]);
+  I.max_outer = prm->max_outer;
+  I.max_inner = prm->max_inner;
+  I.lidar_m = prm->lidar_m;
+  I.w_tan = prm->plan_weight_tan;
+  I.huber_a = prm->use_huber ? 0.1 / prm->lidar_m : 0.0;
+  I.thres_sched[0] = prm->thres0; I.thres_sched[1] = prm->thres1; I.thres_sched[2] = prm->thres2;
+  k_est_init<<<1, 128, 0, st>>>(S, I, ctx->assoc_stats.as<unsigned>(), ctx->acc_out.as<unsigned>());
+  MML_LAUNCHED(ctx);
 
   // graph key: every pointer / capacity baked into the captured launches
   long long key = 1469598103934665603ll;
@@ -619,6 +774,9 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
   // 1 + max_inner evaluations, each fused with its dogleg update | end. The host replays it until the device
   // reports convergence (EST.cpp:1448): a well-predicted scan costs one graph and one short synchronisation
   // and no idle no-op launches for iterations 2-5.
+  static const int solve_env = getenv("MML_SOLVE_MODE") ? atoi(getenv("MML_SOLVE_MODE")) : -1;  // 0 = launch per evaluation
+  const bool small = solve_env >= 0 ? solve_env != 0 : ctx->solve_small != 0;
+  mix(small ? 7 : 3);
   if (!ctx->est_graph || ctx->est_graph_key != key) {
     if (ctx->est_graph) { cudaGraphExecDestroy(ctx->est_graph); ctx->est_graph = nullptr; }
     cudaGraph_t graph = nullptr;
@@ -626,8 +784,10 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
     cudaStream_t st2 = ctx->stream2;
     MML_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     int rc = MML_OK;
-    k_est_begin_outer<<<1, 32, 0, st>>>(S);
-    MML_LAUNCHED(ctx);
+    if (!small) {
+      k_est_begin_outer<<<1, 32, 0, st>>>(S);
+      MML_LAUNCHED(ctx);
+    }
     cudaEventRecord(ctx->ev_fork, st);
     cudaStreamWaitEvent(st2, ctx->ev_fork, 0);
     ctx->stream = st2;
@@ -636,10 +796,21 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
     if (rc == MML_OK) rc = mml_associate_launch(ctx, 0, nullptr, 0.f, S->T_wl, &S->thres, &S->done_outer, cnt_dev, cap_corner);
     cudaEventRecord(ctx->ev_join, st2);
     cudaStreamWaitEvent(st, ctx->ev_join, 0);
-    for (int k = 0; k <= prm->max_inner && rc == MML_OK; k++)
-      rc = mml_accumulate_launch(ctx, nullptr, nullptr, 0, 0, 0, S, cnt_dev, cap_corner, cap_surf, nullptr, nullptr);
-    k_est_end_outer<<<1, 32, 0, st>>>(S, ctx->assoc_stats.as<double>());
-    MML_LAUNCHED(ctx);
+    if (small) {
+      SolveArgs SA;
+      SA.f_line = ctx->f_line.as<float4>();
+      SA.f_plane = ctx->f_plane.as<float4>();
+      SA.n_dev = cnt_dev;
+      SA.st = S;
+      SA.assoc_stats = ctx->assoc_stats.as<double>();
+      k_solve_frame<<<1, kSolveThreads, 0, st>>>(SA);
+      MML_LAUNCHED(ctx);
+    } else {
+      for (int k = 0; k <= prm->max_inner && rc == MML_OK; k++)
+        rc = mml_accumulate_launch(ctx, nullptr, nullptr, 0, 0, 0, S, cnt_dev, cap_corner, cap_surf, nullptr, nullptr);
+      k_est_end_outer<<<1, 32, 0, st>>>(S, ctx->assoc_stats.as<double>());
+      MML_LAUNCHED(ctx);
+    }
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
     ctx->est_launches_per_graph = ctx->launches - launches_before;
     ctx->launches = launches_before;
@@ -649,6 +820,7 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
     cudaGraphDestroy(graph);
     ctx->est_graph_key = key;
   }
+  int* h_cnt = reinterpret_cast<int*>(reinterpret_cast<char*>(h) + sizeof(EstState));
   int launched = 0;
   while (launched < prm->max_outer) {
     // scans whose prediction is poor need several outer iterations: after the first convergence check the
@@ -659,10 +831,18 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
       ctx->launches += ctx->est_launches_per_graph;
       launched++;
     }
+    if (after_first_launch) {  // host work the caller wants overlapped with the solve (next scan's extraction)
+      const int rc = after_first_launch(hook_arg);
+      after_first_launch = nullptr;
+      MML_CHECK(rc);
+    }
     MML_CUDA(ctx, cudaMemcpyAsync(h, S, sizeof(EstState), cudaMemcpyDeviceToHost, st));
+    if (launched == 1) MML_CUDA(ctx, cudaMemcpyAsync(h_cnt, cnt_dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     MML_CUDA(ctx, cudaStreamSynchronize(st));
     if (h->done_outer) break;
   }
+  // frames with more feature slots than one CTA turns over quickly go back to a launch per evaluation
+  ctx->solve_small = (long long)h_cnt[0] + h_cnt[1] <= kSolveFrameMax;
   for (int i = 0; i < 3; i++) P3[i] = h->P[i];
   for (int i = 0; i < 4; i++) q4[i] = h->Q[i];
   if (stats) {

@@ -28,8 +28,6 @@ int mml_split_voxel_capacity();
 int mml_split_voxel_device(mml_ctx* ctx, const float4* pts_d, const float* s_d, const uint8_t* label_d, int n,
                            const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, float4* corner_out,
                            float4* surf_out, int* counts_d);
-int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int cap_surf, const double* exTlb16,
-                        double* P3, double* q4, const mml_est_params* prm, double* stats);
 
 using namespace mml;
 

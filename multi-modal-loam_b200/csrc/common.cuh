@@ -125,6 +125,7 @@ struct mml_ctx {
   mml::DevBuf assoc_part[2];      // per-CTA moment partials of the line / plane association
   cudaGraphExec_t est_graph = nullptr;
   long long est_graph_key = 0;
+  int solve_small = 1;                                   // sticky: scan-sized frames use the one-CTA solve (accumulate.cu)
   long long est_launches_per_graph = 0;
   std::vector<int> last_scan_off;  // scan offsets the resident chunk table was built for
   void* odom = nullptr;            // pipelined odometry runner state (odometry.cu)
@@ -160,3 +161,9 @@ static inline int mml_fail(mml_ctx* ctx, int code, const char* msg) {
 }
 
 static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Estimate loop of one frame on the device (accumulate.cu). after_first_launch (optional) runs on the host right
+// after the first outer iteration has been enqueued, i.e. overlapped with it.
+int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int cap_surf, const double* exTlb16,
+                        double* P3, double* q4, const mml_est_params* prm, double* stats,
+                        int (*after_first_launch)(void*) = nullptr, void* hook_arg = nullptr);

@@ -18,8 +18,6 @@ int mml_split_voxel_capacity();
 int mml_split_voxel_device(mml_ctx* ctx, const float4* pts_d, const float* s_d, const uint8_t* label_d, int n,
                            const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, float4* corner_out,
                            float4* surf_out, int* counts_d);
-int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int cap_surf, const double* exTlb16,
-                        double* P3, double* q4, const mml_est_params* prm, double* stats);
 
 namespace {
 
@@ -136,10 +134,17 @@ int mml_odom_run(mml_ctx* c, const void* const* xyzi, const void* const* line, c
   if (n_scans > 0)
     MML_CHECK(submit(c, o, 0, xyzi[0], line[0], s ? s[0] : nullptr, n_pts[0], n_lines, host_buffers != 0, &xd[0], &sd[0]));
   for (int k = 0; k < n_scans; k++) {
-    // the reference's pipeline: the extractor node is already working on the next scan
-    if (k + 1 < n_scans)
-      MML_CHECK(submit(c, o, k + 1, xyzi[k + 1], line[k + 1], s ? s[k + 1] : nullptr, n_pts[k + 1], n_lines, host_buffers != 0,
-                       &xd[(k + 1) & 1], &sd[(k + 1) & 1]));
+    // the reference's pipeline: the extractor node works on the next scan meanwhile. Its launches are issued from
+    // the hook below, after this scan's critical-path work is already in the stream.
+    struct Next {
+      mml_ctx* c; Odom* o; int k; const void* xyzi; const void* line; const void* s; int n, n_lines; bool host;
+      const void** xd; const void** sd;
+    } nx = {c, o, k + 1, nullptr, nullptr, nullptr, 0, n_lines, host_buffers != 0, &xd[(k + 1) & 1], &sd[(k + 1) & 1]};
+    if (k + 1 < n_scans) { nx.xyzi = xyzi[k + 1]; nx.line = line[k + 1]; nx.s = s ? s[k + 1] : nullptr; nx.n = n_pts[k + 1]; }
+    auto submit_next = [](void* a) -> int {
+      Next* x = static_cast<Next*>(a);
+      return submit(x->c, x->o, x->k, x->xyzi, x->line, x->s, x->n, x->n_lines, x->host, x->xd, x->sd);
+    };
     Slot& S = o->slot[k & 1];
     // constant-velocity prediction and the motion used for undistortion
     double Tinv[16], delta[16], Tp[16];
@@ -160,7 +165,8 @@ int mml_odom_run(mml_ctx* c, const void* const* xyzi, const void* const* line, c
     int* hf = c->pin_flags.as<int>();
     MML_CUDA(c, cudaMemcpyAsync(hf, S.counters.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
     MML_CUDA(c, cudaMemcpyAsync(hf + 4, cnt, 5 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    MML_CHECK(mml_estimate_device(c, cnt, cap, cap, exTlb16, P, q, prm, stats));  // synchronises `st`
+    MML_CHECK(mml_estimate_device(c, cnt, cap, cap, exTlb16, P, q, prm, stats, k + 1 < n_scans ? +submit_next : nullptr,
+                                  &nx));  // synchronises `st`
     if (hf[2] || hf[8]) {
       // capacity overflow of a fused kernel: this scan goes through the general (unpipelined) path
       MML_CUDA(c, cudaStreamSynchronize(c->stream_fe));

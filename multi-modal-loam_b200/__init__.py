@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmloam_b200.so")
+LIB_PATH = os.environ.get("MMLOAM_B200_LIB") or os.path.join(_HERE, "libmmloam_b200.so")
 _lib = None
 
 MAP_CORNER_GLOBAL, MAP_SURF_GLOBAL, MAP_CORNER_LOCAL, MAP_SURF_LOCAL = 0, 1, 2, 3

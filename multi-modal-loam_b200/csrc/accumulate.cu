@@ -118,29 +118,39 @@ __device__ __forceinline__ bool load_plane(const float4* __restrict__ f, int i, 
   return true;
 }
 
+// 1/sqrt in float64: one MUFU seed + Newton steps on the device instead of a square root and a division
+__device__ __forceinline__ double rsqrt64(double x) { return rsqrt(x); }
+
+// Every thread's evaluation is one dependent float64 chain, so square roots followed by divisions are folded
+// into reciprocal square roots and products (results move by an ulp or two against a literal transcription of
+// the functors; the gate for this file is the 1e-4 m / 1e-4 rad pose tolerance, measured at ~1e-15).
+//
 // point-to-line residual + Jacobian + Huber, CF.h:412-440, accumulated into acc[28]
 __device__ __forceinline__ void eval_line(const PoseLin& L, const double* p, const double* a, const double* b, double s_info,
                                           double ha, double* acc) {
   double u[3], P[3];
   for (int r = 0; r < 3; r++) u[r] = L.Rbl[3 * r] * p[0] + L.Rbl[3 * r + 1] * p[1] + L.Rbl[3 * r + 2] * p[2] + L.Pbl[r];
   for (int r = 0; r < 3; r++) P[r] = L.R[3 * r] * u[0] + L.R[3 * r + 1] * u[1] + L.R[3 * r + 2] * u[2] + L.t[r];
-  const double l12 = sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]));
+  const double ab[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+  const double inv_l12 = rsqrt64(ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2]);
   const double c0 = (P[0] - a[0]) * (P[1] - b[1]) - (P[0] - b[0]) * (P[1] - a[1]);
   const double c1 = (P[0] - a[0]) * (P[2] - b[2]) - (P[0] - b[0]) * (P[2] - a[2]);
   const double c2 = (P[1] - a[1]) * (P[2] - b[2]) - (P[1] - b[1]) * (P[2] - a[2]);
-  const double a012 = sqrt(c0 * c0 + c1 * c1 + c2 * c2);
-  const double ld2 = a012 / l12;
+  const double cc = c0 * c0 + c1 * c1 + c2 * c2;
+  const double inv_a012 = rsqrt64(cc);
+  const double a012 = cc * inv_a012;
+  const double ld2 = a012 * inv_l12;  // distance to the line, >= 0
   const double PP = P[0] * P[0] + P[1] * P[1] + P[2] * P[2];
-  const double sq = sqrt(sqrt(PP));
-  const double w = 1.0 - 0.9 * fabs(ld2) / sq;
+  const double inv_sq = rsqrt64(sqrt(PP));  // 1 / |P|^(1/2)
+  const double inv_PP = (inv_sq * inv_sq) * (inv_sq * inv_sq);
+  const double w = 1.0 - 0.9 * ld2 * inv_sq;
   double r = s_info * w * ld2;
-  const double ch[3] = {c2 / a012, -c1 / a012, c0 / a012};
-  const double ab[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
-  const double gd[3] = {(ab[1] * ch[2] - ab[2] * ch[1]) / l12, (ab[2] * ch[0] - ab[0] * ch[2]) / l12,
-                        (ab[0] * ch[1] - ab[1] * ch[0]) / l12};
-  const double k5 = 0.5 * ld2 / (PP * sq);
+  const double ch[3] = {c2 * inv_a012, -c1 * inv_a012, c0 * inv_a012};
+  const double gd[3] = {(ab[1] * ch[2] - ab[2] * ch[1]) * inv_l12, (ab[2] * ch[0] - ab[0] * ch[2]) * inv_l12,
+                        (ab[0] * ch[1] - ab[1] * ch[0]) * inv_l12};
+  const double k5 = 0.5 * ld2 * inv_sq * inv_PP;
   double gr[3];
-  for (int k = 0; k < 3; k++) gr[k] = s_info * (w * gd[k] + ld2 * (-0.9 * (gd[k] / sq - k5 * P[k])));
+  for (int k = 0; k < 3; k++) gr[k] = s_info * (w * gd[k] + ld2 * (-0.9 * (gd[k] * inv_sq - k5 * P[k])));
   // Huber, CF.h:33-63 with rho'' <= 0
   const double s = r * r;
   double k1 = 1.0, rho = s;
@@ -162,19 +172,22 @@ __device__ __forceinline__ void eval_plane(const PoseLin& L, const double* p, co
   for (int r = 0; r < 3; r++) u[r] = L.Rbl[3 * r] * p[0] + L.Rbl[3 * r + 1] * p[1] + L.Rbl[3 * r + 2] * p[2] + L.Pbl[r];
   for (int r = 0; r < 3; r++) P[r] = L.R[3 * r] * u[0] + L.R[3 * r + 1] * u[1] + L.R[3 * r + 2] * u[2] + L.t[r];
   const double e[3] = {P[0] - pp[0], P[1] - pp[1], P[2] - pp[2]};
-  const double en = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+  const double ee = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+  const double inv_en = rsqrt64(ee);
+  const double en = ee * inv_en;
   const double PP = P[0] * P[0] + P[1] * P[1] + P[2] * P[2];
-  const double sq = sqrt(sqrt(PP));
-  const double w = 1.0 - 0.9 * en / sq;
-  const double k5 = 0.5 * en / (PP * sq);
+  const double inv_sq = rsqrt64(sqrt(PP));
+  const double inv_PP = (inv_sq * inv_sq) * (inv_sq * inv_sq);
+  const double w = 1.0 - 0.9 * en * inv_sq;
+  const double k5 = 0.5 * en * inv_sq * inv_PP;
   double gw[3];
-  for (int k = 0; k < 3; k++) gw[k] = -0.9 * ((e[k] / en) / sq - k5 * P[k]);
+  for (int k = 0; k < 3; k++) gw[k] = -0.9 * ((e[k] * inv_en) * inv_sq - k5 * P[k]);
   // residual in the canonical basis [n t1 t2]: sqrt_info^T sqrt_info = (n n^T + w_t^2 (I - n n^T)) / lidar_m^2.
   // ||r||^2 needs no basis: (s w)^2 [ (n.e)^2 + w_t^2 (|e|^2 - (n.e)^2) ]
   const double ne = n[0] * e[0] + n[1] * e[1] + n[2] * e[2];
   const double sw = s_info * w;
   double s = sw * sw * ne * ne;
-  if (w_tan != 0.0) s += sw * sw * w_tan * w_tan * fmax(en * en - ne * ne, 0.0);
+  if (w_tan != 0.0) s += sw * sw * w_tan * w_tan * fmax(ee - ne * ne, 0.0);
   double k1 = 1.0, rho = s;
   if (ha > 0 && s > ha * ha) {
     const double rr = sqrt(s);
@@ -194,8 +207,8 @@ __device__ __forceinline__ void eval_plane(const PoseLin& L, const double* p, co
     double ex[3] = {0, 0, 0};
     ex[kk] = 1.0;
     const double v[3] = {ex[1] * n[2] - ex[2] * n[1], ex[2] * n[0] - ex[0] * n[2], ex[0] * n[1] - ex[1] * n[0]};
-    const double nv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-    const double t1[3] = {v[0] / nv, v[1] / nv, v[2] / nv};
+    const double inv_nv = rsqrt64(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    const double t1[3] = {v[0] * inv_nv, v[1] * inv_nv, v[2] * inv_nv};
     const double t2[3] = {n[1] * t1[2] - n[2] * t1[1], n[2] * t1[0] - n[0] * t1[2], n[0] * t1[1] - n[1] * t1[0]};
     const double sc = k1 * s_info * w_tan;
     const double b1 = t1[0] * e[0] + t1[1] * e[1] + t1[2] * e[2];
@@ -205,6 +218,37 @@ __device__ __forceinline__ void eval_plane(const PoseLin& L, const double* p, co
     add_row(L, u, g1, sc * w * b1, acc);
     add_row(L, u, g2, sc * w * b2, acc);
   }
+}
+
+// Sum acc[0..27] over the 32 lanes of a warp: each exchange step halves the number of values a lane carries
+// (16 + 8 + 4 + 2 + 1 = 31 shuffles of a double instead of 28 x 5). On return lane c (< 28) holds the warp
+// total of component c. Deterministic order.
+__device__ __forceinline__ double warp_reduce28(const double* acc, int lane) {
+  double v16[16], v8[8], v4[4], v2[2];
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const double hi = (i + 16 < 28) ? acc[i + 16] : 0.0;
+    const double send = h16 ? acc[i] : hi, keep = h16 ? hi : acc[i];
+    v16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const double send = h8 ? v16[i] : v16[i + 8], keep = h8 ? v16[i + 8] : v16[i];
+    v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const double send = h4 ? v8[i] : v8[i + 4], keep = h4 ? v8[i + 4] : v8[i];
+    v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const double send = h2 ? v4[i] : v4[i + 2], keep = h2 ? v4[i + 2] : v4[i];
+    v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  const double send = h1 ? v2[0] : v2[1], keep = h1 ? v2[1] : v2[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
 struct AccArgs {
@@ -223,6 +267,24 @@ struct AccArgs {
 };
 
 __host__ __device__ __noinline__ void dogleg_update(EstState& S, const double* out28);
+
+// thread-block cluster primitives (PTX: barrier.cluster, mapa, ld.shared::cluster)
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_dsmem_f64(const double* local_smem_ptr, unsigned cta_rank) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(local_smem_ptr);
+  unsigned ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(cta_rank));
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
 
 #ifndef MML_ACC_MINB
 #define MML_ACC_MINB 2
@@ -327,9 +389,12 @@ __global__ void __launch_bounds__(256, MML_ACC_MINB) k_accumulate(AccArgs A) {
 // ---------------------------------------------------------------- dogleg state machine
 __host__ __device__ inline void unpack28(const double* o, double* cost, double* g, double* H) {
   *cost = o[0];
+#pragma unroll
   for (int i = 0; i < 6; i++) g[i] = o[1 + i];
   int k = 7;
+#pragma unroll
   for (int i = 0; i < 6; i++)
+#pragma unroll
     for (int j = i; j < 6; j++) {
       H[6 * i + j] = o[k];
       H[6 * j + i] = o[k];
@@ -338,21 +403,37 @@ __host__ __device__ inline void unpack28(const double* o, double* cost, double* 
 }
 
 // One DoglegStrategy::ComputeStep + model evaluation. Returns false for an invalid step.
-__host__ __device__ bool dogleg_compute_step(EstState& S) {
-  const int n = 6;
-  double Hs[36], gs[6];
+// Loops are fully unrolled (arrays in registers) and divisions by the Jacobi-scaling diagonal go through one
+// reciprocal per component: this runs on a single thread between two evaluations.
+__host__ __device__ inline bool dogleg_compute_step(EstState& S) {
+  constexpr int n = 6;
+  double Hs[36], gs[6], sc[6];
+#pragma unroll
+  for (int i = 0; i < n; i++) sc[i] = S.scale[i];
+#pragma unroll
   for (int i = 0; i < n; i++) {
-    gs[i] = S.g[i] * S.scale[i];
-    for (int j = 0; j < n; j++) Hs[i * n + j] = S.H[i * n + j] * S.scale[i] * S.scale[j];
+    gs[i] = S.g[i] * sc[i];
+#pragma unroll
+    for (int j = 0; j < n; j++) Hs[i * n + j] = S.H[i * n + j] * sc[i] * sc[j];
   }
   if (!S.reuse) {
     S.reuse = 1;
-    for (int i = 0; i < n; i++) S.diag[i] = sqrt(fmin(fmax(Hs[i * n + i], 1e-6), 1e32));
-    for (int i = 0; i < n; i++) S.grad[i] = gs[i] / S.diag[i];
+    double dg[6], idg[6], gr[6];
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+      dg[i] = sqrt(fmin(fmax(Hs[i * n + i], 1e-6), 1e32));
+      idg[i] = 1.0 / dg[i];
+      gr[i] = gs[i] * idg[i];
+      S.diag[i] = dg[i];
+      S.grad[i] = gr[i];
+    }
     double v[6], gg = 0, vHv = 0;
-    for (int i = 0; i < n; i++) { v[i] = S.grad[i] / S.diag[i]; gg += S.grad[i] * S.grad[i]; }
+#pragma unroll
+    for (int i = 0; i < n; i++) { v[i] = gr[i] * idg[i]; gg += gr[i] * gr[i]; }
+#pragma unroll
     for (int i = 0; i < n; i++) {
       double s = 0;
+#pragma unroll
       for (int j = 0; j < n; j++) s += Hs[i * n + j] * v[j];
       vHv += v[i] * s;
     }
@@ -360,50 +441,68 @@ __host__ __device__ bool dogleg_compute_step(EstState& S) {
     bool ok = false;
     while (S.mu < 1.0) {
       double Amat[36], y[6];
+#pragma unroll
       for (int i = 0; i < 36; i++) Amat[i] = Hs[i];
-      for (int i = 0; i < n; i++) Amat[i * n + i] += S.mu * S.diag[i] * S.diag[i];
+#pragma unroll
+      for (int i = 0; i < n; i++) Amat[i * n + i] += S.mu * dg[i] * dg[i];
       bool s_ok = chol_solve<6>(Amat, gs, y);
-      if (s_ok)
+      if (s_ok) {
+#pragma unroll
         for (int i = 0; i < n; i++)
           if (!isfinite(y[i])) s_ok = false;
+      }
       if (!s_ok) { S.mu *= 10.0; continue; }
-      for (int i = 0; i < n; i++) S.gn[i] = -S.diag[i] * y[i];
+#pragma unroll
+      for (int i = 0; i < n; i++) S.gn[i] = -dg[i] * y[i];
       ok = true;
       break;
     }
     if (!ok) return false;
   }
+  double grad[6], gn[6], idg[6];
+#pragma unroll
+  for (int i = 0; i < n; i++) { grad[i] = S.grad[i]; gn[i] = S.gn[i]; idg[i] = 1.0 / S.diag[i]; }
   double gnorm = 0, gnn = 0;
-  for (int i = 0; i < n; i++) { gnorm += S.grad[i] * S.grad[i]; gnn += S.gn[i] * S.gn[i]; }
+#pragma unroll
+  for (int i = 0; i < n; i++) { gnorm += grad[i] * grad[i]; gnn += gn[i] * gn[i]; }
   gnorm = sqrt(gnorm);
   gnn = sqrt(gnn);
+  const double radius = S.radius, alpha = S.alpha;
   double step[6];
-  if (gnn <= S.radius) {
-    for (int i = 0; i < n; i++) step[i] = S.gn[i];
+  if (gnn <= radius) {
+#pragma unroll
+    for (int i = 0; i < n; i++) step[i] = gn[i];
     S.dogleg_norm = gnn;
-  } else if (gnorm * S.alpha >= S.radius) {
-    for (int i = 0; i < n; i++) step[i] = -(S.radius / gnorm) * S.grad[i];
-    S.dogleg_norm = S.radius;
+  } else if (gnorm * alpha >= radius) {
+    const double f = -(radius / gnorm);
+#pragma unroll
+    for (int i = 0; i < n; i++) step[i] = f * grad[i];
+    S.dogleg_norm = radius;
   } else {
     double b_dot_a = 0;
-    for (int i = 0; i < n; i++) b_dot_a += S.grad[i] * S.gn[i];
-    b_dot_a *= -S.alpha;
-    const double a_sq = (S.alpha * gnorm) * (S.alpha * gnorm);
+#pragma unroll
+    for (int i = 0; i < n; i++) b_dot_a += grad[i] * gn[i];
+    b_dot_a *= -alpha;
+    const double a_sq = (alpha * gnorm) * (alpha * gnorm);
     const double bma = a_sq - 2 * b_dot_a + gnn * gnn;
     const double c = b_dot_a - a_sq;
-    const double d = sqrt(c * c + bma * (S.radius * S.radius - a_sq));
-    const double beta = (c <= 0) ? (d - c) / bma : (S.radius * S.radius - a_sq) / (d + c);
+    const double d = sqrt(c * c + bma * (radius * radius - a_sq));
+    const double beta = (c <= 0) ? (d - c) / bma : (radius * radius - a_sq) / (d + c);
     double sn = 0;
+#pragma unroll
     for (int i = 0; i < n; i++) {
-      step[i] = (-S.alpha * (1.0 - beta)) * S.grad[i] + beta * S.gn[i];
+      step[i] = (-alpha * (1.0 - beta)) * grad[i] + beta * gn[i];
       sn += step[i] * step[i];
     }
     S.dogleg_norm = sqrt(sn);
   }
-  for (int i = 0; i < n; i++) step[i] /= S.diag[i];
+#pragma unroll
+  for (int i = 0; i < n; i++) step[i] *= idg[i];
   double sg = 0, sHs = 0;
+#pragma unroll
   for (int i = 0; i < n; i++) {
     double t = 0;
+#pragma unroll
     for (int j = 0; j < n; j++) t += Hs[i * n + j] * step[j];
     sHs += step[i] * t;
     sg += step[i] * gs[i];
@@ -411,8 +510,9 @@ __host__ __device__ bool dogleg_compute_step(EstState& S) {
   S.model_change = -sg - 0.5 * sHs;
   if (!(S.model_change > 0.0)) return false;
   double sn = 0;
+#pragma unroll
   for (int i = 0; i < n; i++) {
-    const double dlt = step[i] * S.scale[i];
+    const double dlt = step[i] * sc[i];
     S.x_cand[i] = S.x[i] + dlt;
     sn += dlt * dlt;
   }
@@ -420,7 +520,7 @@ __host__ __device__ bool dogleg_compute_step(EstState& S) {
   return true;
 }
 
-__host__ __device__ __noinline__ void dogleg_update(EstState& S, const double* out28) {
+__host__ __device__ __forceinline__ void dogleg_update_inl(EstState& S, const double* out28) {
   double cost, g[6], H[36];
   unpack28(out28, &cost, g, H);
   auto grad_max = [&](const double* gg) {
@@ -479,6 +579,8 @@ __host__ __device__ __noinline__ void dogleg_update(EstState& S, const double* o
     S.reuse = 0;
   }
 }
+
+__host__ __device__ __noinline__ void dogleg_update(EstState& S, const double* out28) { dogleg_update_inl(S, out28); }
 
 // ---------------------------------------------------------------- outer loop bookkeeping
 // EST.cpp:1268-1270 T_wl + thres_dist schedule (EST.cpp:1207, 1377-1381): what the association needs
@@ -570,19 +672,26 @@ __global__ void k_est_end_outer(EstState* S, const double* assoc_stats) {
   est_end(S, assoc_stats);
 }
 
-// ---------------------------------------------------------------- one-CTA solve of a scan-sized frame
-// For a scan's worth of features (a few thousand) a dogleg iteration is a dependent chain of ~5 us, and a
-// kernel launch per evaluation doubles it. k_solve_frame keeps the whole trust-region loop of one outer
-// iteration in one CTA: solver state and linearisation in shared memory, features re-read through L1
-// (<= 8192 x 48 B), fixed-order reduction (warp shuffles, then warps in index order), thread 0 runs the
-// dogleg update, and the tail does the convergence test and prepares T_wl / thres_dist for the next
-// association - so an outer iteration is association || association -> this kernel.
+// ---------------------------------------------------------------- cluster solve of a scan-sized frame
+// For a scan's worth of features (a few thousand) an evaluation is a dependent chain of a few microseconds and
+// a kernel launch per evaluation doubles it. k_solve_frame keeps the whole trust-region loop of one outer
+// iteration in ONE launch of one thread-block cluster (kSolveCluster CTAs on as many SMs: the float64 pipe of a
+// single SM would bound the evaluation): every CTA evaluates its slice of the feature slots (re-read through L1),
+// reduces it to 28 doubles (warp shuffles, then warps in index order), the cluster barrier publishes the partials,
+// CTA 0 sums them over ranks in order through distributed shared memory, its thread 0 runs the dogleg update and
+// publishes the next evaluation point, and a second cluster barrier hands it to the other CTAs. The tail does
+// the convergence test and prepares T_wl / thres_dist for the next association, so an outer iteration is
+// association || association -> this kernel.
 #ifndef MML_SOLVE_THREADS
-#define MML_SOLVE_THREADS 512
+#define MML_SOLVE_THREADS 128
+#endif
+#ifndef MML_SOLVE_CLUSTER
+#define MML_SOLVE_CLUSTER 16
 #endif
 constexpr int kSolveThreads = MML_SOLVE_THREADS;
 constexpr int kSolveWarps = kSolveThreads / 32;
-constexpr int kSolveFrameMax = 6144;  // feature slots (corner + surf queries) above which k_accumulate's grid wins
+constexpr int kSolveCluster = MML_SOLVE_CLUSTER;
+constexpr int kSolveFrameMax = 12288;  // feature slots (corner + surf queries) above which k_accumulate's grid wins
 
 struct SolveArgs {
   const float4* f_line;
@@ -592,38 +701,54 @@ struct SolveArgs {
   const double* assoc_stats;
 };
 
+// R, t, J_r of the evaluation point: rotation on one thread, right Jacobian on another (different warps)
+__device__ __forceinline__ void make_pose_split(const double* x6, const double* Rbl, const double* Pbl, PoseLin& L, int tid) {
+  if (tid == 0) {
+    const Quat q = so3_exp(x6 + 3);
+    quat_to_R(q, L.R);
+    L.t[0] = x6[0]; L.t[1] = x6[1]; L.t[2] = x6[2];
+  } else if (tid == 32) {
+    right_jacobian(x6 + 3, L.Jr);
+  } else if (tid == 33) {
+    for (int i = 0; i < 9; i++) L.Rbl[i] = Rbl[i];
+    for (int i = 0; i < 3; i++) L.Pbl[i] = Pbl[i];
+  }
+}
+
 __global__ void __launch_bounds__(kSolveThreads, 1) k_solve_frame(SolveArgs A) {
-  if (A.st->done_outer) return;
-  __shared__ EstState S;
+  if (A.st->done_outer) return;  // uniform over the cluster
+  __shared__ EstState S;         // authoritative in CTA 0; the others use the parameters only
   __shared__ PoseLin L;
   __shared__ double sred[kSolveWarps][28];
+  __shared__ double part[28];    // this CTA's partial sums (read by CTA 0 through DSMEM)
   __shared__ double tot[28];
+  __shared__ double xb[8];       // CTA 0: next evaluation point (6) and the done flag
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned rank = cluster_ctarank();
   {
     const unsigned* src = reinterpret_cast<const unsigned*>(A.st);
     unsigned* dst = reinterpret_cast<unsigned*>(&S);
     for (int i = tid; i < (int)(sizeof(EstState) / 4); i += kSolveThreads) dst[i] = src[i];
   }
   __syncthreads();
-  if (tid == 0) est_begin_solve(&S);
+  if (tid == 0) est_begin_solve(&S);  // every CTA derives the same start point
   const int n_line = A.n_dev[0], n_all = n_line + A.n_dev[1];
   __syncthreads();
   const double s_info = 1.0 / S.lidar_m, w_tan = S.w_tan, ha = S.huber_a;
+  make_pose_split(S.x, S.Rbl, S.Pbl, L, tid);
+  __syncthreads();
 #ifdef MML_SOLVE_PROF
-  long long tp[5] = {0, 0, 0, 0, 0}, t0 = clock64(), t1;
+  long long tp[6] = {0, 0, 0, 0, 0, 0}, t0 = clock64(), t1;
   int n_it = 0;
 #define TICK(k) { t1 = clock64(); tp[k] += t1 - t0; t0 = t1; }
 #else
 #define TICK(k)
 #endif
   for (;;) {
-    if (tid == 0) make_pose(S.first ? S.x : S.x_cand, S.Rbl, S.Pbl, L);
-    __syncthreads();
-    TICK(0)
     double acc[28];
 #pragma unroll
     for (int k = 0; k < 28; k++) acc[k] = 0.0;
-    for (int i = tid; i < n_all; i += kSolveThreads) {
+    for (int i = rank * kSolveThreads + tid; i < n_all; i += kSolveCluster * kSolveThreads) {
       double p[3], a[3], b[3];
       if (i < n_line) {
         if (load_line(A.f_line, i, p, a, b)) eval_line(L, p, a, b, s_info, ha, acc);
@@ -631,34 +756,56 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve_frame(SolveArgs A) {
         if (load_plane(A.f_plane, i - n_line, p, a, b)) eval_plane(L, p, a, b, s_info, w_tan, ha, acc);
       }
     }
-    TICK(1)
-#pragma unroll
-    for (int k = 0; k < 28; k++) {
-      double v = acc[k];
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-      if (lane == 0) sred[warp][k] = v;
+    TICK(0)
+    {
+      const double v = warp_reduce28(acc, lane);
+      if (lane < 28) sred[warp][lane] = v;
     }
     __syncthreads();
     if (tid < 28) {
       double v = 0;
 #pragma unroll
       for (int w = 0; w < kSolveWarps; w++) v += sred[w][tid];
-      tot[tid] = v;
+      part[tid] = v;
     }
-    __syncthreads();
+    TICK(1)
+    cluster_sync_all();  // partials of every CTA are visible
     TICK(2)
-    if (tid == 0) dogleg_update(S, tot);
-    __syncthreads();
+    if (rank == 0) {
+      if (tid < 28) {
+        double v = 0;
+#pragma unroll
+        for (unsigned r = 0; r < (unsigned)kSolveCluster; r++) v += ld_dsmem_f64(&part[tid], r);
+        tot[tid] = v;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        dogleg_update_inl(S, tot);
+#pragma unroll
+        for (int i = 0; i < 6; i++) xb[i] = S.x_cand[i];
+        xb[6] = S.done_inner ? 1.0 : 0.0;
+      }
+    }
     TICK(3)
+    cluster_sync_all();  // the next evaluation point is visible
+    TICK(4)
+    if (tid < 7) tot[tid] = ld_dsmem_f64(&xb[tid], 0);
+    __syncthreads();
+    if (tot[6] != 0.0) break;
+    make_pose_split(tot, S.Rbl, S.Pbl, L, tid);
+    __syncthreads();
+    TICK(5)
 #ifdef MML_SOLVE_PROF
     n_it++;
 #endif
-    if (S.done_inner) break;
   }
 #ifdef MML_SOLVE_PROF
-  if (tid == 0) printf("solve: n=%d evals=%d pose=%lld eval=%lld reduce=%lld update=%lld cycles\n", n_all, n_it, tp[0], tp[1], tp[2], tp[3]);
+  if (tid == 0 && rank == 0)
+    printf("solve: n=%d evals=%d eval=%lld reduce=%lld sync1=%lld update=%lld sync2=%lld pose=%lld cycles\n", n_all, n_it + 1,
+           tp[0], tp[1], tp[2], tp[3], tp[4], tp[5]);
 #endif
+  cluster_sync_all();  // nobody reads CTA 0's shared memory any more
+  if (rank != 0) return;
   if (tid == 0) {
     est_end(&S, A.assoc_stats);
     if (!S.done_outer) est_begin_assoc(&S);
@@ -803,7 +950,20 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
       SA.n_dev = cnt_dev;
       SA.st = S;
       SA.assoc_stats = ctx->assoc_stats.as<double>();
-      k_solve_frame<<<1, kSolveThreads, 0, st>>>(SA);
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(kSolveCluster);
+      cfg.blockDim = dim3(kSolveThreads);
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = kSolveCluster;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      if (kSolveCluster > 8) cudaFuncSetAttribute(k_solve_frame, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (cudaLaunchKernelEx(&cfg, k_solve_frame, SA) != cudaSuccess) rc = MML_ERR_CUDA;
       MML_LAUNCHED(ctx);
     } else {
       for (int k = 0; k <= prm->max_inner && rc == MML_OK; k++)

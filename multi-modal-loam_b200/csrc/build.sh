@@ -4,20 +4,21 @@
 # baseline x86-64 build (no FMA contraction) for bit-exact feature labels and k-NN sets.
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
-OUT="$HERE/../libmmloam_b200.so"
+OUT="${MML_OUT:-$HERE/../libmmloam_b200.so}"   # MML_OUT / MML_OBJ: variant builds for A/B runs (scratch/)
+OBJ="${MML_OBJ:-$HERE/_obj}"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -Xcompiler -O3 ${MML_EXTRA_NVCC_FLAGS}"
-mkdir -p "$HERE/_obj"
+mkdir -p "$OBJ"
 pids=()
 for f in extract geometry splitvoxel framesort associate accumulate odometry capi; do
-  if [ ! -f "$HERE/_obj/$f.o" ] || [ -n "$(find "$HERE" -maxdepth 1 \( -name '*.cu' -o -name '*.cuh' \) -newer "$HERE/_obj/$f.o" 2>/dev/null)" ] || [ "$HERE/../../include/mmloam_b200.h" -nt "$HERE/_obj/$f.o" ]; then
+  if [ ! -f "$OBJ/$f.o" ] || [ -n "$(find "$HERE" -maxdepth 1 \( -name '*.cu' -o -name '*.cuh' \) -newer "$OBJ/$f.o" 2>/dev/null)" ] || [ "$HERE/../../include/mmloam_b200.h" -nt "$OBJ/$f.o" ]; then
     # accumulate.cu is pure float64 normal-equation arithmetic checked to 1e-9 relative (no bit-exact float32
     # thresholds inside): it may contract multiply-adds into DFMA
     if [ "$f" = "accumulate" ]; then FF="${FLAGS/-fmad=false/-fmad=true}"; else FF="$FLAGS"; fi
-    $NVCC $FF -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" &
+    $NVCC $FF -c "$HERE/$f.cu" -o "$OBJ/$f.o" &
     pids+=($!)
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$HERE"/_obj/{extract,geometry,splitvoxel,framesort,associate,accumulate,odometry,capi}.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$OBJ"/{extract,geometry,splitvoxel,framesort,associate,accumulate,odometry,capi}.o -lcudart
 echo "built $OUT"

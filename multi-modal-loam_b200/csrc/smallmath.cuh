@@ -212,31 +212,46 @@ __host__ __device__ inline Quat quat_from_R9(const double* m) {
   return q;
 }
 
-// SPD solve A x = b, n <= 6. false if a pivot is not positive.
+// SPD solve A x = b, n <= 6, by L D L^T (the pivots d_j are the squares of Cholesky's diagonal, so the
+// positive-definiteness test is the same). One reciprocal per column and no square roots: the dependent chain
+// is what a single solver thread waits on. false if a pivot is not positive.
 template <int N>
 __host__ __device__ inline bool chol_solve(const double* A, const double* b, double* x) {
-  double L[N * N];
-  for (int i = 0; i < N; i++)
-    for (int j = 0; j <= i; j++) {
-      double s = A[i * N + j];
-      for (int k = 0; k < j; k++) s -= L[i * N + k] * L[j * N + k];
-      if (i == j) {
-        if (!(s > 0)) return false;
-        L[i * N + i] = sqrt(s);
-      } else {
-        L[i * N + j] = s / L[j * N + j];
-      }
+  double L[N * N], inv[N], piv[N];
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    double w[N];  // w_k = L_jk d_k
+    double d = A[j * N + j];
+#pragma unroll
+    for (int k = 0; k < j; k++) {
+      w[k] = L[j * N + k] * piv[k];
+      d -= L[j * N + k] * w[k];
     }
-  double y[N];
+    if (!(d > 0)) return false;
+    piv[j] = d;
+    inv[j] = 1.0 / d;
+#pragma unroll
+    for (int i = j + 1; i < N; i++) {
+      double s = A[i * N + j];
+#pragma unroll
+      for (int k = 0; k < j; k++) s -= L[i * N + k] * w[k];
+      L[i * N + j] = s * inv[j];
+    }
+  }
+  double z[N];
+#pragma unroll
   for (int i = 0; i < N; i++) {
     double s = b[i];
-    for (int k = 0; k < i; k++) s -= L[i * N + k] * y[k];
-    y[i] = s / L[i * N + i];
+#pragma unroll
+    for (int k = 0; k < i; k++) s -= L[i * N + k] * z[k];
+    z[i] = s;
   }
+#pragma unroll
   for (int i = N - 1; i >= 0; i--) {
-    double s = y[i];
+    double s = z[i] * inv[i];
+#pragma unroll
     for (int k = i + 1; k < N; k++) s -= L[k * N + i] * x[k];
-    x[i] = s / L[i * N + i];
+    x[i] = s;
   }
   return true;
 }

@@ -17,31 +17,12 @@
 // graph: no host round trip until the final pose is read back.
 #include "common.cuh"
 #include "smallmath.cuh"
+#include "eststate.cuh"
 #include <float.h>
 #include <math.h>
 
 namespace mml {
 
-struct EstState {
-  // pose of the body frame (EST.h:33-56) and extrinsics
-  double P[3], Q[4];
-  double Rbl[9], Pbl[3];
-  double T_wl[16];
-  float thres;
-  int n_line, n_plane;
-  // control
-  int done_outer, done_inner, outer_it, inner_it, first, total_inner, is_degenerate, outer_next;
-  int max_outer, max_inner;
-  double lidar_m, w_tan, huber_a, thres_sched[3];
-  // trust-region state (Ceres 2.1 TrustRegionMinimizer + DoglegStrategy)
-  double x[6], x_cand[6], x_best[6];
-  double cost, min_cost, H[36], g[6], scale[6];
-  double radius, mu, alpha, dogleg_norm, model_change, step_norm, x_norm;
-  double diag[6], grad[6], gn[6];
-  int reuse, num_invalid;
-  double q_before[4], t_before[3];
-  double min_sv, final_cost;
-};
 
 struct PoseLin {
   double R[9], t[3], Jr[9], Rbl[9], Pbl[3];
@@ -583,33 +564,6 @@ __host__ __device__ __forceinline__ void dogleg_update_inl(EstState& S, const do
 __host__ __device__ __noinline__ void dogleg_update(EstState& S, const double* out28) { dogleg_update_inl(S, out28); }
 
 // ---------------------------------------------------------------- outer loop bookkeeping
-// EST.cpp:1268-1270 T_wl + thres_dist schedule (EST.cpp:1207, 1377-1381): what the association needs
-__device__ inline void est_begin_assoc(EstState* S) {
-  const int it = S->outer_next;
-  S->outer_it = it;
-  const Quat Q = {S->Q[0], S->Q[1], S->Q[2], S->Q[3]};
-  double Rq[9];
-  quat_to_R(Q, Rq);
-  // exRbl = Rbl, exPbl = Pbl
-  for (int r = 0; r < 3; r++) {
-    for (int c = 0; c < 3; c++)
-      S->T_wl[4 * r + c] = Rq[3 * r] * S->Rbl[c] + Rq[3 * r + 1] * S->Rbl[3 + c] + Rq[3 * r + 2] * S->Rbl[6 + c];
-    S->T_wl[4 * r + 3] = Rq[3 * r] * S->Pbl[0] + Rq[3 * r + 1] * S->Pbl[1] + Rq[3 * r + 2] * S->Pbl[2] + S->P[r];
-  }
-  S->T_wl[12] = 0; S->T_wl[13] = 0; S->T_wl[14] = 0; S->T_wl[15] = 1;
-  S->thres = (float)S->thres_sched[it < 2 ? it : 2];
-}
-// EST.cpp:1212 vector2double: what the solve needs (idempotent)
-__device__ inline void est_begin_solve(EstState* S) {
-  const Quat Q = {S->Q[0], S->Q[1], S->Q[2], S->Q[3]};
-  S->x[0] = S->P[0]; S->x[1] = S->P[1]; S->x[2] = S->P[2];
-  so3_log(Q, S->x + 3);
-  for (int i = 0; i < 4; i++) S->q_before[i] = S->Q[i];
-  for (int i = 0; i < 3; i++) S->t_before[i] = S->P[i];
-  S->first = 1;
-  S->done_inner = 0;
-}
-
 // EST.cpp:771-775 localizability, EST.cpp:1439-1450 convergence test
 __device__ inline void est_end(EstState* S, const double* assoc_stats) {
   const int* ints = reinterpret_cast<const int*>(assoc_stats + 16);
@@ -641,11 +595,6 @@ __device__ inline void est_end(EstState* S, const double* assoc_stats) {
 
 // Start of a solve: the state upload, the zeroing of the association statistics and the first
 // begin-of-outer-iteration in one launch (parameters travel as kernel arguments).
-struct EstInit {
-  double P[3], Q[4], Rbl[9], Pbl[3];
-  double lidar_m, w_tan, huber_a, thres_sched[3];
-  int max_outer, max_inner;
-};
 __global__ void __launch_bounds__(128) k_est_init(EstState* S, EstInit I, unsigned* assoc_stats_words, unsigned* acc_out_words) {
   unsigned* w = reinterpret_cast<unsigned*>(S);
   for (int i = threadIdx.x; i < (int)(sizeof(EstState) / 4); i += 128) w[i] = 0u;
@@ -653,13 +602,7 @@ __global__ void __launch_bounds__(128) k_est_init(EstState* S, EstInit I, unsign
   if (threadIdx.x < 64) acc_out_words[threadIdx.x] = 0u;  // 32 doubles
   __syncthreads();
   if (threadIdx.x != 0) return;
-  for (int i = 0; i < 3; i++) { S->P[i] = I.P[i]; S->Pbl[i] = I.Pbl[i]; S->thres_sched[i] = I.thres_sched[i]; }
-  for (int i = 0; i < 4; i++) S->Q[i] = I.Q[i];
-  for (int i = 0; i < 9; i++) S->Rbl[i] = I.Rbl[i];
-  S->max_outer = I.max_outer; S->max_inner = I.max_inner;
-  S->lidar_m = I.lidar_m; S->w_tan = I.w_tan; S->huber_a = I.huber_a;
-  est_begin_assoc(S);
-  est_begin_solve(S);
+  est_fill(S, I, I.P, I.Q);
 }
 
 __global__ void k_est_begin_outer(EstState* S) {
@@ -699,7 +642,31 @@ struct SolveArgs {
   const int* n_dev;  // [n_corner, n_surf]
   EstState* st;
   const double* assoc_stats;
+  // chained odometry loop (odometry.cu): when od is set, the kernel that finishes a scan's solve publishes the
+  // pose on the device (outputs + the two poses the next prediction is made from) and drives the WHILE node of
+  // the per-scan graph: one more outer iteration, or on to the next scan
+  OdomDev* od;
+  ChainOut out;
+  cudaGraphConditionalHandle cond;
 };
+
+// end of a scan in the chained loop: T_wb from (P, Q) like the host loop, shift the pose history
+__device__ inline void chain_publish(const SolveArgs& A, const EstState& S) {
+  OdomDev* od = A.od;
+  const int k = od->scan;
+  double R[9];
+  quat_to_R(Quat{S.Q[0], S.Q[1], S.Q[2], S.Q[3]}, R);
+  const double Tn[16] = {R[0], R[1], R[2], S.P[0], R[3], R[4], R[5], S.P[1], R[6], R[7], R[8], S.P[2], 0, 0, 0, 1};
+  for (int i = 0; i < 16; i++) {
+    od->T_before[i] = od->T_last[i];
+    od->T_last[i] = Tn[i];
+    A.out.poses[16 * (size_t)k + i] = Tn[i];
+  }
+  double* st = A.out.stats + 8 * (size_t)k;
+  st[0] = S.outer_it + 1; st[1] = S.total_inner; st[2] = S.n_line; st[3] = S.n_plane;
+  st[4] = S.final_cost; st[5] = S.min_sv; st[6] = S.is_degenerate; st[7] = 0;
+  od->scan = k + 1;
+}
 
 // R, t, J_r of the evaluation point: rotation on one thread, right Jacobian on another (different warps)
 __device__ __forceinline__ void make_pose_split(const double* x6, const double* Rbl, const double* Pbl, PoseLin& L, int tid) {
@@ -809,6 +776,10 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve_frame(SolveArgs A) {
   if (tid == 0) {
     est_end(&S, A.assoc_stats);
     if (!S.done_outer) est_begin_assoc(&S);
+    if (A.od) {
+      if (S.done_outer) chain_publish(A, S);
+      cudaGraphSetConditional(A.cond, S.done_outer ? 0u : 1u);
+    }
   }
   __syncthreads();
   {
@@ -867,6 +838,87 @@ int mml_accumulate_launch(mml_ctx* ctx, const double* x6, const double* T_bl16, 
   return MML_OK;
 }
 
+// graph key: every pointer / capacity baked into the captured launches
+static long long est_graph_key(mml_ctx* ctx, EstState* S, const int* cnt_dev, int cap_corner, int cap_surf, int max_outer,
+                               int max_inner) {
+  long long key = 1469598103934665603ll;
+  auto mix = [&](long long v) { key = (key ^ v) * 1099511628211ll; };
+  mix((long long)(size_t)S); mix((long long)(size_t)ctx->f_line.p); mix((long long)(size_t)ctx->f_plane.p);
+  mix((long long)(size_t)ctx->q_corner.p); mix((long long)(size_t)ctx->q_surf.p); mix((long long)(size_t)cnt_dev);
+  mix((long long)(size_t)ctx->acc_partials.p); mix((long long)(size_t)ctx->acc_out.p); mix((long long)(size_t)ctx->tmp_c.p);
+  mix((long long)(size_t)ctx->assoc_stats.p); mix((long long)(size_t)ctx->assoc_part[0].p); mix((long long)(size_t)ctx->assoc_part[1].p); mix(cap_corner); mix(cap_surf); mix(max_outer); mix(max_inner);
+  for (int k = 0; k < 4; k++) {
+    const GridMap& M = ctx->maps[k];
+    mix(M.valid); mix(M.coarse); mix((long long)(size_t)M.pts2.p); mix((long long)(size_t)M.cell_start2.p); mix((long long)(size_t)M.pts.p); mix((long long)(size_t)M.cell_start.p); mix(M.m); mix(M.ncell);
+    mix(M.dim[0]); mix(M.dim[1]); mix(M.dim[2]); mix((long long)(M.cell * 1e6f)); mix(M.cube_lo[0]); mix(M.cube_lo[1]); mix(M.cube_lo[2]);
+    mix((long long)(M.org_d[0] * 1e6)); mix((long long)(M.org_d[1] * 1e6)); mix((long long)(M.org_d[2] * 1e6));
+    mix(M.cen[0]); mix(M.cen[1]); mix(M.cen[2]);
+  }
+  return key;
+}
+
+// line || plane association of the frame slot on two captured streams (fork / join around ctx->stream)
+static int capture_assoc_pair(mml_ctx* ctx, EstState* S, const int* cnt_dev, int cap_corner, int cap_surf) {
+  cudaStream_t st = ctx->stream, st2 = ctx->stream2;
+  cudaEventRecord(ctx->ev_fork, st);
+  cudaStreamWaitEvent(st2, ctx->ev_fork, 0);
+  ctx->stream = st2;
+  int rc = mml_associate_launch(ctx, 1, nullptr, 0.f, S->T_wl, &S->thres, &S->done_outer, cnt_dev + 1, cap_surf);
+  ctx->stream = st;
+  if (rc == MML_OK) rc = mml_associate_launch(ctx, 0, nullptr, 0.f, S->T_wl, &S->thres, &S->done_outer, cnt_dev, cap_corner);
+  cudaEventRecord(ctx->ev_join, st2);
+  cudaStreamWaitEvent(st, ctx->ev_join, 0);
+  return rc;
+}
+
+static int launch_solve_frame(mml_ctx* ctx, EstState* S, const int* cnt_dev, OdomDev* od, ChainOut out,
+                              cudaGraphConditionalHandle cond) {
+  SolveArgs SA;
+  memset(&SA, 0, sizeof(SA));
+  SA.f_line = ctx->f_line.as<float4>();
+  SA.f_plane = ctx->f_plane.as<float4>();
+  SA.n_dev = cnt_dev;
+  SA.st = S;
+  SA.assoc_stats = ctx->assoc_stats.as<double>();
+  SA.od = od;
+  SA.out = out;
+  SA.cond = cond;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(kSolveCluster);
+  cfg.blockDim = dim3(kSolveThreads);
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kSolveCluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (kSolveCluster > 8) cudaFuncSetAttribute(k_solve_frame, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  const bool ok = cudaLaunchKernelEx(&cfg, k_solve_frame, SA) == cudaSuccess;
+  MML_LAUNCHED(ctx);
+  return ok ? MML_OK : MML_ERR_CUDA;
+}
+
+// solve parameters from the extrinsics and the caller's options (pose fields left to the caller)
+static EstInit make_est_init(const double* exTlb16, const mml_est_params* prm) {
+  EstInit I;
+  memset(&I, 0, sizeof(I));
+  // exRbl = R^T, exPbl = -R^T t (EST.cpp:1155-1156); CF.h:405-408 re-normalises R_bl via a quaternion
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) I.Rbl[3 * r + c] = exTlb16[4 * c + r];
+  for (int r = 0; r < 3; r++)
+    I.Pbl[r] = -1.0 * (I.Rbl[3 * r] * exTlb16[3] + I.Rbl[3 * r + 1] * exTlb16[7] + I.Rbl[3 * r + 2] * exTlb16[11]);
+  I.max_outer = prm->max_outer;
+  I.max_inner = prm->max_inner;
+  I.lidar_m = prm->lidar_m;
+  I.w_tan = prm->plan_weight_tan;
+  I.huber_a = prm->use_huber ? 0.1 / prm->lidar_m : 0.0;
+  I.thres_sched[0] = prm->thres0; I.thres_sched[1] = prm->thres1; I.thres_sched[2] = prm->thres2;
+  return I;
+}
+
 // Full Estimate loop for one frame on the device (window size 1). Queries must be in the
 // frame slot (q_corner / q_surf with device counts in `cnt_dev`, capacities cap_*).
 int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int cap_surf, const double* exTlb16,
@@ -886,37 +938,14 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
   // initial state: one launch (k_est_init), parameters as kernel arguments
   MML_CUDA(ctx, ctx->pin_out.reserve(sizeof(EstState) + 64));
   EstState* h = ctx->pin_out.as<EstState>();
-  EstInit I;
+  EstInit I = make_est_init(exTlb16, prm);
   for (int i = 0; i < 3; i++) I.P[i] = P3[i];
   for (int i = 0; i < 4; i++) I.Q[i] = q4[i];
-  // exRbl = R^T, exPbl = -R^T t (EST.cpp:1155-1156); CF.h:405-408 re-normalises R_bl via a quaternion
-  for (int r = 0; r < 3; r++)
-    for (int c = 0; c < 3; c++) I.Rbl[3 * r + c] = exTlb16[4 * c + r];
-  for (int r = 0; r < 3; r++)
-    I.Pbl[r] = -1.0 * (I.Rbl[3 * r] * exTlb16[3] + I.Rbl[3 * r + 1] * exTlb16[7] + I.Rbl[3 * r + 2] * exTlb16[11]);
-  I.max_outer = prm->max_outer;
-  I.max_inner = prm->max_inner;
-  I.lidar_m = prm->lidar_m;
-  I.w_tan = prm->plan_weight_tan;
-  I.huber_a = prm->use_huber ? 0.1 / prm->lidar_m : 0.0;
-  I.thres_sched[0] = prm->thres0; I.thres_sched[1] = prm->thres1; I.thres_sched[2] = prm->thres2;
   k_est_init<<<1, 128, 0, st>>>(S, I, ctx->assoc_stats.as<unsigned>(), ctx->acc_out.as<unsigned>());
   MML_LAUNCHED(ctx);
 
-  // graph key: every pointer / capacity baked into the captured launches
-  long long key = 1469598103934665603ll;
+  long long key = est_graph_key(ctx, S, cnt_dev, cap_corner, cap_surf, prm->max_outer, prm->max_inner);
   auto mix = [&](long long v) { key = (key ^ v) * 1099511628211ll; };
-  mix((long long)(size_t)S); mix((long long)(size_t)ctx->f_line.p); mix((long long)(size_t)ctx->f_plane.p);
-  mix((long long)(size_t)ctx->q_corner.p); mix((long long)(size_t)ctx->q_surf.p); mix((long long)(size_t)cnt_dev);
-  mix((long long)(size_t)ctx->acc_partials.p); mix((long long)(size_t)ctx->acc_out.p); mix((long long)(size_t)ctx->tmp_c.p);
-  mix((long long)(size_t)ctx->assoc_stats.p); mix((long long)(size_t)ctx->assoc_part[0].p); mix((long long)(size_t)ctx->assoc_part[1].p); mix(cap_corner); mix(cap_surf); mix(prm->max_outer); mix(prm->max_inner);
-  for (int k = 0; k < 4; k++) {
-    const GridMap& M = ctx->maps[k];
-    mix(M.valid); mix(M.coarse); mix((long long)(size_t)M.pts2.p); mix((long long)(size_t)M.cell_start2.p); mix((long long)(size_t)M.pts.p); mix((long long)(size_t)M.cell_start.p); mix(M.m); mix(M.ncell);
-    mix(M.dim[0]); mix(M.dim[1]); mix(M.dim[2]); mix((long long)(M.cell * 1e6f)); mix(M.cube_lo[0]); mix(M.cube_lo[1]); mix(M.cube_lo[2]);
-    mix((long long)(M.org_d[0] * 1e6)); mix((long long)(M.org_d[1] * 1e6)); mix((long long)(M.org_d[2] * 1e6));
-    mix(M.cen[0]); mix(M.cen[1]); mix(M.cen[2]);
-  }
   // One outer iteration = one graph: begin | line association || plane association (two captured streams) |
   // 1 + max_inner evaluations, each fused with its dogleg update | end. The host replays it until the device
   // reports convergence (EST.cpp:1448): a well-predicted scan costs one graph and one short synchronisation
@@ -928,43 +957,15 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
     if (ctx->est_graph) { cudaGraphExecDestroy(ctx->est_graph); ctx->est_graph = nullptr; }
     cudaGraph_t graph = nullptr;
     const long long launches_before = ctx->launches;
-    cudaStream_t st2 = ctx->stream2;
     MML_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     int rc = MML_OK;
     if (!small) {
       k_est_begin_outer<<<1, 32, 0, st>>>(S);
       MML_LAUNCHED(ctx);
     }
-    cudaEventRecord(ctx->ev_fork, st);
-    cudaStreamWaitEvent(st2, ctx->ev_fork, 0);
-    ctx->stream = st2;
-    rc = mml_associate_launch(ctx, 1, nullptr, 0.f, S->T_wl, &S->thres, &S->done_outer, cnt_dev + 1, cap_surf);
-    ctx->stream = st;
-    if (rc == MML_OK) rc = mml_associate_launch(ctx, 0, nullptr, 0.f, S->T_wl, &S->thres, &S->done_outer, cnt_dev, cap_corner);
-    cudaEventRecord(ctx->ev_join, st2);
-    cudaStreamWaitEvent(st, ctx->ev_join, 0);
+    rc = capture_assoc_pair(ctx, S, cnt_dev, cap_corner, cap_surf);
     if (small) {
-      SolveArgs SA;
-      SA.f_line = ctx->f_line.as<float4>();
-      SA.f_plane = ctx->f_plane.as<float4>();
-      SA.n_dev = cnt_dev;
-      SA.st = S;
-      SA.assoc_stats = ctx->assoc_stats.as<double>();
-      cudaLaunchConfig_t cfg;
-      memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = dim3(kSolveCluster);
-      cfg.blockDim = dim3(kSolveThreads);
-      cfg.stream = st;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = kSolveCluster;
-      at[0].val.clusterDim.y = 1;
-      at[0].val.clusterDim.z = 1;
-      cfg.attrs = at;
-      cfg.numAttrs = 1;
-      if (kSolveCluster > 8) cudaFuncSetAttribute(k_solve_frame, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-      if (cudaLaunchKernelEx(&cfg, k_solve_frame, SA) != cudaSuccess) rc = MML_ERR_CUDA;
-      MML_LAUNCHED(ctx);
+      if (rc == MML_OK) rc = launch_solve_frame(ctx, S, cnt_dev, nullptr, ChainOut{nullptr, nullptr, nullptr}, 0);
     } else {
       for (int k = 0; k <= prm->max_inner && rc == MML_OK; k++)
         rc = mml_accumulate_launch(ctx, nullptr, nullptr, 0, 0, 0, S, cnt_dev, cap_corner, cap_surf, nullptr, nullptr);
@@ -1009,6 +1010,61 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
     stats[0] = h->outer_it + 1; stats[1] = h->total_inner; stats[2] = h->n_line; stats[3] = h->n_plane;
     stats[4] = h->final_cost; stats[5] = h->min_sv; stats[6] = h->is_degenerate;
   }
+  return MML_OK;
+}
+
+// ---------------------------------------------------------------- chained odometry loop
+// The solve of one scan as ONE graph launch: WHILE (not converged) { line || plane association -> k_solve_frame }.
+// The WHILE condition is set on the device by k_solve_frame (EST.cpp:1448), which also publishes the pose and
+// shifts the pose history when the scan is done, so the host never waits on a scan (odometry.cu).
+int mml_chain_prepare(mml_ctx* ctx, int cap, mml::EstState** S_out) {
+  MML_CUDA(ctx, ctx->est_state.reserve(sizeof(EstState) + 64));
+  MML_CUDA(ctx, ctx->acc_partials.reserve(sizeof(double) * 28 * (size_t)(4 * kNumSMs) + 64));
+  MML_CUDA(ctx, ctx->acc_out.reserve(sizeof(double) * 32 + 64));
+  MML_CUDA(ctx, ctx->assoc_stats.reserve(512));
+  MML_CUDA(ctx, ctx->f_line.reserve(sizeof(float4) * 3 * (size_t)cap));
+  MML_CUDA(ctx, ctx->f_plane.reserve(sizeof(float4) * 3 * (size_t)cap));
+  MML_CUDA(ctx, ctx->assoc_part[0].reserve(sizeof(double) * 8 * (size_t)(div_up(cap + 1, 4) + 1) + 64));
+  MML_CUDA(ctx, ctx->assoc_part[1].reserve(sizeof(double) * 8 * (size_t)(div_up(cap + 1, 4) + 1) + 64));
+  *S_out = ctx->est_state.as<EstState>();
+  return MML_OK;
+}
+
+mml::EstInit mml_make_est_init(const double* exTlb16, const mml_est_params* prm) { return make_est_init(exTlb16, prm); }
+
+int mml_chain_solve_launch(mml_ctx* ctx, const int* cnt_dev, int cap, mml::OdomDev* od, mml::ChainOut out) {
+  cudaStream_t st = ctx->stream;
+  EstState* S = ctx->est_state.as<EstState>();
+  long long key = est_graph_key(ctx, S, cnt_dev, cap, cap, 0, 0);
+  auto mix = [&](long long v) { key = (key ^ v) * 1099511628211ll; };
+  mix((long long)(size_t)od); mix((long long)(size_t)out.poses); mix((long long)(size_t)out.stats); mix((long long)(size_t)out.counts);
+  if (!ctx->chain_graph || ctx->chain_graph_key != key) {
+    if (ctx->chain_graph) { cudaGraphExecDestroy(ctx->chain_graph); ctx->chain_graph = nullptr; }
+    const long long launches_before = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    MML_CUDA(ctx, cudaGraphCreate(&graph, 0));
+    cudaGraphConditionalHandle cond;
+    MML_CUDA(ctx, cudaGraphConditionalHandleCreate(&cond, graph, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+    np.conditional.handle = cond;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t node;
+    MML_CUDA(ctx, cudaGraphAddNode(&node, graph, nullptr, 0, &np));
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    MML_CUDA(ctx, cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    int rc = capture_assoc_pair(ctx, S, cnt_dev, cap, cap);
+    if (rc == MML_OK) rc = launch_solve_frame(ctx, S, cnt_dev, od, out, cond);
+    cudaError_t ce = cudaStreamEndCapture(st, nullptr);
+    ctx->chain_launches_per_iter = ctx->launches - launches_before;
+    ctx->launches = launches_before;
+    if (rc != MML_OK) { cudaGraphDestroy(graph); return rc; }
+    MML_CUDA(ctx, ce);
+    MML_CUDA(ctx, cudaGraphInstantiate(&ctx->chain_graph, graph, 0));
+    cudaGraphDestroy(graph);
+    ctx->chain_graph_key = key;
+  }
+  MML_CUDA(ctx, cudaGraphLaunch(ctx->chain_graph, st));
   return MML_OK;
 }
 

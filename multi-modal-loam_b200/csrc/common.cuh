@@ -127,6 +127,9 @@ struct mml_ctx {
   long long est_graph_key = 0;
   int solve_small = 1;                                   // sticky: scan-sized frames use the one-CTA solve (accumulate.cu)
   long long est_launches_per_graph = 0;
+  cudaGraphExec_t chain_graph = nullptr;   // chained odometry loop: WHILE graph of one scan's solve (accumulate.cu)
+  long long chain_graph_key = 0;
+  long long chain_launches_per_iter = 0;
   std::vector<int> last_scan_off;  // scan offsets the resident chunk table was built for
   void* odom = nullptr;            // pipelined odometry runner state (odometry.cu)
   cudaStream_t stream_fe = nullptr;  // feature-extraction stream of the pipelined runner

@@ -4,53 +4,60 @@
 // so scan k+1 is labelled on its own stream while scan k is being matched.
 //
 //   stream_fe : [H2D scan k+1] -> extraction k+1 (labels + counters into slot (k+1)%2)
-//   stream    : wait(slot k) -> fused split + undistort + voxel -> Estimate graphs -> pose k
+//   stream    : wait(slot k) -> fused split + undistort + voxel -> Estimate -> pose k
 //
 // Pose prediction is the constant-velocity model the reference uses before IMU initialisation
 // (delta of the last two poses, PE.cpp:847-852, 882-890); the same delta drives undistortion.
+//
+// Two drivers share the kernels:
+//   chained (default): the last two poses live on the device (OdomDev); the split/voxel launch derives the
+//     prediction from them and starts the solve, and the solve is one graph whose WHILE node repeats the outer
+//     iteration until the device-side convergence test passes. The host only enqueues - it never waits on a
+//     scan - and reads all poses back once at the end.
+//   classic (MML_ODOM_CLASSIC=1, and for scans whose fused kernels overflow): host-driven, one short
+//     synchronisation per outer iteration.
 #include "common.cuh"
 #include "smallmath.cuh"
+#include "eststate.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_d, const int* scan_off, int n_scans,
                        int n_lines, uint8_t* label_d, bool force_sequential);
 int mml_split_voxel_capacity();
 int mml_split_voxel_device(mml_ctx* ctx, const float4* pts_d, const float* s_d, const uint8_t* label_d, int n,
                            const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, float4* corner_out,
-                           float4* surf_out, int* counts_d);
+                           float4* surf_out, int* counts_d, const mml::SvChain* chain = nullptr);
+int mml_chain_prepare(mml_ctx* ctx, int cap, mml::EstState** S_out);
+mml::EstInit mml_make_est_init(const double* exTlb16, const mml_est_params* prm);
+int mml_chain_solve_launch(mml_ctx* ctx, const int* cnt_dev, int cap, mml::OdomDev* od, mml::ChainOut out);
 
 namespace {
 
+using mml::mat4_mul;
+using mml::rigid_inv;
+
 struct Slot {
   mml::DevBuf label, counters, in_xyzi, in_line, in_s;
-  cudaEvent_t done = nullptr;
+  cudaEvent_t done = nullptr;      // extraction of the scan in this slot has finished (FE stream)
+  cudaEvent_t consumed = nullptr;  // the matcher has read the slot (main stream): the next scan may overwrite it
+  bool used = false;
 };
 
 struct Odom {
   Slot slot[2];
+  mml::DevBuf state;  // OdomDev
+  mml::DevBuf out;    // ChainOut arrays
+  mml::PinBuf host;   // staging: OdomDev upload + ChainOut read-back
 };
-
-void mat4_mul(const double* A, const double* B, double* C) {
-  for (int r = 0; r < 4; r++)
-    for (int c = 0; c < 4; c++) {
-      double s = 0;
-      for (int k = 0; k < 4; k++) s += A[4 * r + k] * B[4 * k + c];
-      C[4 * r + c] = s;
-    }
-}
-void rigid_inv(const double* T, double* Ti) {
-  for (int r = 0; r < 3; r++) {
-    for (int c = 0; c < 3; c++) Ti[4 * r + c] = T[4 * c + r];
-    Ti[4 * r + 3] = -(T[0 * 4 + r] * T[3] + T[1 * 4 + r] * T[7] + T[2 * 4 + r] * T[11]);
-  }
-  Ti[12] = Ti[13] = Ti[14] = 0;
-  Ti[15] = 1;
-}
 
 Odom* get_odom(mml_ctx* c) {
   if (!c->odom) {
     Odom* o = new Odom();
-    for (int k = 0; k < 2; k++) cudaEventCreateWithFlags(&o->slot[k].done, cudaEventDisableTiming);
+    for (int k = 0; k < 2; k++) {
+      cudaEventCreateWithFlags(&o->slot[k].done, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&o->slot[k].consumed, cudaEventDisableTiming);
+    }
     cudaStreamCreateWithFlags(&c->stream_fe, cudaStreamNonBlocking);
     c->odom = o;
   }
@@ -63,6 +70,7 @@ int submit(mml_ctx* c, Odom* o, int k, const void* xyzi, const void* line, const
   Slot& S = o->slot[k & 1];
   MML_CUDA(c, S.label.reserve((size_t)n + 16));
   MML_CUDA(c, S.counters.reserve(64));
+  if (S.used) MML_CUDA(c, cudaStreamWaitEvent(c->stream_fe, S.consumed, 0));
   const void* xd = xyzi;
   const void* ld = line;
   const void* sd = s;
@@ -88,19 +96,171 @@ int submit(mml_ctx* c, Odom* o, int k, const void* xyzi, const void* line, const
   c->stream = main_stream;
   MML_CHECK(rc);
   MML_CUDA(c, cudaEventRecord(S.done, c->stream_fe));
+  S.used = true;
   return MML_OK;
 }
+
+struct RunArgs {
+  const void* const* xyzi; const void* const* line; const void* const* s; const int* n_pts;
+  int n_scans, n_lines, host_buffers;
+  const double* exTlb16; float leaf_corner, leaf_surf; const mml_est_params* prm;
+  double* poses_out; int* counts_out;
+};
 
 }  // namespace
 
 extern "C" {
-
 int mml_scan_to_pose_dev(mml_ctx* c, const void* xyzi_dev, const void* line_id_dev, const void* s_dev, int n, int n_lines,
                          const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, const double* exTlb16,
                          double* P3, double* q_wxyz4, const mml_est_params* prm, double* stats, int* out_counts);
 int mml_scan_to_pose(mml_ctx* c, const float* xyzi, const uint16_t* line_id, const float* s, int n, int n_lines,
                      const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, const double* exTlb16,
                      double* P3, double* q_wxyz4, const mml_est_params* prm, double* stats, int* out_counts);
+}
+
+// ---------------------------------------------------------------- classic driver: scans [first, n_scans)
+static int run_classic(mml_ctx* c, Odom* o, const RunArgs& R, int first, const double* T_init16, const double* T_prev16) {
+  cudaStream_t st = c->stream;
+  const int cap = mml_split_voxel_capacity();
+  const int n_scans = R.n_scans, n_lines = R.n_lines;
+  const bool host = R.host_buffers != 0;
+  double T_last[16], T_before[16];
+  memcpy(T_last, T_init16, sizeof(T_last));
+  memcpy(T_before, T_prev16, sizeof(T_before));
+  const void* xd[2] = {nullptr, nullptr};
+  const void* sd[2] = {nullptr, nullptr};
+  if (first < n_scans)
+    MML_CHECK(submit(c, o, first, R.xyzi[first], R.line[first], R.s ? R.s[first] : nullptr, R.n_pts[first], n_lines, host,
+                     &xd[first & 1], &sd[first & 1]));
+  for (int k = first; k < n_scans; k++) {
+    // the reference's pipeline: the extractor node works on the next scan meanwhile. Its launches are issued from
+    // the hook below, after this scan's critical-path work is already in the stream.
+    struct Next {
+      mml_ctx* c; Odom* o; int k; const void* xyzi; const void* line; const void* s; int n, n_lines; bool host;
+      const void** xd; const void** sd;
+    } nx = {c, o, k + 1, nullptr, nullptr, nullptr, 0, n_lines, host, &xd[(k + 1) & 1], &sd[(k + 1) & 1]};
+    if (k + 1 < n_scans) { nx.xyzi = R.xyzi[k + 1]; nx.line = R.line[k + 1]; nx.s = R.s ? R.s[k + 1] : nullptr; nx.n = R.n_pts[k + 1]; }
+    auto submit_next = [](void* a) -> int {
+      Next* x = static_cast<Next*>(a);
+      return submit(x->c, x->o, x->k, x->xyzi, x->line, x->s, x->n, x->n_lines, x->host, x->xd, x->sd);
+    };
+    Slot& S = o->slot[k & 1];
+    // constant-velocity prediction and the motion used for undistortion
+    double Tinv[16], delta[16], Tp[16];
+    rigid_inv(T_before, Tinv);
+    mat4_mul(Tinv, T_last, delta);
+    mat4_mul(T_last, delta, Tp);
+    const double dR[9] = {delta[0], delta[1], delta[2], delta[4], delta[5], delta[6], delta[8], delta[9], delta[10]};
+    const double dt[3] = {delta[3], delta[7], delta[11]};
+    const double Rp[9] = {Tp[0], Tp[1], Tp[2], Tp[4], Tp[5], Tp[6], Tp[8], Tp[9], Tp[10]};
+    const mml::Quat qp = mml::quat_from_R9(Rp);
+    double P[3] = {Tp[3], Tp[7], Tp[11]}, q[4] = {qp.w, qp.x, qp.y, qp.z};
+    double stats[16];
+    const int n = R.n_pts[k];
+    int* cnt = c->frame_cnt.as<int>();
+    MML_CUDA(c, cudaStreamWaitEvent(st, S.done, 0));
+    MML_CHECK(mml_split_voxel_device(c, (const float4*)xd[k & 1], (const float*)sd[k & 1], S.label.as<uint8_t>(), n, dR, dt,
+                                     R.leaf_corner, R.leaf_surf, c->q_corner.as<float4>(), c->q_surf.as<float4>(), cnt));
+    int* hf = c->pin_flags.as<int>();
+    MML_CUDA(c, cudaMemcpyAsync(hf, S.counters.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    MML_CUDA(c, cudaMemcpyAsync(hf + 4, cnt, 5 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    MML_CUDA(c, cudaEventRecord(S.consumed, st));
+    MML_CHECK(mml_estimate_device(c, cnt, cap, cap, R.exTlb16, P, q, R.prm, stats, k + 1 < n_scans ? +submit_next : nullptr,
+                                  &nx));  // synchronises `st`
+    if (hf[2] || hf[8]) {
+      // capacity overflow of a fused kernel: this scan goes through the general (unpipelined) path
+      MML_CUDA(c, cudaStreamSynchronize(c->stream_fe));
+      P[0] = Tp[3]; P[1] = Tp[7]; P[2] = Tp[11];
+      q[0] = qp.w; q[1] = qp.x; q[2] = qp.y; q[3] = qp.z;
+      int oc[4];
+      if (host)
+        MML_CHECK(mml_scan_to_pose(c, (const float*)R.xyzi[k], (const uint16_t*)R.line[k], R.s ? (const float*)R.s[k] : nullptr,
+                                   n, n_lines, dR, dt, R.leaf_corner, R.leaf_surf, R.exTlb16, P, q, R.prm, stats, oc));
+      else
+        MML_CHECK(mml_scan_to_pose_dev(c, R.xyzi[k], R.line[k], R.s ? R.s[k] : nullptr, n, n_lines, dR, dt, R.leaf_corner,
+                                       R.leaf_surf, R.exTlb16, P, q, R.prm, stats, oc));
+      if (R.counts_out) memcpy(R.counts_out + 4 * k, oc, sizeof(oc));
+    } else if (R.counts_out) {
+      R.counts_out[4 * k] = hf[0]; R.counts_out[4 * k + 1] = hf[1]; R.counts_out[4 * k + 2] = hf[4]; R.counts_out[4 * k + 3] = hf[5];
+    }
+    double Rm[9];
+    mml::quat_to_R(mml::Quat{q[0], q[1], q[2], q[3]}, Rm);
+    double Tn[16] = {Rm[0], Rm[1], Rm[2], P[0], Rm[3], Rm[4], Rm[5], P[1], Rm[6], Rm[7], Rm[8], P[2], 0, 0, 0, 1};
+    memcpy(R.poses_out + 16 * (size_t)k, Tn, sizeof(Tn));
+    memcpy(T_before, T_last, sizeof(T_last));
+    memcpy(T_last, Tn, sizeof(Tn));
+  }
+  return MML_OK;
+}
+
+// ---------------------------------------------------------------- chained driver
+// Returns the index of the first scan whose results are not valid (a fused kernel overflowed its capacity), or
+// n_scans when every scan went through.
+static int run_chained(mml_ctx* c, Odom* o, const RunArgs& R, const double* T_init16, const double* T_prev16, int* first_bad) {
+  cudaStream_t st = c->stream;
+  const int cap = mml_split_voxel_capacity();
+  const int n_scans = R.n_scans, n_lines = R.n_lines;
+  const bool host = R.host_buffers != 0;
+  *first_bad = n_scans;
+  if (n_scans == 0) return MML_OK;
+  mml::EstState* S = nullptr;
+  MML_CHECK(mml_chain_prepare(c, cap, &S));
+  const size_t out_doubles = (size_t)n_scans * 24, out_ints = (size_t)n_scans * 8;
+  const size_t out_bytes = out_doubles * sizeof(double) + out_ints * sizeof(int);
+  MML_CUDA(c, o->state.reserve(sizeof(mml::OdomDev) + 64));
+  MML_CUDA(c, o->out.reserve(out_bytes + 64));
+  MML_CUDA(c, o->host.reserve(out_bytes + sizeof(mml::OdomDev) + 64));
+  mml::OdomDev* od = o->state.as<mml::OdomDev>();
+  mml::ChainOut out;
+  out.poses = o->out.as<double>();
+  out.stats = out.poses + (size_t)n_scans * 16;
+  out.counts = reinterpret_cast<int*>(out.poses + out_doubles);
+  // pose history on the device
+  char* hp = o->host.as<char>();
+  mml::OdomDev* h_od = reinterpret_cast<mml::OdomDev*>(hp + out_bytes);
+  memset(h_od, 0, sizeof(*h_od));
+  memcpy(h_od->T_last, T_init16, sizeof(h_od->T_last));
+  memcpy(h_od->T_before, T_prev16, sizeof(h_od->T_before));
+  MML_CUDA(c, cudaMemcpyAsync(od, h_od, sizeof(*h_od), cudaMemcpyHostToDevice, st));
+  MML_CUDA(c, cudaMemsetAsync(out.counts, 0, out_ints * sizeof(int), st));
+  mml::SvChain ch;
+  ch.od = od;
+  ch.est = S;
+  ch.I = mml_make_est_init(R.exTlb16, R.prm);
+  const void* xd[2] = {nullptr, nullptr};
+  const void* sd[2] = {nullptr, nullptr};
+  MML_CHECK(submit(c, o, 0, R.xyzi[0], R.line[0], R.s ? R.s[0] : nullptr, R.n_pts[0], n_lines, host, &xd[0], &sd[0]));
+  int* cnt = c->frame_cnt.as<int>();
+  for (int k = 0; k < n_scans; k++) {
+    Slot& SL = o->slot[k & 1];
+    MML_CUDA(c, cudaStreamWaitEvent(st, SL.done, 0));
+    ch.fe_counters = SL.counters.as<int>();
+    ch.counts_out = out.counts + 8 * (size_t)k;
+    MML_CHECK(mml_split_voxel_device(c, (const float4*)xd[k & 1], (const float*)sd[k & 1], SL.label.as<uint8_t>(), R.n_pts[k],
+                                     nullptr, nullptr, R.leaf_corner, R.leaf_surf, c->q_corner.as<float4>(),
+                                     c->q_surf.as<float4>(), cnt, &ch));
+    MML_CUDA(c, cudaEventRecord(SL.consumed, st));
+    MML_CHECK(mml_chain_solve_launch(c, cnt, cap, od, out));
+    if (k + 1 < n_scans)
+      MML_CHECK(submit(c, o, k + 1, R.xyzi[k + 1], R.line[k + 1], R.s ? R.s[k + 1] : nullptr, R.n_pts[k + 1], n_lines, host,
+                       &xd[(k + 1) & 1], &sd[(k + 1) & 1]));
+  }
+  MML_CUDA(c, cudaMemcpyAsync(hp, out.poses, out_bytes, cudaMemcpyDeviceToHost, st));
+  MML_CUDA(c, cudaStreamSynchronize(st));
+  MML_CUDA(c, cudaStreamSynchronize(c->stream_fe));
+  const double* h_poses = reinterpret_cast<const double*>(hp);
+  const double* h_stats = h_poses + (size_t)n_scans * 16;
+  const int* h_counts = reinterpret_cast<const int*>(h_poses + out_doubles);
+  for (int k = 0; k < n_scans; k++) {
+    if (h_counts[8 * k + 4] || h_counts[8 * k + 5]) { *first_bad = k; break; }
+    memcpy(R.poses_out + 16 * (size_t)k, h_poses + 16 * (size_t)k, 16 * sizeof(double));
+    if (R.counts_out) memcpy(R.counts_out + 4 * (size_t)k, h_counts + 8 * (size_t)k, 4 * sizeof(int));
+    c->launches += c->chain_launches_per_iter * (long long)h_stats[8 * (size_t)k];  // launches inside the WHILE body
+  }
+  return MML_OK;
+}
+
+extern "C" {
 
 // Run the odometry loop over n_scans scans. xyzi/line/s are arrays of per-scan pointers (device pointers when
 // host_buffers == 0, host — ideally pinned — pointers otherwise). T_init16 = pose of the frame before the first
@@ -123,72 +283,20 @@ int mml_odom_run(mml_ctx* c, const void* const* xyzi, const void* const* line, c
   MML_CUDA(c, c->q_surf.reserve(sizeof(float4) * (size_t)cap));
   MML_CUDA(c, c->pin_flags.reserve(64));
   c->has_perm[0] = c->has_perm[1] = false;
-  double T_last[16], T_before[16];
-  memcpy(T_last, T_init16, sizeof(T_last));
-  memcpy(T_before, T_prev16, sizeof(T_before));
   MML_CUDA(c, cudaStreamSynchronize(st));
   MML_CUDA(c, cudaStreamSynchronize(c->stream_fe));
+  o->slot[0].used = o->slot[1].used = false;
   if (total_ms) MML_CUDA(c, cudaEventRecord(c->ev0, st));
-  const void* xd[2] = {nullptr, nullptr};
-  const void* sd[2] = {nullptr, nullptr};
-  if (n_scans > 0)
-    MML_CHECK(submit(c, o, 0, xyzi[0], line[0], s ? s[0] : nullptr, n_pts[0], n_lines, host_buffers != 0, &xd[0], &sd[0]));
-  for (int k = 0; k < n_scans; k++) {
-    // the reference's pipeline: the extractor node works on the next scan meanwhile. Its launches are issued from
-    // the hook below, after this scan's critical-path work is already in the stream.
-    struct Next {
-      mml_ctx* c; Odom* o; int k; const void* xyzi; const void* line; const void* s; int n, n_lines; bool host;
-      const void** xd; const void** sd;
-    } nx = {c, o, k + 1, nullptr, nullptr, nullptr, 0, n_lines, host_buffers != 0, &xd[(k + 1) & 1], &sd[(k + 1) & 1]};
-    if (k + 1 < n_scans) { nx.xyzi = xyzi[k + 1]; nx.line = line[k + 1]; nx.s = s ? s[k + 1] : nullptr; nx.n = n_pts[k + 1]; }
-    auto submit_next = [](void* a) -> int {
-      Next* x = static_cast<Next*>(a);
-      return submit(x->c, x->o, x->k, x->xyzi, x->line, x->s, x->n, x->n_lines, x->host, x->xd, x->sd);
-    };
-    Slot& S = o->slot[k & 1];
-    // constant-velocity prediction and the motion used for undistortion
-    double Tinv[16], delta[16], Tp[16];
-    rigid_inv(T_before, Tinv);
-    mat4_mul(Tinv, T_last, delta);
-    mat4_mul(T_last, delta, Tp);
-    const double dR[9] = {delta[0], delta[1], delta[2], delta[4], delta[5], delta[6], delta[8], delta[9], delta[10]};
-    const double dt[3] = {delta[3], delta[7], delta[11]};
-    const double Rp[9] = {Tp[0], Tp[1], Tp[2], Tp[4], Tp[5], Tp[6], Tp[8], Tp[9], Tp[10]};
-    const mml::Quat qp = mml::quat_from_R9(Rp);
-    double P[3] = {Tp[3], Tp[7], Tp[11]}, q[4] = {qp.w, qp.x, qp.y, qp.z};
-    double stats[16];
-    const int n = n_pts[k];
-    int* cnt = c->frame_cnt.as<int>();
-    MML_CUDA(c, cudaStreamWaitEvent(st, S.done, 0));
-    MML_CHECK(mml_split_voxel_device(c, (const float4*)xd[k & 1], (const float*)sd[k & 1], S.label.as<uint8_t>(), n, dR, dt,
-                                     leaf_corner, leaf_surf, c->q_corner.as<float4>(), c->q_surf.as<float4>(), cnt));
-    int* hf = c->pin_flags.as<int>();
-    MML_CUDA(c, cudaMemcpyAsync(hf, S.counters.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    MML_CUDA(c, cudaMemcpyAsync(hf + 4, cnt, 5 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    MML_CHECK(mml_estimate_device(c, cnt, cap, cap, exTlb16, P, q, prm, stats, k + 1 < n_scans ? +submit_next : nullptr,
-                                  &nx));  // synchronises `st`
-    if (hf[2] || hf[8]) {
-      // capacity overflow of a fused kernel: this scan goes through the general (unpipelined) path
-      MML_CUDA(c, cudaStreamSynchronize(c->stream_fe));
-      P[0] = Tp[3]; P[1] = Tp[7]; P[2] = Tp[11];
-      q[0] = qp.w; q[1] = qp.x; q[2] = qp.y; q[3] = qp.z;
-      int oc[4];
-      if (host_buffers)
-        MML_CHECK(mml_scan_to_pose(c, (const float*)xyzi[k], (const uint16_t*)line[k], s ? (const float*)s[k] : nullptr, n,
-                                   n_lines, dR, dt, leaf_corner, leaf_surf, exTlb16, P, q, prm, stats, oc));
-      else
-        MML_CHECK(mml_scan_to_pose_dev(c, xyzi[k], line[k], s ? s[k] : nullptr, n, n_lines, dR, dt, leaf_corner, leaf_surf,
-                                       exTlb16, P, q, prm, stats, oc));
-      if (counts_out) memcpy(counts_out + 4 * k, oc, sizeof(oc));
-    } else if (counts_out) {
-      counts_out[4 * k] = hf[0]; counts_out[4 * k + 1] = hf[1]; counts_out[4 * k + 2] = hf[4]; counts_out[4 * k + 3] = hf[5];
-    }
-    double R[9];
-    mml::quat_to_R(mml::Quat{q[0], q[1], q[2], q[3]}, R);
-    double Tn[16] = {R[0], R[1], R[2], P[0], R[3], R[4], R[5], P[1], R[6], R[7], R[8], P[2], 0, 0, 0, 1};
-    memcpy(poses_out + 16 * (size_t)k, Tn, sizeof(Tn));
-    memcpy(T_before, T_last, sizeof(T_last));
-    memcpy(T_last, Tn, sizeof(Tn));
+  RunArgs R = {xyzi, line, s, n_pts, n_scans, n_lines, host_buffers, exTlb16, leaf_corner, leaf_surf, prm, poses_out, counts_out};
+  const bool classic = getenv("MML_ODOM_CLASSIC") && atoi(getenv("MML_ODOM_CLASSIC")) != 0;
+  int first = 0;
+  if (!classic) MML_CHECK(run_chained(c, o, R, T_init16, T_prev16, &first));
+  if (first < n_scans) {
+    // classic driver from the first scan the chained one could not finish, seeded with the poses before it
+    const double* Ti = first >= 1 ? poses_out + 16 * (size_t)(first - 1) : T_init16;
+    const double* Tp = first >= 2 ? poses_out + 16 * (size_t)(first - 2) : (first == 1 ? T_init16 : T_prev16);
+    o->slot[0].used = o->slot[1].used = false;
+    MML_CHECK(run_classic(c, o, R, first, Ti, Tp));
   }
   if (total_ms) {
     MML_CUDA(c, cudaEventRecord(c->ev1, st));

@@ -15,6 +15,7 @@
 // Arithmetic is bit-identical to the multi-kernel path and to the CPU oracle (-fmad=false).
 #include "common.cuh"
 #include "undistort.cuh"
+#include "eststate.cuh"
 
 namespace mml {
 
@@ -31,6 +32,15 @@ struct SplitVoxelArgs {
   float4* scratch[2];     // compact undistorted labelled points, capacity kSvCap each
   float4* out[2];         // voxel centroids, capacity kSvCap each
   int* counts;            // [0..1] voxel output counts, [2..3] raw labelled counts, [4] overflow flag
+  // chained odometry loop (odometry.cu): the motion used for undistortion and the start pose of the solve come
+  // from the device-side pose history, and this launch also starts the scan's solve (k_est_init's job)
+  const OdomDev* od;
+  EstState* est;
+  EstInit I;
+  unsigned* assoc_stats_words;
+  unsigned* acc_out_words;
+  const int* fe_counters;  // the extraction's slot counters: n_sharp, n_flat, overflow
+  int* counts_out;         // ChainOut.counts of this scan
 };
 
 __device__ __forceinline__ unsigned sv_f2ord(float f) {
@@ -49,6 +59,36 @@ __global__ void __launch_bounds__(kSvThreads) k_split_voxel(SplitVoxelArgs A) {
   const uint8_t want = (uint8_t)(kind + 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float4* scratch = A.scratch[kind];
+  __shared__ UndistortParams sU;
+  const UndistortParams* Up = &A.U;
+  if (A.od) {
+    Up = &sU;
+    if (kind == 0) {  // fresh solver state and statistics (k_est_init)
+      unsigned* w = reinterpret_cast<unsigned*>(A.est);
+      for (int i = tid; i < (int)(sizeof(EstState) / 4); i += kSvThreads) w[i] = 0u;
+      if (tid < 128) A.assoc_stats_words[tid] = 0u;
+      if (tid < 64) A.acc_out_words[tid] = 0u;
+    }
+    __syncthreads();
+    if (tid == 0 || (kind == 0 && tid == 32)) {
+      // constant-velocity model: delta = T_before^-1 T_last, prediction = T_last delta (PE.cpp:847-852, 882-890)
+      double Tinv[16], delta[16];
+      rigid_inv(A.od->T_before, Tinv);
+      mat4_mul(Tinv, A.od->T_last, delta);
+      if (tid == 0) {
+        const double dR[9] = {delta[0], delta[1], delta[2], delta[4], delta[5], delta[6], delta[8], delta[9], delta[10]};
+        const double dt[3] = {delta[3], delta[7], delta[11]};
+        sU = make_undistort_params(A.s ? dR : nullptr, A.s ? dt : nullptr);
+      } else {
+        double Tp[16];
+        mat4_mul(A.od->T_last, delta, Tp);
+        const double Rp[9] = {Tp[0], Tp[1], Tp[2], Tp[4], Tp[5], Tp[6], Tp[8], Tp[9], Tp[10]};
+        const Quat qp = quat_from_R9(Rp);
+        const double P[3] = {Tp[3], Tp[7], Tp[11]}, Q[4] = {qp.w, qp.x, qp.y, qp.z};
+        est_fill(A.est, A.I, P, Q);
+      }
+    }
+  }
   if (tid == 0) s_base = 0;
   if (tid < 3) s_bbox[tid] = 0xffffffffu;
   else if (tid < 6) s_bbox[tid] = 0u;
@@ -112,7 +152,7 @@ __global__ void __launch_bounds__(kSvThreads) k_split_voxel(SplitVoxelArgs A) {
   for (int k = tid; k < cnt; k += kSvThreads) {
     const int i = (int)keys[k];
     float4 p = A.pts[i];
-    if (A.U.enabled) p = undistort_point(p, (double)A.s[i], A.U);
+    if (Up->enabled) p = undistort_point(p, (double)A.s[i], *Up);
     scratch[k] = p;
     const unsigned e[3] = {sv_f2ord(p.x), sv_f2ord(p.y), sv_f2ord(p.z)};
 #pragma unroll
@@ -132,9 +172,16 @@ __global__ void __launch_bounds__(kSvThreads) k_split_voxel(SplitVoxelArgs A) {
   if (tid == 0) {
     A.counts[2 + kind] = s_base;
     if (overflow) atomicExch(&A.counts[4], 1);
+    if (A.counts_out) {
+      if (overflow) A.counts_out[5] = 1;
+      if (kind == 0) { A.counts_out[0] = A.fe_counters[0]; A.counts_out[1] = A.fe_counters[1]; A.counts_out[4] = A.fe_counters[2]; }
+    }
   }
   if (cnt == 0) {
-    if (tid == 0) A.counts[kind] = 0;
+    if (tid == 0) {
+      A.counts[kind] = 0;
+      if (A.counts_out) A.counts_out[2 + kind] = 0;
+    }
     return;
   }
 
@@ -221,7 +268,10 @@ __global__ void __launch_bounds__(kSvThreads) k_split_voxel(SplitVoxelArgs A) {
     const float c = (float)(j - k);
     out[pos++] = make_float4(sx / c, sy / c, sz / c, si / c);
   }
-  if (tid == 0) A.counts[kind] = s_total;
+  if (tid == 0) {
+    A.counts[kind] = s_total;
+    if (A.counts_out) A.counts_out[2 + kind] = s_total;
+  }
 }
 
 }  // namespace mml
@@ -233,7 +283,7 @@ int mml_split_voxel_capacity() { return kSvCap; }
 // counts_d: int[5] = {n_corner_ds, n_surf_ds, n_corner_raw, n_surf_raw, overflow}
 int mml_split_voxel_device(mml_ctx* ctx, const float4* pts_d, const float* s_d, const uint8_t* label_d, int n,
                            const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, float4* corner_out,
-                           float4* surf_out, int* counts_d) {
+                           float4* surf_out, int* counts_d, const mml::SvChain* chain) {
   cudaStream_t st = ctx->stream;
   MML_CUDA(ctx, ctx->corner_raw.reserve(sizeof(float4) * (size_t)kSvCap));
   MML_CUDA(ctx, ctx->surf_raw.reserve(sizeof(float4) * (size_t)kSvCap));
@@ -251,7 +301,17 @@ int mml_split_voxel_device(mml_ctx* ctx, const float4* pts_d, const float* s_d, 
   A.out[0] = corner_out;
   A.out[1] = surf_out;
   A.counts = counts_d;
-  MML_CUDA(ctx, cudaMemsetAsync(counts_d + 4, 0, sizeof(int), st));
+  if (chain) {
+    A.od = chain->od;
+    A.est = chain->est;
+    A.I = chain->I;
+    A.assoc_stats_words = ctx->assoc_stats.as<unsigned>();
+    A.acc_out_words = ctx->acc_out.as<unsigned>();
+    A.fe_counters = chain->fe_counters;
+    A.counts_out = chain->counts_out;
+  } else {
+    MML_CUDA(ctx, cudaMemsetAsync(counts_d + 4, 0, sizeof(int), st));
+  }
   const size_t smem = sizeof(unsigned long long) * (size_t)kSvCap;
   static bool attr_set = false;
   if (!attr_set) {

@@ -45,8 +45,8 @@ __device__ __forceinline__ float4 undistort_point(float4 p, double s, const Undi
   return p;
 }
 
-// host: quaternion of dRlc and the slerp constants (libm, like the reference's host code)
-static inline UndistortParams make_undistort_params(const double* dR9, const double* dt3) {
+// quaternion of dRlc and the slerp constants (host: libm, like the reference's host code; device: chained loop)
+__host__ __device__ inline UndistortParams make_undistort_params(const double* dR9, const double* dt3) {
   UndistortParams P;
   memset(&P, 0, sizeof(P));
   if (!dR9 || !dt3) return P;

@@ -360,6 +360,14 @@ def test_native_odometry_loop_matches_oracle(ctx, mm, orc, synth, scene):
         for p in d[:3]:
             ctx.dev_free(p)
     assert np.array_equal(poses_h, poses_d) and np.array_equal(cnt_h, cnt_d)
+    # the host-driven driver (one synchronisation per outer iteration) must agree with the chained one
+    import os
+    os.environ["MML_ODOM_CLASSIC"] = "1"
+    try:
+        poses_c, ms_c, cnt_c = ctx.odom_run(host, 22, Ts[first], Ts[first - 1], np.eye(4), host_buffers=True)
+    finally:
+        del os.environ["MML_ODOM_CLASSIC"]
+    assert np.array_equal(cnt_c, cnt_h) and np.abs(poses_c - poses_h).max() < 1e-9
     for k, Tn in enumerate(ref):
         assert np.abs(poses_d[k][:3, 3] - Tn[:3, 3]).max() <= POSE_TOL_M
         assert np.linalg.norm(synth.R_to_rotvec(poses_d[k][:3, :3].T @ Tn[:3, :3])) <= POSE_TOL_RAD

@@ -594,7 +594,6 @@ __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
   if (A.gate && *A.gate) return;
   constexpr int QPB = 128 / G;  // queries per block
   const int lg = threadIdx.x % G;
-  const int slot_i = blockIdx.x * QPB + threadIdx.x / G;
   const unsigned mask = group_mask<G>();
   double T[16];
   float thres = A.thres;
@@ -607,17 +606,19 @@ __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
     for (int k = 0; k < 16; k++) T[k] = A.T[k];
   }
   double mom[7] = {0, 0, 0, 0, 0, 0, 0};
-  int found = 0;
   int nq = A.nq_dev ? *A.nq_dev : A.nq;
   if (nq > A.nq) {  // more queries than this launch was sized for: flag it, the host re-launches
     if (blockIdx.x == 0 && threadIdx.x == 0 && A.overflow) atomicExch(A.overflow, 1);
     nq = A.nq;
   }
+  // The grid is sized for the machine, not for the capacity of the query buffer: groups stride over the queries.
   // CTAs beyond the last query leave at once; the reduction below only spans the active ones
-  const unsigned n_active = nq > 0 ? (unsigned)((nq + QPB - 1) / QPB) : 1u;
+  const unsigned n_need = nq > 0 ? (unsigned)((nq + QPB - 1) / QPB) : 1u;
+  const unsigned n_active = n_need < gridDim.x ? n_need : gridDim.x;
   if (blockIdx.x >= n_active) return;
-  const int i = (slot_i < nq && A.qlist) ? A.qlist[slot_i] : slot_i;
-  if (slot_i < nq) {
+  for (int slot_i = blockIdx.x * QPB + threadIdx.x / G; slot_i < nq; slot_i += gridDim.x * QPB) {
+    int found = 0;
+    const int i = A.qlist ? A.qlist[slot_i] : slot_i;
     const float4 q = A.q[i];
     const double pin[3] = {(double)q.x, (double)q.y, (double)q.z};
     float sel[3];
@@ -673,7 +674,7 @@ __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
               f0.w = (fabs(err) > 1e-5) ? 1.f : 0.f;
               f2.w = (float)err;
               const double n0 = nrm[0], n1 = nrm[1], n2 = nrm[2];
-              mom[0] = n0 * n0; mom[1] = n0 * n1; mom[2] = n0 * n2; mom[3] = n1 * n1; mom[4] = n1 * n2; mom[5] = n2 * n2;
+              mom[0] += n0 * n0; mom[1] += n0 * n1; mom[2] += n0 * n2; mom[3] += n1 * n1; mom[4] += n1 * n2; mom[5] += n2 * n2;
               ok = 1;
             }
           }
@@ -686,9 +687,9 @@ __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
       A.feat[3 * slot] = f0;
       A.feat[3 * slot + 1] = f1;
       A.feat[3 * slot + 2] = f2;
+      mom[6] += (double)found;
     }
   }
-  mom[6] = (lg == 0) ? (double)found : 0.0;
   __shared__ double sred[4][7];
   __shared__ bool is_last;
 #pragma unroll
@@ -1128,7 +1129,10 @@ int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres,
   // lanes per query: a whole warp for scan-sized query sets (latency), 8 lanes for map-sized sweeps
   static const int g_env = getenv("MML_ASSOC_G") ? atoi(getenv("MML_ASSOC_G")) : 0;
   const int G = g_env ? g_env : (cap <= 32768 ? 32 : 1);
-  const int grid = G == 1 ? div_up(nq > 0 ? nq : 1, 128) : div_up(nq > 0 ? nq : 1, 128 / G);
+  // group kernels stride over the queries: at most kAssocWave CTAs (4 per SM), however large the query buffer is
+  const int kAssocWave = 4 * kNumSMs;
+  int grid = G == 1 ? div_up(nq > 0 ? nq : 1, 128) : div_up(nq > 0 ? nq : 1, 128 / G);
+  if (G != 1 && grid > kAssocWave) grid = kAssocWave;
   mml::DevBuf& fb = kind == 0 ? ctx->f_line : ctx->f_plane;
   MML_CUDA(ctx, fb.reserve(sizeof(float4) * 3 * (size_t)(nq > 0 ? nq : 1)));
   // assoc_stats layout (doubles): [0..7] line moments/count, [8..15] plane moments/count,

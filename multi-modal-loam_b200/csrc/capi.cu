@@ -50,7 +50,11 @@ int mml_ctx_create(int device, int stream_count, mml_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess) return MML_ERR_NO_DEVICE;
   mml_ctx* c = new mml_ctx();
   c->device = device;
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  // the matcher's streams outrank the extraction stream of the pipelined loop (odometry.cu): when both have CTAs
+  // waiting, the critical path gets the SMs first
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
     delete c;
     return MML_ERR_CUDA;
   }
@@ -58,7 +62,7 @@ int mml_ctx_create(int device, int stream_count, mml_ctx** out) {
     cudaStream_t s;
     if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess) c->extra_streams.push_back(s);
   }
-  cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+  cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi);
   cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   cudaEventCreate(&c->ev0);
@@ -78,7 +82,7 @@ int mml_ctx_destroy(mml_ctx* c) {
                          &c->chunk_tab, &c->chunk_hist, &c->line_start, &c->line_count, &c->curv, &c->refl, &c->attr,
                          &c->sort_ind, &c->refl_ind, &c->counters, &c->tmp_a, &c->tmp_b, &c->tmp_c, &c->tmp_d, &c->tmp_e,
                          &c->vox_keys[0], &c->vox_keys[1], &c->vox_vals[0], &c->vox_vals[1], &c->vox_hist, &c->vox_bbox,
-                         &c->corner_raw, &c->surf_raw, &c->q_corner, &c->q_surf, &c->f_line, &c->f_plane,
+                         &c->corner_raw, &c->surf_raw, &c->sv_bbox, &c->q_corner, &c->q_surf, &c->f_line, &c->f_plane,
                          &c->acc_partials, &c->acc_out, &c->est_state, &c->assoc_stats, &c->frame_cnt, &c->export_buf};
   for (auto* b : bufs) b->release();
   for (int k = 0; k < 4; k++) {

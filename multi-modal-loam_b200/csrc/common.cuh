@@ -108,6 +108,7 @@ struct mml_ctx {
   mml::DevBuf tmp_a, tmp_b, tmp_c, tmp_d, tmp_e;         // generic
   mml::DevBuf vox_keys[2], vox_vals[2], vox_hist, vox_bbox;
   mml::DevBuf corner_raw, surf_raw;                      // label-split clouds
+  mml::DevBuf sv_bbox;                                   // per-CTA boxes of the clustered split/voxel launch
   mml::PinBuf pin_in, pin_out, pin_small, pin_flags;
 
   // resident maps

@@ -54,18 +54,25 @@ struct SvChain {
   EstInit I;
   const int* fe_counters;
   int* counts_out;
+  const int* pre_idx[2];  // labelled indices compacted on the extraction stream (k_label_compact), or null
+  const int* pre_cnt;
 };
 
 __host__ __device__ inline void mat4_mul(const double* A, const double* B, double* C) {
+#pragma unroll
   for (int r = 0; r < 4; r++)
+#pragma unroll
     for (int c = 0; c < 4; c++) {
       double s = 0;
+#pragma unroll
       for (int k = 0; k < 4; k++) s += A[4 * r + k] * B[4 * k + c];
       C[4 * r + c] = s;
     }
 }
 __host__ __device__ inline void rigid_inv(const double* T, double* Ti) {
+#pragma unroll
   for (int r = 0; r < 3; r++) {
+#pragma unroll
     for (int c = 0; c < 3; c++) Ti[4 * r + c] = T[4 * c + r];
     Ti[4 * r + 3] = -(T[0 * 4 + r] * T[3] + T[1 * 4 + r] * T[7] + T[2 * 4 + r] * T[11]);
   }

@@ -21,6 +21,7 @@
 #include "eststate.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <vector>
 
 int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_d, const int* scan_off, int n_scans,
                        int n_lines, uint8_t* label_d, bool force_sequential);
@@ -28,6 +29,7 @@ int mml_split_voxel_capacity();
 int mml_split_voxel_device(mml_ctx* ctx, const float4* pts_d, const float* s_d, const uint8_t* label_d, int n,
                            const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, float4* corner_out,
                            float4* surf_out, int* counts_d, const mml::SvChain* chain = nullptr);
+int mml_label_compact_device(mml_ctx* ctx, const uint8_t* label_d, int n, int* idx0, int* idx1, int* cnt_d);
 int mml_chain_prepare(mml_ctx* ctx, int cap, mml::EstState** S_out);
 mml::EstInit mml_make_est_init(const double* exTlb16, const mml_est_params* prm);
 int mml_chain_solve_launch(mml_ctx* ctx, const int* cnt_dev, int cap, mml::OdomDev* od, mml::ChainOut out);
@@ -39,6 +41,7 @@ using mml::rigid_inv;
 
 struct Slot {
   mml::DevBuf label, counters, in_xyzi, in_line, in_s;
+  mml::DevBuf idx;                 // chained loop: [2][cap] compacted labelled indices + int[2] counts (k_label_compact)
   cudaEvent_t done = nullptr;      // extraction of the scan in this slot has finished (FE stream)
   cudaEvent_t consumed = nullptr;  // the matcher has read the slot (main stream): the next scan may overwrite it
   bool used = false;
@@ -58,19 +61,25 @@ Odom* get_odom(mml_ctx* c) {
       cudaEventCreateWithFlags(&o->slot[k].done, cudaEventDisableTiming);
       cudaEventCreateWithFlags(&o->slot[k].consumed, cudaEventDisableTiming);
     }
-    cudaStreamCreateWithFlags(&c->stream_fe, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaStreamCreateWithPriority(&c->stream_fe, cudaStreamNonBlocking, prio_lo);
     c->odom = o;
   }
   return static_cast<Odom*>(c->odom);
 }
 
 // enqueue (optional H2D +) extraction of one scan on the FE stream
+struct Trace;
+void trace_rec(Trace* t, int k, int j, cudaStream_t st);
+
 int submit(mml_ctx* c, Odom* o, int k, const void* xyzi, const void* line, const void* s, int n, int n_lines, bool host,
-           const void** xyzi_dev, const void** s_dev) {
+           const void** xyzi_dev, const void** s_dev, bool compact = false, Trace* tr = nullptr) {
   Slot& S = o->slot[k & 1];
   MML_CUDA(c, S.label.reserve((size_t)n + 16));
   MML_CUDA(c, S.counters.reserve(64));
   if (S.used) MML_CUDA(c, cudaStreamWaitEvent(c->stream_fe, S.consumed, 0));
+  if (tr) trace_rec(tr, k, 3, c->stream_fe);
   const void* xd = xyzi;
   const void* ld = line;
   const void* sd = s;
@@ -91,14 +100,53 @@ int submit(mml_ctx* c, Odom* o, int k, const void* xyzi, const void* line, const
   cudaStream_t main_stream = c->stream;
   c->stream = c->stream_fe;
   c->counters_alt = S.counters.as<int>();
-  const int rc = mml_extract_device(c, (const float4*)xd, (const uint16_t*)ld, off, 1, n_lines, S.label.as<uint8_t>(), false);
+  int rc = mml_extract_device(c, (const float4*)xd, (const uint16_t*)ld, off, 1, n_lines, S.label.as<uint8_t>(), false);
+  if (rc == MML_OK && compact) {
+    const int cap = mml_split_voxel_capacity();
+    if (S.idx.reserve(sizeof(int) * (2 * (size_t)cap + 4)) != cudaSuccess) rc = MML_ERR_CUDA;
+    int* ix = S.idx.as<int>();
+    if (rc == MML_OK) rc = mml_label_compact_device(c, S.label.as<uint8_t>(), n, ix, ix + cap, ix + 2 * cap);
+  }
   c->counters_alt = nullptr;
   c->stream = main_stream;
   MML_CHECK(rc);
+  if (tr) trace_rec(tr, k, 4, c->stream_fe);
   MML_CUDA(c, cudaEventRecord(S.done, c->stream_fe));
   S.used = true;
   return MML_OK;
 }
+
+// MML_ODOM_TRACE=1: CUDA-event timeline of the chained loop (per-scan stage durations on both streams), printed
+// to stderr. Events perturb the pipeline a little; never enabled in bench numbers.
+struct Trace {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;  // per scan: main after-wait, after split/voxel, after solve; FE start, FE end
+  cudaEvent_t at(int k, int j) { return ev[5 * (size_t)k + j]; }
+  void init(int n) {
+    on = getenv("MML_ODOM_TRACE") && atoi(getenv("MML_ODOM_TRACE")) != 0;
+    if (!on) return;
+    ev.resize(5 * (size_t)n);
+    for (auto& e : ev) cudaEventCreate(&e);
+  }
+  void rec(int k, int j, cudaStream_t st) { if (on) cudaEventRecord(at(k, j), st); }
+  void report(int n) {
+    if (!on) return;
+    double sv = 0, solve = 0, fe = 0, wait = 0, period = 0;
+    float ms;
+    for (int k = 1; k < n; k++) {
+      cudaEventElapsedTime(&ms, at(k, 0), at(k, 1)); sv += ms;
+      cudaEventElapsedTime(&ms, at(k, 1), at(k, 2)); solve += ms;
+      cudaEventElapsedTime(&ms, at(k, 3), at(k, 4)); fe += ms;
+      cudaEventElapsedTime(&ms, at(k - 1, 2), at(k, 0)); wait += ms;
+      cudaEventElapsedTime(&ms, at(k - 1, 2), at(k, 2)); period += ms;
+    }
+    const double d = 1e3 / (n - 1);
+    fprintf(stderr, "odom trace (us/scan over %d scans): period %.1f = wait-for-extraction %.1f + split/voxel %.1f + solve %.1f; "
+            "extraction stream busy %.1f\n", n - 1, period * d, wait * d, sv * d, solve * d, fe * d);
+    for (auto& e : ev) cudaEventDestroy(e);
+    ev.clear();
+  }
+};
 
 struct RunArgs {
   const void* const* xyzi; const void* const* line; const void* const* s; const int* n_pts;
@@ -106,6 +154,8 @@ struct RunArgs {
   const double* exTlb16; float leaf_corner, leaf_surf; const mml_est_params* prm;
   double* poses_out; int* counts_out;
 };
+
+void trace_rec(Trace* t, int k, int j, cudaStream_t st) { t->rec(k, j, st); }
 
 }  // namespace
 
@@ -229,25 +279,34 @@ static int run_chained(mml_ctx* c, Odom* o, const RunArgs& R, const double* T_in
   ch.I = mml_make_est_init(R.exTlb16, R.prm);
   const void* xd[2] = {nullptr, nullptr};
   const void* sd[2] = {nullptr, nullptr};
-  MML_CHECK(submit(c, o, 0, R.xyzi[0], R.line[0], R.s ? R.s[0] : nullptr, R.n_pts[0], n_lines, host, &xd[0], &sd[0]));
+  Trace tr;
+  tr.init(n_scans);
+  MML_CHECK(submit(c, o, 0, R.xyzi[0], R.line[0], R.s ? R.s[0] : nullptr, R.n_pts[0], n_lines, host, &xd[0], &sd[0], true, &tr));
   int* cnt = c->frame_cnt.as<int>();
   for (int k = 0; k < n_scans; k++) {
     Slot& SL = o->slot[k & 1];
     MML_CUDA(c, cudaStreamWaitEvent(st, SL.done, 0));
+    tr.rec(k, 0, st);
     ch.fe_counters = SL.counters.as<int>();
     ch.counts_out = out.counts + 8 * (size_t)k;
+    ch.pre_idx[0] = SL.idx.as<int>();
+    ch.pre_idx[1] = SL.idx.as<int>() + cap;
+    ch.pre_cnt = SL.idx.as<int>() + 2 * cap;
     MML_CHECK(mml_split_voxel_device(c, (const float4*)xd[k & 1], (const float*)sd[k & 1], SL.label.as<uint8_t>(), R.n_pts[k],
                                      nullptr, nullptr, R.leaf_corner, R.leaf_surf, c->q_corner.as<float4>(),
                                      c->q_surf.as<float4>(), cnt, &ch));
     MML_CUDA(c, cudaEventRecord(SL.consumed, st));
+    tr.rec(k, 1, st);
     MML_CHECK(mml_chain_solve_launch(c, cnt, cap, od, out));
+    tr.rec(k, 2, st);
     if (k + 1 < n_scans)
       MML_CHECK(submit(c, o, k + 1, R.xyzi[k + 1], R.line[k + 1], R.s ? R.s[k + 1] : nullptr, R.n_pts[k + 1], n_lines, host,
-                       &xd[(k + 1) & 1], &sd[(k + 1) & 1]));
+                       &xd[(k + 1) & 1], &sd[(k + 1) & 1], true, &tr));
   }
   MML_CUDA(c, cudaMemcpyAsync(hp, out.poses, out_bytes, cudaMemcpyDeviceToHost, st));
   MML_CUDA(c, cudaStreamSynchronize(st));
   MML_CUDA(c, cudaStreamSynchronize(c->stream_fe));
+  tr.report(n_scans);
   const double* h_poses = reinterpret_cast<const double*>(hp);
   const double* h_stats = h_poses + (size_t)n_scans * 16;
   const int* h_counts = reinterpret_cast<const int*>(h_poses + out_doubles);

@@ -648,6 +648,7 @@ struct SolveArgs {
   OdomDev* od;
   ChainOut out;
   cudaGraphConditionalHandle cond;
+  unsigned long long* tl;  // MML_TIMELINE
 };
 
 // end of a scan in the chained loop: T_wb from (P, Q) like the host loop, shift the pose history
@@ -684,6 +685,7 @@ __device__ __forceinline__ void make_pose_split(const double* x6, const double* 
 
 __global__ void __launch_bounds__(kSolveThreads, 1) k_solve_frame(SolveArgs A) {
   if (A.st->done_outer) return;  // uniform over the cluster
+  if (blockIdx.x == 0 && threadIdx.x == 0) MML_TL(A.tl, 6);
   __shared__ EstState S;         // authoritative in CTA 0; the others use the parameters only
   __shared__ PoseLin L;
   __shared__ double sred[kSolveWarps][28];
@@ -780,6 +782,14 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve_frame(SolveArgs A) {
       if (S.done_outer) chain_publish(A, S);
       cudaGraphSetConditional(A.cond, S.done_outer ? 0u : 1u);
     }
+#ifdef MML_TIMELINE
+    if (A.tl) {  // log this outer iteration's stamps: tl[16 + 8 * n ...], n = running iteration count in tl[9]
+      tl_stamp(A.tl, 7);
+      const unsigned long long n = A.tl[9];
+      if (n < 4000) for (int i = 0; i < 8; i++) A.tl[16 + 8 * n + i] = A.tl[i];
+      A.tl[9] = n + 1;
+    }
+#endif
   }
   __syncthreads();
   {
@@ -883,6 +893,7 @@ static int launch_solve_frame(mml_ctx* ctx, EstState* S, const int* cnt_dev, Odo
   SA.od = od;
   SA.out = out;
   SA.cond = cond;
+  SA.tl = od ? ctx->timeline.as<unsigned long long>() : nullptr;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(kSolveCluster);

@@ -249,6 +249,8 @@ struct AssocArgs {
   const int* gate;          // device flag: nonzero -> skip (used by the estimate graph)
   const double* T_dev;      // optional: T and thres read from device state
   const float* thres_dev;
+  unsigned long long* tl;   // MML_TIMELINE
+  int tl_slot;
 };
 
 __device__ bool fit_line(const float4* pts, const Knn5& r, float* a, float* b) {
@@ -480,7 +482,8 @@ __device__ __forceinline__ void scan_cells(const GridLevel& L, int c0, int c1, f
 // acceptable 5-list exists); false when rr1 was exhausted without a verdict.
 template <int G>
 __device__ bool search_shells(const GridLevel& L, const int* c, const int* lo, const int* hi, float qx, float qy, float qz,
-                              float thres, int rr0, int rr1, Knn5& r, Knn5& m, unsigned mask, int lg) {
+                              float thres, int rr0, int rr1, Knn5& r, Knn5& m, unsigned mask, int lg, int* lst) {
+  constexpr int kListCap = 8 * G;  // candidate indices staged per group
   for (int rr = rr0; rr <= rr1; rr++) {
     const int side = 2 * rr + 1;
     const int nseg = rr == 1 ? 27 : 2 * side * side;
@@ -517,18 +520,41 @@ __device__ bool search_shells(const GridLevel& L, const int* c, const int* lo, c
           p1 = __ldg(L.cell_start + rowb + x1 + 1);
         }
       }
-      unsigned live = __ballot_sync(mask, p1 > p0);
-      if (G < 32) live = (live >> ((threadIdx.x & 31u) & ~(unsigned)(G - 1))) & ((1u << (G & 31)) - 1u);
-      while (live) {
-        const int src = __ffs(live) - 1;  // lane within the group
-        live &= live - 1;
-        const int b0 = __shfl_sync(mask, p0, src, G), b1 = __shfl_sync(mask, p1, src, G);
-        for (int k = b0 + lg; k < b1; k += G) {
-          const float4 p = __ldg(L.pts + k);
-          const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-          const float d = (dx * dx + dy * dy) + dz * dz;
-          knn_push(r, d, __float_as_int(p.w), k);
+      // The non-empty ranges are flattened into one candidate list in shared memory (group prefix sum of the range
+      // lengths), so that the point loads of a whole batch of cells are issued back to back - one memory round trip
+      // per batch instead of one per cell range, which is what a lone query's latency is made of.
+      const int len = p1 - p0;
+      int incl = len;
+#pragma unroll
+      for (int d = 1; d < G; d <<= 1) {
+        const int y = __shfl_up_sync(mask, incl, d, G);
+        if (lg >= d) incl += y;
+      }
+      const int excl = incl - len;
+      const int total = __shfl_sync(mask, incl, G - 1, G);
+      for (int cbase = 0; cbase < total; cbase += kListCap) {
+        const int s0 = max(excl, cbase), s1 = min(incl, cbase + kListCap);
+        for (int c = s0; c < s1; c++) lst[c - cbase] = p0 + (c - excl);
+        __syncwarp(mask);
+        const int ncand = min(total - cbase, kListCap);
+        for (int c0 = 0; c0 < ncand; c0 += 4 * G) {
+          int kk[4];
+          float4 pp[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int c = c0 + u * G + lg;
+            kk[u] = c < ncand ? lst[c] : -1;
+            if (kk[u] >= 0) pp[u] = __ldg(L.pts + kk[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if (kk[u] < 0) continue;
+            const float dx = qx - pp[u].x, dy = qy - pp[u].y, dz = qz - pp[u].z;
+            const float d = (dx * dx + dy * dy) + dz * dz;
+            knn_push(r, d, __float_as_int(pp[u].w), kk[u]);
+          }
         }
+        __syncwarp(mask);
       }
     }
     group_merge<G>(r, m, mask, lg);
@@ -554,7 +580,7 @@ __device__ int g_fine_shells = 2;
 
 template <int G>
 __device__ bool knn5_grid_group(const GridDev& Gd, float qx, float qy, float qz, float thres, Knn5& m, unsigned mask, int lg,
-                                const float4*& base) {
+                                const float4*& base, int* lst) {
   base = Gd.pts;
   Knn5 r;
   knn_init(r);
@@ -571,7 +597,7 @@ __device__ bool knn5_grid_group(const GridDev& Gd, float qx, float qy, float qz,
   L0.dim[0] = Gd.dim[0]; L0.dim[1] = Gd.dim[1]; L0.dim[2] = Gd.dim[2];
   const int rmax = (int)ceilf(sqrtf(thres) / Gd.cell) + 1;
   const bool two_level = Gd.pts2 != nullptr && rmax > kFineShells;
-  bool done = search_shells<G>(L0, c, lo, hi, qx, qy, qz, thres, 1, two_level ? kFineShells : rmax, r, m, mask, lg);
+  bool done = search_shells<G>(L0, c, lo, hi, qx, qy, qz, thres, 1, two_level ? kFineShells : rmax, r, m, mask, lg, lst);
   if (!done && two_level) {
     GridLevel L1;
     L1.pts = Gd.pts2; L1.cell_start = Gd.cell_start2; L1.cell = Gd.cell * (float)Gd.coarse;
@@ -583,7 +609,7 @@ __device__ bool knn5_grid_group(const GridDev& Gd, float qx, float qy, float qz,
     knn_init(r);
     knn_init(m);
     const int rmax2 = (int)ceilf(sqrtf(thres) / L1.cell) + 1;
-    search_shells<G>(L1, c2, lo2, hi2, qx, qy, qz, thres, 1, rmax2, r, m, mask, lg);
+    search_shells<G>(L1, c2, lo2, hi2, qx, qy, qz, thres, 1, rmax2, r, m, mask, lg, lst);
     base = Gd.pts2;  // the 5-list now indexes the coarse-sorted copy
   }
   return m.cnt == 5 && m.d[4] < thres;
@@ -593,6 +619,9 @@ template <int KIND, int G>
 __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
   if (A.gate && *A.gate) return;
   constexpr int QPB = 128 / G;  // queries per block
+  __shared__ int s_lst[QPB][8 * G];
+  int* lst = s_lst[threadIdx.x / G];
+  if (blockIdx.x == 0 && threadIdx.x == 0) MML_TL(A.tl, A.tl_slot);
   const int lg = threadIdx.x % G;
   const unsigned mask = group_mask<G>();
   double T[16];
@@ -618,6 +647,9 @@ __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
   if (blockIdx.x >= n_active) return;
   for (int slot_i = blockIdx.x * QPB + threadIdx.x / G; slot_i < nq; slot_i += gridDim.x * QPB) {
     int found = 0;
+#ifdef MML_TIMELINE
+    const long long qc0 = clock64();
+#endif
     const int i = A.qlist ? A.qlist[slot_i] : slot_i;
     const float4 q = A.q[i];
     const double pin[3] = {(double)q.x, (double)q.y, (double)q.z};
@@ -635,7 +667,19 @@ __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
         const GridDev& Gd = A.G[mp];
         if (!Gd.valid) continue;
         const float4* base;
-        if (!knn5_grid_group<G>(Gd, sel[0], sel[1], sel[2], thres, r, mask, lg, base)) continue;  // group-uniform
+#ifdef MML_TIMELINE
+        const long long qc1 = clock64();
+#endif
+        const bool knn_ok = knn5_grid_group<G>(Gd, sel[0], sel[1], sel[2], thres, r, mask, lg, base, lst);
+#ifdef MML_TIMELINE
+        if (A.tl && lg == 0) {
+          unsigned* dbg = reinterpret_cast<unsigned*>(A.tl + 16 + 8 * 4000) + 32768;
+          const int sl = (KIND ? 16384 : 0) + (slot_i < 16384 ? slot_i : 16383);
+          dbg[sl] = (unsigned)(qc1 - qc0);                 // setup
+          dbg[32768 + sl] = (unsigned)(clock64() - qc1);   // search
+        }
+#endif
+        if (!knn_ok) continue;  // group-uniform
         int ok = 0;
         if (lg == 0) {
           if (KIND == 0) {
@@ -688,6 +732,9 @@ __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
       A.feat[3 * slot + 1] = f1;
       A.feat[3 * slot + 2] = f2;
       mom[6] += (double)found;
+#ifdef MML_TIMELINE
+      if (A.tl) reinterpret_cast<unsigned*>(A.tl + 16 + 8 * 4000)[(KIND ? 16384 : 0) + (slot_i < 16384 ? slot_i : 16383)] = (unsigned)(clock64() - qc0);
+#endif
     }
   }
   __shared__ double sred[4][7];
@@ -718,6 +765,7 @@ __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
       if (threadIdx.x == 6) *A.n_feat_out = (int)s;
     }
     if (threadIdx.x == 0) *A.ticket = 0;
+    if (threadIdx.x == 0) MML_TL(A.tl, A.tl_slot + 1);
   }
 }
 
@@ -1159,6 +1207,8 @@ int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres,
   A.gate = gate;
   A.T_dev = T_dev;
   A.thres_dev = thres_dev;
+  A.tl = ctx->timeline.as<unsigned long long>();
+  A.tl_slot = kind == 1 ? 2 : 4;
   A.overflow = ints + 6;
   A.perm = ctx->has_perm[kind] ? ctx->perm[kind].as<unsigned>() : nullptr;
   static const int tile_env = getenv("MML_ASSOC_TILE") ? atoi(getenv("MML_ASSOC_TILE")) : 0;  // experiment: lost to the sorted thread-per-query kernel

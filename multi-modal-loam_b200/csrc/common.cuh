@@ -108,6 +108,7 @@ struct mml_ctx {
   mml::DevBuf tmp_a, tmp_b, tmp_c, tmp_d, tmp_e;         // generic
   mml::DevBuf vox_keys[2], vox_vals[2], vox_hist, vox_bbox;
   mml::DevBuf corner_raw, surf_raw;                      // label-split clouds
+  mml::DevBuf timeline;                                  // MML_TIMELINE debug stamps
   mml::DevBuf sv_bbox;                                   // per-CTA boxes of the clustered split/voxel launch
   mml::PinBuf pin_in, pin_out, pin_small, pin_flags;
 
@@ -158,6 +159,20 @@ struct mml_ctx {
   } while (0)
 
 #define MML_LAUNCHED(ctx) ((ctx)->launches++)
+
+// MML_TIMELINE builds: every kernel of the chained loop stamps %globaltimer into a small device array so that the
+// last kernel of a scan can print where the scan's time went (debug only; never in bench numbers).
+#ifdef MML_TIMELINE
+__device__ __forceinline__ void tl_stamp(unsigned long long* tl, int k) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  tl[k] = t;
+}
+#define MML_TL(tl, k) do { if (tl) mml_tl_stamp_once(tl, k); } while (0)
+__device__ __forceinline__ void mml_tl_stamp_once(unsigned long long* tl, int k) { tl_stamp(tl, k); }
+#else
+#define MML_TL(tl, k) do { } while (0)
+#endif
 
 static inline int mml_fail(mml_ctx* ctx, int code, const char* msg) {
   if (ctx) ctx->err = msg;

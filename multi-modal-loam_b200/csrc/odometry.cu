@@ -22,6 +22,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <vector>
+#include <algorithm>
 
 int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_d, const int* scan_off, int n_scans,
                        int n_lines, uint8_t* label_d, bool force_sequential);
@@ -255,6 +256,10 @@ static int run_chained(mml_ctx* c, Odom* o, const RunArgs& R, const double* T_in
   if (n_scans == 0) return MML_OK;
   mml::EstState* S = nullptr;
   MML_CHECK(mml_chain_prepare(c, cap, &S));
+#ifdef MML_TIMELINE
+  MML_CUDA(c, c->timeline.reserve(8 * (16 + 8 * 4000) + 4 * 32768 * 3));
+  MML_CUDA(c, cudaMemsetAsync(c->timeline.p, 0, 8 * 16, st));
+#endif
   const size_t out_doubles = (size_t)n_scans * 24, out_ints = (size_t)n_scans * 8;
   const size_t out_bytes = out_doubles * sizeof(double) + out_ints * sizeof(int);
   MML_CUDA(c, o->state.reserve(sizeof(mml::OdomDev) + 64));
@@ -307,6 +312,42 @@ static int run_chained(mml_ctx* c, Odom* o, const RunArgs& R, const double* T_in
   MML_CUDA(c, cudaStreamSynchronize(st));
   MML_CUDA(c, cudaStreamSynchronize(c->stream_fe));
   tr.report(n_scans);
+#ifdef MML_TIMELINE
+  {  // device-side stamps of every kernel on the matcher's path (debug build only)
+    std::vector<unsigned long long> tl(16 + 8 * 4000);
+    cudaMemcpy(tl.data(), c->timeline.p, tl.size() * 8, cudaMemcpyDeviceToHost);
+    const int n = (int)tl[9] < 4000 ? (int)tl[9] : 4000;
+    double gap = 0, sv = 0, entry = 0, a1 = 0, a0 = 0, join = 0, solve = 0;
+    int m = 0;
+    for (int i = 1; i < n; i++) {
+      const unsigned long long* t = &tl[16 + 8 * i];
+      const unsigned long long* p = &tl[16 + 8 * (i - 1)];
+      if (t[0] == p[0]) continue;  // second outer iteration of the same scan
+      gap += (double)(t[0] - p[7]); sv += (double)(t[1] - t[0]);
+      const unsigned long long as = t[2] < t[4] ? t[2] : t[4], ae = t[3] > t[5] ? t[3] : t[5];
+      entry += (double)(as - t[1]); a1 += (double)(t[3] - t[2]); a0 += (double)(t[5] - t[4]); join += (double)(t[6] - ae);
+      solve += (double)(t[7] - t[6]);
+      m++;
+    }
+    std::vector<unsigned> qc(32768 * 3);
+    cudaMemcpy(qc.data(), (char*)c->timeline.p + 8 * (16 + 8 * 4000), 4 * 32768 * 3, cudaMemcpyDeviceToHost);
+    for (int kind = 0; kind < 2; kind++) {
+      double su = 0, se = 0; int nn = 0;
+      for (int i = 0; i < 16384; i++) if (qc[65536 + kind * 16384 + i]) { su += qc[32768 + kind * 16384 + i]; se += qc[65536 + kind * 16384 + i]; nn++; }
+      if (nn) fprintf(stderr, "association kind %d: mean setup %.0f, search %.0f cycles\n", kind, su / nn, se / nn);
+      std::vector<unsigned> v;
+      for (int i = 0; i < 16384; i++) if (qc[kind * 16384 + i]) v.push_back(qc[kind * 16384 + i]);
+      if (v.empty()) continue;
+      std::sort(v.begin(), v.end());
+      double sum = 0; for (unsigned x : v) sum += x;
+      fprintf(stderr, "association kind %d, last scan: %zu queries, cycles per query mean %.0f p50 %u p90 %u p99 %u max %u\n", kind, v.size(),
+              sum / v.size(), v[v.size() / 2], v[v.size() * 9 / 10], v[v.size() * 99 / 100], v.back());
+    }
+    if (m) fprintf(stderr, "device timeline (us, %d scans): prev solve end -> split/voxel start %.1f | split/voxel %.1f | -> first association start %.1f | "
+                   "plane association %.1f, line association %.1f | -> solve start %.1f | solve %.1f\n", m, gap / m / 1e3, sv / m / 1e3,
+                   entry / m / 1e3, a1 / m / 1e3, a0 / m / 1e3, join / m / 1e3, solve / m / 1e3);
+  }
+#endif
   const double* h_poses = reinterpret_cast<const double*>(hp);
   const double* h_stats = h_poses + (size_t)n_scans * 16;
   const int* h_counts = reinterpret_cast<const int*>(h_poses + out_doubles);

@@ -46,6 +46,7 @@ struct SplitVoxelArgs {
   const int* pre_idx[2];   // input-order indices of the points with label 1 / 2, capacity kSvCap each
   const int* pre_cnt;      // [2] raw labelled counts (may exceed kSvCap: overflow)
   unsigned* bbox_part;     // cluster launch: [2][CL][6] per-CTA bounding boxes
+  unsigned long long* tl;  // MML_TIMELINE
 };
 
 __device__ __forceinline__ unsigned sv_f2ord(float f) {
@@ -246,6 +247,7 @@ __global__ void __launch_bounds__(kSvThreads) k_split_voxel(SplitVoxelArgs A) {
   const uint8_t want = (uint8_t)(kind + 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float4* scratch = A.scratch[kind];
+  if (blockIdx.x == CL && tid == 0) MML_TL(A.tl, 0);
 #ifdef MML_SV_PROF
   long long tp[6] = {0, 0, 0, 0, 0, 0}, t0 = clock64(), t1;
 #define SV_TICK(k) { t1 = clock64(); tp[k] += t1 - t0; t0 = t1; }
@@ -472,6 +474,7 @@ __global__ void __launch_bounds__(kSvThreads) k_split_voxel(SplitVoxelArgs A) {
   if (tid == 0) {
     A.counts[kind] = s_total;
     if (A.counts_out) A.counts_out[2 + kind] = s_total;
+    if (kind == 1) MML_TL(A.tl, 1);
   }
   SV_TICK(5)
 #ifdef MML_SV_PROF
@@ -518,6 +521,7 @@ int mml_split_voxel_device(mml_ctx* ctx, const float4* pts_d, const float* s_d, 
     A.pre_idx[0] = chain->pre_idx[0];
     A.pre_idx[1] = chain->pre_idx[1];
     A.pre_cnt = chain->pre_cnt;
+    A.tl = ctx->timeline.as<unsigned long long>();
   } else {
     MML_CUDA(ctx, cudaMemsetAsync(counts_d + 4, 0, sizeof(int), st));
   }

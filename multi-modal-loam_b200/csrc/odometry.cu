@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <vector>
 #include <algorithm>
+#include <utility>
 
 int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_d, const int* scan_off, int n_scans,
                        int n_lines, uint8_t* label_d, bool force_sequential);
@@ -40,16 +41,40 @@ namespace {
 using mml::mat4_mul;
 using mml::rigid_inv;
 
+constexpr int kSlots = 4;   // scans in flight: being copied, being labelled (x2), being matched
+constexpr int kLanes = 2;   // extraction lanes (streams + scratch sets): scans k and k+1 are labelled concurrently
+
 struct Slot {
   mml::DevBuf label, counters, in_xyzi, in_line, in_s;
   mml::DevBuf idx;                 // chained loop: [2][cap] compacted labelled indices + int[2] counts (k_label_compact)
-  cudaEvent_t done = nullptr;      // extraction of the scan in this slot has finished (FE stream)
+  cudaEvent_t copied = nullptr;    // host -> device copy of the scan has finished (copy stream)
+  cudaEvent_t done = nullptr;      // extraction of the scan in this slot has finished (extraction lane)
   cudaEvent_t consumed = nullptr;  // the matcher has read the slot (main stream): the next scan may overwrite it
   bool used = false;
+  const void* xd = nullptr;        // device pointers of the scan currently in the slot
+  const void* ld = nullptr;
+  const void* sd = nullptr;
 };
 
+// the extraction's working buffers (mml_ctx members), one set per lane; swapped into the context around a launch
+struct FeScratch {
+  mml::DevBuf srt_xyzi, srt_src, srt_line, chunk_tab, chunk_hist, line_start, line_count, curv, refl, attr, sort_ind, refl_ind;
+  mml::PinBuf pin_small;
+  std::vector<int> last_scan_off;
+};
+void swap_scratch(mml_ctx* c, FeScratch& f) {
+  std::swap(c->srt_xyzi, f.srt_xyzi); std::swap(c->srt_src, f.srt_src); std::swap(c->srt_line, f.srt_line);
+  std::swap(c->chunk_tab, f.chunk_tab); std::swap(c->chunk_hist, f.chunk_hist); std::swap(c->line_start, f.line_start);
+  std::swap(c->line_count, f.line_count); std::swap(c->curv, f.curv); std::swap(c->refl, f.refl); std::swap(c->attr, f.attr);
+  std::swap(c->sort_ind, f.sort_ind); std::swap(c->refl_ind, f.refl_ind); std::swap(c->pin_small, f.pin_small);
+  std::swap(c->last_scan_off, f.last_scan_off);
+}
+
 struct Odom {
-  Slot slot[2];
+  Slot slot[kSlots];
+  cudaStream_t lane[kLanes] = {nullptr, nullptr};  // lane[0] == ctx->stream_fe
+  cudaStream_t copy = nullptr;
+  FeScratch scratch[kLanes];  // scratch[0] stays empty: lane 0 works in the context's own buffers
   mml::DevBuf state;  // OdomDev
   mml::DevBuf out;    // ChainOut arrays
   mml::PinBuf host;   // staging: OdomDev upload + ChainOut read-back
@@ -58,62 +83,86 @@ struct Odom {
 Odom* get_odom(mml_ctx* c) {
   if (!c->odom) {
     Odom* o = new Odom();
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < kSlots; k++) {
+      cudaEventCreateWithFlags(&o->slot[k].copied, cudaEventDisableTiming);
       cudaEventCreateWithFlags(&o->slot[k].done, cudaEventDisableTiming);
       cudaEventCreateWithFlags(&o->slot[k].consumed, cudaEventDisableTiming);
     }
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     cudaStreamCreateWithPriority(&c->stream_fe, cudaStreamNonBlocking, prio_lo);
+    o->lane[0] = c->stream_fe;
+    for (int k = 1; k < kLanes; k++) cudaStreamCreateWithPriority(&o->lane[k], cudaStreamNonBlocking, prio_lo);
+    cudaStreamCreateWithPriority(&o->copy, cudaStreamNonBlocking, prio_lo);
     c->odom = o;
   }
   return static_cast<Odom*>(c->odom);
 }
 
-// enqueue (optional H2D +) extraction of one scan on the FE stream
 struct Trace;
 void trace_rec(Trace* t, int k, int j, cudaStream_t st);
 
-int submit(mml_ctx* c, Odom* o, int k, const void* xyzi, const void* line, const void* s, int n, int n_lines, bool host,
-           const void** xyzi_dev, const void** s_dev, bool compact = false, Trace* tr = nullptr) {
-  Slot& S = o->slot[k & 1];
-  MML_CUDA(c, S.label.reserve((size_t)n + 16));
-  MML_CUDA(c, S.counters.reserve(64));
-  if (S.used) MML_CUDA(c, cudaStreamWaitEvent(c->stream_fe, S.consumed, 0));
-  if (tr) trace_rec(tr, k, 3, c->stream_fe);
-  const void* xd = xyzi;
-  const void* ld = line;
-  const void* sd = s;
+// Stage 1 of a scan: make it resident. Host buffers are copied into the scan's slot - on the copy stream when
+// `own_stream` (chained loop: the copy of scan k+3 runs beside the labelling of k+1, k+2), else on lane 0.
+int submit_copy(mml_ctx* c, Odom* o, int k, const void* xyzi, const void* line, const void* s, int n, bool host, bool own_stream) {
+  Slot& S = o->slot[k % kSlots];
+  cudaStream_t sc = own_stream ? o->copy : o->lane[0];
+  if (S.used) MML_CUDA(c, cudaStreamWaitEvent(sc, S.consumed, 0));
+  S.xd = xyzi;
+  S.ld = line;
+  S.sd = s;
   if (host) {
     MML_CUDA(c, S.in_xyzi.reserve(sizeof(float4) * (size_t)n));
     MML_CUDA(c, S.in_line.reserve(sizeof(uint16_t) * (size_t)n));
     MML_CUDA(c, S.in_s.reserve(sizeof(float) * (size_t)n));
-    MML_CUDA(c, cudaMemcpyAsync(S.in_xyzi.p, xyzi, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream_fe));
-    MML_CUDA(c, cudaMemcpyAsync(S.in_line.p, line, sizeof(uint16_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream_fe));
-    if (s) MML_CUDA(c, cudaMemcpyAsync(S.in_s.p, s, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, c->stream_fe));
-    xd = S.in_xyzi.p;
-    ld = S.in_line.p;
-    sd = s ? S.in_s.p : nullptr;
+    MML_CUDA(c, cudaMemcpyAsync(S.in_xyzi.p, xyzi, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, sc));
+    MML_CUDA(c, cudaMemcpyAsync(S.in_line.p, line, sizeof(uint16_t) * (size_t)n, cudaMemcpyHostToDevice, sc));
+    if (s) MML_CUDA(c, cudaMemcpyAsync(S.in_s.p, s, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, sc));
+    S.xd = S.in_xyzi.p;
+    S.ld = S.in_line.p;
+    S.sd = s ? S.in_s.p : nullptr;
   }
-  *xyzi_dev = xd;
-  *s_dev = sd;
+  MML_CUDA(c, cudaEventRecord(S.copied, sc));
+  return MML_OK;
+}
+
+// Stage 2: label the scan (and, for the chained loop, compact the labelled indices) on extraction lane `ln`.
+int submit_extract(mml_ctx* c, Odom* o, int k, int n, int n_lines, int ln, bool compact, Trace* tr) {
+  Slot& S = o->slot[k % kSlots];
+  cudaStream_t sfe = o->lane[ln];
+  MML_CUDA(c, S.label.reserve((size_t)n + 16));
+  MML_CUDA(c, S.counters.reserve(64));
+  MML_CUDA(c, cudaStreamWaitEvent(sfe, S.copied, 0));  // also orders the lane after the slot's previous consumer
+  if (tr) trace_rec(tr, k, 3, sfe);
   const int off[2] = {0, n};
   cudaStream_t main_stream = c->stream;
-  c->stream = c->stream_fe;
+  c->stream = sfe;
   c->counters_alt = S.counters.as<int>();
-  int rc = mml_extract_device(c, (const float4*)xd, (const uint16_t*)ld, off, 1, n_lines, S.label.as<uint8_t>(), false);
+  if (ln > 0) swap_scratch(c, o->scratch[ln]);
+  int rc = mml_extract_device(c, (const float4*)S.xd, (const uint16_t*)S.ld, off, 1, n_lines, S.label.as<uint8_t>(), false);
   if (rc == MML_OK && compact) {
     const int cap = mml_split_voxel_capacity();
     if (S.idx.reserve(sizeof(int) * (2 * (size_t)cap + 4)) != cudaSuccess) rc = MML_ERR_CUDA;
     int* ix = S.idx.as<int>();
     if (rc == MML_OK) rc = mml_label_compact_device(c, S.label.as<uint8_t>(), n, ix, ix + cap, ix + 2 * cap);
   }
+  if (ln > 0) swap_scratch(c, o->scratch[ln]);
   c->counters_alt = nullptr;
   c->stream = main_stream;
   MML_CHECK(rc);
-  if (tr) trace_rec(tr, k, 4, c->stream_fe);
-  MML_CUDA(c, cudaEventRecord(S.done, c->stream_fe));
+  if (tr) trace_rec(tr, k, 4, sfe);
+  MML_CUDA(c, cudaEventRecord(S.done, sfe));
   S.used = true;
+  return MML_OK;
+}
+
+// classic driver: copy + labelling of one scan on lane 0
+int submit(mml_ctx* c, Odom* o, int k, const void* xyzi, const void* line, const void* s, int n, int n_lines, bool host,
+           const void** xyzi_dev, const void** s_dev) {
+  MML_CHECK(submit_copy(c, o, k, xyzi, line, s, n, host, false));
+  MML_CHECK(submit_extract(c, o, k, n, n_lines, 0, false, nullptr));
+  *xyzi_dev = o->slot[k % kSlots].xd;
+  *s_dev = o->slot[k % kSlots].sd;
   return MML_OK;
 }
 
@@ -195,7 +244,7 @@ static int run_classic(mml_ctx* c, Odom* o, const RunArgs& R, int first, const d
       Next* x = static_cast<Next*>(a);
       return submit(x->c, x->o, x->k, x->xyzi, x->line, x->s, x->n, x->n_lines, x->host, x->xd, x->sd);
     };
-    Slot& S = o->slot[k & 1];
+    Slot& S = o->slot[k % kSlots];
     // constant-velocity prediction and the motion used for undistortion
     double Tinv[16], delta[16], Tp[16];
     rigid_inv(T_before, Tinv);
@@ -282,14 +331,16 @@ static int run_chained(mml_ctx* c, Odom* o, const RunArgs& R, const double* T_in
   ch.od = od;
   ch.est = S;
   ch.I = mml_make_est_init(R.exTlb16, R.prm);
-  const void* xd[2] = {nullptr, nullptr};
-  const void* sd[2] = {nullptr, nullptr};
   Trace tr;
   tr.init(n_scans);
-  MML_CHECK(submit(c, o, 0, R.xyzi[0], R.line[0], R.s ? R.s[0] : nullptr, R.n_pts[0], n_lines, host, &xd[0], &sd[0], true, &tr));
+  // pipeline depth: copies run three scans ahead of the matcher, labelling two (one scan per extraction lane)
+  auto copy_of = [&](int k) { return submit_copy(c, o, k, R.xyzi[k], R.line[k], R.s ? R.s[k] : nullptr, R.n_pts[k], host, true); };
+  auto extract_of = [&](int k) { return submit_extract(c, o, k, R.n_pts[k], n_lines, k % kLanes, true, &tr); };
+  for (int k = 0; k < 3 && k < n_scans; k++) MML_CHECK(copy_of(k));
+  for (int k = 0; k < 2 && k < n_scans; k++) MML_CHECK(extract_of(k));
   int* cnt = c->frame_cnt.as<int>();
   for (int k = 0; k < n_scans; k++) {
-    Slot& SL = o->slot[k & 1];
+    Slot& SL = o->slot[k % kSlots];
     MML_CUDA(c, cudaStreamWaitEvent(st, SL.done, 0));
     tr.rec(k, 0, st);
     ch.fe_counters = SL.counters.as<int>();
@@ -297,20 +348,20 @@ static int run_chained(mml_ctx* c, Odom* o, const RunArgs& R, const double* T_in
     ch.pre_idx[0] = SL.idx.as<int>();
     ch.pre_idx[1] = SL.idx.as<int>() + cap;
     ch.pre_cnt = SL.idx.as<int>() + 2 * cap;
-    MML_CHECK(mml_split_voxel_device(c, (const float4*)xd[k & 1], (const float*)sd[k & 1], SL.label.as<uint8_t>(), R.n_pts[k],
+    MML_CHECK(mml_split_voxel_device(c, (const float4*)SL.xd, (const float*)SL.sd, SL.label.as<uint8_t>(), R.n_pts[k],
                                      nullptr, nullptr, R.leaf_corner, R.leaf_surf, c->q_corner.as<float4>(),
                                      c->q_surf.as<float4>(), cnt, &ch));
     MML_CUDA(c, cudaEventRecord(SL.consumed, st));
     tr.rec(k, 1, st);
     MML_CHECK(mml_chain_solve_launch(c, cnt, cap, od, out));
     tr.rec(k, 2, st);
-    if (k + 1 < n_scans)
-      MML_CHECK(submit(c, o, k + 1, R.xyzi[k + 1], R.line[k + 1], R.s ? R.s[k + 1] : nullptr, R.n_pts[k + 1], n_lines, host,
-                       &xd[(k + 1) & 1], &sd[(k + 1) & 1], true, &tr));
+    if (k + 3 < n_scans) MML_CHECK(copy_of(k + 3));
+    if (k + 2 < n_scans) MML_CHECK(extract_of(k + 2));
   }
   MML_CUDA(c, cudaMemcpyAsync(hp, out.poses, out_bytes, cudaMemcpyDeviceToHost, st));
   MML_CUDA(c, cudaStreamSynchronize(st));
-  MML_CUDA(c, cudaStreamSynchronize(c->stream_fe));
+  for (int k = 0; k < kLanes; k++) MML_CUDA(c, cudaStreamSynchronize(o->lane[k]));
+  MML_CUDA(c, cudaStreamSynchronize(o->copy));
   tr.report(n_scans);
 #ifdef MML_TIMELINE
   {  // device-side stamps of every kernel on the matcher's path (debug build only)
@@ -360,6 +411,33 @@ static int run_chained(mml_ctx* c, Odom* o, const RunArgs& R, const double* T_in
   return MML_OK;
 }
 
+// called by mml_ctx_destroy: streams, events and buffers of the pipelined runner
+void mml_odom_destroy(mml_ctx* c) {
+  if (!c->odom) return;
+  Odom* o = static_cast<Odom*>(c->odom);
+  for (int k = 0; k < kLanes; k++)
+    if (o->lane[k]) { cudaStreamSynchronize(o->lane[k]); if (k > 0) cudaStreamDestroy(o->lane[k]); }
+  if (o->copy) { cudaStreamSynchronize(o->copy); cudaStreamDestroy(o->copy); }
+  for (int k = 0; k < kSlots; k++) {
+    Slot& S = o->slot[k];
+    cudaEventDestroy(S.copied); cudaEventDestroy(S.done); cudaEventDestroy(S.consumed);
+    mml::DevBuf* b[] = {&S.label, &S.counters, &S.in_xyzi, &S.in_line, &S.in_s, &S.idx};
+    for (auto* x : b) x->release();
+  }
+  for (int k = 0; k < kLanes; k++) {
+    FeScratch& f = o->scratch[k];
+    mml::DevBuf* b[] = {&f.srt_xyzi, &f.srt_src, &f.srt_line, &f.chunk_tab, &f.chunk_hist, &f.line_start, &f.line_count,
+                        &f.curv, &f.refl, &f.attr, &f.sort_ind, &f.refl_ind};
+    for (auto* x : b) x->release();
+    f.pin_small.release();
+  }
+  o->state.release();
+  o->out.release();
+  o->host.release();
+  delete o;
+  c->odom = nullptr;
+}
+
 extern "C" {
 
 // Run the odometry loop over n_scans scans. xyzi/line/s are arrays of per-scan pointers (device pointers when
@@ -384,8 +462,9 @@ int mml_odom_run(mml_ctx* c, const void* const* xyzi, const void* const* line, c
   MML_CUDA(c, c->pin_flags.reserve(64));
   c->has_perm[0] = c->has_perm[1] = false;
   MML_CUDA(c, cudaStreamSynchronize(st));
-  MML_CUDA(c, cudaStreamSynchronize(c->stream_fe));
-  o->slot[0].used = o->slot[1].used = false;
+  for (int k = 0; k < kLanes; k++) MML_CUDA(c, cudaStreamSynchronize(o->lane[k]));
+  MML_CUDA(c, cudaStreamSynchronize(o->copy));
+  for (int k = 0; k < kSlots; k++) o->slot[k].used = false;
   if (total_ms) MML_CUDA(c, cudaEventRecord(c->ev0, st));
   RunArgs R = {xyzi, line, s, n_pts, n_scans, n_lines, host_buffers, exTlb16, leaf_corner, leaf_surf, prm, poses_out, counts_out};
   const bool classic = getenv("MML_ODOM_CLASSIC") && atoi(getenv("MML_ODOM_CLASSIC")) != 0;
@@ -395,7 +474,7 @@ int mml_odom_run(mml_ctx* c, const void* const* xyzi, const void* const* line, c
     // classic driver from the first scan the chained one could not finish, seeded with the poses before it
     const double* Ti = first >= 1 ? poses_out + 16 * (size_t)(first - 1) : T_init16;
     const double* Tp = first >= 2 ? poses_out + 16 * (size_t)(first - 2) : (first == 1 ? T_init16 : T_prev16);
-    o->slot[0].used = o->slot[1].used = false;
+    for (int k = 0; k < kSlots; k++) o->slot[k].used = false;
     MML_CHECK(run_classic(c, o, R, first, Ti, Tp));
   }
   if (total_ms) {

@@ -723,6 +723,13 @@ __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
             }
           }
         }
+#ifdef MML_TIMELINE
+        if (A.tl && lg == 0) {
+          unsigned* dbg = reinterpret_cast<unsigned*>(A.tl + 16 + 8 * 4000) + 32768 * 3;
+          const int sl = (KIND ? 16384 : 0) + (slot_i < 16384 ? slot_i : 16383);
+          dbg[sl] = (unsigned)(clock64() - qc0);  // up to and including the fit
+        }
+#endif
         found = __shfl_sync(mask, ok, 0, G);
       }
     }

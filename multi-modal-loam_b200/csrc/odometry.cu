@@ -306,7 +306,7 @@ static int run_chained(mml_ctx* c, Odom* o, const RunArgs& R, const double* T_in
   mml::EstState* S = nullptr;
   MML_CHECK(mml_chain_prepare(c, cap, &S));
 #ifdef MML_TIMELINE
-  MML_CUDA(c, c->timeline.reserve(8 * (16 + 8 * 4000) + 4 * 32768 * 3));
+  MML_CUDA(c, c->timeline.reserve(8 * (16 + 8 * 4000) + 4 * 32768 * 4));
   MML_CUDA(c, cudaMemsetAsync(c->timeline.p, 0, 8 * 16, st));
 #endif
   const size_t out_doubles = (size_t)n_scans * 24, out_ints = (size_t)n_scans * 8;
@@ -380,8 +380,18 @@ static int run_chained(mml_ctx* c, Odom* o, const RunArgs& R, const double* T_in
       solve += (double)(t[7] - t[6]);
       m++;
     }
-    std::vector<unsigned> qc(32768 * 3);
-    cudaMemcpy(qc.data(), (char*)c->timeline.p + 8 * (16 + 8 * 4000), 4 * 32768 * 3, cudaMemcpyDeviceToHost);
+    std::vector<unsigned> qc(32768 * 4);
+    cudaMemcpy(qc.data(), (char*)c->timeline.p + 8 * (16 + 8 * 4000), 4 * 32768 * 4, cudaMemcpyDeviceToHost);
+    for (int kind = 0; kind < 2; kind++) {  // the five slowest queries: total = setup + search + fit + store
+      std::vector<std::pair<unsigned, int>> v;
+      for (int i = 0; i < 16384; i++) if (qc[kind * 16384 + i]) v.push_back({qc[kind * 16384 + i], i});
+      std::sort(v.begin(), v.end());
+      for (size_t j = v.size() > 5 ? v.size() - 5 : 0; j < v.size(); j++) {
+        const int i = kind * 16384 + v[j].second;
+        fprintf(stderr, "  kind %d slow query %d: total %u setup %u search %u through-fit %u\n", kind, v[j].second, qc[i], qc[32768 + i],
+                qc[65536 + i], qc[98304 + i]);
+      }
+    }
     for (int kind = 0; kind < 2; kind++) {
       double su = 0, se = 0; int nn = 0;
       for (int i = 0; i < 16384; i++) if (qc[65536 + kind * 16384 + i]) { su += qc[32768 + kind * 16384 + i]; se += qc[65536 + kind * 16384 + i]; nn++; }

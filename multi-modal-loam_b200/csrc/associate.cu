@@ -222,6 +222,105 @@ __device__ bool knn5_grid(const GridDev& G, float qx, float qy, float qz, float 
   return r.cnt == 5 && r.d[4] < thres;
 }
 
+// ---- thread-per-query search (map-sized query sets): packed keys + box pruning
+// The 5-list is kept as 64-bit keys (distance bits << 32 | original index): squared distances are >= +0, so their bit
+// patterns order like unsigned integers and one 64-bit compare implements "closer, ties to the lower index". The
+// insertion is branch-free (new_i = p_{i-1} ? old_{i-1} : p_i ? x : old_i with p_i = x < old_i).
+struct KnnP {
+  unsigned long long key[5];
+  int loc[5];
+};
+__device__ __forceinline__ void knnp_init(KnnP& r) {
+#pragma unroll
+  for (int k = 0; k < 5; k++) { r.key[k] = 0x7f800000ffffffffull; r.loc[k] = -1; }  // +inf distance
+}
+__device__ __forceinline__ void knnp_push(KnnP& r, float d, int id, int loc) {
+  const unsigned long long x = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)id;
+  if (x >= r.key[4]) return;
+  const bool p0 = x < r.key[0], p1 = x < r.key[1], p2 = x < r.key[2], p3 = x < r.key[3];
+  r.key[4] = p3 ? r.key[3] : x;            r.loc[4] = p3 ? r.loc[3] : loc;
+  r.key[3] = p2 ? r.key[2] : (p3 ? x : r.key[3]); r.loc[3] = p2 ? r.loc[2] : (p3 ? loc : r.loc[3]);
+  r.key[2] = p1 ? r.key[1] : (p2 ? x : r.key[2]); r.loc[2] = p1 ? r.loc[1] : (p2 ? loc : r.loc[2]);
+  r.key[1] = p0 ? r.key[0] : (p1 ? x : r.key[1]); r.loc[1] = p0 ? r.loc[0] : (p1 ? loc : r.loc[1]);
+  r.key[0] = p0 ? x : r.key[0];            r.loc[0] = p0 ? loc : r.loc[0];
+}
+__device__ __forceinline__ float knnp_d(const KnnP& r, int k) { return __uint_as_float((unsigned)(r.key[k] >> 32)); }
+
+__device__ __forceinline__ void scan_range_p(const GridDev& G, int c0, int c1, float qx, float qy, float qz, KnnP& r) {
+  const int s = __ldg(G.cell_start + c0), e = __ldg(G.cell_start + c1 + 1);
+  for (int k = s; k < e; k++) {
+    const float4 p = __ldg(G.pts + k);
+    const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+    const float d = (dx * dx + dy * dy) + dz * dz;
+    knnp_push(r, d, __float_as_int(p.w), k);
+  }
+}
+
+// distance (in cells, conservative) from a point at fraction f of its cell to the cell at offset o along one axis
+__device__ __forceinline__ float axis_gap(float f, int o) {
+  const float g = o > 0 ? (float)o - f : (o < 0 ? f - (float)(o + 1) : 0.f);
+  return fmaxf(g - 1e-3f, 0.f);
+}
+
+// exact 5-NN within squared radius `thres` (same result as knn5_grid). Rows of cells are visited nearest first
+// inside each shell and a row (or end cell) is skipped when its box lies farther than the current 5th neighbour.
+__device__ bool knn5_grid_packed(const GridDev& G, float qx, float qy, float qz, float thres, KnnP& r) {
+  knnp_init(r);
+  int c[3], lo[3], hi[3], cube;
+  if (!locate(G, qx, qy, qz, c, lo, hi, cube)) return false;
+  if (G.global) {
+    if (!(__ldg(G.cube_count + cube) > G.min_cube_pts)) return false;
+  } else {
+    if (!(G.m > G.min_local_pts)) return false;
+  }
+  const float cellf = G.cell;
+  const float cell2 = cellf * cellf;
+  // position of the query inside its (possibly clamped) cell, in cells
+  const float fx = (float)(((double)qx - G.org[0]) * G.inv_cell - (double)c[0]);
+  const float fy = (float)(((double)qy - G.org[1]) * G.inv_cell - (double)c[1]);
+  const float fz = (float)(((double)qz - G.org[2]) * G.inv_cell - (double)c[2]);
+  const int rmax = (int)ceilf(sqrtf(thres) / cellf) + 1;
+  for (int rr = 1; rr <= rmax; rr++) {
+    // ring order: |dz| + |dy| ascending puts the nearest rows first, so the bound tightens before the far rows are tested
+    for (int sum = 0; sum <= 2 * rr; sum++) {
+      for (int adz = 0; adz <= min(sum, rr); adz++) {
+        const int ady = sum - adz;
+        if (ady > rr) continue;
+        for (int sz = (adz ? -1 : 1); sz <= 1; sz += 2) {
+          for (int sy = (ady ? -1 : 1); sy <= 1; sy += 2) {
+            const int dz = sz * adz, dy = sy * ady;
+            const int z = c[2] + dz, y = c[1] + dy;
+            if (z < lo[2] || z > hi[2] || y < lo[1] || y > hi[1]) continue;
+            const float gy = axis_gap(fy, dy), gz = axis_gap(fz, dz);
+            const float row2 = (gy * gy + gz * gz) * cell2;
+            const float bound = knnp_d(r, 4);  // +inf until five candidates have been seen
+            if (row2 > bound) continue;
+            const int row = (z * G.dim[1] + y) * G.dim[0];
+            const bool full = (rr == 1) || adz == rr || ady == rr;
+            if (full) {
+              const int x0 = max(c[0] - rr, lo[0]), x1 = min(c[0] + rr, hi[0]);
+              if (x0 <= x1) scan_range_p(G, row + x0, row + x1, qx, qy, qz, r);
+            } else {
+              const int xa = c[0] - rr, xb = c[0] + rr;
+              const float ga = axis_gap(fx, -rr), gb = axis_gap(fx, rr);
+              if (xa >= lo[0] && row2 + ga * ga * cell2 <= bound) scan_range_p(G, row + xa, row + xa, qx, qy, qz, r);
+              if (xb <= hi[0] && row2 + gb * gb * cell2 <= knnp_d(r, 4)) scan_range_p(G, row + xb, row + xb, qx, qy, qz, r);
+            }
+          }
+        }
+      }
+    }
+    if (c[0] - rr < lo[0] && c[0] + rr > hi[0] && c[1] - rr < lo[1] && c[1] + rr > hi[1] && c[2] - rr < lo[2] &&
+        c[2] + rr > hi[2])
+      break;
+    const float reach = fmaxf((float)rr * cellf - 1e-3f, 0.f);
+    const float reach2 = reach * reach;
+    if (r.loc[4] >= 0 && knnp_d(r, 4) <= reach2) break;
+    if (reach2 >= thres) break;
+  }
+  return r.loc[4] >= 0 && knnp_d(r, 4) < thres;
+}
+
 // ---------------------------------------------------------------- features
 // compact feature record: 3 x float4 per query slot
 //   line : f0 = (p.xyz, valid) f1 = (a.xyz, b.x) f2 = (b.y, b.z, 0, 0)
@@ -253,7 +352,8 @@ struct AssocArgs {
   int tl_slot;
 };
 
-__device__ bool fit_line(const float4* pts, const Knn5& r, float* a, float* b) {
+template <class KnnT>
+__device__ bool fit_line(const float4* pts, const KnnT& r, float* a, float* b) {
   float px[5], py[5], pz[5];
 #pragma unroll
   for (int j = 0; j < 5; j++) {
@@ -282,7 +382,8 @@ __device__ bool fit_line(const float4* pts, const Knn5& r, float* a, float* b) {
   return true;
 }
 
-__device__ bool fit_plane(const float4* pts, const Knn5& r, float sx, float sy, float sz, float* nrm, float* dist_out) {
+template <class KnnT>
+__device__ bool fit_plane(const float4* pts, const KnnT& r, float sx, float sy, float sz, float* nrm, float* dist_out) {
   double A[5][3], bb[5];
   float px[5], py[5], pz[5];
 #pragma unroll
@@ -335,11 +436,11 @@ __global__ void __launch_bounds__(128) k_associate(AssocArgs A) {
     const bool in_grid = cube_of(sel[0], sel[1], sel[2], A.G[0].cen, cI, cJ, cK);
     const bool finite = !(isnan(sel[0]) || isnan(sel[1]) || isnan(sel[2]));
     if (in_grid && finite) {
-      Knn5 r;
+      KnnP r;
       for (int mp = 0; mp < 2 && !found; mp++) {
         const GridDev& G = A.G[mp];
         if (!G.valid) continue;
-        if (!knn5_grid(G, sel[0], sel[1], sel[2], thres, r)) continue;
+        if (!knn5_grid_packed(G, sel[0], sel[1], sel[2], thres, r)) continue;
         if (KIND == 0) {
           float a[3], b[3];
           if (!fit_line(G.pts, r, a, b)) continue;

@@ -323,9 +323,19 @@ static int read_assoc_stats(mml_ctx* c, int* n_line, int* n_plane, double* momen
 int mml_frame_associate_async(mml_ctx* c, const double* T_wl16, double thres_dist, int repeat) {
   if (!c || !T_wl16) return MML_ERR_INVALID;
   cudaSetDevice(c->device);
+  // line || plane like the reference's two association threads (EST.cpp:1265-1299): the plane kind runs on the
+  // context's second stream, forked from and joined back into the main one
+  cudaStream_t st = c->stream, st2 = c->stream2;
   for (int r = 0; r < repeat; r++) {
+    MML_CUDA(c, cudaEventRecord(c->ev_fork, st));
+    MML_CUDA(c, cudaStreamWaitEvent(st2, c->ev_fork, 0));
+    c->stream = st2;
+    const int rc1 = mml_associate_launch(c, 1, T_wl16, (float)thres_dist, nullptr, nullptr, nullptr, nullptr, c->n_surf);
+    c->stream = st;
+    MML_CHECK(rc1);
     MML_CHECK(mml_associate_launch(c, 0, T_wl16, (float)thres_dist, nullptr, nullptr, nullptr, nullptr, c->n_corner));
-    MML_CHECK(mml_associate_launch(c, 1, T_wl16, (float)thres_dist, nullptr, nullptr, nullptr, nullptr, c->n_surf));
+    MML_CUDA(c, cudaEventRecord(c->ev_join, st2));
+    MML_CUDA(c, cudaStreamWaitEvent(st, c->ev_join, 0));
   }
   return MML_OK;
 }

@@ -73,25 +73,38 @@ __host__ __device__ inline void eig3_sym(const double* Ain, double* ev, double* 
   }
 }
 
-// least-squares solution of A x = b (5x3), Householder QR with column pivoting
+// least-squares solution of A x = b (5x3), Householder QR with column pivoting.
+// Every loop is unrolled over compile-time indices and the column pivoting is done with conditional swaps, so the
+// 5x3 matrix lives in registers (a run-time column index would put it in local memory); the arithmetic and its order
+// are those of the plain triple loop.
 __host__ __device__ inline void qr5x3_solve(double A[5][3], double b[5], double x[3]) {
-  int perm[3] = {0, 1, 2};
+  int perm0 = 0, perm1 = 1, perm2 = 2;
   double rdiag[3];
   double maxpivot = 0.0;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     int best = k;
     double bestn = -1.0;
+#pragma unroll
     for (int j = k; j < 3; j++) {
       double s = 0.0;
+#pragma unroll
       for (int i = k; i < 5; i++) s += A[i][j] * A[i][j];
       if (s > bestn) { bestn = s; best = j; }
     }
-    if (best != k) {
-      for (int i = 0; i < 5; i++) { const double t = A[i][k]; A[i][k] = A[i][best]; A[i][best] = t; }
-      const int t = perm[k]; perm[k] = perm[best]; perm[best] = t;
+#pragma unroll
+    for (int j = k + 1; j < 3; j++) {
+      if (best == j) {
+#pragma unroll
+        for (int i = 0; i < 5; i++) { const double t = A[i][k]; A[i][k] = A[i][j]; A[i][j] = t; }
+        // perm[k] <-> perm[j]
+        int& pk = k == 0 ? perm0 : (k == 1 ? perm1 : perm2);
+        int& pj = j == 1 ? perm1 : perm2;
+        const int t = pk; pk = pj; pj = t;
+      }
     }
     double tail = 0.0;
+#pragma unroll
     for (int i = k + 1; i < 5; i++) tail += A[i][k] * A[i][k];
     const double c0 = A[k][k];
     double beta, tau;
@@ -102,20 +115,26 @@ __host__ __device__ inline void qr5x3_solve(double A[5][3], double b[5], double 
     } else {
       beta = sqrt(c0 * c0 + tail);
       if (c0 >= 0) beta = -beta;
+#pragma unroll
       for (int i = k + 1; i < 5; i++) v[i] = A[i][k] / (c0 - beta);
       tau = (beta - c0) / beta;
     }
     v[k] = 1.0;
     if (tau != 0.0) {
+#pragma unroll
       for (int j = k + 1; j < 3; j++) {
         double s = 0.0;
+#pragma unroll
         for (int i = k; i < 5; i++) s += v[i] * A[i][j];
         s *= tau;
+#pragma unroll
         for (int i = k; i < 5; i++) A[i][j] -= s * v[i];
       }
       double s = 0.0;
+#pragma unroll
       for (int i = k; i < 5; i++) s += v[i] * b[i];
       s *= tau;
+#pragma unroll
       for (int i = k; i < 5; i++) b[i] -= s * v[i];
     }
     A[k][k] = beta;
@@ -124,16 +143,24 @@ __host__ __device__ inline void qr5x3_solve(double A[5][3], double b[5], double 
   }
   const double thr = 2.220446049250313e-16 * 3.0 * maxpivot;
   int rank = 0;
+#pragma unroll
   for (int k = 0; k < 3; k++)
     if (fabs(rdiag[k]) > thr) rank++;
   double y[3] = {0, 0, 0};
-  for (int k = rank - 1; k >= 0; k--) {
-    double s = b[k];
-    for (int j = k + 1; j < rank; j++) s -= A[k][j] * y[j];
-    y[k] = s / A[k][k];
+#pragma unroll
+  for (int k = 2; k >= 0; k--) {
+    if (k < rank) {
+      double s = b[k];
+#pragma unroll
+      for (int j = k + 1; j < 3; j++)
+        if (j < rank) s -= A[k][j] * y[j];
+      y[k] = s / A[k][k];
+    }
   }
-  x[0] = x[1] = x[2] = 0.0;
-  for (int k = 0; k < 3; k++) x[perm[k]] = (k < rank) ? y[k] : 0.0;
+  const double y0 = rank > 0 ? y[0] : 0.0, y1 = rank > 1 ? y[1] : 0.0, y2 = rank > 2 ? y[2] : 0.0;
+  x[0] = perm0 == 0 ? y0 : (perm1 == 0 ? y1 : y2);
+  x[1] = perm0 == 1 ? y0 : (perm1 == 1 ? y1 : y2);
+  x[2] = perm0 == 2 ? y0 : (perm1 == 2 ? y1 : y2);
 }
 
 struct Quat { double w, x, y, z; };

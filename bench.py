@@ -277,7 +277,8 @@ def main():
     config = {"workload": workload, "points_per_scan": 28800 + a.livox_pts, "window": 1,
               "l2": f"inputs larger than L2: {a.steps} distinct scans ({a.steps * scan_mb:.0f} MB) streamed once through the "
                     "timed region; the 1.7 MB feature map is reused by design (resident map)",
-              "pipeline": "extraction of scan k+1 overlaps the matching of scan k (the reference's two-node pipeline)",
+              "pipeline": "chained device-side loop: copy of scan k+3 | labelling of scans k+1, k+2 | matching of scan k "
+                          "(the reference's two-node pipeline); pose prediction on the device, no host wait per scan",
               "seed": 1003}
 
     if a.impl == "reference":
@@ -435,12 +436,19 @@ def main():
     x6 = np.concatenate([T1[:3, 3], synth.R_to_rotvec(T1[:3, :3])])
     ctx.frame_set(corner, surf)
     ms_assoc = time_kernels(lambda r: ctx.frame_associate_async(T1, 1.0, r), 50)
+    ms_assoc_plane = time_kernels(lambda r: ctx.frame_associate_kind_async(1, T1, 25.0, r), 50)
+    ms_assoc_line = time_kernels(lambda r: ctx.frame_associate_kind_async(0, T1, 25.0, r), 50)
     ms_acc = time_kernels(lambda r: ctx.frame_accumulate_async(x6, np.eye(4), repeat=r), 200)
     nq = corner.shape[0] + surf.shape[0]
     roof["s3_associate"] = {"queries": nq, "ms": ms_assoc, "gbs": nq * BYTES_PER_QUERY_ASSOC / ms_assoc / 1e6,
-                            "note": "latency-bound at one-scan size"}
+                            "note": "line || plane on two streams, thres_dist 1; latency-bound at one-scan size"}
+    roof["s3_associate_plane"] = {"queries": int(surf.shape[0]), "ms": ms_assoc_plane, "thres_dist": 25.0,
+                                  "gbs": surf.shape[0] * BYTES_PER_QUERY_ASSOC / ms_assoc_plane / 1e6}
+    roof["s3_associate_line"] = {"queries": int(corner.shape[0]), "ms": ms_assoc_line, "thres_dist": 25.0,
+                                 "gbs": corner.shape[0] * BYTES_PER_QUERY_ASSOC / ms_assoc_line / 1e6}
     roof["s3_accumulate"] = {"features": nq, "ms": ms_acc, "gbs": nq * BYTES_PER_FEATURE_EVAL / ms_acc / 1e6,
-                             "note": "latency-bound at one-scan size"}
+                             "note": "one evaluation as its own launch (k_accumulate); the loop runs all evaluations of an "
+                                     "outer iteration inside one k_solve_frame launch"}
 
     # batched extraction (SURVEY §8 d: >= 256 scans per launch), device resident, kernels only
     nb = 256
@@ -499,13 +507,18 @@ def main():
                                 "accumulate_frac": nq4 * BYTES_PER_FEATURE_EVAL / ms_ac / 1e6 / peak})
         ctx4.close()
 
-    # the kernel that dominates the step: the estimate stage = associate + accumulate launches
-    dom_ms = ms_acc
-    achieved = nq * BYTES_PER_FEATURE_EVAL / dom_ms / 1e6
-    roofline = {"bound": "hbm", "kernel": "k_accumulate (residual+Jacobian+J^T J, one launch per dogleg iteration)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": nq * BYTES_PER_FEATURE_EVAL,
-                "launch_ms": dom_ms, "note": "one-scan working set (~0.1 MB): launch-latency-bound; see s4 for the HBM-sized sweep",
+    # the kernel with the largest share of the step in the ncu launch list (profiles/): the plane association
+    # (5-NN search in the spatial hash + plane fit + feature write), timed alone on the context's stream at the
+    # loop's first-iteration threshold
+    dom_ms = ms_assoc_plane
+    dom_bytes = int(surf.shape[0]) * BYTES_PER_QUERY_ASSOC
+    achieved = dom_bytes / dom_ms / 1e6
+    roofline = {"bound": "hbm", "kernel": "k_associate_g<1,32> (plane association: hash-grid 5-NN + plane fit, one warp per query)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": 1322752,  # dram read + write per launch, ncu --set full (profiles/r1g_ncu_full_summary.txt)
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
+                "note": "one-scan working set (~1.1 k queries, 0.1 MB): a dependent chain of memory round trips and float64 "
+                        "fits, not bandwidth; the HBM-sized sweep is in s4 (there the kernels are issue / FP64-pipe bound)",
                 "stage_ms_per_scan": {"extract": stage_ms[0], "undistort_split_voxel": stage_ms[1], "estimate": stage_ms[2]},
                 "per_scan_avg": {"outer_iters": float(np.mean([i[0] for i in iters])), "dogleg_iters": float(np.mean([i[1] for i in iters])),
                                  "corner_queries": float(np.mean([i[2] for i in iters])), "surf_queries": float(np.mean([i[3] for i in iters]))},

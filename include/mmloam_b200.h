@@ -176,6 +176,8 @@ int mml_profile_read(mml_ctx* ctx, double* stage_ms3, long long* n_scans);
 int mml_frame_associate_async(mml_ctx* ctx, const double* T_wl16, double thres_dist, int repeat);
 int mml_frame_accumulate_async(mml_ctx* ctx, const double* x6, const double* T_bl16, double plan_weight_tan,
                                double huber_a, int repeat);
+/* one association kind only (0 line / 1 plane): times a single kernel                  */
+int mml_frame_associate_kind_async(mml_ctx* ctx, int kind, const double* T_wl16, double thres_dist, int repeat);
 /* CUDA-event timing on the context's stream (bench.py cannot see it from torch).       */
 int mml_timer_start(mml_ctx* ctx);
 int mml_timer_stop_ms(mml_ctx* ctx, float* ms);

@@ -257,6 +257,11 @@ class Context:
         T = _f64(T_wl).reshape(16)
         self._ck(self.lib.mml_frame_associate_async(self.h, _p(T), C.c_double(thres), int(repeat)))
 
+    def frame_associate_kind_async(self, kind, T_wl, thres, repeat=1):
+        """one association kernel only (0 line / 1 plane): used to time a single kernel"""
+        T = _f64(T_wl).reshape(16)
+        self._ck(self.lib.mml_frame_associate_kind_async(self.h, int(kind), _p(T), C.c_double(thres), int(repeat)))
+
     def frame_accumulate_async(self, x6, T_bl, plan_weight_tan=0.0, huber_a=0.1 / 1.5e-3, repeat=1):
         x6 = _f64(x6)
         T = _f64(T_bl).reshape(16)

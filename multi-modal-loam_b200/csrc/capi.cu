@@ -340,6 +340,15 @@ int mml_frame_associate_async(mml_ctx* c, const double* T_wl16, double thres_dis
   return MML_OK;
 }
 
+// one kind only (0 line / 1 plane), for timing a single association kernel
+int mml_frame_associate_kind_async(mml_ctx* c, int kind, const double* T_wl16, double thres_dist, int repeat) {
+  if (!c || !T_wl16 || kind < 0 || kind > 1) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  for (int r = 0; r < repeat; r++)
+    MML_CHECK(mml_associate_launch(c, kind, T_wl16, (float)thres_dist, nullptr, nullptr, nullptr, nullptr, kind ? c->n_surf : c->n_corner));
+  return MML_OK;
+}
+
 int mml_frame_associate(mml_ctx* c, const double* T_wl16, double thres_dist, int* n_line, int* n_plane,
                         double* normal_moment9, int* n_normals) {
   MML_CHECK(mml_frame_associate_async(c, T_wl16, thres_dist, 1));

@@ -683,6 +683,9 @@ __device__ __forceinline__ void make_pose_split(const double* x6, const double* 
   }
 }
 
+// CHAIN: the chained odometry loop's instance (publishes the pose, drives the WHILE node). The per-scan API uses the
+// plain instance, which contains no device-side graph call and therefore stays visible to profilers.
+template <bool CHAIN>
 __global__ void __launch_bounds__(kSolveThreads, 1) k_solve_frame(SolveArgs A) {
   if (A.st->done_outer) return;  // uniform over the cluster
   if (blockIdx.x == 0 && threadIdx.x == 0) MML_TL(A.tl, 6);
@@ -778,7 +781,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve_frame(SolveArgs A) {
   if (tid == 0) {
     est_end(&S, A.assoc_stats);
     if (!S.done_outer) est_begin_assoc(&S);
-    if (A.od) {
+    if (CHAIN) {
       if (S.done_outer) chain_publish(A, S);
       cudaGraphSetConditional(A.cond, S.done_outer ? 0u : 1u);
     }
@@ -906,8 +909,11 @@ static int launch_solve_frame(mml_ctx* ctx, EstState* S, const int* cnt_dev, Odo
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  if (kSolveCluster > 8) cudaFuncSetAttribute(k_solve_frame, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  const bool ok = cudaLaunchKernelEx(&cfg, k_solve_frame, SA) == cudaSuccess;
+  if (kSolveCluster > 8) {
+    cudaFuncSetAttribute(k_solve_frame<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(k_solve_frame<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  }
+  const bool ok = (od ? cudaLaunchKernelEx(&cfg, k_solve_frame<true>, SA) : cudaLaunchKernelEx(&cfg, k_solve_frame<false>, SA)) == cudaSuccess;
   MML_LAUNCHED(ctx);
   return ok ? MML_OK : MML_ERR_CUDA;
 }

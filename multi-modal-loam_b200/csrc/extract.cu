@@ -175,11 +175,30 @@ __global__ void __launch_bounds__(256) k_point_attr(const float4* __restrict__ P
     // ---- FE.cpp:407-451
     const float dis = range3(pi);
     const V3d cur = {(double)pi.x, (double)pi.y, (double)pi.z};
-    const V3d dl = vsub(pm1, pi), dn = vsub(pp1, pi);
-    const double ncur = vnorm(cur);
-    const double angle_last = vdot(dl, cur) / (vnorm(dl) * ncur);
-    const double angle_next = vdot(dn, cur) / (vnorm(dn) * ncur);
-    const bool graze = fabs(angle_last) > 0.966 && fabs(angle_next) > 0.966;
+    // The reference evaluates the two grazing-angle cosines in float64 (Eigen Vector3d). A float32 evaluation is
+    // within ~1e-6 of it, so it decides every case farther than 1e-4 from the 0.966 threshold; only the (rare)
+    // borderline cases - and NaNs, for which every comparison below is false - pay for the float64 form. The
+    // decision is the reference's bit for bit, the FP64 pipe is no longer what bounds this kernel.
+    bool graze;
+    {
+      const float ax = pm1.x - pi.x, ay = pm1.y - pi.y, az = pm1.z - pi.z;
+      const float bx = pp1.x - pi.x, by = pp1.y - pi.y, bz = pp1.z - pi.z;
+      const float nc = sqrtf(pi.x * pi.x + pi.y * pi.y + pi.z * pi.z);
+      const float al = fabsf((ax * pi.x + ay * pi.y + az * pi.z) / (sqrtf(ax * ax + ay * ay + az * az) * nc));
+      const float an = fabsf((bx * pi.x + by * pi.y + bz * pi.z) / (sqrtf(bx * bx + by * by + bz * bz) * nc));
+      const float kT = 0.966f, kM = 1e-4f;
+      if (al < kT - kM || an < kT - kM) {
+        graze = false;
+      } else if (al > kT + kM && an > kT + kM) {
+        graze = true;
+      } else {
+        const V3d dl = vsub(pm1, pi), dn = vsub(pp1, pi);
+        const double ncur = vnorm(cur);
+        const double angle_last = vdot(dl, cur) / (vnorm(dl) * ncur);
+        const double angle_next = vdot(dn, cur) / (vnorm(dn) * ncur);
+        graze = fabs(angle_last) > 0.966 && fabs(angle_next) > 0.966;
+      }
+    }
     const int w = (dis > 50.0f || graze) ? 2 : 3;
     if (graze) a |= A_ANGLE;
     if (w == 3) a |= A_W3;
@@ -212,7 +231,38 @@ __global__ void __launch_bounds__(256) k_point_attr(const float4* __restrict__ P
       float right_curv = rX * rX + rY * rY + rZ * rZ;
       const bool lf = left_curv < thF * dis, rf = right_curv < thF * dis;
       if (rf) a |= A_RF;
+      // same two-tier evaluation for the corner test (FE.cpp:571-650): float32 first, float64 only near a threshold
+      int c150 = -1;  // -1: undecided
       if (lf && rf) {
+        float nl[3] = {0.f, 0.f, 0.f}, nr[3] = {0.f, 0.f, 0.f};
+        const float4 L[4] = {pm1, pm2, pm3, pm4};
+        const float4 R[4] = {pp1, pp2, pp3, pp4};
+#pragma unroll
+        for (int k = 1; k < 5; k++) {
+          const float wk = (float)k / 10.0f;
+          {
+            const float tx = L[k - 1].x - pi.x, ty = L[k - 1].y - pi.y, tz = L[k - 1].z - pi.z;
+            const float inv = wk / sqrtf(tx * tx + ty * ty + tz * tz);
+            nl[0] += inv * tx; nl[1] += inv * ty; nl[2] += inv * tz;
+          }
+          {
+            const float tx = R[k - 1].x - pi.x, ty = R[k - 1].y - pi.y, tz = R[k - 1].z - pi.z;
+            const float inv = wk / sqrtf(tx * tx + ty * ty + tz * tz);
+            nr[0] += inv * tx; nr[1] += inv * ty; nr[2] += inv * tz;
+          }
+        }
+        const float nnl = sqrtf(nl[0] * nl[0] + nl[1] * nl[1] + nl[2] * nl[2]);
+        const float nnr = sqrtf(nr[0] * nr[0] + nr[1] * nr[1] + nr[2] * nr[2]);
+        const float cc = fabsf((nl[0] * nr[0] + nl[1] * nr[1] + nl[2] * nr[2]) / (nnl * nnr));
+        const float l4x = pm4.x - pi.x, l4y = pm4.y - pi.y, l4z = pm4.z - pi.z;
+        const float r4x = pp4.x - pi.x, r4y = pp4.y - pi.y, r4z = pp4.z - pi.z;
+        const float ld = sqrtf(l4x * l4x + l4y * l4y + l4z * l4z), cd = sqrtf(r4x * r4x + r4y * r4y + r4z * r4z);
+        const bool conditioned = nnl > 0.05f && nnr > 0.05f;  // cancelling direction sums: the ratio is ill-conditioned
+        if ((conditioned && cc > 0.5f + 1e-3f) || ld < 0.05f - 1e-5f || cd < 0.05f - 1e-5f) c150 = 0;
+        else if (conditioned && cc < 0.5f - 1e-3f && ld > 0.05f + 1e-5f && cd > 0.05f + 1e-5f) c150 = 1;
+      }
+      if (c150 == 1) a |= A_C150;
+      if (lf && rf && c150 < 0) {
         V3d nl = {0, 0, 0}, nr = {0, 0, 0};
         const float4 L[4] = {pm1, pm2, pm3, pm4};
         const float4 R[4] = {pp1, pp2, pp3, pp4};
@@ -247,14 +297,14 @@ __global__ void __launch_bounds__(256) k_point_attr(const float4* __restrict__ P
       if (fabsf(diff_right - diff_left) > 1.0f) {
         if (diff_right > diff_left) {
           V3d sv = vsub(pm1, pi);
-          double cc = fabs(vdot(sv, cur) / (vnorm(sv) * ncur));
+          double cc = fabs(vdot(sv, cur) / (vnorm(sv) * vnorm(cur)));
           if (cc < 0.95) {
             if (depth_right > depth_left) f100 = true;
             else if (depth_right == 0.f) f100 = true;
           }
         } else {
           V3d sv = vsub(pp1, pi);
-          double cc = fabs(vdot(sv, cur) / (vnorm(sv) * ncur));
+          double cc = fabs(vdot(sv, cur) / (vnorm(sv) * vnorm(cur)));
           if (cc < 0.95) {
             if (depth_right < depth_left) f100 = true;
             else if (depth_left == 0.f) f100 = true;

@@ -565,11 +565,10 @@ __host__ __device__ __noinline__ void dogleg_update(EstState& S, const double* o
 
 // ---------------------------------------------------------------- outer loop bookkeeping
 // EST.cpp:771-775 localizability, EST.cpp:1439-1450 convergence test
-__device__ inline void est_end(EstState* S, const double* assoc_stats) {
+// checkLocalizability (EST.cpp:536-565): smallest singular value of the stacked plane normals, from their 3x3
+// moment matrix (assoc_stats, written by the plane association); -1 when there are too few planes
+__device__ inline double localizability_sv(const double* assoc_stats) {
   const int* ints = reinterpret_cast<const int*>(assoc_stats + 16);
-  S->n_line = ints[0];
-  S->n_plane = ints[1];
-  // checkLocalizability (EST.cpp:536-565): singular values of stacked normals
   const double* mo = assoc_stats + 8;
   double sv = -1.0;
   if (ints[1] > 10) {
@@ -578,6 +577,15 @@ __device__ inline void est_end(EstState* S, const double* assoc_stats) {
     eig3_sym(M, ev, V);
     sv = sqrt(fmax(ev[0], 0.0));
   }
+  return sv;
+}
+
+// sv_pre: localizability value already evaluated by the plane association's last CTA (assoc_stats[15]), or null
+__device__ inline void est_end(EstState* S, const double* assoc_stats, const double* sv_pre = nullptr) {
+  const int* ints = reinterpret_cast<const int*>(assoc_stats + 16);
+  S->n_line = ints[0];
+  S->n_plane = ints[1];
+  const double sv = sv_pre ? *sv_pre : localizability_sv(assoc_stats);
   S->min_sv = sv;
   if (sv < 3.0) S->is_degenerate = 1;
   S->final_cost = S->min_cost;
@@ -779,7 +787,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve_frame(SolveArgs A) {
   cluster_sync_all();  // nobody reads CTA 0's shared memory any more
   if (rank != 0) return;
   if (tid == 0) {
-    est_end(&S, A.assoc_stats);
+    est_end(&S, A.assoc_stats, A.assoc_stats + 15);  // localizability value left by the plane association's last CTA
     if (!S.done_outer) est_begin_assoc(&S);
     if (CHAIN) {
       if (S.done_outer) chain_publish(A, S);

@@ -321,6 +321,21 @@ __device__ bool knn5_grid_packed(const GridDev& G, float qx, float qy, float qz,
   return r.loc[4] >= 0 && knnp_d(r, 4) < thres;
 }
 
+// checkLocalizability (EST.cpp:536-565) on the plane association's own statistics: the last CTA leaves the smallest
+// singular value of the stacked normals next to the moments (slot 7 of the plane block of assoc_stats), so the
+// solve does not spend its tail on a serial 3x3 eigen-solve. Called by one thread after the moments are final.
+__device__ inline void publish_localizability(double* moment_out /* [8]: 6 moments, count, value */) {
+  double sv = -1.0;
+  if ((int)moment_out[6] > 10) {
+    const double* mo = moment_out;
+    const double M[9] = {mo[0], mo[1], mo[2], mo[1], mo[3], mo[4], mo[2], mo[4], mo[5]};
+    double ev[3], V[9];
+    eig3_sym(M, ev, V);
+    sv = sqrt(fmax(ev[0], 0.0));
+  }
+  moment_out[7] = sv;
+}
+
 // ---------------------------------------------------------------- features
 // compact feature record: 3 x float4 per query slot
 //   line : f0 = (p.xyz, valid) f1 = (a.xyz, b.x) f2 = (b.y, b.z, 0, 0)
@@ -515,6 +530,8 @@ __global__ void __launch_bounds__(128) k_associate(AssocArgs A) {
       A.moment_out[threadIdx.x] = s;
       if (threadIdx.x == 6) *A.n_feat_out = (int)s;
     }
+    __syncwarp();
+    if (KIND == 1 && threadIdx.x == 0) publish_localizability(A.moment_out);
     if (threadIdx.x == 0) *A.ticket = 0;
   }
 }
@@ -872,6 +889,8 @@ __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
       A.moment_out[threadIdx.x] = s;
       if (threadIdx.x == 6) *A.n_feat_out = (int)s;
     }
+    __syncwarp();
+    if (KIND == 1 && threadIdx.x == 0) publish_localizability(A.moment_out);
     if (threadIdx.x == 0) *A.ticket = 0;
     if (threadIdx.x == 0) MML_TL(A.tl, A.tl_slot + 1);
   }
@@ -1081,6 +1100,8 @@ __global__ void __launch_bounds__(kTileQ) k_associate_tile(AssocArgs A) {
       A.moment_out[tid] = t;
       if (tid == 6) *A.n_feat_out = (int)t;
     }
+    __syncwarp();
+    if (KIND == 1 && tid == 0) publish_localizability(A.moment_out);
     if (tid == 0) *A.ticket = 0;
   }
 }

@@ -881,6 +881,12 @@ static long long est_graph_key(mml_ctx* ctx, EstState* S, const int* cnt_dev, in
 // line || plane association of the frame slot on two captured streams (fork / join around ctx->stream)
 static int capture_assoc_pair(mml_ctx* ctx, EstState* S, const int* cnt_dev, int cap_corner, int cap_surf) {
   cudaStream_t st = ctx->stream, st2 = ctx->stream2;
+  static const bool serial = getenv("MML_ASSOC_SERIAL") && atoi(getenv("MML_ASSOC_SERIAL")) != 0;  // experiment
+  if (serial) {
+    int rc = mml_associate_launch(ctx, 1, nullptr, 0.f, S->T_wl, &S->thres, &S->done_outer, cnt_dev + 1, cap_surf);
+    if (rc == MML_OK) rc = mml_associate_launch(ctx, 0, nullptr, 0.f, S->T_wl, &S->thres, &S->done_outer, cnt_dev, cap_corner);
+    return rc;
+  }
   cudaEventRecord(ctx->ev_fork, st);
   cudaStreamWaitEvent(st2, ctx->ev_fork, 0);
   ctx->stream = st2;
@@ -1057,12 +1063,13 @@ int mml_chain_prepare(mml_ctx* ctx, int cap, mml::EstState** S_out) {
 
 mml::EstInit mml_make_est_init(const double* exTlb16, const mml_est_params* prm) { return make_est_init(exTlb16, prm); }
 
-int mml_chain_solve_launch(mml_ctx* ctx, const int* cnt_dev, int cap, mml::OdomDev* od, mml::ChainOut out) {
+int mml_chain_solve_launch(mml_ctx* ctx, const int* cnt_dev, int cap, mml::OdomDev* od, mml::ChainOut out, cudaEvent_t wait_ev) {
   cudaStream_t st = ctx->stream;
   EstState* S = ctx->est_state.as<EstState>();
   long long key = est_graph_key(ctx, S, cnt_dev, cap, cap, 0, 0);
   auto mix = [&](long long v) { key = (key ^ v) * 1099511628211ll; };
   mix((long long)(size_t)od); mix((long long)(size_t)out.poses); mix((long long)(size_t)out.stats); mix((long long)(size_t)out.counts);
+  mix((long long)(size_t)wait_ev);
   if (!ctx->chain_graph || ctx->chain_graph_key != key) {
     if (ctx->chain_graph) { cudaGraphExecDestroy(ctx->chain_graph); ctx->chain_graph = nullptr; }
     const long long launches_before = ctx->launches;
@@ -1074,8 +1081,15 @@ int mml_chain_solve_launch(mml_ctx* ctx, const int* cnt_dev, int cap, mml::OdomD
     np.conditional.handle = cond;
     np.conditional.type = cudaGraphCondTypeWhile;
     np.conditional.size = 1;
-    cudaGraphNode_t node;
-    MML_CUDA(ctx, cudaGraphAddNode(&node, graph, nullptr, 0, &np));
+    // wait_ev (optional): the scan's split / voxel launch runs on its own stream; waiting for it INSIDE the graph lets
+    // the launch latency of the graph (front-end set-up of the WHILE node) overlap that kernel instead of following it
+    cudaGraphNode_t node, wait_node;
+    if (wait_ev) {
+      MML_CUDA(ctx, cudaGraphAddEventWaitNode(&wait_node, graph, nullptr, 0, wait_ev));
+      MML_CUDA(ctx, cudaGraphAddNode(&node, graph, &wait_node, 1, &np));
+    } else {
+      MML_CUDA(ctx, cudaGraphAddNode(&node, graph, nullptr, 0, &np));
+    }
     cudaGraph_t body = np.conditional.phGraph_out[0];
     MML_CUDA(ctx, cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
     int rc = capture_assoc_pair(ctx, S, cnt_dev, cap, cap);

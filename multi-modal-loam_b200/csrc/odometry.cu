@@ -34,7 +34,7 @@ int mml_split_voxel_device(mml_ctx* ctx, const float4* pts_d, const float* s_d, 
 int mml_label_compact_device(mml_ctx* ctx, const uint8_t* label_d, int n, int* idx0, int* idx1, int* cnt_d);
 int mml_chain_prepare(mml_ctx* ctx, int cap, mml::EstState** S_out);
 mml::EstInit mml_make_est_init(const double* exTlb16, const mml_est_params* prm);
-int mml_chain_solve_launch(mml_ctx* ctx, const int* cnt_dev, int cap, mml::OdomDev* od, mml::ChainOut out);
+int mml_chain_solve_launch(mml_ctx* ctx, const int* cnt_dev, int cap, mml::OdomDev* od, mml::ChainOut out, cudaEvent_t wait_ev);
 
 namespace {
 
@@ -74,6 +74,9 @@ struct Odom {
   Slot slot[kSlots];
   cudaStream_t lane[kLanes] = {nullptr, nullptr};  // lane[0] == ctx->stream_fe
   cudaStream_t copy = nullptr;
+  cudaStream_t sv = nullptr;        // chained loop: the split / voxel launch of scan k (beside the graph launch of scan k)
+  cudaEvent_t sv_done = nullptr;    // ... finished (waited for inside the scan's graph)
+  cudaEvent_t scan_done = nullptr;  // the solve of the previous scan has finished (matcher stream)
   FeScratch scratch[kLanes];  // scratch[0] stays empty: lane 0 works in the context's own buffers
   mml::DevBuf state;  // OdomDev
   mml::DevBuf out;    // ChainOut arrays
@@ -94,6 +97,9 @@ Odom* get_odom(mml_ctx* c) {
     o->lane[0] = c->stream_fe;
     for (int k = 1; k < kLanes; k++) cudaStreamCreateWithPriority(&o->lane[k], cudaStreamNonBlocking, prio_lo);
     cudaStreamCreateWithPriority(&o->copy, cudaStreamNonBlocking, prio_lo);
+    cudaStreamCreateWithPriority(&o->sv, cudaStreamNonBlocking, prio_hi);
+    cudaEventCreateWithFlags(&o->sv_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&o->scan_done, cudaEventDisableTiming);
     c->odom = o;
   }
   return static_cast<Odom*>(c->odom);
@@ -333,6 +339,7 @@ static int run_chained(mml_ctx* c, Odom* o, const RunArgs& R, const double* T_in
   ch.I = mml_make_est_init(R.exTlb16, R.prm);
   Trace tr;
   tr.init(n_scans);
+  MML_CUDA(c, cudaEventRecord(o->scan_done, st));  // the pose history upload above precedes the first split / voxel launch
   // pipeline depth: copies run three scans ahead of the matcher, labelling two (one scan per extraction lane)
   auto copy_of = [&](int k) { return submit_copy(c, o, k, R.xyzi[k], R.line[k], R.s ? R.s[k] : nullptr, R.n_pts[k], host, true); };
   auto extract_of = [&](int k) { return submit_extract(c, o, k, R.n_pts[k], n_lines, k % kLanes, true, &tr); };
@@ -341,19 +348,28 @@ static int run_chained(mml_ctx* c, Odom* o, const RunArgs& R, const double* T_in
   int* cnt = c->frame_cnt.as<int>();
   for (int k = 0; k < n_scans; k++) {
     Slot& SL = o->slot[k % kSlots];
-    MML_CUDA(c, cudaStreamWaitEvent(st, SL.done, 0));
-    tr.rec(k, 0, st);
+    // split / voxel of scan k on its own stream: after the labelling of scan k and the solve of scan k-1 ...
+    MML_CUDA(c, cudaStreamWaitEvent(o->sv, SL.done, 0));
+    MML_CUDA(c, cudaStreamWaitEvent(o->sv, o->scan_done, 0));
+    tr.rec(k, 0, o->sv);
     ch.fe_counters = SL.counters.as<int>();
     ch.counts_out = out.counts + 8 * (size_t)k;
     ch.pre_idx[0] = SL.idx.as<int>();
     ch.pre_idx[1] = SL.idx.as<int>() + cap;
     ch.pre_cnt = SL.idx.as<int>() + 2 * cap;
-    MML_CHECK(mml_split_voxel_device(c, (const float4*)SL.xd, (const float*)SL.sd, SL.label.as<uint8_t>(), R.n_pts[k],
-                                     nullptr, nullptr, R.leaf_corner, R.leaf_surf, c->q_corner.as<float4>(),
-                                     c->q_surf.as<float4>(), cnt, &ch));
-    MML_CUDA(c, cudaEventRecord(SL.consumed, st));
-    tr.rec(k, 1, st);
-    MML_CHECK(mml_chain_solve_launch(c, cnt, cap, od, out));
+    c->stream = o->sv;
+    const int rc_sv = mml_split_voxel_device(c, (const float4*)SL.xd, (const float*)SL.sd, SL.label.as<uint8_t>(), R.n_pts[k], nullptr,
+                                             nullptr, R.leaf_corner, R.leaf_surf, c->q_corner.as<float4>(), c->q_surf.as<float4>(),
+                                             cnt, &ch);
+    c->stream = st;
+    MML_CHECK(rc_sv);
+    MML_CUDA(c, cudaEventRecord(SL.consumed, o->sv));
+    MML_CUDA(c, cudaEventRecord(o->sv_done, o->sv));
+    tr.rec(k, 1, o->sv);
+    // ... and the scan's graph on the matcher stream: it waits for sv_done inside (event-wait node), so its launch
+    // latency overlaps the split / voxel kernel
+    MML_CHECK(mml_chain_solve_launch(c, cnt, cap, od, out, o->sv_done));
+    MML_CUDA(c, cudaEventRecord(o->scan_done, st));
     tr.rec(k, 2, st);
     if (k + 3 < n_scans) MML_CHECK(copy_of(k + 3));
     if (k + 2 < n_scans) MML_CHECK(extract_of(k + 2));
@@ -362,6 +378,7 @@ static int run_chained(mml_ctx* c, Odom* o, const RunArgs& R, const double* T_in
   MML_CUDA(c, cudaStreamSynchronize(st));
   for (int k = 0; k < kLanes; k++) MML_CUDA(c, cudaStreamSynchronize(o->lane[k]));
   MML_CUDA(c, cudaStreamSynchronize(o->copy));
+  MML_CUDA(c, cudaStreamSynchronize(o->sv));
   tr.report(n_scans);
 #ifdef MML_TIMELINE
   {  // device-side stamps of every kernel on the matcher's path (debug build only)
@@ -428,6 +445,9 @@ void mml_odom_destroy(mml_ctx* c) {
   for (int k = 0; k < kLanes; k++)
     if (o->lane[k]) { cudaStreamSynchronize(o->lane[k]); if (k > 0) cudaStreamDestroy(o->lane[k]); }
   if (o->copy) { cudaStreamSynchronize(o->copy); cudaStreamDestroy(o->copy); }
+  if (o->sv) { cudaStreamSynchronize(o->sv); cudaStreamDestroy(o->sv); }
+  if (o->sv_done) cudaEventDestroy(o->sv_done);
+  if (o->scan_done) cudaEventDestroy(o->scan_done);
   for (int k = 0; k < kSlots; k++) {
     Slot& S = o->slot[k];
     cudaEventDestroy(S.copied); cudaEventDestroy(S.done); cudaEventDestroy(S.consumed);

@@ -33,7 +33,8 @@ EXPORTS = [
     "mml_extract_features", "mml_extract_features_batch", "mml_velo_ring_time", "mml_hori_filter", "mml_undistort",
     "mml_voxel_downsample", "mml_map_set", "mml_associate", "mml_accumulate", "mml_est_params_default",
     "mml_estimate", "mml_scan_to_pose", "mml_scan_to_pose_dev", "mml_frame_set", "mml_frame_associate",
-    "mml_frame_accumulate", "mml_frame_associate_async", "mml_frame_accumulate_async", "mml_timer_start",
+    "mml_frame_accumulate", "mml_frame_associate_async", "mml_frame_associate_kind_async", "mml_frame_accumulate_async",
+    "mml_odom_run", "mml_timer_start",
     "mml_timer_stop_ms", "mml_frame_accumulate_partial_dev", "mml_stream_handle",
 ]
 

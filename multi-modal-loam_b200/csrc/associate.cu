@@ -324,7 +324,7 @@ __device__ bool knn5_grid_packed(const GridDev& G, float qx, float qy, float qz,
 // checkLocalizability (EST.cpp:536-565) on the plane association's own statistics: the last CTA leaves the smallest
 // singular value of the stacked normals next to the moments (slot 7 of the plane block of assoc_stats), so the
 // solve does not spend its tail on a serial 3x3 eigen-solve. Called by one thread after the moments are final.
-__device__ inline void publish_localizability(double* moment_out /* [8]: 6 moments, count, value */) {
+__device__ __noinline__ void publish_localizability(double* moment_out /* [8]: 6 moments, count, value */) {
   double sv = -1.0;
   if ((int)moment_out[6] > 10) {
     const double* mo = moment_out;
@@ -710,25 +710,29 @@ __device__ bool knn5_grid_group(const GridDev& Gd, float qx, float qy, float qz,
   } else {
     if (!(Gd.m > Gd.min_local_pts)) return false;
   }
-  GridLevel L0;
-  L0.pts = Gd.pts; L0.cell_start = Gd.cell_start; L0.cell = Gd.cell;
-  L0.dim[0] = Gd.dim[0]; L0.dim[1] = Gd.dim[1]; L0.dim[2] = Gd.dim[2];
   const int rmax = (int)ceilf(sqrtf(thres) / Gd.cell) + 1;
   const bool two_level = Gd.pts2 != nullptr && rmax > kFineShells;
-  bool done = search_shells<G>(L0, c, lo, hi, qx, qy, qz, thres, 1, two_level ? kFineShells : rmax, r, m, mask, lg, lst);
-  if (!done && two_level) {
-    GridLevel L1;
-    L1.pts = Gd.pts2; L1.cell_start = Gd.cell_start2; L1.cell = Gd.cell * (float)Gd.coarse;
-    int c2[3], lo2[3], hi2[3];
+  // one copy of the shell search in the instruction stream, run once per level (a query's warp executes this kernel
+  // exactly once, so every extra inlined copy is paid for in instruction fetch, ncu's `no_instruction` stall)
+#pragma unroll 1
+  for (int lvl = 0; lvl < 2; lvl++) {
+    GridLevel L;
+    int cc[3], llo[3], hhi[3];
+    const int f = lvl == 0 ? 1 : Gd.coarse;
+    L.pts = lvl == 0 ? Gd.pts : Gd.pts2;
+    L.cell_start = lvl == 0 ? Gd.cell_start : Gd.cell_start2;
+    L.cell = Gd.cell * (float)f;
+#pragma unroll
     for (int a = 0; a < 3; a++) {
-      L1.dim[a] = Gd.dim2[a];
-      c2[a] = c[a] / Gd.coarse; lo2[a] = lo[a] / Gd.coarse; hi2[a] = hi[a] / Gd.coarse;
+      L.dim[a] = lvl == 0 ? Gd.dim[a] : Gd.dim2[a];
+      cc[a] = c[a] / f; llo[a] = lo[a] / f; hhi[a] = hi[a] / f;
     }
+    const int last = lvl == 0 ? (two_level ? kFineShells : rmax) : (int)ceilf(sqrtf(thres) / L.cell) + 1;
+    const bool done = search_shells<G>(L, cc, llo, hhi, qx, qy, qz, thres, 1, last, r, m, mask, lg, lst);
+    base = L.pts;  // the 5-list indexes this level's sorted copy
+    if (done || !two_level) break;
     knn_init(r);
     knn_init(m);
-    const int rmax2 = (int)ceilf(sqrtf(thres) / L1.cell) + 1;
-    search_shells<G>(L1, c2, lo2, hi2, qx, qy, qz, thres, 1, rmax2, r, m, mask, lg, lst);
-    base = Gd.pts2;  // the 5-list now indexes the coarse-sorted copy
   }
   return m.cnt == 5 && m.d[4] < thres;
 }
@@ -781,6 +785,7 @@ __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
     const bool finite = !(isnan(sel[0]) || isnan(sel[1]) || isnan(sel[2]));
     if (in_grid && finite) {
       Knn5 r;
+#pragma unroll 1
       for (int mp = 0; mp < 2 && !found; mp++) {
         const GridDev& Gd = A.G[mp];
         if (!Gd.valid) continue;

@@ -375,6 +375,40 @@ def test_native_odometry_loop_matches_oracle(ctx, mm, orc, synth, scene):
     assert ms_d > 0 and (cnt_d[:, 2] > 20).all() and (cnt_d[:, 3] > 200).all()
 
 
+def test_odometry_loop_short_and_ragged_sequences(ctx, mm, synth, scene):
+    """Pipeline edge cases of mml_odom_run: fewer scans than the pipeline is deep (1, 2, 3) and scans of different
+    sizes (slot buffers and the extraction's chunk table change between scans). The chained driver must agree with
+    the host-driven one on every pose and count."""
+    import os
+    Ts = synth.trajectory(6, v=0.5, yaw_rate=0.2, dt=0.1)
+    sizes = [6000, 9000, 12000, 7000, 12000]
+    scans = []
+    for k in range(5):
+        vx, vr, vs = synth.vlp16_scan(Ts[k + 1], seed=500 + 2 * k, T_ws_start=Ts[k], n_az=900)
+        hx, hl, hs = synth.horizon_scan(Ts[k + 1], sizes[k], seed=501 + 2 * k, T_ws_start=Ts[k])
+        x = np.ascontiguousarray(np.concatenate([vx, hx]))
+        scans.append((x, np.ascontiguousarray(np.concatenate([vr, hl + 16]).astype(np.uint16)),
+                      np.ascontiguousarray(np.concatenate([vs, hs]).astype(np.float32)), x.shape[0]))
+    assert len({s[3] for s in scans}) > 1
+    ctx.map_set(mm.MAP_CORNER_GLOBAL, np.zeros((0, 4), np.float32)); ctx.map_set(mm.MAP_SURF_GLOBAL, np.zeros((0, 4), np.float32))
+    ctx.map_set(mm.MAP_SURF_LOCAL, scene["map_surf"]); ctx.map_set(mm.MAP_CORNER_LOCAL, scene["map_corner"])
+    for n in (1, 2, 3, 4):
+        sub = scans[1:1 + n]
+        poses_a, _, cnt_a = ctx.odom_run(sub, 22, Ts[1], Ts[0], np.eye(4), host_buffers=True)
+        os.environ["MML_ODOM_CLASSIC"] = "1"
+        try:
+            poses_b, _, cnt_b = ctx.odom_run(sub, 22, Ts[1], Ts[0], np.eye(4), host_buffers=True)
+        finally:
+            del os.environ["MML_ODOM_CLASSIC"]
+        assert poses_a.shape == (n, 4, 4) and np.array_equal(cnt_a, cnt_b)
+        assert np.abs(poses_a - poses_b).max() < 1e-9
+        for k in range(n):
+            assert np.abs(poses_a[k][:3, 3] - Ts[2 + k][:3, 3]).max() < 0.03
+    # an empty sequence is a no-op
+    poses_e, _, _ = ctx.odom_run([], 22, Ts[1], Ts[0], np.eye(4), host_buffers=True)
+    assert poses_e.shape[0] == 0
+
+
 def test_large_query_set_is_sorted_but_slots_keep_caller_order(ctx, mm, orc, synth):
     """Query sets above 32768 are Morton-sorted on the device; feature slot i must still belong to query i."""
     ms, mc = synth.feature_map(200_000, 2_000, seed=9)

@@ -573,9 +573,7 @@ __device__ inline double localizability_sv(const double* assoc_stats) {
   double sv = -1.0;
   if (ints[1] > 10) {
     const double M[9] = {mo[0], mo[1], mo[2], mo[1], mo[3], mo[4], mo[2], mo[4], mo[5]};
-    double ev[3], V[9];
-    eig3_sym(M, ev, V);
-    sv = sqrt(fmax(ev[0], 0.0));
+    sv = sqrt(fmax(eig3_sym_min(M), 0.0));
   }
   return sv;
 }

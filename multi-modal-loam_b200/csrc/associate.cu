@@ -324,14 +324,12 @@ __device__ bool knn5_grid_packed(const GridDev& G, float qx, float qy, float qz,
 // checkLocalizability (EST.cpp:536-565) on the plane association's own statistics: the last CTA leaves the smallest
 // singular value of the stacked normals next to the moments (slot 7 of the plane block of assoc_stats), so the
 // solve does not spend its tail on a serial 3x3 eigen-solve. Called by one thread after the moments are final.
-__device__ __noinline__ void publish_localizability(double* moment_out /* [8]: 6 moments, count, value */) {
+__device__ inline void publish_localizability(double* moment_out /* [8]: 6 moments, count, value */) {
   double sv = -1.0;
   if ((int)moment_out[6] > 10) {
     const double* mo = moment_out;
     const double M[9] = {mo[0], mo[1], mo[2], mo[1], mo[3], mo[4], mo[2], mo[4], mo[5]};
-    double ev[3], V[9];
-    eig3_sym(M, ev, V);
-    sv = sqrt(fmax(ev[0], 0.0));
+    sv = sqrt(fmax(eig3_sym_min(M), 0.0));
   }
   moment_out[7] = sv;
 }

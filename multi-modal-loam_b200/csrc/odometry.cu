@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <vector>
 #include <algorithm>
+#include <chrono>
 #include <utility>
 
 int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_d, const int* scan_off, int n_scans,
@@ -346,6 +347,7 @@ static int run_chained(mml_ctx* c, Odom* o, const RunArgs& R, const double* T_in
   for (int k = 0; k < 3 && k < n_scans; k++) MML_CHECK(copy_of(k));
   for (int k = 0; k < 2 && k < n_scans; k++) MML_CHECK(extract_of(k));
   int* cnt = c->frame_cnt.as<int>();
+  const auto host_t0 = std::chrono::steady_clock::now();
   for (int k = 0; k < n_scans; k++) {
     Slot& SL = o->slot[k % kSlots];
     // split / voxel of scan k on its own stream: after the labelling of scan k and the solve of scan k-1 ...
@@ -374,6 +376,8 @@ static int run_chained(mml_ctx* c, Odom* o, const RunArgs& R, const double* T_in
     if (k + 3 < n_scans) MML_CHECK(copy_of(k + 3));
     if (k + 2 < n_scans) MML_CHECK(extract_of(k + 2));
   }
+  const double host_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count();
+  if (tr.on) fprintf(stderr, "odom trace: host enqueue time %.1f us per scan (%d scans)\n", host_us / n_scans, n_scans);
   MML_CUDA(c, cudaMemcpyAsync(hp, out.poses, out_bytes, cudaMemcpyDeviceToHost, st));
   MML_CUDA(c, cudaStreamSynchronize(st));
   for (int k = 0; k < kLanes; k++) MML_CUDA(c, cudaStreamSynchronize(o->lane[k]));

@@ -73,6 +73,25 @@ __host__ __device__ inline void eig3_sym(const double* Ain, double* ev, double* 
   }
 }
 
+// Smallest eigenvalue of a symmetric 3x3 matrix in closed form (trigonometric solution of the characteristic
+// polynomial). Absolute error ~1e-15 x the largest eigenvalue: used where the value only meets a coarse threshold
+// (checkLocalizability, EST.cpp:536-565: sqrt(lambda_min) against 2.0 / 3.0), never where the oracle's digits matter.
+__host__ __device__ inline double eig3_sym_min(const double* A) {
+  const double a00 = A[0], a01 = A[1], a02 = A[2], a11 = A[4], a12 = A[5], a22 = A[8];
+  const double p1 = a01 * a01 + a02 * a02 + a12 * a12;
+  const double q = (a00 + a11 + a22) / 3.0;
+  const double b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
+  const double p2 = b00 * b00 + b11 * b11 + b22 * b22 + 2.0 * p1;
+  if (!(p2 > 0.0)) return q;  // multiple of the identity
+  const double p = sqrt(p2 / 6.0);
+  const double ip = 1.0 / p;
+  const double c00 = b00 * ip, c11 = b11 * ip, c22 = b22 * ip, c01 = a01 * ip, c02 = a02 * ip, c12 = a12 * ip;
+  double r = 0.5 * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) + c02 * (c01 * c12 - c11 * c02));
+  r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+  const double phi = acos(r) / 3.0;
+  return q + 2.0 * p * cos(phi + 2.0943951023931953);  // + 2 pi / 3: the smallest root
+}
+
 // least-squares solution of A x = b (5x3), Householder QR with column pivoting.
 // Every loop is unrolled over compile-time indices and the column pivoting is done with conditional swaps, so the
 // 5x3 matrix lives in registers (a run-time column index would put it in local memory); the arithmetic and its order

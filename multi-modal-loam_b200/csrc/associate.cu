@@ -138,6 +138,12 @@ __global__ void __launch_bounds__(256) k_count_nonzero(const int* __restrict__ a
   if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, (unsigned long long)v);
 }
 
+// distance (in cells, conservative) from a point at fraction f of its cell to the cell at offset o along one axis
+__device__ __forceinline__ float axis_gap(float f, int o) {
+  const float g = o > 0 ? (float)o - f : (o < 0 ? f - (float)(o + 1) : 0.f);
+  return fmaxf(g - 1e-3f, 0.f);
+}
+
 // ---------------------------------------------------------------- k-NN
 struct Knn5 {
   float d[5];
@@ -254,12 +260,6 @@ __device__ __forceinline__ void scan_range_p(const GridDev& G, int c0, int c1, f
     const float d = (dx * dx + dy * dy) + dz * dz;
     knnp_push(r, d, __float_as_int(p.w), k);
   }
-}
-
-// distance (in cells, conservative) from a point at fraction f of its cell to the cell at offset o along one axis
-__device__ __forceinline__ float axis_gap(float f, int o) {
-  const float g = o > 0 ? (float)o - f : (o < 0 ? f - (float)(o + 1) : 0.f);
-  return fmaxf(g - 1e-3f, 0.f);
 }
 
 // exact 5-NN within squared radius `thres` (same result as knn5_grid). Rows of cells are visited nearest first
@@ -598,8 +598,10 @@ __device__ __forceinline__ void scan_cells(const GridLevel& L, int c0, int c1, f
 // acceptable 5-list exists); false when rr1 was exhausted without a verdict.
 template <int G>
 __device__ bool search_shells(const GridLevel& L, const int* c, const int* lo, const int* hi, float qx, float qy, float qz,
-                              float thres, int rr0, int rr1, Knn5& r, Knn5& m, unsigned mask, int lg, int* lst) {
+                              float thres, int rr0, int rr1, Knn5& r, Knn5& m, unsigned mask, int lg, int* lst,
+                              const float* fpos) {
   constexpr int kListCap = 8 * G;  // candidate indices staged per group
+  const float cell2 = L.cell * L.cell;
   for (int rr = rr0; rr <= rr1; rr++) {
     const int side = 2 * rr + 1;
     const int nseg = rr == 1 ? 27 : 2 * side * side;
@@ -630,6 +632,14 @@ __device__ bool search_shells(const GridLevel& L, const int* c, const int* lo, c
           }
         }
         ok = ok && !(z < lo[2] || z > hi[2] || y < lo[1] || y > hi[1]);
+        if (ok && rr > 1 && m.cnt == 5) {
+          // outer shells of a far query: a row / end cell whose box lies farther than the current 5th neighbour
+          // (list merged after the previous shell) cannot change the result and is not read at all
+          const float gy = axis_gap(fpos[1], y - c[1]), gz = axis_gap(fpos[2], z - c[2]);
+          float g2 = gy * gy + gz * gz;
+          if (x0 == x1) { const float gx = axis_gap(fpos[0], x0 - c[0]); g2 += gx * gx; }
+          ok = !(g2 * cell2 > m.d[4]);
+        }
         if (ok) {
           const int rowb = (z * L.dim[1] + y) * L.dim[0];
           p0 = __ldg(L.cell_start + rowb + x0);
@@ -726,7 +736,12 @@ __device__ bool knn5_grid_group(const GridDev& Gd, float qx, float qy, float qz,
       cc[a] = c[a] / f; llo[a] = lo[a] / f; hhi[a] = hi[a] / f;
     }
     const int last = lvl == 0 ? (two_level ? kFineShells : rmax) : (int)ceilf(sqrtf(thres) / L.cell) + 1;
-    const bool done = search_shells<G>(L, cc, llo, hhi, qx, qy, qz, thres, 1, last, r, m, mask, lg, lst);
+    // position of the query inside its (possibly clamped) cell of this level, in cells
+    const double inv_l = Gd.inv_cell / (double)f;
+    const float fpos[3] = {(float)(((double)qx - Gd.org[0]) * inv_l - (double)cc[0]),
+                           (float)(((double)qy - Gd.org[1]) * inv_l - (double)cc[1]),
+                           (float)(((double)qz - Gd.org[2]) * inv_l - (double)cc[2])};
+    const bool done = search_shells<G>(L, cc, llo, hhi, qx, qy, qz, thres, 1, last, r, m, mask, lg, lst, fpos);
     base = L.pts;  // the 5-list indexes this level's sorted copy
     if (done || !two_level) break;
     knn_init(r);

@@ -599,7 +599,7 @@ __device__ __forceinline__ void scan_cells(const GridLevel& L, int c0, int c1, f
 template <int G>
 __device__ bool search_shells(const GridLevel& L, const int* c, const int* lo, const int* hi, float qx, float qy, float qz,
                               float thres, int rr0, int rr1, Knn5& r, Knn5& m, unsigned mask, int lg, int* lst,
-                              const float* fpos) {
+                              const float* fpos, float prune_d) {
   constexpr int kListCap = 8 * G;  // candidate indices staged per group
   const float cell2 = L.cell * L.cell;
   for (int rr = rr0; rr <= rr1; rr++) {
@@ -632,13 +632,14 @@ __device__ bool search_shells(const GridLevel& L, const int* c, const int* lo, c
           }
         }
         ok = ok && !(z < lo[2] || z > hi[2] || y < lo[1] || y > hi[1]);
-        if (ok && rr > 1 && m.cnt == 5) {
+        const float bound = m.cnt == 5 ? fminf(m.d[4], prune_d) : prune_d;  // prune_d: 5th distance of the finer level
+        if (ok && bound < INFINITY) {
           // outer shells of a far query: a row / end cell whose box lies farther than the current 5th neighbour
           // (list merged after the previous shell) cannot change the result and is not read at all
           const float gy = axis_gap(fpos[1], y - c[1]), gz = axis_gap(fpos[2], z - c[2]);
           float g2 = gy * gy + gz * gz;
           if (x0 == x1) { const float gx = axis_gap(fpos[0], x0 - c[0]); g2 += gx * gx; }
-          ok = !(g2 * cell2 > m.d[4]);
+          ok = !(g2 * cell2 > bound);
         }
         if (ok) {
           const int rowb = (z * L.dim[1] + y) * L.dim[0];
@@ -722,6 +723,7 @@ __device__ bool knn5_grid_group(const GridDev& Gd, float qx, float qy, float qz,
   const bool two_level = Gd.pts2 != nullptr && rmax > kFineShells;
   // one copy of the shell search in the instruction stream, run once per level (a query's warp executes this kernel
   // exactly once, so every extra inlined copy is paid for in instruction fetch, ncu's `no_instruction` stall)
+  float prune_d = INFINITY;
 #pragma unroll 1
   for (int lvl = 0; lvl < 2; lvl++) {
     GridLevel L;
@@ -741,9 +743,12 @@ __device__ bool knn5_grid_group(const GridDev& Gd, float qx, float qy, float qz,
     const float fpos[3] = {(float)(((double)qx - Gd.org[0]) * inv_l - (double)cc[0]),
                            (float)(((double)qy - Gd.org[1]) * inv_l - (double)cc[1]),
                            (float)(((double)qz - Gd.org[2]) * inv_l - (double)cc[2])};
-    const bool done = search_shells<G>(L, cc, llo, hhi, qx, qy, qz, thres, 1, last, r, m, mask, lg, lst, fpos);
+    const bool done = search_shells<G>(L, cc, llo, hhi, qx, qy, qz, thres, 1, last, r, m, mask, lg, lst, fpos, prune_d);
     base = L.pts;  // the 5-list indexes this level's sorted copy
     if (done || !two_level) break;
+    // the coarse level starts over (its list indexes another copy of the points), but five points found on the
+    // fine level already bound the 5th distance: cells farther than that are skipped from the first coarse shell on
+    if (m.cnt == 5) prune_d = m.d[4];
     knn_init(r);
     knn_init(m);
   }

@@ -409,6 +409,42 @@ def test_odometry_loop_short_and_ragged_sequences(ctx, mm, synth, scene):
     assert poses_e.shape[0] == 0
 
 
+def test_odometry_loop_many_labelled_points(ctx, mm, orc, synth, scene):
+    """More than 2048 labelled points of a kind (54 scan lines): the clustered split / voxel launch leaves its
+    register-sort fast path for the shared-memory sort. Chained and host-driven drivers must agree, and the voxel
+    filter of the first scan must equal the oracle's bit for bit."""
+    import os
+    Ts = synth.trajectory(4, v=0.5, yaw_rate=0.2, dt=0.1)
+    scans = []
+    for k in range(3):
+        xs, ls, ss = [], [], []
+        for rep in range(3):  # three 16-ring sweeps with independent noise = 48 lines
+            vx, vr, vs = synth.vlp16_scan(Ts[k + 1], seed=700 + 10 * k + rep, T_ws_start=Ts[k])
+            xs.append(vx); ls.append(vr + 16 * rep); ss.append(vs)
+        hx, hl, hs = synth.horizon_scan(Ts[k + 1], 24000, seed=705 + 10 * k, T_ws_start=Ts[k])
+        xs.append(hx); ls.append(hl + 48); ss.append(hs)
+        x = np.ascontiguousarray(np.concatenate(xs))
+        scans.append((x, np.ascontiguousarray(np.concatenate(ls).astype(np.uint16)),
+                      np.ascontiguousarray(np.concatenate(ss).astype(np.float32)), x.shape[0]))
+    label = orc.extract_scan(scans[0][0], scans[0][1], 54)
+    assert int((label == 2).sum()) > 2048
+    ctx.map_set(mm.MAP_CORNER_GLOBAL, np.zeros((0, 4), np.float32)); ctx.map_set(mm.MAP_SURF_GLOBAL, np.zeros((0, 4), np.float32))
+    ctx.map_set(mm.MAP_SURF_LOCAL, scene["map_surf"]); ctx.map_set(mm.MAP_CORNER_LOCAL, scene["map_corner"])
+    poses_a, _, cnt_a = ctx.odom_run(scans, 54, Ts[0], Ts[0], np.eye(4), host_buffers=True)
+    os.environ["MML_ODOM_CLASSIC"] = "1"
+    try:
+        poses_b, _, cnt_b = ctx.odom_run(scans, 54, Ts[0], Ts[0], np.eye(4), host_buffers=True)
+    finally:
+        del os.environ["MML_ODOM_CLASSIC"]
+    assert np.array_equal(cnt_a, cnt_b) and np.abs(poses_a - poses_b).max() < 1e-9
+    # first scan: T_prev == T_init, so the motion used for undistortion is the identity and the voxel counts are the
+    # oracle's on the raw labelled points
+    assert cnt_a[0][0] == int((label == 1).sum()) and cnt_a[0][1] == int((label == 2).sum())
+    x0 = scans[0][0]
+    assert cnt_a[0][2] == orc.voxel_downsample(x0[label == 1], 0.4).shape[0]
+    assert cnt_a[0][3] == orc.voxel_downsample(x0[label == 2], 0.2).shape[0]
+
+
 def test_large_query_set_is_sorted_but_slots_keep_caller_order(ctx, mm, orc, synth):
     """Query sets above 32768 are Morton-sorted on the device; feature slot i must still belong to query i."""
     ms, mc = synth.feature_map(200_000, 2_000, seed=9)

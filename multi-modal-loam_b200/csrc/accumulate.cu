@@ -267,6 +267,13 @@ __device__ __forceinline__ double ld_dsmem_f64(const double* local_smem_ptr, uns
   return v;
 }
 
+__device__ __forceinline__ void st_dsmem_f64(double* local_smem_ptr, unsigned cta_rank, double v) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(local_smem_ptr);
+  unsigned ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(cta_rank));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
+
 #ifndef MML_ACC_MINB
 #define MML_ACC_MINB 2
 #endif
@@ -695,12 +702,11 @@ template <bool CHAIN>
 __global__ void __launch_bounds__(kSolveThreads, 1) k_solve_frame(SolveArgs A) {
   if (A.st->done_outer) return;  // uniform over the cluster
   if (blockIdx.x == 0 && threadIdx.x == 0) MML_TL(A.tl, 6);
-  __shared__ EstState S;         // authoritative in CTA 0; the others use the parameters only
+  __shared__ EstState S;         // every CTA keeps the full solver state and takes the same steps
   __shared__ PoseLin L;
   __shared__ double sred[kSolveWarps][28];
-  __shared__ double part[28];    // this CTA's partial sums (read by CTA 0 through DSMEM)
+  __shared__ double gather[2][kSolveCluster][28];  // partial sums of every CTA, written by their owners (DSMEM), two phases
   __shared__ double tot[28];
-  __shared__ double xb[8];       // CTA 0: next evaluation point (6) and the done flag
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned rank = cluster_ctarank();
   {
@@ -722,6 +728,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve_frame(SolveArgs A) {
 #else
 #define TICK(k)
 #endif
+  int buf = 0;
   for (;;) {
     double acc[28];
 #pragma unroll
@@ -740,49 +747,46 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_solve_frame(SolveArgs A) {
       if (lane < 28) sred[warp][lane] = v;
     }
     __syncthreads();
+    // all-gather through distributed shared memory: every CTA stores its 28 partial sums into every CTA's `gather`,
+    // ONE cluster barrier publishes them, and every CTA sums them in rank order and runs the same dogleg update on
+    // its own copy of the state (identical inputs, identical code: identical steps) - no second barrier and no
+    // broadcast of the next evaluation point. The two phases of `gather` keep a fast CTA's next stores away from a
+    // slow CTA's reads.
     if (tid < 28) {
       double v = 0;
 #pragma unroll
       for (int w = 0; w < kSolveWarps; w++) v += sred[w][tid];
-      part[tid] = v;
+#pragma unroll
+      for (unsigned r = 0; r < (unsigned)kSolveCluster; r++) st_dsmem_f64(&gather[buf][rank][tid], r, v);
     }
     TICK(1)
-    cluster_sync_all();  // partials of every CTA are visible
+    cluster_sync_all();
     TICK(2)
-    if (rank == 0) {
-      if (tid < 28) {
-        double v = 0;
+    if (tid < 28) {
+      double v = 0;
 #pragma unroll
-        for (unsigned r = 0; r < (unsigned)kSolveCluster; r++) v += ld_dsmem_f64(&part[tid], r);
-        tot[tid] = v;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        dogleg_update_inl(S, tot);
-#pragma unroll
-        for (int i = 0; i < 6; i++) xb[i] = S.x_cand[i];
-        xb[6] = S.done_inner ? 1.0 : 0.0;
-      }
+      for (int r = 0; r < kSolveCluster; r++) v += gather[buf][r][tid];
+      tot[tid] = v;
     }
-    TICK(3)
-    cluster_sync_all();  // the next evaluation point is visible
-    TICK(4)
-    if (tid < 7) tot[tid] = ld_dsmem_f64(&xb[tid], 0);
     __syncthreads();
-    if (tot[6] != 0.0) break;
-    make_pose_split(tot, S.Rbl, S.Pbl, L, tid);
+    if (tid == 0) dogleg_update_inl(S, tot);
+    __syncthreads();
+    TICK(3)
+    if (S.done_inner) break;
+    make_pose_split(S.x_cand, S.Rbl, S.Pbl, L, tid);
     __syncthreads();
     TICK(5)
+    buf ^= 1;
 #ifdef MML_SOLVE_PROF
     n_it++;
 #endif
   }
 #ifdef MML_SOLVE_PROF
   if (tid == 0 && rank == 0)
-    printf("solve: n=%d evals=%d eval=%lld reduce=%lld sync1=%lld update=%lld sync2=%lld pose=%lld cycles\n", n_all, n_it + 1,
-           tp[0], tp[1], tp[2], tp[3], tp[4], tp[5]);
+    printf("solve: n=%d evals=%d eval=%lld reduce+scatter=%lld barrier=%lld sum+update=%lld pose=%lld cycles\n", n_all, n_it + 1,
+           tp[0], tp[1], tp[2], tp[3], tp[5]);
 #endif
-  cluster_sync_all();  // nobody reads CTA 0's shared memory any more
+  // every remote store was completed by the last barrier and all CTAs leave the loop in the same iteration
   if (rank != 0) return;
   if (tid == 0) {
     est_end(&S, A.assoc_stats, A.assoc_stats + 15);  // localizability value left by the plane association's last CTA

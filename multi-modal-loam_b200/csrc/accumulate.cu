@@ -406,26 +406,23 @@ __host__ __device__ inline bool dogleg_compute_step(EstState& S) {
   }
   if (!S.reuse) {
     S.reuse = 1;
+    S.alpha = -1.0;  // the Cauchy step length is only formed when a step leaves the Gauss-Newton branch (below)
     double dg[6], idg[6], gr[6];
 #pragma unroll
     for (int i = 0; i < n; i++) {
-      dg[i] = sqrt(fmin(fmax(Hs[i * n + i], 1e-6), 1e32));
+      const double d2 = fmin(fmax(Hs[i * n + i], 1e-6), 1e32);
+#ifdef __CUDA_ARCH__
+      idg[i] = rsqrt(d2);  // one reciprocal square root instead of a square root and a division
+      dg[i] = d2 * idg[i];
+#else
+      dg[i] = sqrt(d2);
       idg[i] = 1.0 / dg[i];
+#endif
       gr[i] = gs[i] * idg[i];
       S.diag[i] = dg[i];
+      S.idiag[i] = idg[i];
       S.grad[i] = gr[i];
     }
-    double v[6], gg = 0, vHv = 0;
-#pragma unroll
-    for (int i = 0; i < n; i++) { v[i] = gr[i] * idg[i]; gg += gr[i] * gr[i]; }
-#pragma unroll
-    for (int i = 0; i < n; i++) {
-      double s = 0;
-#pragma unroll
-      for (int j = 0; j < n; j++) s += Hs[i * n + j] * v[j];
-      vHv += v[i] * s;
-    }
-    S.alpha = gg / vHv;
     bool ok = false;
     while (S.mu < 1.0) {
       double Amat[36], y[6];
@@ -449,13 +446,28 @@ __host__ __device__ inline bool dogleg_compute_step(EstState& S) {
   }
   double grad[6], gn[6], idg[6];
 #pragma unroll
-  for (int i = 0; i < n; i++) { grad[i] = S.grad[i]; gn[i] = S.gn[i]; idg[i] = 1.0 / S.diag[i]; }
+  for (int i = 0; i < n; i++) { grad[i] = S.grad[i]; gn[i] = S.gn[i]; idg[i] = S.idiag[i]; }
   double gnorm = 0, gnn = 0;
 #pragma unroll
   for (int i = 0; i < n; i++) { gnorm += grad[i] * grad[i]; gnn += gn[i] * gn[i]; }
   gnorm = sqrt(gnorm);
   gnn = sqrt(gnn);
-  const double radius = S.radius, alpha = S.alpha;
+  const double radius = S.radius;
+  if (!(gnn <= radius) && S.alpha < 0.0) {
+    // alpha = |g|^2 / (g^T D^-1 H D^-1 g) of the current linearisation (unchanged while steps are rejected)
+    double v[6], gg = 0, vHv = 0;
+#pragma unroll
+    for (int i = 0; i < n; i++) { v[i] = grad[i] * idg[i]; gg += grad[i] * grad[i]; }
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+      double t = 0;
+#pragma unroll
+      for (int j = 0; j < n; j++) t += Hs[i * n + j] * v[j];
+      vHv += v[i] * t;
+    }
+    S.alpha = gg / vHv;
+  }
+  const double alpha = S.alpha;
   double step[6];
   if (gnn <= radius) {
 #pragma unroll

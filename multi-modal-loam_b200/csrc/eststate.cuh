@@ -20,7 +20,7 @@ struct EstState {
   double x[6], x_cand[6], x_best[6];
   double cost, min_cost, H[36], g[6], scale[6];
   double radius, mu, alpha, dogleg_norm, model_change, step_norm, x_norm;
-  double diag[6], grad[6], gn[6];
+  double diag[6], idiag[6], grad[6], gn[6];
   int reuse, num_invalid;
   double q_before[4], t_before[3];
   double min_sv, final_cost;

@@ -515,7 +515,7 @@ def main():
     achieved = dom_bytes / dom_ms / 1e6
     roofline = {"bound": "hbm", "kernel": "k_associate_g<1,32> (plane association: hash-grid 5-NN + plane fit, one warp per query)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": 1109000,  # dram read + write bytes per launch, ncu --set full (profiles/r1g_ncu_full_summary.txt)
+                "traffic": 975000,  # dram read + write bytes per launch, ncu --set full (profiles/r1h_ncu_full_summary.txt)
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
                 "note": "one-scan working set (~1.1 k queries, 0.1 MB): a dependent chain of memory round trips and float64 "
                         "fits, not bandwidth; the HBM-sized sweep is in s4 (there the kernels are issue / FP64-pipe bound)",

@@ -895,12 +895,6 @@ static long long est_graph_key(mml_ctx* ctx, EstState* S, const int* cnt_dev, in
 // line || plane association of the frame slot on two captured streams (fork / join around ctx->stream)
 static int capture_assoc_pair(mml_ctx* ctx, EstState* S, const int* cnt_dev, int cap_corner, int cap_surf) {
   cudaStream_t st = ctx->stream, st2 = ctx->stream2;
-  static const bool serial = getenv("MML_ASSOC_SERIAL") && atoi(getenv("MML_ASSOC_SERIAL")) != 0;  // experiment
-  if (serial) {
-    int rc = mml_associate_launch(ctx, 1, nullptr, 0.f, S->T_wl, &S->thres, &S->done_outer, cnt_dev + 1, cap_surf);
-    if (rc == MML_OK) rc = mml_associate_launch(ctx, 0, nullptr, 0.f, S->T_wl, &S->thres, &S->done_outer, cnt_dev, cap_corner);
-    return rc;
-  }
   cudaEventRecord(ctx->ev_fork, st);
   cudaStreamWaitEvent(st2, ctx->ev_fork, 0);
   ctx->stream = st2;

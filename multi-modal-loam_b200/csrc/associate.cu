@@ -1330,8 +1330,7 @@ int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres,
   static const int g_env = getenv("MML_ASSOC_G") ? atoi(getenv("MML_ASSOC_G")) : 0;
   const int G = g_env ? g_env : (cap <= 32768 ? 32 : 1);
   // group kernels stride over the queries: at most kAssocWave CTAs (4 per SM), however large the query buffer is
-  static const int wave_env = getenv("MML_ASSOC_WAVE") ? atoi(getenv("MML_ASSOC_WAVE")) : 4;  // CTAs per SM (experiments)
-  const int kAssocWave = wave_env * kNumSMs;
+  const int kAssocWave = 4 * kNumSMs;
   int grid = G == 1 ? div_up(nq > 0 ? nq : 1, 128) : div_up(nq > 0 ? nq : 1, 128 / G);
   if (G != 1 && grid > kAssocWave) grid = kAssocWave;
   mml::DevBuf& fb = kind == 0 ? ctx->f_line : ctx->f_plane;

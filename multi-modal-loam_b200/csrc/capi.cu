@@ -464,14 +464,6 @@ static int scan_to_pose_general(mml_ctx* c, const void* xyzi_dev, const void* li
   if (c->profile) MML_CUDA(c, cudaEventRecord(c->pev[0], st));
   MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, c->in_label.as<uint8_t>(),
                                c->sel_tier >= 2));
-  // undistort a copy of the scan (the caller's buffer stays untouched)
-  mml::DevBuf& wbuf = c->srt_xyzi;  // the line-sorted copy is dead after extraction: reuse its storage
-  MML_CUDA(c, wbuf.reserve(sizeof(float4) * (size_t)(n > 0 ? n : 1)));
-  float4* work = wbuf.as<float4>();
-  if (c->profile) MML_CUDA(c, cudaEventRecord(c->pev[1], st));
-  if (n) MML_CUDA(c, cudaMemcpyAsync(work, xyzi_dev, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, st));
-  if (dR9 && dt3 && s_dev) MML_CHECK(mml_undistort_device(c, work, (const float*)s_dev, n, dR9, dt3));
-  // label split (EST.cpp:992-1011); capacities from the counts of the extractor
   MML_CUDA(c, c->frame_cnt.reserve(64));
   int* cnt = c->frame_cnt.as<int>();  // [0..1] voxel outputs, [2..3] raw split counts
   int hc[3] = {0, 0, 0};
@@ -484,6 +476,15 @@ static int scan_to_pose_general(mml_ctx* c, const void* xyzi_dev, const void* li
     MML_CHECK(download(c, hc, c->counters.p, sizeof(hc)));
     MML_CUDA(c, cudaStreamSynchronize(st));
   }
+  // undistort a copy of the scan (the caller's buffer stays untouched). Only now: the copy lives in the storage of
+  // the extraction's line-sorted cloud, which every (re-)run of the extraction above overwrites.
+  mml::DevBuf& wbuf = c->srt_xyzi;
+  MML_CUDA(c, wbuf.reserve(sizeof(float4) * (size_t)(n > 0 ? n : 1)));
+  float4* work = wbuf.as<float4>();
+  if (c->profile) MML_CUDA(c, cudaEventRecord(c->pev[1], st));
+  if (n) MML_CUDA(c, cudaMemcpyAsync(work, xyzi_dev, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+  if (dR9 && dt3 && s_dev) MML_CHECK(mml_undistort_device(c, work, (const float*)s_dev, n, dR9, dt3));
+  // label split (EST.cpp:992-1011); capacities from the counts of the extractor
   const int n_sharp = hc[0], n_flat = hc[1];
   MML_CUDA(c, c->corner_raw.reserve(sizeof(float4) * (size_t)(n_sharp + 1)));
   MML_CUDA(c, c->surf_raw.reserve(sizeof(float4) * (size_t)(n_flat + 1)));

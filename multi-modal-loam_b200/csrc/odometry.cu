@@ -78,6 +78,8 @@ struct Odom {
   cudaStream_t sv = nullptr;        // chained loop: the split / voxel launch of scan k (beside the graph launch of scan k)
   cudaEvent_t sv_done = nullptr;    // ... finished (waited for inside the scan's graph)
   cudaEvent_t scan_done = nullptr;  // the solve of the previous scan has finished (matcher stream)
+  bool big_scans = false;           // sticky: scans label more points than the fused split / voxel kernel holds ->
+                                    // straight to the general path until a scan fits comfortably again
   FeScratch scratch[kLanes];  // scratch[0] stays empty: lane 0 works in the context's own buffers
   mml::DevBuf state;  // OdomDev
   mml::DevBuf out;    // ChainOut arrays
@@ -236,9 +238,7 @@ static int run_classic(mml_ctx* c, Odom* o, const RunArgs& R, int first, const d
   memcpy(T_before, T_prev16, sizeof(T_before));
   const void* xd[2] = {nullptr, nullptr};
   const void* sd[2] = {nullptr, nullptr};
-  if (first < n_scans)
-    MML_CHECK(submit(c, o, first, R.xyzi[first], R.line[first], R.s ? R.s[first] : nullptr, R.n_pts[first], n_lines, host,
-                     &xd[first & 1], &sd[first & 1]));
+  int next_submit = first;  // first scan whose extraction has not been enqueued yet
   for (int k = first; k < n_scans; k++) {
     // the reference's pipeline: the extractor node works on the next scan meanwhile. Its launches are issued from
     // the hook below, after this scan's critical-path work is already in the stream.
@@ -247,6 +247,11 @@ static int run_classic(mml_ctx* c, Odom* o, const RunArgs& R, int first, const d
       const void** xd; const void** sd;
     } nx = {c, o, k + 1, nullptr, nullptr, nullptr, 0, n_lines, host, &xd[(k + 1) & 1], &sd[(k + 1) & 1]};
     if (k + 1 < n_scans) { nx.xyzi = R.xyzi[k + 1]; nx.line = R.line[k + 1]; nx.s = R.s ? R.s[k + 1] : nullptr; nx.n = R.n_pts[k + 1]; }
+    const bool fused = !o->big_scans;
+    if (fused && next_submit <= k) {
+      MML_CHECK(submit(c, o, k, R.xyzi[k], R.line[k], R.s ? R.s[k] : nullptr, R.n_pts[k], n_lines, host, &xd[k & 1], &sd[k & 1]));
+      next_submit = k + 1;
+    }
     auto submit_next = [](void* a) -> int {
       Next* x = static_cast<Next*>(a);
       return submit(x->c, x->o, x->k, x->xyzi, x->line, x->s, x->n, x->n_lines, x->host, x->xd, x->sd);
@@ -265,16 +270,21 @@ static int run_classic(mml_ctx* c, Odom* o, const RunArgs& R, int first, const d
     double stats[16];
     const int n = R.n_pts[k];
     int* cnt = c->frame_cnt.as<int>();
-    MML_CUDA(c, cudaStreamWaitEvent(st, S.done, 0));
-    MML_CHECK(mml_split_voxel_device(c, (const float4*)xd[k & 1], (const float*)sd[k & 1], S.label.as<uint8_t>(), n, dR, dt,
-                                     R.leaf_corner, R.leaf_surf, c->q_corner.as<float4>(), c->q_surf.as<float4>(), cnt));
     int* hf = c->pin_flags.as<int>();
-    MML_CUDA(c, cudaMemcpyAsync(hf, S.counters.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    MML_CUDA(c, cudaMemcpyAsync(hf + 4, cnt, 5 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    MML_CUDA(c, cudaEventRecord(S.consumed, st));
-    MML_CHECK(mml_estimate_device(c, cnt, cap, cap, R.exTlb16, P, q, R.prm, stats, k + 1 < n_scans ? +submit_next : nullptr,
-                                  &nx));  // synchronises `st`
-    if (hf[2] || hf[8]) {
+    if (fused) {
+      MML_CUDA(c, cudaStreamWaitEvent(st, S.done, 0));
+      MML_CHECK(mml_split_voxel_device(c, (const float4*)xd[k & 1], (const float*)sd[k & 1], S.label.as<uint8_t>(), n, dR, dt,
+                                       R.leaf_corner, R.leaf_surf, c->q_corner.as<float4>(), c->q_surf.as<float4>(), cnt));
+      MML_CUDA(c, cudaMemcpyAsync(hf, S.counters.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+      MML_CUDA(c, cudaMemcpyAsync(hf + 4, cnt, 5 * sizeof(int), cudaMemcpyDeviceToHost, st));
+      MML_CUDA(c, cudaEventRecord(S.consumed, st));
+      const bool pipeline_next = k + 1 < n_scans && next_submit == k + 1;
+      MML_CHECK(mml_estimate_device(c, cnt, cap, cap, R.exTlb16, P, q, R.prm, stats, pipeline_next ? +submit_next : nullptr,
+                                    &nx));  // synchronises `st`
+      if (pipeline_next) next_submit = k + 2;
+      if (hf[8]) o->big_scans = true;  // the labelled points do not fit the fused kernel: stop trying for now
+    }
+    if (!fused || hf[2] || hf[8]) {
       // capacity overflow of a fused kernel: this scan goes through the general (unpipelined) path
       MML_CUDA(c, cudaStreamSynchronize(c->stream_fe));
       P[0] = Tp[3]; P[1] = Tp[7]; P[2] = Tp[11];
@@ -287,6 +297,7 @@ static int run_classic(mml_ctx* c, Odom* o, const RunArgs& R, int first, const d
         MML_CHECK(mml_scan_to_pose_dev(c, R.xyzi[k], R.line[k], R.s ? R.s[k] : nullptr, n, n_lines, dR, dt, R.leaf_corner,
                                        R.leaf_surf, R.exTlb16, P, q, R.prm, stats, oc));
       if (R.counts_out) memcpy(R.counts_out + 4 * k, oc, sizeof(oc));
+      if (o->big_scans && oc[0] < cap / 2 && oc[1] < cap / 2) o->big_scans = false;
     } else if (R.counts_out) {
       R.counts_out[4 * k] = hf[0]; R.counts_out[4 * k + 1] = hf[1]; R.counts_out[4 * k + 2] = hf[4]; R.counts_out[4 * k + 3] = hf[5];
     }
@@ -503,7 +514,7 @@ int mml_odom_run(mml_ctx* c, const void* const* xyzi, const void* const* line, c
   RunArgs R = {xyzi, line, s, n_pts, n_scans, n_lines, host_buffers, exTlb16, leaf_corner, leaf_surf, prm, poses_out, counts_out};
   const bool classic = getenv("MML_ODOM_CLASSIC") && atoi(getenv("MML_ODOM_CLASSIC")) != 0;
   int first = 0;
-  if (!classic) MML_CHECK(run_chained(c, o, R, T_init16, T_prev16, &first));
+  if (!classic && !o->big_scans) MML_CHECK(run_chained(c, o, R, T_init16, T_prev16, &first));
   if (first < n_scans) {
     // classic driver from the first scan the chained one could not finish, seeded with the poses before it
     const double* Ti = first >= 1 ? poses_out + 16 * (size_t)(first - 1) : T_init16;

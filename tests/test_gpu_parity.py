@@ -409,6 +409,37 @@ def test_odometry_loop_short_and_ragged_sequences(ctx, mm, synth, scene):
     assert poses_e.shape[0] == 0
 
 
+def test_first_large_scan_on_a_fresh_context(mm, orc, synth, scene):
+    """A 240k-point Horizon scan (40k points per line) as the FIRST call on a new context: the selection kernel's
+    shared-memory tier is bumped inside the call and more than 16384 points are labelled flat, so the scan takes the
+    general path. The result must not depend on whether the tier had been bumped before (regression: the
+    undistorted copy used to be overwritten by the extraction's re-run) and must match the oracle."""
+    T0 = synth.make_T(synth.rot_z(0.3), np.array([-3.0, -1.0, 0.2]))
+    T1 = T0 @ synth.s1_offset_pose()
+    hx, hl, hs = synth.horizon_scan(T1, 240000, seed=77, T_ws_start=T0)
+    x, line, s = np.ascontiguousarray(hx), np.ascontiguousarray(hl.astype(np.uint16)), np.ascontiguousarray(hs.astype(np.float32))
+    delta = np.linalg.inv(T0) @ T1
+    q0, _ = orc.so3_exp(synth.R_to_rotvec(T1[:3, :3]))
+    fresh = mm.Context(0)
+    try:
+        fresh.map_set(mm.MAP_SURF_LOCAL, scene["map_surf"]); fresh.map_set(mm.MAP_CORNER_LOCAL, scene["map_corner"])
+        xd, ld, sd = fresh.dev_upload(x), fresh.dev_upload(line), fresh.dev_upload(s)
+        P1, q1, st1, cnt1 = fresh.scan_to_pose_dev(xd, ld, sd, x.shape[0], 6, delta[:3, :3], delta[:3, 3], np.eye(4), T1[:3, 3], q0)
+        P2, q2, st2, cnt2 = fresh.scan_to_pose_dev(xd, ld, sd, x.shape[0], 6, delta[:3, :3], delta[:3, 3], np.eye(4), T1[:3, 3], q0)
+    finally:
+        fresh.close()
+    assert np.array_equal(cnt1, cnt2) and np.array_equal(P1, P2) and np.array_equal(q1, q2)
+    label = orc.extract_scan(x, line, 6)
+    assert int((label == 2).sum()) > 16384
+    xu = orc.undistort(x, s, delta[:3, :3], delta[:3, 3])
+    corner = orc.voxel_downsample(xu[label == 1], 0.4); surf = orc.voxel_downsample(xu[label == 2], 0.2)
+    assert cnt1[0] == int((label == 1).sum()) and cnt1[1] == int((label == 2).sum())
+    assert abs(int(cnt1[2]) - corner.shape[0]) <= 1 and abs(int(cnt1[3]) - surf.shape[0]) <= 2  # undistortion: libm vs CUDA sin, 1 ulp
+    om = orc.Map(); om.set(orc.SURF_LOCAL, scene["map_surf"]); om.set(orc.CORNER_LOCAL, scene["map_corner"])
+    Po, qo, _ = om.estimate(corner, surf, np.eye(4), T1[:3, 3], q0)
+    assert np.abs(P1 - Po).max() <= POSE_TOL_M and 2 * np.abs(q1 - qo).max() <= POSE_TOL_RAD
+
+
 def test_odometry_loop_many_labelled_points(ctx, mm, orc, synth, scene):
     """More than 2048 labelled points of a kind (54 scan lines): the clustered split / voxel launch leaves its
     register-sort fast path for the shared-memory sort. Chained and host-driven drivers must agree, and the voxel

@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--s4-queries", type=int, default=240_000)
     ap.add_argument("--s4-map", type=int, default=1_000_000)
     ap.add_argument("--no-s4", action="store_true")
+    ap.add_argument("--no-s2", action="store_true")
+    ap.add_argument("--s2-pts", type=int, default=240_000)
     ap.add_argument("--s5-map", type=int, default=2_000_000, help="S5 global map points per GPU (multi-GPU runs only)")
     ap.add_argument("--s5-queries", type=int, default=200_000)
     return ap.parse_args()
@@ -507,6 +509,30 @@ def main():
                                 "accumulate_frac": nq4 * BYTES_PER_FEATURE_EVAL / ms_ac / 1e6 / peak})
         ctx4.close()
 
+    # S2 (BASELINE config 2): Livox Horizon 240k-pt scans (6 lines x 40k points), scan-to-map against the 100k-pt local
+    # map, <= 10 outer iterations. More than 16384 points are labelled flat at this density, so every scan takes the
+    # general (multi-kernel, host-sequenced) path: reported for completeness, not tuned this round.
+    s2 = None
+    if not a.no_s2:
+        n2 = 7
+        Ts2 = synth.trajectory(n2, v=0.5, yaw_rate=0.2, dt=0.1)
+        sc2 = []
+        for k in range(n2):
+            hx, hl, hs = synth.horizon_scan(Ts2[k + 1], a.s2_pts, seed=2002 + k, T_ws_start=Ts2[k])
+            sc2.append((ctx.dev_upload(np.ascontiguousarray(hx)), ctx.dev_upload(np.ascontiguousarray(hl.astype(np.uint16))),
+                        ctx.dev_upload(np.ascontiguousarray(hs.astype(np.float32))), hx.shape[0]))
+        prm2 = mm.est_params()
+        prm2.max_outer = 10
+        ctx.odom_run(sc2[1:], 6, Ts2[1], Ts2[0], ex, host_buffers=False, params=prm2)  # warm-up (buffers, selection tier)
+        p2, ms2, c2 = ctx.odom_run(sc2[1:], 6, Ts2[1], Ts2[0], ex, host_buffers=False, params=prm2)
+        s2 = {"points_per_scan": int(a.s2_pts), "scans": n2 - 1, "ms_per_scan": ms2 / (n2 - 1), "scans_per_s": 1e3 * (n2 - 1) / ms2,
+              "labelled_sharp_flat": [int(c2[0][0]), int(c2[0][1])], "queries_corner_surf": [int(c2[0][2]), int(c2[0][3])],
+              "max_pos_err_m": float(max(np.abs(p2[k][:3, 3] - Ts2[2 + k][:3, 3]).max() for k in range(n2 - 1))),
+              "path": "general (labelled points exceed the fused split/voxel kernel's 16384)"}
+        for d2 in sc2:
+            for ptr in d2[:3]:
+                ctx.dev_free(ptr)
+
     # the kernel with the largest share of the step in the ncu launch list (profiles/): the plane association
     # (5-NN search in the spatial hash + plane fit + feature write), timed alone on the context's stream at the
     # loop's first-iteration threshold
@@ -522,7 +548,7 @@ def main():
                 "stage_ms_per_scan": {"extract": stage_ms[0], "undistort_split_voxel": stage_ms[1], "estimate": stage_ms[2]},
                 "per_scan_avg": {"outer_iters": float(np.mean([i[0] for i in iters])), "dogleg_iters": float(np.mean([i[1] for i in iters])),
                                  "corner_queries": float(np.mean([i[2] for i in iters])), "surf_queries": float(np.mean([i[3] for i in iters]))},
-                "detail": roof, "s4": s4}
+                "detail": roof, "s2": s2, "s4": s4}
 
     # ---- CPU baseline on a bounded sample of the same workload (rank 0, host cores)
     orc.build()

@@ -234,8 +234,11 @@ __device__ __forceinline__ void sv_bitonic32(unsigned& a0, unsigned& a1, int N2,
 // CL > 1 (chained loop, labels pre-compacted): a cluster of CL CTAs per label shares the float64 undistortion - one SM's
 // FP64 pipe would bound it - then the cluster's first CTA builds the voxel grid; CTA 1 of the corner cluster starts
 // the scan's solve (k_est_init's job) off the voxel filter's critical path.
+#ifndef MML_SV_MINB
+#define MML_SV_MINB 1
+#endif
 template <int CL>
-__global__ void __launch_bounds__(kSvThreads) k_split_voxel(SplitVoxelArgs A) {
+__global__ void __launch_bounds__(kSvThreads, MML_SV_MINB) k_split_voxel(SplitVoxelArgs A) {
   extern __shared__ __align__(16) unsigned char sv_smem[];
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(sv_smem);  // [kSvCap]; fast path: [2][2048] + points
   float4* spts = reinterpret_cast<float4*>(sv_smem + 2 * kSvFast * sizeof(unsigned long long));  // fast path: [2048]

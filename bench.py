@@ -546,7 +546,8 @@ def main():
                 "note": "one-scan working set (~1.1 k queries, 0.1 MB): a dependent chain of memory round trips and float64 "
                         "fits, not bandwidth; the HBM-sized sweep is in s4 (there the kernels are issue / FP64-pipe bound)",
                 "stage_ms_per_scan": {"extract": stage_ms[0], "undistort_split_voxel": stage_ms[1], "estimate": stage_ms[2]},
-                "per_scan_avg": {"outer_iters": float(np.mean([i[0] for i in iters])), "dogleg_iters": float(np.mean([i[1] for i in iters])),
+                "per_scan_avg": {"outer_iters_timed_loop": (launches / max(a.steps, 1) - 8.0) / 3.0,  # 8 launches per scan + 3 per outer iteration
+                                 "outer_iters": float(np.mean([i[0] for i in iters])), "dogleg_iters": float(np.mean([i[1] for i in iters])),
                                  "corner_queries": float(np.mean([i[2] for i in iters])), "surf_queries": float(np.mean([i[3] for i in iters]))},
                 "detail": roof, "s2": s2, "s4": s4}
 

@@ -1084,7 +1084,7 @@ int mml_chain_solve_launch(mml_ctx* ctx, const int* cnt_dev, int cap, mml::OdomD
     cudaGraph_t graph = nullptr;
     MML_CUDA(ctx, cudaGraphCreate(&graph, 0));
     // Layout: [wait for the scan's split / voxel launch] -> first outer iteration as plain kernel nodes -> WHILE node
-    // holding the same iteration for scans that have not converged (5 % of the benchmark's scans). The body of a
+    // holding the same iteration for scans that have not converged (one in three of the benchmark's scans). The body of a
     // conditional node is launched from the device, which costs ~15 us before its first kernel runs: the common
     // case therefore never enters it; its condition is set by the first iteration's solve kernel.
     cudaGraphConditionalHandle cond;

@@ -436,8 +436,8 @@ static int run_chained(mml_ctx* c, Odom* o, const RunArgs& R, const double* T_in
       fprintf(stderr, "association kind %d, last scan: %zu queries, cycles per query mean %.0f p50 %u p90 %u p99 %u max %u\n", kind, v.size(),
               sum / v.size(), v[v.size() / 2], v[v.size() * 9 / 10], v[v.size() * 99 / 100], v.back());
     }
-    if (m) fprintf(stderr, "device timeline (us, %d scans): prev solve end -> split/voxel start %.1f | split/voxel %.1f | -> first association start %.1f | "
-                   "plane association %.1f, line association %.1f | -> solve start %.1f | solve %.1f\n", m, gap / m / 1e3, sv / m / 1e3,
+    if (m) fprintf(stderr, "device timeline (us, %d scans, %d outer iterations in total): prev solve end -> split/voxel start %.1f | split/voxel %.1f | -> first association start %.1f | "
+                   "plane association %.1f, line association %.1f | -> solve start %.1f | solve %.1f\n", m, n, gap / m / 1e3, sv / m / 1e3,
                    entry / m / 1e3, a1 / m / 1e3, a0 / m / 1e3, join / m / 1e3, solve / m / 1e3);
   }
 #endif

@@ -35,6 +35,23 @@ def test_extract_merged_scan_bit_exact(ctx, orc, scene):
     assert np.array_equal(label, orc.extract_scan(x, line, 22))
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_extract_random_scenes_bit_exact(ctx, orc, synth, seed):
+    """Seeded random poses, range-noise levels and scan densities: every label must equal the oracle's. Guards the
+    float32 screening of the float64 direction tests in k_point_attr (borderline cases fall back to float64)."""
+    rng = np.random.default_rng(4000 + seed)
+    T = synth.make_T(synth.rot_z(rng.uniform(-3.1, 3.1)), np.array([rng.uniform(-7, 7), rng.uniform(-4, 4), rng.uniform(-0.5, 1.5)]))
+    noise = float(rng.choice([0.0, 0.002, 0.01, 0.03]))
+    vx, vr, _ = synth.vlp16_scan(T, seed=4100 + seed, noise=noise, n_az=int(rng.choice([900, 1800])))
+    hx, hl, _ = synth.horizon_scan(T, int(rng.choice([12000, 24000, 60000])), seed=4200 + seed, noise=noise)
+    x = np.concatenate([vx, hx])
+    line = np.concatenate([vr, hl + 16]).astype(np.uint16)
+    label, ns, nf = ctx.extract_features(x, line, 22)
+    ref = orc.extract_scan(x, line, 22)
+    assert np.array_equal(label, ref)
+    assert ns == int((ref == 1).sum()) and nf == int((ref == 2).sum()) and nf > 100
+
+
 def test_extract_batch_matches_single(ctx, orc, synth):
     xs, ls, offs = [], [], [0]
     for k in range(3):

@@ -462,18 +462,32 @@ static int scan_to_pose_general(mml_ctx* c, const void* xyzi_dev, const void* li
   MML_CUDA(c, c->tmp_e.reserve(sizeof(float4) * (size_t)(n > 0 ? n : 1)));
   const int off[2] = {0, n};
   if (c->profile) MML_CUDA(c, cudaEventRecord(c->pev[0], st));
-  MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, c->in_label.as<uint8_t>(),
-                               c->sel_tier >= 2));
+  // labels: extracted here, or already there (the odometry loop labels the next scan on an extraction lane while this
+  // one is matched and hands over the slot's label / counter buffers; the stream already waits for that lane)
+  uint8_t* label_d = c->in_label.as<uint8_t>();
+  const int* counters_d = c->counters.as<int>();
+  if (c->pre_label) {
+    label_d = c->pre_label;
+    counters_d = c->pre_counters;
+  } else {
+    MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, label_d, c->sel_tier >= 2));
+  }
   MML_CUDA(c, c->frame_cnt.reserve(64));
   int* cnt = c->frame_cnt.as<int>();  // [0..1] voxel outputs, [2..3] raw split counts
   int hc[3] = {0, 0, 0};
-  MML_CHECK(download(c, hc, c->counters.p, sizeof(hc)));
+  MML_CHECK(download(c, hc, counters_d, sizeof(hc)));
   MML_CUDA(c, cudaStreamSynchronize(st));
+  if (hc[2] && c->pre_label) {  // the pre-labelled scan overflowed the tier it was labelled with: label it again here
+    label_d = c->in_label.as<uint8_t>();
+    counters_d = c->counters.as<int>();
+    MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, label_d, c->sel_tier >= 2));
+    MML_CHECK(download(c, hc, counters_d, sizeof(hc)));
+    MML_CUDA(c, cudaStreamSynchronize(st));
+  }
   while (hc[2] && c->sel_tier < 2) {  // a line overflowed the selection kernel's tier: next tier (2 = sequential)
     c->sel_tier++;
-    MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, c->in_label.as<uint8_t>(),
-                                 c->sel_tier >= 2));
-    MML_CHECK(download(c, hc, c->counters.p, sizeof(hc)));
+    MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, label_d, c->sel_tier >= 2));
+    MML_CHECK(download(c, hc, counters_d, sizeof(hc)));
     MML_CUDA(c, cudaStreamSynchronize(st));
   }
   // undistort a copy of the scan (the caller's buffer stays untouched). Only now: the copy lives in the storage of
@@ -491,7 +505,7 @@ static int scan_to_pose_general(mml_ctx* c, const void* xyzi_dev, const void* li
   const int cap_c = round_cap(n_sharp), cap_s = round_cap(n_flat);
   MML_CUDA(c, c->q_corner.reserve(sizeof(float4) * (size_t)cap_c));
   MML_CUDA(c, c->q_surf.reserve(sizeof(float4) * (size_t)cap_s));
-  MML_CHECK(mml_label_split_device(c, work, c->in_label.as<uint8_t>(), n, c->corner_raw.as<float4>(), c->surf_raw.as<float4>(), cnt + 2));
+  MML_CHECK(mml_label_split_device(c, work, label_d, n, c->corner_raw.as<float4>(), c->surf_raw.as<float4>(), cnt + 2));
   MML_CHECK(mml_voxel_device(c, c->corner_raw.as<float4>(), cnt + 2, n_sharp, leaf_corner, c->q_corner.as<float4>(), cnt));
   MML_CHECK(mml_voxel_device(c, c->surf_raw.as<float4>(), cnt + 3, n_flat, leaf_surf, c->q_surf.as<float4>(), cnt + 1));
   if (c->profile) MML_CUDA(c, cudaEventRecord(c->pev[2], st));
@@ -535,6 +549,9 @@ int mml_scan_to_pose_dev(mml_ctx* c, const void* xyzi_dev, const void* line_id_d
   MML_CUDA(c, c->q_corner.reserve(sizeof(float4) * (size_t)cap));
   MML_CUDA(c, c->q_surf.reserve(sizeof(float4) * (size_t)cap));
   MML_CUDA(c, c->pin_flags.reserve(64));
+  if (c->prefer_general)  // the caller knows the scan does not fit the fused kernels (odometry loop, big scans)
+    return scan_to_pose_general(c, xyzi_dev, line_id_dev, s_dev, n, n_lines, dR9, dt3, leaf_corner, leaf_surf, exTlb16, P3,
+                                q_wxyz4, prm, stats, out_counts);
   const double P_in[3] = {P3[0], P3[1], P3[2]}, q_in[4] = {q_wxyz4[0], q_wxyz4[1], q_wxyz4[2], q_wxyz4[3]};
   const int off[2] = {0, n};
   if (c->profile) MML_CUDA(c, cudaEventRecord(c->pev[0], st));

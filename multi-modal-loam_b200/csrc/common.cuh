@@ -127,6 +127,9 @@ struct mml_ctx {
   mml::DevBuf assoc_part[2];      // per-CTA moment partials of the line / plane association
   cudaGraphExec_t est_graph = nullptr;
   long long est_graph_key = 0;
+  uint8_t* pre_label = nullptr;                          // general path: labels / counters of the scan already extracted by the caller
+  const int* pre_counters = nullptr;
+  bool prefer_general = false;                           // mml_scan_to_pose[_dev]: skip the fused attempt (set by the odometry loop for big scans)
   int solve_small = 1;                                   // sticky: scan-sized frames use the one-CTA solve (accumulate.cu)
   long long est_launches_per_graph = 0;
   cudaGraphExec_t chain_graph = nullptr;   // chained odometry loop: WHILE graph of one scan's solve (accumulate.cu)

@@ -247,15 +247,27 @@ static int run_classic(mml_ctx* c, Odom* o, const RunArgs& R, int first, const d
       const void** xd; const void** sd;
     } nx = {c, o, k + 1, nullptr, nullptr, nullptr, 0, n_lines, host, &xd[(k + 1) & 1], &sd[(k + 1) & 1]};
     if (k + 1 < n_scans) { nx.xyzi = R.xyzi[k + 1]; nx.line = R.line[k + 1]; nx.s = R.s ? R.s[k + 1] : nullptr; nx.n = R.n_pts[k + 1]; }
+    auto submit_next = [](void* a) -> int {
+      Next* x = static_cast<Next*>(a);
+      return submit(x->c, x->o, x->k, x->xyzi, x->line, x->s, x->n, x->n_lines, x->host, x->xd, x->sd);
+    };
     const bool fused = !o->big_scans;
     if (fused && next_submit <= k) {
       MML_CHECK(submit(c, o, k, R.xyzi[k], R.line[k], R.s ? R.s[k] : nullptr, R.n_pts[k], n_lines, host, &xd[k & 1], &sd[k & 1]));
       next_submit = k + 1;
     }
-    auto submit_next = [](void* a) -> int {
-      Next* x = static_cast<Next*>(a);
-      return submit(x->c, x->o, x->k, x->xyzi, x->line, x->s, x->n, x->n_lines, x->host, x->xd, x->sd);
+    // general mode (scans beyond the fused kernels' capacity): scans k and k+1 are copied / labelled on the copy stream
+    // and extraction lane 1 (its own scratch set: the general path below works in the context's), so that the
+    // labelling of scan k+1 overlaps the matching of scan k
+    auto prefetch = [&](int j) -> int {
+      MML_CHECK(submit_copy(c, o, j, R.xyzi[j], R.line[j], R.s ? R.s[j] : nullptr, R.n_pts[j], host, true));
+      return submit_extract(c, o, j, R.n_pts[j], n_lines, 1, false, nullptr);
     };
+    bool prelabelled = false;
+    if (!fused) {
+      while (next_submit <= k + 1 && next_submit < n_scans) { MML_CHECK(prefetch(next_submit)); next_submit++; }
+      prelabelled = true;
+    }
     Slot& S = o->slot[k % kSlots];
     // constant-velocity prediction and the motion used for undistortion
     double Tinv[16], delta[16], Tp[16];
@@ -290,12 +302,23 @@ static int run_classic(mml_ctx* c, Odom* o, const RunArgs& R, int first, const d
       P[0] = Tp[3]; P[1] = Tp[7]; P[2] = Tp[11];
       q[0] = qp.w; q[1] = qp.x; q[2] = qp.y; q[3] = qp.z;
       int oc[4];
-      if (host)
+      c->prefer_general = !fused;  // a scan already known not to fit goes straight to the general path
+      struct Reset { mml_ctx* c; ~Reset() { c->prefer_general = false; c->pre_label = nullptr; c->pre_counters = nullptr; } } reset{c};
+      if (prelabelled) {
+        // labels, counters and the device copy of the scan are in its slot (lane 1); the matcher stream waits for them
+        MML_CUDA(c, cudaStreamWaitEvent(st, S.done, 0));
+        c->pre_label = S.label.as<uint8_t>();
+        c->pre_counters = S.counters.as<int>();
+        MML_CHECK(mml_scan_to_pose_dev(c, S.xd, S.ld, S.sd, n, n_lines, dR, dt, R.leaf_corner, R.leaf_surf, R.exTlb16, P, q, R.prm,
+                                       stats, oc));
+        MML_CUDA(c, cudaEventRecord(S.consumed, st));
+      } else if (host) {
         MML_CHECK(mml_scan_to_pose(c, (const float*)R.xyzi[k], (const uint16_t*)R.line[k], R.s ? (const float*)R.s[k] : nullptr,
                                    n, n_lines, dR, dt, R.leaf_corner, R.leaf_surf, R.exTlb16, P, q, R.prm, stats, oc));
-      else
+      } else {
         MML_CHECK(mml_scan_to_pose_dev(c, R.xyzi[k], R.line[k], R.s ? R.s[k] : nullptr, n, n_lines, dR, dt, R.leaf_corner,
                                        R.leaf_surf, R.exTlb16, P, q, R.prm, stats, oc));
+      }
       if (R.counts_out) memcpy(R.counts_out + 4 * k, oc, sizeof(oc));
       if (o->big_scans && oc[0] < cap / 2 && oc[1] < cap / 2) o->big_scans = false;
     } else if (R.counts_out) {

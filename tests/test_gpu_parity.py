@@ -424,6 +424,18 @@ def test_odometry_loop_short_and_ragged_sequences(ctx, mm, synth, scene):
     # an empty sequence is a no-op
     poses_e, _, _ = ctx.odom_run([], 22, Ts[1], Ts[0], np.eye(4), host_buffers=True)
     assert poses_e.shape[0] == 0
+    # an empty scan inside a sequence (a dropped message): no features, so its pose is the constant-velocity prediction
+    empty = (np.zeros((0, 4), np.float32), np.zeros(0, np.uint16), np.zeros(0, np.float32), 0)
+    seq = [scans[1], empty, scans[2]]
+    poses_a, _, cnt_a = ctx.odom_run(seq, 22, Ts[1], Ts[0], np.eye(4), host_buffers=True)
+    os.environ["MML_ODOM_CLASSIC"] = "1"
+    try:
+        poses_b, _, cnt_b = ctx.odom_run(seq, 22, Ts[1], Ts[0], np.eye(4), host_buffers=True)
+    finally:
+        del os.environ["MML_ODOM_CLASSIC"]
+    assert np.array_equal(cnt_a, cnt_b) and (cnt_a[1] == 0).all() and np.abs(poses_a - poses_b).max() < 1e-9
+    pred = poses_a[0] @ (np.linalg.inv(Ts[1]) @ poses_a[0])
+    assert np.abs(poses_a[1] - pred).max() < 1e-9
 
 
 def test_first_large_scan_on_a_fresh_context(mm, orc, synth, scene):

@@ -145,8 +145,12 @@ int mml_scan_to_pose_dev(mml_ctx* ctx, const void* xyzi_dev, const void* line_id
                          double* stats, int* out_counts);
 
 /* ---- native odometry loop: the per-scan body of process() (src/unionPoseEstimation.cpp:650-906) over a
- * sequence of scans, keeping the reference's node pipeline (extraction of scan k+1 overlaps the matching of
- * scan k on a second stream). xyzi / line / s: arrays of per-scan pointers, device pointers when
+ * sequence of scans, keeping the reference's node pipeline (the copy of scan k+3 and the feature extraction of
+ * scans k+1, k+2 overlap the matching of scan k). The loop is chained on the device: the pose history and the
+ * constant-velocity prediction live in device memory and a scan's solve is one graph launch, so the call enqueues
+ * the whole sequence and reads the poses back once. Scans that exceed the fused kernels' capacities (a scan line
+ * beyond the selection kernel's tier, more than 16384 labelled points of a kind) are re-run on the general path;
+ * results are the same either way. MML_ODOM_CLASSIC=1 selects the host-driven driver (one wait per outer iteration). xyzi / line / s: arrays of per-scan pointers, device pointers when
  * host_buffers == 0, host (ideally pinned) pointers otherwise. T_init16 / T_prev16: the two poses before the
  * first scan (constant-velocity seed, PE.cpp:847-852). poses_out: n_scans x 16 row-major T_wb.
  * total_ms (may be NULL): CUDA-event time of the run. counts_out (may be NULL): n_scans x 4.            */

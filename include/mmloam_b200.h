@@ -159,6 +159,17 @@ int mml_odom_run(mml_ctx* ctx, const void* const* xyzi, const void* const* line,
                  const double* T_prev16, const double* exTlb16, float leaf_corner, float leaf_surf,
                  const mml_est_params* prm, double* poses_out, float* total_ms, int* counts_out);
 
+/* ---- local feature map kept on the device: Estimator::MapIncrementLocal, src/lio/Estimator.cpp:1585-1643
+ * (SURVEY.md 8 f, row F1). One call = one map update: the frame's corner / surf clouds (LiDAR frame) are moved to
+ * the world frame with T_wl16 (MAP_MANAGER::pointAssociateToMap, MM.cpp:75-89), stored in the 50-frame ring, the
+ * previous filtered map and the ring are concatenated (EST.cpp:1620-1624) and voxel-filtered (EST.cpp:1630-1635),
+ * and the spatial hash of the local map kinds (2, 3) is rebuilt from the result - no host copy of the map exists.  */
+int mml_local_map_push(mml_ctx* ctx, const float* corner_xyzi, int n_corner, const float* surf_xyzi, int n_surf,
+                       const double* T_wl16, float leaf_corner, float leaf_surf, int* n_corner_map, int* n_surf_map);
+/* current local map of one kind (0 corner / 1 surf); out_xyzi may be NULL to query the size only                  */
+int mml_local_map_get(mml_ctx* ctx, int kind, float* out_xyzi, int cap, int* n_out);
+int mml_local_map_reset(mml_ctx* ctx);
+
 /* ---- device-resident building blocks used by bench.py's roofline sweep (S4):
  * queries and maps stay in HBM; one call = one association or one evaluation.          */
 int mml_frame_set(mml_ctx* ctx, const float* corner_xyzi, int n_corner, const float* surf_xyzi, int n_surf);

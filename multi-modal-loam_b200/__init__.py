@@ -34,7 +34,7 @@ EXPORTS = [
     "mml_voxel_downsample", "mml_map_set", "mml_associate", "mml_accumulate", "mml_est_params_default",
     "mml_estimate", "mml_scan_to_pose", "mml_scan_to_pose_dev", "mml_frame_set", "mml_frame_associate",
     "mml_frame_accumulate", "mml_frame_associate_async", "mml_frame_associate_kind_async", "mml_frame_accumulate_async",
-    "mml_odom_run", "mml_timer_start",
+    "mml_odom_run", "mml_local_map_push", "mml_local_map_get", "mml_local_map_reset", "mml_timer_start",
     "mml_timer_stop_ms", "mml_frame_accumulate_partial_dev", "mml_stream_handle",
 ]
 
@@ -347,6 +347,28 @@ class Context:
                                        _p(ex), C.c_float(leaf_corner), C.c_float(leaf_surf), C.byref(prm), _p(poses),
                                        C.byref(ms), _p(counts)))
         return poses[:k].reshape(k, 4, 4), ms.value, counts[:k]
+
+    # ---- local feature map on the device (Estimator::MapIncrementLocal, EST.cpp:1585-1643)
+    def local_map_push(self, corner, surf, T_wl, leaf_corner=0.4, leaf_surf=0.2):
+        """One map update from a frame's corner / surf clouds (LiDAR frame) and its pose. Returns the sizes of the new
+        local corner / surf maps; the association searches them from now on (map kinds 2 / 3)."""
+        corner = np.ascontiguousarray(corner, np.float32).reshape(-1, 4)
+        surf = np.ascontiguousarray(surf, np.float32).reshape(-1, 4)
+        T = _f64(T_wl).reshape(16)
+        nc, ns = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.mml_local_map_push(self.h, _p(corner), int(corner.shape[0]), _p(surf), int(surf.shape[0]), _p(T),
+                                             C.c_float(leaf_corner), C.c_float(leaf_surf), C.byref(nc), C.byref(ns)))
+        return nc.value, ns.value
+
+    def local_map_get(self, kind):
+        n = C.c_int(0)
+        self._ck(self.lib.mml_local_map_get(self.h, int(kind), None, 0, C.byref(n)))
+        out = np.zeros((max(n.value, 1), 4), np.float32)
+        self._ck(self.lib.mml_local_map_get(self.h, int(kind), _p(out), int(out.shape[0]), C.byref(n)))
+        return out[: n.value].copy()
+
+    def local_map_reset(self):
+        self._ck(self.lib.mml_local_map_reset(self.h))
 
     # ---- device-resident scans (bench.py)
     def dev_upload(self, arr):

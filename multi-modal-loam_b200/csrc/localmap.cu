@@ -1,0 +1,155 @@
+// Device-side local feature map: Estimator::MapIncrementLocal (src/lio/Estimator.cpp:1585-1643), the first of the
+// "next" rows of SURVEY.md §8 (f) F1. The last 50 frames' corner / surf clouds are kept in the world frame in HBM;
+// an update transforms the new frame (MAP_MANAGER::pointAssociateToMap, MM.cpp:75-89), concatenates the previous
+// filtered map and the 50 ring entries (EST.cpp:1620-1624: the previous result is NOT cleared first), runs the voxel
+// filter (EST.cpp:1630-1635, pcl::VoxelGrid restated in geometry.cu) and rebuilds the spatial hash of the local map
+// kind - the map the association searches never leaves the device and is never re-uploaded.
+// Checked against the CPU restatement in tests/test_gpu_parity.py::test_local_map_increment_matches_oracle.
+#include "common.cuh"
+
+int mml_voxel_device(mml_ctx* ctx, const float4* pts_d, const int* n_dev, int n_max, float leaf, float4* out_d, int* m_dev);
+int mml_map_set_device(mml_ctx* ctx, int kind, const float4* pts_d, int m, const int* cen3, float cell_hint);
+
+namespace {
+
+constexpr int kLocalWindow = 50;  // localMapWindowSize, include/Estimator/Estimator.h:326
+
+struct Pose16 { double T[16]; };
+
+// p_w = R p + t in float64, summed left to right, rounded to float32 (MM.cpp:75-89); intensity kept
+__global__ void __launch_bounds__(256) k_point_to_map(const float4* __restrict__ in, int n, Pose16 P, float4* __restrict__ out) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = in[i];
+  const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
+  float4 o;
+  o.x = (float)(((P.T[0] * x + P.T[1] * y) + P.T[2] * z) + P.T[3]);
+  o.y = (float)(((P.T[4] * x + P.T[5] * y) + P.T[6] * z) + P.T[7]);
+  o.z = (float)(((P.T[8] * x + P.T[9] * y) + P.T[10] * z) + P.T[11]);
+  o.w = p.w;
+  out[i] = o;
+}
+
+struct LocalMapDev {
+  mml::DevBuf ring[2][kLocalWindow];
+  int ring_n[2][kLocalWindow];
+  mml::DevBuf from_local[2];
+  int from_n[2] = {0, 0};
+  mml::DevBuf stage, concat, out, cnt;
+  long long id = 0;  // localMapID
+  LocalMapDev() { memset(ring_n, 0, sizeof(ring_n)); }
+};
+
+LocalMapDev* get(mml_ctx* c) {
+  if (!c->local_map) c->local_map = new LocalMapDev();
+  return static_cast<LocalMapDev*>(c->local_map);
+}
+
+}  // namespace
+
+void mml_local_map_destroy(mml_ctx* c) {
+  if (!c->local_map) return;
+  LocalMapDev* L = static_cast<LocalMapDev*>(c->local_map);
+  for (int k = 0; k < 2; k++) {
+    for (int i = 0; i < kLocalWindow; i++) L->ring[k][i].release();
+    L->from_local[k].release();
+  }
+  L->stage.release(); L->concat.release(); L->out.release(); L->cnt.release();
+  delete L;
+  c->local_map = nullptr;
+}
+
+extern "C" {
+
+int mml_local_map_reset(mml_ctx* c) {
+  if (!c) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  MML_CUDA(c, cudaStreamSynchronize(c->stream));
+  mml_local_map_destroy(c);
+  return MML_OK;
+}
+
+// One MapIncrementLocal. corner / surf: the frame's (down-sampled) feature clouds in the LiDAR frame, T_wl16 the
+// LiDAR-to-world transform (transformTobeMapped). On return the local corner / surf maps (kinds 2 / 3) are the new
+// filtered clouds; n_corner_map / n_surf_map (may be NULL) receive their sizes.
+int mml_local_map_push(mml_ctx* c, const float* corner_xyzi, int n_corner, const float* surf_xyzi, int n_surf, const double* T_wl16,
+                       float leaf_corner, float leaf_surf, int* n_corner_map, int* n_surf_map) {
+  if (!c || !T_wl16 || n_corner < 0 || n_surf < 0 || (n_corner && !corner_xyzi) || (n_surf && !surf_xyzi) || !(leaf_corner > 0.f) ||
+      !(leaf_surf > 0.f))
+    return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  cudaStream_t st = c->stream;
+  LocalMapDev* L = get(c);
+  const int slot = (int)(L->id % kLocalWindow);  // EST.cpp:1597
+  Pose16 P;
+  for (int i = 0; i < 16; i++) P.T[i] = T_wl16[i];
+  MML_CUDA(c, L->cnt.reserve(64));
+  for (int k = 0; k < 2; k++) {
+    const float* src = k == 0 ? corner_xyzi : surf_xyzi;
+    const int n = k == 0 ? n_corner : n_surf;
+    const float leaf = k == 0 ? leaf_corner : leaf_surf;
+    // new frame -> world frame -> ring slot (EST.cpp:1600-1612)
+    if (n > 0) {
+      MML_CUDA(c, L->stage.reserve(sizeof(float4) * (size_t)n));
+      MML_CUDA(c, L->ring[k][slot].reserve(sizeof(float4) * (size_t)n));
+      MML_CUDA(c, cudaMemcpyAsync(L->stage.p, src, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
+      k_point_to_map<<<div_up(n, 256), 256, 0, st>>>(L->stage.as<float4>(), n, P, L->ring[k][slot].as<float4>());
+      MML_LAUNCHED(c);
+    }
+    L->ring_n[k][slot] = n;
+    // previous filtered map + the 50 ring entries, in that order (EST.cpp:1620-1624)
+    long long total = L->from_n[k];
+    for (int i = 0; i < kLocalWindow; i++) total += L->ring_n[k][i];
+    if (total > 0x7fffffffLL / 32) return mml_fail(c, MML_ERR_CAPACITY, "local map too large");
+    int m = 0;
+    if (total > 0) {
+      MML_CUDA(c, L->concat.reserve(sizeof(float4) * (size_t)total));
+      MML_CUDA(c, L->out.reserve(sizeof(float4) * (size_t)total));
+      float4* dst = L->concat.as<float4>();
+      size_t at = 0;
+      if (L->from_n[k]) {
+        MML_CUDA(c, cudaMemcpyAsync(dst, L->from_local[k].p, sizeof(float4) * (size_t)L->from_n[k], cudaMemcpyDeviceToDevice, st));
+        at += (size_t)L->from_n[k];
+      }
+      for (int i = 0; i < kLocalWindow; i++) {
+        if (!L->ring_n[k][i]) continue;
+        MML_CUDA(c, cudaMemcpyAsync(dst + at, L->ring[k][i].p, sizeof(float4) * (size_t)L->ring_n[k][i], cudaMemcpyDeviceToDevice, st));
+        at += (size_t)L->ring_n[k][i];
+      }
+      // voxel filter (EST.cpp:1630-1635)
+      int* cnt = L->cnt.as<int>();
+      const int tot = (int)total;
+      MML_CUDA(c, cudaMemcpyAsync(cnt, &tot, sizeof(int), cudaMemcpyHostToDevice, st));
+      MML_CHECK(mml_voxel_device(c, dst, cnt, tot, leaf, L->out.as<float4>(), cnt + 1));
+      MML_CUDA(c, cudaMemcpyAsync(&m, cnt + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+      MML_CUDA(c, cudaStreamSynchronize(st));
+      MML_CUDA(c, L->from_local[k].reserve(sizeof(float4) * (size_t)(m > 0 ? m : 1)));
+      if (m > 0) MML_CUDA(c, cudaMemcpyAsync(L->from_local[k].p, L->out.p, sizeof(float4) * (size_t)m, cudaMemcpyDeviceToDevice, st));
+    }
+    L->from_n[k] = m;
+    // the association's search structure for this kind (replaces the kd-tree rebuild at EST.cpp:1159-1167)
+    MML_CHECK(mml_map_set_device(c, k == 0 ? MML_MAP_CORNER_LOCAL : MML_MAP_SURF_LOCAL, L->from_local[k].as<float4>(), m, nullptr, 0.f));
+    if (k == 0 && n_corner_map) *n_corner_map = m;
+    if (k == 1 && n_surf_map) *n_surf_map = m;
+  }
+  MML_CUDA(c, cudaStreamSynchronize(st));
+  L->id++;  // EST.cpp:1640
+  return MML_OK;
+}
+
+// Copy of the current local map of one kind (0 corner / 1 surf): out has room for cap points; *n_out = its size.
+int mml_local_map_get(mml_ctx* c, int kind, float* out_xyzi, int cap, int* n_out) {
+  if (!c || kind < 0 || kind > 1 || !n_out) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  LocalMapDev* L = get(c);
+  *n_out = L->from_n[kind];
+  if (!out_xyzi) return MML_OK;
+  if (cap < L->from_n[kind]) return mml_fail(c, MML_ERR_CAPACITY, "output buffer too small for the local map");
+  if (L->from_n[kind]) {
+    MML_CUDA(c, cudaMemcpyAsync(out_xyzi, L->from_local[kind].p, sizeof(float4) * (size_t)L->from_n[kind], cudaMemcpyDeviceToHost, c->stream));
+    MML_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return MML_OK;
+}
+
+}  // extern "C"

@@ -505,6 +505,41 @@ def test_odometry_loop_many_labelled_points(ctx, mm, orc, synth, scene):
     assert cnt_a[0][3] == orc.voxel_downsample(x0[label == 2], 0.2).shape[0]
 
 
+def test_local_map_increment_matches_oracle(ctx, mm, orc, synth, scene):
+    """Device-side MapIncrementLocal (SURVEY §8 f, F1) against oracle/map_maintenance.py: three updates from moving
+    poses must give bit-identical local corner / surf maps, and the association must search the pushed map."""
+    from oracle import map_maintenance as mmt
+    rng = np.random.default_rng(11)
+    lm = mmt.LocalMap()
+    ctx.local_map_reset()
+    surf_all = scene["map_surf"]
+    corner_all = scene["map_corner"]
+    for k in range(3):
+        T = synth.make_T(synth.rot_z(0.05 * k), np.array([0.3 * k, -0.1 * k, 0.02 * k]))
+        Ti = np.linalg.inv(T)
+        # a frame = a random part of the scene seen from pose T (LiDAR frame), plus range noise
+        s = surf_all[rng.choice(surf_all.shape[0], 6000, replace=False)].copy()
+        c = corner_all[rng.choice(corner_all.shape[0], 500, replace=False)].copy()
+        for cloud in (s, c):
+            cloud[:, :3] = (cloud[:, :3].astype(np.float64) @ Ti[:3, :3].T + Ti[:3, 3]).astype(np.float32)
+            cloud[:, :3] += rng.normal(0, 0.01, size=cloud[:, :3].shape).astype(np.float32)
+        oc, os_ = lm.increment(c, s, T)
+        nc, ns = ctx.local_map_push(c, s, T)
+        assert (nc, ns) == (oc.shape[0], os_.shape[0])
+        assert np.array_equal(ctx.local_map_get(0), oc) and np.array_equal(ctx.local_map_get(1), os_)
+    # the association now runs against the pushed maps (kinds 2 / 3), like against the same clouds set explicitly
+    ctx.map_set(mm.MAP_CORNER_GLOBAL, np.zeros((0, 4), np.float32)); ctx.map_set(mm.MAP_SURF_GLOBAL, np.zeros((0, 4), np.float32))
+    om = orc.Map()
+    om.set(orc.SURF_LOCAL, os_); om.set(orc.CORNER_LOCAL, oc)
+    corner_q, surf_q = _assoc_inputs(orc, scene)
+    Tq = scene["T_true"] @ synth.s1_offset_pose()
+    fp, np_, _, _ = ctx.associate(1, surf_q, Tq, 1.0)
+    rp, rnp, _, _ = om.associate_plane(surf_q, Tq, 1.0)
+    assert np_ == rnp and np_ > 100
+    _cmp_features(fp, rp, 1)
+    ctx.local_map_reset()
+
+
 def test_large_query_set_is_sorted_but_slots_keep_caller_order(ctx, mm, orc, synth):
     """Query sets above 32768 are Morton-sorted on the device; feature slot i must still belong to query i."""
     ms, mc = synth.feature_map(200_000, 2_000, seed=9)

@@ -1,6 +1,7 @@
 // Compile-and-link check of the C++ adapters (build()), and a small GPU run (tests, -m gpu):
-//   host_check <n_az>   extracts features of a synthetic ring through
-//   LidarFeatureExtractor::detectFeaturePoint and prints the index lists.
+//   host_check <n_az>       extracts features of a synthetic ring through
+//                           LidarFeatureExtractor::detectFeaturePoint and prints the index lists;
+//   host_check <n_az> map   additionally runs Estimator::MapIncrementLocal on the ring.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -30,6 +31,14 @@ int main(int argc, char** argv) {
     std::printf("\nflat %zu:", flat.size());
     for (int v : flat) std::printf(" %d", v);
     std::printf("\n");
+    if (argc > 2) {  // host_check <n> map: also the Estimator adapter's map update (the ring doubles as both clouds)
+      mmloam::Estimator est(ctx, 0.4f, 0.2f);
+      const double I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+      est.MapIncrementLocal(line, line, I16);
+      int n_surf_map = 0;
+      ctx.check(mml_local_map_get(ctx.get(), 1, nullptr, 0, &n_surf_map));
+      std::printf("local surf map %d\n", n_surf_map);
+    }
   } catch (const std::exception& e) {
     std::fprintf(stderr, "%s\n", e.what());
     return 2;

@@ -142,6 +142,17 @@ class Estimator {
     ctx_.check(mml_map_set(ctx_.get(), kind, xyzi.data(), (int)cloud.size(), cube_centre3));
   }
 
+  // Estimator::MapIncrementLocal (EST.cpp:1585-1643; the non-feature cloud is not on the window-1 path): ring of
+  // the last 50 frames, concatenation with the previous filtered map, voxel filter and rebuild of the local maps'
+  // search structure on the device. transformTobeMapped = T_wl row-major.
+  template <class Cloud>
+  void MapIncrementLocal(const Cloud& laserCloudCornerStack, const Cloud& laserCloudSurfStack, const double* transformTobeMapped) {
+    std::vector<float> c = to_xyzi(laserCloudCornerStack), s = to_xyzi(laserCloudSurfStack);
+    ctx_.check(mml_local_map_push(ctx_.get(), c.data(), (int)laserCloudCornerStack.size(), s.data(),
+                                  (int)laserCloudSurfStack.size(), transformTobeMapped, filter_corner_, filter_surf_, nullptr,
+                                  nullptr));
+  }
+
   // EST.h:159-165. m4d = T_wl row-major.
   template <class Cloud>
   void processPointToLine(std::vector<FeatureLine>& vLineFeatures, const Cloud& laserCloudCorner, const double* m4d) {

@@ -448,6 +448,12 @@ class Estimator:
         self.ctx.map_set(MAP_CORNER_GLOBAL, corner_xyzi, cen)
         self.ctx.map_set(MAP_SURF_GLOBAL, surf_xyzi, cen)
 
+    def MapIncrementLocal(self, laserCloudCornerStack, laserCloudSurfStack, transformTobeMapped):
+        """EST.cpp:1585-1643 (corner and surf clouds): the frame joins the 50-frame ring, the previous filtered map and
+        the ring are voxel-filtered again and become the local maps the association searches. Returns their sizes."""
+        return self.ctx.local_map_push(laserCloudCornerStack, laserCloudSurfStack, transformTobeMapped, self.filter_corner,
+                                       self.filter_surf)
+
     def processPointToLine(self, laserCloudCorner, m4d):
         """EST.h:159-165. Returns the FeatureLine records (12 doubles each, see mmloam_b200.h)."""
         feat, n, _, _ = self.ctx.associate(0, laserCloudCorner, m4d, self.thres_dist)

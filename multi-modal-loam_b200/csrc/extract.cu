@@ -43,8 +43,14 @@ constexpr int kChunkPts = 1024;
 constexpr int kMaxLines = 64;
 
 struct V3d { double x, y, z; };
+// Vector3d - Vector3d of widened points (FE.cpp:417-422): float64 subtraction.
 __device__ __forceinline__ V3d vsub(const float4& a, const float4& b) {
   return {(double)a.x - (double)b.x, (double)a.y - (double)b.y, (double)a.z - (double)b.z};
+}
+// Eigen::Vector3d(a.x - b.x, ...) (FE.cpp:618-620, 625-627, 635-640, 680-682, 717-719, 772-774, 790-792):
+// float32 subtraction, widened afterwards (-fmad=false keeps the subtraction a plain FSUB).
+__device__ __forceinline__ V3d vsubf(const float4& a, const float4& b) {
+  return {(double)(a.x - b.x), (double)(a.y - b.y), (double)(a.z - b.z)};
 }
 __device__ __forceinline__ double vdot(const V3d& a, const V3d& b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 __device__ __forceinline__ double vnorm(const V3d& a) { return sqrt(vdot(a, a)); }
@@ -268,21 +274,21 @@ __global__ void __launch_bounds__(256) k_point_attr(const float4* __restrict__ P
         const float4 R[4] = {pp1, pp2, pp3, pp4};
 #pragma unroll
         for (int k = 1; k < 5; k++) {
-          V3d t = vsub(L[k - 1], pi);
+          V3d t = vsubf(L[k - 1], pi);
           vnormalize(t);
           double wk = k / 10.0;
           nl.x += wk * t.x; nl.y += wk * t.y; nl.z += wk * t.z;
         }
 #pragma unroll
         for (int k = 1; k < 5; k++) {
-          V3d t = vsub(R[k - 1], pi);
+          V3d t = vsubf(R[k - 1], pi);
           vnormalize(t);
           double wk = k / 10.0;
           nr.x += wk * t.x; nr.y += wk * t.y; nr.z += wk * t.z;
         }
         double cc = fabs(vdot(nl, nr) / (vnorm(nl) * vnorm(nr)));
-        double last_dis = vnorm(vsub(pm4, pi));
-        double current_dis = vnorm(vsub(pp4, pi));
+        double last_dis = vnorm(vsubf(pm4, pi));
+        double current_dis = vnorm(vsubf(pp4, pi));
         if (cc < 0.5 && last_dis > 0.05 && current_dis > 0.05) a |= A_C150;
       }
     }
@@ -296,14 +302,14 @@ __global__ void __launch_bounds__(256) k_point_attr(const float4* __restrict__ P
       bool f100 = false;
       if (fabsf(diff_right - diff_left) > 1.0f) {
         if (diff_right > diff_left) {
-          V3d sv = vsub(pm1, pi);
+          V3d sv = vsubf(pm1, pi);
           double cc = fabs(vdot(sv, cur) / (vnorm(sv) * vnorm(cur)));
           if (cc < 0.95) {
             if (depth_right > depth_left) f100 = true;
             else if (depth_right == 0.f) f100 = true;
           }
         } else {
-          V3d sv = vsub(pp1, pi);
+          V3d sv = vsubf(pp1, pi);
           double cc = fabs(vdot(sv, cur) / (vnorm(sv) * vnorm(cur)));
           if (cc < 0.95) {
             if (depth_right < depth_left) f100 = true;
@@ -318,7 +324,7 @@ __global__ void __launch_bounds__(256) k_point_attr(const float4* __restrict__ P
 #pragma unroll
         for (int k = 1; k < 4; k++) {
           if (range3(L[k - 1]) < 1.0f) continue;
-          V3d t = vsub(L[k - 1], pi);
+          V3d t = vsubf(L[k - 1], pi);
           vnormalize(t);
           double wk = k / 6.0;
           nf.x += wk * t.x; nf.y += wk * t.y; nf.z += wk * t.z;
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(256) k_point_attr(const float4* __restrict__ P
 #pragma unroll
         for (int k = 1; k < 4; k++) {
           if (range3(L[k - 1]) < 1.0f) continue;  // sic, FE.cpp:782 tests i-k for the back side too
-          V3d t = vsub(R[k - 1], pi);
+          V3d t = vsubf(R[k - 1], pi);
           vnormalize(t);
           double wk = k / 6.0;
           nb.x += wk * t.x; nb.y += wk * t.y; nb.z += wk * t.z;

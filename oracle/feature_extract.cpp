@@ -12,8 +12,8 @@
 //   * work arrays are sized to n (the reference overflows at 20000).
 //   * inputs must be finite; non-finite points are compacted away and indices
 //     are reported in the compacted numbering exactly as the reference does.
-// Arithmetic: float32 where the reference uses float, float64 where it uses
-// Eigen::Vector3d; no FMA contraction (build with -ffp-contract=off, matching
+// Arithmetic: float32 where the reference uses float (including the float32 differences it
+// feeds into Eigen::Vector3d constructors), float64 where it operates on Eigen::Vector3d; no FMA contraction (build with -ffp-contract=off, matching
 // the reference's baseline x86-64 Release build, mm-loam/CMakeLists.txt:4-5).
 // Eigen 3.3 reduces a fixed 3-vector dot/squaredNorm as (e0+e1)+e2.
 #include "oracle.h"
@@ -29,8 +29,14 @@ struct P4 { float x, y, z, i; };
 struct V3 {
   double x, y, z;
 };
+// Vector3d - Vector3d of points widened first (FE.cpp:417-422): float64 subtraction.
 inline V3 sub(const P4& a, const P4& b) {
   return {(double)a.x - (double)b.x, (double)a.y - (double)b.y, (double)a.z - (double)b.z};
+}
+// Eigen::Vector3d(a.x - b.x, a.y - b.y, a.z - b.z) (FE.cpp:618-620, 625-627, 635-640, 680-682,
+// 717-719, 772-774, 790-792): the subtraction is float32, the result is widened afterwards.
+inline V3 subf(const P4& a, const P4& b) {
+  return {(double)(a.x - b.x), (double)(a.y - b.y), (double)(a.z - b.z)};
 }
 inline double dot(const V3& a, const V3& b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 inline double norm(const V3& a) { return std::sqrt(dot(a, a)); }
@@ -186,20 +192,20 @@ void detect_line(const P4* in, int n_in, std::vector<int>& sharp, std::vector<in
     if (left_surf_flag && right_surf_flag) {
       V3 nl = {0, 0, 0}, nr = {0, 0, 0};
       for (int k = 1; k < 5; k++) {
-        V3 t = sub(p[i - k], p[i]);
+        V3 t = subf(p[i - k], p[i]);
         normalize(t);
         double w = k / 10.0;
         nl.x += w * t.x; nl.y += w * t.y; nl.z += w * t.z;
       }
       for (int k = 1; k < 5; k++) {
-        V3 t = sub(p[i + k], p[i]);
+        V3 t = subf(p[i + k], p[i]);
         normalize(t);
         double w = k / 10.0;
         nr.x += w * t.x; nr.y += w * t.y; nr.z += w * t.z;
       }
       double cc = std::fabs(dot(nl, nr) / (norm(nl) * norm(nr)));
-      double last_dis = norm(sub(p[i - 4], p[i]));
-      double current_dis = norm(sub(p[i + 4], p[i]));
+      double last_dis = norm(subf(p[i - 4], p[i]));
+      double current_dis = norm(subf(p[i + 4], p[i]));
       if (cc < 0.5 && last_dis > 0.05 && current_dis > 0.05) flag[i] = 150;
     }
   }
@@ -219,14 +225,14 @@ void detect_line(const P4* in, int n_in, std::vector<int>& sharp, std::vector<in
     if (std::fabs(diff_right[0] - diff_left[0]) > thBreakCornerDis) {
       V3 lidar_vector = {(double)p[i].x, (double)p[i].y, (double)p[i].z};
       if (diff_right[0] > diff_left[0]) {
-        V3 surf_vector = sub(p[i - 1], p[i]);
+        V3 surf_vector = subf(p[i - 1], p[i]);
         double cc = std::fabs(dot(surf_vector, lidar_vector) / (norm(surf_vector) * norm(lidar_vector)));
         if (cc < 0.95) {
           if (depth_right > depth_left) flag[i] = 100;
           else if (depth_right == 0) flag[i] = 100;
         }
       } else {
-        V3 surf_vector = sub(p[i + 1], p[i]);
+        V3 surf_vector = subf(p[i + 1], p[i]);
         double cc = std::fabs(dot(surf_vector, lidar_vector) / (norm(surf_vector) * norm(lidar_vector)));
         if (cc < 0.95) {
           if (depth_right < depth_left) flag[i] = 100;
@@ -241,7 +247,7 @@ void detect_line(const P4* in, int n_in, std::vector<int>& sharp, std::vector<in
       for (int k = 1; k < 4; k++) {
         float temp_depth = range3(p[i - k]);
         if (temp_depth < 1) continue;
-        V3 t = sub(p[i - k], p[i]);
+        V3 t = subf(p[i - k], p[i]);
         normalize(t);
         double w = k / 6.0;
         nf.x += w * t.x; nf.y += w * t.y; nf.z += w * t.z;
@@ -249,7 +255,7 @@ void detect_line(const P4* in, int n_in, std::vector<int>& sharp, std::vector<in
       for (int k = 1; k < 4; k++) {
         float temp_depth = range3(p[i - k]);  // sic: the reference tests i-k here too (FE.cpp:782)
         if (temp_depth < 1) continue;
-        V3 t = sub(p[i + k], p[i]);
+        V3 t = subf(p[i + k], p[i]);
         normalize(t);
         double w = k / 6.0;
         nb.x += w * t.x; nb.y += w * t.y; nb.z += w * t.z;

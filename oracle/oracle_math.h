@@ -4,6 +4,7 @@
 #define MMLOAM_ORACLE_MATH_H
 #include <algorithm>
 #include <cmath>
+#include <vector>
 
 namespace orc {
 
@@ -237,10 +238,11 @@ inline void qr5x3_solve(const double A_in[5][3], const double b_in[5], double x[
   for (int k = 0; k < 3; k++) x[perm[k]] = (k < rank) ? y[k] : 0.0;
 }
 
-// Dense symmetric positive-definite solve (Cholesky), n <= 64. Returns false when the
+// Dense symmetric positive-definite solve (Cholesky). Returns false when the
 // factorisation meets a non-positive pivot.
 inline bool chol_solve(int n, const double* A, const double* b, double* x) {
-  double L[64 * 64];
+  std::vector<double> Lv((size_t)n * n), yv(n);
+  double* L = Lv.data();
   for (int i = 0; i < n; i++)
     for (int j = 0; j <= i; j++) {
       double s = A[i * n + j];
@@ -251,7 +253,7 @@ inline bool chol_solve(int n, const double* A, const double* b, double* x) {
       } else
         L[i * n + j] = s / L[j * n + j];
     }
-  double y[64];
+  double* y = yv.data();
   for (int i = 0; i < n; i++) {
     double s = b[i];
     for (int k = 0; k < i; k++) s -= L[i * n + k] * y[k];

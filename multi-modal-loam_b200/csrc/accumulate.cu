@@ -147,8 +147,13 @@ __device__ __forceinline__ void eval_line(const PoseLin& L, const double* p, con
 }
 
 // point-to-plane (vector form) residual + Jacobian + Huber, CF.h:533-555
-__device__ __forceinline__ void eval_plane(const PoseLin& L, const double* p, const double* pp, const double* n, double s_info,
+__device__ __forceinline__ void eval_plane(const PoseLin& L, const double* p, const double* pp, const double* n_f32, double s_info,
                                            double w_tan, double ha, double* acc) {
+  // The factor's direction is the UNIT vector along the float32 normal: sqrt_info = info * (V U^T)^T from
+  // JacobiSVD(e1 n^T) (EST.cpp:675-682) keeps the singular vector and drops the singular value |n| = 1 +- 6e-8.
+  // (p_proj keeps the float32 normal as it is, EST.cpp:672-673.)
+  const double inv_nn = rsqrt64(n_f32[0] * n_f32[0] + n_f32[1] * n_f32[1] + n_f32[2] * n_f32[2]);
+  const double n[3] = {n_f32[0] * inv_nn, n_f32[1] * inv_nn, n_f32[2] * inv_nn};
   double u[3], P[3];
   for (int r = 0; r < 3; r++) u[r] = L.Rbl[3 * r] * p[0] + L.Rbl[3 * r + 1] * p[1] + L.Rbl[3 * r + 2] * p[2] + L.Pbl[r];
   for (int r = 0; r < 3; r++) P[r] = L.R[3 * r] * u[0] + L.R[3 * r + 1] * u[1] + L.R[3 * r + 2] * u[2] + L.t[r];

@@ -5,7 +5,8 @@
 //                          ResidualBlockInfo::Evaluate             include/utils/ceresfunc.h:33-63
 // Ceres evaluates the Jacobians by automatic differentiation of those functors; the
 // oracle uses the closed-form derivatives of the same expressions (checked against
-// central finite differences in tests/test_oracle_residual.py).
+// central finite differences in tests/test_oracle.py and against the reference's functors under
+// dual-number autodiff in tests/test_ref_pin.py).
 //
 // Parameterisation (EST.cpp:937-950, 1227-1229): x = [t_wb (3), phi (3)], R_wb = Exp(phi),
 // plain 6-vector update (no manifold). P_map = R_wb (R_bl p + P_bl) + t_wb (CF.h:418-423).
@@ -140,7 +141,11 @@ void plane_basis(const double* n, double* t1, double* t2) {
 
 // CF.h:545-552. feat = [p(3) p_proj(3) n(3) ...]. 3 residuals, J 3x6 (row-major).
 void plane_residual(const PoseLin& L, const double* f, double s_info, double w_tan, double* r, double* J) {
-  const double *p = f, *pp = f + 3, *n = f + 6;
+  const double *p = f, *pp = f + 3, *n_f32 = f + 6;
+  // sqrt_info = info * (V U^T)^T with JacobiSVD(e1 n^T) (EST.cpp:675-682): the factor's direction is the unit
+  // singular vector n / |n| in float64; the singular value |n| (1 +- 6e-8 for the float32 normal) is dropped.
+  const double nn = std::sqrt((n_f32[0] * n_f32[0] + n_f32[1] * n_f32[1]) + n_f32[2] * n_f32[2]);
+  const double n[3] = {n_f32[0] / nn, n_f32[1] / nn, n_f32[2] / nn};
   double P[3], JP[18];
   map_point(L, p, P, J ? JP : nullptr);
   double e[3] = {P[0] - pp[0], P[1] - pp[1], P[2] - pp[2]};

@@ -85,7 +85,8 @@ def test_cube_map_bins_filters_and_reports_touched_cubes(orc):
     cm = mmt.CubeMap()
     near = _cloud(rng, 250, -20, 20)          # centre cube only, below the 300-point threshold
     c, s = cm.increment(near[:20], near)
-    centre = int(mmt.cube_index(np.zeros((1, 3), np.float32))[0])
+    centre = (10, 10, 5)                      # (i, j, k) of the cube around the origin with the initial centre
+    assert mmt.CubeMap._to_index(*centre) == int(mmt.cube_index(np.zeros((1, 3), np.float32))[0])
     assert set(cm.cubes[1]) == {centre} and np.array_equal(s, near)  # not filtered yet: order of arrival kept
     more = _cloud(rng, 200, -20, 20)
     far = _cloud(rng, 50, 30, 70)              # cube (+1, +1, +1)
@@ -93,7 +94,7 @@ def test_cube_map_bins_filters_and_reports_touched_cubes(orc):
     out = _cloud(rng, 5, 600, 700)             # outside the grid: dropped (MM.cpp:168-175)
     _, s = cm.increment(near[:0], np.concatenate([more, far, out]))
     assert len(cm.cubes[1]) == 2
-    filtered = orc.voxel_downsample(np.concatenate([near, more]), 0.2)
+    filtered = orc.voxel_downsample(np.concatenate([near, more]), 0.4)   # MM.cpp:56-58: leaf 0.4 for every kind
     assert np.array_equal(cm.cubes[1][centre], filtered)            # 450 > 300: filtered in place
     other = [k for k in cm.cubes[1] if k != centre][0]
     assert np.array_equal(cm.cubes[1][other], far)                  # 50 points: kept as they arrived

@@ -295,3 +295,26 @@ def trajectory(n_frames, v=0.5, yaw_rate=0.2, dt=0.1, start=(-3.0, -1.0, 0.0)):
             y += -v / yaw_rate * (np.cos(yaw + yaw_rate * dt) - np.cos(yaw))
         yaw += yaw_rate * dt
     return Ts
+
+
+def imu_stream(n_frames, v=0.5, yaw_rate=0.2, dt=0.1, rate_hz=200.0, seed=1003, gyr_sigma=0.004, acc_sigma=0.08,
+               gnorm=9.805):
+    """S3: 200 Hz IMU samples for the constant-twist `trajectory` (body frame = IMU = LiDAR frame when the extrinsic
+    is the identity). Returns per frame k = 1..n_frames a tuple (t [m], gyr [m,3] rad/s, acc [m,3] in units of g) holding
+    the samples of (t_{k-1}, t_k], plus the frame stamps t_k (frame 0 at t = 0). Specific force of the unicycle:
+    (0, v * yaw_rate, g) in the body frame; white noise with the densities of IMUIntegrator.h:79-82."""
+    rng = np.random.default_rng(seed)
+    per = int(round(rate_hz * dt))
+    stamps = np.arange(n_frames + 1) * dt
+    out = [(np.zeros(0), np.zeros((0, 3)), np.zeros((0, 3)))]
+    for k in range(1, n_frames + 1):
+        t = stamps[k - 1] + (np.arange(per) + 1) * (dt / per)
+        gyr = np.tile(np.array([0.0, 0.0, yaw_rate]), (per, 1)) + rng.normal(0, gyr_sigma, (per, 3))
+        acc = (np.tile(np.array([0.0, v * yaw_rate, gnorm]), (per, 1)) + rng.normal(0, acc_sigma, (per, 3))) / gnorm
+        out.append((t, gyr, acc))
+    return out, stamps
+
+
+def body_velocity_world(T_wb, v=0.5):
+    """World-frame velocity of the unicycle at pose T_wb."""
+    return T_wb[:3, :3] @ np.array([v, 0.0, 0.0])

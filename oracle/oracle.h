@@ -98,7 +98,7 @@ int orc_residual(int kind, const double* feat12, const double* x6, const double*
 void orc_so3_exp(const double* phi3, double* q_wxyz4, double* R9);
 void orc_so3_log(const double* q_wxyz4, double* phi3);
 
-/* ---- A12: src/lio/Estimator.cpp:1143-1581, window size 1..4 (no IMU factor) */
+/* ---- A12: src/lio/Estimator.cpp:1143-1581, window size 1 (see orc_estimate_window for 2..4) */
 typedef struct {
   int    max_outer;        /* 5   EST.cpp:1210 */
   int    max_inner;        /* 10  EST.cpp:1428 */
@@ -115,6 +115,23 @@ void orc_est_params_default(orc_est_params*);
 int orc_estimate(const orc_map*, const float* corner_xyzi, int n_corner,
                  const float* surf_xyzi, int n_surf, const double* exTlb16,
                  double* P3, double* q_wxyz4, const orc_est_params*, double* stats);
+
+/* ---- sliding window (2 <= W <= 4: IMU factors, no marginalisation) ------------------------------ */
+/* IMUIntegrator::PreIntegration, src/lio/IMUIntegrator.cpp:105-166. t/gyr/acc: n samples (acc in g).
+ * preint_out: opaque block of orc_preint_size() bytes.                                                */
+int orc_preint_size(void);
+int orc_imu_preintegrate(const double* t, const double* gyr, const double* acc, int n, double last_time,
+                         const double* bg3, const double* ba3, void* preint_out);
+/* Cost_NavState_PRV_Bias (include/utils/ceresfunc.h:321-393) weighted by LLT(cov^-1).matrixL()^T
+ * (EST.cpp:1240-1242): r15 and J (15 x 30 row-major, columns [PR_i 6 | VBias_i 9 | PR_j 6 | VBias_j 9]). */
+int orc_imu_factor(const void* preint, const double* gravity3, const double* pri6, const double* vbi9,
+                   const double* prj6, const double* vbj9, double* r15, double* J450);
+/* pose prediction of process(), src/unionPoseEstimation.cpp:812-829. state = P3 q_wxyz4 V3 bg3 ba3.   */
+int orc_imu_predict(const double* prev16, const void* preint, double* next16);
+/* Estimator::Estimate for window sizes 1..4, src/lio/Estimator.cpp:1143-1581. states: W x 16, in place. */
+int orc_estimate_window(const orc_map*, int W, const float* const* corner, const int* n_corner,
+                        const float* const* surf, const int* n_surf, const double* exTlb16, double* states,
+                        const void* const* preints, const double* gravity3, const orc_est_params*, double* stats);
 
 #ifdef __cplusplus
 }

@@ -252,3 +252,58 @@ def so3_log(q):
     phi = np.zeros(3)
     lib().orc_so3_log(_p(q), _p(phi))
     return phi
+
+
+# ---- sliding window (IMU factors) -------------------------------------------------------------------
+class Preint:
+    """IMUIntegrator::PreIntegration result (opaque block + the fields tests look at)."""
+
+    def __init__(self, t, gyr, acc, last_time, bg=(0, 0, 0), ba=(0, 0, 0)):
+        t = _f64(t)
+        gyr = _f64(gyr).reshape(-1, 3)
+        acc = _f64(acc).reshape(-1, 3)
+        self.buf = np.zeros(lib().orc_preint_size() // 8, np.float64)
+        lib().orc_imu_preintegrate(_p(t), _p(gyr), _p(acc), t.shape[0], C.c_double(last_time), _p(_f64(bg)), _p(_f64(ba)),
+                                   _p(self.buf))
+
+    dq = property(lambda s: s.buf[0:4])
+    dp = property(lambda s: s.buf[4:7])
+    dv = property(lambda s: s.buf[7:10])
+    dt = property(lambda s: float(s.buf[10]))
+    cov = property(lambda s: s.buf[17:17 + 225].reshape(15, 15))
+    jac = property(lambda s: s.buf[17 + 225:17 + 450].reshape(15, 15))
+    sqrt_info = property(lambda s: s.buf[17 + 450:17 + 675].reshape(15, 15))
+
+
+def imu_factor(pre, gravity, pri, vbi, prj, vbj, jac=True):
+    r = np.zeros(15)
+    J = np.zeros((15, 30))
+    lib().orc_imu_factor(_p(pre.buf), _p(_f64(gravity)), _p(_f64(pri)), _p(_f64(vbi)), _p(_f64(prj)), _p(_f64(vbj)), _p(r),
+                         _p(J) if jac else None)
+    return r, J
+
+
+def imu_predict(prev16, pre):
+    out = np.zeros(16)
+    lib().orc_imu_predict(_p(_f64(prev16)), _p(pre.buf), _p(out))
+    return out
+
+
+def estimate_window(omap, corners, surfs, exTlb, states, preints, gravity=(0, 0, -9.805), params=None):
+    """Estimator::Estimate for a window of len(corners) frames. states: [W, 16] (P, q_wxyz, V, bg, ba), returned
+    updated. preints[f] links frame f-1 to f (preints[0] is ignored)."""
+    W = len(corners)
+    cs = [_f32(c).reshape(-1, 4) for c in corners]
+    ss = [_f32(s).reshape(-1, 4) for s in surfs]
+    cp = (C.c_void_p * W)(*[c.ctypes.data for c in cs])
+    sp = (C.c_void_p * W)(*[s.ctypes.data for s in ss])
+    nc = np.array([c.shape[0] for c in cs], np.int32)
+    ns = np.array([s.shape[0] for s in ss], np.int32)
+    pp = (C.c_void_p * W)(*[(p.buf.ctypes.data if p is not None else None) for p in preints])
+    st = _f64(states).reshape(W, 16).copy()
+    stats = np.zeros(16)
+    prm = params if params is not None else est_params()
+    rc = lib().orc_estimate_window(omap.h, W, cp, _p(nc), sp, _p(ns), _p(_f64(exTlb).reshape(16)), _p(st), pp,
+                                   _p(_f64(gravity)), C.byref(prm), _p(stats))
+    assert rc == 0
+    return st, stats

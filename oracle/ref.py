@@ -129,6 +129,31 @@ def residual(kind, feat, x6, T_bl, lidar_m=1.5e-3):
     return r[:n].copy(), J[: 6 * n].reshape(n, 6).copy()
 
 
+def imu_preintegrate(t, gyr, acc, last_time, bg=(0, 0, 0), ba=(0, 0, 0)):
+    """IMUIntegrator::PreIntegration (IMU.cpp:105-166). Returns dq(wxyz), dp, dv, dt, cov, jac."""
+    t = _f64(t)
+    gyr = _f64(gyr).reshape(-1, 3)
+    acc = _f64(acc).reshape(-1, 3)
+    out = np.zeros(11 + 450)
+    lib().ref_imu_preintegrate(_p(t), _p(gyr), _p(acc), t.shape[0], C.c_double(last_time), _p(_f64(bg)), _p(_f64(ba)), _p(out))
+    return out[0:4].copy(), out[4:7].copy(), out[7:10].copy(), float(out[10]), out[11:236].reshape(15, 15).copy(), \
+        out[236:461].reshape(15, 15).copy()
+
+
+def imu_factor(t, gyr, acc, last_time, bg, ba, gravity, pri, vbi, prj, vbj):
+    """Cost_NavState_PRV_Bias (CF.h:321-393) with the reference's sqrt_information (EST.cpp:1238-1242), residuals and
+    Jacobian (15 x 30, columns [PR_i | VBias_i | PR_j | VBias_j]) by dual-number autodiff."""
+    t = _f64(t)
+    gyr = _f64(gyr).reshape(-1, 3)
+    acc = _f64(acc).reshape(-1, 3)
+    r = np.zeros(15)
+    J = np.zeros((15, 30))
+    rc = lib().ref_imu_factor(_p(t), _p(gyr), _p(acc), t.shape[0], C.c_double(last_time), _p(_f64(bg)), _p(_f64(ba)),
+                              _p(_f64(gravity)), _p(_f64(pri)), _p(_f64(vbi)), _p(_f64(prj)), _p(_f64(vbj)), _p(r), _p(J))
+    assert rc == 0
+    return r, J
+
+
 class Estimator:
     """The reference's Estimator object (EST.h / EST.cpp verbatim) with its MAP_MANAGER."""
 
@@ -216,3 +241,19 @@ class Estimator:
         lib().ref_est_estimate_lidar_pose(self.h, _p(cloud7), cloud7.shape[0], _p(P), _p(q), _p(ex), lidar_mode,
                                           C.byref(fail))
         return P, q, bool(fail.value)
+
+    def estimate_window(self, clouds7, states, stamps, imu, exTlb=np.eye(4), gravity=(0, 0, -9.805), lidar_mode=2):
+        """EstimateLidarPose on W frames. clouds7: list of [n,7]; states [W,16]; stamps [W]; imu: list of
+        (t, gyr, acc) per frame (entry 0 unused)."""
+        W = len(clouds7)
+        cl = _f32(np.concatenate([np.asarray(c, np.float32).reshape(-1, 7) for c in clouds7]))
+        npts = np.array([len(c) for c in clouds7], np.int32)
+        st = _f64(states).reshape(W, 16).copy()
+        it = _f64(np.concatenate([np.asarray(i[0], float).ravel() for i in imu]))
+        ig = _f64(np.concatenate([np.asarray(i[1], float).reshape(-1, 3) for i in imu]))
+        ia = _f64(np.concatenate([np.asarray(i[2], float).reshape(-1, 3) for i in imu]))
+        inn = np.array([len(np.asarray(i[0]).ravel()) for i in imu], np.int32)
+        fail = C.c_int(0)
+        lib().ref_est_estimate_window(self.h, W, _p(cl), _p(npts), _p(st), _p(_f64(stamps)), _p(it), _p(ig), _p(ia), _p(inn),
+                                      _p(_f64(exTlb).reshape(16)), _p(_f64(gravity)), lidar_mode, C.byref(fail))
+        return st, bool(fail.value)

@@ -420,4 +420,95 @@ int ref_est_estimate_lidar_pose(void* hv, const float* cloud7, int n, double* P3
   return 0;
 }
 
+// ---- sliding window: IMUIntegrator (IMU.cpp verbatim), Cost_NavState_PRV_Bias (CF.h:321-393 verbatim, dual-number
+// autodiff), Estimator::EstimateLidarPose / Estimate with W frames (EST.cpp verbatim) ---------------------------
+static std::vector<sensor_msgs::ImuConstPtr> make_imu(const double* t, const double* gyr, const double* acc, int n) {
+  std::vector<sensor_msgs::ImuConstPtr> v;
+  for (int i = 0; i < n; i++) {
+    auto m = std::make_shared<sensor_msgs::Imu>();
+    m->header.stamp.fromSec(t[i]);
+    m->angular_velocity.x = gyr[3 * i]; m->angular_velocity.y = gyr[3 * i + 1]; m->angular_velocity.z = gyr[3 * i + 2];
+    m->linear_acceleration.x = acc[3 * i]; m->linear_acceleration.y = acc[3 * i + 1]; m->linear_acceleration.z = acc[3 * i + 2];
+    v.push_back(m);
+  }
+  return v;
+}
+// out: dq(wxyz) dp dv dt | cov 15x15 row-major | jac 15x15 row-major  (11 + 225 + 225 doubles)
+int ref_imu_preintegrate(const double* t, const double* gyr, const double* acc, int n, double last_time, const double* bg,
+                         const double* ba, double* out) {
+  IMUIntegrator imu(make_imu(t, gyr, acc, n));
+  imu.PreIntegration(last_time, Eigen::Vector3d(bg[0], bg[1], bg[2]), Eigen::Vector3d(ba[0], ba[1], ba[2]));
+  const Eigen::Quaterniond& q = imu.GetDeltaQ();
+  out[0] = q.w(); out[1] = q.x(); out[2] = q.y(); out[3] = q.z();
+  for (int k = 0; k < 3; k++) { out[4 + k] = imu.GetDeltaP()[k]; out[7 + k] = imu.GetDeltaV()[k]; }
+  out[10] = imu.GetDeltaTime();
+  for (int r = 0; r < 15; r++) for (int c = 0; c < 15; c++) { out[11 + 15 * r + c] = imu.GetCovariance()(r, c); out[236 + 15 * r + c] = imu.GetJacobian()(r, c); }
+  return 0;
+}
+int ref_imu_factor(const double* t, const double* gyr, const double* acc, int n, double last_time, const double* bg,
+                   const double* ba, const double* gravity, const double* pri, const double* vbi, const double* prj,
+                   const double* vbj, double* r15, double* J450) {
+  IMUIntegrator imu(make_imu(t, gyr, acc, n));
+  imu.PreIntegration(last_time, Eigen::Vector3d(bg[0], bg[1], bg[2]), Eigen::Vector3d(ba[0], ba[1], ba[2]));
+  Eigen::Vector3d g(gravity[0], gravity[1], gravity[2]);
+  // EST.cpp:1238-1242
+  ceres::CostFunction* c = Cost_NavState_PRV_Bias::Create(imu, g,
+      Eigen::LLT<Eigen::Matrix<double, 15, 15>>(imu.GetCovariance().inverse()).matrixL().transpose());
+  const double* params[4] = {pri, vbi, prj, vbj};
+  double J0[90], J1[135], J2[90], J3[135];
+  double* jac[4] = {J0, J1, J2, J3};
+  bool ok = c->Evaluate(params, r15, jac);
+  for (int r = 0; r < 15; r++) {
+    for (int k = 0; k < 6; k++) { J450[30 * r + k] = J0[6 * r + k]; J450[30 * r + 15 + k] = J2[6 * r + k]; }
+    for (int k = 0; k < 9; k++) { J450[30 * r + 6 + k] = J1[9 * r + k]; J450[30 * r + 21 + k] = J3[9 * r + k]; }
+  }
+  delete c;
+  return ok ? 0 : -1;
+}
+// EstimateLidarPose on a list of W frames, as process() hands it over in the IMU-initialised state
+// (PE.cpp:796-835): frame f >= 1 carries the IMU messages of (t_{f-1}, t_f] and was pre-integrated with the
+// previous frame's biases. clouds: rows of 7 floats (label in column 6), concatenated; states W x 16 in place
+// (P, q_wxyz, V, bg, ba); imu_*: concatenated samples, imu_n[f] per frame; stamps[f] = frame time.
+int ref_est_estimate_window(void* hv, int W, const float* clouds7, const int* n_pts, double* states, const double* stamps,
+                            const double* imu_t, const double* imu_gyr, const double* imu_acc, const int* imu_n,
+                            const double* exTlb16, const double* gravity, int lidarMode, int* fail_detected) {
+  Estimator* e = ((RefEst*)hv)->est;
+  std::list<Estimator::LidarFrame> frames;
+  size_t po = 0, io = 0;
+  for (int f = 0; f < W; f++) {
+    frames.emplace_back();
+    Estimator::LidarFrame& fr = frames.back();
+    fr.laserCloud.reset(new Cloud);
+    for (int i = 0; i < n_pts[f]; i++) {
+      PointType p; const float* o = clouds7 + 7 * (po + i);
+      p.x = o[0]; p.y = o[1]; p.z = o[2]; p.intensity = o[3]; p.normal_x = o[4]; p.normal_y = o[5]; p.normal_z = o[6];
+      fr.laserCloud->push_back(p);
+    }
+    po += n_pts[f];
+    const double* s = states + 16 * f;
+    fr.P = Eigen::Vector3d(s[0], s[1], s[2]);
+    fr.Q = Eigen::Quaterniond(s[3], s[4], s[5], s[6]);
+    fr.V = Eigen::Vector3d(s[7], s[8], s[9]);
+    fr.bg = Eigen::Vector3d(s[10], s[11], s[12]);
+    fr.ba = Eigen::Vector3d(s[13], s[14], s[15]);
+    fr.timeStamp = stamps[f];
+    if (f >= 1) {
+      fr.imuIntegrator.PushIMUMsg(make_imu(imu_t + io, imu_gyr + 3 * io, imu_acc + 3 * io, imu_n[f]));
+      const double* sp = states + 16 * (f - 1);
+      fr.imuIntegrator.PreIntegration(stamps[f - 1], Eigen::Vector3d(sp[10], sp[11], sp[12]), Eigen::Vector3d(sp[13], sp[14], sp[15]));
+    }
+    io += imu_n[f];
+  }
+  Eigen::Vector3d g(gravity[0], gravity[1], gravity[2]);
+  e->EstimateLidarPose(frames, mat4(exTlb16), g, lidarMode);
+  int f = 0;
+  for (const auto& fr : frames) {
+    double* s = states + 16 * f++;
+    for (int k = 0; k < 3; k++) { s[k] = fr.P[k]; s[7 + k] = fr.V[k]; s[10 + k] = fr.bg[k]; s[13 + k] = fr.ba[k]; }
+    s[3] = fr.Q.w(); s[4] = fr.Q.x(); s[5] = fr.Q.y(); s[6] = fr.Q.z();
+  }
+  *fail_detected = e->failureDetected() ? 1 : 0;
+  return 0;
+}
+
 }  // extern "C"

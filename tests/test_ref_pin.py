@@ -290,3 +290,76 @@ def test_map_increment_matches_oracle(orc, synth):
             assert np.array_equal(gs, cm.cloud(1))
     finally:
         E.close()
+
+
+# ------------------------------------------------------------------------------------------- sliding window (IMU)
+def test_imu_preintegration_and_factor(orc, synth):
+    """IMUIntegrator::PreIntegration (IMU.cpp:105-166) and Cost_NavState_PRV_Bias under autodiff (CF.h:321-393) with
+    the reference's sqrt_information (EST.cpp:1238-1242) against the oracle's restatement."""
+    imu, stamps = synth.imu_stream(4)
+    Ts = synth.trajectory(4)
+    rng = np.random.default_rng(0)
+    grav = np.array([0, 0, -9.805])
+
+    def x6(T):
+        return np.concatenate([T[:3, 3], synth.R_to_rotvec(T[:3, :3])])
+
+    for k in (1, 2, 3):
+        bg = rng.normal(0, 2e-3, 3)
+        ba = rng.normal(0, 2e-2, 3)
+        t, gy, ac = imu[k]
+        dq, dp, dv, dt, cov, jac = ref.imu_preintegrate(t, gy, ac, stamps[k - 1], bg, ba)
+        P = orc.Preint(t, gy, ac, stamps[k - 1], bg, ba)
+        assert np.abs(dq - P.dq).max() < 1e-14 and np.abs(dp - P.dp).max() < 1e-14 and np.abs(dv - P.dv).max() < 1e-13
+        assert dt == P.dt
+        assert np.abs(cov - P.cov).max() <= 1e-12 * np.abs(cov).max() and np.abs(jac - P.jac).max() < 1e-13
+        for _ in range(3):
+            pri = x6(Ts[k - 1]) + rng.normal(0, 0.01, 6)
+            prj = x6(Ts[k]) + rng.normal(0, 0.01, 6)
+            vbi = np.concatenate([synth.body_velocity_world(Ts[k - 1]) + rng.normal(0, 0.02, 3), bg + rng.normal(0, 1e-3, 3),
+                                  ba + rng.normal(0, 1e-2, 3)])
+            vbj = np.concatenate([synth.body_velocity_world(Ts[k]) + rng.normal(0, 0.02, 3), bg + rng.normal(0, 1e-3, 3),
+                                  ba + rng.normal(0, 1e-2, 3)])
+            r1, J1 = ref.imu_factor(t, gy, ac, stamps[k - 1], bg, ba, grav, pri, vbi, prj, vbj)
+            r2, J2 = orc.imu_factor(P, grav, pri, vbi, prj, vbj)
+            assert np.abs(r1 - r2).max() <= 1e-10 * np.abs(r1).max()
+            assert np.abs(J1 - J2).max() <= 1e-10 * np.abs(J1).max()
+
+
+@pytest.mark.parametrize("W", [2, 3, 4])
+def test_estimate_window_with_imu(orc, synth, matched, W):
+    """Estimator::EstimateLidarPose on a list of W frames with IMU factors (EST.cpp:967-1141 -> Estimate 1143-1581,
+    IMU blocks 1235-1254), reference text against orc_estimate_window. BASELINE config 3 is W = 3."""
+    E, om = matched["E"], matched["om"]
+    imu, stamps = synth.imu_stream(8)
+    Ts = synth.trajectory(8)
+    rng = np.random.default_rng(W)
+    base = 1
+    clouds, corners, surfs, pre = [], [], [], [None]
+    states = np.zeros((W, 16))
+    for f in range(W):
+        k = base + f
+        x, _, _ = synth.vlp16_scan(Ts[k], seed=50 + k)
+        c7 = ref.velo_extract(x)
+        clouds.append(c7)
+        lab = c7[:, 6].astype(int)
+        corners.append(orc.voxel_downsample(c7[lab == 1][:, :4], 0.4))
+        surfs.append(orc.voxel_downsample(c7[lab == 2][:, :4], 0.2))
+        Tn = Ts[k] @ synth.make_T(synth.rot_z(rng.normal(0, 0.004)), rng.normal(0, 0.03, 3))
+        q, _ = orc.so3_exp(synth.R_to_rotvec(Tn[:3, :3]))
+        states[f, :3] = Tn[:3, 3]
+        states[f, 3:7] = q
+        states[f, 7:10] = synth.body_velocity_world(Ts[k]) + rng.normal(0, 0.02, 3)
+        if f >= 1:
+            pre.append(orc.Preint(*imu[k], stamps[k - 1], states[f - 1, 10:13], states[f - 1, 13:16]))
+    om.set(orc.CORNER_LOCAL, E.local_map(0))
+    om.set(orc.SURF_LOCAL, E.local_map(1))
+    s1, fail = E.estimate_window(clouds, states, stamps[base:base + W], [imu[base + f] for f in range(W)])
+    s2, st = orc.estimate_window(om, corners, surfs, np.eye(4), states, pre)
+    assert not fail and st[0] >= 1
+    assert np.abs(s1[:, :3] - s2[:, :3]).max() < 1e-7          # positions
+    assert 2 * np.abs(s1[:, 3:7] - s2[:, 3:7]).max() < 1e-7    # rotations
+    assert np.abs(s1[:, 7:10] - s2[:, 7:10]).max() < 1e-6      # velocities
+    assert np.abs(s1[:, 10:] - s2[:, 10:]).max() < 1e-5        # biases
+    for f in range(W):
+        assert np.abs(s2[f, :3] - Ts[base + f][:3, 3]).max() < 0.05

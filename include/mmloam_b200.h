@@ -170,6 +170,59 @@ int mml_local_map_push(mml_ctx* ctx, const float* corner_xyzi, int n_corner, con
 int mml_local_map_get(mml_ctx* ctx, int kind, float* out_xyzi, int cap, int* n_out);
 int mml_local_map_reset(mml_ctx* ctx);
 
+/* ---- sliding window, sizes 2-4 (IMU factors, no marginalisation; BASELINE config 3 is window 3):
+ * Estimator::Estimate for windowSize < SLIDEWINDOWSIZE, src/lio/Estimator.cpp:1143-1581.
+ * mml_preint = IMUIntegrator after PreIntegration (src/lio/IMUIntegrator.cpp:105-166): delta rotation (w, x, y, z),
+ * position, velocity, time, the biases it was linearised at, covariance and Jacobian (15 x 15 row-major, order
+ * P R V BG BA, include/IMUIntegrator/IMUIntegrator.h:86-93) and sqrt_info = LLT(cov^-1).matrixL()^T (EST.cpp:1240-1242). */
+typedef struct {
+  double dq[4];
+  double dp[3], dv[3], dt;
+  double bg[3], ba[3];
+  double cov[225], jac[225], sqrt_info[225];
+} mml_preint;
+/* t / gyr / acc: n samples in (last_time, t_frame]; acc in units of g (scaled by gnorm = 9.805, IMU.h:84). Host code. */
+int mml_imu_preintegrate(const double* t, const double* gyr, const double* acc, int n, double last_time,
+                         const double* bg3, const double* ba3, mml_preint* out);
+/* Cost_NavState_PRV_Bias (include/utils/ceresfunc.h:321-393) weighted by sqrt_info: r15 and, if J450 != NULL, the
+ * Jacobian (15 x 30 row-major, columns [PR_i 6 | VBias_i 9 | PR_j 6 | VBias_j 9]) by forward-mode differentiation. */
+int mml_imu_factor(const mml_preint* pre, const double* gravity3, const double* pri6, const double* vbi9,
+                   const double* prj6, const double* vbj9, double* r15, double* J450);
+/* Pose prediction of process(), src/unionPoseEstimation.cpp:812-829. state = P(3) q_wxyz(4) V(3) bg(3) ba(3).      */
+int mml_imu_predict(const double* prev16, const mml_preint* pre, double* next16);
+/* Window frames live in HBM as their downsampled corner / surf clouds. A push drops the oldest frame when the
+ * window already holds max_frames (PE.cpp:830-832).                                                               */
+int mml_window_reset(mml_ctx* ctx);
+int mml_window_size(mml_ctx* ctx);
+int mml_window_push_frame(mml_ctx* ctx, const float* corner_xyzi, int n_corner, const float* surf_xyzi, int n_surf,
+                          int max_frames);
+/* raw scan resident in HBM: extraction -> undistortion + label split + voxel filter on the device               */
+int mml_window_push_scan_dev(mml_ctx* ctx, const void* xyzi_dev, const void* line_id_dev, const void* s_dev, int n,
+                             int n_lines, const double* dR9, const double* dt3, float leaf_corner, float leaf_surf,
+                             int max_frames, int* out_counts);
+int mml_window_get_frame(mml_ctx* ctx, int frame, int kind, float* out_xyzi, int cap, int* n_out);
+/* Estimate over the frames in the window. states: W x 16 doubles in place; preints[f] (f >= 1) links frame f-1 -> f.
+ * Association and the lidar normal equations of all frames run on the device (one launch per evaluation for the
+ * whole window); the W-1 IMU factors and the (15 W)-dimensional dogleg step run on the host.
+ * stats (may be NULL, 16 doubles): [outer, inner, n_line, n_plane (newest frame), final_cost, min_sv, degenerate, evaluations]. */
+int mml_estimate_window(mml_ctx* ctx, double* states, const mml_preint* const* preints, const double* exTlb16,
+                        const double* gravity3, const mml_est_params* prm, double* stats);
+
+/* Odometry loop with an IMU-initialised sliding window of `window` frames: the per-scan body of process() in its
+ * LidarIMUInited branch (src/unionPoseEstimation.cpp:796-891): pre-integration of the IMU samples of
+ * (t_{k-1}, t_k], state prediction, undistortion with the predicted LiDAR motion, window push, EstimateLidarPose.
+ * xyzi / line / s: per-scan pointers (device pointers when host_buffers == 0). imu_*: all samples concatenated, scan
+ * k owns imu_n[k] of them (acc in units of g). state0 / stamp0: state and time of the frame before the first scan.
+ * poses_front: the reference's odometry output, the OLDEST frame of the window (EST.cpp:1043-1049); poses_newest:
+ * the newest frame; states_out: its full state; stats_out: n_scans x 8 (see mml_estimate_window). Any may be NULL.
+ * The context's feature maps are used as they are (not updated by this call).                                      */
+int mml_odom_run_window(mml_ctx* ctx, const void* const* xyzi, const void* const* line, const void* const* s,
+                        const int* n_pts, int n_scans, int n_lines, int host_buffers, int window, const double* stamps,
+                        double stamp0, const double* imu_t, const double* imu_gyr, const double* imu_acc, const int* imu_n,
+                        const double* state0, const double* exTlb16, const double* gravity3, float leaf_corner,
+                        float leaf_surf, const mml_est_params* prm, double* poses_front, double* poses_newest,
+                        double* states_out, double* stats_out, float* total_ms);
+
 /* ---- device-resident building blocks used by bench.py's roofline sweep (S4):
  * queries and maps stay in HBM; one call = one association or one evaluation.          */
 int mml_frame_set(mml_ctx* ctx, const float* corner_xyzi, int n_corner, const float* surf_xyzi, int n_surf);

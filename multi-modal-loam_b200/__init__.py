@@ -36,11 +36,54 @@ EXPORTS = [
     "mml_frame_accumulate", "mml_frame_associate_async", "mml_frame_associate_kind_async", "mml_frame_accumulate_async",
     "mml_odom_run", "mml_local_map_push", "mml_local_map_get", "mml_local_map_reset", "mml_timer_start",
     "mml_timer_stop_ms", "mml_frame_accumulate_partial_dev", "mml_stream_handle",
+    "mml_imu_preintegrate", "mml_imu_factor", "mml_imu_predict", "mml_window_reset", "mml_window_size",
+    "mml_window_push_frame", "mml_window_push_scan_dev", "mml_window_get_frame", "mml_estimate_window",
+    "mml_odom_run_window",
 ]
 
 
 class MmlError(RuntimeError):
     pass
+
+
+class Preint(C.Structure):
+    """mml_preint: IMUIntegrator after PreIntegration (IMU.cpp:105-166)."""
+    _fields_ = [("dq", C.c_double * 4), ("dp", C.c_double * 3), ("dv", C.c_double * 3), ("dt", C.c_double),
+                ("bg", C.c_double * 3), ("ba", C.c_double * 3), ("cov", C.c_double * 225), ("jac", C.c_double * 225),
+                ("sqrt_info", C.c_double * 225)]
+
+
+def imu_preintegrate(t, gyr, acc, last_time, bg=(0, 0, 0), ba=(0, 0, 0)):
+    """IMUIntegrator::PreIntegration on the samples of (last_time, t_frame] (host code, no GPU needed)."""
+    t = _f64(t)
+    gyr = _f64(gyr).reshape(-1, 3)
+    acc = _f64(acc).reshape(-1, 3)
+    out = Preint()
+    rc = load_library().mml_imu_preintegrate(_p(t), _p(gyr), _p(acc), int(t.shape[0]), C.c_double(last_time), _p(_f64(bg)),
+                                             _p(_f64(ba)), C.byref(out))
+    if rc != 0:
+        raise MmlError(f"mml_imu_preintegrate: {ERRORS.get(rc, rc)}")
+    return out
+
+
+def imu_factor(pre, gravity, pri, vbi, prj, vbj):
+    """Cost_NavState_PRV_Bias weighted by sqrt_info: (r15, J[15, 30])."""
+    r = np.zeros(15)
+    J = np.zeros((15, 30))
+    rc = load_library().mml_imu_factor(C.byref(pre), _p(_f64(gravity)), _p(_f64(pri)), _p(_f64(vbi)), _p(_f64(prj)),
+                                       _p(_f64(vbj)), _p(r), _p(J))
+    if rc != 0:
+        raise MmlError(f"mml_imu_factor: {ERRORS.get(rc, rc)}")
+    return r, J
+
+
+def imu_predict(prev16, pre):
+    """Pose prediction of process() (PE.cpp:812-829): state = P, q_wxyz, V, bg, ba."""
+    out = np.zeros(16)
+    rc = load_library().mml_imu_predict(_p(_f64(prev16)), C.byref(pre), _p(out))
+    if rc != 0:
+        raise MmlError(f"mml_imu_predict: {ERRORS.get(rc, rc)}")
+    return out
 
 
 class EstParams(C.Structure):
@@ -349,6 +392,87 @@ class Context:
         return poses[:k].reshape(k, 4, 4), ms.value, counts[:k]
 
     # ---- local feature map on the device (Estimator::MapIncrementLocal, EST.cpp:1585-1643)
+    # ---- sliding window (sizes 2-4, IMU factors) --------------------------------------------------------------
+    def window_reset(self):
+        self._ck(self.lib.mml_window_reset(self.h))
+
+    def window_size(self):
+        return int(self.lib.mml_window_size(self.h))
+
+    def window_push_frame(self, corner, surf, max_frames=3):
+        corner = _f32(corner).reshape(-1, 4)
+        surf = _f32(surf).reshape(-1, 4)
+        self._ck(self.lib.mml_window_push_frame(self.h, _p(corner), corner.shape[0], _p(surf), surf.shape[0], int(max_frames)))
+
+    def window_push_scan_dev(self, xyzi_dev, line_dev, s_dev, n, n_lines, dR, dt, max_frames=3, leaf_corner=0.4,
+                             leaf_surf=0.2):
+        dRa = _f64(dR).reshape(9) if dR is not None else None
+        dta = _f64(dt).reshape(3) if dt is not None else None
+        counts = np.zeros(4, np.int32)
+        self._ck(self.lib.mml_window_push_scan_dev(self.h, C.c_void_p(xyzi_dev), C.c_void_p(line_dev),
+                                                   C.c_void_p(s_dev) if s_dev else None, int(n), int(n_lines), _p(dRa),
+                                                   _p(dta), C.c_float(leaf_corner), C.c_float(leaf_surf), int(max_frames),
+                                                   _p(counts)))
+        return counts
+
+    def window_get_frame(self, f, kind):
+        n = C.c_int(0)
+        self._ck(self.lib.mml_window_get_frame(self.h, int(f), int(kind), None, 0, C.byref(n)))
+        out = np.zeros((max(n.value, 1), 4), np.float32)
+        self._ck(self.lib.mml_window_get_frame(self.h, int(f), int(kind), _p(out), n.value, C.byref(n)))
+        return out[: n.value].copy()
+
+    def estimate_window(self, states, preints, exTlb=np.eye(4), gravity=(0, 0, -9.805), params=None):
+        """Estimator::Estimate on the frames in the window. states [W, 16] = P, q_wxyz, V, bg, ba per frame;
+        preints[f] (f >= 1) links frame f-1 to f. Returns (states, stats)."""
+        W = self.window_size()
+        st = _f64(states).reshape(W, 16).copy()
+        pp = (C.POINTER(Preint) * W)()
+        for f in range(W):
+            if preints[f] is not None:
+                pp[f] = C.pointer(preints[f])
+        stats = np.zeros(16)
+        prm = params if params is not None else est_params()
+        self._ck(self.lib.mml_estimate_window(self.h, _p(st), pp, _p(_f64(exTlb).reshape(16)), _p(_f64(gravity)),
+                                              C.byref(prm), _p(stats)))
+        return st, stats
+
+    def odom_run_window(self, scans, n_lines, window, stamps, stamp0, imu, state0, exTlb=np.eye(4), gravity=(0, 0, -9.805),
+                        host_buffers=False, leaf_corner=0.4, leaf_surf=0.2, params=None):
+        """mml_odom_run_window. scans: list of (xyzi, line, s, n) with device pointers (ints) or, with
+        host_buffers=True, numpy arrays. imu: list of (t, gyr, acc) per scan. Returns dict with poses_front,
+        poses_newest, states, stats, total_ms."""
+        n = len(scans)
+        keep = []
+
+        def ptr(v):
+            if host_buffers:
+                keep.append(v)
+                return v.ctypes.data
+            return int(v)
+
+        xs = (C.c_void_p * n)(*[ptr(sc[0]) for sc in scans])
+        ls = (C.c_void_p * n)(*[ptr(sc[1]) for sc in scans])
+        ss = (C.c_void_p * n)(*[ptr(sc[2]) for sc in scans])
+        npts = np.array([int(sc[3]) for sc in scans], np.int32)
+        it = _f64(np.concatenate([np.asarray(i[0], float).ravel() for i in imu]))
+        ig = _f64(np.concatenate([np.asarray(i[1], float).reshape(-1, 3) for i in imu]))
+        ia = _f64(np.concatenate([np.asarray(i[2], float).reshape(-1, 3) for i in imu]))
+        inn = np.array([len(np.asarray(i[0]).ravel()) for i in imu], np.int32)
+        pf = np.zeros((n, 16))
+        pn = np.zeros((n, 16))
+        so = np.zeros((n, 16))
+        st = np.zeros((n, 8))
+        ms = C.c_float(0)
+        prm = params if params is not None else est_params()
+        self._ck(self.lib.mml_odom_run_window(self.h, xs, ls, ss, _p(npts), n, int(n_lines), 1 if host_buffers else 0,
+                                              int(window), _p(_f64(stamps)), C.c_double(stamp0), _p(it), _p(ig), _p(ia),
+                                              _p(inn), _p(_f64(state0)), _p(_f64(exTlb).reshape(16)), _p(_f64(gravity)),
+                                              C.c_float(leaf_corner), C.c_float(leaf_surf), C.byref(prm), _p(pf), _p(pn),
+                                              _p(so), _p(st), C.byref(ms)))
+        return dict(poses_front=pf.reshape(n, 4, 4), poses_newest=pn.reshape(n, 4, 4), states=so, stats=st,
+                    total_ms=float(ms.value))
+
     def local_map_push(self, corner, surf, T_wl, leaf_corner=0.4, leaf_surf=0.2):
         """One map update from a frame's corner / surf clouds (LiDAR frame) and its pose. Returns the sizes of the new
         local corner / surf maps; the association searches them from now on (map kinds 2 / 3)."""

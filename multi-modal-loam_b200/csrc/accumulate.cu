@@ -379,6 +379,86 @@ __global__ void __launch_bounds__(256, MML_ACC_MINB) k_accumulate(AccArgs A) {
   }
 }
 
+// ---------------------------------------------------------------- sliding window: all frames in one launch
+// Window sizes 2-4 (EST.cpp:1265-1418): every frame of the window has its own pose block PR_f, so one evaluation
+// of the lidar terms is W independent 28-sum reductions. blockIdx.y = frame; the per-frame sums land in
+// out28[f][28] and the (15 W)^2 system is assembled where the IMU factors are added (window.cu).
+struct AccWinArgs {
+  const float4* f_line[4];
+  const float4* f_plane[4];
+  int n_line[4], n_plane[4];
+  double x6[4][6];
+  double Rbl[9], Pbl[3];
+  double lidar_m, w_tan, huber_a;
+  double* partials;   // [W][gridDim.x][28]
+  unsigned* ticket;   // [W]
+  double* out28;      // [W][28]
+};
+
+__global__ void __launch_bounds__(256, MML_ACC_MINB) k_accumulate_window(AccWinArgs A) {
+  const int f = blockIdx.y;
+  __shared__ PoseLin L;
+  if (threadIdx.x == 0) make_pose(A.x6[f], A.Rbl, A.Pbl, L);
+  __syncthreads();
+  const double s_info = 1.0 / A.lidar_m, w_tan = A.w_tan, ha = A.huber_a;
+  const int n_line = A.n_line[f], n_plane = A.n_plane[f];
+  const float4* __restrict__ fl = A.f_line[f];
+  const float4* __restrict__ fp = A.f_plane[f];
+  double acc[28];
+#pragma unroll
+  for (int k = 0; k < 28; k++) acc[k] = 0.0;
+  const int stride = gridDim.x * 256;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n_line; i += stride) {
+    double p[3], a[3], b[3];
+    if (!load_line(fl, i, p, a, b)) continue;
+    eval_line(L, p, a, b, s_info, ha, acc);
+  }
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n_plane; i += stride) {
+    double p[3], n[3], pp[3];
+    if (!load_plane(fp, i, p, pp, n)) continue;
+    eval_plane(L, p, pp, n, s_info, w_tan, ha, acc);
+  }
+  __shared__ double sred[8][28];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 28; k++) {
+    double v = acc[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) sred[warp][k] = v;
+  }
+  __syncthreads();
+  double* part = A.partials + (size_t)f * gridDim.x * 28;
+  if (threadIdx.x < 28) {
+    double v = 0;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; w8++) v += sred[w8][threadIdx.x];
+    part[(size_t)blockIdx.x * 28 + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(A.ticket + f, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  {
+    const int k = threadIdx.x & 31, pt = threadIdx.x >> 5;
+    double v = 0;
+    if (k < 28)
+      for (unsigned b = pt; b < gridDim.x; b += 8) v += __ldcg(part + (size_t)b * 28 + k);
+    if (k < 28) sred[pt][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 28) {
+    double v = 0;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; w8++) v += sred[w8][threadIdx.x];
+    A.out28[28 * f + threadIdx.x] = v;
+  }
+  if (threadIdx.x == 0) A.ticket[f] = 0;
+}
+
 // ---------------------------------------------------------------- dogleg state machine
 __host__ __device__ inline void unpack28(const double* o, double* cost, double* g, double* H) {
   *cost = o[0];
@@ -1149,6 +1229,37 @@ int mml_chain_solve_launch(mml_ctx* ctx, const int* cnt_dev, int cap, mml::OdomD
 struct mml_solver {
   mml::EstState S;
 };
+
+int mml_accumulate_window_grid_max() { return MML_ACC_MINB * kNumSMs; }
+
+// One evaluation of the lidar terms of a W-frame window: per-frame [cost, g6, H21] -> out_dev[W][28].
+// slots' feature buffers and counts come from the caller (window.cu).
+int mml_accumulate_window_launch(mml_ctx* ctx, int W, const float4* const* f_line, const float4* const* f_plane,
+                                 const int* n_line, const int* n_plane, const double* x6s, const double* Rbl9,
+                                 const double* Pbl3, double lidar_m, double w_tan, double huber_a, double* partials_dev,
+                                 unsigned* ticket_dev, double* out_dev) {
+  // partials_dev: W x mml_accumulate_window_grid_max() x 28 doubles; ticket_dev: W zeroed words (self-resetting)
+  int nmax = 1;
+  for (int f = 0; f < W; f++) { nmax = nmax > n_line[f] ? nmax : n_line[f]; nmax = nmax > n_plane[f] ? nmax : n_plane[f]; }
+  const int grid = acc_grid(nmax);
+  AccWinArgs A;
+  memset(&A, 0, sizeof(A));
+  for (int f = 0; f < W; f++) {
+    A.f_line[f] = f_line[f]; A.f_plane[f] = f_plane[f];
+    A.n_line[f] = n_line[f]; A.n_plane[f] = n_plane[f];
+    for (int i = 0; i < 6; i++) A.x6[f][i] = x6s[6 * f + i];
+  }
+  for (int i = 0; i < 9; i++) A.Rbl[i] = Rbl9[i];
+  for (int i = 0; i < 3; i++) A.Pbl[i] = Pbl3[i];
+  A.lidar_m = lidar_m; A.w_tan = w_tan; A.huber_a = huber_a;
+  A.partials = partials_dev;
+  A.ticket = ticket_dev;
+  A.out28 = out_dev;
+  k_accumulate_window<<<dim3(grid, W), 256, 0, ctx->stream>>>(A);
+  MML_LAUNCHED(ctx);
+  MML_CUDA(ctx, cudaGetLastError());
+  return MML_OK;
+}
 
 extern "C" {
 

@@ -391,7 +391,6 @@ class Context:
                                        C.byref(ms), _p(counts)))
         return poses[:k].reshape(k, 4, 4), ms.value, counts[:k]
 
-    # ---- local feature map on the device (Estimator::MapIncrementLocal, EST.cpp:1585-1643)
     # ---- sliding window (sizes 2-4, IMU factors) --------------------------------------------------------------
     def window_reset(self):
         self._ck(self.lib.mml_window_reset(self.h))
@@ -406,6 +405,7 @@ class Context:
 
     def window_push_scan_dev(self, xyzi_dev, line_dev, s_dev, n, n_lines, dR, dt, max_frames=3, leaf_corner=0.4,
                              leaf_surf=0.2):
+        xyzi_dev, line_dev, s_dev = [v.value if isinstance(v, C.c_void_p) else v for v in (xyzi_dev, line_dev, s_dev)]
         dRa = _f64(dR).reshape(9) if dR is not None else None
         dta = _f64(dt).reshape(3) if dt is not None else None
         counts = np.zeros(4, np.int32)
@@ -446,10 +446,12 @@ class Context:
         keep = []
 
         def ptr(v):
-            if host_buffers:
+            if isinstance(v, C.c_void_p):
+                return v.value
+            if isinstance(v, np.ndarray):
                 keep.append(v)
                 return v.ctypes.data
-            return int(v)
+            return int(v) if v is not None else None
 
         xs = (C.c_void_p * n)(*[ptr(sc[0]) for sc in scans])
         ls = (C.c_void_p * n)(*[ptr(sc[1]) for sc in scans])
@@ -473,6 +475,7 @@ class Context:
         return dict(poses_front=pf.reshape(n, 4, 4), poses_newest=pn.reshape(n, 4, 4), states=so, stats=st,
                     total_ms=float(ms.value))
 
+    # ---- local feature map on the device (Estimator::MapIncrementLocal, EST.cpp:1585-1643)
     def local_map_push(self, corner, surf, T_wl, leaf_corner=0.4, leaf_surf=0.2):
         """One map update from a frame's corner / surf clouds (LiDAR frame) and its pose. Returns the sizes of the new
         local corner / surf maps; the association searches them from now on (map kinds 2 / 3)."""

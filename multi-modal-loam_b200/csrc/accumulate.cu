@@ -393,6 +393,11 @@ struct AccWinArgs {
   double* partials;   // [W][gridDim.x][28]
   unsigned* ticket;   // [W]
   double* out28;      // [W][28]
+  // optional zero-copy hand-over to the host solver: the last CTA of frame f also stores its 28 sums into mapped
+  // pinned host memory and then publishes `seq` in host_seq[f] (the host spins on it instead of synchronising)
+  double* host_out;
+  volatile unsigned* host_seq;
+  unsigned seq;
 };
 
 __global__ void __launch_bounds__(256, MML_ACC_MINB) k_accumulate_window(AccWinArgs A) {
@@ -455,8 +460,16 @@ __global__ void __launch_bounds__(256, MML_ACC_MINB) k_accumulate_window(AccWinA
 #pragma unroll
     for (int w8 = 0; w8 < 8; w8++) v += sred[w8][threadIdx.x];
     A.out28[28 * f + threadIdx.x] = v;
+    if (A.host_out) A.host_out[28 * f + threadIdx.x] = v;
   }
-  if (threadIdx.x == 0) A.ticket[f] = 0;
+  if (A.host_out) {
+    __threadfence_system();
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    A.ticket[f] = 0;
+    if (A.host_out) A.host_seq[f] = A.seq;
+  }
 }
 
 // ---------------------------------------------------------------- dogleg state machine
@@ -1237,7 +1250,7 @@ int mml_accumulate_window_grid_max() { return MML_ACC_MINB * kNumSMs; }
 int mml_accumulate_window_launch(mml_ctx* ctx, int W, const float4* const* f_line, const float4* const* f_plane,
                                  const int* n_line, const int* n_plane, const double* x6s, const double* Rbl9,
                                  const double* Pbl3, double lidar_m, double w_tan, double huber_a, double* partials_dev,
-                                 unsigned* ticket_dev, double* out_dev) {
+                                 unsigned* ticket_dev, double* out_dev, double* host_out_dev, unsigned* host_seq_dev, unsigned seq) {
   // partials_dev: W x mml_accumulate_window_grid_max() x 28 doubles; ticket_dev: W zeroed words (self-resetting)
   int nmax = 1;
   for (int f = 0; f < W; f++) { nmax = nmax > n_line[f] ? nmax : n_line[f]; nmax = nmax > n_plane[f] ? nmax : n_plane[f]; }
@@ -1255,6 +1268,9 @@ int mml_accumulate_window_launch(mml_ctx* ctx, int W, const float4* const* f_lin
   A.partials = partials_dev;
   A.ticket = ticket_dev;
   A.out28 = out_dev;
+  A.host_out = host_out_dev;
+  A.host_seq = host_seq_dev;
+  A.seq = seq;
   k_accumulate_window<<<dim3(grid, W), 256, 0, ctx->stream>>>(A);
   MML_LAUNCHED(ctx);
   MML_CUDA(ctx, cudaGetLastError());

@@ -15,6 +15,9 @@ for f in extract geometry splitvoxel framesort associate accumulate odometry loc
     # accumulate.cu is pure float64 normal-equation arithmetic checked to 1e-9 relative (no bit-exact float32
     # thresholds inside): it may contract multiply-adds into DFMA
     if [ "$f" = "accumulate" ]; then FF="${FLAGS/-fmad=false/-fmad=true}"; else FF="$FLAGS"; fi
+    # window.cu carries the host side of the sliding-window solve (IMU factors under forward-mode differentiation,
+    # dense (15 W)-dim dogleg): let the host compiler vectorise it (every B200 host CPU has AVX2 + FMA)
+    if [ "$f" = "window" ]; then FF="$FF -Xcompiler -mavx2 -Xcompiler -mfma -Xcompiler -ffp-contract=fast"; fi
     $NVCC $FF -c "$HERE/$f.cu" -o "$OBJ/$f.o" &
     pids+=($!)
   fi

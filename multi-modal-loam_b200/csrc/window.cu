@@ -24,7 +24,7 @@ int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres,
 int mml_accumulate_window_launch(mml_ctx* ctx, int W, const float4* const* f_line, const float4* const* f_plane,
                                  const int* n_line, const int* n_plane, const double* x6s, const double* Rbl9,
                                  const double* Pbl3, double lidar_m, double w_tan, double huber_a, double* partials_dev,
-                                 unsigned* ticket_dev, double* out_dev);
+                                 unsigned* ticket_dev, double* out_dev, double* host_out_dev, unsigned* host_seq_dev, unsigned seq);
 int mml_accumulate_window_grid_max();
 int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_d, const int* scan_off, int n_scans,
                        int n_lines, uint8_t* label_d, bool sequential);
@@ -36,47 +36,80 @@ int mml_split_voxel_device(mml_ctx* ctx, const float4* pts_d, const float* s_d, 
 
 namespace {
 
+// MML_WIN_PROF=1: wall-clock split of the window loop (debug aid; printed by mml_odom_run_window)
+struct WinProf { double push = 0, assoc = 0, launch = 0, imu = 0, wait = 0, solve = 0, other = 0; long evals = 0, scans = 0; };
+WinProf g_prof;
+const bool g_prof_on = getenv("MML_WIN_PROF") != nullptr;
+inline double now_us() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+
 constexpr int kMaxWindow = 4;
 
 struct WinSlot {
   DevBuf q_corner, q_surf, f_line, f_plane;
+  DevBuf assoc_stats, assoc_part[2];  // per-frame association statistics: frames are associated concurrently
   int n_corner = 0, n_surf = 0;
 };
 struct WindowState {
   WinSlot slot[kMaxWindow];
   int n_slots = 0;
-  DevBuf partials, out;   // out: [W][28] sums, then [W][20] association statistics
-  PinBuf host;
+  DevBuf partials, out;   // out: [W][28] sums
+  // zero-copy hand-over of an evaluation to the host solver: mapped pinned memory written by the kernel
+  // [0, 28 W) sums | [28 W, 28 W + 20 W) association statistics (copied) | sequence words
+  void* mapped = nullptr;
+  double* mapped_dev = nullptr;
+  unsigned seq = 0;
+  cudaStream_t fstream[kMaxWindow][2] = {};
+  cudaEvent_t fev[kMaxWindow][2] = {};
+  cudaEvent_t fork = nullptr;
+  bool streams_ok = false;
+  // odometry loop: the next scan is copied (host buffers) and labelled on its own stream while the window is solved
+  cudaStream_t xstream = nullptr;
+  cudaEvent_t xev[2] = {nullptr, nullptr}, xfree[2] = {nullptr, nullptr};
+  DevBuf x_xyzi[2], x_line[2], x_s[2], x_label[2], x_counters[2];
 };
+constexpr int kMapDoubles = (28 + 20) * kMaxWindow;
+constexpr size_t kMapBytes = sizeof(double) * kMapDoubles + 64;
 
 WindowState* win(mml_ctx* c) {
   if (!c->window) c->window = new WindowState();
   return static_cast<WindowState*>(c->window);
 }
+int win_prepare(mml_ctx* c, WindowState* w) {
+  if (!w->mapped) {
+    MML_CUDA(c, cudaHostAlloc(&w->mapped, kMapBytes, cudaHostAllocMapped));
+    memset(w->mapped, 0, kMapBytes);
+    void* d = nullptr;
+    MML_CUDA(c, cudaHostGetDevicePointer(&d, w->mapped, 0));
+    w->mapped_dev = static_cast<double*>(d);
+  }
+  if (!w->streams_ok) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    for (int f = 0; f < kMaxWindow; f++) for (int k = 0; k < 2; k++) {
+      MML_CUDA(c, cudaStreamCreateWithPriority(&w->fstream[f][k], cudaStreamNonBlocking, hi));
+      MML_CUDA(c, cudaEventCreateWithFlags(&w->fev[f][k], cudaEventDisableTiming));
+    }
+    MML_CUDA(c, cudaEventCreateWithFlags(&w->fork, cudaEventDisableTiming));
+    MML_CUDA(c, cudaStreamCreateWithPriority(&w->xstream, cudaStreamNonBlocking, lo));
+    for (int k = 0; k < 2; k++) {
+      MML_CUDA(c, cudaEventCreateWithFlags(&w->xev[k], cudaEventDisableTiming));
+      MML_CUDA(c, cudaEventCreateWithFlags(&w->xfree[k], cudaEventDisableTiming));
+    }
+    w->streams_ok = true;
+  }
+  return MML_OK;
+}
 
-// ---- forward-mode dual number over ONE direction: the IMU functor is differentiated one parameter at a time,
-// exactly what Ceres' Jet does 30 directions at once (same derivative values, no hand-derived Jacobian to get wrong)
-struct Dual {
-  double a, v;
-  __host__ __device__ Dual() : a(0), v(0) {}
-  __host__ __device__ Dual(double s) : a(s), v(0) {}
-  __host__ __device__ Dual(double s, double d) : a(s), v(d) {}
-};
-__host__ __device__ inline Dual operator+(Dual f, Dual g) { return {f.a + g.a, f.v + g.v}; }
-__host__ __device__ inline Dual operator-(Dual f, Dual g) { return {f.a - g.a, f.v - g.v}; }
-__host__ __device__ inline Dual operator-(Dual f) { return {-f.a, -f.v}; }
-__host__ __device__ inline Dual operator*(Dual f, Dual g) { return {f.a * g.a, f.a * g.v + f.v * g.a}; }
-__host__ __device__ inline Dual operator/(Dual f, Dual g) { const double gi = 1.0 / g.a, q = f.a * gi; return {q, (f.v - q * g.v) * gi}; }
-__host__ __device__ inline Dual dsqrt(Dual f) { const double t = sqrt(f.a); return {t, f.v / (2.0 * t)}; }
-__host__ __device__ inline Dual dsin(Dual f) { return {sin(f.a), cos(f.a) * f.v}; }
-__host__ __device__ inline Dual dcos(Dual f) { return {cos(f.a), -sin(f.a) * f.v}; }
-__host__ __device__ inline Dual datan(Dual f) { return {atan(f.a), f.v / (1.0 + f.a * f.a)}; }
+// ---- scalar overloads used by the functor text below when it is instantiated for plain doubles
 __host__ __device__ inline double dsqrt(double f) { return sqrt(f); }
 __host__ __device__ inline double dsin(double f) { return sin(f); }
 __host__ __device__ inline double dcos(double f) { return cos(f); }
 __host__ __device__ inline double datan(double f) { return atan(f); }
 __host__ __device__ inline double val(double x) { return x; }
-__host__ __device__ inline double val(Dual x) { return x.a; }
 
 template <class T> struct Q4 { T w, x, y, z; };
 template <class T> __host__ __device__ inline Q4<T> qmul(const Q4<T>& a, const Q4<T>& b) {  // sophus/so3.hpp:326-340
@@ -159,6 +192,25 @@ __host__ __device__ void imu_residual(const mml_preint& m, const double* g, cons
   for (int k = 0; k < 6; k++) r[9 + k] = vbj[3 + k] - vbi[3 + k];
 }
 
+// Forward-mode dual number over the 30 parameters of the IMU factor: what Ceres' Jet<double, 30> is. The functor is
+// differentiated automatically, exactly as the reference does (same derivative values, no hand-derived Jacobian).
+struct Dual30 {
+  double a, v[30];
+  __host__ __device__ Dual30() : a(0) { for (int i = 0; i < 30; i++) v[i] = 0; }
+  __host__ __device__ Dual30(double s) : a(s) { for (int i = 0; i < 30; i++) v[i] = 0; }
+};
+__host__ __device__ inline Dual30 operator+(const Dual30& f, const Dual30& g) { Dual30 h; h.a = f.a + g.a; for (int i = 0; i < 30; i++) h.v[i] = f.v[i] + g.v[i]; return h; }
+__host__ __device__ inline Dual30 operator-(const Dual30& f, const Dual30& g) { Dual30 h; h.a = f.a - g.a; for (int i = 0; i < 30; i++) h.v[i] = f.v[i] - g.v[i]; return h; }
+__host__ __device__ inline Dual30 operator-(const Dual30& f) { Dual30 h; h.a = -f.a; for (int i = 0; i < 30; i++) h.v[i] = -f.v[i]; return h; }
+__host__ __device__ inline Dual30 operator*(const Dual30& f, const Dual30& g) { Dual30 h; h.a = f.a * g.a; for (int i = 0; i < 30; i++) h.v[i] = f.a * g.v[i] + f.v[i] * g.a; return h; }
+__host__ __device__ inline Dual30 operator/(const Dual30& f, const Dual30& g) { Dual30 h; const double gi = 1.0 / g.a, q = f.a * gi; h.a = q; for (int i = 0; i < 30; i++) h.v[i] = (f.v[i] - q * g.v[i]) * gi; return h; }
+__host__ __device__ inline Dual30 chain30(double val_, double d, const Dual30& f) { Dual30 h; h.a = val_; for (int i = 0; i < 30; i++) h.v[i] = d * f.v[i]; return h; }
+__host__ __device__ inline Dual30 dsqrt(const Dual30& f) { const double t = sqrt(f.a); return chain30(t, 1.0 / (2.0 * t), f); }
+__host__ __device__ inline Dual30 dsin(const Dual30& f) { return chain30(sin(f.a), cos(f.a), f); }
+__host__ __device__ inline Dual30 dcos(const Dual30& f) { return chain30(cos(f.a), -sin(f.a), f); }
+__host__ __device__ inline Dual30 datan(const Dual30& f) { return chain30(atan(f.a), 1.0 / (1.0 + f.a * f.a), f); }
+__host__ __device__ inline double val(const Dual30& x) { return x.a; }
+
 // weighted residual r15 = sqrt_info * r and Jacobian J (15 x 30 row-major, columns [PR_i | VBias_i | PR_j | VBias_j])
 void imu_factor_eval(const mml_preint& m, const double* g, const double* pri, const double* vbi, const double* prj,
                      const double* vbj, double* r15, double* J450) {
@@ -167,15 +219,14 @@ void imu_factor_eval(const mml_preint& m, const double* g, const double* pri, co
   double x[30];
   for (int b = 0; b < 4; b++) for (int k = 0; k < sz[b]; k++) x[off[b] + k] = src[b][k];
   double r[15], rw[15 * 31];
-  {
+  if (!J450) {
     imu_residual<double>(m, g, x, x + 6, x + 15, x + 21, r);
     for (int i = 0; i < 15; i++) rw[i] = r[i];
-  }
-  if (J450) for (int c = 0; c < 30; c++) {
-    Dual xd[30], rd[15];
-    for (int k = 0; k < 30; k++) xd[k] = Dual(x[k], k == c ? 1.0 : 0.0);
-    imu_residual<Dual>(m, g, xd, xd + 6, xd + 15, xd + 21, rd);
-    for (int i = 0; i < 15; i++) rw[15 * (1 + c) + i] = rd[i].v;
+  } else {
+    Dual30 xd[30], rd[15];
+    for (int k = 0; k < 30; k++) { xd[k] = Dual30(x[k]); xd[k].v[k] = 1.0; }
+    imu_residual<Dual30>(m, g, xd, xd + 6, xd + 15, xd + 21, rd);
+    for (int i = 0; i < 15; i++) { rw[i] = rd[i].a; for (int c = 0; c < 30; c++) rw[15 * (1 + c) + i] = rd[i].v[c]; }
   }
   for (int i = 0; i < 15; i++) {
     double s = 0;
@@ -216,15 +267,19 @@ bool invert_n(int n, const double* A, double* inv) {  // Gauss-Jordan, partial p
   for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) inv[i * n + j] = a[(size_t)i * 2 * n + n + j];
   return true;
 }
-bool chol_solve_n(int n, const double* A, const double* b, double* x, std::vector<double>& L) {
-  L.assign((size_t)n * n, 0.0);
-  for (int i = 0; i < n; i++) for (int j = 0; j <= i; j++) {
-    double s = A[i * n + j];
-    for (int k = 0; k < j; k++) s -= L[i * n + k] * L[j * n + k];
-    if (i == j) { if (!(s > 0)) return false; L[i * n + i] = sqrt(s); }
-    else L[i * n + j] = s / L[j * n + j];
+bool chol_solve_n(int n, const double* A, const double* b, double* x, std::vector<double>& L, std::vector<double>& y) {
+  L.resize((size_t)n * n);
+  y.resize(n);
+  for (int i = 0; i < n; i++) {
+    double* Li = &L[(size_t)i * n];
+    for (int j = 0; j <= i; j++) {
+      const double* Lj = &L[(size_t)j * n];
+      double s = A[i * n + j];
+      for (int k = 0; k < j; k++) s -= Li[k] * Lj[k];
+      if (i == j) { if (!(s > 0)) return false; Li[i] = sqrt(s); }
+      else Li[j] = s / Lj[j];
+    }
   }
-  std::vector<double> y(n);
   for (int i = 0; i < n; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= L[i * n + k] * y[k]; y[i] = s / L[i * n + i]; }
   for (int i = n - 1; i >= 0; i--) { double s = y[i]; for (int k = i + 1; k < n; k++) s -= L[k * n + i] * x[k]; x[i] = s / L[i * n + i]; }
   return true;
@@ -235,7 +290,7 @@ bool chol_solve_n(int n, const double* A, const double* b, double* x, std::vecto
 // device version (accumulate.cu dogleg_update), driven by evaluations the caller supplies.
 struct DoglegN {
   int n = 0, max_it = 10, it = 0;
-  std::vector<double> x, x_cand, x_best, H, g, scale, Hs, gs, diag, grad, gn, step, A, y, L;
+  std::vector<double> x, x_cand, x_best, H, g, scale, Hs, gs, diag, grad, gn, step, A, y, L, ytmp, vtmp;
   double cost = 0, min_cost = 0, radius = 1e4, mu = 1e-8, alpha = 0, dogleg_norm = 0, model_change = 0, step_norm = 0, x_norm = 0;
   bool reuse = false, first = true, done = false;
   int num_invalid = 0, iterations = 0;
@@ -256,7 +311,8 @@ struct DoglegN {
       for (int i = 0; i < n; i++) diag[i] = sqrt(std::min(std::max(Hs[(size_t)i * n + i], 1e-6), 1e32));
       for (int i = 0; i < n; i++) grad[i] = gs[i] / diag[i];
       double gg = 0, vHv = 0;
-      std::vector<double> v(n);
+      std::vector<double>& v = vtmp;
+      v.resize(n);
       for (int i = 0; i < n; i++) { v[i] = grad[i] / diag[i]; gg += grad[i] * grad[i]; }
       for (int i = 0; i < n; i++) { double s = 0; for (int j = 0; j < n; j++) s += Hs[(size_t)i * n + j] * v[j]; vHv += v[i] * s; }
       alpha = gg / vHv;
@@ -264,7 +320,7 @@ struct DoglegN {
       while (mu < 1.0) {
         A = Hs;
         for (int i = 0; i < n; i++) A[(size_t)i * n + i] += mu * diag[i] * diag[i];
-        bool s_ok = chol_solve_n(n, A.data(), gs.data(), y.data(), L);
+        bool s_ok = chol_solve_n(n, A.data(), gs.data(), y.data(), L, ytmp);
         if (s_ok) for (int i = 0; i < n; i++) if (!std::isfinite(y[i])) s_ok = false;
         if (!s_ok) { mu *= 10.0; continue; }
         for (int i = 0; i < n; i++) gn[i] = -diag[i] * y[i];
@@ -356,8 +412,19 @@ struct DoglegN {
 void mml_window_destroy(mml_ctx* c) {
   if (!c->window) return;
   WindowState* w = static_cast<WindowState*>(c->window);
-  for (auto& s : w->slot) { s.q_corner.release(); s.q_surf.release(); s.f_line.release(); s.f_plane.release(); }
-  w->partials.release(); w->out.release(); w->host.release();
+  for (auto& s : w->slot) {
+    s.q_corner.release(); s.q_surf.release(); s.f_line.release(); s.f_plane.release();
+    s.assoc_stats.release(); s.assoc_part[0].release(); s.assoc_part[1].release();
+  }
+  w->partials.release(); w->out.release();
+  if (w->mapped) cudaFreeHost(w->mapped);
+  if (w->streams_ok) {
+    for (int f = 0; f < kMaxWindow; f++) for (int k = 0; k < 2; k++) { cudaStreamDestroy(w->fstream[f][k]); cudaEventDestroy(w->fev[f][k]); }
+    cudaEventDestroy(w->fork);
+    cudaStreamDestroy(w->xstream);
+    for (int k = 0; k < 2; k++) { cudaEventDestroy(w->xev[k]); cudaEventDestroy(w->xfree[k]); }
+  }
+  for (int k = 0; k < 2; k++) { w->x_xyzi[k].release(); w->x_line[k].release(); w->x_s[k].release(); w->x_label[k].release(); w->x_counters[k].release(); }
   delete w;
   c->window = nullptr;
 }
@@ -519,9 +586,22 @@ int mml_window_push_frame(mml_ctx* c, const float* corner_xyzi, int n_corner, co
 // push a raw scan resident in HBM: extraction (A1) -> undistortion + label split + voxel filter (A4, A6) on the
 // device, the downsampled clouds become the newest window frame. out_counts (may be NULL): n_sharp, n_flat,
 // n_corner_ds, n_surf_ds.
+static int window_push_scan(mml_ctx* c, const void* xyzi_dev, const void* line_id_dev, const void* s_dev, int n, int n_lines,
+                            const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, int max_frames,
+                            int* out_counts, const uint8_t* pre_label, const int* pre_counters);
+
 int mml_window_push_scan_dev(mml_ctx* c, const void* xyzi_dev, const void* line_id_dev, const void* s_dev, int n, int n_lines,
                              const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, int max_frames,
                              int* out_counts) {
+  return window_push_scan(c, xyzi_dev, line_id_dev, s_dev, n, n_lines, dR9, dt3, leaf_corner, leaf_surf, max_frames, out_counts,
+                          nullptr, nullptr);
+}
+
+// pre_label / pre_counters: labels and extractor counters already produced for this scan (the loop labels scan k+1
+// on its own stream while the window of scan k is solved; the caller has made c->stream wait for them)
+static int window_push_scan(mml_ctx* c, const void* xyzi_dev, const void* line_id_dev, const void* s_dev, int n, int n_lines,
+                            const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, int max_frames,
+                            int* out_counts, const uint8_t* pre_label, const int* pre_counters) {
   if (!c || n < 0) return MML_ERR_INVALID;
   cudaSetDevice(c->device);
   MML_CHECK(window_make_room(c, max_frames));
@@ -535,13 +615,19 @@ int mml_window_push_scan_dev(mml_ctx* c, const void* xyzi_dev, const void* line_
   MML_CUDA(c, s.q_surf.reserve(sizeof(float4) * (size_t)cap));
   MML_CUDA(c, c->pin_flags.reserve(64));
   const int off[2] = {0, n};
-  MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, c->in_label.as<uint8_t>(), false));
+  const uint8_t* label_d = pre_label;
+  const int* counters_d = pre_counters;
+  if (!label_d) {
+    MML_CHECK(mml_extract_device(c, (const float4*)xyzi_dev, (const uint16_t*)line_id_dev, off, 1, n_lines, c->in_label.as<uint8_t>(), false));
+    label_d = c->in_label.as<uint8_t>();
+    counters_d = c->counters.as<int>();
+  }
   int* cnt = c->frame_cnt.as<int>();
   const bool undist = dR9 && dt3 && s_dev;
-  MML_CHECK(mml_split_voxel_device(c, (const float4*)xyzi_dev, undist ? (const float*)s_dev : nullptr, c->in_label.as<uint8_t>(), n,
+  MML_CHECK(mml_split_voxel_device(c, (const float4*)xyzi_dev, undist ? (const float*)s_dev : nullptr, label_d, n,
                                    dR9, dt3, leaf_corner, leaf_surf, s.q_corner.as<float4>(), s.q_surf.as<float4>(), cnt));
   int* hf = c->pin_flags.as<int>();
-  MML_CUDA(c, cudaMemcpyAsync(hf, c->counters.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  MML_CUDA(c, cudaMemcpyAsync(hf, counters_d, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
   MML_CUDA(c, cudaMemcpyAsync(hf + 4, cnt, 5 * sizeof(int), cudaMemcpyDeviceToHost, st));
   MML_CUDA(c, cudaStreamSynchronize(st));
   if (hf[2] || hf[8]) return mml_fail(c, MML_ERR_CAPACITY, "scan exceeds the fused extraction / split-voxel capacities (window path)");
@@ -582,7 +668,7 @@ int mml_estimate_window(mml_ctx* c, double* states, const mml_preint* const* pre
   mml_est_params def;
   mml_est_params_default(&def);
   if (!prm) prm = &def;
-  cudaStream_t st = c->stream, st2 = c->stream2;
+  cudaStream_t st = c->stream;
 
   // exRbl = R^T, exPbl = -R^T t (EST.cpp:1155-1156); the functors re-normalise the rotation through a quaternion (CF.h:405-408)
   double Rbl_raw[9], Pbl[3];
@@ -592,20 +678,21 @@ int mml_estimate_window(mml_ctx* c, double* states, const mml_preint* const* pre
   quat_to_R(quat_from_R9(Rbl_raw), Rbl_q);
 
   const int gmax = mml_accumulate_window_grid_max();
+  MML_CHECK(win_prepare(c, w));
   MML_CUDA(c, w->partials.reserve(sizeof(double) * 28 * (size_t)gmax * kMaxWindow + 256));
-  MML_CUDA(c, w->out.reserve(sizeof(double) * (28 + 20) * kMaxWindow + 64));
-  MML_CUDA(c, w->host.reserve(sizeof(double) * (28 + 20) * kMaxWindow + 64));
+  MML_CUDA(c, w->out.reserve(sizeof(double) * 28 * kMaxWindow + 64));
   double* out_dev = w->out.as<double>();
-  double* stat_dev = out_dev + 28 * kMaxWindow;
   unsigned* ticket_dev = reinterpret_cast<unsigned*>(w->partials.as<double>() + 28 * (size_t)gmax * kMaxWindow);
-  double* host = w->host.as<double>();
+  double* host = static_cast<double*>(w->mapped);                 // [0, 28 W) sums, [28 kMaxWindow, ...) statistics
+  volatile unsigned* host_seq = reinterpret_cast<volatile unsigned*>(host + kMapDoubles);
+  unsigned* host_seq_dev = reinterpret_cast<unsigned*>(w->mapped_dev + kMapDoubles);
 
   const int n = (W == 1) ? 6 : 15 * W;  // a lone frame's velocity / bias block has no residual (Ceres drops it)
   double thres = prm->thres0;
   const double huber_a = prm->use_huber ? 0.1 / prm->lidar_m : 0.0;
   int outer_done = 0, inner_total = 0, evals = 0, n_line_last = 0, n_plane_last = 0, is_degenerate = 0;
   double final_cost = 0, min_sv = -1;
-  std::vector<double> x(15 * W), H((size_t)n * n), g(n);
+  std::vector<double> x(15 * W), H((size_t)n * n), g(n), Himu((size_t)n * n), gimu(n);
   DoglegN D;
   const float4* fl[kMaxWindow];
   const float4* fp[kMaxWindow];
@@ -622,7 +709,10 @@ int mml_estimate_window(mml_ctx* c, double* states, const mml_preint* const* pre
     double* sb = states + 16 * (W - 1);
     const Quat q_before = {sb[3], sb[4], sb[5], sb[6]};
     const double t_before[3] = {sb[0], sb[1], sb[2]};
-    // association of every frame (EST.cpp:1265-1299): line || plane on two streams, frames back to back
+    // association of every frame (EST.cpp:1265-1299). The reference joins its two association threads frame by
+    // frame; the frames do not depend on each other, so here all 2 W kernels run side by side on their own streams.
+    const double tp0 = g_prof_on ? now_us() : 0;
+    MML_CUDA(c, cudaEventRecord(w->fork, st));
     for (int f = 0; f < W; f++) {
       WinSlot& s = w->slot[f];
       const double* sf = states + 16 * f;
@@ -633,36 +723,96 @@ int mml_estimate_window(mml_ctx* c, double* states, const mml_preint* const* pre
         T[4 * r + 3] = Rq[3 * r] * Pbl[0] + Rq[3 * r + 1] * Pbl[1] + Rq[3 * r + 2] * Pbl[2] + sf[r];
       }
       T[15] = 1;
-      // the association works on the context's frame slot: lend it this frame's buffers
-      std::swap(c->q_corner, s.q_corner); std::swap(c->q_surf, s.q_surf);
-      std::swap(c->f_line, s.f_line); std::swap(c->f_plane, s.f_plane);
+      // the association works on the context's frame slot and statistics: lend it this frame's buffers
+      auto lend = [&]() {
+        std::swap(c->q_corner, s.q_corner); std::swap(c->q_surf, s.q_surf);
+        std::swap(c->f_line, s.f_line); std::swap(c->f_plane, s.f_plane);
+        std::swap(c->assoc_stats, s.assoc_stats);
+        std::swap(c->assoc_part[0], s.assoc_part[0]); std::swap(c->assoc_part[1], s.assoc_part[1]);
+      };
+      lend();
       c->has_perm[0] = c->has_perm[1] = false;
       int rc = MML_OK;
-      if (cudaEventRecord(c->ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(st2, c->ev_fork, 0) != cudaSuccess) rc = MML_ERR_CUDA;
-      if (rc == MML_OK) {
-        c->stream = st2;
-        rc = mml_associate_launch(c, 1, T, (float)thres, nullptr, nullptr, nullptr, nullptr, s.n_surf);
+      for (int kind = 1; kind >= 0 && rc == MML_OK; kind--) {
+        cudaStream_t fs = w->fstream[f][kind];
+        if (cudaStreamWaitEvent(fs, w->fork, 0) != cudaSuccess) { rc = MML_ERR_CUDA; break; }
+        c->stream = fs;
+        rc = mml_associate_launch(c, kind, T, (float)thres, nullptr, nullptr, nullptr, nullptr, kind ? s.n_surf : s.n_corner);
         c->stream = st;
+        if (rc == MML_OK && cudaEventRecord(w->fev[f][kind], fs) != cudaSuccess) rc = MML_ERR_CUDA;
       }
-      if (rc == MML_OK) rc = mml_associate_launch(c, 0, T, (float)thres, nullptr, nullptr, nullptr, nullptr, s.n_corner);
-      if (rc == MML_OK && (cudaEventRecord(c->ev_join, st2) != cudaSuccess || cudaStreamWaitEvent(st, c->ev_join, 0) != cudaSuccess)) rc = MML_ERR_CUDA;
-      std::swap(c->q_corner, s.q_corner); std::swap(c->q_surf, s.q_surf);
-      std::swap(c->f_line, s.f_line); std::swap(c->f_plane, s.f_plane);
+      lend();
       MML_CHECK(rc);
-      MML_CUDA(c, cudaMemcpyAsync(stat_dev + 20 * f, c->assoc_stats.p, sizeof(double) * 20, cudaMemcpyDeviceToDevice, st));
       fl[f] = s.f_line.as<float4>(); fp[f] = s.f_plane.as<float4>();
       nl[f] = s.n_corner; np[f] = s.n_surf;
     }
+    for (int f = 0; f < W; f++) for (int kind = 0; kind < 2; kind++) MML_CUDA(c, cudaStreamWaitEvent(st, w->fev[f][kind], 0));
+    for (int f = 0; f < W; f++)  // both kinds of a frame write into the same 160-byte block (line: [0, 8), plane: [8, 16), counts)
+      MML_CUDA(c, cudaMemcpyAsync(host + 28 * kMaxWindow + 20 * f, w->slot[f].assoc_stats.p, sizeof(double) * 20, cudaMemcpyDeviceToHost, st));
     thres = (it == 0) ? prm->thres1 : prm->thres2;  // EST.cpp:1377-1381
+    if (g_prof_on) g_prof.assoc += now_us() - tp0;
 
     D.begin(n, x.data(), prm->max_inner);
     bool stats_read = false;
     while (!D.done) {
       const double* xe = D.eval_point();
+      const unsigned seq = ++w->seq;
+      const double te0 = g_prof_on ? now_us() : 0;
       MML_CHECK(mml_accumulate_window_launch(c, W, fl, fp, nl, np, xe, Rbl_q, Pbl, prm->lidar_m, prm->plan_weight_tan, huber_a,
-                                             w->partials.as<double>(), ticket_dev, out_dev));
-      MML_CUDA(c, cudaMemcpyAsync(host, out_dev, sizeof(double) * (stats_read ? 28 * W : (28 + 20) * kMaxWindow), cudaMemcpyDeviceToHost, st));
-      MML_CUDA(c, cudaStreamSynchronize(st));
+                                             w->partials.as<double>(), ticket_dev, out_dev, w->mapped_dev, host_seq_dev, seq));
+      // while the device evaluates the lidar terms, the host evaluates the IMU factors at the same point
+      const double te1 = g_prof_on ? now_us() : 0;
+      double cost_imu = 0;
+      std::fill(Himu.begin(), Himu.end(), 0.0);
+      std::fill(gimu.begin(), gimu.end(), 0.0);
+      for (int f = 1; f < W; f++) {
+        double r[15], J[450];
+        imu_factor_eval(*preints[f], gravity3, xe + 6 * (f - 1), xe + 6 * W + 9 * (f - 1), xe + 6 * f, xe + 6 * W + 9 * f, r, J);
+        for (int k = 0; k < 15; k++) cost_imu += 0.5 * r[k] * r[k];
+        int gidx[30];
+        {
+          const int off[4] = {6 * (f - 1), 6 * W + 9 * (f - 1), 6 * f, 6 * W + 9 * f};
+          const int sz[4] = {6, 9, 6, 9};
+          int q = 0;
+          for (int b = 0; b < 4; b++) for (int i = 0; i < sz[b]; i++) gidx[q++] = off[b] + i;
+        }
+        double JtJ[900];
+        for (int i = 0; i < 30; i++) {
+          double sg = 0;
+          for (int k = 0; k < 15; k++) sg += J[k * 30 + i] * r[k];
+          gimu[gidx[i]] += sg;
+          for (int j = i; j < 30; j++) {
+            double sh = 0;
+            for (int k = 0; k < 15; k++) sh += J[k * 30 + i] * J[k * 30 + j];
+            JtJ[i * 30 + j] = sh;
+          }
+        }
+        for (int i = 0; i < 30; i++) for (int j = i; j < 30; j++) {
+          Himu[(size_t)gidx[i] * n + gidx[j]] += JtJ[i * 30 + j];
+          if (j != i) Himu[(size_t)gidx[j] * n + gidx[i]] += JtJ[i * 30 + j];
+        }
+      }
+      // wait for the device: the kernel's last CTAs publish `seq` after their sums (system-scope fence)
+      const double te2 = g_prof_on ? now_us() : 0;
+      {
+        long spins = 0;
+        bool ready = false;
+        while (!ready) {
+          ready = true;
+          for (int f = 0; f < W; f++) if (host_seq[f] != seq) { ready = false; break; }
+          if (!ready && (++spins & 0xFFFF) == 0) {
+            cudaError_t e = cudaStreamQuery(st);
+            if (e != cudaSuccess && e != cudaErrorNotReady) { c->err = std::string("window evaluation: ") + cudaGetErrorString(e); return MML_ERR_CUDA; }
+            if (e == cudaSuccess) {  // stream drained: the flags must be there now
+              bool all = true;
+              for (int f = 0; f < W; f++) all = all && host_seq[f] == seq;
+              if (!all) return mml_fail(c, MML_ERR_CUDA, "window evaluation finished without publishing its result");
+            }
+          }
+        }
+        __sync_synchronize();
+      }
+      const double te3 = g_prof_on ? now_us() : 0;
       evals++;
       if (!stats_read) {
         stats_read = true;
@@ -677,10 +827,10 @@ int mml_estimate_window(mml_ctx* c, double* states, const mml_preint* const* pre
           if (f == W - 1) { n_line_last = ints[0]; n_plane_last = ints[1]; min_sv = sv; }
         }
       }
-      // assemble: lidar blocks from the device sums, IMU factors on the host
-      double cost = 0;
-      std::fill(H.begin(), H.end(), 0.0);
-      std::fill(g.begin(), g.end(), 0.0);
+      // assemble: lidar blocks from the device sums + the IMU part
+      double cost = cost_imu;
+      H = Himu;
+      g = gimu;
       for (int f = 0; f < W; f++) {
         const double* o = host + 28 * f;
         cost += o[0];
@@ -691,25 +841,11 @@ int mml_estimate_window(mml_ctx* c, double* states, const mml_preint* const* pre
           if (j != i) H[(size_t)(6 * f + j) * n + 6 * f + i] += o[k];
         }
       }
-      for (int f = 1; f < W; f++) {
-        double r[15], J[450];
-        imu_factor_eval(*preints[f], gravity3, xe + 6 * (f - 1), xe + 6 * W + 9 * (f - 1), xe + 6 * f, xe + 6 * W + 9 * f, r, J);
-        for (int k = 0; k < 15; k++) cost += 0.5 * r[k] * r[k];
-        const int off[4] = {6 * (f - 1), 6 * W + 9 * (f - 1), 6 * f, 6 * W + 9 * f};
-        const int sz[4] = {6, 9, 6, 9}, col0[4] = {0, 6, 15, 21};
-        for (int b = 0; b < 4; b++) for (int i = 0; i < sz[b]; i++) {
-          const int gi = off[b] + i, ci = col0[b] + i;
-          double sg = 0;
-          for (int k = 0; k < 15; k++) sg += J[k * 30 + ci] * r[k];
-          g[gi] += sg;
-          for (int b2 = 0; b2 < 4; b2++) for (int j = 0; j < sz[b2]; j++) {
-            double sh = 0;
-            for (int k = 0; k < 15; k++) sh += J[k * 30 + ci] * J[k * 30 + col0[b2] + j];
-            H[(size_t)gi * n + off[b2] + j] += sh;
-          }
-        }
-      }
       D.feed(cost, H.data(), g.data());
+      if (g_prof_on) {
+        const double te4 = now_us();
+        g_prof.launch += te1 - te0; g_prof.imu += te2 - te1; g_prof.wait += te3 - te2; g_prof.solve += te4 - te3; g_prof.evals++;
+      }
     }
     inner_total += D.iterations;
     final_cost = D.min_cost;
@@ -767,7 +903,43 @@ int mml_odom_run_window(mml_ctx* c, const void* const* xyzi, const void* const* 
   memcpy(prev, state0, sizeof(prev));
   double t_prev = stamp0;
   size_t imu_off = 0;
+  WindowState* w = win(c);
+  MML_CHECK(win_prepare(c, w));
   if (total_ms) { MML_CUDA(c, cudaEventRecord(c->ev0, c->stream)); }
+  // labels do not depend on the pose (the extraction node of the reference runs ahead of the estimator, FE.cpp ->
+  // /union_feature_cloud -> PE.cpp): scan k+1 is copied and labelled on its own stream while scan k is solved
+  const void* xdv[2] = {nullptr, nullptr};
+  const void* ldv[2] = {nullptr, nullptr};
+  const void* sdv[2] = {nullptr, nullptr};
+  auto prefetch = [&](int k) -> int {
+    const int b = k & 1;
+    const size_t n = (size_t)n_pts[k];
+    cudaStream_t xs = w->xstream;
+    MML_CUDA(c, cudaStreamWaitEvent(xs, w->xfree[b], 0));  // the previous user of this buffer pair (scan k-2) is done with it
+    xdv[b] = xyzi[k]; ldv[b] = line[k]; sdv[b] = s ? s[k] : nullptr;
+    if (host_buffers) {
+      MML_CUDA(c, w->x_xyzi[b].reserve(sizeof(float4) * (n + 1)));
+      MML_CUDA(c, w->x_line[b].reserve(sizeof(uint16_t) * (n + 1)));
+      MML_CUDA(c, w->x_s[b].reserve(sizeof(float) * (n + 1)));
+      MML_CUDA(c, cudaMemcpyAsync(w->x_xyzi[b].p, xyzi[k], sizeof(float4) * n, cudaMemcpyHostToDevice, xs));
+      MML_CUDA(c, cudaMemcpyAsync(w->x_line[b].p, line[k], sizeof(uint16_t) * n, cudaMemcpyHostToDevice, xs));
+      if (sdv[b]) MML_CUDA(c, cudaMemcpyAsync(w->x_s[b].p, s[k], sizeof(float) * n, cudaMemcpyHostToDevice, xs));
+      xdv[b] = w->x_xyzi[b].p; ldv[b] = w->x_line[b].p; sdv[b] = sdv[b] ? w->x_s[b].p : nullptr;
+    }
+    MML_CUDA(c, w->x_label[b].reserve(n + 16));
+    MML_CUDA(c, w->x_counters[b].reserve(sizeof(int) * 80));
+    const int off[2] = {0, (int)n};
+    cudaStream_t keep = c->stream;
+    c->stream = xs;
+    c->counters_alt = w->x_counters[b].as<int>();
+    const int rc = mml_extract_device(c, (const float4*)xdv[b], (const uint16_t*)ldv[b], off, 1, n_lines, w->x_label[b].as<uint8_t>(), false);
+    c->counters_alt = nullptr;
+    c->stream = keep;
+    MML_CHECK(rc);
+    MML_CUDA(c, cudaEventRecord(w->xev[b], xs));
+    return MML_OK;
+  };
+  if (n_scans > 0) MML_CHECK(prefetch(0));
   auto pose16 = [](const double* st, double* T) {
     double R[9];
     quat_to_R(Quat{st[3], st[4], st[5], st[6]}, R);
@@ -790,22 +962,19 @@ int mml_odom_run_window(mml_ctx* c, const void* const* xyzi, const void* const* 
     mat4_mul(inv, Twl_n, dT);
     const double dR9[9] = {dT[0], dT[1], dT[2], dT[4], dT[5], dT[6], dT[8], dT[9], dT[10]};
     const double dt3[3] = {dT[3], dT[7], dT[11]};
-    const void *xd = xyzi[k], *ld = line[k], *sd = s ? s[k] : nullptr;
-    if (host_buffers) {
-      const size_t n = (size_t)n_pts[k];
-      MML_CUDA(c, c->in_xyzi.reserve(sizeof(float4) * (n + 1)));
-      MML_CUDA(c, c->in_line.reserve(sizeof(uint16_t) * (n + 1)));
-      MML_CUDA(c, c->in_s.reserve(sizeof(float) * (n + 1)));
-      MML_CUDA(c, cudaMemcpyAsync(c->in_xyzi.p, xyzi[k], sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream));
-      MML_CUDA(c, cudaMemcpyAsync(c->in_line.p, line[k], sizeof(uint16_t) * n, cudaMemcpyHostToDevice, c->stream));
-      if (sd) MML_CUDA(c, cudaMemcpyAsync(c->in_s.p, s[k], sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
-      xd = c->in_xyzi.p; ld = c->in_line.p; sd = sd ? c->in_s.p : nullptr;
-    }
+    const int b = k & 1;
+    const void *xd = xdv[b], *ld = ldv[b], *sd = sdv[b];
+    MML_CUDA(c, cudaStreamWaitEvent(c->stream, w->xev[b], 0));
+    const double tq0 = g_prof_on ? now_us() : 0;
     if ((int)(states.size() / 16) >= window) {  // PE.cpp:830-832
       states.erase(states.begin(), states.begin() + 16);
       pre_store.erase(pre_store.begin());
     }
-    MML_CHECK(mml_window_push_scan_dev(c, xd, ld, sd, n_pts[k], n_lines, dR9, dt3, leaf_corner, leaf_surf, window, nullptr));
+    MML_CHECK(window_push_scan(c, xd, ld, sd, n_pts[k], n_lines, dR9, dt3, leaf_corner, leaf_surf, window, nullptr,
+                               w->x_label[b].as<uint8_t>(), w->x_counters[b].as<int>()));
+    MML_CUDA(c, cudaEventRecord(w->xfree[b], c->stream));  // raw scan, labels and counters of this buffer pair are consumed
+    if (k + 1 < n_scans) MML_CHECK(prefetch(k + 1));
+    if (g_prof_on) { g_prof.push += now_us() - tq0; g_prof.scans++; }
     states.insert(states.end(), next, next + 16);
     pre_store.push_back(pre);
     const int W = (int)(states.size() / 16);
@@ -824,6 +993,12 @@ int mml_odom_run_window(mml_ctx* c, const void* const* xyzi, const void* const* 
     MML_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     MML_CUDA(c, cudaEventSynchronize(c->ev1));
     MML_CUDA(c, cudaEventElapsedTime(total_ms, c->ev0, c->ev1));
+  }
+  if (g_prof_on && g_prof.scans) {
+    const double ns = (double)g_prof.scans, ne = (double)(g_prof.evals ? g_prof.evals : 1);
+    fprintf(stderr, "[mml window prof] per scan: push %.1f us, association enqueue %.1f us, evaluations %.1f; per evaluation: launch %.1f, imu %.1f, wait %.1f, assemble+dogleg %.1f us\n",
+            g_prof.push / ns, g_prof.assoc / ns, g_prof.evals / ns, g_prof.launch / ne, g_prof.imu / ne, g_prof.wait / ne, g_prof.solve / ne);
+    g_prof = WinProf();
   }
   return MML_OK;
 }

@@ -345,11 +345,15 @@ struct AssocArgs {
   const int* nq_dev;        // optional: query count read from device memory (<= nq)
   int* overflow;            // set to 1 when *nq_dev exceeds the launch capacity nq
   const unsigned* perm;     // optional: queries were spatially sorted; perm[i] = original index of query i
-  const int* qlist;         // optional: process queries qlist[0 .. *nq_dev) instead of 0 .. nq (tile fallback)
-  int* fallback_list;       // tile kernel: queries it could not finish, and their count
-  int* fallback_count;
+  const int* qlist;         // optional: process queries qlist[0 .. *nq_dev) instead of 0 .. nq
   int accumulate_out;       // add to moment_out / n_feat_out instead of overwriting
-  int tile_halo;            // tile kernel: halo (cells) around the queries' cell box
+  // map-sized sets: the neighbour search runs in its own kernel (k_knn_walk) and leaves, per sorted query, the five
+  // neighbours' positions in the cell-sorted point array and a status; the fit kernel (k_associate<KIND, true>)
+  // picks them up. pre_map = index (0 global / 1 local) of the map that was searched.
+  int* pre_loc;             // [nq][5]
+  int* pre_status;          // [nq]: -1 no search (query outside the grid / NaN), 0 no 5 neighbours inside thres,
+                            //        1 found, 2 undecided (the fit kernel searches itself)
+  int pre_map;
   double T[16];
   float thres;
   GridDev G[2];  // [0] global, [1] local
@@ -419,7 +423,37 @@ __device__ bool fit_plane(const float4* pts, const KnnT& r, float sx, float sy, 
   return true;
 }
 
-template <int KIND>
+// ---------------------------------------------------------------- map-sized sets: search kernel
+// Map-sized query sets (S4 / S5) run the neighbour search and the fit as two kernels: the search keeps 56 registers
+// (the fused kernel: 72 + 248 B of stack for the float64 QR), the fit runs with every lane busy, and the pair is
+// 12 % faster than the fused kernel at 1.05 M queries (0.685 vs 0.776 ms, profiles/r2_s4_knn_experiments.txt).
+__global__ void __launch_bounds__(128) k_knn_walk(AssocArgs A) {
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= A.nq) return;
+  const GridDev& G = A.G[A.pre_map];
+  const float4 q = A.q[i];
+  const double pin[3] = {(double)q.x, (double)q.y, (double)q.z};
+  float sel[3];
+#pragma unroll
+  for (int rr = 0; rr < 3; rr++)
+    sel[rr] = (float)(((A.T[4 * rr] * pin[0] + A.T[4 * rr + 1] * pin[1]) + A.T[4 * rr + 2] * pin[2]) + A.T[4 * rr + 3]);
+  int cI, cJ, cK;
+  const bool in_grid = cube_of(sel[0], sel[1], sel[2], A.G[0].cen, cI, cJ, cK);
+  const bool finite = !(isnan(sel[0]) || isnan(sel[1]) || isnan(sel[2]));
+  int status = -1;
+  if (in_grid && finite) {
+    KnnP r;
+    status = knn5_grid_packed(G, sel[0], sel[1], sel[2], A.thres, r) ? 1 : 0;
+    if (status == 1) {
+#pragma unroll
+      for (int k = 0; k < 5; k++) A.pre_loc[5 * (size_t)i + k] = r.loc[k];
+    }
+  }
+  A.pre_status[i] = status;
+}
+
+// PRE: the neighbour search of map A.pre_map was done by k_knn_walk
+template <int KIND, bool PRE>
 __global__ void __launch_bounds__(128) k_associate(AssocArgs A) {
   if (A.gate && *A.gate) return;
   const int i = blockIdx.x * 128 + threadIdx.x;
@@ -453,7 +487,19 @@ __global__ void __launch_bounds__(128) k_associate(AssocArgs A) {
       for (int mp = 0; mp < 2 && !found; mp++) {
         const GridDev& G = A.G[mp];
         if (!G.valid) continue;
-        if (!knn5_grid_packed(G, sel[0], sel[1], sel[2], thres, r)) continue;
+        bool have;
+        int pre = 2;
+        if (PRE && mp == A.pre_map) pre = A.pre_status[i];
+        if (pre == 2) {
+          have = knn5_grid_packed(G, sel[0], sel[1], sel[2], thres, r);
+        } else {
+          have = pre == 1;
+          if (have) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) r.loc[k] = A.pre_loc[5 * (size_t)i + k];
+          }
+        }
+        if (!have) continue;
         if (KIND == 0) {
           float a[3], b[3];
           if (!fit_line(G.pts, r, a, b)) continue;
@@ -919,216 +965,6 @@ __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
   }
 }
 
-// ---------------------------------------------------------------- tile kernel (dense, sorted query sets)
-// 128 spatially consecutive queries per CTA, one thread each. The CTA stages every map point of the cell box
-// that covers the 3x3x3 neighbourhoods of all its queries into shared memory (row ranges are contiguous in
-// HBM: coalesced float4 loads), then every thread scans the staged points from shared memory: the loop is
-// uniform across the CTA (broadcast LDS, no divergent pointer chasing) and the 5-list insertion is rare after
-// the first few points. A query is final when its 5th distance is inside the one-cell reach; the few others
-// (and tiles whose box does not fit) go to a fallback list that the group kernel finishes.
-constexpr int kTileQ = 128;
-constexpr int kTilePts = 2560;   // staged points (40 KB)
-constexpr int kTileRows = 384;   // (y,z) rows of the staged cell box
-
-template <int KIND>
-__global__ void __launch_bounds__(kTileQ) k_associate_tile(AssocArgs A) {
-  __shared__ float4 sp[kTilePts];
-  __shared__ int row_start[kTileRows + 1];
-  __shared__ int row_src[kTileRows];
-  __shared__ int s_min[3], s_max[3], s_region_ok, s_npts;
-  __shared__ double sred[4][7];
-  __shared__ bool is_last;
-  const int tid = threadIdx.x;
-  const int i = blockIdx.x * kTileQ + tid;
-  const int nq = A.nq;
-  const GridDev& Gd = A.G[1];  // dense sweeps run against the local (single-region) map
-  double T[16];
-#pragma unroll
-  for (int k = 0; k < 16; k++) T[k] = A.T[k];
-  const float thres = A.thres;
-  if (tid < 3) { s_min[tid] = 0x7fffffff; s_max[tid] = -0x7fffffff; }
-  if (tid == 0) { s_region_ok = 1; s_npts = 0; }
-  __syncthreads();
-  float4 q = make_float4(0, 0, 0, 0);
-  float sel[3] = {0, 0, 0};
-  int c[3] = {0, 0, 0}, lo[3], hi[3], cube;
-  bool valid = false;
-  if (i < nq) {
-    q = A.q[i];
-    const double pin[3] = {(double)q.x, (double)q.y, (double)q.z};
-#pragma unroll
-    for (int rr = 0; rr < 3; rr++)
-      sel[rr] = (float)(((T[4 * rr] * pin[0] + T[4 * rr + 1] * pin[1]) + T[4 * rr + 2] * pin[2]) + T[4 * rr + 3]);
-    int cI, cJ, cK;
-    const bool in_grid = cube_of(sel[0], sel[1], sel[2], A.G[0].cen, cI, cJ, cK);
-    const bool finite = !(isnan(sel[0]) || isnan(sel[1]) || isnan(sel[2]));
-    valid = in_grid && finite && locate(Gd, sel[0], sel[1], sel[2], c, lo, hi, cube) && Gd.m > Gd.min_local_pts;
-    if (valid) {
-#pragma unroll
-      for (int a = 0; a < 3; a++) { atomicMin(&s_min[a], c[a]); atomicMax(&s_max[a], c[a]); }
-    }
-  }
-  __syncthreads();
-  // cell box with a halo of tile_halo cells, clipped to the grid
-  int b0[3], b1[3];
-#pragma unroll
-  for (int a = 0; a < 3; a++) { b0[a] = max(s_min[a] - A.tile_halo, 0); b1[a] = min(s_max[a] + A.tile_halo, Gd.dim[a] - 1); }
-  const bool any = s_max[0] >= s_min[0];
-  const int ny = b1[1] - b0[1] + 1, nz = b1[2] - b0[2] + 1;
-  const int nrows = any ? ny * nz : 0;
-  if (tid == 0 && nrows > kTileRows) s_region_ok = 0;
-  __syncthreads();
-  bool tile_ok = any && s_region_ok;
-  if (tile_ok) {
-    for (int r = tid; r < nrows; r += kTileQ) {
-      const int y = b0[1] + r % ny, z = b0[2] + r / ny;
-      const int rowb = (z * Gd.dim[1] + y) * Gd.dim[0];
-      const int s0 = __ldg(Gd.cell_start + rowb + b0[0]), e0 = __ldg(Gd.cell_start + rowb + b1[0] + 1);
-      row_src[r] = s0;
-      row_start[r] = e0 - s0;  // length for now
-    }
-    __syncthreads();
-    if (tid == 0) {  // exclusive scan of the row lengths (<= 384 rows)
-      int run = 0;
-      for (int r = 0; r < nrows; r++) { const int len = row_start[r]; row_start[r] = run; run += len; }
-      row_start[nrows] = run;
-      s_npts = run;
-      if (run > kTilePts) s_region_ok = 0;
-    }
-    __syncthreads();
-    tile_ok = s_region_ok;
-    if (tile_ok) {
-      for (int r = 0; r < nrows; r++) {
-        const int len = row_start[r + 1] - row_start[r];
-        for (int k = tid; k < len; k += kTileQ) sp[row_start[r] + k] = __ldg(Gd.pts + row_src[r] + k);
-      }
-    }
-    __syncthreads();
-  }
-  double mom[7] = {0, 0, 0, 0, 0, 0, 0};
-  int found = 0;
-  bool need_fallback = false;
-  if (i < nq) {
-    float4 f0 = make_float4(q.x, q.y, q.z, -1.f), f1 = make_float4(0, 0, 0, 0), f2 = make_float4(0, 0, 0, 0);
-    if (valid && !tile_ok) {
-      need_fallback = true;
-    } else if (valid) {
-      Knn5 r;
-      knn_init(r);
-      const int np_ = s_npts;
-      for (int k = 0; k < np_; k++) {
-        const float4 p = sp[k];
-        const float dx = sel[0] - p.x, dy = sel[1] - p.y, dz = sel[2] - p.z;
-        const float d = (dx * dx + dy * dy) + dz * dz;
-        knn_push(r, d, __float_as_int(p.w), k);
-      }
-      // distance from the query to the edge of the staged box (everything outside is farther than that);
-      // a box side clipped at the grid boundary has nothing beyond it
-      const float cellf = Gd.cell;
-      bool closed = true;  // the box spans the whole grid
-      int margin_cells = 0x7fffffff;
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        if (b0[a] > 0) { closed = false; margin_cells = min(margin_cells, c[a] - b0[a]); }
-        if (b1[a] < Gd.dim[a] - 1) { closed = false; margin_cells = min(margin_cells, b1[a] - c[a]); }
-      }
-      const float reach = closed ? INFINITY : fmaxf((float)margin_cells * cellf - 1e-3f, 0.f);
-      const float reach2 = reach * reach;
-      const bool final_list = (r.cnt == 5 && r.d[4] <= reach2) || reach2 >= thres;
-      if (!final_list) {
-        need_fallback = true;
-      } else if (r.cnt == 5 && r.d[4] < thres) {
-        const double pin[3] = {(double)q.x, (double)q.y, (double)q.z};
-        if (KIND == 0) {
-          float a[3], b[3];
-          if (fit_line(sp, r, a, b)) {
-            f1 = make_float4(a[0], a[1], a[2], b[0]);
-            f2 = make_float4(b[1], b[2], 0.f, 0.f);
-            double P[3];
-#pragma unroll
-            for (int rr = 0; rr < 3; rr++)
-              P[rr] = ((T[4 * rr] * pin[0] + T[4 * rr + 1] * pin[1]) + T[4 * rr + 2] * pin[2]) + T[4 * rr + 3];
-            const double da[3] = {a[0], a[1], a[2]}, db[3] = {b[0], b[1], b[2]};
-            const double l12 = sqrt((da[0] - db[0]) * (da[0] - db[0]) + (da[1] - db[1]) * (da[1] - db[1]) +
-                                    (da[2] - db[2]) * (da[2] - db[2]));
-            const double c0 = (P[0] - da[0]) * (P[1] - db[1]) - (P[0] - db[0]) * (P[1] - da[1]);
-            const double c1 = (P[0] - da[0]) * (P[2] - db[2]) - (P[0] - db[0]) * (P[2] - da[2]);
-            const double c2 = (P[1] - da[1]) * (P[2] - db[2]) - (P[1] - db[1]) * (P[2] - da[2]);
-            const double err = sqrt(c0 * c0 + c1 * c1 + c2 * c2) / l12;
-            f0.w = (fabs(err) > 1e-5) ? 1.f : 0.f;
-            f2.z = (float)err;
-            found = 1;
-          }
-        } else {
-          float nrm[3], dist;
-          if (fit_plane(sp, r, sel[0], sel[1], sel[2], nrm, &dist)) {
-            f1 = make_float4(sel[0], sel[1], sel[2], dist);
-            f2 = make_float4(nrm[0], nrm[1], nrm[2], 0.f);
-            double e[3];
-#pragma unroll
-            for (int rr = 0; rr < 3; rr++) {
-              const double P = ((T[4 * rr] * pin[0] + T[4 * rr + 1] * pin[1]) + T[4 * rr + 2] * pin[2]) + T[4 * rr + 3];
-              const double proj = (double)sel[rr] - (double)dist * (double)nrm[rr];
-              e[rr] = P - proj;
-            }
-            const double err = sqrt((e[0] * e[0] + e[1] * e[1]) + e[2] * e[2]);
-            f0.w = (fabs(err) > 1e-5) ? 1.f : 0.f;
-            f2.w = (float)err;
-            const double n0 = nrm[0], n1 = nrm[1], n2 = nrm[2];
-            mom[0] = n0 * n0; mom[1] = n0 * n1; mom[2] = n0 * n2; mom[3] = n1 * n1; mom[4] = n1 * n2; mom[5] = n2 * n2;
-            found = 1;
-          }
-        }
-      }
-    }
-    if (need_fallback) {
-      A.fallback_list[atomicAdd(A.fallback_count, 1)] = i;
-    } else {
-      const size_t slot = A.perm ? (size_t)A.perm[i] : (size_t)i;
-      A.feat[3 * slot] = f0;
-      A.feat[3 * slot + 1] = f1;
-      A.feat[3 * slot + 2] = f2;
-    }
-  }
-  mom[6] = (double)found;
-#pragma unroll
-  for (int k = 0; k < 7; k++) {
-    double v = mom[k];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    if ((tid & 31) == 0) sred[tid >> 5][k] = v;
-  }
-  __syncthreads();
-  if (tid < 7) {
-    const double v = ((sred[0][tid] + sred[1][tid]) + sred[2][tid]) + sred[3][tid];
-    A.moment_partials[(size_t)blockIdx.x * 8 + tid] = v;
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) is_last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    // 7 components x 16 interleaved lanes, then a fixed-order combine
-    __shared__ double part[16][7];
-    const int comp = tid & 7, lane16 = tid >> 3;
-    double s = 0;
-    if (comp < 7)
-      for (unsigned b = lane16; b < gridDim.x; b += 16) s += __ldcg(A.moment_partials + (size_t)b * 8 + comp);
-    if (comp < 7) part[lane16][comp] = s;
-    __syncthreads();
-    if (tid < 7) {
-      double t = 0;
-      for (int k = 0; k < 16; k++) t += part[k][tid];
-      A.moment_out[tid] = t;
-      if (tid == 6) *A.n_feat_out = (int)t;
-    }
-    __syncwarp();
-    if (KIND == 1 && tid == 0) publish_localizability(A.moment_out);
-    if (tid == 0) *A.ticket = 0;
-  }
-}
-
 // expand compact features to the host-visible 12-double records of include/mmloam_b200.h
 template <int KIND>
 __global__ void __launch_bounds__(256) k_export_features(const float4* __restrict__ feat, int nq, double* __restrict__ out) {
@@ -1363,34 +1199,23 @@ int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres,
   A.tl_slot = kind == 1 ? 2 : 4;
   A.overflow = ints + 6;
   A.perm = ctx->has_perm[kind] ? ctx->perm[kind].as<unsigned>() : nullptr;
-  static const int tile_env = getenv("MML_ASSOC_TILE") ? atoi(getenv("MML_ASSOC_TILE")) : 0;  // experiment: lost to the sorted thread-per-query kernel
-  const bool use_tile = tile_env && ctx->has_perm[kind] && !nq_dev && !T_dev && !A.G[0].valid && A.G[1].valid && !g_env;
-  if (use_tile) {
-    // dense sorted sweep: tile kernel, then the group kernel finishes whatever the tiles left open
-    MML_CUDA(ctx, ctx->fallback[kind].reserve(sizeof(int) * ((size_t)nq + 16)));
-    int* fb_cnt = ctx->fallback[kind].as<int>();
-    int* fb_list = fb_cnt + 16;
-    MML_CUDA(ctx, cudaMemsetAsync(fb_cnt, 0, sizeof(int), ctx->stream));
-    const int tgrid = div_up(nq, kTileQ);
-    const int g8 = div_up(nq, 128 / 8);  // fallback launch: 8 lanes per query
-    MML_CUDA(ctx, ctx->assoc_part[kind].reserve(sizeof(double) * 8 * (size_t)(tgrid > g8 ? tgrid : g8) + 64));
-    A.moment_partials = ctx->assoc_part[kind].as<double>();
-    A.fallback_list = fb_list;
-    A.fallback_count = fb_cnt;
-    static const int halo_env = getenv("MML_TILE_HALO") ? atoi(getenv("MML_TILE_HALO")) : 3;
-    A.tile_halo = halo_env;
-    if (kind == 0) k_associate_tile<0><<<tgrid, kTileQ, 0, ctx->stream>>>(A);
-    else k_associate_tile<1><<<tgrid, kTileQ, 0, ctx->stream>>>(A);
-    MML_LAUNCHED(ctx);
-    AssocArgs B = A;
-    B.qlist = fb_list;
-    B.nq_dev = fb_cnt;
-    B.accumulate_out = 1;
-    if (kind == 0) k_associate_g<0, 8><<<g8, 128, 0, ctx->stream>>>(B);
-    else k_associate_g<1, 8><<<g8, 128, 0, ctx->stream>>>(B);
-    MML_LAUNCHED(ctx);
-    MML_CUDA(ctx, cudaGetLastError());
-    return MML_OK;
+  // map-sized, spatially sorted sets: search kernel, then fit kernel (MML_ASSOC_SPLIT=0: the fused kernel)
+  static const int split_env = getenv("MML_ASSOC_SPLIT") ? atoi(getenv("MML_ASSOC_SPLIT")) : 1;
+  if (G == 1 && split_env && ctx->has_perm[kind] && !nq_dev && !T_dev && !gate && nq > 0) {
+    mml::DevBuf& pb = ctx->pre_knn[kind];  // [nq][5] positions + [nq] status
+    MML_CUDA(ctx, pb.reserve(sizeof(int) * 6 * (size_t)nq + 64));
+    A.pre_loc = pb.as<int>();
+    A.pre_status = pb.as<int>() + 5 * (size_t)nq;
+    A.pre_map = A.G[0].valid ? 0 : 1;
+    if (A.G[A.pre_map].valid) {
+      k_knn_walk<<<grid, 128, 0, ctx->stream>>>(A);
+      MML_LAUNCHED(ctx);
+      if (kind == 0) k_associate<0, true><<<grid, 128, 0, ctx->stream>>>(A);
+      else k_associate<1, true><<<grid, 128, 0, ctx->stream>>>(A);
+      MML_LAUNCHED(ctx);
+      MML_CUDA(ctx, cudaGetLastError());
+      return MML_OK;
+    }
   }
   if (G == 32) {
     if (kind == 0) k_associate_g<0, 32><<<grid, 128, 0, ctx->stream>>>(A);
@@ -1405,8 +1230,8 @@ int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres,
     if (kind == 0) k_associate_g<0, 4><<<grid, 128, 0, ctx->stream>>>(A);
     else k_associate_g<1, 4><<<grid, 128, 0, ctx->stream>>>(A);
   } else {
-    if (kind == 0) k_associate<0><<<grid, 128, 0, ctx->stream>>>(A);
-    else k_associate<1><<<grid, 128, 0, ctx->stream>>>(A);
+    if (kind == 0) k_associate<0, false><<<grid, 128, 0, ctx->stream>>>(A);
+    else k_associate<1, false><<<grid, 128, 0, ctx->stream>>>(A);
   }
   MML_LAUNCHED(ctx);
   MML_CUDA(ctx, cudaGetLastError());

@@ -103,8 +103,8 @@ int mml_ctx_destroy(mml_ctx* c) {
   c->pin_small.release();
   c->pin_flags.release();
   for (auto s : c->extra_streams) cudaStreamDestroy(s);
-  c->fallback[0].release();
-  c->fallback[1].release();
+  c->pre_knn[0].release();
+  c->pre_knn[1].release();
   c->perm[0].release();
   c->perm[1].release();
   c->assoc_part[0].release();

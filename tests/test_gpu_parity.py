@@ -555,3 +555,68 @@ def test_large_query_set_is_sorted_but_slots_keep_caller_order(ctx, mm, orc, syn
     ok = r[:, 10] >= 0
     assert np.array_equal(f[ok, :3], r[ok, :3]) and np.array_equal(f[ok, 6:9], r[ok, 6:9])
     assert np.abs(f[ok, 3:6] - r[ok, 3:6]).max() <= 1e-9
+
+
+# ---- map-sized query sets (S4 / S5): box search per warp (k_knn_box) + fit kernel against the oracle ------------------
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("thres", [1.0, 25.0])
+def test_map_sized_association_240k_both_kinds(ctx, mm, orc, synth, kind, thres):
+    """240 000 queries against a 1 M-point map, line and plane kinds, through the sorted map-sized path; sparse regions,
+    queries far from the map and queries outside it exercise the undecided / fallback branches."""
+    hs, hc = synth.feature_map(1_000_000, 50_000, seed=1004, box=synth.HALL, pillars=[])
+    cloud = hc if kind == 0 else hs
+    ctx.map_set(mm.MAP_CORNER_GLOBAL, np.zeros((0, 4), np.float32)); ctx.map_set(mm.MAP_SURF_GLOBAL, np.zeros((0, 4), np.float32))
+    ctx.map_set(mm.MAP_CORNER_LOCAL, hc); ctx.map_set(mm.MAP_SURF_LOCAL, hs)
+    om = orc.Map()
+    om.set(orc.CORNER_LOCAL if kind == 0 else orc.SURF_LOCAL, cloud)
+    T = synth.s1_offset_pose()
+    q = synth.queries_from_map(cloud, 240_000, np.eye(4), seed=1004 + kind)
+    rng = np.random.default_rng(5)
+    q[:2000, :3] += rng.normal(0, 0.6, (2000, 3)).astype(np.float32)      # off the surfaces: larger search radii
+    q[2000:2100, :3] = rng.uniform(-400, 400, (100, 3)).astype(np.float32)  # far outside the map
+    q[2100:2110, 0] = np.nan
+    f, n, M, nn = ctx.associate(kind, q, T, thres)
+    if kind == 0:
+        r, rn = om.associate_line(q, T, thres)
+    else:
+        r, rn, rM, rnn = om.associate_plane(q, T, thres)
+        assert nn == rnn and np.allclose(M, rM, rtol=1e-9, atol=1e-6)
+    assert n == rn and n > 100_000
+    _cmp_features(f, r, kind)
+
+
+def test_map_sized_association_global_cubes(ctx, mm, orc, synth):
+    """Global kinds (50 m cube rule) at map size: warps whose queries straddle two cubes take the per-thread search."""
+    so, co = synth.tiled_feature_map(600_000, 30_000, tiles=(2, 2, 1), seed=1005)
+    ctx.map_set(mm.MAP_CORNER_LOCAL, np.zeros((0, 4), np.float32)); ctx.map_set(mm.MAP_SURF_LOCAL, np.zeros((0, 4), np.float32))
+    ctx.map_set(mm.MAP_CORNER_GLOBAL, co); ctx.map_set(mm.MAP_SURF_GLOBAL, so)
+    om = orc.Map()
+    om.set(orc.SURF_GLOBAL, so)
+    T = synth.s1_offset_pose()
+    q = synth.queries_from_map(so, 100_000, np.eye(4), seed=77)
+    f, n, M, nn = ctx.associate(1, q, T, 1.0)
+    r, rn, rM, rnn = om.associate_plane(q, T, 1.0)
+    assert n == rn and n > 50_000
+    _cmp_features(f, r, 1)
+    ctx.map_set(mm.MAP_CORNER_GLOBAL, np.zeros((0, 4), np.float32)); ctx.map_set(mm.MAP_SURF_GLOBAL, np.zeros((0, 4), np.float32))
+
+
+def test_s4_one_million_queries_match_oracle(ctx, mm, orc, synth):
+    """BASELINE config 4 at full size: 1 M-point map, 1 M plane queries + 50 k line queries, accepted sets and
+    features against the oracle (the oracle's kd-tree needs a few seconds for this)."""
+    hs, hc = synth.feature_map(1_000_000, 50_000, seed=1004, box=synth.HALL, pillars=[])
+    ctx.map_set(mm.MAP_CORNER_GLOBAL, np.zeros((0, 4), np.float32)); ctx.map_set(mm.MAP_SURF_GLOBAL, np.zeros((0, 4), np.float32))
+    ctx.map_set(mm.MAP_CORNER_LOCAL, hc); ctx.map_set(mm.MAP_SURF_LOCAL, hs)
+    om = orc.Map()
+    om.set(orc.SURF_LOCAL, hs); om.set(orc.CORNER_LOCAL, hc)
+    T = synth.s1_offset_pose()
+    qs = synth.queries_from_map(hs, 1_000_000, np.eye(4), seed=1004)
+    qc = synth.queries_from_map(hc, 50_000, np.eye(4), seed=1005)
+    f, n, M, nn = ctx.associate(1, qs, T, 1.0)
+    r, rn, rM, rnn = om.associate_plane(qs, T, 1.0)
+    assert n == rn and n > 900_000
+    _cmp_features(f, r, 1)
+    f, n, _, _ = ctx.associate(0, qc, T, 1.0)
+    r, rn = om.associate_line(qc, T, 1.0)
+    assert n == rn
+    _cmp_features(f, r, 0)

@@ -319,6 +319,53 @@ def test_cpp_host_shim(orc):
     assert sharp == sorted(rs.tolist()) and flat == sorted(rf.tolist())
 
 
+def test_cpp_host_shim_estimator(orc, synth, scene, tmp_path):
+    """The whole C++ Estimator adapter instantiated (host_check est): setMap, processPointToLine,
+    processPointToPlanVec, EstimateLidarPose, MapIncrementLocal (host_check <n> map) against the oracle."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "multi-modal-loam_b200", "host", "host_check")
+    if not os.path.exists(exe):
+        subprocess.check_call(["bash", os.path.join(root, "multi-modal-loam_b200", "host", "build_check.sh")])
+    out = subprocess.run([exe, "1800", "map"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert int(out.stdout.strip().splitlines()[-1].split()[-1]) > 0
+    x, ring, _ = scene["vlp"]
+    label = orc.extract_scan(x, ring, 16)
+    corner, surf = orc.voxel_downsample(x[label == 1], 0.4), orc.voxel_downsample(x[label == 2], 0.2)
+    T = scene["T_true"] @ synth.s1_offset_pose()
+    q0, _ = orc.so3_exp(synth.R_to_rotvec(T[:3, :3]))
+    ex = np.eye(4)
+    scan7 = np.zeros((len(x), 7), np.float32)
+    scan7[:, :4] = x
+    scan7[:, 6] = label
+    d = str(tmp_path)
+    np.ascontiguousarray(scene["map_surf"], np.float32).tofile(d + "/map_surf.bin")
+    np.ascontiguousarray(scene["map_corner"], np.float32).tofile(d + "/map_corner.bin")
+    np.ascontiguousarray(corner, np.float32).tofile(d + "/corner.bin")
+    np.ascontiguousarray(surf, np.float32).tofile(d + "/surf.bin")
+    scan7.tofile(d + "/scan7.bin")
+    np.concatenate([T[:3, 3], q0, T.reshape(16), ex.reshape(16)]).astype(np.float64).tofile(d + "/pose.bin")
+    out = subprocess.run([exe, "est", d], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    rows = {r.split()[0]: r.split()[1:] for r in out.stdout.strip().splitlines()}
+    om = orc.Map()
+    om.set(orc.SURF_LOCAL, scene["map_surf"]); om.set(orc.CORNER_LOCAL, scene["map_corner"])
+    rl, _ = om.associate_line(corner, T, 1.0)
+    rp, _, M, nn = om.associate_plane(surf, T, 1.0)
+    for key, ref in (("lines", rl), ("planes", rp)):
+        emitted = ref[:, 10] >= 0
+        assert int(rows[key][0]) == int(emitted.sum()) and int(rows[key][1]) == int((ref[:, 10] > 0.5).sum())
+        assert abs(float(rows[key][2]) - ref[emitted, 9].sum()) <= 1e-6 * max(1.0, abs(ref[emitted, 9].sum()))
+    assert int(rows["degenerate"][0]) == int(orc.localizability(M, nn) < 3.0)
+    Po, qo, so = om.estimate(corner, surf, ex, T[:3, 3], q0)
+    got = np.array([float(v) for v in rows["pose"]])
+    dP, dq = _pose_err(got[:3], got[3:], Po, qo)
+    assert dP <= POSE_TOL_M and dq <= POSE_TOL_RAD
+    assert int(rows["fail"][0]) == int(so[6] != 0)
+
+
 def test_large_scan_round_trip_properties(ctx, synth):
     """BASELINE-size Horizon cloud (240k points): size-independent properties instead of the oracle."""
     T = synth.make_T(synth.rot_z(0.2), np.array([-2.0, 1.0, 0.3]))

@@ -10,11 +10,11 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -Xcompiler -O3 ${MML_EXTRA_NVCC_FLAGS}"
 mkdir -p "$OBJ"
 pids=()
-for f in extract geometry splitvoxel framesort associate accumulate odometry localmap window capi; do
+for f in extract geometry splitvoxel framesort associate accumulate odometry localmap window windowsolve capi; do
   if [ ! -f "$OBJ/$f.o" ] || [ -n "$(find "$HERE" -maxdepth 1 \( -name '*.cu' -o -name '*.cuh' \) -newer "$OBJ/$f.o" 2>/dev/null)" ] || [ "$HERE/../../include/mmloam_b200.h" -nt "$OBJ/$f.o" ]; then
     # accumulate.cu is pure float64 normal-equation arithmetic checked to 1e-9 relative (no bit-exact float32
     # thresholds inside): it may contract multiply-adds into DFMA
-    if [ "$f" = "accumulate" ]; then FF="${FLAGS/-fmad=false/-fmad=true}"; else FF="$FLAGS"; fi
+    if [ "$f" = "accumulate" ] || [ "$f" = "windowsolve" ]; then FF="${FLAGS/-fmad=false/-fmad=true}"; else FF="$FLAGS"; fi
     # window.cu carries the host side of the sliding-window solve (IMU factors under forward-mode differentiation,
     # dense (15 W)-dim dogleg): let the host compiler vectorise it (every B200 host CPU has AVX2 + FMA)
     if [ "$f" = "window" ]; then FF="$FF -Xcompiler -mavx2 -Xcompiler -mfma -Xcompiler -ffp-contract=fast"; fi
@@ -23,5 +23,5 @@ for f in extract geometry splitvoxel framesort associate accumulate odometry loc
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$OBJ"/{extract,geometry,splitvoxel,framesort,associate,accumulate,odometry,localmap,window,capi}.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$OBJ"/{extract,geometry,splitvoxel,framesort,associate,accumulate,odometry,localmap,window,windowsolve,capi}.o -lcudart
 echo "built $OUT"

@@ -12,6 +12,8 @@
 #include "common.cuh"
 #include "smallmath.cuh"
 #include "eststate.cuh"
+#include "imufactor.cuh"
+#include "windowstate.cuh"
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -21,11 +23,6 @@ using namespace mml;
 
 int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres, const double* T_dev,
                          const float* thres_dev, const int* gate, const int* nq_dev, int cap);
-int mml_accumulate_window_launch(mml_ctx* ctx, int W, const float4* const* f_line, const float4* const* f_plane,
-                                 const int* n_line, const int* n_plane, const double* x6s, const double* Rbl9,
-                                 const double* Pbl3, double lidar_m, double w_tan, double huber_a, double* partials_dev,
-                                 unsigned* ticket_dev, double* out_dev, double* host_out_dev, unsigned* host_seq_dev, unsigned seq);
-int mml_accumulate_window_grid_max();
 int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_d, const int* scan_off, int n_scans,
                        int n_lines, uint8_t* label_d, bool sequential);
 int mml_split_voxel_capacity();
@@ -46,34 +43,6 @@ inline double now_us() {
   return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
 }
 
-constexpr int kMaxWindow = 4;
-
-struct WinSlot {
-  DevBuf q_corner, q_surf, f_line, f_plane;
-  DevBuf assoc_stats, assoc_part[2];  // per-frame association statistics: frames are associated concurrently
-  int n_corner = 0, n_surf = 0;
-};
-struct WindowState {
-  WinSlot slot[kMaxWindow];
-  int n_slots = 0;
-  DevBuf partials, out;   // out: [W][28] sums
-  // zero-copy hand-over of an evaluation to the host solver: mapped pinned memory written by the kernel
-  // [0, 28 W) sums | [28 W, 28 W + 20 W) association statistics (copied) | sequence words
-  void* mapped = nullptr;
-  double* mapped_dev = nullptr;
-  unsigned seq = 0;
-  cudaStream_t fstream[kMaxWindow][2] = {};
-  cudaEvent_t fev[kMaxWindow][2] = {};
-  cudaEvent_t fork = nullptr;
-  bool streams_ok = false;
-  // odometry loop: the next scan is copied (host buffers) and labelled on its own stream while the window is solved
-  cudaStream_t xstream = nullptr;
-  cudaEvent_t xev[2] = {nullptr, nullptr}, xfree[2] = {nullptr, nullptr};
-  DevBuf x_xyzi[2], x_line[2], x_s[2], x_label[2], x_counters[2];
-};
-constexpr int kMapDoubles = (28 + 20) * kMaxWindow;
-constexpr size_t kMapBytes = sizeof(double) * kMapDoubles + 64;
-
 WindowState* win(mml_ctx* c) {
   if (!c->window) c->window = new WindowState();
   return static_cast<WindowState*>(c->window);
@@ -86,6 +55,7 @@ int win_prepare(mml_ctx* c, WindowState* w) {
     MML_CUDA(c, cudaHostGetDevicePointer(&d, w->mapped, 0));
     w->mapped_dev = static_cast<double*>(d);
   }
+  if (!w->pin_up) MML_CUDA(c, cudaHostAlloc(&w->pin_up, kPinUpBytes, cudaHostAllocDefault));
   if (!w->streams_ok) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -104,112 +74,6 @@ int win_prepare(mml_ctx* c, WindowState* w) {
   return MML_OK;
 }
 
-// ---- scalar overloads used by the functor text below when it is instantiated for plain doubles
-__host__ __device__ inline double dsqrt(double f) { return sqrt(f); }
-__host__ __device__ inline double dsin(double f) { return sin(f); }
-__host__ __device__ inline double dcos(double f) { return cos(f); }
-__host__ __device__ inline double datan(double f) { return atan(f); }
-__host__ __device__ inline double val(double x) { return x; }
-
-template <class T> struct Q4 { T w, x, y, z; };
-template <class T> __host__ __device__ inline Q4<T> qmul(const Q4<T>& a, const Q4<T>& b) {  // sophus/so3.hpp:326-340
-  return {a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
-          a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z, a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x};
-}
-template <class T> __host__ __device__ inline Q4<T> qconj(const Q4<T>& q) { return {q.w, -q.x, -q.y, -q.z}; }
-template <class T> __host__ __device__ inline void qrot(const Q4<T>& q, const T* p, T* out) {  // so3.hpp:358-371
-  T uv[3] = {q.y * p[2] - q.z * p[1], q.z * p[0] - q.x * p[2], q.x * p[1] - q.y * p[0]};
-  for (int k = 0; k < 3; k++) uv[k] = uv[k] + uv[k];
-  T c[3] = {q.y * uv[2] - q.z * uv[1], q.z * uv[0] - q.x * uv[2], q.x * uv[1] - q.y * uv[0]};
-  for (int k = 0; k < 3; k++) out[k] = p[k] + q.w * uv[k] + c[k];
-}
-template <class T> __host__ __device__ inline Q4<T> qexp(const T* om) {  // so3.hpp:585-623, epsilon 1e-10
-  T theta_sq = (om[0] * om[0] + om[1] * om[1]) + om[2] * om[2];
-  T imag, real;
-  if (val(theta_sq) < 1e-20) {
-    T theta_po4 = theta_sq * theta_sq;
-    imag = T(0.5) - T(1.0 / 48.0) * theta_sq + T(1.0 / 3840.0) * theta_po4;
-    real = T(1.0) - T(1.0 / 8.0) * theta_sq + T(1.0 / 384.0) * theta_po4;
-  } else {
-    T theta = dsqrt(theta_sq);
-    T half = T(0.5) * theta;
-    imag = dsin(half) / theta;
-    real = dcos(half);
-  }
-  return {real, imag * om[0], imag * om[1], imag * om[2]};
-}
-template <class T> __host__ __device__ inline void qlog(const Q4<T>& q, T* out) {  // so3.hpp:247-292
-  T squared_n = (q.x * q.x + q.y * q.y) + q.z * q.z;
-  T w = q.w;
-  T f;
-  if (val(squared_n) < 1e-20) {
-    T squared_w = w * w;
-    f = T(2.0) / w - T(2.0 / 3.0) * squared_n / (w * squared_w);
-  } else {
-    T n = dsqrt(squared_n);
-    if (fabs(val(w)) < 1e-10) f = T(val(w) > 0 ? 3.14159265358979323846 : -3.14159265358979323846) / n;
-    else f = T(2.0) * datan(n / w) / n;
-  }
-  out[0] = f * q.x; out[1] = f * q.y; out[2] = f * q.z;
-}
-
-// Cost_NavState_PRV_Bias::operator(), CF.h:331-377, before the multiplication by sqrt_information
-template <class T>
-__host__ __device__ void imu_residual(const mml_preint& m, const double* g, const T* pri, const T* vbi, const T* prj,
-                                      const T* vbj, T* r) {
-  const Q4<T> Ri = qexp(pri + 3), Rj = qexp(prj + 3);
-  T dbg[3], dba[3];
-  for (int k = 0; k < 3; k++) { dbg[k] = vbi[3 + k] - T(m.bg[k]); dba[k] = vbi[6 + k] - T(m.ba[k]); }
-  const double dT = m.dt, dT2 = m.dt * m.dt;
-  Q4<T> dRij;
-  {  // Sophus::SO3<T>(quaternion) normalises, so3.hpp:487-494
-    const double n = sqrt(((m.dq[1] * m.dq[1] + m.dq[2] * m.dq[2]) + m.dq[3] * m.dq[3]) + m.dq[0] * m.dq[0]);
-    dRij = {T(m.dq[0] / n), T(m.dq[1] / n), T(m.dq[2] / n), T(m.dq[3] / n)};
-  }
-  const Q4<T> RiT = qconj(Ri);
-#define MML_J(r0, c0, r, c) m.jac[((r0) + (r)) * 15 + (c0) + (c)]
-  T a[3], ra[3];
-  for (int k = 0; k < 3; k++) a[k] = prj[k] - pri[k] - vbi[k] * T(dT) - T(0.5 * g[k]) * T(dT2);
-  qrot(RiT, a, ra);
-  for (int k = 0; k < 3; k++) {
-    T c = T(m.dp[k]) + ((T(MML_J(0, 9, k, 0)) * dbg[0] + T(MML_J(0, 9, k, 1)) * dbg[1]) + T(MML_J(0, 9, k, 2)) * dbg[2]) +
-          ((T(MML_J(0, 12, k, 0)) * dba[0] + T(MML_J(0, 12, k, 1)) * dba[1]) + T(MML_J(0, 12, k, 2)) * dba[2]);
-    r[k] = ra[k] - c;
-  }
-  T w[3];
-  for (int k = 0; k < 3; k++) w[k] = (T(MML_J(3, 9, k, 0)) * dbg[0] + T(MML_J(3, 9, k, 1)) * dbg[1]) + T(MML_J(3, 9, k, 2)) * dbg[2];
-  const Q4<T> dR_dbg = qexp(w);
-  const Q4<T> rR = qmul(qmul(qconj(qmul(dRij, dR_dbg)), RiT), Rj);
-  qlog(rR, r + 3);
-  for (int k = 0; k < 3; k++) a[k] = vbj[k] - vbi[k] - T(g[k]) * T(dT);
-  qrot(RiT, a, ra);
-  for (int k = 0; k < 3; k++) {
-    T c = T(m.dv[k]) + ((T(MML_J(6, 9, k, 0)) * dbg[0] + T(MML_J(6, 9, k, 1)) * dbg[1]) + T(MML_J(6, 9, k, 2)) * dbg[2]) +
-          ((T(MML_J(6, 12, k, 0)) * dba[0] + T(MML_J(6, 12, k, 1)) * dba[1]) + T(MML_J(6, 12, k, 2)) * dba[2]);
-    r[6 + k] = ra[k] - c;
-  }
-#undef MML_J
-  for (int k = 0; k < 6; k++) r[9 + k] = vbj[3 + k] - vbi[3 + k];
-}
-
-// Forward-mode dual number over the 30 parameters of the IMU factor: what Ceres' Jet<double, 30> is. The functor is
-// differentiated automatically, exactly as the reference does (same derivative values, no hand-derived Jacobian).
-struct Dual30 {
-  double a, v[30];
-  __host__ __device__ Dual30() : a(0) { for (int i = 0; i < 30; i++) v[i] = 0; }
-  __host__ __device__ Dual30(double s) : a(s) { for (int i = 0; i < 30; i++) v[i] = 0; }
-};
-__host__ __device__ inline Dual30 operator+(const Dual30& f, const Dual30& g) { Dual30 h; h.a = f.a + g.a; for (int i = 0; i < 30; i++) h.v[i] = f.v[i] + g.v[i]; return h; }
-__host__ __device__ inline Dual30 operator-(const Dual30& f, const Dual30& g) { Dual30 h; h.a = f.a - g.a; for (int i = 0; i < 30; i++) h.v[i] = f.v[i] - g.v[i]; return h; }
-__host__ __device__ inline Dual30 operator-(const Dual30& f) { Dual30 h; h.a = -f.a; for (int i = 0; i < 30; i++) h.v[i] = -f.v[i]; return h; }
-__host__ __device__ inline Dual30 operator*(const Dual30& f, const Dual30& g) { Dual30 h; h.a = f.a * g.a; for (int i = 0; i < 30; i++) h.v[i] = f.a * g.v[i] + f.v[i] * g.a; return h; }
-__host__ __device__ inline Dual30 operator/(const Dual30& f, const Dual30& g) { Dual30 h; const double gi = 1.0 / g.a, q = f.a * gi; h.a = q; for (int i = 0; i < 30; i++) h.v[i] = (f.v[i] - q * g.v[i]) * gi; return h; }
-__host__ __device__ inline Dual30 chain30(double val_, double d, const Dual30& f) { Dual30 h; h.a = val_; for (int i = 0; i < 30; i++) h.v[i] = d * f.v[i]; return h; }
-__host__ __device__ inline Dual30 dsqrt(const Dual30& f) { const double t = sqrt(f.a); return chain30(t, 1.0 / (2.0 * t), f); }
-__host__ __device__ inline Dual30 dsin(const Dual30& f) { return chain30(sin(f.a), cos(f.a), f); }
-__host__ __device__ inline Dual30 dcos(const Dual30& f) { return chain30(cos(f.a), -sin(f.a), f); }
-__host__ __device__ inline Dual30 datan(const Dual30& f) { return chain30(atan(f.a), 1.0 / (1.0 + f.a * f.a), f); }
-__host__ __device__ inline double val(const Dual30& x) { return x.a; }
 
 // weighted residual r15 = sqrt_info * r and Jacobian J (15 x 30 row-major, columns [PR_i | VBias_i | PR_j | VBias_j])
 void imu_factor_eval(const mml_preint& m, const double* g, const double* pri, const double* vbi, const double* prj,
@@ -267,146 +131,6 @@ bool invert_n(int n, const double* A, double* inv) {  // Gauss-Jordan, partial p
   for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) inv[i * n + j] = a[(size_t)i * 2 * n + n + j];
   return true;
 }
-bool chol_solve_n(int n, const double* A, const double* b, double* x, std::vector<double>& L, std::vector<double>& y) {
-  L.resize((size_t)n * n);
-  y.resize(n);
-  for (int i = 0; i < n; i++) {
-    double* Li = &L[(size_t)i * n];
-    for (int j = 0; j <= i; j++) {
-      const double* Lj = &L[(size_t)j * n];
-      double s = A[i * n + j];
-      for (int k = 0; k < j; k++) s -= Li[k] * Lj[k];
-      if (i == j) { if (!(s > 0)) return false; Li[i] = sqrt(s); }
-      else Li[j] = s / Lj[j];
-    }
-  }
-  for (int i = 0; i < n; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= L[i * n + k] * y[k]; y[i] = s / L[i * n + i]; }
-  for (int i = n - 1; i >= 0; i--) { double s = y[i]; for (int k = i + 1; k < n; k++) s -= L[k * n + i] * x[k]; x[i] = s / L[i * n + i]; }
-  return true;
-}
-
-// ceres::Solve as EST.cpp:1425-1432 configures it (TrustRegionMinimizer, traditional dogleg, Jacobi scaling,
-// Ceres 2.1.0 defaults otherwise) on dense normal equations of any size: the same state machine as the 6-dim
-// device version (accumulate.cu dogleg_update), driven by evaluations the caller supplies.
-struct DoglegN {
-  int n = 0, max_it = 10, it = 0;
-  std::vector<double> x, x_cand, x_best, H, g, scale, Hs, gs, diag, grad, gn, step, A, y, L, ytmp, vtmp;
-  double cost = 0, min_cost = 0, radius = 1e4, mu = 1e-8, alpha = 0, dogleg_norm = 0, model_change = 0, step_norm = 0, x_norm = 0;
-  bool reuse = false, first = true, done = false;
-  int num_invalid = 0, iterations = 0;
-  void begin(int n_, const double* x0, int max_iterations) {
-    n = n_; max_it = max_iterations; it = 0; iterations = 0;
-    x.assign(x0, x0 + n); x_cand = x; x_best = x;
-    H.assign((size_t)n * n, 0); g.assign(n, 0); scale.assign(n, 1); Hs = H; gs = g; diag = g; grad = g; gn = g; step = g; y = g;
-    radius = 1e4; mu = 1e-8; reuse = false; first = true; done = false; num_invalid = 0;
-  }
-  const double* eval_point() const { return first ? x.data() : x_cand.data(); }
-  double gmax(const std::vector<double>& v) const { double m = 0; for (double e : v) m = std::max(m, fabs(e)); return m; }
-  void apply_scale() {
-    for (int i = 0; i < n; i++) { gs[i] = g[i] * scale[i]; for (int j = 0; j < n; j++) Hs[(size_t)i * n + j] = H[(size_t)i * n + j] * scale[i] * scale[j]; }
-  }
-  bool compute_step() {
-    if (!reuse) {
-      reuse = true;
-      for (int i = 0; i < n; i++) diag[i] = sqrt(std::min(std::max(Hs[(size_t)i * n + i], 1e-6), 1e32));
-      for (int i = 0; i < n; i++) grad[i] = gs[i] / diag[i];
-      double gg = 0, vHv = 0;
-      std::vector<double>& v = vtmp;
-      v.resize(n);
-      for (int i = 0; i < n; i++) { v[i] = grad[i] / diag[i]; gg += grad[i] * grad[i]; }
-      for (int i = 0; i < n; i++) { double s = 0; for (int j = 0; j < n; j++) s += Hs[(size_t)i * n + j] * v[j]; vHv += v[i] * s; }
-      alpha = gg / vHv;
-      bool ok = false;
-      while (mu < 1.0) {
-        A = Hs;
-        for (int i = 0; i < n; i++) A[(size_t)i * n + i] += mu * diag[i] * diag[i];
-        bool s_ok = chol_solve_n(n, A.data(), gs.data(), y.data(), L, ytmp);
-        if (s_ok) for (int i = 0; i < n; i++) if (!std::isfinite(y[i])) s_ok = false;
-        if (!s_ok) { mu *= 10.0; continue; }
-        for (int i = 0; i < n; i++) gn[i] = -diag[i] * y[i];
-        ok = true;
-        break;
-      }
-      if (!ok) return false;
-    }
-    double gnorm = 0, gnn = 0;
-    for (int i = 0; i < n; i++) { gnorm += grad[i] * grad[i]; gnn += gn[i] * gn[i]; }
-    gnorm = sqrt(gnorm); gnn = sqrt(gnn);
-    if (gnn <= radius) { step = gn; dogleg_norm = gnn; }
-    else if (gnorm * alpha >= radius) { for (int i = 0; i < n; i++) step[i] = -(radius / gnorm) * grad[i]; dogleg_norm = radius; }
-    else {
-      double b_dot_a = 0;
-      for (int i = 0; i < n; i++) b_dot_a += grad[i] * gn[i];
-      b_dot_a *= -alpha;
-      const double a_sq = (alpha * gnorm) * (alpha * gnorm);
-      const double bma = a_sq - 2 * b_dot_a + gnn * gnn;
-      const double c = b_dot_a - a_sq;
-      const double d = sqrt(c * c + bma * (radius * radius - a_sq));
-      const double beta = (c <= 0) ? (d - c) / bma : (radius * radius - a_sq) / (d + c);
-      double sn = 0;
-      for (int i = 0; i < n; i++) { step[i] = (-alpha * (1.0 - beta)) * grad[i] + beta * gn[i]; sn += step[i] * step[i]; }
-      dogleg_norm = sqrt(sn);
-    }
-    for (int i = 0; i < n; i++) step[i] /= diag[i];
-    double sg = 0, sHs = 0;
-    for (int i = 0; i < n; i++) { double t = 0; for (int j = 0; j < n; j++) t += Hs[(size_t)i * n + j] * step[j]; sHs += step[i] * t; sg += step[i] * gs[i]; }
-    model_change = -sg - 0.5 * sHs;
-    if (!(model_change > 0.0)) return false;
-    double sn = 0;
-    for (int i = 0; i < n; i++) { const double d = step[i] * scale[i]; x_cand[i] = x[i] + d; sn += d * d; }
-    step_norm = sqrt(sn);
-    return true;
-  }
-  // next step (with Ceres' handling of invalid steps); sets done when the iteration budget or the retries run out
-  void advance() {
-    while (true) {
-      if (it >= max_it) { done = true; return; }
-      it++; iterations = it;
-      if (compute_step()) { num_invalid = 0; return; }
-      if (++num_invalid >= 5) { done = true; return; }
-      mu *= 10.0;
-      reuse = false;
-    }
-  }
-  // feed the evaluation at eval_point(): cost, H (n x n), g
-  void feed(double c, const double* Hn, const double* gn_) {
-    auto xnorm = [&]() { double s = 0; for (double e : x) s += e * e; return sqrt(s); };
-    if (first) {
-      first = false;
-      cost = c; min_cost = c;
-      H.assign(Hn, Hn + (size_t)n * n); g.assign(gn_, gn_ + n);
-      for (int i = 0; i < n; i++) scale[i] = 1.0 / (1.0 + sqrt(H[(size_t)i * n + i]));
-      apply_scale();
-      x_norm = xnorm();
-      if (!std::isfinite(c) || gmax(g) <= 1e-10) { done = true; return; }
-      advance();
-      return;
-    }
-    const double cand_cost = std::isfinite(c) ? c : DBL_MAX;
-    if (step_norm <= 1e-8 * (x_norm + 1e-8)) { done = true; return; }
-    const double cost_change = cost - cand_cost;
-    if (fabs(cost_change) <= 1e-6 * cost) { done = true; return; }
-    const double rel = cost_change / model_change;
-    if (rel > 1e-3) {
-      x = x_cand; cost = cand_cost;
-      H.assign(Hn, Hn + (size_t)n * n); g.assign(gn_, gn_ + n);
-      apply_scale();
-      x_norm = xnorm();
-      if (rel < 0.25) radius *= 0.5;
-      if (rel > 0.75) radius = std::max(radius, 3.0 * dogleg_norm);
-      mu = std::max(1e-8, 2.0 * mu / 10.0);
-      reuse = false;
-      if (cost < min_cost) { min_cost = cost; x_best = x; }
-      if (gmax(g) <= 1e-10) { done = true; return; }
-    } else {
-      radius *= 0.5;
-      reuse = true;
-    }
-    if (radius < 1e-32) { done = true; return; }
-    advance();
-  }
-};
-
 }  // namespace
 
 void mml_window_destroy(mml_ctx* c) {
@@ -414,10 +138,12 @@ void mml_window_destroy(mml_ctx* c) {
   WindowState* w = static_cast<WindowState*>(c->window);
   for (auto& s : w->slot) {
     s.q_corner.release(); s.q_surf.release(); s.f_line.release(); s.f_plane.release();
-    s.assoc_stats.release(); s.assoc_part[0].release(); s.assoc_part[1].release();
+    s.assoc_stats.release(); s.assoc_part[0].release(); s.assoc_part[1].release(); s.cnt.release();
   }
-  w->partials.release(); w->out.release();
+  w->dev.release(); w->push_dev.release();
+  if (w->graph) cudaGraphExecDestroy(w->graph);
   if (w->mapped) cudaFreeHost(w->mapped);
+  if (w->pin_up) cudaFreeHost(w->pin_up);
   if (w->streams_ok) {
     for (int f = 0; f < kMaxWindow; f++) for (int k = 0; k < 2; k++) { cudaStreamDestroy(w->fstream[f][k]); cudaEventDestroy(w->fev[f][k]); }
     cudaEventDestroy(w->fork);
@@ -547,6 +273,8 @@ int mml_imu_predict(const double* prev16, const mml_preint* pre, double* next16)
 }
 
 // ---- window slots: the downsampled corner / surf clouds of the frames in the window stay in HBM -----------------
+// Frames live in PHYSICAL slots (the association nodes of the solve graph are bound to them); order[f] maps frame f
+// (0 = oldest) to its slot.
 int mml_window_reset(mml_ctx* c) {
   if (!c) return MML_ERR_INVALID;
   win(c)->n_slots = 0;
@@ -557,12 +285,20 @@ int mml_window_size(mml_ctx* c) { return c ? win(c)->n_slots : 0; }
 static int window_make_room(mml_ctx* c, int max_frames) {
   WindowState* w = win(c);
   if (max_frames < 1 || max_frames > kMaxWindow) return mml_fail(c, MML_ERR_INVALID, "window size must be 1..4");
-  while (w->n_slots >= max_frames) {  // drop the oldest frame (PE.cpp:830-832), buffers rotate to the back
-    WinSlot first = w->slot[0];
-    for (int f = 0; f + 1 < w->n_slots; f++) w->slot[f] = w->slot[f + 1];
-    w->slot[w->n_slots - 1] = first;
+  while (w->n_slots >= max_frames) {  // drop the oldest frame (PE.cpp:830-832), its slot rotates to the back
+    const int first = w->order[0];
+    for (int f = 0; f + 1 < w->n_slots; f++) w->order[f] = w->order[f + 1];
+    w->order[w->n_slots - 1] = first;
     w->n_slots--;
   }
+  return MML_OK;
+}
+
+static int slot_reserve_queries(mml_ctx* c, WinSlot& s, int need) {
+  if (s.cap < need) s.cap = (need + 4095) / 4096 * 4096;  // coarse steps: the solve graph is keyed on the capacities
+  MML_CUDA(c, s.q_corner.reserve(sizeof(float4) * (size_t)(s.cap + 1)));
+  MML_CUDA(c, s.q_surf.reserve(sizeof(float4) * (size_t)(s.cap + 1)));
+  MML_CUDA(c, s.cnt.reserve(64));
   return MML_OK;
 }
 
@@ -572,11 +308,12 @@ int mml_window_push_frame(mml_ctx* c, const float* corner_xyzi, int n_corner, co
   cudaSetDevice(c->device);
   MML_CHECK(window_make_room(c, max_frames));
   WindowState* w = win(c);
-  WinSlot& s = w->slot[w->n_slots];
-  MML_CUDA(c, s.q_corner.reserve(sizeof(float4) * (size_t)(n_corner + 1)));
-  MML_CUDA(c, s.q_surf.reserve(sizeof(float4) * (size_t)(n_surf + 1)));
+  WinSlot& s = w->slot[w->order[w->n_slots]];
+  MML_CHECK(slot_reserve_queries(c, s, (n_corner > n_surf ? n_corner : n_surf) + 1));
   if (n_corner) MML_CUDA(c, cudaMemcpyAsync(s.q_corner.p, corner_xyzi, sizeof(float4) * (size_t)n_corner, cudaMemcpyHostToDevice, c->stream));
   if (n_surf) MML_CUDA(c, cudaMemcpyAsync(s.q_surf.p, surf_xyzi, sizeof(float4) * (size_t)n_surf, cudaMemcpyHostToDevice, c->stream));
+  const int cnt[8] = {n_corner, n_surf, 0, 0, 0, 0, 0, 0};
+  MML_CUDA(c, cudaMemcpyAsync(s.cnt.p, cnt, sizeof(cnt), cudaMemcpyHostToDevice, c->stream));
   MML_CUDA(c, cudaStreamSynchronize(c->stream));
   s.n_corner = n_corner; s.n_surf = n_surf;
   w->n_slots++;
@@ -586,33 +323,21 @@ int mml_window_push_frame(mml_ctx* c, const float* corner_xyzi, int n_corner, co
 // push a raw scan resident in HBM: extraction (A1) -> undistortion + label split + voxel filter (A4, A6) on the
 // device, the downsampled clouds become the newest window frame. out_counts (may be NULL): n_sharp, n_flat,
 // n_corner_ds, n_surf_ds.
-static int window_push_scan(mml_ctx* c, const void* xyzi_dev, const void* line_id_dev, const void* s_dev, int n, int n_lines,
-                            const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, int max_frames,
-                            int* out_counts, const uint8_t* pre_label, const int* pre_counters);
-
-int mml_window_push_scan_dev(mml_ctx* c, const void* xyzi_dev, const void* line_id_dev, const void* s_dev, int n, int n_lines,
-                             const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, int max_frames,
-                             int* out_counts) {
-  return window_push_scan(c, xyzi_dev, line_id_dev, s_dev, n, n_lines, dR9, dt3, leaf_corner, leaf_surf, max_frames, out_counts,
-                          nullptr, nullptr);
-}
-
 // pre_label / pre_counters: labels and extractor counters already produced for this scan (the loop labels scan k+1
-// on its own stream while the window of scan k is solved; the caller has made c->stream wait for them)
+// on its own stream while the window of scan k is solved; the caller has made c->stream wait for them).
+// flags_async: pinned int[16] that receives the extractor counters [0, 3) and the split / voxel counts [4, 9) with
+// an asynchronous copy instead of a synchronisation (the loop reads them after the scan's solve has been awaited).
 static int window_push_scan(mml_ctx* c, const void* xyzi_dev, const void* line_id_dev, const void* s_dev, int n, int n_lines,
                             const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, int max_frames,
-                            int* out_counts, const uint8_t* pre_label, const int* pre_counters) {
+                            int* out_counts, const uint8_t* pre_label, const int* pre_counters, int* flags_async) {
   if (!c || n < 0) return MML_ERR_INVALID;
   cudaSetDevice(c->device);
   MML_CHECK(window_make_room(c, max_frames));
   WindowState* w = win(c);
-  WinSlot& s = w->slot[w->n_slots];
+  WinSlot& s = w->slot[w->order[w->n_slots]];
   cudaStream_t st = c->stream;
-  const int cap = mml_split_voxel_capacity();
   MML_CUDA(c, c->in_label.reserve((size_t)n + 16));
-  MML_CUDA(c, c->frame_cnt.reserve(64));
-  MML_CUDA(c, s.q_corner.reserve(sizeof(float4) * (size_t)cap));
-  MML_CUDA(c, s.q_surf.reserve(sizeof(float4) * (size_t)cap));
+  MML_CHECK(slot_reserve_queries(c, s, mml_split_voxel_capacity()));
   MML_CUDA(c, c->pin_flags.reserve(64));
   const int off[2] = {0, n};
   const uint8_t* label_d = pre_label;
@@ -622,26 +347,39 @@ static int window_push_scan(mml_ctx* c, const void* xyzi_dev, const void* line_i
     label_d = c->in_label.as<uint8_t>();
     counters_d = c->counters.as<int>();
   }
-  int* cnt = c->frame_cnt.as<int>();
+  int* cnt = s.cnt.as<int>();  // [n_corner, n_surf, ., ., overflow]: the association and the solve read the counts here
   const bool undist = dR9 && dt3 && s_dev;
   MML_CHECK(mml_split_voxel_device(c, (const float4*)xyzi_dev, undist ? (const float*)s_dev : nullptr, label_d, n,
                                    dR9, dt3, leaf_corner, leaf_surf, s.q_corner.as<float4>(), s.q_surf.as<float4>(), cnt));
-  int* hf = c->pin_flags.as<int>();
+  int* hf = flags_async ? flags_async : c->pin_flags.as<int>();
   MML_CUDA(c, cudaMemcpyAsync(hf, counters_d, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
   MML_CUDA(c, cudaMemcpyAsync(hf + 4, cnt, 5 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  MML_CUDA(c, cudaStreamSynchronize(st));
-  if (hf[2] || hf[8]) return mml_fail(c, MML_ERR_CAPACITY, "scan exceeds the fused extraction / split-voxel capacities (window path)");
-  s.n_corner = hf[4]; s.n_surf = hf[5];
-  if (out_counts) { out_counts[0] = hf[0]; out_counts[1] = hf[1]; out_counts[2] = hf[4]; out_counts[3] = hf[5]; }
+  s.n_corner = s.n_surf = -1;
+  if (!flags_async) {
+    MML_CUDA(c, cudaStreamSynchronize(st));
+    if (hf[2] || hf[8]) return mml_fail(c, MML_ERR_CAPACITY, "scan exceeds the fused extraction / split-voxel capacities (window path)");
+    s.n_corner = hf[4]; s.n_surf = hf[5];
+    if (out_counts) { out_counts[0] = hf[0]; out_counts[1] = hf[1]; out_counts[2] = hf[4]; out_counts[3] = hf[5]; }
+  }
   w->n_slots++;
   return MML_OK;
+}
+
+int mml_window_push_scan_dev(mml_ctx* c, const void* xyzi_dev, const void* line_id_dev, const void* s_dev, int n, int n_lines,
+                             const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, int max_frames,
+                             int* out_counts) {
+  return window_push_scan(c, xyzi_dev, line_id_dev, s_dev, n, n_lines, dR9, dt3, leaf_corner, leaf_surf, max_frames, out_counts,
+                          nullptr, nullptr, nullptr);
 }
 
 int mml_window_get_frame(mml_ctx* c, int f, int kind, float* out_xyzi, int cap, int* n_out) {
   if (!c || f < 0 || f >= win(c)->n_slots || kind < 0 || kind > 1) return MML_ERR_INVALID;
   cudaSetDevice(c->device);
-  WinSlot& s = win(c)->slot[f];
-  const int n = kind == 0 ? s.n_corner : s.n_surf;
+  WinSlot& s = win(c)->frame(f);
+  int cnt[2] = {0, 0};
+  MML_CUDA(c, cudaMemcpyAsync(cnt, s.cnt.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+  MML_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int n = cnt[kind];
   if (n_out) *n_out = n;
   if (out_xyzi && n) {
     if (cap < n) return MML_ERR_CAPACITY;
@@ -651,9 +389,46 @@ int mml_window_get_frame(mml_ctx* c, int f, int kind, float* out_xyzi, int cap, 
   return MML_OK;
 }
 
+// solve parameters and extrinsics of a window solve into the head of a WinDev image
+static void fill_win_params(WinDev* h, const double* exTlb16, const double* gravity3, const mml_est_params* prm) {
+  // exRbl = R^T, exPbl = -R^T t (EST.cpp:1155-1156); the functors re-normalise the rotation through a quaternion (CF.h:405-408)
+  for (int r = 0; r < 3; r++) for (int k = 0; k < 3; k++) h->Rbl_raw[3 * r + k] = exTlb16[4 * k + r];
+  for (int r = 0; r < 3; r++)
+    h->Pbl[r] = -1.0 * (h->Rbl_raw[3 * r] * exTlb16[3] + h->Rbl_raw[3 * r + 1] * exTlb16[7] + h->Rbl_raw[3 * r + 2] * exTlb16[11]);
+  quat_to_R(quat_from_R9(h->Rbl_raw), h->Rbl_q);
+  for (int k = 0; k < 3; k++) h->gravity[k] = gravity3[k];
+  h->max_outer = prm->max_outer; h->max_inner = prm->max_inner;
+  h->lidar_m = prm->lidar_m; h->w_tan = prm->plan_weight_tan;
+  h->huber_a = prm->use_huber ? 0.1 / prm->lidar_m : 0.0;
+  h->thres_sched[0] = prm->thres0; h->thres_sched[1] = prm->thres1; h->thres_sched[2] = prm->thres2;  // EST.cpp:1207, 1377-1381
+}
+
+// wait for the solve that publishes `seq` in the mapped result block (the kernel's tail stores the result with a
+// system-scope fence before the sequence word: no stream synchronisation on the way)
+static int wait_window_result(mml_ctx* c, WindowState* w, unsigned seq) {
+  volatile unsigned* host_seq = reinterpret_cast<volatile unsigned*>(static_cast<double*>(w->mapped) + kMapDoubles);
+  long spins = 0;
+  while (*host_seq != seq) {
+    if ((++spins & 0x3FFF) == 0) {
+      cudaError_t e = cudaStreamQuery(c->stream);
+      if (e != cudaSuccess && e != cudaErrorNotReady) { c->err = std::string("window solve: ") + cudaGetErrorString(e); return MML_ERR_CUDA; }
+      if (e == cudaSuccess && *host_seq != seq) return mml_fail(c, MML_ERR_CUDA, "window solve finished without publishing its result");
+    }
+  }
+  __sync_synchronize();
+  return MML_OK;
+}
+
+static int window_cap(WindowState* w) {
+  int cap = 1;
+  for (int p = 0; p < kMaxWindow; p++) cap = cap > w->slot[p].cap ? cap : w->slot[p].cap;
+  return cap;
+}
+
 // Estimator::Estimate on the frames currently in the window (W = mml_window_size). states: W x 16 doubles
 // (P, q_wxyz, V, bg, ba), in place. preints[f] (f >= 1) links frame f-1 to f. stats (optional, 16 doubles):
 // [outer, inner_total, n_line(last frame), n_plane(last frame), final_cost, min_sv(last frame), degenerate, evals].
+// The whole solve runs on the device (windowsolve.cu): one graph launch, one wait.
 int mml_estimate_window(mml_ctx* c, double* states, const mml_preint* const* preints, const double* exTlb16,
                         const double* gravity3, const mml_est_params* prm, double* stats) {
   if (!c || !states || !exTlb16 || !gravity3) return MML_ERR_INVALID;
@@ -669,206 +444,27 @@ int mml_estimate_window(mml_ctx* c, double* states, const mml_preint* const* pre
   mml_est_params_default(&def);
   if (!prm) prm = &def;
   cudaStream_t st = c->stream;
-
-  // exRbl = R^T, exPbl = -R^T t (EST.cpp:1155-1156); the functors re-normalise the rotation through a quaternion (CF.h:405-408)
-  double Rbl_raw[9], Pbl[3];
-  for (int r = 0; r < 3; r++) for (int k = 0; k < 3; k++) Rbl_raw[3 * r + k] = exTlb16[4 * k + r];
-  for (int r = 0; r < 3; r++) Pbl[r] = -1.0 * (Rbl_raw[3 * r] * exTlb16[3] + Rbl_raw[3 * r + 1] * exTlb16[7] + Rbl_raw[3 * r + 2] * exTlb16[11]);
-  double Rbl_q[9];
-  quat_to_R(quat_from_R9(Rbl_raw), Rbl_q);
-
-  const int gmax = mml_accumulate_window_grid_max();
   MML_CHECK(win_prepare(c, w));
-  MML_CUDA(c, w->partials.reserve(sizeof(double) * 28 * (size_t)gmax * kMaxWindow + 256));
-  MML_CUDA(c, w->out.reserve(sizeof(double) * 28 * kMaxWindow + 64));
-  double* out_dev = w->out.as<double>();
-  unsigned* ticket_dev = reinterpret_cast<unsigned*>(w->partials.as<double>() + 28 * (size_t)gmax * kMaxWindow);
-  double* host = static_cast<double*>(w->mapped);                 // [0, 28 W) sums, [28 kMaxWindow, ...) statistics
-  volatile unsigned* host_seq = reinterpret_cast<volatile unsigned*>(host + kMapDoubles);
-  unsigned* host_seq_dev = reinterpret_cast<unsigned*>(w->mapped_dev + kMapDoubles);
-
-  const int n = (W == 1) ? 6 : 15 * W;  // a lone frame's velocity / bias block has no residual (Ceres drops it)
-  double thres = prm->thres0;
-  const double huber_a = prm->use_huber ? 0.1 / prm->lidar_m : 0.0;
-  int outer_done = 0, inner_total = 0, evals = 0, n_line_last = 0, n_plane_last = 0, is_degenerate = 0;
-  double final_cost = 0, min_sv = -1;
-  std::vector<double> x(15 * W), H((size_t)n * n), g(n), Himu((size_t)n * n), gimu(n);
-  DoglegN D;
-  const float4* fl[kMaxWindow];
-  const float4* fp[kMaxWindow];
-  int nl[kMaxWindow], np[kMaxWindow];
-
-  for (int it = 0; it < prm->max_outer; ++it) {
-    // vector2double, EST.cpp:937-950
-    for (int f = 0; f < W; f++) {
-      const double* s = states + 16 * f;
-      for (int k = 0; k < 3; k++) x[6 * f + k] = s[k];
-      so3_log(Quat{s[3], s[4], s[5], s[6]}, &x[6 * f + 3]);
-      for (int k = 0; k < 9; k++) x[6 * W + 9 * f + k] = s[7 + k];
-    }
-    double* sb = states + 16 * (W - 1);
-    const Quat q_before = {sb[3], sb[4], sb[5], sb[6]};
-    const double t_before[3] = {sb[0], sb[1], sb[2]};
-    // association of every frame (EST.cpp:1265-1299). The reference joins its two association threads frame by
-    // frame; the frames do not depend on each other, so here all 2 W kernels run side by side on their own streams.
-    const double tp0 = g_prof_on ? now_us() : 0;
-    MML_CUDA(c, cudaEventRecord(w->fork, st));
-    for (int f = 0; f < W; f++) {
-      WinSlot& s = w->slot[f];
-      const double* sf = states + 16 * f;
-      double Rq[9], T[16] = {0};
-      quat_to_R(Quat{sf[3], sf[4], sf[5], sf[6]}, Rq);
-      for (int r = 0; r < 3; r++) {
-        for (int k = 0; k < 3; k++) T[4 * r + k] = Rq[3 * r] * Rbl_raw[k] + Rq[3 * r + 1] * Rbl_raw[3 + k] + Rq[3 * r + 2] * Rbl_raw[6 + k];
-        T[4 * r + 3] = Rq[3 * r] * Pbl[0] + Rq[3 * r + 1] * Pbl[1] + Rq[3 * r + 2] * Pbl[2] + sf[r];
-      }
-      T[15] = 1;
-      // the association works on the context's frame slot and statistics: lend it this frame's buffers
-      auto lend = [&]() {
-        std::swap(c->q_corner, s.q_corner); std::swap(c->q_surf, s.q_surf);
-        std::swap(c->f_line, s.f_line); std::swap(c->f_plane, s.f_plane);
-        std::swap(c->assoc_stats, s.assoc_stats);
-        std::swap(c->assoc_part[0], s.assoc_part[0]); std::swap(c->assoc_part[1], s.assoc_part[1]);
-      };
-      lend();
-      c->has_perm[0] = c->has_perm[1] = false;
-      int rc = MML_OK;
-      for (int kind = 1; kind >= 0 && rc == MML_OK; kind--) {
-        cudaStream_t fs = w->fstream[f][kind];
-        if (cudaStreamWaitEvent(fs, w->fork, 0) != cudaSuccess) { rc = MML_ERR_CUDA; break; }
-        c->stream = fs;
-        rc = mml_associate_launch(c, kind, T, (float)thres, nullptr, nullptr, nullptr, nullptr, kind ? s.n_surf : s.n_corner);
-        c->stream = st;
-        if (rc == MML_OK && cudaEventRecord(w->fev[f][kind], fs) != cudaSuccess) rc = MML_ERR_CUDA;
-      }
-      lend();
-      MML_CHECK(rc);
-      fl[f] = s.f_line.as<float4>(); fp[f] = s.f_plane.as<float4>();
-      nl[f] = s.n_corner; np[f] = s.n_surf;
-    }
-    for (int f = 0; f < W; f++) for (int kind = 0; kind < 2; kind++) MML_CUDA(c, cudaStreamWaitEvent(st, w->fev[f][kind], 0));
-    for (int f = 0; f < W; f++)  // both kinds of a frame write into the same 160-byte block (line: [0, 8), plane: [8, 16), counts)
-      MML_CUDA(c, cudaMemcpyAsync(host + 28 * kMaxWindow + 20 * f, w->slot[f].assoc_stats.p, sizeof(double) * 20, cudaMemcpyDeviceToHost, st));
-    thres = (it == 0) ? prm->thres1 : prm->thres2;  // EST.cpp:1377-1381
-    if (g_prof_on) g_prof.assoc += now_us() - tp0;
-
-    D.begin(n, x.data(), prm->max_inner);
-    bool stats_read = false;
-    while (!D.done) {
-      const double* xe = D.eval_point();
-      const unsigned seq = ++w->seq;
-      const double te0 = g_prof_on ? now_us() : 0;
-      MML_CHECK(mml_accumulate_window_launch(c, W, fl, fp, nl, np, xe, Rbl_q, Pbl, prm->lidar_m, prm->plan_weight_tan, huber_a,
-                                             w->partials.as<double>(), ticket_dev, out_dev, w->mapped_dev, host_seq_dev, seq));
-      // while the device evaluates the lidar terms, the host evaluates the IMU factors at the same point
-      const double te1 = g_prof_on ? now_us() : 0;
-      double cost_imu = 0;
-      std::fill(Himu.begin(), Himu.end(), 0.0);
-      std::fill(gimu.begin(), gimu.end(), 0.0);
-      for (int f = 1; f < W; f++) {
-        double r[15], J[450];
-        imu_factor_eval(*preints[f], gravity3, xe + 6 * (f - 1), xe + 6 * W + 9 * (f - 1), xe + 6 * f, xe + 6 * W + 9 * f, r, J);
-        for (int k = 0; k < 15; k++) cost_imu += 0.5 * r[k] * r[k];
-        int gidx[30];
-        {
-          const int off[4] = {6 * (f - 1), 6 * W + 9 * (f - 1), 6 * f, 6 * W + 9 * f};
-          const int sz[4] = {6, 9, 6, 9};
-          int q = 0;
-          for (int b = 0; b < 4; b++) for (int i = 0; i < sz[b]; i++) gidx[q++] = off[b] + i;
-        }
-        double JtJ[900];
-        for (int i = 0; i < 30; i++) {
-          double sg = 0;
-          for (int k = 0; k < 15; k++) sg += J[k * 30 + i] * r[k];
-          gimu[gidx[i]] += sg;
-          for (int j = i; j < 30; j++) {
-            double sh = 0;
-            for (int k = 0; k < 15; k++) sh += J[k * 30 + i] * J[k * 30 + j];
-            JtJ[i * 30 + j] = sh;
-          }
-        }
-        for (int i = 0; i < 30; i++) for (int j = i; j < 30; j++) {
-          Himu[(size_t)gidx[i] * n + gidx[j]] += JtJ[i * 30 + j];
-          if (j != i) Himu[(size_t)gidx[j] * n + gidx[i]] += JtJ[i * 30 + j];
-        }
-      }
-      // wait for the device: the kernel's last CTAs publish `seq` after their sums (system-scope fence)
-      const double te2 = g_prof_on ? now_us() : 0;
-      {
-        long spins = 0;
-        bool ready = false;
-        while (!ready) {
-          ready = true;
-          for (int f = 0; f < W; f++) if (host_seq[f] != seq) { ready = false; break; }
-          if (!ready && (++spins & 0xFFFF) == 0) {
-            cudaError_t e = cudaStreamQuery(st);
-            if (e != cudaSuccess && e != cudaErrorNotReady) { c->err = std::string("window evaluation: ") + cudaGetErrorString(e); return MML_ERR_CUDA; }
-            if (e == cudaSuccess) {  // stream drained: the flags must be there now
-              bool all = true;
-              for (int f = 0; f < W; f++) all = all && host_seq[f] == seq;
-              if (!all) return mml_fail(c, MML_ERR_CUDA, "window evaluation finished without publishing its result");
-            }
-          }
-        }
-        __sync_synchronize();
-      }
-      const double te3 = g_prof_on ? now_us() : 0;
-      evals++;
-      if (!stats_read) {
-        stats_read = true;
-        for (int f = 0; f < W; f++) {
-          const double* a = host + 28 * kMaxWindow + 20 * f;
-          const int* ints = reinterpret_cast<const int*>(a + 16);
-          const double* m = a + 8;
-          const double M[9] = {m[0], m[1], m[2], m[1], m[3], m[4], m[2], m[4], m[5]};
-          double sv = -1.0;
-          if (ints[1] > 10) sv = sqrt(fmax(eig3_sym_min(M), 0.0));  // checkLocalizability, EST.cpp:536-565
-          if (sv < 3.0) is_degenerate = 1;                         // EST.cpp:771-775
-          if (f == W - 1) { n_line_last = ints[0]; n_plane_last = ints[1]; min_sv = sv; }
-        }
-      }
-      // assemble: lidar blocks from the device sums + the IMU part
-      double cost = cost_imu;
-      H = Himu;
-      g = gimu;
-      for (int f = 0; f < W; f++) {
-        const double* o = host + 28 * f;
-        cost += o[0];
-        for (int i = 0; i < 6; i++) g[6 * f + i] += o[1 + i];
-        int k = 7;
-        for (int i = 0; i < 6; i++) for (int j = i; j < 6; j++, k++) {
-          H[(size_t)(6 * f + i) * n + 6 * f + j] += o[k];
-          if (j != i) H[(size_t)(6 * f + j) * n + 6 * f + i] += o[k];
-        }
-      }
-      D.feed(cost, H.data(), g.data());
-      if (g_prof_on) {
-        const double te4 = now_us();
-        g_prof.launch += te1 - te0; g_prof.imu += te2 - te1; g_prof.wait += te3 - te2; g_prof.solve += te4 - te3; g_prof.evals++;
-      }
-    }
-    inner_total += D.iterations;
-    final_cost = D.min_cost;
-    // double2vector, EST.cpp:952-964
-    for (int f = 0; f < W; f++) {
-      double* s = states + 16 * f;
-      for (int k = 0; k < 3; k++) s[k] = D.x_best[6 * f + k];
-      const Quat q = so3_exp(&D.x_best[6 * f + 3]);
-      s[3] = q.w; s[4] = q.x; s[5] = q.y; s[6] = q.z;
-      if (W > 1) for (int k = 0; k < 9; k++) s[7 + k] = D.x_best[6 * W + 9 * f + k];
-    }
-    outer_done = it + 1;
-    const Quat Q = {sb[3], sb[4], sb[5], sb[6]};
-    const Quat dq = quat_mul(q_before, Quat{Q.w, -Q.x, -Q.y, -Q.z});
-    const double deltaR = 2.0 * atan2(sqrt((dq.x * dq.x + dq.y * dq.y) + dq.z * dq.z), fabs(dq.w)) * 180.0 / 3.14159265358979323846;
-    const double d0 = t_before[0] - sb[0], d1 = t_before[1] - sb[1], d2 = t_before[2] - sb[2];
-    const double deltaT = sqrt((d0 * d0 + d1 * d1) + d2 * d2);
-    if ((deltaR < 0.05 && deltaT < 0.05) || (it + 1) == prm->max_outer) break;
-  }
-  if (stats) {
-    stats[0] = outer_done; stats[1] = inner_total; stats[2] = n_line_last; stats[3] = n_plane_last;
-    stats[4] = final_cost; stats[5] = min_sv; stats[6] = is_degenerate; stats[7] = evals;
-  }
+  MML_CHECK(mml_window_solve_graph(c, w, window_cap(w)));
+  WinDev* h = static_cast<WinDev*>(w->pin_up);
+  memset(h, 0, offsetof(WinDev, upload_end));
+  h->W = W;
+  for (int f = 0; f < kMaxWindow; f++) h->slot_of[f] = w->order[f];
+  memcpy(h->states, states, sizeof(double) * 16 * (size_t)W);
+  for (int f = 1; f < W; f++) h->pre[f] = *preints[f];
+  fill_win_params(h, exTlb16, gravity3, prm);
+  const unsigned seq = ++w->seq;
+  h->seq = seq;
+  MML_CUDA(c, cudaMemcpyAsync(w->dev.p, h, offsetof(WinDev, upload_end), cudaMemcpyHostToDevice, st));
+  MML_CHECK(mml_window_begin_launch(c, w));
+  MML_CUDA(c, cudaGraphLaunch(w->graph, st));
+  MML_CHECK(wait_window_result(c, w, seq));
+  const double* out = static_cast<const double*>(w->mapped);
+  memcpy(states, out, sizeof(double) * 16 * (size_t)W);
+  const double* so = out + 16 * kMaxWindow;
+  c->launches += w->graph_launches * (long long)so[0];
+  if (stats) for (int k = 0; k < 8; k++) stats[k] = so[k];
+  MML_CUDA(c, cudaStreamSynchronize(st));  // per-call API: leave the stream idle (tail of the graph: gated no-op nodes)
   return MML_OK;
 }
 
@@ -880,6 +476,10 @@ int mml_estimate_window(mml_ctx* c, double* states, const mml_preint* const* pre
 //   push the frame, drop the oldest beyond the window                                   PE.cpp:830-832
 //   EstimateLidarPose on the window                                                     PE.cpp:872
 //   the odometry output is the OLDEST frame of the window (EST.cpp:1043-1049, PE.cpp:879-880)
+// The window (states, pre-integrations, clouds) lives on the device between scans; per scan the host pre-integrates
+// the IMU samples at the biases the previous solve returned (~20 samples of 15 x 15 algebra), enqueues
+// [undistortion + voxel filter of the new frame -> window shift -> solve graph] and waits once, on the mapped
+// result of the solve. Extraction of scan k+1 runs on its own stream meanwhile.
 // xyzi / line / s: per-scan pointers (device when host_buffers == 0). imu_t / imu_gyr / imu_acc: all samples
 // concatenated, scan k owns imu_n[k] of them. state0: state of the frame before the first scan (t = stamp0).
 // poses_front / poses_newest (n_scans x 16 row-major T_wb, either may be NULL), states_out (n_scans x 16, newest
@@ -893,19 +493,33 @@ int mml_odom_run_window(mml_ctx* c, const void* const* xyzi, const void* const* 
                         double* states_out, double* stats_out, float* total_ms) {
   if (!c || n_scans < 0 || window < 1 || window > kMaxWindow || !state0 || !exTlb16 || !gravity3 || !stamps) return MML_ERR_INVALID;
   cudaSetDevice(c->device);
+  bool any_map = false;
+  for (int k = 0; k < 4; k++) any_map = any_map || c->maps[k].valid;
+  if (!any_map) return mml_fail(c, MML_ERR_STATE, "odom_run_window: no feature map set");
+  mml_est_params def;
+  mml_est_params_default(&def);
+  if (!prm) prm = &def;
   MML_CHECK(mml_window_reset(c));
+  WindowState* w = win(c);
+  MML_CHECK(win_prepare(c, w));
+  cudaStream_t st = c->stream;
+  for (int p = 0; p < kMaxWindow; p++) MML_CHECK(slot_reserve_queries(c, w->slot[p], mml_split_voxel_capacity()));
+  MML_CHECK(mml_window_solve_graph(c, w, window_cap(w)));
+  MML_CUDA(c, c->pin_flags.reserve(sizeof(int) * 64));
+  // an empty window with this run's parameters
+  WinDev* h = static_cast<WinDev*>(w->pin_up);
+  memset(h, 0, offsetof(WinDev, upload_end));
+  fill_win_params(h, exTlb16, gravity3, prm);
+  MML_CUDA(c, cudaMemcpyAsync(w->dev.p, h, offsetof(WinDev, upload_end), cudaMemcpyHostToDevice, st));
+  WinPush* ring = reinterpret_cast<WinPush*>(static_cast<char*>(w->pin_up) + sizeof(WinDev));
   double Rbl[9], Pbl[3];
-  for (int r = 0; r < 3; r++) for (int k = 0; k < 3; k++) Rbl[3 * r + k] = exTlb16[4 * k + r];
-  for (int r = 0; r < 3; r++) Pbl[r] = -1.0 * (Rbl[3 * r] * exTlb16[3] + Rbl[3 * r + 1] * exTlb16[7] + Rbl[3 * r + 2] * exTlb16[11]);
-  std::vector<double> states;           // frames in the window, 16 doubles each
-  std::vector<mml_preint> pre_store;    // same indexing
+  memcpy(Rbl, h->Rbl_raw, sizeof(Rbl));
+  memcpy(Pbl, h->Pbl, sizeof(Pbl));
   double prev[16];
   memcpy(prev, state0, sizeof(prev));
   double t_prev = stamp0;
   size_t imu_off = 0;
-  WindowState* w = win(c);
-  MML_CHECK(win_prepare(c, w));
-  if (total_ms) { MML_CUDA(c, cudaEventRecord(c->ev0, c->stream)); }
+  if (total_ms) { MML_CUDA(c, cudaEventRecord(c->ev0, st)); }
   // labels do not depend on the pose (the extraction node of the reference runs ahead of the estimator, FE.cpp ->
   // /union_feature_cloud -> PE.cpp): scan k+1 is copied and labelled on its own stream while scan k is solved
   const void* xdv[2] = {nullptr, nullptr};
@@ -940,18 +554,19 @@ int mml_odom_run_window(mml_ctx* c, const void* const* xyzi, const void* const* 
     return MML_OK;
   };
   if (n_scans > 0) MML_CHECK(prefetch(0));
-  auto pose16 = [](const double* st, double* T) {
+  auto pose16 = [](const double* st16, double* T) {
     double R[9];
-    quat_to_R(Quat{st[3], st[4], st[5], st[6]}, R);
-    const double Tn[16] = {R[0], R[1], R[2], st[0], R[3], R[4], R[5], st[1], R[6], R[7], R[8], st[2], 0, 0, 0, 1};
+    quat_to_R(Quat{st16[3], st16[4], st16[5], st16[6]}, R);
+    const double Tn[16] = {R[0], R[1], R[2], st16[0], R[3], R[4], R[5], st16[1], R[6], R[7], R[8], st16[2], 0, 0, 0, 1};
     memcpy(T, Tn, sizeof(Tn));
   };
   for (int k = 0; k < n_scans; k++) {
-    mml_preint pre;
-    MML_CHECK(mml_imu_preintegrate(imu_t + imu_off, imu_gyr + 3 * imu_off, imu_acc + 3 * imu_off, imu_n[k], t_prev, prev + 10, prev + 13, &pre));
+    const double tq0 = g_prof_on ? now_us() : 0;
+    WinPush* hp = ring + (k & 7);
+    MML_CHECK(mml_imu_preintegrate(imu_t + imu_off, imu_gyr + 3 * imu_off, imu_acc + 3 * imu_off, imu_n[k], t_prev, prev + 10, prev + 13, &hp->pre));
     imu_off += imu_n[k];
     double next[16];
-    MML_CHECK(mml_imu_predict(prev, &pre, next));
+    MML_CHECK(mml_imu_predict(prev, &hp->pre, next));
     // LiDAR motion over the sweep, PE.cpp:822-829: delta = T_wl(prev)^-1 T_wl(predicted)
     double Tp[16], Tn[16], Twl_p[16], Twl_n[16], Tbl_h[16] = {0}, inv[16], dT[16];
     pose16(prev, Tp); pose16(next, Tn);
@@ -964,40 +579,48 @@ int mml_odom_run_window(mml_ctx* c, const void* const* xyzi, const void* const* 
     const double dt3[3] = {dT[3], dT[7], dT[11]};
     const int b = k & 1;
     const void *xd = xdv[b], *ld = ldv[b], *sd = sdv[b];
-    MML_CUDA(c, cudaStreamWaitEvent(c->stream, w->xev[b], 0));
-    const double tq0 = g_prof_on ? now_us() : 0;
-    if ((int)(states.size() / 16) >= window) {  // PE.cpp:830-832
-      states.erase(states.begin(), states.begin() + 16);
-      pre_store.erase(pre_store.begin());
-    }
+    const double tq1 = g_prof_on ? now_us() : 0;
+    MML_CUDA(c, cudaStreamWaitEvent(st, w->xev[b], 0));
+    int* flags = c->pin_flags.as<int>() + 16 * b;
     MML_CHECK(window_push_scan(c, xd, ld, sd, n_pts[k], n_lines, dR9, dt3, leaf_corner, leaf_surf, window, nullptr,
-                               w->x_label[b].as<uint8_t>(), w->x_counters[b].as<int>()));
-    MML_CUDA(c, cudaEventRecord(w->xfree[b], c->stream));  // raw scan, labels and counters of this buffer pair are consumed
+                               w->x_label[b].as<uint8_t>(), w->x_counters[b].as<int>(), flags));
+    MML_CUDA(c, cudaEventRecord(w->xfree[b], st));  // raw scan, labels and counters of this buffer pair are consumed
+    const int W = w->n_slots;
+    memcpy(hp->state, next, sizeof(next));
+    hp->slot = w->order[W - 1];
+    hp->window = window;
+    const unsigned seq = ++w->seq;
+    hp->seq = seq;
+    MML_CUDA(c, cudaMemcpyAsync(w->push_dev.p, hp, sizeof(WinPush), cudaMemcpyHostToDevice, st));
+    MML_CHECK(mml_window_push_launch(c, w, w->push_dev.as<WinPush>()));
+    MML_CUDA(c, cudaGraphLaunch(w->graph, st));
     if (k + 1 < n_scans) MML_CHECK(prefetch(k + 1));
-    if (g_prof_on) { g_prof.push += now_us() - tq0; g_prof.scans++; }
-    states.insert(states.end(), next, next + 16);
-    pre_store.push_back(pre);
-    const int W = (int)(states.size() / 16);
-    const mml_preint* pp[kMaxWindow] = {nullptr, nullptr, nullptr, nullptr};
-    for (int f = 1; f < W; f++) pp[f] = &pre_store[f];
-    double st8[16];
-    MML_CHECK(mml_estimate_window(c, states.data(), pp, exTlb16, gravity3, prm, st8));
-    memcpy(prev, &states[16 * (W - 1)], sizeof(prev));
+    const double tq2 = g_prof_on ? now_us() : 0;
+    MML_CHECK(wait_window_result(c, w, seq));
+    const double tq3 = g_prof_on ? now_us() : 0;
+    if (flags[2] || flags[8]) return mml_fail(c, MML_ERR_CAPACITY, "scan exceeds the fused extraction / split-voxel capacities (window path)");
+    const double* out = static_cast<const double*>(w->mapped);
+    const double* so = out + 16 * kMaxWindow;
+    c->launches += w->graph_launches * (long long)so[0] + 1;
+    memcpy(prev, out + 16 * (W - 1), sizeof(prev));
     t_prev = stamps[k];
-    if (poses_front) pose16(&states[0], poses_front + 16 * (size_t)k);
+    if (poses_front) pose16(out, poses_front + 16 * (size_t)k);
     if (poses_newest) pose16(prev, poses_newest + 16 * (size_t)k);
     if (states_out) memcpy(states_out + 16 * (size_t)k, prev, sizeof(prev));
-    if (stats_out) memcpy(stats_out + 8 * (size_t)k, st8, sizeof(double) * 8);
+    if (stats_out) memcpy(stats_out + 8 * (size_t)k, so, sizeof(double) * 8);
+    if (g_prof_on) { g_prof.imu += tq1 - tq0; g_prof.launch += tq2 - tq1; g_prof.wait += tq3 - tq2; g_prof.evals += (long)so[7]; g_prof.scans++; }
   }
   if (total_ms) {
-    MML_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    MML_CUDA(c, cudaEventRecord(c->ev1, st));
     MML_CUDA(c, cudaEventSynchronize(c->ev1));
     MML_CUDA(c, cudaEventElapsedTime(total_ms, c->ev0, c->ev1));
+  } else {
+    MML_CUDA(c, cudaStreamSynchronize(st));
   }
   if (g_prof_on && g_prof.scans) {
-    const double ns = (double)g_prof.scans, ne = (double)(g_prof.evals ? g_prof.evals : 1);
-    fprintf(stderr, "[mml window prof] per scan: push %.1f us, association enqueue %.1f us, evaluations %.1f; per evaluation: launch %.1f, imu %.1f, wait %.1f, assemble+dogleg %.1f us\n",
-            g_prof.push / ns, g_prof.assoc / ns, g_prof.evals / ns, g_prof.launch / ne, g_prof.imu / ne, g_prof.wait / ne, g_prof.solve / ne);
+    const double ns = (double)g_prof.scans;
+    fprintf(stderr, "[mml window prof] per scan: host pre-integration + prediction %.1f us, enqueue %.1f us, wait for the solve %.1f us, evaluations %.1f\n",
+            g_prof.imu / ns, g_prof.launch / ns, g_prof.wait / ns, g_prof.evals / ns);
     g_prof = WinProf();
   }
   return MML_OK;

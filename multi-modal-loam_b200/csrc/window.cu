@@ -165,7 +165,7 @@ int mml_imu_preintegrate(const double* t, const double* gyr, const double* acc, 
   const double acc_n = 0.08, gyr_n = 0.004, acc_w = 2.0e-4, gyr_w = 2.0e-5, gnorm = 9.805;  // IMU.h:79-84
   Quat dq = {1, 0, 0, 0};
   double dp[3] = {0, 0, 0}, dv[3] = {0, 0, 0}, dtime = 0;
-  std::vector<double> cov(225, 0.0), jac(225, 0.0), noise(144, 0.0), tmp(225), tmp2(225), AT(225), BN(180), BT(180), BNB(225);
+  std::vector<double> cov(225, 0.0), jac(225, 0.0), noise(144, 0.0), tmp(225), tmp2(225), AT(225), BNB(225);
   for (int i = 0; i < 15; i++) jac[i * 15 + i] = 1.0;
   for (int i = 0; i < 3; i++) {
     noise[i * 12 + i] = gyr_n * gyr_n; noise[(3 + i) * 12 + 3 + i] = acc_n * acc_n;
@@ -193,26 +193,58 @@ int mml_imu_preintegrate(const double* t, const double* gyr, const double* acc, 
     quat_to_R(dq, Rq);
     hat3(a3, Ha);
     mat_mul(3, 3, 3, Rq, Ha, RH);
-    double A[225], B[180];
-    memset(A, 0, sizeof(A)); memset(B, 0, sizeof(B));
-    for (int i = 0; i < 15; i++) A[i * 15 + i] = 1.0;
-    auto setA = [&](int r0, int c0, const double* M, double f) { for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) A[(r0 + r) * 15 + c0 + c] = f * M[3 * r + c]; };
-    auto setB = [&](int r0, int c0, const double* M, double f) { for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) B[(r0 + r) * 12 + c0 + c] = f * M[3 * r + c]; };
-    const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    // A = d(state_{k+1}) / d(state_k) and B = d(state_{k+1}) / d(noise) (IMU.cpp:131-156) are identity plus a few
+    // 3 x 3 blocks: the products A jac, A cov A^T and B N B^T are formed block-wise, every sum in the order of the
+    // dense products (ascending inner index; the skipped terms are exact zeros)
     const double dRT[9] = {dR[0], dR[3], dR[6], dR[1], dR[4], dR[7], dR[2], dR[5], dR[8]};
-    setA(0, 3, RH, -0.5 * dt2); setA(0, 6, I3, dt); setA(0, 12, Rq, -0.5 * dt2);
-    setA(3, 3, dRT, 1.0); setA(3, 9, Jr, -dt);
-    setA(6, 3, RH, -dt); setA(6, 12, Rq, -dt);
-    setB(0, 3, Rq, 0.5 * dt2); setB(3, 0, Jr, dt); setB(6, 3, Rq, dt); setB(9, 6, I3, dt); setB(12, 9, I3, dt);
-    mat_mul(15, 15, 15, A, jac.data(), tmp.data());
+    double A03[9], A012[9], A39[9], A63[9], A612[9];
+    for (int i = 0; i < 9; i++) {
+      A03[i] = -0.5 * dt2 * RH[i]; A012[i] = -0.5 * dt2 * Rq[i]; A39[i] = -dt * Jr[i];
+      A63[i] = -dt * RH[i]; A612[i] = -dt * Rq[i];
+    }
+    // out = A M (rows of M in, rows of out out); M and out are 15 x 15 row-major and distinct
+    auto applyA = [&](const double* M, double* out) {
+      for (int j = 0; j < 15; j++) {
+        for (int r = 0; r < 3; r++) {
+          double v = M[r * 15 + j];
+          for (int c = 0; c < 3; c++) v += A03[3 * r + c] * M[(3 + c) * 15 + j];
+          v += dt * M[(6 + r) * 15 + j];
+          for (int c = 0; c < 3; c++) v += A012[3 * r + c] * M[(12 + c) * 15 + j];
+          out[r * 15 + j] = v;
+          double w = 0;
+          for (int c = 0; c < 3; c++) w += dRT[3 * r + c] * M[(3 + c) * 15 + j];
+          for (int c = 0; c < 3; c++) w += A39[3 * r + c] * M[(9 + c) * 15 + j];
+          out[(3 + r) * 15 + j] = w;
+          double u = 0;
+          for (int c = 0; c < 3; c++) u += A63[3 * r + c] * M[(3 + c) * 15 + j];
+          u += M[(6 + r) * 15 + j];
+          for (int c = 0; c < 3; c++) u += A612[3 * r + c] * M[(12 + c) * 15 + j];
+          out[(6 + r) * 15 + j] = u;
+        }
+        for (int r = 9; r < 15; r++) out[r * 15 + j] = M[r * 15 + j];
+      }
+    };
+    applyA(jac.data(), tmp.data());
     jac = tmp;
-    for (int i = 0; i < 15; i++) for (int j = 0; j < 15; j++) AT[i * 15 + j] = A[j * 15 + i];
-    mat_mul(15, 15, 15, A, cov.data(), tmp.data());
-    mat_mul(15, 15, 15, tmp.data(), AT.data(), tmp2.data());
-    mat_mul(15, 12, 12, B, noise.data(), BN.data());
-    for (int i = 0; i < 12; i++) for (int j = 0; j < 15; j++) BT[i * 15 + j] = B[j * 12 + i];
-    mat_mul(15, 12, 15, BN.data(), BT.data(), BNB.data());
-    for (int i = 0; i < 225; i++) cov[i] = tmp2[i] + BNB[i];
+    // cov <- A cov A^T + B N B^T: T = A cov, then (T A^T)[i][j] = sum_t T[i][t] A[j][t] = (A T^T)[j][i]
+    applyA(cov.data(), tmp.data());
+    for (int i = 0; i < 15; i++) for (int j = 0; j < 15; j++) AT[i * 15 + j] = tmp[j * 15 + i];
+    applyA(AT.data(), tmp2.data());  // tmp2 = A T^T = (T A^T)^T
+    // B N B^T: B has blocks (0,3) = Rq dt2/2, (3,0) = Jr dt, (6,3) = Rq dt, (9,6) = (12,9) = I dt; N is diagonal
+    const double ng = noise[0], na = noise[3 * 12 + 3], nwg = noise[6 * 12 + 6], nwa = noise[9 * 12 + 9];
+    std::fill(BNB.begin(), BNB.end(), 0.0);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+      double pp = 0, pv = 0, vp = 0, vv = 0, rr = 0;
+      for (int k = 0; k < 3; k++) {
+        const double bpi = 0.5 * dt2 * Rq[3 * i + k], bpj = 0.5 * dt2 * Rq[3 * j + k], bvi = dt * Rq[3 * i + k], bvj = dt * Rq[3 * j + k];
+        pp += (bpi * na) * bpj; pv += (bpi * na) * bvj; vp += (bvi * na) * bpj; vv += (bvi * na) * bvj;
+        rr += ((dt * Jr[3 * i + k]) * ng) * (dt * Jr[3 * j + k]);
+      }
+      BNB[i * 15 + j] = pp; BNB[i * 15 + 6 + j] = pv; BNB[(6 + i) * 15 + j] = vp; BNB[(6 + i) * 15 + 6 + j] = vv;
+      BNB[(3 + i) * 15 + 3 + j] = rr;
+    }
+    for (int i = 0; i < 3; i++) { BNB[(9 + i) * 15 + 9 + i] = (dt * nwg) * dt; BNB[(12 + i) * 15 + 12 + i] = (dt * nwa) * dt; }
+    for (int i = 0; i < 15; i++) for (int j = 0; j < 15; j++) cov[i * 15 + j] = tmp2[j * 15 + i] + BNB[i * 15 + j];
     const double Ra[3] = {Rq[0] * a3[0] + Rq[1] * a3[1] + Rq[2] * a3[2], Rq[3] * a3[0] + Rq[4] * a3[1] + Rq[5] * a3[2],
                           Rq[6] * a3[0] + Rq[7] * a3[1] + Rq[8] * a3[2]};
     for (int k = 0; k < 3; k++) dp[k] += dv[k] * dt + 0.5 * Ra[k] * dt2;
@@ -457,7 +489,7 @@ int mml_estimate_window(mml_ctx* c, double* states, const mml_preint* const* pre
   h->seq = seq;
   MML_CUDA(c, cudaMemcpyAsync(w->dev.p, h, offsetof(WinDev, upload_end), cudaMemcpyHostToDevice, st));
   MML_CHECK(mml_window_begin_launch(c, w));
-  MML_CUDA(c, cudaGraphLaunch(w->graph, st));
+  MML_CHECK(mml_window_solve_launch(c, w, window_cap(w), prm->max_outer));
   MML_CHECK(wait_window_result(c, w, seq));
   const double* out = static_cast<const double*>(w->mapped);
   memcpy(states, out, sizeof(double) * 16 * (size_t)W);
@@ -593,7 +625,7 @@ int mml_odom_run_window(mml_ctx* c, const void* const* xyzi, const void* const* 
     hp->seq = seq;
     MML_CUDA(c, cudaMemcpyAsync(w->push_dev.p, hp, sizeof(WinPush), cudaMemcpyHostToDevice, st));
     MML_CHECK(mml_window_push_launch(c, w, w->push_dev.as<WinPush>()));
-    MML_CUDA(c, cudaGraphLaunch(w->graph, st));
+    MML_CHECK(mml_window_solve_launch(c, w, window_cap(w), prm->max_outer));
     if (k + 1 < n_scans) MML_CHECK(prefetch(k + 1));
     const double tq2 = g_prof_on ? now_us() : 0;
     MML_CHECK(wait_window_result(c, w, seq));

@@ -51,12 +51,17 @@ struct WinSolveArgs {
   int use_cond;
 };
 
+// The solver works in FRAME-MAJOR order ([P, log Q, V, bg, ba] of frame 0, then frame 1, ...): position p of the
+// system <-> unknown unpos[p] of the parameter vector x ([P, log Q] x W, then [V, bg, ba] x W, EST.cpp:937-950).
+// In that order the normal equations are block tridiagonal with blocks of 15 (an IMU factor couples consecutive
+// frames, a lidar factor one frame).
 struct WinShared {
   double Hn[kWinN * kWLD];                // normal equations of the newest evaluation
   double Hs[kWinN * kWLD];                // Jacobi-scaled normal equations of the current linearisation
   double A[(kWinN + 1) * kWLD];           // Hs + mu diag^2 (rows 0..n-1) and the right-hand side (row n); factor in place
-  double x[kWinN], x_cand[kWinN], x_best[kWinN], gs[kWinN], gnew[kWinN], scale[kWinN], diag[kWinN], grad[kWinN], gn[kWinN],
-      step[kWinN], tv[kWinN], tt[kWinN], ysol[kWinN];
+  double x[kWinN], x_cand[kWinN], x_best[kWinN];                 // parameter order
+  double gs[kWinN], gnew[kWinN], scale[kWinN], diag[kWinN], grad[kWinN], gn[kWinN], step[kWinN], tv[kWinN], tt[kWinN],
+      ysol[kWinN];                                               // frame-major order
   double raw[kMaxWindow - 1][31][15];     // unweighted IMU residual (column 30) and Jacobian columns
   double Jw[kMaxWindow - 1][31][15];      // weighted by sqrt_info
   double gather[2][kWCluster][28];
@@ -66,24 +71,15 @@ struct WinShared {
   mml_preint pre[kMaxWindow - 1];
   double gravity[3], Rbl_q[9], Pbl[3];
   double q_before[4], t_before[3];
-  double cost, min_cost, cost_new, cost_imu, radius, mu, alpha, dogleg_norm, model_change, step_norm, x_norm;
-  int gidx[kMaxWindow - 1][30];
-  int lidx[kMaxWindow - 1][kWinN];
+  double cost_new, cost_imu, min_cost_out;
+  int gidx[kMaxWindow - 1][30];           // factor column -> unknown (parameter order)
+  int lidx[kMaxWindow - 1][kWinN];        // position -> factor column, or -1
   int nnz;
-  unsigned short nz[kWinN * (kWinN + 1) / 2];  // upper-triangle entries some factor touches: (row << 8) | column
+  unsigned short nz[kWinN * (kWinN + 1) / 2];  // upper-triangle positions some factor touches: (row << 8) | column
   unsigned char tri[27 * 28 / 2][2];        // (row, column) of the idx-th entry of a lower triangle, row-major
-  int pos[kWinN], unpos[kWinN];           // unknown g <-> frame-major position (the order the factorisation works in)
-  int reuse, first, done, it, num_invalid, total_inner, evals, action, done_after, chol_ok;
-#ifdef MML_WIN_DEVPROF
-  long long prof[16], prof_t0;
-#endif
+  int pos[kWinN], unpos[kWinN];
+  int total_inner_out, evals_out;
 };
-
-#ifdef MML_WIN_DEVPROF
-#define FTICK(k) if (tid == 0) { const long long t_ = clock64(); s.prof[k] += t_ - s.prof_t0; s.prof_t0 = t_; }
-#else
-#define FTICK(k)
-#endif
 
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
@@ -95,53 +91,70 @@ __device__ __forceinline__ double wmax(double v) {
   for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, d));
   return v;
 }
-// sum over i < n of a[i] * b[i], formed redundantly by every warp (same order in each: the result is uniform over the CTA)
-__device__ __forceinline__ double wdot(const double* a, const double* b, int n, int lane) {
-  double v = 0;
-  for (int i = lane; i < n; i += 32) v += a[i] * b[i];
+// Reductions over the n <= 64 components of a vector are formed by EVERY warp (components lane and lane + 32, then
+// a butterfly): the same operations in the same order everywhere, so the result is uniform over the CTA - and over
+// the cluster - without a broadcast or a barrier.
+__device__ __forceinline__ double wdot2(const double* a, const double* b, int n, int lane) {
+  double v = lane < n ? a[lane] * b[lane] : 0.0;
+  if (lane + 32 < n) v += a[lane + 32] * b[lane + 32];
   return wsum(v);
 }
 // out = M v (n x n, leading dimension kWLD): warps stride over the rows
-__device__ __forceinline__ void cta_matvec(const double* M, const double* v, double* out, int n, int warp, int lane) {
+__device__ __noinline__ void cta_matvec(const double* M, const double* v, double* out, int n, int warp, int lane) {
+  const double v0 = lane < n ? v[lane] : 0.0, v1 = lane + 32 < n ? v[lane + 32] : 0.0;
+#pragma unroll 1
   for (int i = warp; i < n; i += kWWarps) {
-    double t = 0;
-    for (int j = lane; j < n; j += 32) t += M[i * kWLD + j] * v[j];
+    double t = lane < n ? M[i * kWLD + lane] * v0 : 0.0;
+    if (lane + 32 < n) t += M[i * kWLD + lane + 32] * v1;
     t = wsum(t);
     if (lane == 0) out[i] = t;
   }
 }
 
-// Cholesky factorisation and solve of A y = b by the whole CTA. A holds the matrix in frame-major order
-// ([P, log Q, V, bg, ba] of frame 0, then frame 1, ...) in rows 0..n-1 and the right-hand side as row n.
-// In that order the normal equations are block tridiagonal with blocks of B = 15 (an IMU factor couples consecutive
-// frames, a lidar factor one frame), so the factor has no entries outside the band: a column in frame block b only
-// reaches the rows of blocks b and b + 1 and the right-hand side row.
+// Cholesky factorisation and solve of A y = b by the CTA. A holds the matrix (frame-major order) in rows 0..n-1 and
+// the right-hand side as row n. The factor has no entries outside the band of the block-tridiagonal system: a column
+// in frame block b only reaches the rows of blocks b and b + 1 and the right-hand side row.
 // Right-looking, three columns per step: every thread factors the 3 x 3 diagonal block in registers (same inputs,
-// same result, so the positive-definiteness test is uniform and nothing is broadcast), one thread per row solves
+// same result, so the positive-definiteness test is uniform and nothing is broadcast; the pivots come out of an
+// LDL^T recurrence so that the three reciprocal square roots do not wait for each other), one thread per row solves
 // the panel below it, one barrier, the trailing entries of the band take their rank-3 update spread over all
-// threads, one barrier. What bounds a step is the dependent chain (three reciprocal square roots) and the two
-// barriers, not the flops. The back substitution runs the same way from the last block up.
-// On success ysol (caller's order) = A^-1 b and the function returns true (uniform over the CTA).
-// Replaces chol_solve_n of the reference restatement (oracle/window.cpp), which factors the same matrix densely.
-__device__ bool cta_chol_solve(WinShared& s, int n, int B, int tid) {
+// threads, one barrier. What bounds a step is the dependent chain and the two barriers, not the flops. The back
+// substitution runs on warp 0 alone, three unknowns per step, the solution in registers (components lane and
+// lane + 32) and exchanged by shuffles: no barrier on the way.
+// On success ysol = A^-1 b and the function returns true (uniform over the CTA).
+// Replaces chol_solve_n of the reference restatement, which factors the same matrix densely.
+#if defined(MML_WIN_DEVPROF) && MML_WIN_DEVPROF >= 2
+__device__ long long g_cholprof[8];
+#define CTICK(k) if (tid == 0 && blockIdx.x == 0) { const long long t_ = clock64(); g_cholprof[k] += t_ - ct0; ct0 = t_; }
+#else
+#define CTICK(k)
+#endif
+__device__ __noinline__ bool cta_chol_solve(WinShared& s, int n, int B, int tid) {
   double* A = s.A;
+#if defined(MML_WIN_DEVPROF) && MML_WIN_DEVPROF >= 2
+  long long ct0 = clock64();
+#endif
+#pragma unroll 1
   for (int c0 = 0; c0 < n; c0 += 3) {
     const int bj = c0 / B;
     const int rend = min(n, B * (bj + 2));
     const int m = rend - (c0 + 3);  // panel rows below the diagonal block (band only); the right-hand side row is extra
     const double* D0 = A + c0 * kWLD + c0;
     __syncthreads();  // the previous step's update is complete
+    CTICK(0)
     const double d00 = D0[0], d10 = D0[kWLD], d11 = D0[kWLD + 1], d20 = D0[2 * kWLD], d21 = D0[2 * kWLD + 1], d22 = D0[2 * kWLD + 2];
     if (!(d00 > 0.0)) return false;
-    const double i00 = rsqrt(d00);
-    const double l10 = d10 * i00, l20 = d20 * i00;
-    const double t11 = d11 - l10 * l10;
-    if (!(t11 > 0.0)) return false;
-    const double i11 = rsqrt(t11);
-    const double l21 = (d21 - l20 * l10) * i11;
-    const double t22 = d22 - l20 * l20 - l21 * l21;
-    if (!(t22 > 0.0)) return false;
-    const double i22 = rsqrt(t22);
+    const double r0 = __drcp_rn(d00);
+    const double m10 = d10 * r0, m20 = d20 * r0;
+    const double p1 = d11 - m10 * d10;
+    if (!(p1 > 0.0)) return false;
+    const double e21 = d21 - m20 * d10;
+    const double m21 = e21 * __drcp_rn(p1);
+    const double p2 = d22 - m20 * d20 - m21 * e21;
+    if (!(p2 > 0.0)) return false;
+    const double i00 = rsqrt(d00), i11 = rsqrt(p1), i22 = rsqrt(p2);
+    const double l10 = d10 * i00, l20 = d20 * i00, l21 = e21 * i11;
+    CTICK(1)
     if (tid <= m) {
       const int r = tid < m ? c0 + 3 + tid : n;
       double* Ar = A + r * kWLD + c0;
@@ -150,15 +163,18 @@ __device__ bool cta_chol_solve(WinShared& s, int n, int B, int tid) {
       const double x2 = (Ar[2] - x0 * l20 - x1 * l21) * i22;
       Ar[0] = x0; Ar[1] = x1; Ar[2] = x2;
     }
+    CTICK(2)
     __syncthreads();  // panel complete; every thread has read the diagonal block, which may now be overwritten
+    CTICK(3)
     if (tid == kWThreads - 1) {
       double* Dw = A + c0 * kWLD + c0;
       Dw[0] = d00 * i00;
-      Dw[kWLD] = l10; Dw[kWLD + 1] = t11 * i11;
-      Dw[2 * kWLD] = l20; Dw[2 * kWLD + 1] = l21; Dw[2 * kWLD + 2] = t22 * i22;
+      Dw[kWLD] = l10; Dw[kWLD + 1] = p1 * i11;
+      Dw[2 * kWLD] = l20; Dw[2 * kWLD + 1] = l21; Dw[2 * kWLD + 2] = p2 * i22;
       s.tv[c0] = i00; s.tv[c0 + 1] = i11; s.tv[c0 + 2] = i22;  // 1 / L[j][j] for the back substitution
     }
     const int ntri = m * (m + 1) / 2;
+#pragma unroll 1
     for (int idx = tid; idx < ntri + m; idx += kWThreads) {
       int r, c;
       if (idx < ntri) { r = c0 + 3 + s.tri[idx][0]; c = c0 + 3 + s.tri[idx][1]; }
@@ -167,99 +183,74 @@ __device__ bool cta_chol_solve(WinShared& s, int n, int B, int tid) {
       const double* Xc = A + c * kWLD + c0;
       A[r * kWLD + c] -= (Xr[0] * Xc[0] + Xr[1] * Xc[1]) + Xr[2] * Xc[2];
     }
+    CTICK(4)
   }
   __syncthreads();
+  CTICK(5)
   // row n now holds L^-1 b; back substitution L^T y = (row n), three unknowns per step, last block first
-  double* y = A + n * kWLD;
-  for (int c0 = n - 3; c0 >= 0; c0 -= 3) {
-    const double* D0 = A + c0 * kWLD + c0;
-    const double x2 = y[c0 + 2] * s.tv[c0 + 2];
-    const double x1 = (y[c0 + 1] - D0[2 * kWLD + 1] * x2) * s.tv[c0 + 1];
-    const double x0 = (y[c0] - D0[kWLD] * x1 - D0[2 * kWLD] * x2) * s.tv[c0];
-    const int bj = c0 / B, lo = bj > 0 ? B * (bj - 1) : 0;  // rows c0..c0+2 of the factor start at the previous block
-    __syncthreads();
-    const int i = lo + tid;
-    if (i < c0) y[i] -= (D0[i - c0] * x0 + D0[kWLD + i - c0] * x1) + D0[2 * kWLD + i - c0] * x2;
-    else if (tid == kWThreads - 1) { y[c0] = x0; y[c0 + 1] = x1; y[c0 + 2] = x2; }
-    __syncthreads();
-  }
   bool ok = true;
-  for (int i = tid; i < n; i += kWThreads) {
-    const double v = y[i];
-    s.ysol[s.unpos[i]] = v;
-    if (!isfinite(v)) ok = false;
+  if (tid < 32) {
+    const int lane = tid;
+    const double* yrow = A + n * kWLD;
+    double y0 = lane < n ? yrow[lane] : 0.0, y1 = lane + 32 < n ? yrow[lane + 32] : 0.0;
+#pragma unroll 1
+    for (int c0 = n - 3; c0 >= 0; c0 -= 3) {
+      const double* D0 = A + c0 * kWLD + c0;
+      const int bj = c0 / B, lo = bj > 0 ? B * (bj - 1) : 0;  // rows c0..c0+2 of the factor start at the previous block
+      // this lane's entries of those rows and the block's own entries: loads that do not wait for the chain below
+      const bool u0 = lane >= lo && lane < c0, u1 = lane + 32 >= lo && lane + 32 < c0;
+      const double a00 = u0 ? D0[lane - c0] : 0.0, a01 = u0 ? D0[kWLD + lane - c0] : 0.0, a02 = u0 ? D0[2 * kWLD + lane - c0] : 0.0;
+      const double a10 = u1 ? D0[lane + 32 - c0] : 0.0, a11 = u1 ? D0[kWLD + lane + 32 - c0] : 0.0, a12 = u1 ? D0[2 * kWLD + lane + 32 - c0] : 0.0;
+      const double L10 = D0[kWLD], L20 = D0[2 * kWLD], L21 = D0[2 * kWLD + 1];
+      const double t0 = s.tv[c0], t1 = s.tv[c0 + 1], t2 = s.tv[c0 + 2];
+      const double v2 = __shfl_sync(0xffffffffu, ((c0 + 2) >> 5) ? y1 : y0, (c0 + 2) & 31);
+      const double v1 = __shfl_sync(0xffffffffu, ((c0 + 1) >> 5) ? y1 : y0, (c0 + 1) & 31);
+      const double v0 = __shfl_sync(0xffffffffu, (c0 >> 5) ? y1 : y0, c0 & 31);
+      const double x2 = v2 * t2;
+      const double x1 = (v1 - L21 * x2) * t1;
+      const double x0 = (v0 - L10 * x1 - L20 * x2) * t0;
+      y0 -= (a00 * x0 + a01 * x1) + a02 * x2;
+      y1 -= (a10 * x0 + a11 * x1) + a12 * x2;
+      if (lane == (c0 & 31)) { if (c0 >> 5) y1 = x0; else y0 = x0; }
+      if (lane == ((c0 + 1) & 31)) { if ((c0 + 1) >> 5) y1 = x1; else y0 = x1; }
+      if (lane == ((c0 + 2) & 31)) { if ((c0 + 2) >> 5) y1 = x2; else y0 = x2; }
+    }
+    if (lane < n) { s.ysol[lane] = y0; if (!isfinite(y0)) ok = false; }
+    if (lane + 32 < n) { s.ysol[lane + 32] = y1; if (!isfinite(y1)) ok = false; }
   }
-  return __syncthreads_and(ok) != 0;
+  CTICK(6)
+  const bool res_ = __syncthreads_and(ok) != 0;
+  CTICK(7)
+  return res_;
 }
 
-// DoglegStrategy::ComputeStep + the model evaluation (DoglegN::compute_step of the host solver). All threads of the
-// CTA call it; scalars that steer the control flow are formed redundantly per warp, so they are uniform.
-__device__ bool win_compute_step(WinShared& s, int n, int tid) {
+// The dogleg step outside the Gauss-Newton branch (the Gauss-Newton step leaves the trust region): the Cauchy step
+// length, the interpolated step and the model change through products with Hs. DoglegStrategy::ComputeStep of
+// Ceres 2.1.0 as restated by DoglegN::compute_step. Rare: the radius starts at 1e4.
+// In: grad, gn, gs, diag, Hs. Out: step (scaled space, divided by diag), *model_change; returns the dogleg norm.
+__device__ __noinline__ double win_dogleg_branch(WinShared& s, int n, int tid, double gg, double gnorm, double gnn, double radius,
+                                                 double* alpha_io, double* model_change) {
   const int lane = tid & 31, warp = tid >> 5;
-  FTICK(2)
-  if (!s.reuse) {
-    for (int i = tid; i < n; i += kWThreads) {
-      const double dg = sqrt(fmin(fmax(s.Hs[i * kWLD + i], 1e-6), 1e32));
-      s.diag[i] = dg;
-      s.grad[i] = s.gs[i] / dg;
-    }
-    __syncthreads();
-    if (tid == 0) { s.reuse = 1; s.alpha = -1.0; }  // the Cauchy step length is formed on demand (below)
-    for (;;) {
-      const double mu = s.mu;
-      if (!(mu < 1.0)) { __syncthreads(); return false; }
-      for (int i = warp; i < n; i += kWWarps) {
-        const int pi = s.pos[i] * kWLD;
-        for (int j = lane; j < n; j += 32) {
-          double v = s.Hs[i * kWLD + j];
-          if (i == j) v += mu * s.diag[i] * s.diag[i];
-          s.A[pi + s.pos[j]] = v;
-        }
-      }
-      for (int j = tid; j < n; j += kWThreads) s.A[n * kWLD + s.pos[j]] = s.gs[j];
-      __syncthreads();
-      FTICK(3)
-      const bool solved = cta_chol_solve(s, n, n < 15 ? n : 15, tid);
-      FTICK(4)
-      if (solved) break;
-      __syncthreads();
-      if (tid == 0) s.mu = mu * 10.0;
-      __syncthreads();
-    }
-    for (int i = tid; i < n; i += kWThreads) s.gn[i] = -s.diag[i] * s.ysol[i];
-    __syncthreads();
-  }
-  FTICK(6)
-  const double gg = wdot(s.grad, s.grad, n, lane);
-  const double gnorm = sqrt(gg);
-  const double gnn = sqrt(wdot(s.gn, s.gn, n, lane));
-  const double radius = s.radius;
-  double alpha = s.alpha;
-  if (!(gnn <= radius) && alpha < 0.0) {
+  double alpha = *alpha_io;
+  if (alpha < 0.0) {
     // alpha = |g|^2 / (g^T D^-1 H D^-1 g) of the current linearisation (unchanged while steps are rejected)
-    for (int i = tid; i < n; i += kWThreads) s.tv[i] = s.grad[i] / s.diag[i];
+    if (tid < n) s.tv[tid] = s.grad[tid] / s.diag[tid];
     __syncthreads();
     cta_matvec(s.Hs, s.tv, s.tt, n, warp, lane);
     __syncthreads();
-    alpha = gg / wdot(s.tv, s.tt, n, lane);
-    __syncthreads();
-    if (tid == 0) s.alpha = alpha;
+    alpha = gg / wdot2(s.tv, s.tt, n, lane);
+    *alpha_io = alpha;
   }
   double dogleg_norm;
-  // the step, component i on lanes i and i + 32 of every warp (warp 0 stores it)
   double st0 = 0, st1 = 0;
   const int i0 = lane, i1 = lane + 32;
-  if (gnn <= radius) {
-    if (i0 < n) st0 = s.gn[i0];
-    if (i1 < n) st1 = s.gn[i1];
-    dogleg_norm = gnn;
-  } else if (gnorm * alpha >= radius) {
+  if (gnorm * alpha >= radius) {
     const double f = -(radius / gnorm);
     if (i0 < n) st0 = f * s.grad[i0];
     if (i1 < n) st1 = f * s.grad[i1];
     dogleg_norm = radius;
   } else {
-    double b_dot_a = wdot(s.grad, s.gn, n, lane);
+    double b_dot_a = wdot2(s.grad, s.gn, n, lane);
     b_dot_a *= -alpha;
     const double a_sq = (alpha * gnorm) * (alpha * gnorm);
     const double bma = a_sq - 2 * b_dot_a + gnn * gnn;
@@ -270,133 +261,17 @@ __device__ bool win_compute_step(WinShared& s, int n, int tid) {
     if (i1 < n) st1 = (-alpha * (1.0 - beta)) * s.grad[i1] + beta * s.gn[i1];
     dogleg_norm = sqrt(wsum(st0 * st0 + st1 * st1));
   }
-  if (i0 < n) st0 /= s.diag[i0];
-  if (i1 < n) st1 /= s.diag[i1];
+  __syncthreads();  // every warp has formed its copy of the step before warp 0 stores it (tv / tt are reused below)
   if (warp == 0) {
-    if (i0 < n) s.step[i0] = st0;
-    if (i1 < n) s.step[i1] = st1;
+    if (i0 < n) s.step[i0] = st0 / s.diag[i0];
+    if (i1 < n) s.step[i1] = st1 / s.diag[i1];
   }
   __syncthreads();
-  FTICK(7)
   cta_matvec(s.Hs, s.step, s.tt, n, warp, lane);
   __syncthreads();
-  FTICK(8)
-  const double sg = wdot(s.step, s.gs, n, lane), sHs = wdot(s.step, s.tt, n, lane);
-  const double model_change = -sg - 0.5 * sHs;
-  if (!(model_change > 0.0)) { __syncthreads(); return false; }
-  double d0 = 0, d1 = 0;
-  if (i0 < n) d0 = st0 * s.scale[i0];
-  if (i1 < n) d1 = st1 * s.scale[i1];
-  const double step_norm = sqrt(wsum(d0 * d0 + d1 * d1));
-  if (warp == 0) {
-    if (i0 < n) s.x_cand[i0] = s.x[i0] + d0;
-    if (i1 < n) s.x_cand[i1] = s.x[i1] + d1;
-    if (lane == 0) { s.model_change = model_change; s.step_norm = step_norm; s.dogleg_norm = dogleg_norm; }
-  }
-  __syncthreads();
-  FTICK(9)
-  return true;
-}
-
-// TrustRegionMinimizer: take the evaluation (cost_new, Hn, gnew) at the current evaluation point and move on
-// (DoglegN::feed + advance of the host solver). Returns with s.done set or with the next evaluation point in x_cand.
-__device__ void win_feed(WinShared& s, int n, int max_it, int tid) {
-  const int lane = tid & 31, warp = tid >> 5;
-#ifdef MML_WIN_DEVPROF
-  if (tid == 0) s.prof_t0 = clock64();
-#endif
-  double gm = 0;
-  for (int i = lane; i < n; i += 32) gm = fmax(gm, fabs(s.gnew[i]));
-  gm = wmax(gm);
-  if (tid == 0) {
-    const double c = s.cost_new;
-    int action = 0, done_after = 0;  // 0 stop, 1 accept (or first evaluation), 2 reject
-    if (s.first) {
-      s.cost = c; s.min_cost = c;
-      action = 1;
-      done_after = (!isfinite(c) || gm <= 1e-10);
-    } else {
-      const double cand = isfinite(c) ? c : DBL_MAX;
-      if (!(s.step_norm <= 1e-8 * (s.x_norm + 1e-8))) {
-        const double cost_change = s.cost - cand;
-        if (!(fabs(cost_change) <= 1e-6 * s.cost)) {
-          const double rel = cost_change / s.model_change;
-          if (rel > 1e-3) {
-            action = 1;
-            s.cost = cand;
-            if (rel < 0.25) s.radius *= 0.5;
-            if (rel > 0.75) s.radius = fmax(s.radius, 3.0 * s.dogleg_norm);
-            s.mu = fmax(1e-8, 2.0 * s.mu / 10.0);
-            s.reuse = 0;
-            done_after = gm <= 1e-10;
-          } else {
-            action = 2;
-            s.radius *= 0.5;
-            s.reuse = 1;
-          }
-        }
-      }
-    }
-    s.action = action;
-    s.done_after = done_after;
-    if (action == 0) s.done = 1;
-  }
-  __syncthreads();
-  FTICK(0)
-  const int action = s.action;
-  if (action == 0) return;
-  if (action == 1) {
-    const bool first = s.first != 0;
-    const bool better = first || s.cost < s.min_cost;
-    if (first) {
-      for (int i = tid; i < n; i += kWThreads) s.scale[i] = 1.0 / (1.0 + sqrt(s.Hn[i * kWLD + i]));
-    } else {
-      for (int i = tid; i < n; i += kWThreads) s.x[i] = s.x_cand[i];
-    }
-    __syncthreads();
-    for (int i = warp; i < n; i += kWWarps) {
-      const double si = s.scale[i];
-      for (int j = lane; j < n; j += 32) s.Hs[i * kWLD + j] = s.Hn[i * kWLD + j] * si * s.scale[j];
-    }
-    for (int i = tid; i < n; i += kWThreads) s.gs[i] = s.gnew[i] * s.scale[i];
-    const double xn = sqrt(wdot(s.x, s.x, n, lane));
-    if (better) for (int i = tid; i < n; i += kWThreads) s.x_best[i] = s.x[i];
-    if (tid == 0) {
-      s.x_norm = xn;
-      if (better) s.min_cost = s.cost;
-      if (s.done_after) s.done = 1;
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    if (!s.first && s.radius < 1e-32) s.done = 1;
-    s.first = 0;
-  }
-  __syncthreads();
-  FTICK(1)
-  if (s.done) return;
-  for (;;) {
-    if (s.it >= max_it) {
-      __syncthreads();
-      if (tid == 0) s.done = 1;
-      __syncthreads();
-      return;
-    }
-    __syncthreads();
-    if (tid == 0) { s.it++; s.total_inner++; }
-    __syncthreads();
-    if (win_compute_step(s, n, tid)) {
-      if (tid == 0) s.num_invalid = 0;
-      __syncthreads();
-      return;
-    }
-    if (tid == 0) {
-      if (++s.num_invalid >= 5) s.done = 1;
-      else { s.mu *= 10.0; s.reuse = 0; }
-    }
-    __syncthreads();
-    if (s.done) return;
-  }
+  const double sg = wdot2(s.step, s.gs, n, lane), sHs = wdot2(s.step, s.tt, n, lane);
+  *model_change = -sg - 0.5 * sHs;
+  return dogleg_norm;
 }
 
 // T_wl = [Q exRbl, Q exPbl + P] of every frame (EST.cpp:1268-1270), stored by physical slot, and the thres_dist of
@@ -494,11 +369,13 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned rank = cluster_ctarank();
   const int W = wd->W, n = wd->n, max_it = wd->max_inner;
-  const int nf = W - 1;  // IMU factors
+  const int nf = W - 1;            // IMU factors
+  const int B = n < 15 ? n : 15;   // frame block of the system
   // ---- set-up: pre-integrations and parameters into shared memory, vector2double (EST.cpp:937-950)
   for (int f = 0; f < nf; f++) {
     const unsigned* src = reinterpret_cast<const unsigned*>(&wd->pre[f + 1]);
     unsigned* dst = reinterpret_cast<unsigned*>(&s.pre[f]);
+#pragma unroll 1
     for (int i = tid; i < (int)(sizeof(mml_preint) / 4); i += kWThreads) dst[i] = src[i];
   }
   if (tid < 3) { s.gravity[tid] = wd->gravity[tid]; s.Pbl[tid] = wd->Pbl[tid]; }
@@ -514,39 +391,38 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
       for (int k = 0; k < 3; k++) s.t_before[k] = sf[k];
     }
   }
-  for (int c = tid; c < 30 * nf; c += kWThreads) {
-    const int fi = c / 30, col = c - 30 * fi;
+  if (tid < 30 * nf) {
+    const int fi = tid / 30, col = tid - 30 * fi;
     const int off[4] = {6 * fi, 6 * W + 9 * fi, 6 * (fi + 1), 6 * W + 9 * (fi + 1)};
     s.gidx[fi][col] = col < 6 ? off[0] + col : col < 15 ? off[1] + col - 6 : col < 21 ? off[2] + col - 15 : off[3] + col - 21;
   }
+#pragma unroll 1
   for (int c = tid; c < nf * kWinN; c += kWThreads) (&s.lidx[0][0])[c] = -1;
-  for (int r = tid; r < 27; r += kWThreads)
-    for (int c = 0; c <= r; c++) { s.tri[r * (r + 1) / 2 + c][0] = (unsigned char)r; s.tri[r * (r + 1) / 2 + c][1] = (unsigned char)c; }
-  for (int g = tid; g < n; g += kWThreads) {
+  if (tid < 27)
+    for (int c = 0; c <= tid; c++) { s.tri[tid * (tid + 1) / 2 + c][0] = (unsigned char)tid; s.tri[tid * (tid + 1) / 2 + c][1] = (unsigned char)c; }
+  if (tid < n) {
+    const int g = tid;
     int ps = g;
     if (W > 1) ps = g < 6 * W ? 15 * (g / 6) + g % 6 : 15 * ((g - 6 * W) / 9) + 6 + (g - 6 * W) % 9;
     s.pos[g] = ps;
     s.unpos[ps] = g;
   }
-  if (tid == 0) {
-    s.first = 1; s.done = 0; s.it = 0; s.radius = 1e4; s.mu = 1e-8; s.reuse = 0; s.num_invalid = 0;
-    s.total_inner = 0; s.evals = 0; s.alpha = -1.0; s.cost_imu = 0.0; s.nnz = 0;
-#ifdef MML_WIN_DEVPROF
-    for (int k = 0; k < 16; k++) s.prof[k] = 0;
-#endif
-  }
+  if (tid == 0) { s.cost_imu = 0.0; s.nnz = 0; }
+#pragma unroll 1
+  for (int i = tid; i < kWinN * kWLD; i += kWThreads) s.Hn[i] = 0.0;
   __syncthreads();
-  for (int c = tid; c < 30 * nf; c += kWThreads) {
-    const int fi = c / 30, col = c - 30 * fi;
-    s.lidx[fi][s.gidx[fi][col]] = col;
+  if (tid < 30 * nf) {
+    const int fi = tid / 30, col = tid - 30 * fi;
+    s.lidx[fi][s.pos[s.gidx[fi][col]]] = col;
   }
   __syncthreads();
   // entries of the normal equations that are re-formed by every evaluation: those an IMU factor couples, and the
   // pose blocks the lidar terms add to; everything else stays zero
-  for (int i = tid; i < kWinN * kWLD; i += kWThreads) s.Hn[i] = 0.0;
+#pragma unroll 1
   for (int i = warp; i < n; i += kWWarps)
+#pragma unroll 1
     for (int j = i + lane; j < n; j += 32) {
-      bool hit = i < 6 * W && j < 6 * W && i / 6 == j / 6;
+      bool hit = i / B == j / B && i % B < 6 && j % B < 6;
       for (int fi = 0; fi < nf; fi++) hit = hit || (s.lidx[fi][i] >= 0 && s.lidx[fi][j] >= 0);
       if (hit) s.nz[atomicAdd(&s.nnz, 1)] = (unsigned short)((i << 8) | j);
     }
@@ -558,19 +434,27 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
   const int n_line = A.cnt[slot][0], n_all = n_line + A.cnt[slot][1];
   const double s_info = 1.0 / wd->lidar_m, w_tan = wd->w_tan, ha = wd->huber_a;
   __syncthreads();
+  // trust-region state (Ceres 2.1 TrustRegionMinimizer + DoglegStrategy, as restated by the test oracle): every
+  // thread carries its own copy in registers and all copies take the same values
+  double cost = 0, min_cost = 0, radius = 1e4, mu = 1e-8, mu_built = -1.0, alpha = -1.0, dogleg_norm = 0, model_change = 0, step_norm = 0, x_norm = 0;
+  int first = 1, reuse = 0, it = 0, num_invalid = 0, evals = 0;
   int buf = 0;
 #ifdef MML_WIN_DEVPROF
   long long wtp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, wt0 = clock64();
 #endif
+#pragma unroll 1
   for (;;) {
-    const double* xe = s.first ? s.x : s.x_cand;
-    make_pose_split(xe + 6 * fr, s.Rbl_q, s.Pbl, s.L, tid);
-    __syncthreads();
-    WTICK(0)
+    const double* xe = first ? s.x : s.x_cand;
     if (warp < kWLidarWarps) {
+      // the pose of this CTA's frame is formed by threads 0, 32, 33 and only the lidar warps wait for it (named
+      // barrier 1): the IMU warps start on their factors at once, theirs is the longer evaluation
+      make_pose_split(xe + 6 * fr, s.Rbl_q, s.Pbl, s.L, tid);
+      asm volatile("bar.sync 1, %0;" ::"n"(kWLidarThreads) : "memory");
+      WTICK(0)
       double acc[28];
 #pragma unroll
       for (int k = 0; k < 28; k++) acc[k] = 0.0;
+#pragma unroll 1
       for (int i = sub * kWLidarThreads + tid; i < n_all; i += ncta_f * kWLidarThreads) {
         double p[3], a[3], b[3];
         if (i < n_line) {
@@ -602,6 +486,7 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
     __syncthreads();
     WTICK(2)
     // all-gather of the lidar sums through distributed shared memory (published by the cluster barrier below)
+#pragma unroll 1
     for (int t = tid; t < 28 * kWCluster; t += kWThreads) {
       const int r = t / 28, k = t - 28 * r;
       double v = 0;
@@ -610,6 +495,7 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
       st_dsmem_f64(&s.gather[buf][rank][k], (unsigned)r, v);
     }
     // rows weighted by sqrt_info (EST.cpp:1240-1242): Jw[fi][c][i] = sum_k sqrt_info[i][k] raw[fi][c][k]
+#pragma unroll 1
     for (int item = tid; item < nf * 465; item += kWThreads) {
       const int fi = item / 465, rem = item - 465 * fi, c = rem / 15, i = rem - 15 * c;
       const double* S = s.pre[fi].sqrt_info + 15 * i;
@@ -621,7 +507,8 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
     }
     __syncthreads();
     WTICK(3)
-    // the factors' J^T J and J^T r into the dense system (upper triangle formed, mirrored)
+    // the factors' J^T J and J^T r into the dense system (upper triangle formed, mirrored), frame-major positions
+#pragma unroll 1
     for (int e = tid; e < s.nnz; e += kWThreads) {
       const int gi = s.nz[e] >> 8, gj = s.nz[e] & 255;
       double v = 0;
@@ -630,76 +517,217 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
         if (li < 0 || lj < 0) continue;
         const double* a = s.Jw[fi][li];
         const double* b = s.Jw[fi][lj];
-        double t = 0;
+        double t0 = 0, t1 = 0;
 #pragma unroll
-        for (int k = 0; k < 15; k++) t += a[k] * b[k];
-        v += t;
+        for (int k = 0; k < 14; k += 2) { t0 += a[k] * b[k]; t1 += a[k + 1] * b[k + 1]; }
+        v += (t0 + a[14] * b[14]) + t1;
       }
       s.Hn[gi * kWLD + gj] = v;
       s.Hn[gj * kWLD + gi] = v;
     }
-    for (int gi = tid; gi < n; gi += kWThreads) {
+    if (tid < n) {
+      const int gi = tid;
       double v = 0;
       for (int fi = 0; fi < nf; fi++) {
         const int li = s.lidx[fi][gi];
         if (li < 0) continue;
         const double* a = s.Jw[fi][li];
         const double* r = s.Jw[fi][30];
-        double t = 0;
+        double t0 = 0, t1 = 0;
 #pragma unroll
-        for (int k = 0; k < 15; k++) t += a[k] * r[k];
-        v += t;
+        for (int k = 0; k < 14; k += 2) { t0 += a[k] * r[k]; t1 += a[k + 1] * r[k + 1]; }
+        v += (t0 + a[14] * r[14]) + t1;
       }
       s.gnew[gi] = v;
-    }
-    if (tid == kWThreads - 1) {
+    } else if (tid == kWThreads - 1) {
       double cimu = 0;
       for (int fi = 0; fi < nf; fi++)
+#pragma unroll 1
         for (int k = 0; k < 15; k++) cimu += 0.5 * s.Jw[fi][30][k] * s.Jw[fi][30][k];
       s.cost_imu = cimu;
     }
     WTICK(4)
     cluster_sync_all();
     WTICK(5)
-    // lidar blocks: sums over the CTAs of a frame in rank order
+    // lidar blocks: sums over the CTAs of a frame in rank order, added to the frame's pose block
     if (tid < 28 * W) {
       const int f = tid / 28, k = tid - 28 * f;
       double v = 0;
+#pragma unroll 1
       for (int r = f; r < kWCluster; r += W) v += s.gather[buf][r][k];
-      s.tot[f][k] = v;
-    }
-    __syncthreads();
-    if (tid < 28 * W) {
-      const int f = tid / 28, k = tid - 28 * f;
-      const double v = s.tot[f][k];
-      if (k >= 1 && k < 7) s.gnew[6 * f + k - 1] += v;
-      else if (k >= 7) {
+      const int p0 = B * f;  // position of the frame's pose block
+      if (k == 0) s.tot[f][0] = v;
+      else if (k < 7) s.gnew[p0 + k - 1] += v;
+      else {
         int i = 0, q = k - 7;
         while (q >= 6 - i) { q -= 6 - i; i++; }
         const int j = i + q;
-        s.Hn[(6 * f + i) * kWLD + 6 * f + j] += v;
-        if (j != i) s.Hn[(6 * f + j) * kWLD + 6 * f + i] += v;
+        s.Hn[(p0 + i) * kWLD + p0 + j] += v;
+        if (j != i) s.Hn[(p0 + j) * kWLD + p0 + i] += v;
       }
-    } else if (tid == 28 * W) {
-      double c = s.cost_imu;
-      for (int f = 0; f < W; f++) c += s.tot[f][0];
-      s.cost_new = c;
-      s.evals++;
     }
     __syncthreads();
     WTICK(6)
-    win_feed(s, n, max_it, tid);
+    evals++;
+    // ---- TrustRegionMinimizer: take the evaluation (cost, Hn, gnew) at the evaluation point and move on
+    double c_new = s.cost_imu;
+    for (int f = 0; f < W; f++) c_new += s.tot[f][0];
+    double gm = fmax(lane < n ? fabs(s.gnew[lane]) : 0.0, lane + 32 < n ? fabs(s.gnew[lane + 32]) : 0.0);
+    gm = wmax(gm);
+    int action = 0, done_after = 0;  // 0 stop, 1 accept (or first evaluation), 2 reject
+    if (first) {
+      cost = c_new; min_cost = c_new;
+      action = 1;
+      done_after = (!isfinite(c_new) || gm <= 1e-10);
+    } else {
+      const double cand = isfinite(c_new) ? c_new : DBL_MAX;
+      if (!(step_norm <= 1e-8 * (x_norm + 1e-8))) {
+        const double cost_change = cost - cand;
+        if (!(fabs(cost_change) <= 1e-6 * cost)) {
+          const double rel = cost_change / model_change;
+          if (rel > 1e-3) {
+            action = 1;
+            cost = cand;
+            if (rel < 0.25) radius *= 0.5;
+            if (rel > 0.75) radius = fmax(radius, 3.0 * dogleg_norm);
+            mu = fmax(1e-8, 2.0 * mu / 10.0);
+            reuse = 0;
+            done_after = gm <= 1e-10;
+          } else {
+            action = 2;
+            radius *= 0.5;
+            reuse = 1;
+          }
+        }
+      }
+    }
+    if (action == 0) break;
+    if (action == 1) {
+      if (first) {
+        if (tid < n) s.scale[tid] = 1.0 / (1.0 + sqrt(s.Hn[tid * kWLD + tid]));
+        __syncthreads();
+      }
+      // the new linearisation: Jacobi-scaled copy, and the regularised copy + right-hand side the factorisation works on
+#pragma unroll 1
+      for (int i = warp; i < n; i += kWWarps) {
+        const double si = s.scale[i];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int j = lane + 32 * h;
+          if (j < n) {
+            double v = s.Hn[i * kWLD + j] * si * s.scale[j];
+            s.Hs[i * kWLD + j] = v;
+            if (i == j) {
+              const double dg = sqrt(fmin(fmax(v, 1e-6), 1e32));
+              const double g = s.gnew[i] * si;
+              s.diag[i] = dg;
+              s.gs[i] = g;
+              s.grad[i] = g / dg;
+              s.A[n * kWLD + i] = g;
+              v += mu * dg * dg;
+            }
+            s.A[i * kWLD + j] = v;
+          }
+        }
+      }
+      mu_built = mu;
+      const bool better = first || cost < min_cost;
+      if (tid < n) {
+        const double xv = first ? s.x[tid] : s.x_cand[tid];
+        s.x[tid] = xv;
+        if (better) s.x_best[tid] = xv;
+      }
+      if (better) min_cost = cost;
+      __syncthreads();
+      x_norm = sqrt(wdot2(s.x, s.x, n, lane));
+      if (done_after) break;
+    }
+    if (!first && radius < 1e-32) break;
+    first = 0;
+    // ---- next step (with Ceres' handling of invalid steps)
+    bool stop = false;
+#pragma unroll 1
+    for (;;) {
+      if (it >= max_it) { stop = true; break; }
+      it++;
+      bool valid = true;
+      if (!reuse) {
+        reuse = 1;
+        alpha = -1.0;  // the Cauchy step length is formed on demand
+#pragma unroll 1
+        for (;;) {
+          if (!(mu < 1.0)) { valid = false; break; }
+          if (mu_built != mu) {  // retry with a larger regularisation: rebuild the working copy from Hs
+            __syncthreads();
+#pragma unroll 1
+            for (int i = warp; i < n; i += kWWarps)
+#pragma unroll
+              for (int h = 0; h < 2; h++) {
+                const int j = lane + 32 * h;
+                if (j < n) s.A[i * kWLD + j] = s.Hs[i * kWLD + j] + (i == j ? mu * s.diag[i] * s.diag[i] : 0.0);
+              }
+            if (tid < n) s.A[n * kWLD + tid] = s.gs[tid];
+            mu_built = mu;
+          }
+          const bool solved = cta_chol_solve(s, n, B, tid);
+          mu_built = -1.0;  // the working copy now holds the factor
+          if (solved) break;
+          mu *= 10.0;
+        }
+        if (valid) {
+          if (tid < n) s.gn[tid] = -s.diag[tid] * s.ysol[tid];
+          __syncthreads();
+        }
+      }
+      if (valid) {
+        const double gg = wdot2(s.grad, s.grad, n, lane);
+        const double gnorm = sqrt(gg);
+        const double gnn = sqrt(wdot2(s.gn, s.gn, n, lane));
+        double st0 = 0, st1 = 0;  // the step in scaled space, components lane and lane + 32
+        if (gnn <= radius) {
+          // Gauss-Newton branch: step = gn / diag = -y with (Hs + mu D^2) y = gs, so Hs step = -gs + mu D^2 y and the
+          // model change -step.gs - step.Hs.step / 2 = (y.gs + mu |D y|^2) / 2 needs no product with Hs
+          if (lane < n) st0 = s.gn[lane] / s.diag[lane];
+          if (lane + 32 < n) st1 = s.gn[lane + 32] / s.diag[lane + 32];
+          dogleg_norm = gnn;
+          const double ygs = -wsum((lane < n ? st0 * s.gs[lane] : 0.0) + (lane + 32 < n ? st1 * s.gs[lane + 32] : 0.0));
+          model_change = 0.5 * (ygs + mu * (gnn * gnn));
+        } else {
+          dogleg_norm = win_dogleg_branch(s, n, tid, gg, gnorm, gnn, radius, &alpha, &model_change);
+          if (lane < n) st0 = s.step[lane];
+          if (lane + 32 < n) st1 = s.step[lane + 32];
+        }
+        if (!(model_change > 0.0)) valid = false;
+        else {
+          const double d0 = lane < n ? st0 * s.scale[lane] : 0.0, d1 = lane + 32 < n ? st1 * s.scale[lane + 32] : 0.0;
+          step_norm = sqrt(wsum(d0 * d0 + d1 * d1));
+          if (warp == 0) {
+            if (lane < n) { const int g = s.unpos[lane]; s.x_cand[g] = s.x[g] + d0; }
+            if (lane + 32 < n) { const int g = s.unpos[lane + 32]; s.x_cand[g] = s.x[g] + d1; }
+          }
+        }
+      }
+      if (valid) { num_invalid = 0; break; }
+      if (++num_invalid >= 5) { stop = true; break; }
+      mu *= 10.0;
+      reuse = 0;
+    }
+    if (stop) break;
+    __syncthreads();
     WTICK(7)
-    if (s.done) break;
     buf ^= 1;
   }
 #ifdef MML_WIN_DEVPROF
-  if (rank == 0 && tid == 0)
-    printf("  feed: decide=%lld apply=%lld advance=%lld buildA=%lld chol=%lld sync=%lld gn=%lld step=%lld matvec=%lld finish=%lld\n", s.prof[0], s.prof[1],
-           s.prof[2], s.prof[3], s.prof[4], s.prof[5], s.prof[6], s.prof[7], s.prof[8], s.prof[9]);
+#if MML_WIN_DEVPROF >= 2
+  if (rank == 0 && tid == 0) {
+    printf("  chol: topsync=%lld factor=%lld panel=%lld sync=%lld update=%lld endsync=%lld backsub=%lld finalsync=%lld\n", g_cholprof[0], g_cholprof[1],
+           g_cholprof[2], g_cholprof[3], g_cholprof[4], g_cholprof[5], g_cholprof[6], g_cholprof[7]);
+    for (int k = 0; k < 8; k++) g_cholprof[k] = 0;
+  }
+#endif
   if (rank == 0 && (tid == 0 || tid == kWLidarThreads))
     printf("win solve tid %d: evals=%d pose=%lld eval=%lld wait=%lld weight=%lld assemble=%lld cluster=%lld totals=%lld feed=%lld cycles\n", tid,
-           s.evals, wtp[0], wtp[1], wtp[2], wtp[3], wtp[4], wtp[5], wtp[6], wtp[7]);
+           evals, wtp[0], wtp[1], wtp[2], wtp[3], wtp[4], wtp[5], wtp[6], wtp[7]);
 #endif
   // every remote store was completed by the last cluster barrier and all CTAs leave the loop in the same iteration
   if (rank != 0) return;
@@ -716,7 +744,7 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
   __syncthreads();
   if (tid == 0) {
     __threadfence();
-    const int it = wd->outer_it;
+    const int oit = wd->outer_it;
     int degenerate = wd->is_degenerate;
     for (int f = 0; f < W; f++) {
       const double* as = A.assoc_stats[wd->slot_of[f]];
@@ -726,23 +754,23 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
       if (f == W - 1) { wd->n_line_last = ints[0]; wd->n_plane_last = ints[1]; wd->min_sv = sv; }
     }
     wd->is_degenerate = degenerate;
-    wd->total_inner += s.total_inner;
-    wd->evals += s.evals;
-    wd->final_cost = s.min_cost;
+    wd->total_inner += it;
+    wd->evals += evals;
+    wd->final_cost = min_cost;
     const double* sb = wd->states[W - 1];
     const Quat qb = {s.q_before[0], s.q_before[1], s.q_before[2], s.q_before[3]};
     const Quat dq = quat_mul(qb, Quat{sb[3], -sb[4], -sb[5], -sb[6]});
     const double deltaR = 2.0 * atan2(sqrt((dq.x * dq.x + dq.y * dq.y) + dq.z * dq.z), fabs(dq.w)) * 180.0 / 3.14159265358979323846;
     const double d0 = s.t_before[0] - sb[0], d1 = s.t_before[1] - sb[1], d2 = s.t_before[2] - sb[2];
     const double deltaT = sqrt((d0 * d0 + d1 * d1) + d2 * d2);
-    const int done = ((deltaR < 0.05 && deltaT < 0.05) || (it + 1) >= wd->max_outer) ? 1 : 0;
-    wd->outer_it = it + 1;
-    if (!done) win_prepare_assoc(wd, it + 1);
+    const int done = ((deltaR < 0.05 && deltaT < 0.05) || (oit + 1) >= wd->max_outer) ? 1 : 0;
+    wd->outer_it = oit + 1;
+    if (!done) win_prepare_assoc(wd, oit + 1);
     if (done && A.host_out) {
       for (int f = 0; f < W; f++)
         for (int k = 0; k < 16; k++) A.host_out[16 * f + k] = wd->states[f][k];
       double* st = A.host_out + 16 * kMaxWindow;
-      st[0] = it + 1; st[1] = wd->total_inner; st[2] = wd->n_line_last; st[3] = wd->n_plane_last;
+      st[0] = oit + 1; st[1] = wd->total_inner; st[2] = wd->n_line_last; st[3] = wd->n_plane_last;
       st[4] = wd->final_cost; st[5] = wd->min_sv; st[6] = degenerate; st[7] = wd->evals; st[8] = W;
       __threadfence_system();
       *A.host_seq = wd->seq;
@@ -922,6 +950,22 @@ int mml_window_solve_graph(mml_ctx* c, WindowState* w, int cap) {
   MML_CUDA(c, cudaGraphInstantiate(&w->graph, graph, 0));
   cudaGraphDestroy(graph);
   w->graph_key = key;
+  return MML_OK;
+}
+
+// The window's solve as one graph launch, or (MML_WINDOW_DIRECT=1: profilers cannot look inside a graph that holds a
+// conditional node) as max_outer plain outer iterations on the stream, the surplus ones gated off by done_outer.
+int mml_window_solve_launch(mml_ctx* c, WindowState* w, int cap, int max_outer) {
+  static const bool direct = getenv("MML_WINDOW_DIRECT") != nullptr;
+  if (!direct) {
+    MML_CUDA(c, cudaGraphLaunch(w->graph, c->stream));
+    return MML_OK;
+  }
+  cudaGraphConditionalHandle none;
+  memset(&none, 0, sizeof(none));
+  const long long before = c->launches;
+  for (int it = 0; it < max_outer; it++) MML_CHECK(capture_outer_iteration(c, w, cap, none, 0));
+  c->launches = before;
   return MML_OK;
 }
 

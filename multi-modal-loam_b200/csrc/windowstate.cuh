@@ -82,5 +82,6 @@ constexpr size_t kPinUpBytes = sizeof(WinDev) + 8 * sizeof(WinPush);
 
 // windowsolve.cu
 int mml_window_solve_graph(mml_ctx* c, mml::WindowState* w, int cap);
+int mml_window_solve_launch(mml_ctx* c, mml::WindowState* w, int cap, int max_outer);
 int mml_window_begin_launch(mml_ctx* c, mml::WindowState* w);
 int mml_window_push_launch(mml_ctx* c, mml::WindowState* w, const mml::WinPush* push_dev);

@@ -121,7 +121,11 @@ typedef struct {
   double plan_weight_tan; /* 0.0  EST.cpp:1206 */
   double thres0, thres1, thres2; /* 25, 10, 1  EST.cpp:1207, 1377-1381 */
   int use_huber;          /* 1    EST.cpp:1221 */
-  int reserved;
+  int map_update;         /* 0    mml_odom_run_window only. 0: the context's maps are used as they are. 1: after a
+                           *      solve the loop runs the map update of EstimateLidarPose (EST.cpp:1073-1135, the
+                           *      lidarMode 2 branch PE.cpp:709, 872 takes): when the solve is not degenerate and the
+                           *      sensor has moved by >= sqrt(0.5) m since the last update, the OLDEST frame's clouds
+                           *      go through Estimator::MapIncrementLocal (mml_local_map_push_dev, clear_first) */
 } mml_est_params;
 void mml_est_params_default(mml_est_params* p);
 /* stats (may be NULL, 16 doubles): [outer_iters, inner_iters, n_line, n_plane, final_cost,
@@ -167,7 +171,17 @@ int mml_odom_run(mml_ctx* ctx, const void* const* xyzi, const void* const* line,
 int mml_local_map_push(mml_ctx* ctx, const float* corner_xyzi, int n_corner, const float* surf_xyzi, int n_surf,
                        const double* T_wl16, float leaf_corner, float leaf_surf, int* n_corner_map, int* n_surf_map);
 /* current local map of one kind (0 corner / 1 surf); out_xyzi may be NULL to query the size only                  */
+/* the same with the clouds resident in HBM (float4 xyzi). clear_first != 0: laserCloud*FromLocal were cleared by the
+ * caller (EST.cpp:1085-1087, 1127-1129, what EstimateLidarPose does), so the map becomes the filtered ring alone.
+ * An update is transactional: ring, map sizes and the association's search structures change only when every step
+ * of both kinds succeeded.                                                                                        */
+int mml_local_map_push_dev(mml_ctx* ctx, const void* corner_dev, int n_corner, const void* surf_dev, int n_surf,
+                           const double* T_wl16, float leaf_corner, float leaf_surf, int clear_first,
+                           int* n_corner_map, int* n_surf_map);
+/* place a world-frame cloud into ring entry `slot` (0..49) of one kind: the state after earlier frames were pushed */
+int mml_local_map_seed(mml_ctx* ctx, int kind, int slot, const float* xyzi_world, int n);
 int mml_local_map_get(mml_ctx* ctx, int kind, float* out_xyzi, int cap, int* n_out);
+/* forget the ring and the filtered maps; map kinds 2 / 3 become invalid (nothing is matched against them)          */
 int mml_local_map_reset(mml_ctx* ctx);
 
 /* ---- sliding window, sizes 2-4 (IMU factors, no marginalisation; BASELINE config 3 is window 3):
@@ -202,8 +216,8 @@ int mml_window_push_scan_dev(mml_ctx* ctx, const void* xyzi_dev, const void* lin
                              int max_frames, int* out_counts);
 int mml_window_get_frame(mml_ctx* ctx, int frame, int kind, float* out_xyzi, int cap, int* n_out);
 /* Estimate over the frames in the window. states: W x 16 doubles in place; preints[f] (f >= 1) links frame f-1 -> f.
- * Association and the lidar normal equations of all frames run on the device (one launch per evaluation for the
- * whole window); the W-1 IMU factors and the (15 W)-dimensional dogleg step run on the host.
+ * The whole solve runs on the device (csrc/windowsolve.cu): association of every frame, lidar terms, the W-1 IMU
+ * factors and the (15 W)-dimensional dogleg step, one graph launch and one host wait per call.
  * stats (may be NULL, 16 doubles): [outer, inner, n_line, n_plane (newest frame), final_cost, min_sv, degenerate, evaluations]. */
 int mml_estimate_window(mml_ctx* ctx, double* states, const mml_preint* const* preints, const double* exTlb16,
                         const double* gravity3, const mml_est_params* prm, double* stats);
@@ -215,7 +229,7 @@ int mml_estimate_window(mml_ctx* ctx, double* states, const mml_preint* const* p
  * k owns imu_n[k] of them (acc in units of g). state0 / stamp0: state and time of the frame before the first scan.
  * poses_front: the reference's odometry output, the OLDEST frame of the window (EST.cpp:1043-1049); poses_newest:
  * the newest frame; states_out: its full state; stats_out: n_scans x 8 (see mml_estimate_window). Any may be NULL.
- * The context's feature maps are used as they are (not updated by this call).                                      */
+ * prm->map_update selects whether the local feature maps follow the trajectory (see mml_est_params).               */
 int mml_odom_run_window(mml_ctx* ctx, const void* const* xyzi, const void* const* line, const void* const* s,
                         const int* n_pts, int n_scans, int n_lines, int host_buffers, int window, const double* stamps,
                         double stamp0, const double* imu_t, const double* imu_gyr, const double* imu_acc, const int* imu_n,
@@ -250,7 +264,7 @@ int mml_frame_associate_kind_async(mml_ctx* ctx, int kind, const double* T_wl16,
 int mml_timer_start(mml_ctx* ctx);
 int mml_timer_stop_ms(mml_ctx* ctx, float* ms);
 /* Partial normal equations of this rank's map shard, left on the device for an NCCL
- * all-reduce: returns the device pointer to 28 doubles [H upper triangle 21, g 6, cost]. */
+ * all-reduce: returns the device pointer to 28 doubles [cost, g 6, H upper triangle 21]. */
 int mml_frame_accumulate_partial_dev(mml_ctx* ctx, const double* x6, const double* T_bl16, double plan_weight_tan,
                                      double huber_a, void** partial28_dev);
 void* mml_stream_handle(mml_ctx* ctx);

@@ -34,7 +34,7 @@ EXPORTS = [
     "mml_voxel_downsample", "mml_map_set", "mml_associate", "mml_accumulate", "mml_est_params_default",
     "mml_estimate", "mml_scan_to_pose", "mml_scan_to_pose_dev", "mml_frame_set", "mml_frame_associate",
     "mml_frame_accumulate", "mml_frame_associate_async", "mml_frame_associate_kind_async", "mml_frame_accumulate_async",
-    "mml_odom_run", "mml_local_map_push", "mml_local_map_get", "mml_local_map_reset", "mml_timer_start",
+    "mml_odom_run", "mml_local_map_push", "mml_local_map_push_dev", "mml_local_map_seed", "mml_local_map_get", "mml_local_map_reset", "mml_timer_start",
     "mml_timer_stop_ms", "mml_frame_accumulate_partial_dev", "mml_stream_handle",
     "mml_imu_preintegrate", "mml_imu_factor", "mml_imu_predict", "mml_window_reset", "mml_window_size",
     "mml_window_push_frame", "mml_window_push_scan_dev", "mml_window_get_frame", "mml_estimate_window",
@@ -89,7 +89,7 @@ def imu_predict(prev16, pre):
 class EstParams(C.Structure):
     _fields_ = [("max_outer", C.c_int), ("max_inner", C.c_int), ("lidar_m", C.c_double),
                 ("plan_weight_tan", C.c_double), ("thres0", C.c_double), ("thres1", C.c_double),
-                ("thres2", C.c_double), ("use_huber", C.c_int), ("reserved", C.c_int)]
+                ("thres2", C.c_double), ("use_huber", C.c_int), ("map_update", C.c_int)]
 
 
 def load_library():
@@ -486,6 +486,11 @@ class Context:
         self._ck(self.lib.mml_local_map_push(self.h, _p(corner), int(corner.shape[0]), _p(surf), int(surf.shape[0]), _p(T),
                                              C.c_float(leaf_corner), C.c_float(leaf_surf), C.byref(nc), C.byref(ns)))
         return nc.value, ns.value
+
+    def local_map_seed(self, kind, slot, xyzi_world):
+        """Place a world-frame cloud into ring entry `slot` of one kind (0 corner / 1 surf)."""
+        x = np.ascontiguousarray(xyzi_world, np.float32).reshape(-1, 4)
+        self._ck(self.lib.mml_local_map_seed(self.h, int(kind), int(slot), _p(x), int(x.shape[0])))
 
     def local_map_get(self, kind):
         n = C.c_int(0)

@@ -357,6 +357,8 @@ struct AssocArgs {
   double T[16];
   float thres;
   GridDev G[2];  // [0] global, [1] local
+  const GridDev* G_tab[2];  // TAB kernels: the same two descriptors read from device memory (ctx->grid_table), so that a
+                            // captured launch stays valid when a map is rebuilt (mml_map_set / mml_local_map_push)
   float4* feat;
   double* moment_partials;  // [grid][8]: 6 moments, count, pad  (plane only)
   unsigned* ticket;
@@ -801,11 +803,18 @@ __device__ bool knn5_grid_group(const GridDev& Gd, float qx, float qy, float qz,
   return m.cnt == 5 && m.d[4] < thres;
 }
 
-template <int KIND, int G>
+template <int KIND, int G, bool TAB = false>
 __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
   if (A.gate && *A.gate) return;
   constexpr int QPB = 128 / G;  // queries per block
   __shared__ int s_lst[QPB][8 * G];
+  __shared__ GridDev s_G[TAB ? 2 : 1];
+  if (TAB) {
+    constexpr int kWords = (int)(sizeof(GridDev) / 4);
+    for (int i = threadIdx.x; i < 2 * kWords; i += 128)
+      reinterpret_cast<unsigned*>(s_G)[i] = reinterpret_cast<const unsigned*>(A.G_tab[i / kWords])[i % kWords];
+    __syncthreads();
+  }
   int* lst = s_lst[threadIdx.x / G];
   if (blockIdx.x == 0 && threadIdx.x == 0) MML_TL(A.tl, A.tl_slot);
   const int lg = threadIdx.x % G;
@@ -845,13 +854,13 @@ __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
       sel[rr] = (float)(((T[4 * rr] * pin[0] + T[4 * rr + 1] * pin[1]) + T[4 * rr + 2] * pin[2]) + T[4 * rr + 3]);
     float4 f0 = make_float4(q.x, q.y, q.z, -1.f), f1 = make_float4(0, 0, 0, 0), f2 = make_float4(0, 0, 0, 0);
     int cI, cJ, cK;
-    const bool in_grid = cube_of(sel[0], sel[1], sel[2], A.G[0].cen, cI, cJ, cK);
+    const bool in_grid = cube_of(sel[0], sel[1], sel[2], (TAB ? s_G[0] : A.G[0]).cen, cI, cJ, cK);
     const bool finite = !(isnan(sel[0]) || isnan(sel[1]) || isnan(sel[2]));
     if (in_grid && finite) {
       Knn5 r;
 #pragma unroll 1
       for (int mp = 0; mp < 2 && !found; mp++) {
-        const GridDev& Gd = A.G[mp];
+        const GridDev& Gd = TAB ? s_G[mp] : A.G[mp];
         if (!Gd.valid) continue;
         const float4* base;
 #ifdef MML_TIMELINE
@@ -997,6 +1006,7 @@ using namespace mml;
 // ---------------------------------------------------------------- host side
 constexpr int kCoarseFactor = 4;
 static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, float cell_hint);
+int mml_grid_table_sync(mml_ctx* ctx);
 
 int mml_map_set_device(mml_ctx* ctx, int kind, const float4* pts_d, int m, const int* cen3, float cell_hint) {
   if (kind < 0 || kind > 3) return mml_fail(ctx, MML_ERR_INVALID, "map kind must be 0..3");
@@ -1005,8 +1015,12 @@ int mml_map_set_device(mml_ctx* ctx, int kind, const float4* pts_d, int m, const
   if (cen3) { M.cen[0] = cen3[0]; M.cen[1] = cen3[1]; M.cen[2] = cen3[2]; }
   M.valid = false;
   M.m = m;
-  if (m <= 0) return MML_OK;
-  return build_grid(ctx, M, pts_d, m, cell_hint);
+  ctx->grid_table_dirty = true;
+  int rc = MML_OK;
+  if (m > 0) rc = build_grid(ctx, M, pts_d, m, cell_hint);
+  // captured association launches read the descriptors from device memory: keep that copy current
+  if (ctx->grid_table.p) { const int rc2 = mml_grid_table_sync(ctx); if (rc == MML_OK) rc = rc2; }
+  return rc;
 }
 
 extern int mml_bbox_device(mml_ctx* ctx, const float4* pts_d, int n, float* mn3, float* mx3);
@@ -1159,6 +1173,23 @@ static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, floa
 
 // Launch association of the frame slot's corner (kind 0) or surf (kind 1) queries.
 // T_dev / thres_dev / gate non-null: parameters come from the device-side solver state.
+// Device-resident copy of the four maps' descriptors (ctx->grid_table): written on the context's stream whenever a
+// map has been (re)built or dropped since the last call, so kernels enqueued afterwards see the new geometry.
+int mml_grid_table_sync(mml_ctx* ctx) {
+  MML_CUDA(ctx, ctx->grid_table.reserve(sizeof(GridDev) * 4));
+  MML_CUDA(ctx, ctx->grid_table_pin.reserve(sizeof(GridDev) * 4 * 8));
+  if (!ctx->grid_table_dirty) return MML_OK;
+  // a ring of pinned staging copies: an earlier asynchronous copy may still be in flight
+  GridDev* h = ctx->grid_table_pin.as<GridDev>() + 4 * (ctx->grid_table_gen++ & 7);
+  for (int k = 0; k < 4; k++) {
+    h[k] = grid_dev(ctx->maps[k], k);
+    for (int a = 0; a < 3; a++) h[k].cen[a] = ctx->maps[k].cen[a];  // the cube rule needs the centre even without a map
+  }
+  MML_CUDA(ctx, cudaMemcpyAsync(ctx->grid_table.p, h, sizeof(GridDev) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->grid_table_dirty = false;
+  return MML_OK;
+}
+
 int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres, const double* T_dev,
                          const float* thres_dev, const int* gate, const int* nq_dev, int cap) {
   const int nq = cap;
@@ -1217,7 +1248,14 @@ int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres,
       return MML_OK;
     }
   }
-  if (G == 32) {
+  if (G == 32 && ctx->assoc_table_mode) {
+    if (!ctx->grid_table.p) return mml_fail(ctx, MML_ERR_STATE, "map descriptor table not initialised");
+    const GridDev* tab = ctx->grid_table.as<GridDev>();
+    A.G_tab[0] = tab + (kind == 0 ? MML_MAP_CORNER_GLOBAL : MML_MAP_SURF_GLOBAL);
+    A.G_tab[1] = tab + (kind == 0 ? MML_MAP_CORNER_LOCAL : MML_MAP_SURF_LOCAL);
+    if (kind == 0) k_associate_g<0, 32, true><<<grid, 128, 0, ctx->stream>>>(A);
+    else k_associate_g<1, 32, true><<<grid, 128, 0, ctx->stream>>>(A);
+  } else if (G == 32) {
     if (kind == 0) k_associate_g<0, 32><<<grid, 128, 0, ctx->stream>>>(A);
     else k_associate_g<1, 32><<<grid, 128, 0, ctx->stream>>>(A);
   } else if (G == 8) {

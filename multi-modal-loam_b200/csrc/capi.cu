@@ -98,6 +98,8 @@ int mml_ctx_destroy(mml_ctx* c) {
     c->maps[k].pts2.release();
     c->maps[k].cell_start2.release();
   }
+  c->grid_table.release();
+  c->grid_table_pin.release();
   c->pin_in.release();
   c->pin_out.release();
   c->pin_small.release();
@@ -151,7 +153,14 @@ void mml_est_params_default(mml_est_params* p) {
   p->thres1 = 10.0;
   p->thres2 = 1.0;
   p->use_huber = 1;
-  p->reserved = 0;
+  p->map_update = 0;
+}
+
+// association / estimation without any valid feature map: MML_ERR_STATE (the header documents it)
+static int require_map(mml_ctx* c, const char* who) {
+  for (int k = 0; k < 4; k++)
+    if (c->maps[k].valid) return MML_OK;
+  return mml_fail(c, MML_ERR_STATE, (std::string(who) + ": no feature map set (mml_map_set / mml_local_map_push first)").c_str());
 }
 
 // ---- staging helpers -----------------------------------------------------------------
@@ -355,6 +364,8 @@ int mml_frame_associate_kind_async(mml_ctx* c, int kind, const double* T_wl16, d
 
 int mml_frame_associate(mml_ctx* c, const double* T_wl16, double thres_dist, int* n_line, int* n_plane,
                         double* normal_moment9, int* n_normals) {
+  if (!c || !T_wl16) return MML_ERR_INVALID;
+  MML_CHECK(require_map(c, "mml_frame_associate"));
   MML_CHECK(mml_frame_associate_async(c, T_wl16, thres_dist, 1));
   return read_assoc_stats(c, n_line, n_plane, normal_moment9, n_normals);
 }
@@ -402,8 +413,10 @@ int mml_frame_accumulate_partial_dev(mml_ctx* c, const double* x6, const double*
 
 int mml_frame_get_features(mml_ctx* c, int kind, double* out_feat) {
   if (!c || (kind != 0 && kind != 1)) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
   const int nq = kind == 0 ? c->n_corner : c->n_surf;
   if (nq <= 0) return MML_OK;
+  if (!out_feat) return MML_ERR_INVALID;
   MML_CUDA(c, c->export_buf.reserve(sizeof(double) * 12 * (size_t)nq));
   MML_CHECK(mml_export_features(c, kind, nq, c->export_buf.as<double>()));
   MML_CHECK(download(c, out_feat, c->export_buf.p, sizeof(double) * 12 * (size_t)nq));
@@ -414,6 +427,7 @@ int mml_frame_get_features(mml_ctx* c, int kind, double* out_feat) {
 int mml_associate(mml_ctx* c, int kind, const float* q_xyzi, int nq, const double* T_wl16, double thres_dist,
                   double* out_feat, int* n_feat, double* normal_moment9, int* n_normals) {
   if (!c || (kind != 0 && kind != 1) || nq < 0 || !T_wl16) return MML_ERR_INVALID;
+  MML_CHECK(require_map(c, "mml_associate"));
   if (kind == 0) MML_CHECK(mml_frame_set(c, q_xyzi, nq, nullptr, 0));
   else MML_CHECK(mml_frame_set(c, nullptr, 0, q_xyzi, nq));
   MML_CHECK(mml_associate_launch(c, kind, T_wl16, (float)thres_dist, nullptr, nullptr, nullptr, nullptr, nq));
@@ -444,6 +458,7 @@ int mml_accumulate(mml_ctx* c, const double* line_feat, int n_line, const double
 int mml_estimate(mml_ctx* c, const float* corner_xyzi, int n_corner, const float* surf_xyzi, int n_surf,
                  const double* exTlb16, double* P3, double* q_wxyz4, const mml_est_params* prm, double* stats) {
   if (!c || !exTlb16 || !P3 || !q_wxyz4) return MML_ERR_INVALID;
+  MML_CHECK(require_map(c, "mml_estimate"));
   mml_est_params def;
   mml_est_params_default(&def);
   if (!prm) prm = &def;

@@ -114,6 +114,12 @@ struct mml_ctx {
 
   // resident maps
   mml::GridMap maps[4];
+  // device-resident copy of the maps' descriptors for captured association launches (associate.cu, windowsolve.cu)
+  mml::DevBuf grid_table;
+  mml::PinBuf grid_table_pin;
+  bool grid_table_dirty = true;
+  unsigned grid_table_gen = 0;
+  bool assoc_table_mode = false;
 
   // frame slot (queries + features)
   mml::DevBuf q_corner, q_surf;   // float4

@@ -171,6 +171,11 @@ __global__ void __launch_bounds__(256) k_vox_keys(const float4* __restrict__ pts
   const int maxb0 = (int)floorf(mxx * inv), maxb1 = (int)floorf(mxy * inv);
   const int div0 = maxb0 - minb0 + 1, div1 = maxb1 - minb1 + 1;
   const float4 p = pts[i];
+  if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) {  // dropped like PCL drops them from a non-dense cloud: sorted last, never a head
+    keys[i] = 0xFFFFFFFFu;
+    vals[i] = (unsigned)i;
+    return;
+  }
   const int i0 = (int)(floorf(p.x * inv) - (float)minb0);
   const int i1 = (int)(floorf(p.y * inv) - (float)minb1);
   const int i2 = (int)(floorf(p.z * inv) - (float)minb2);
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(256) k_vox_heads(const unsigned* __restrict__ 
   const int n = *n_dev;
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
-  head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+  head[i] = (keys[i] != 0xFFFFFFFFu && (i == 0 || keys[i] != keys[i - 1])) ? 1 : 0;
 }
 
 // one thread per voxel head: sum members in sorted (= ascending input index) order
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(256) k_vox_centroid(const float4* __restrict__
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const unsigned key = keys[i];
-  if (i > 0 && keys[i - 1] == key) return;
+  if (key == 0xFFFFFFFFu || (i > 0 && keys[i - 1] == key)) return;
   float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
   int j = i;
   for (; j < n && keys[j] == key; j++) {

@@ -35,7 +35,8 @@ struct LocalMapDev {
   int ring_n[2][kLocalWindow];
   mml::DevBuf from_local[2];
   int from_n[2] = {0, 0};
-  mml::DevBuf stage, concat, out, cnt;
+  mml::DevBuf stage, concat, cnt;
+  mml::DevBuf pending[2], result[2];  // an update is prepared here and committed only when both kinds succeeded
   long long id = 0;  // localMapID
   LocalMapDev() { memset(ring_n, 0, sizeof(ring_n)); }
 };
@@ -45,6 +46,95 @@ LocalMapDev* get(mml_ctx* c) {
   return static_cast<LocalMapDev*>(c->local_map);
 }
 
+// the local maps of the association become invalid (nothing is matched against them) until the next update
+int drop_local_maps(mml_ctx* c) {
+  int rc = mml_map_set_device(c, MML_MAP_CORNER_LOCAL, nullptr, 0, nullptr, 0.f);
+  const int rc2 = mml_map_set_device(c, MML_MAP_SURF_LOCAL, nullptr, 0, nullptr, 0.f);
+  return rc != MML_OK ? rc : rc2;
+}
+
+// One MapIncrementLocal (EST.cpp:1585-1643). src_device: the clouds are device pointers. clear_first: the caller
+// cleared laserCloud*FromLocal beforehand (EST.cpp:1085-1087, 1127-1129: what EstimateLidarPose does), so the new
+// map is the filtered concatenation of the ring alone.
+// Transactional: the new ring entry and the new filtered maps of BOTH kinds are prepared in side buffers; ring,
+// sizes, localMapID and the association's search structures change only after every fallible step has succeeded.
+int local_map_push_impl(mml_ctx* c, const void* corner, int n_corner, const void* surf, int n_surf, bool src_device,
+                        const double* T_wl16, float leaf_corner, float leaf_surf, bool clear_first, int* n_corner_map,
+                        int* n_surf_map) {
+  cudaStream_t st = c->stream;
+  LocalMapDev* L = get(c);
+  const int slot = (int)(L->id % kLocalWindow);  // EST.cpp:1597
+  Pose16 P;
+  for (int i = 0; i < 16; i++) P.T[i] = T_wl16[i];
+  MML_CUDA(c, L->cnt.reserve(64));
+  int m_new[2] = {0, 0};
+  for (int k = 0; k < 2; k++) {
+    const void* src = k == 0 ? corner : surf;
+    const int n = k == 0 ? n_corner : n_surf;
+    const float leaf = k == 0 ? leaf_corner : leaf_surf;
+    // new frame -> world frame -> pending ring entry (EST.cpp:1600-1612)
+    if (n > 0) {
+      MML_CUDA(c, L->pending[k].reserve(sizeof(float4) * (size_t)n));
+      const float4* in = static_cast<const float4*>(src);
+      if (!src_device) {
+        MML_CUDA(c, L->stage.reserve(sizeof(float4) * (size_t)n));
+        MML_CUDA(c, cudaMemcpyAsync(L->stage.p, src, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
+        in = L->stage.as<float4>();
+      }
+      k_point_to_map<<<div_up(n, 256), 256, 0, st>>>(in, n, P, L->pending[k].as<float4>());
+      MML_LAUNCHED(c);
+    }
+    // previous filtered map (unless cleared) + the 50 ring entries, in that order (EST.cpp:1620-1624)
+    const int keep = clear_first ? 0 : L->from_n[k];
+    long long total = keep;
+    for (int i = 0; i < kLocalWindow; i++) total += (i == slot) ? n : L->ring_n[k][i];
+    if (total > 0x7fffffffLL / 32) return mml_fail(c, MML_ERR_CAPACITY, "local map too large");
+    int m = 0;
+    if (total > 0) {
+      MML_CUDA(c, L->concat.reserve(sizeof(float4) * (size_t)total));
+      MML_CUDA(c, L->result[k].reserve(sizeof(float4) * (size_t)total));
+      float4* dst = L->concat.as<float4>();
+      size_t at = 0;
+      if (keep) {
+        MML_CUDA(c, cudaMemcpyAsync(dst, L->from_local[k].p, sizeof(float4) * (size_t)keep, cudaMemcpyDeviceToDevice, st));
+        at += (size_t)keep;
+      }
+      for (int i = 0; i < kLocalWindow; i++) {
+        const int ni = (i == slot) ? n : L->ring_n[k][i];
+        if (!ni) continue;
+        const void* from = (i == slot) ? L->pending[k].p : L->ring[k][i].p;
+        MML_CUDA(c, cudaMemcpyAsync(dst + at, from, sizeof(float4) * (size_t)ni, cudaMemcpyDeviceToDevice, st));
+        at += (size_t)ni;
+      }
+      // voxel filter (EST.cpp:1630-1635)
+      int* cnt = L->cnt.as<int>() + 4 * k;
+      const int tot = (int)total;
+      MML_CUDA(c, cudaMemcpyAsync(cnt, &tot, sizeof(int), cudaMemcpyHostToDevice, st));
+      MML_CHECK(mml_voxel_device(c, dst, cnt, tot, leaf, L->result[k].as<float4>(), cnt + 1));
+      MML_CUDA(c, cudaMemcpyAsync(&m, cnt + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+      MML_CUDA(c, cudaStreamSynchronize(st));
+    }
+    m_new[k] = m;
+  }
+  // ---- commit
+  for (int k = 0; k < 2; k++) {
+    std::swap(L->ring[k][slot], L->pending[k]);
+    L->ring_n[k][slot] = k == 0 ? n_corner : n_surf;
+    std::swap(L->from_local[k], L->result[k]);
+    L->from_n[k] = m_new[k];
+  }
+  L->id++;  // EST.cpp:1640
+  // the association's search structures (replace the kd-tree rebuilds at EST.cpp:1159-1167)
+  for (int k = 0; k < 2; k++) {
+    const int rc = mml_map_set_device(c, k == 0 ? MML_MAP_CORNER_LOCAL : MML_MAP_SURF_LOCAL, L->from_local[k].as<float4>(), L->from_n[k], nullptr, 0.f);
+    if (rc != MML_OK) { drop_local_maps(c); return rc; }  // never leave one kind new and the other stale
+  }
+  if (n_corner_map) *n_corner_map = m_new[0];
+  if (n_surf_map) *n_surf_map = m_new[1];
+  MML_CUDA(c, cudaStreamSynchronize(st));
+  return MML_OK;
+}
+
 }  // namespace
 
 void mml_local_map_destroy(mml_ctx* c) {
@@ -52,21 +142,22 @@ void mml_local_map_destroy(mml_ctx* c) {
   LocalMapDev* L = static_cast<LocalMapDev*>(c->local_map);
   for (int k = 0; k < 2; k++) {
     for (int i = 0; i < kLocalWindow; i++) L->ring[k][i].release();
-    L->from_local[k].release();
+    L->from_local[k].release(); L->pending[k].release(); L->result[k].release();
   }
-  L->stage.release(); L->concat.release(); L->out.release(); L->cnt.release();
+  L->stage.release(); L->concat.release(); L->cnt.release();
   delete L;
   c->local_map = nullptr;
 }
 
 extern "C" {
 
+// forget the ring and the filtered maps; the association's local maps become invalid with them
 int mml_local_map_reset(mml_ctx* c) {
   if (!c) return MML_ERR_INVALID;
   cudaSetDevice(c->device);
   MML_CUDA(c, cudaStreamSynchronize(c->stream));
   mml_local_map_destroy(c);
-  return MML_OK;
+  return drop_local_maps(c);
 }
 
 // One MapIncrementLocal. corner / surf: the frame's (down-sampled) feature clouds in the LiDAR frame, T_wl16 the
@@ -78,62 +169,33 @@ int mml_local_map_push(mml_ctx* c, const float* corner_xyzi, int n_corner, const
       !(leaf_surf > 0.f))
     return MML_ERR_INVALID;
   cudaSetDevice(c->device);
-  cudaStream_t st = c->stream;
+  return local_map_push_impl(c, corner_xyzi, n_corner, surf_xyzi, n_surf, false, T_wl16, leaf_corner, leaf_surf, false, n_corner_map, n_surf_map);
+}
+
+// The same with the clouds resident in HBM (float4 xyzi) and the caller's clear of laserCloud*FromLocal
+// (clear_first != 0: the local map becomes the filtered concatenation of the ring, as in EstimateLidarPose).
+int mml_local_map_push_dev(mml_ctx* c, const void* corner_dev, int n_corner, const void* surf_dev, int n_surf, const double* T_wl16,
+                           float leaf_corner, float leaf_surf, int clear_first, int* n_corner_map, int* n_surf_map) {
+  if (!c || !T_wl16 || n_corner < 0 || n_surf < 0 || (n_corner && !corner_dev) || (n_surf && !surf_dev) || !(leaf_corner > 0.f) ||
+      !(leaf_surf > 0.f))
+    return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  return local_map_push_impl(c, corner_dev, n_corner, surf_dev, n_surf, true, T_wl16, leaf_corner, leaf_surf, clear_first != 0, n_corner_map, n_surf_map);
+}
+
+// Place a world-frame cloud into ring entry `slot` of one kind (0 corner / 1 surf): the state after earlier frames
+// had been pushed (tests and benchmarks start from a map instead of building it up scan by scan). The filtered maps
+// change with the next push.
+int mml_local_map_seed(mml_ctx* c, int kind, int slot, const float* xyzi_world, int n) {
+  if (!c || kind < 0 || kind > 1 || slot < 0 || slot >= kLocalWindow || n < 0 || (n && !xyzi_world)) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
   LocalMapDev* L = get(c);
-  const int slot = (int)(L->id % kLocalWindow);  // EST.cpp:1597
-  Pose16 P;
-  for (int i = 0; i < 16; i++) P.T[i] = T_wl16[i];
-  MML_CUDA(c, L->cnt.reserve(64));
-  for (int k = 0; k < 2; k++) {
-    const float* src = k == 0 ? corner_xyzi : surf_xyzi;
-    const int n = k == 0 ? n_corner : n_surf;
-    const float leaf = k == 0 ? leaf_corner : leaf_surf;
-    // new frame -> world frame -> ring slot (EST.cpp:1600-1612)
-    if (n > 0) {
-      MML_CUDA(c, L->stage.reserve(sizeof(float4) * (size_t)n));
-      MML_CUDA(c, L->ring[k][slot].reserve(sizeof(float4) * (size_t)n));
-      MML_CUDA(c, cudaMemcpyAsync(L->stage.p, src, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
-      k_point_to_map<<<div_up(n, 256), 256, 0, st>>>(L->stage.as<float4>(), n, P, L->ring[k][slot].as<float4>());
-      MML_LAUNCHED(c);
-    }
-    L->ring_n[k][slot] = n;
-    // previous filtered map + the 50 ring entries, in that order (EST.cpp:1620-1624)
-    long long total = L->from_n[k];
-    for (int i = 0; i < kLocalWindow; i++) total += L->ring_n[k][i];
-    if (total > 0x7fffffffLL / 32) return mml_fail(c, MML_ERR_CAPACITY, "local map too large");
-    int m = 0;
-    if (total > 0) {
-      MML_CUDA(c, L->concat.reserve(sizeof(float4) * (size_t)total));
-      MML_CUDA(c, L->out.reserve(sizeof(float4) * (size_t)total));
-      float4* dst = L->concat.as<float4>();
-      size_t at = 0;
-      if (L->from_n[k]) {
-        MML_CUDA(c, cudaMemcpyAsync(dst, L->from_local[k].p, sizeof(float4) * (size_t)L->from_n[k], cudaMemcpyDeviceToDevice, st));
-        at += (size_t)L->from_n[k];
-      }
-      for (int i = 0; i < kLocalWindow; i++) {
-        if (!L->ring_n[k][i]) continue;
-        MML_CUDA(c, cudaMemcpyAsync(dst + at, L->ring[k][i].p, sizeof(float4) * (size_t)L->ring_n[k][i], cudaMemcpyDeviceToDevice, st));
-        at += (size_t)L->ring_n[k][i];
-      }
-      // voxel filter (EST.cpp:1630-1635)
-      int* cnt = L->cnt.as<int>();
-      const int tot = (int)total;
-      MML_CUDA(c, cudaMemcpyAsync(cnt, &tot, sizeof(int), cudaMemcpyHostToDevice, st));
-      MML_CHECK(mml_voxel_device(c, dst, cnt, tot, leaf, L->out.as<float4>(), cnt + 1));
-      MML_CUDA(c, cudaMemcpyAsync(&m, cnt + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-      MML_CUDA(c, cudaStreamSynchronize(st));
-      MML_CUDA(c, L->from_local[k].reserve(sizeof(float4) * (size_t)(m > 0 ? m : 1)));
-      if (m > 0) MML_CUDA(c, cudaMemcpyAsync(L->from_local[k].p, L->out.p, sizeof(float4) * (size_t)m, cudaMemcpyDeviceToDevice, st));
-    }
-    L->from_n[k] = m;
-    // the association's search structure for this kind (replaces the kd-tree rebuild at EST.cpp:1159-1167)
-    MML_CHECK(mml_map_set_device(c, k == 0 ? MML_MAP_CORNER_LOCAL : MML_MAP_SURF_LOCAL, L->from_local[k].as<float4>(), m, nullptr, 0.f));
-    if (k == 0 && n_corner_map) *n_corner_map = m;
-    if (k == 1 && n_surf_map) *n_surf_map = m;
+  if (n > 0) {
+    MML_CUDA(c, L->ring[kind][slot].reserve(sizeof(float4) * (size_t)n));
+    MML_CUDA(c, cudaMemcpyAsync(L->ring[kind][slot].p, xyzi_world, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    MML_CUDA(c, cudaStreamSynchronize(c->stream));
   }
-  MML_CUDA(c, cudaStreamSynchronize(st));
-  L->id++;  // EST.cpp:1640
+  L->ring_n[kind][slot] = n;
   return MML_OK;
 }
 

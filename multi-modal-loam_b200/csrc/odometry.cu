@@ -517,6 +517,12 @@ int mml_odom_run(mml_ctx* c, const void* const* xyzi, const void* const* line, c
                  const double* exTlb16, float leaf_corner, float leaf_surf, const mml_est_params* prm, double* poses_out,
                  float* total_ms, int* counts_out /* n_scans x 4, optional */) {
   if (!c || n_scans < 0 || !T_init16 || !T_prev16 || !exTlb16 || !poses_out) return MML_ERR_INVALID;
+  if (n_scans > 0 && (!xyzi || !line || !n_pts)) return MML_ERR_INVALID;
+  {
+    bool any_map = false;
+    for (int k = 0; k < 4; k++) any_map = any_map || c->maps[k].valid;
+    if (!any_map) return mml_fail(c, MML_ERR_STATE, "mml_odom_run: no feature map set");
+  }
   cudaSetDevice(c->device);
   mml_est_params def;
   mml_est_params_default(&def);

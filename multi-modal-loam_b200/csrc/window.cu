@@ -26,6 +26,8 @@ int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres,
 int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_d, const int* scan_off, int n_scans,
                        int n_lines, uint8_t* label_d, bool sequential);
 int mml_split_voxel_capacity();
+extern "C" int mml_local_map_push_dev(mml_ctx* c, const void* corner_dev, int n_corner, const void* surf_dev, int n_surf, const double* T_wl16,
+                                      float leaf_corner, float leaf_surf, int clear_first, int* n_corner_map, int* n_surf_map);
 namespace mml { struct SvChain; }
 int mml_split_voxel_device(mml_ctx* ctx, const float4* pts_d, const float* s_d, const uint8_t* label_d, int n,
                            const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, float4* corner_out,
@@ -551,6 +553,12 @@ int mml_odom_run_window(mml_ctx* c, const void* const* xyzi, const void* const* 
   memcpy(prev, state0, sizeof(prev));
   double t_prev = stamp0;
   size_t imu_off = 0;
+  // map update of EstimateLidarPose (prm->map_update): counts of the frame in every physical slot, the transform the
+  // reference carries from call to call (transformTobeMapped) and the position of the last update (EST.h:339)
+  int slot_counts[kMaxWindow][3] = {};  // n_corner_ds, n_surf_ds, n_sharp
+  double T_map[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  double last_update_pose[3] = {-1.0, -1.0, -1.0};
+  long map_updates = 0;
   if (total_ms) { MML_CUDA(c, cudaEventRecord(c->ev0, st)); }
   // labels do not depend on the pose (the extraction node of the reference runs ahead of the estimator, FE.cpp ->
   // /union_feature_cloud -> PE.cpp): scan k+1 is copied and labelled on its own stream while scan k is solved
@@ -640,6 +648,41 @@ int mml_odom_run_window(mml_ctx* c, const void* const* xyzi, const void* const* 
     if (poses_newest) pose16(prev, poses_newest + 16 * (size_t)k);
     if (states_out) memcpy(states_out + 16 * (size_t)k, prev, sizeof(prev));
     if (stats_out) memcpy(stats_out + 8 * (size_t)k, so, sizeof(double) * 8);
+    slot_counts[hp->slot][0] = flags[4]; slot_counts[hp->slot][1] = flags[5]; slot_counts[hp->slot][2] = flags[0];
+    if (prm->map_update) {
+      // EST.cpp:973-977: transformTobeMapped starts from the newest frame; 1041-1062: the oldest frame's pose replaces
+      // it when enough corner points were seen (lidarMode 2: corner_cnt > 50), else only x and y are taken over
+      auto twl = [&](const double* st16, double* T) {
+        double Rq[9];
+        quat_to_R(Quat{st16[3], st16[4], st16[5], st16[6]}, Rq);
+        for (int r = 0; r < 3; r++) {
+          for (int q = 0; q < 3; q++) T[4 * r + q] = Rq[3 * r] * Rbl[q] + Rq[3 * r + 1] * Rbl[3 + q] + Rq[3 * r + 2] * Rbl[6 + q];
+          T[4 * r + 3] = Rq[3 * r] * Pbl[0] + Rq[3 * r + 1] * Pbl[1] + Rq[3 * r + 2] * Pbl[2] + st16[r];
+        }
+        T[12] = 0; T[13] = 0; T[14] = 0; T[15] = 1;
+      };
+      int corner_cnt = 0;
+      for (int f = 0; f < W; f++) corner_cnt += slot_counts[w->order[f]][2];
+      const bool degenerate = so[6] != 0.0;
+      if (corner_cnt > 50) twl(out, T_map);
+      else {
+        double Tb[16];
+        twl(next, Tb);  // the pose the call started from (the predicted newest frame)
+        memcpy(T_map, Tb, sizeof(Tb));
+        T_map[3] = out[0]; T_map[7] = out[1];
+      }
+      if (!degenerate) {  // EST.cpp:1066-1135
+        const double dx = last_update_pose[0] - T_map[3], dy = last_update_pose[1] - T_map[7], dz = last_update_pose[2] - T_map[11];
+        const float dis = (float)(dx * dx + dy * dy + dz * dz);
+        if (dis >= 0.5f) {
+          WinSlot& f0 = w->frame(0);
+          MML_CHECK(mml_local_map_push_dev(c, f0.q_corner.p, slot_counts[w->order[0]][0], f0.q_surf.p, slot_counts[w->order[0]][1], T_map,
+                                           leaf_corner, leaf_surf, 1, nullptr, nullptr));
+          last_update_pose[0] = T_map[3]; last_update_pose[1] = T_map[7]; last_update_pose[2] = T_map[11];
+          map_updates++;
+        }
+      }
+    }
     if (g_prof_on) { g_prof.imu += tq1 - tq0; g_prof.launch += tq2 - tq1; g_prof.wait += tq3 - tq2; g_prof.evals += (long)so[7]; g_prof.scans++; }
   }
   if (total_ms) {
@@ -651,8 +694,8 @@ int mml_odom_run_window(mml_ctx* c, const void* const* xyzi, const void* const* 
   }
   if (g_prof_on && g_prof.scans) {
     const double ns = (double)g_prof.scans;
-    fprintf(stderr, "[mml window prof] per scan: host pre-integration + prediction %.1f us, enqueue %.1f us, wait for the solve %.1f us, evaluations %.1f\n",
-            g_prof.imu / ns, g_prof.launch / ns, g_prof.wait / ns, g_prof.evals / ns);
+    fprintf(stderr, "[mml window prof] per scan: host pre-integration + prediction %.1f us, enqueue %.1f us, wait for the solve %.1f us, evaluations %.1f; map updates %ld\n",
+            g_prof.imu / ns, g_prof.launch / ns, g_prof.wait / ns, g_prof.evals / ns, map_updates);
     g_prof = WinProf();
   }
   return MML_OK;

@@ -29,6 +29,7 @@
 
 int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres, const double* T_dev,
                          const float* thres_dev, const int* gate, const int* nq_dev, int cap);
+int mml_grid_table_sync(mml_ctx* ctx);
 
 namespace mml {
 
@@ -793,7 +794,14 @@ static int win_lend(mml_ctx* c, WinSlot& s) {
 }
 
 // association of every physical slot (2 kinds x kMaxWindow kernels side by side on captured streams), then the solve
+static int capture_outer_iteration_impl(mml_ctx* c, WindowState* w, int cap, cudaGraphConditionalHandle cond, int use_cond);
 static int capture_outer_iteration(mml_ctx* c, WindowState* w, int cap, cudaGraphConditionalHandle cond, int use_cond) {
+  c->assoc_table_mode = cap <= 32768;
+  const int rc = capture_outer_iteration_impl(c, w, cap, cond, use_cond);
+  c->assoc_table_mode = false;
+  return rc;
+}
+static int capture_outer_iteration_impl(mml_ctx* c, WindowState* w, int cap, cudaGraphConditionalHandle cond, int use_cond) {
   cudaStream_t st = c->stream;
   WinDev* wd = w->dev.as<WinDev>();
   if (cudaEventRecord(w->fork, st) != cudaSuccess) return MML_ERR_CUDA;
@@ -890,15 +898,21 @@ int mml_window_solve_graph(mml_ctx* c, WindowState* w, int cap) {
     mix((long long)(size_t)s.f_plane.p); mix((long long)(size_t)s.assoc_stats.p); mix((long long)(size_t)s.cnt.p);
     mix((long long)(size_t)s.assoc_part[0].p); mix((long long)(size_t)s.assoc_part[1].p);
   }
-  for (int k = 0; k < 4; k++) {
-    const GridMap& M = c->maps[k];
-    mix(M.valid); mix(M.coarse); mix((long long)(size_t)M.pts2.p); mix((long long)(size_t)M.cell_start2.p);
-    mix((long long)(size_t)M.pts.p); mix((long long)(size_t)M.cell_start.p); mix(M.m); mix(M.ncell);
-    mix(M.dim[0]); mix(M.dim[1]); mix(M.dim[2]); mix((long long)(M.cell * 1e6f));
-    mix(M.cube_lo[0]); mix(M.cube_lo[1]); mix(M.cube_lo[2]);
-    mix((long long)(M.org_d[0] * 1e6)); mix((long long)(M.org_d[1] * 1e6)); mix((long long)(M.org_d[2] * 1e6));
-    mix(M.cen[0]); mix(M.cen[1]); mix(M.cen[2]);
-  }
+  // scan-sized frames: the association kernels read the maps' descriptors from device memory (ctx->grid_table), so
+  // the graph survives map updates; map-sized frames bake the geometry into the launch and are re-captured
+  const bool table_mode = cap <= 32768;
+  MML_CHECK(mml_grid_table_sync(c));
+  mix(table_mode ? 1 : 0); mix((long long)(size_t)c->grid_table.p);
+  if (!table_mode)
+    for (int k = 0; k < 4; k++) {
+      const GridMap& M = c->maps[k];
+      mix(M.valid); mix(M.coarse); mix((long long)(size_t)M.pts2.p); mix((long long)(size_t)M.cell_start2.p);
+      mix((long long)(size_t)M.pts.p); mix((long long)(size_t)M.cell_start.p); mix(M.m); mix(M.ncell);
+      mix(M.dim[0]); mix(M.dim[1]); mix(M.dim[2]); mix((long long)(M.cell * 1e6f));
+      mix(M.cube_lo[0]); mix(M.cube_lo[1]); mix(M.cube_lo[2]);
+      mix((long long)(M.org_d[0] * 1e6)); mix((long long)(M.org_d[1] * 1e6)); mix((long long)(M.org_d[2] * 1e6));
+      mix(M.cen[0]); mix(M.cen[1]); mix(M.cen[2]);
+    }
   if (w->graph && w->graph_key == key) return MML_OK;
   if (w->graph) { cudaGraphExecDestroy(w->graph); w->graph = nullptr; }
   // the table of count pointers the begin / push kernels use to silence unused slots

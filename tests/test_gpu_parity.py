@@ -667,3 +667,46 @@ def test_s4_one_million_queries_match_oracle(ctx, mm, orc, synth):
     r, rn = om.associate_line(qc, T, 1.0)
     assert n == rn
     _cmp_features(f, r, 0)
+
+
+def test_local_map_ring_wraps_and_reset_invalidates(ctx, mm, orc, synth, scene):
+    """More than 50 updates (the ring slot of update k is reused by update k + 50 with a different size, one frame is
+    empty): maps bit-identical to the oracle along the way; after a reset nothing is matched against the old map."""
+    from oracle import map_maintenance as mmt
+    rng = np.random.default_rng(12)
+    lm = mmt.LocalMap()
+    ctx.local_map_reset()
+    surf_all, corner_all = scene["map_surf"], scene["map_corner"]
+    for k in range(54):
+        T = synth.make_T(synth.rot_z(0.01 * k), np.array([0.05 * k, -0.02 * k, 0.0]))
+        Ti = np.linalg.inv(T)
+        ns_k, nc_k = (0, 0) if k == 7 else (int(rng.integers(150, 400)), int(rng.integers(10, 40)))
+        s = surf_all[rng.choice(surf_all.shape[0], ns_k, replace=False)].copy()
+        c = corner_all[rng.choice(corner_all.shape[0], nc_k, replace=False)].copy()
+        for cloud in (s, c):
+            cloud[:, :3] = (cloud[:, :3].astype(np.float64) @ Ti[:3, :3].T + Ti[:3, 3]).astype(np.float32)
+        oc, os_ = lm.increment(c, s, T)
+        nc, ns = ctx.local_map_push(c, s, T)
+        assert (nc, ns) == (oc.shape[0], os_.shape[0]), k
+        if k in (0, 7, 8, 49, 50, 53):
+            assert np.array_equal(ctx.local_map_get(0), oc) and np.array_equal(ctx.local_map_get(1), os_), k
+    ctx.map_set(mm.MAP_CORNER_GLOBAL, np.zeros((0, 4), np.float32)); ctx.map_set(mm.MAP_SURF_GLOBAL, np.zeros((0, 4), np.float32))
+    corner_q, surf_q = _assoc_inputs(orc, scene)
+    Tq = scene["T_true"] @ synth.s1_offset_pose()
+    ctx.local_map_reset()
+    with pytest.raises(mm.MmlError):   # no valid map at all: MML_ERR_STATE instead of a silent empty result
+        ctx.associate(1, surf_q, Tq, 1.0)
+
+
+def test_voxel_downsample_drops_non_finite_points(ctx, orc, scene):
+    """NaN / Inf rows are dropped like the oracle (and PCL for a non-dense cloud) drops them."""
+    x, _, _ = scene["vlp"]
+    pts = x[:5000].copy()
+    pts[17, 0] = np.nan
+    pts[400, 2] = np.inf
+    pts[4999, 1] = -np.inf
+    ref = orc.voxel_downsample(pts, 0.4)
+    got = ctx.voxel_downsample(pts, 0.4)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+    assert np.isfinite(got).all()
+

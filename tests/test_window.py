@@ -145,3 +145,48 @@ def test_odom_run_window_matches_oracle_loop(ctx, mm, orc, synth, scene, W):
     assert np.array_equal(res_g["stats"][:, 0], res_o["stats"][:, 0])
     err = np.abs(res_g["poses_newest"][:, :3, 3] - np.array([Ts[k][:3, 3] for k in range(1, n + 1)])).max()
     assert err < 0.05
+
+
+@pytest.mark.gpu
+def test_odom_run_window_with_map_updates_matches_oracle_loop(ctx, mm, orc, synth, scene):
+    """The loop with the map update of EstimateLidarPose switched on (mml_est_params.map_update): a fast trajectory
+    (0.4 m per scan) crosses the sqrt(0.5) m gate every other scan; poses, update count and the final local maps
+    (bit for bit) against the oracle loop driving map_maintenance.LocalMap."""
+    from oracle import map_maintenance as mmt
+    from oracle import window_loop
+
+    n, W, v = 8, 3, 4.0
+    Ts = synth.trajectory(n, v=v)
+    imu, stamps = synth.imu_stream(n, v=v)
+    scans = []
+    for k in range(1, n + 1):
+        xv, rv, sv = synth.vlp16_scan(Ts[k], seed=4000 + k, T_ws_start=Ts[k - 1])
+        xh, lh, sh = synth.horizon_scan(Ts[k], 24000, seed=5000 + k, T_ws_start=Ts[k - 1])
+        scans.append((np.concatenate([xv, xh]), np.concatenate([rv, lh + 16]).astype(np.uint16), np.concatenate([sv, sh])))
+    ctx.local_map_reset()
+    ctx.map_set(mm.MAP_SURF_GLOBAL, np.zeros((0, 4), np.float32))
+    ctx.map_set(mm.MAP_CORNER_GLOBAL, np.zeros((0, 4), np.float32))
+    ctx.map_set(mm.MAP_SURF_LOCAL, scene["map_surf"])
+    ctx.map_set(mm.MAP_CORNER_LOCAL, scene["map_corner"])
+    ctx.local_map_seed(0, 49, scene["map_corner"])   # the map "earlier frames" built
+    ctx.local_map_seed(1, 49, scene["map_surf"])
+    om = orc.Map()
+    om.set(orc.SURF_LOCAL, scene["map_surf"])
+    om.set(orc.CORNER_LOCAL, scene["map_corner"])
+    lm = mmt.LocalMap(0.4, 0.2)
+    lm.ring[0][49] = np.ascontiguousarray(scene["map_corner"], np.float32)
+    lm.ring[1][49] = np.ascontiguousarray(scene["map_surf"], np.float32)
+    state0 = _state(orc, synth, Ts[0], v)
+    res_o = window_loop.run(om, scans, 22, W, stamps[1:], stamps[0], imu[1:], state0, local_map=lm)
+    assert res_o["map_updates"] >= 3
+    host = [(np.ascontiguousarray(x, np.float32), np.ascontiguousarray(l, np.uint16), np.ascontiguousarray(s, np.float32), len(x))
+            for x, l, s in scans]
+    res_g = ctx.odom_run_window(host, 22, W, stamps[1:], stamps[0], imu[1:], state0, host_buffers=True,
+                                params=mm.est_params(map_update=1))
+    dpos = np.abs(res_g["poses_newest"][:, :3, 3] - res_o["poses_newest"][:, :3, 3]).max()
+    drot = np.abs(res_g["poses_newest"][:, :3, :3] - res_o["poses_newest"][:, :3, :3]).max()
+    assert dpos < 1e-4 and drot < 1e-4, (dpos, drot)
+    assert np.array_equal(res_g["stats"][:, 0], res_o["stats"][:, 0])
+    assert np.array_equal(ctx.local_map_get(0), lm.from_local[0]) and np.array_equal(ctx.local_map_get(1), lm.from_local[1])
+    ctx.local_map_reset()
+

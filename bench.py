@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--s5-map", type=int, default=2_000_000, help="S5 global map points per GPU (multi-GPU runs only)")
     ap.add_argument("--s5-queries", type=int, default=200_000)
     ap.add_argument("--window", type=int, default=3, help="sliding-window size of the headline loop (BASELINE config 3: 3)")
+    ap.add_argument("--map-update", type=int, default=1, help="1: both arms run EstimateLidarPose's local-map update (sqrt(0.5) m gate, "
+                    "MapIncrementLocal) inside the loop; 0: frozen maps")
     ap.add_argument("--reps", type=int, default=5, help="repetitions of the timed --steps loop; the median is reported")
     return ap.parse_args()
 
@@ -233,6 +235,9 @@ def state_of(synth, T, v=0.5):
     return st
 
 
+MAP_UPDATE = 1  # set from --map-update
+
+
 def cpu_window_loop(orc, synth, scans, Ts, imu, stamps, first, n, ms, mc, threads, window):
     """The oracle through the config-3 loop (oracle/window_loop.py). Extraction is timed apart from the rest: the
     reference runs them as two pipelined ROS nodes, so its throughput is that of the slower stage."""
@@ -247,8 +252,14 @@ def cpu_window_loop(orc, synth, scans, Ts, imu, stamps, first, n, ms, mc, thread
     labels = [orc.extract_scan(x, line, N_LINES, threads=threads) for (x, line, s) in sub]
     t_fe = time.perf_counter() - t0
     t0 = time.perf_counter()
+    lm = None
+    if MAP_UPDATE:  # the map the earlier frames built sits in the ring (slot 49); updates follow the trajectory
+        from oracle import map_maintenance
+        lm = map_maintenance.LocalMap(LEAF_CORNER, LEAF_SURF)
+        lm.ring[0][49] = np.ascontiguousarray(mc, np.float32)
+        lm.ring[1][49] = np.ascontiguousarray(ms, np.float32)
     res = window_loop.run(omap, sub, N_LINES, window, stamps[first + 1:first + n + 1], stamps[first], imu[first + 1:first + n + 1],
-                          state_of(synth, Ts[first]), params=prm, threads=threads, labels=labels)
+                          state_of(synth, Ts[first]), params=prm, threads=threads, labels=labels, local_map=lm)
     t_rest = time.perf_counter() - t0
     cpu_window_loop.pipelined = n / max(t_fe, t_rest)
     cpu_window_loop.stage_ms = {"extract": 1e3 * t_fe / n, "rest": 1e3 * t_rest / n}
@@ -308,6 +319,8 @@ def main():
     synth = ge.load_synth()
     n_threads = len(os.sched_getaffinity(0))
     W = a.window
+    global MAP_UPDATE
+    MAP_UPDATE = int(a.map_update)
     workload = (f"S3 (BASELINE config 3): merged VLP-16 28800 + Horizon {a.livox_pts} pts/scan with motion distortion + 200 Hz IMU, "
                 f"IMU pre-integration -> extract -> undistort -> voxel {LEAF_CORNER}/{LEAF_SURF} -> Estimate over a sliding window of {W} "
                 f"frames with IMU factors (<=5 outer x <=10 dogleg) vs {a.map_surf}+{a.map_corner}-pt local feature map")
@@ -317,9 +330,12 @@ def main():
                     "timed region; the 1.7 MB feature map is reused by design (resident map)",
               "timing": f"median of {a.reps} repetitions of the {a.steps}-step loop, each timed with CUDA events on the launching "
                         "stream (value) / wall clock around the API call (e2e), max over ranks per repetition",
-              "pipeline": "mml_odom_run_window: per scan, host IMU pre-integration + prediction, device extraction + undistortion + "
-                          "voxel filter, device association + per-frame normal equations (all window frames per launch), host IMU "
-                          "factors + (15 W)-dim dogleg step",
+              "pipeline": "mml_odom_run_window: per scan, host IMU pre-integration + prediction (the biases come from the previous "
+                          "solve), device extraction + undistortion + voxel filter, then ONE graph launch for the whole window solve "
+                          "(association of all frames, lidar terms, IMU factors and the (15 W)-dim dogleg on the device), one host "
+                          "wait per scan; the local feature maps follow the trajectory (MapIncrementLocal at the sqrt(0.5) m gate) "
+                          "in both arms" if MAP_UPDATE else "mml_odom_run_window with frozen maps",
+              "map_update": bool(MAP_UPDATE),
               "seed": 1003}
 
     if a.impl == "reference":
@@ -413,10 +429,17 @@ def main():
     def run_window(first, n, host):
         """BASELINE config 3: the IMU-initialised sliding-window loop (mml_odom_run_window)"""
         src = pinned_np if host else dev
+        # every run starts from the same maps (untimed): the local maps as uploaded, the same clouds in the ring
+        ctx.local_map_reset()
+        ctx.map_set(mm.MAP_SURF_LOCAL, ms)
+        ctx.map_set(mm.MAP_CORNER_LOCAL, mc)
+        if MAP_UPDATE:
+            ctx.local_map_seed(0, 49, mc)
+            ctx.local_map_seed(1, 49, ms)
         t0 = time.perf_counter()
         r = ctx.odom_run_window(src[first:first + n], N_LINES, W, stamps[first + 1:first + n + 1], stamps[first],
                                 imu[first + 1:first + n + 1], state_of(synth, Ts[first]), ex, host_buffers=host,
-                                leaf_corner=LEAF_CORNER, leaf_surf=LEAF_SURF)
+                                leaf_corner=LEAF_CORNER, leaf_surf=LEAF_SURF, params=mm.est_params(map_update=1 if MAP_UPDATE else 0))
         return r["total_ms"], time.perf_counter() - t0, r
 
     # pinned host copies for the e2e arm
@@ -469,10 +492,13 @@ def main():
     npts = scans[0][0].shape[0]
     imu_per_scan = int(np.mean([len(i[0]) for i in imu[1:]]))
     h2d = npts * (16 + 2 + 4)                       # the scan; IMU samples stay on the host (pre-integration is host code)
-    d2h = 3 * 16 * 8 + 8 * 8 + 8 * 4                # poses (front, newest) + state + stats + counts per scan
+    d2h = (16 * W + 16) * 8 + 16 * 4                # per scan: the window's states + statistics (mapped result block) and the counters
     evals_per_scan = float(np.mean(res_w["stats"][:, 7]))
-    d2h += int(evals_per_scan * 28 * 8 * W)         # per-frame normal-equation sums read back per evaluation
 
+    # the window runs moved the local maps along the trajectory: back to the uploaded maps for everything below
+    ctx.local_map_reset()
+    ctx.map_set(mm.MAP_SURF_LOCAL, ms)
+    ctx.map_set(mm.MAP_CORNER_LOCAL, mc)
     # ---- window 1 (the branch the shipped launch file runs): chained device-side loop, same scans
     run_native(0, a.warmup, False)
     w1_ms, _, out1 = timed_reps(lambda: run_native(a.warmup, a.steps, False), lambda o: o[0])

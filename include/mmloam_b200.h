@@ -64,6 +64,26 @@ int mml_velo_ring_time(mml_ctx* ctx, const float* xyzi, int n, int16_t* line_out
 int mml_hori_filter(mml_ctx* ctx, const uint32_t* offset_time, const float* xyz3, const uint8_t* line, int n,
                     uint8_t* keep, float* reltime_out);
 
+/* ---- F2: the message stages either side of the extractor, on the device (csrc/msgpack.cu).
+ * livox_ros_driver/CustomMsg points (CustomPoint.msg:3-9 serialised: 19 packed bytes per point) -> xyzi, line and sweep
+ * fraction behind the filter of getHoriFeatureExtract (FE.cpp:985-998: line <= used_line - 1, x >= 0.01), in message
+ * order. Outputs may be NULL (the unpacked scan also stays in the context's staging buffers); *m_out = points kept.     */
+int mml_unpack_custom_points(mml_ctx* ctx, const void* points19, int n, int used_line, float* xyzi_out,
+                             uint16_t* line_out, float* s_out, int* m_out);
+/* sensor_msgs/PointCloud2 data (point_step bytes per point, float32 fields at the given byte offsets, off_intensity < 0:
+ * none) -> xyzi with pcl::removeNaNFromPointCloud (FE.cpp:1129-1133).                                                   */
+int mml_unpack_pointcloud2(mml_ctx* ctx, const void* data, int n, int point_step, int off_x, int off_y, int off_z,
+                           int off_intensity, float* xyzi_out, int* m_out);
+/* labelled scan -> the three clouds of union_cloud.msg as pcl::PointXYZINormal records (48 B: x y z 1 | normal_x = s,
+ * normal_y = line, normal_z = label, 0 | intensity, curvature = 0, 0, 0: the bytes pcl::toROSMsg copies).
+ * full: every point inside [near_full, far_full]; corner / surf: label 1 / 2 inside [near_feat, far_feat]; a far
+ * threshold <= 0 switches that cut off (removeNearPointCloud vs removeNearFarPoints, lidars_extrinsic_cali.h:424-477;
+ * FE.cpp:916-937 Horizon, 1278-1297 VLP-16). zero_full_intensity: the VLP-16 branch zeroes the full cloud's intensity
+ * (FE.cpp:1263-1265). counts3 = points written to full / corner / surf; the outputs hold n records each.              */
+int mml_pack_union_clouds(mml_ctx* ctx, const float* xyzi, const float* s, const uint16_t* line, const uint8_t* label,
+                          int n, float near_full, float far_full, float near_feat, float far_feat,
+                          int zero_full_intensity, void* full_out, void* corner_out, void* surf_out, int* counts3);
+
 /* ---- A4: RemoveLidarDistortion, src/unionPoseEstimation.cpp:402-421. In place.      */
 int mml_undistort(mml_ctx* ctx, float* xyzi, const float* s, int n, const double* dR9, const double* dt3);
 

@@ -34,7 +34,7 @@ EXPORTS = [
     "mml_voxel_downsample", "mml_map_set", "mml_associate", "mml_accumulate", "mml_est_params_default",
     "mml_estimate", "mml_scan_to_pose", "mml_scan_to_pose_dev", "mml_frame_set", "mml_frame_associate",
     "mml_frame_accumulate", "mml_frame_associate_async", "mml_frame_associate_kind_async", "mml_frame_accumulate_async",
-    "mml_odom_run", "mml_local_map_push", "mml_local_map_push_dev", "mml_local_map_seed", "mml_local_map_get", "mml_local_map_reset", "mml_timer_start",
+    "mml_odom_run", "mml_local_map_push", "mml_local_map_push_dev", "mml_local_map_seed", "mml_unpack_custom_points", "mml_unpack_pointcloud2", "mml_pack_union_clouds", "mml_local_map_get", "mml_local_map_reset", "mml_timer_start",
     "mml_timer_stop_ms", "mml_frame_accumulate_partial_dev", "mml_stream_handle",
     "mml_imu_preintegrate", "mml_imu_factor", "mml_imu_predict", "mml_window_reset", "mml_window_size",
     "mml_window_push_frame", "mml_window_push_scan_dev", "mml_window_get_frame", "mml_estimate_window",
@@ -474,6 +474,41 @@ class Context:
                                               _p(so), _p(st), C.byref(ms)))
         return dict(poses_front=pf.reshape(n, 4, 4), poses_newest=pn.reshape(n, 4, 4), states=so, stats=st,
                     total_ms=float(ms.value))
+
+    # ---- F2: message unpack / pack on the device (csrc/msgpack.cu)
+    def unpack_custom_points(self, points19, used_line=6):
+        """CustomMsg points (19-byte records) -> (xyzi [m,4] f32, line [m] u16, s [m] f32), FE.cpp:985-998."""
+        raw = np.ascontiguousarray(points19, np.uint8).reshape(-1)
+        n = raw.size // 19
+        xyzi = np.zeros((max(n, 1), 4), np.float32)
+        line = np.zeros(max(n, 1), np.uint16)
+        s = np.zeros(max(n, 1), np.float32)
+        m = C.c_int(0)
+        self._ck(self.lib.mml_unpack_custom_points(self.h, _p(raw), n, int(used_line), _p(xyzi), _p(line), _p(s), C.byref(m)))
+        return xyzi[:m.value], line[:m.value], s[:m.value]
+
+    def unpack_pointcloud2(self, data, point_step, off_x=0, off_y=4, off_z=8, off_intensity=12):
+        raw = np.ascontiguousarray(data, np.uint8).reshape(-1)
+        n = raw.size // int(point_step)
+        xyzi = np.zeros((max(n, 1), 4), np.float32)
+        m = C.c_int(0)
+        self._ck(self.lib.mml_unpack_pointcloud2(self.h, _p(raw), n, int(point_step), int(off_x), int(off_y), int(off_z),
+                                                 int(off_intensity), _p(xyzi), C.byref(m)))
+        return xyzi[:m.value]
+
+    def pack_union_clouds(self, xyzi, s, line, label, near_full, far_full, near_feat, far_feat, zero_full_intensity=False):
+        """-> (full, corner, surf) as [m, 12] float32 views of pcl::PointXYZINormal records."""
+        xyzi = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+        n = xyzi.shape[0]
+        s = np.ascontiguousarray(s, np.float32)
+        line = np.ascontiguousarray(line, np.uint16)
+        label = np.ascontiguousarray(label, np.uint8)
+        outs = [np.zeros((max(n, 1), 12), np.float32) for _ in range(3)]
+        cnt = np.zeros(3, np.int32)
+        self._ck(self.lib.mml_pack_union_clouds(self.h, _p(xyzi), _p(s), _p(line), _p(label), n, C.c_float(near_full), C.c_float(far_full),
+                                                C.c_float(near_feat), C.c_float(far_feat), 1 if zero_full_intensity else 0,
+                                                _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(cnt)))
+        return tuple(o[:int(c)] for o, c in zip(outs, cnt))
 
     # ---- local feature map on the device (Estimator::MapIncrementLocal, EST.cpp:1585-1643)
     def local_map_push(self, corner, surf, T_wl, leaf_corner=0.4, leaf_surf=0.2):

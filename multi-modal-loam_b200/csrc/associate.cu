@@ -1139,8 +1139,7 @@ static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, floa
   MML_CUDA(ctx, M.pts.reserve(sizeof(float4) * (size_t)m));
   int* cell_start = M.cell_start.as<int>();
   MML_CHECK(count_pass(cell_start));
-  k_exclusive_scan<<<1, kScanThreads, 0, st>>>(cell_start, nullptr, (int)(M.ncell + 1), nullptr);
-  MML_LAUNCHED(ctx);
+  MML_CHECK(exclusive_scan_device(ctx, cell_start, nullptr, (int)(M.ncell + 1), nullptr));
   MML_CUDA(ctx, cudaMemsetAsync(ctx->tmp_e.p, 0, sizeof(int) * (size_t)M.ncell, st));
   k_map_scatter<<<div_up(m, 256), 256, 0, st>>>(pts_d, m, cell_of, cell_start, ctx->tmp_e.as<int>(), M.pts.as<float4>());
   MML_LAUNCHED(ctx);
@@ -1160,8 +1159,7 @@ static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, floa
     k_map_coarse_count<<<div_up(m, 256), 256, 0, st>>>(cell_of, m, M.dim[0], M.dim[1], kCoarseFactor, M.dim2[0], M.dim2[1],
                                                        cell_of2, cs2);
     MML_LAUNCHED(ctx);
-    k_exclusive_scan<<<1, kScanThreads, 0, st>>>(cs2, nullptr, (int)(ncell2 + 1), nullptr);
-    MML_LAUNCHED(ctx);
+    MML_CHECK(exclusive_scan_device(ctx, cs2, nullptr, (int)(ncell2 + 1), nullptr));
     MML_CUDA(ctx, cudaMemsetAsync(ctx->tmp_e.p, 0, sizeof(int) * (size_t)ncell2, st));
     k_map_scatter<<<div_up(m, 256), 256, 0, st>>>(pts_d, m, cell_of2, cs2, ctx->tmp_e.as<int>(), M.pts2.as<float4>());
     MML_LAUNCHED(ctx);

@@ -86,7 +86,7 @@ int mml_ctx_destroy(mml_ctx* c) {
   if (c->stream_fe) { cudaStreamSynchronize(c->stream_fe); cudaStreamDestroy(c->stream_fe); }
   mml::DevBuf* bufs[] = {&c->in_xyzi, &c->in_line, &c->in_s, &c->in_label, &c->srt_xyzi, &c->srt_src, &c->srt_line,
                          &c->chunk_tab, &c->chunk_hist, &c->line_start, &c->line_count, &c->curv, &c->refl, &c->attr,
-                         &c->sort_ind, &c->refl_ind, &c->counters, &c->tmp_a, &c->tmp_b, &c->tmp_c, &c->tmp_d, &c->tmp_e,
+                         &c->sort_ind, &c->refl_ind, &c->counters, &c->tmp_a, &c->tmp_b, &c->tmp_c, &c->tmp_d, &c->tmp_e, &c->scan_state, &c->msg_raw,
                          &c->vox_keys[0], &c->vox_keys[1], &c->vox_vals[0], &c->vox_vals[1], &c->vox_hist, &c->vox_bbox,
                          &c->corner_raw, &c->surf_raw, &c->sv_bbox, &c->q_corner, &c->q_surf, &c->f_line, &c->f_plane,
                          &c->acc_partials, &c->acc_out, &c->est_state, &c->assoc_stats, &c->frame_cnt, &c->export_buf};

@@ -99,6 +99,7 @@ struct mml_ctx {
 
   // scratch (grow-only)
   mml::DevBuf in_xyzi, in_line, in_s, in_label;          // staged scan
+  mml::DevBuf msg_raw;                                   // raw message bytes / packed output clouds (msgpack.cu)
   mml::DevBuf srt_xyzi, srt_src, srt_line;               // line-sorted scan
   mml::DevBuf chunk_tab, chunk_hist, line_start, line_count;
   mml::DevBuf curv, refl, attr, sort_ind, refl_ind;      // per-point extraction state
@@ -106,6 +107,7 @@ struct mml_ctx {
   int sel_tier = 0;                                      // shared-memory tier of the selection kernel (extract.cu)
   int* counters_alt = nullptr;                           // when set, extraction writes its counters here
   mml::DevBuf tmp_a, tmp_b, tmp_c, tmp_d, tmp_e;         // generic
+  mml::DevBuf scan_state;                                // tile status words of the look-back scan (sort.cuh)
   mml::DevBuf vox_keys[2], vox_vals[2], vox_hist, vox_bbox;
   mml::DevBuf corner_raw, surf_raw;                      // label-split clouds
   mml::DevBuf timeline;                                  // MML_TIMELINE debug stamps

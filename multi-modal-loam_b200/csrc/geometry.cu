@@ -237,10 +237,8 @@ int mml_label_split_device(mml_ctx* ctx, const float4* pts_d, const uint8_t* lab
   int* f2 = ctx->tmp_b.as<int>();
   k_label_flags<<<div_up(n, 256), 256, 0, st>>>(label_d, n, f1, f2);
   MML_LAUNCHED(ctx);
-  k_exclusive_scan<<<1, kScanThreads, 0, st>>>(f1, nullptr, n, cnt_d);
-  MML_LAUNCHED(ctx);
-  k_exclusive_scan<<<1, kScanThreads, 0, st>>>(f2, nullptr, n, cnt_d + 1);
-  MML_LAUNCHED(ctx);
+  MML_CHECK(exclusive_scan_device(ctx, f1, nullptr, n, cnt_d));
+  MML_CHECK(exclusive_scan_device(ctx, f2, nullptr, n, cnt_d + 1));
   k_label_scatter<<<div_up(n, 256), 256, 0, st>>>(pts_d, label_d, n, f1, f2, corner_d, surf_d);
   MML_LAUNCHED(ctx);
   MML_CUDA(ctx, cudaGetLastError());
@@ -279,7 +277,7 @@ int mml_voxel_device(mml_ctx* ctx, const float4* pts_d, const int* n_dev, int n_
   MML_CHECK(radix_sort_pairs(ctx, keys, vals, n_dev, n_max, hist));
   k_vox_heads<<<g, 256, 0, st>>>(keys[0], n_dev, head);
   MML_LAUNCHED(ctx);
-  k_exclusive_scan<<<1, kScanThreads, 0, st>>>(head, n_dev, 0, m_dev);
+  MML_CHECK(exclusive_scan_device(ctx, head, n_dev, n_max, m_dev));
   MML_LAUNCHED(ctx);
   k_vox_centroid<<<g, 256, 0, st>>>(pts_d, keys[0], vals[0], n_dev, head, out_d);
   MML_LAUNCHED(ctx);

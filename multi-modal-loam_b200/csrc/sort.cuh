@@ -62,6 +62,116 @@ static __global__ void __launch_bounds__(kScanThreads) k_exclusive_scan(int* __r
   if (threadIdx.x == 0 && total_out) *total_out = carry_s;
 }
 
+// ---- single-pass scan of large arrays: decoupled look-back (one read and one write per element). Tiles are
+// handed out by an atomic ticket so that a tile's predecessors are always resident or finished; a tile publishes its
+// aggregate, looks back over its predecessors' status words (AGGREGATE / INCLUSIVE, value in the low 32 bits) until
+// it meets an inclusive prefix, then publishes its own inclusive prefix.
+constexpr int kLbThreads = 256;
+constexpr int kLbItems = 16;
+constexpr int kLbTile = kLbThreads * kLbItems;  // 4096 elements per tile
+constexpr unsigned long long kLbAggregate = 1ull << 32, kLbInclusive = 2ull << 32;
+
+static __global__ void __launch_bounds__(kLbThreads) k_scan_lookback(int* __restrict__ data, const int* __restrict__ n_dev, int n_host,
+                                                              int* __restrict__ total_out, unsigned long long* __restrict__ status,
+                                                              unsigned* __restrict__ ticket) {
+  __shared__ int s_tile, s_prefix;
+  __shared__ int warp_sum[kLbThreads / 32];
+  const int n = n_dev ? *n_dev : n_host;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  const int base = tile * kLbTile;
+  if (base >= n) return;
+  // blocked arrangement: thread t owns items [t * kLbItems, (t + 1) * kLbItems) of the tile
+  int v[kLbItems];
+  int tsum = 0;
+  const int i0 = base + threadIdx.x * kLbItems;
+  if (i0 + kLbItems <= n) {
+    const int4* p = reinterpret_cast<const int4*>(data + i0);
+#pragma unroll
+    for (int k = 0; k < kLbItems / 4; k++) {
+      const int4 q = p[k];
+      v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kLbItems; k++) v[k] = (i0 + k < n) ? data[i0 + k] : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < kLbItems; k++) tsum += v[k];
+  int x = tsum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) warp_sum[warp] = x;
+  __syncthreads();
+  int woff = 0, tile_sum = 0;
+#pragma unroll
+  for (int w = 0; w < kLbThreads / 32; w++) {
+    if (w < warp) woff += warp_sum[w];
+    tile_sum += warp_sum[w];
+  }
+  if (threadIdx.x == 0) {
+    int prefix = 0;
+    if (tile == 0) {
+      atomicExch(&status[0], kLbInclusive | (unsigned)tile_sum);
+    } else {
+      atomicExch(&status[tile], kLbAggregate | (unsigned)tile_sum);
+      for (int t = tile - 1;; t--) {
+        unsigned long long st;
+        do { st = atomicAdd(&status[t], 0ull); } while ((st >> 32) == 0);
+        prefix += (int)(unsigned)st;
+        if ((st >> 32) == 2) break;
+      }
+      atomicExch(&status[tile], kLbInclusive | (unsigned)(prefix + tile_sum));
+    }
+    s_prefix = prefix;
+    if (total_out && base + kLbTile >= n) *total_out = prefix + tile_sum;
+  }
+  __syncthreads();
+  int run = s_prefix + woff + (x - tsum);
+  if (i0 + kLbItems <= n) {
+    int4* p = reinterpret_cast<int4*>(data + i0);
+#pragma unroll
+    for (int k = 0; k < kLbItems / 4; k++) {
+      int4 q;
+      q.x = run; run += v[4 * k];
+      q.y = run; run += v[4 * k + 1];
+      q.z = run; run += v[4 * k + 2];
+      q.w = run; run += v[4 * k + 3];
+      p[k] = q;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kLbItems; k++) {
+      if (i0 + k < n) data[i0 + k] = run;
+      run += v[k];
+    }
+  }
+}
+
+// data[i] <- sum_{k<i} data[k] for i < n (n = *n_dev when given, at most n_max), *total_out (may be null) <- the sum.
+// Small arrays: one CTA, one launch (latency). Large arrays: the look-back scan over div_up(n_max, 4096) tiles.
+static inline int exclusive_scan_device(mml_ctx* ctx, int* data, const int* n_dev, int n_max, int* total_out) {
+  if (n_max <= 4 * kScanThreads * kScanItems) {
+    k_exclusive_scan<<<1, kScanThreads, 0, ctx->stream>>>(data, n_dev, n_dev ? 0 : n_max, total_out);
+    MML_LAUNCHED(ctx);
+    return MML_OK;
+  }
+  const int tiles = div_up(n_max, kLbTile);
+  MML_CUDA(ctx, ctx->scan_state.reserve(sizeof(unsigned long long) * (size_t)(tiles + 2)));
+  MML_CUDA(ctx, cudaMemsetAsync(ctx->scan_state.p, 0, sizeof(unsigned long long) * (size_t)(tiles + 2), ctx->stream));
+  unsigned long long* status = ctx->scan_state.as<unsigned long long>() + 1;
+  if (total_out && n_dev) MML_CUDA(ctx, cudaMemsetAsync(total_out, 0, sizeof(int), ctx->stream));  // n may be 0
+  k_scan_lookback<<<tiles, kLbThreads, 0, ctx->stream>>>(data, n_dev, n_dev ? 0 : n_max, total_out, status,
+                                                       reinterpret_cast<unsigned*>(ctx->scan_state.p));
+  MML_LAUNCHED(ctx);
+  return MML_OK;
+}
+
 constexpr int kRadixTile = 1024;  // elements per CTA (4 rounds of 256)
 
 static __global__ void __launch_bounds__(256) k_radix_hist(const unsigned* __restrict__ keys, const int* __restrict__ n_dev,
@@ -133,8 +243,7 @@ static inline int radix_sort_pairs(mml_ctx* ctx, unsigned* keys[2], unsigned* va
     const int a = pass & 1, b = a ^ 1;
     k_radix_hist<<<nblocks, 256, 0, ctx->stream>>>(keys[a], n_dev, shift, nblocks, hist);
     MML_LAUNCHED(ctx);
-    k_exclusive_scan<<<1, kScanThreads, 0, ctx->stream>>>(hist, nullptr, 256 * nblocks, nullptr);
-    MML_LAUNCHED(ctx);
+    MML_CHECK(exclusive_scan_device(ctx, hist, nullptr, 256 * nblocks, nullptr));
     k_radix_scatter<<<nblocks, 256, 0, ctx->stream>>>(keys[a], vals[a], keys[b], vals[b], n_dev, shift, nblocks, hist);
     MML_LAUNCHED(ctx);
   }

@@ -710,3 +710,34 @@ def test_voxel_downsample_drops_non_finite_points(ctx, orc, scene):
     assert got.shape == ref.shape and np.array_equal(got, ref)
     assert np.isfinite(got).all()
 
+
+
+def test_message_unpack_and_pack_match_oracle(ctx, orc, synth, scene):
+    """F2: CustomMsg / PointCloud2 unpack and the union_cloud clouds, device against oracle/msgs.py (bit for bit)."""
+    from oracle import msgs
+    hx, hl, hs = scene["hori"]
+    off, xyz, refl, line = synth.horizon_custom_msg(hx, hl, hs)
+    line = line.copy(); xyz = xyz.copy()
+    line[::97] = 7                       # lines beyond Used_Line are dropped
+    xyz[5::211, 0] = 0.005               # and points closer than x = 0.01
+    raw = msgs.pack_custom_points(off, xyz, refl, line, tag=16)
+    ox, ol, os_ = msgs.unpack_custom_points(raw, 6)
+    gx, gl, gs = ctx.unpack_custom_points(raw, 6)
+    assert gx.shape == ox.shape and 0 < gx.shape[0] < len(off)
+    assert np.array_equal(gx, ox) and np.array_equal(gl, ol) and np.array_equal(gs, os_)
+    # PointCloud2 with a 32-byte point (x y z pad intensity ring time pad), NaN rows removed
+    vx, vr, _ = scene["vlp"]
+    pc = np.zeros((len(vx), 8), np.float32)
+    pc[:, 0:3] = vx[:, :3]; pc[:, 4] = vx[:, 3]; pc[:, 5] = vr
+    pc[3, 1] = np.nan; pc[1000, 2] = np.inf
+    rawpc = pc.view(np.uint8).reshape(-1)
+    o2 = msgs.unpack_pointcloud2(rawpc, 32, 0, 4, 8, 16)
+    g2 = ctx.unpack_pointcloud2(rawpc, 32, 0, 4, 8, 16)
+    assert g2.shape == o2.shape == (len(vx) - 2, 4) and np.array_equal(g2, o2)
+    # union_cloud clouds: Horizon form (near/far on the full cloud, near only on the feature clouds) and VLP-16 form
+    label = orc.extract_scan(hx, hl, 6)
+    for args in ((3.0, 9.0, 3.0, 0.0, False), (2.5, 8.0, 2.5, 8.0, True)):
+        of, oc, osf = msgs.pack_union_clouds(hx, hs, hl, label, *args)
+        gf, gc, gsf = ctx.pack_union_clouds(hx, hs, hl, label, *args)
+        assert 0 < oc.shape[0] and 0 < osf.shape[0] < of.shape[0] < len(hx)
+        assert np.array_equal(gf, of) and np.array_equal(gc, oc) and np.array_equal(gsf, osf)

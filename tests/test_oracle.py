@@ -348,3 +348,22 @@ def test_golden_fixtures(orc):
     assert nf == int(meta["n_plane"]) and np.array_equal(pf[:, 10], g["plane_valid"])
     P, q, st = m.estimate(g["corner_ds"], g["surf_ds"], np.eye(4), g["P0"], g["q0"])
     assert np.abs(P - g["P_est"]).max() < 1e-9 and np.abs(q - g["q_est"]).max() < 1e-9
+
+
+def test_message_oracle_round_trip(synth):
+    """oracle/msgs.py: CustomPoint records serialise to 19 bytes, the filter keeps message order, the near / far cuts
+    are float32 squared ranges."""
+    from oracle import msgs
+    T = synth.make_T(synth.rot_z(0.1), np.array([-3.0, -1.0, 0.2]))
+    hx, hl, hs = synth.horizon_scan(T, 2400, seed=5)
+    off, xyz, refl, line = synth.horizon_custom_msg(hx, hl, hs)
+    raw = msgs.pack_custom_points(off, xyz, refl, line)
+    assert raw.size == 19 * len(off)
+    x, l, s = msgs.unpack_custom_points(raw, 6)
+    keep = (line <= 5) & (xyz[:, 0] >= 0.01)
+    assert np.array_equal(x[:, :3], xyz[keep]) and np.array_equal(l, line[keep].astype(np.uint16))
+    assert np.all(np.diff(s) >= 0) and abs(float(s[-1]) - 1.0) < 1e-6
+    full, corner, surf = msgs.pack_union_clouds(hx, hs, hl, np.where(np.arange(len(hx)) % 7 == 0, 1, 2), 3.0, 9.0, 3.0, 0.0)
+    r2 = (full[:, 0] * full[:, 0] + full[:, 1] * full[:, 1]) + full[:, 2] * full[:, 2]
+    assert np.all(r2 >= np.float32(9.0)) and np.all(r2 <= np.float32(81.0)) and np.all(full[:, 3] == 1.0)
+    assert np.all(corner[:, 6] == 1) and np.all(surf[:, 6] == 2)

@@ -56,8 +56,8 @@ def parse():
     ap.add_argument("--no-s4", action="store_true")
     ap.add_argument("--no-s2", action="store_true")
     ap.add_argument("--s2-pts", type=int, default=240_000)
-    ap.add_argument("--s5-map", type=int, default=2_000_000, help="S5 global map points per GPU (multi-GPU runs only)")
-    ap.add_argument("--s5-queries", type=int, default=200_000)
+    ap.add_argument("--s5-map", type=int, default=8_000_000, help="S5 global map points in total (multi-GPU runs only; BASELINE config 5)")
+    ap.add_argument("--s5-queries", type=int, default=1_000_000)
     ap.add_argument("--window", type=int, default=3, help="sliding-window size of the headline loop (BASELINE config 3: 3)")
     ap.add_argument("--map-update", type=int, default=1, help="1: both arms run EstimateLidarPose's local-map update (sqrt(0.5) m gate, "
                     "MapIncrementLocal) inside the loop; 0: frozen maps")
@@ -268,46 +268,66 @@ def cpu_window_loop(orc, synth, scans, Ts, imu, stamps, first, n, ms, mc, thread
 
 # ------------------------------------------------------------------------------------------
 def run_s5_sharded(a, mm, synth, local_rank, rank, world):
-    """SURVEY §8 e / S5: one Estimate against a cube-sharded global map. Every rank holds the points of its
-    cubes only, the query set is replicated, and each evaluation all-reduces 28 doubles over NCCL."""
+    """SURVEY 8 e / S5 (BASELINE config 5): one Estimate against the 8 M-point global map sharded by 50 m cube over the
+    ranks, 1 M replicated queries, STRONG scaling (the map and the queries are the same at every GPU count). The
+    partial sums are exchanged through peer memory from inside the kernels (mml_estimate_sharded); rank 0 also solves
+    the same problem unsharded on its own GPU: the poses must agree."""
     import torch
     import torch.distributed as dist
     from mmloam_b200 import sharded
 
-    n_surf, n_corner = a.s5_map * world, a.s5_map * world // 20  # the map grows with the GPU count (weak scaling)
+    n_surf, n_corner = a.s5_map, a.s5_map // 20
     ms, mc = synth.tiled_feature_map(n_surf, n_corner, tiles=(4, 4, 1), seed=1005)
-    owner = sharded.cube_owner(sharded.cube_index(ms), world)
+    owner = sharded.cube_owner_union([ms, mc], world)
     ms_r, _ = sharded.shard_points(ms, rank, world, owner=owner)
     mc_r, _ = sharded.shard_points(mc, rank, world, owner=owner)
-    ctx5 = mm.Context(local_rank)
-    ctx5.map_set(mm.MAP_SURF_GLOBAL, ms_r)
-    ctx5.map_set(mm.MAP_CORNER_GLOBAL, mc_r)
     T_true = synth.make_T(np.eye(3), np.zeros(3))
     qs = synth.queries_from_map(ms, a.s5_queries, T_true, seed=1005)
     qc = synth.queries_from_map(mc, max(a.s5_queries // 20, 64), T_true, seed=1006)
-    ctx5.frame_set(qc, qs)
     T0 = synth.s1_offset_pose()
-    x0 = np.concatenate([T0[:3, 3], synth.R_to_rotvec(T0[:3, :3])])
-    backend = sharded.GpuShardBackend(ctx5, local_rank)
-    est = sharded.ShardedEstimator(backend, sharded.nccl_allreduce_on(ctx5))
-    est.estimate(x0)  # warm-up (graph-free path: kernels + NCCL)
+    P0 = T0[:3, 3].copy()
+    q0 = R_to_quat(T0[:3, :3])
+    empty = np.zeros((0, 4), np.float32)
+    # unsharded reference (rank 0, before the shard contexts exist): the same map on ONE GPU
+    ref = None
+    if rank == 0:
+        full = mm.Context(local_rank)
+        full.map_set(mm.MAP_SURF_GLOBAL, ms); full.map_set(mm.MAP_CORNER_GLOBAL, mc)
+        full.map_set(mm.MAP_SURF_LOCAL, empty); full.map_set(mm.MAP_CORNER_LOCAL, empty)
+        full.estimate(qc, qs, np.eye(4), P0, q0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        Pf, qf, stf = full.estimate(qc, qs, np.eye(4), P0, q0)
+        ref = (Pf, qf, stf, 1e3 * (time.perf_counter() - t0))
+        full.close()
+    ctx5 = mm.Context(local_rank)
+    ctx5.map_set(mm.MAP_SURF_GLOBAL, ms_r); ctx5.map_set(mm.MAP_CORNER_GLOBAL, mc_r)
+    ctx5.map_set(mm.MAP_SURF_LOCAL, empty); ctx5.map_set(mm.MAP_CORNER_LOCAL, empty)
+    sharded.connect_ranks(ctx5, rank, world)
+    ctx5.estimate_sharded(qc, qs, np.eye(4), P0, q0)  # warm-up: buffers, graph
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    x, stats = est.estimate(x0)
-    torch.cuda.synchronize()
+    P, q, st = ctx5.estimate_sharded(qc, qs, np.eye(4), P0, q0)
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local_rank}")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    xs = [torch.zeros(6, dtype=torch.float64, device=f"cuda:{local_rank}") for _ in range(world)]
-    dist.all_gather(xs, torch.from_numpy(x).to(f"cuda:{local_rank}"))
+    mine = torch.from_numpy(np.concatenate([P, q])).to(f"cuda:{local_rank}")
+    xs = [torch.zeros(7, dtype=torch.float64, device=f"cuda:{local_rank}") for _ in range(world)]
+    dist.all_gather(xs, mine)
     same = all(bool(torch.equal(xs[0], v)) for v in xs)
+    out = {"map_points": int(ms.shape[0] + mc.shape[0]), "points_this_rank": int(ms_r.shape[0] + mc_r.shape[0]),
+           "queries": int(qs.shape[0] + qc.shape[0]), "scaling": "strong", "estimate_ms": 1e3 * float(t.item()),
+           "outer_iters": int(st[0]), "dogleg_iters": int(st[1]), "features": int(st[2] + st[3]),
+           "pose_identical_on_all_ranks": same, "pos_err_m": float(np.abs(P).max()),
+           "collective": "28 doubles per evaluation (+18 per association) stored into every rank's exchange buffer over NVLink by the "
+                         "evaluation kernel's last CTA, summed in rank order on the device; one host wait per outer iteration"}
+    if ref is not None:
+        Pf, qf, stf, ms_1 = ref
+        out["unsharded_1gpu"] = {"estimate_ms": ms_1, "max_dpos_m": float(np.abs(P - Pf).max()), "max_dquat": float(np.abs(q - qf).max()),
+                                 "outer_iters": int(stf[0]), "features": int(stf[2] + stf[3])}
     ctx5.close()
-    return {"map_points": int(ms.shape[0] + mc.shape[0]), "points_this_rank": int(ms_r.shape[0] + mc_r.shape[0]),
-            "queries": int(qs.shape[0] + qc.shape[0]), "estimate_ms": 1e3 * float(t.item()),
-            "allreduces_per_estimate": est.n_allreduce // 2, "outer_iters": stats["outer"], "features": stats["n_line"] + stats["n_plane"],
-            "pose_identical_on_all_ranks": same, "pos_err_m": float(np.abs(x[:3]).max()), "rot_err_rad": float(np.abs(x[3:]).max()),
-            "collective": "NCCL all-reduce of 28 doubles per evaluation (+12 per association) on the context's stream"}
+    return out
 
 
 # ------------------------------------------------------------------------------------------

@@ -257,6 +257,26 @@ int mml_odom_run_window(mml_ctx* ctx, const void* const* xyzi, const void* const
                         float leaf_surf, const mml_est_params* prm, double* poses_front, double* poses_newest,
                         double* states_out, double* stats_out, float* total_ms);
 
+/* ---- (e) multi-GPU: the global map sharded by 50 m cube over up to 8 GPUs (MM.cpp:583-605 is the shard boundary; replaces
+ * the `_allreduce(ncclComm_t)` variant SURVEY.md 8 b sketches). Rank r uploads only its cubes (mml_map_set on the global
+ * kinds); queries are replicated; each query is matched on exactly one rank; the only exchange - 28 doubles per
+ * evaluation, 18 per association - goes through PEER MEMORY from inside the kernels: the last CTA of an evaluation stores
+ * its sums into every rank's exchange buffer over NVLink, publishes a sequence word, waits for the others and sums in
+ * rank order, then takes the dogleg step on the device. No NCCL or host call between two evaluations.
+ *   mml_shard_init         allocate this rank's exchange buffer; ipc_handle64_out (may be NULL) receives its 64-byte
+ *                          cudaIpcMemHandle for the caller to all-gather (MPI, torch.distributed, a file ...)
+ *   mml_shard_connect_ipc  handles of all ranks in rank order (world x 64 bytes), one process per GPU
+ *   mml_shard_connect_ptrs exchange-buffer pointers of all ranks when they live in one process (mml_shard_local_ptr),
+ *                          devices[r] = CUDA device of rank r (peer access is enabled here)
+ *   mml_estimate_sharded   collective: same queries and start pose on every rank; every rank returns the same pose.  */
+int mml_shard_init(mml_ctx* ctx, int rank, int world, void* ipc_handle64_out);
+int mml_shard_local_ptr(mml_ctx* ctx, void** buf_out);
+int mml_shard_connect_ipc(mml_ctx* ctx, const void* handles);
+int mml_shard_connect_ptrs(mml_ctx* ctx, void* const* bufs, const int* devices);
+int mml_shard_close(mml_ctx* ctx);
+int mml_estimate_sharded(mml_ctx* ctx, const float* corner_xyzi, int n_corner, const float* surf_xyzi, int n_surf,
+                         const double* exTlb16, double* P3, double* q_wxyz4, const mml_est_params* prm, double* stats);
+
 /* ---- device-resident building blocks used by bench.py's roofline sweep (S4):
  * queries and maps stay in HBM; one call = one association or one evaluation.          */
 int mml_frame_set(mml_ctx* ctx, const float* corner_xyzi, int n_corner, const float* surf_xyzi, int n_surf);

@@ -38,7 +38,8 @@ EXPORTS = [
     "mml_timer_stop_ms", "mml_frame_accumulate_partial_dev", "mml_stream_handle",
     "mml_imu_preintegrate", "mml_imu_factor", "mml_imu_predict", "mml_window_reset", "mml_window_size",
     "mml_window_push_frame", "mml_window_push_scan_dev", "mml_window_get_frame", "mml_estimate_window",
-    "mml_odom_run_window",
+    "mml_odom_run_window", "mml_shard_init", "mml_shard_local_ptr", "mml_shard_connect_ipc", "mml_shard_connect_ptrs",
+    "mml_shard_close", "mml_estimate_sharded",
 ]
 
 
@@ -341,6 +342,45 @@ class Context:
         prm = params if params is not None else est_params()
         self._ck(self.lib.mml_estimate(self.h, _p(corner), corner.shape[0], _p(surf), surf.shape[0], _p(ex), _p(P), _p(q),
                                        C.byref(prm), _p(stats)))
+        return P, q, stats
+
+    # ---- (e) cube-sharded global map over several GPUs: exchange through peer memory inside the kernels
+    def shard_init(self, rank, world):
+        """Allocate this rank's exchange buffer; returns its 64-byte cudaIpcMemHandle (bytes) for an all-gather."""
+        h = (C.c_ubyte * 64)()
+        self._ck(self.lib.mml_shard_init(self.h, int(rank), int(world), h))
+        return bytes(h)
+
+    def shard_local_ptr(self):
+        p = C.c_void_p()
+        self._ck(self.lib.mml_shard_local_ptr(self.h, C.byref(p)))
+        return p.value
+
+    def shard_connect_ipc(self, handles):
+        """handles: list of the ranks' 64-byte handles in rank order (one process per GPU)."""
+        raw = b"".join(handles)
+        self._ck(self.lib.mml_shard_connect_ipc(self.h, raw))
+
+    def shard_connect_ptrs(self, ptrs, devices=None):
+        """ptrs: exchange-buffer pointers of all ranks living in this process (shard_local_ptr of each context)."""
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        dev = (C.c_int * len(ptrs))(*devices) if devices is not None else None
+        self._ck(self.lib.mml_shard_connect_ptrs(self.h, arr, dev))
+
+    def shard_close(self):
+        self._ck(self.lib.mml_shard_close(self.h))
+
+    def estimate_sharded(self, corner, surf, exTlb, P, q_wxyz, params=None):
+        """mml_estimate_sharded: a collective over the ranks of shard_init (same queries and start pose on each)."""
+        corner = _f32(corner).reshape(-1, 4)
+        surf = _f32(surf).reshape(-1, 4)
+        ex = _f64(exTlb).reshape(16)
+        P = _f64(P).copy()
+        q = _f64(q_wxyz).copy()
+        stats = np.zeros(16)
+        prm = params if params is not None else est_params()
+        self._ck(self.lib.mml_estimate_sharded(self.h, _p(corner), corner.shape[0], _p(surf), surf.shape[0], _p(ex), _p(P), _p(q),
+                                               C.byref(prm), _p(stats)))
         return P, q, stats
 
     # ---- whole per-scan path

@@ -39,6 +39,7 @@ struct AccArgs {
   unsigned* ticket;
   double* out28;
   EstState* st;          // optional: evaluation point and parameters come from the solver state
+  ShardDev* shard;       // optional: sum the 28 sums over the ranks of a cube-sharded map before the dogleg update
 };
 
 __host__ __device__ __noinline__ void dogleg_update(EstState& S, const double* out28);
@@ -138,6 +139,11 @@ __global__ void __launch_bounds__(256, MML_ACC_MINB) k_accumulate(AccArgs A) {
     sred[0][threadIdx.x] = v;
   }
   __syncthreads();
+  if (A.shard && threadIdx.x < 32) {  // this rank's shard -> all ranks, through peer memory
+    shard_allreduce(A.shard, sred[0], 28, sred[1]);
+    if (threadIdx.x < 28) { sred[0][threadIdx.x] = sred[1][threadIdx.x]; A.out28[threadIdx.x] = sred[1][threadIdx.x]; }
+    __syncwarp();
+  }
   if (threadIdx.x == 0) {
     *A.ticket = 0;
     if (S) dogleg_update(*S, sred[0]);
@@ -409,8 +415,26 @@ __global__ void k_est_begin_outer(EstState* S) {
   est_begin_assoc(S);
   est_begin_solve(S);
 }
-__global__ void k_est_end_outer(EstState* S, const double* assoc_stats) {
-  if (threadIdx.x != 0 || S->done_outer) return;
+__global__ void k_est_end_outer(EstState* S, const double* assoc_stats, ShardDev* shard) {
+  if (S->done_outer) return;
+  if (shard) {
+    // association statistics of all shards: feature counts and the plane normals' moments add up over the ranks
+    __shared__ double loc[20], tot[20], blk[20];
+    const int* ints = reinterpret_cast<const int*>(assoc_stats + 16);
+    if (threadIdx.x < 16) loc[threadIdx.x] = assoc_stats[threadIdx.x];
+    if (threadIdx.x == 16) loc[16] = (double)ints[0];
+    if (threadIdx.x == 17) loc[17] = (double)ints[1];
+    __syncwarp();
+    shard_allreduce(shard, loc, 18, tot);
+    if (threadIdx.x == 0) {
+      for (int k = 0; k < 16; k++) blk[k] = tot[k];
+      int* bi = reinterpret_cast<int*>(blk + 16);
+      bi[0] = (int)(tot[16] + 0.5); bi[1] = (int)(tot[17] + 0.5);
+      est_end(S, blk);
+    }
+    return;
+  }
+  if (threadIdx.x != 0) return;
   est_end(S, assoc_stats);
 }
 
@@ -626,6 +650,7 @@ int mml_accumulate_launch(mml_ctx* ctx, const double* x6, const double* T_bl16, 
   A.out28 = ctx->acc_out.as<double>();
   A.ticket = reinterpret_cast<unsigned*>(ctx->acc_out.as<double>() + 30);
   A.st = st_dev;
+  A.shard = (st_dev && ctx->shard_active) ? ctx->shard_dev.as<ShardDev>() : nullptr;
   if (wide_line_dev || wide_plane_dev) k_accumulate<true><<<grid, 256, 0, ctx->stream>>>(A);
   else k_accumulate<false><<<grid, 256, 0, ctx->stream>>>(A);
   MML_LAUNCHED(ctx);
@@ -750,9 +775,12 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
   // reports convergence (EST.cpp:1448): a well-predicted scan costs one graph and one short synchronisation
   // and no idle no-op launches for iterations 2-5.
   static const int solve_env = getenv("MML_SOLVE_MODE") ? atoi(getenv("MML_SOLVE_MODE")) : -1;  // 0 = launch per evaluation
-  const bool small = solve_env >= 0 ? solve_env != 0 : ctx->solve_small != 0;
+  // a cube-sharded map is solved with a launch per evaluation: the exchange sits in the last CTA of k_accumulate
+  const bool small = ctx->shard_active ? false : (solve_env >= 0 ? solve_env != 0 : ctx->solve_small != 0);
   mix(small ? 7 : 3);
+  mix(ctx->shard_active ? (long long)(size_t)ctx->shard_dev.p : 0);
   if (!ctx->est_graph || ctx->est_graph_key != key) {
+    std::lock_guard<std::recursive_mutex> capture_lock(capture_mutex());
     if (ctx->est_graph) { cudaGraphExecDestroy(ctx->est_graph); ctx->est_graph = nullptr; }
     cudaGraph_t graph = nullptr;
     const long long launches_before = ctx->launches;
@@ -768,7 +796,7 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
     } else {
       for (int k = 0; k <= prm->max_inner && rc == MML_OK; k++)
         rc = mml_accumulate_launch(ctx, nullptr, nullptr, 0, 0, 0, S, cnt_dev, cap_corner, cap_surf, nullptr, nullptr);
-      k_est_end_outer<<<1, 32, 0, st>>>(S, ctx->assoc_stats.as<double>());
+      k_est_end_outer<<<1, 32, 0, st>>>(S, ctx->assoc_stats.as<double>(), ctx->shard_active ? ctx->shard_dev.as<ShardDev>() : nullptr);
       MML_LAUNCHED(ctx);
     }
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
@@ -839,6 +867,7 @@ int mml_chain_solve_launch(mml_ctx* ctx, const int* cnt_dev, int cap, mml::OdomD
   mix((long long)(size_t)od); mix((long long)(size_t)out.poses); mix((long long)(size_t)out.stats); mix((long long)(size_t)out.counts);
   mix((long long)(size_t)wait_ev);
   if (!ctx->chain_graph || ctx->chain_graph_key != key) {
+    std::lock_guard<std::recursive_mutex> capture_lock(capture_mutex());
     if (ctx->chain_graph) { cudaGraphExecDestroy(ctx->chain_graph); ctx->chain_graph = nullptr; }
     const long long launches_before = ctx->launches;
     cudaGraph_t graph = nullptr;

@@ -1,6 +1,7 @@
 // C-ABI of libmmloam_b200.so (include/mmloam_b200.h): host-buffer entry points stage through
 // pinned memory, run the device pipeline on the context's stream and copy results back.
 #include "common.cuh"
+#include "eststate.cuh"
 #include <math.h>
 #include <stdlib.h>
 
@@ -99,6 +100,7 @@ int mml_ctx_destroy(mml_ctx* c) {
     c->maps[k].cell_start2.release();
   }
   c->grid_table.release();
+  mml_shard_close(c);
   c->grid_table_pin.release();
   c->pin_in.release();
   c->pin_out.release();
@@ -455,10 +457,117 @@ int mml_accumulate(mml_ctx* c, const double* line_feat, int n_line, const double
   return MML_OK;
 }
 
+// ---- cube-sharded global map over several GPUs (SURVEY.md 8 e): exchange through peer memory (eststate.cuh) ----------
+static int shard_upload_desc(mml_ctx* c, double* const* peers) {
+  mml::ShardDev h;
+  memset(&h, 0, sizeof(h));
+  h.rank = c->shard_rank; h.world = c->shard_world;
+  for (int r = 0; r < c->shard_world; r++) h.peer[r] = peers[r];
+  MML_CUDA(c, c->shard_dev.reserve(sizeof(mml::ShardDev)));
+  MML_CUDA(c, cudaMemcpy(c->shard_dev.p, &h, sizeof(h), cudaMemcpyHostToDevice));
+  return MML_OK;
+}
+
+int mml_shard_init(mml_ctx* c, int rank, int world, void* ipc_handle64_out) {
+  if (!c || world < 1 || world > mml::kShardMaxWorld || rank < 0 || rank >= world) return MML_ERR_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaSetDevice(c->device);
+  MML_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->shard_rank = rank; c->shard_world = world;
+  MML_CUDA(c, c->shard_buf.reserve(sizeof(double) * mml::kShardBufDoubles));
+  MML_CUDA(c, cudaMemset(c->shard_buf.p, 0, sizeof(double) * mml::kShardBufDoubles));
+  if (ipc_handle64_out) {
+    cudaIpcMemHandle_t hd;
+    MML_CUDA(c, cudaIpcGetMemHandle(&hd, c->shard_buf.p));
+    memcpy(ipc_handle64_out, &hd, 64);
+  }
+  double* peers[mml::kShardMaxWorld] = {};
+  peers[rank] = c->shard_buf.as<double>();
+  if (world == 1) return shard_upload_desc(c, peers);
+  return MML_OK;
+}
+
+int mml_shard_local_ptr(mml_ctx* c, void** out) {
+  if (!c || !out || !c->shard_buf.p) return MML_ERR_INVALID;
+  *out = c->shard_buf.p;
+  return MML_OK;
+}
+
+// every rank's handle (world x 64 bytes, rank order): other processes' buffers are opened for peer access
+int mml_shard_connect_ipc(mml_ctx* c, const void* handles) {
+  if (!c || !handles || !c->shard_buf.p) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  double* peers[mml::kShardMaxWorld] = {};
+  for (int r = 0; r < c->shard_world; r++) {
+    if (r == c->shard_rank) { peers[r] = c->shard_buf.as<double>(); continue; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, static_cast<const char*>(handles) + 64 * (size_t)r, 64);
+    void* p = nullptr;
+    MML_CUDA(c, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    c->shard_peer_opened[r] = p;
+    peers[r] = static_cast<double*>(p);
+  }
+  return shard_upload_desc(c, peers);
+}
+
+// the same for ranks that live in ONE process (several contexts): plain device pointers, peer access enabled here
+int mml_shard_connect_ptrs(mml_ctx* c, void* const* bufs, const int* devices) {
+  if (!c || !bufs || !c->shard_buf.p) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  double* peers[mml::kShardMaxWorld] = {};
+  for (int r = 0; r < c->shard_world; r++) {
+    if (!bufs[r]) return MML_ERR_INVALID;
+    peers[r] = static_cast<double*>(bufs[r]);
+    if (devices && devices[r] != c->device) {
+      const cudaError_t e = cudaDeviceEnablePeerAccess(devices[r], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); MML_CUDA(c, e); }
+      cudaGetLastError();
+    }
+  }
+  return shard_upload_desc(c, peers);
+}
+
+int mml_shard_close(mml_ctx* c) {
+  if (!c) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (int r = 0; r < mml::kShardMaxWorld; r++)
+    if (c->shard_peer_opened[r]) { cudaIpcCloseMemHandle(c->shard_peer_opened[r]); c->shard_peer_opened[r] = nullptr; }
+  c->shard_dev.release();
+  c->shard_buf.release();
+  c->shard_world = 1; c->shard_rank = 0;
+  return MML_OK;
+}
+
+int mml_estimate(mml_ctx* c, const float* corner_xyzi, int n_corner, const float* surf_xyzi, int n_surf,
+                 const double* exTlb16, double* P3, double* q_wxyz4, const mml_est_params* prm, double* stats);
+
+// Estimator::Estimate (window size 1) against a global map sharded by 50 m cube over the ranks of mml_shard_init:
+// a collective - every rank calls it with the same queries and the same start pose; each rank matches the queries
+// that fall into the cubes it holds, the partial sums are exchanged through peer memory inside the kernels, and every
+// rank returns the same pose (bit for bit). One host wait per outer iteration.
+int mml_estimate_sharded(mml_ctx* c, const float* corner_xyzi, int n_corner, const float* surf_xyzi, int n_surf,
+                         const double* exTlb16, double* P3, double* q_wxyz4, const mml_est_params* prm, double* stats) {
+  if (!c || !exTlb16 || !P3 || !q_wxyz4) return MML_ERR_INVALID;
+  if (!c->shard_dev.p) return mml_fail(c, MML_ERR_STATE, "mml_estimate_sharded: mml_shard_init / mml_shard_connect_* first");
+  // a query whose cube lives on another rank must find NO map here: the local-map fallback (EST.cpp:283, 702) would
+  // match it on every rank and the exchange would count it world times
+  if (c->maps[MML_MAP_CORNER_LOCAL].valid || c->maps[MML_MAP_SURF_LOCAL].valid)
+    return mml_fail(c, MML_ERR_STATE, "mml_estimate_sharded: local maps must not be set on a shard context");
+  c->shard_active = true;
+  const int rc = mml_estimate(c, corner_xyzi, n_corner, surf_xyzi, n_surf, exTlb16, P3, q_wxyz4, prm, stats);
+  c->shard_active = false;
+  if (rc != MML_OK) return rc;
+  mml::ShardDev h;
+  MML_CUDA(c, cudaMemcpy(&h, c->shard_dev.p, sizeof(h), cudaMemcpyDeviceToHost));
+  if (h.pad) return mml_fail(c, MML_ERR_CUDA, "mml_estimate_sharded: a peer rank did not arrive (exchange timed out)");
+  return MML_OK;
+}
+
 int mml_estimate(mml_ctx* c, const float* corner_xyzi, int n_corner, const float* surf_xyzi, int n_surf,
                  const double* exTlb16, double* P3, double* q_wxyz4, const mml_est_params* prm, double* stats) {
   if (!c || !exTlb16 || !P3 || !q_wxyz4) return MML_ERR_INVALID;
-  MML_CHECK(require_map(c, "mml_estimate"));
+  if (!c->shard_active) MML_CHECK(require_map(c, "mml_estimate"));  // a shard may hold no cube at all
   mml_est_params def;
   mml_est_params_default(&def);
   if (!prm) prm = &def;

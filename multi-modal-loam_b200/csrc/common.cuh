@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/mmloam_b200.h"
@@ -16,11 +17,20 @@ constexpr int kCubeW = 21, kCubeH = 11, kCubeD = 21;  // MM.h:117-119
 constexpr int kNumCubes = kCubeW * kCubeH * kCubeD;
 constexpr int kCubeNone = 5000;         // MM.cpp:601
 
+// Several contexts may be driven from several host threads (the reference calls the extractor from six threads and
+// matches on two). A stream capture must not overlap another thread's allocation + legacy-stream memset or another
+// capture: both take this process-wide lock (recursive: a capture may find a buffer to grow).
+inline std::recursive_mutex& capture_mutex() {
+  static std::recursive_mutex m;
+  return m;
+}
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    std::lock_guard<std::recursive_mutex> lk(capture_mutex());
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -122,6 +132,11 @@ struct mml_ctx {
   bool grid_table_dirty = true;
   unsigned grid_table_gen = 0;
   bool assoc_table_mode = false;
+  // cube-sharded map over several GPUs: exchange buffer of this rank, device-side descriptor (eststate.cuh ShardDev)
+  mml::DevBuf shard_buf, shard_dev;
+  bool shard_active = false;
+  int shard_rank = 0, shard_world = 1;
+  void* shard_peer_opened[8] = {};
 
   // frame slot (queries + features)
   mml::DevBuf q_corner, q_surf;   // float4

@@ -33,6 +33,62 @@ struct EstInit {
   int max_outer, max_inner;
 };
 
+// Cube-sharded global map over several GPUs (SURVEY.md 8 e): every rank evaluates the queries that fall into its cubes and
+// the ranks exchange their partial sums THROUGH PEER MEMORY from inside the kernel that formed them: the last CTA of an
+// evaluation stores its 28 sums into every rank's exchange buffer (NVLink / NVSwitch peer stores), publishes a sequence
+// word behind a system-scope fence, waits for the other ranks' words in its own buffer, and sums the contributions in
+// rank order - every rank gets the same bits, takes the same dogleg step on the device, and no host or library call
+// sits between two evaluations.
+constexpr int kShardMaxWorld = 8;
+constexpr int kShardSlot = 40;   // doubles per message
+constexpr int kShardBufDoubles = 2 * kShardMaxWorld * kShardSlot + 2 * kShardMaxWorld;  // slots[2][8][40] + sequence words [2][8]
+struct ShardDev {
+  int rank, world;
+  unsigned seq;                   // exchanges completed (the same number on every rank)
+  int pad;                        // set to 1 when a wait for a peer timed out
+  double* peer[kShardMaxWorld];   // exchange buffers of all ranks, peer[rank] = this rank's own
+};
+
+// Executed by one full warp. local / total: `count` (<= kShardSlot) doubles in shared or global memory.
+__device__ inline void shard_allreduce(ShardDev* sh, const double* local, int count, double* total) {
+  const int lane = threadIdx.x & 31;
+  const int rank = sh->rank, world = sh->world;
+  const unsigned seq = sh->seq + 1u;
+  const int par = (int)(seq & 1u);
+  __syncwarp();
+  for (int p = 0; p < world; p++) {
+    double* dst = sh->peer[p] + (size_t)(par * kShardMaxWorld + rank) * kShardSlot;
+    for (int k = lane; k < count; k += 32) dst[k] = local[k];
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (lane < world) {
+    volatile unsigned long long* flag =
+        reinterpret_cast<volatile unsigned long long*>(sh->peer[lane] + 2 * kShardMaxWorld * kShardSlot) + par * kShardMaxWorld + rank;
+    *flag = (unsigned long long)seq;
+  }
+  double* own = sh->peer[rank];
+  if (lane < world) {
+    volatile unsigned long long* flag =
+        reinterpret_cast<volatile unsigned long long*>(own + 2 * kShardMaxWorld * kShardSlot) + par * kShardMaxWorld + lane;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*flag != (unsigned long long)seq) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 2000000000ull) { sh->pad = 1; break; }  // 2 s: a peer never arrived (it failed) - give up instead of hanging the device
+    }
+  }
+  __threadfence_system();
+  __syncwarp();
+  for (int k = lane; k < count; k += 32) {
+    double v = 0;
+    for (int r = 0; r < world; r++) v += reinterpret_cast<volatile double*>(own)[(size_t)(par * kShardMaxWorld + r) * kShardSlot + k];
+    total[k] = v;
+  }
+  __syncwarp();
+  if (lane == 0) sh->seq = seq;
+}
+
 // Chained odometry loop (odometry.cu): the last two poses live on the device, so that the constant-velocity
 // prediction of scan k+1 (PE.cpp:847-852, 882-890) needs no host round trip after scan k.
 struct OdomDev {

@@ -914,6 +914,7 @@ int mml_window_solve_graph(mml_ctx* c, WindowState* w, int cap) {
       mix(M.cen[0]); mix(M.cen[1]); mix(M.cen[2]);
     }
   if (w->graph && w->graph_key == key) return MML_OK;
+  std::lock_guard<std::recursive_mutex> capture_lock(capture_mutex());
   if (w->graph) { cudaGraphExecDestroy(w->graph); w->graph = nullptr; }
   // the table of count pointers the begin / push kernels use to silence unused slots
   {

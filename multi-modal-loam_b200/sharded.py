@@ -11,8 +11,13 @@ The reference already cuts the global map into 50 m cubes and lets a query see o
     one small all-reduce over NCCL / NVLink, after which every rank takes the same dogleg step
     with the host-side solver (mml_solver_*), keeping poses bit-identical across ranks.
 
-The collective layer is `torch.distributed` (NCCL on GPUs, gloo in the CPU tests); the compute
-backend is injected so the host logic can be tested without a GPU.
+Two drivers of the same partition:
+  * `connect_ranks` + `Context.estimate_sharded` (C-ABI mml_estimate_sharded): the exchange goes through PEER MEMORY from
+    inside the kernels (the last CTA of an evaluation stores its sums into every rank's buffer over NVLink, waits for the
+    others and sums in rank order) and the dogleg step stays on the device - no NCCL or host call between evaluations;
+    `torch.distributed` only carries the 64-byte IPC handles once at set-up;
+  * `ShardedEstimator`: the same loop driven from the host with a `torch.distributed` all-reduce per evaluation (NCCL on
+    GPUs, gloo in the CPU tests), compute backend injected so the host logic can be tested without a GPU.
 """
 from __future__ import annotations
 
@@ -203,3 +208,24 @@ def nccl_allreduce_on(ctx):
             t.copy_(tc.cpu())
 
     return fn
+
+
+
+def cube_owner_union(clouds, world, cen=(10, 5, 10)):
+    """cube id -> owning rank over the cubes populated by ANY of the clouds (corner and surf maps share the table: a
+    corner cube without surf points must still have an owner)."""
+    ids = np.concatenate([cube_index(c, cen) for c in clouds if len(c)]) if any(len(c) for c in clouds) else np.zeros(0, np.int64)
+    return cube_owner(ids, world)
+
+
+def connect_ranks(ctx, rank, world):
+    """One process per GPU: all-gather the exchange buffers' IPC handles over torch.distributed and open the peers."""
+    import torch.distributed as dist
+
+    mine = ctx.shard_init(rank, world)
+    if world == 1:
+        return
+    handles = [None] * world
+    dist.all_gather_object(handles, mine)
+    ctx.shard_connect_ipc(handles)
+    dist.barrier()

@@ -741,3 +741,68 @@ def test_message_unpack_and_pack_match_oracle(ctx, orc, synth, scene):
         gf, gc, gsf = ctx.pack_union_clouds(hx, hs, hl, label, *args)
         assert 0 < oc.shape[0] and 0 < osf.shape[0] < of.shape[0] < len(hx)
         assert np.array_equal(gf, of) and np.array_equal(gc, oc) and np.array_equal(gsf, osf)
+
+
+def test_sharded_estimate_through_peer_memory_matches_unsharded(mm, orc, synth, scene):
+    """(e) multi-GPU path on one device: two contexts act as two ranks of a cube-sharded global map (the scene straddles
+    the cube boundary at x = 25 m), each holding its cubes only; the partial sums are exchanged through the ranks'
+    buffers from inside the kernels. Both ranks must return the same bits, and the pose of the unsharded solve."""
+    import threading
+    from mmloam_b200 import sharded
+    corner, surf = _assoc_inputs(orc, scene)
+    shift = np.array([27.0, 0.0, 0.0])
+    ms = scene["map_surf"].copy(); ms[:, :3] += shift.astype(np.float32)
+    mc = scene["map_corner"].copy(); mc[:, :3] += shift.astype(np.float32)
+    T = scene["T_true"] @ synth.s1_offset_pose()
+    T = T.copy(); T[:3, 3] += shift
+    q0, _ = orc.so3_exp(synth.R_to_rotvec(T[:3, :3]))
+    empty = np.zeros((0, 4), np.float32)
+    # unsharded reference on its own context
+    full = mm.Context(0)
+    full.map_set(mm.MAP_SURF_GLOBAL, ms); full.map_set(mm.MAP_CORNER_GLOBAL, mc)
+    P_ref, q_ref, st_ref = full.estimate(corner, surf, np.eye(4), T[:3, 3], q0)
+    full.close()
+    world = 2
+    owner = sharded.cube_owner_union([ms, mc], world)
+    assert len(owner) >= 2                                   # the map really spans more than one cube
+    ranks = [mm.Context(0) for _ in range(world)]
+    for r, c in enumerate(ranks):
+        c.map_set(mm.MAP_SURF_GLOBAL, sharded.shard_points(ms, r, world, owner=owner)[0])
+        c.map_set(mm.MAP_CORNER_GLOBAL, sharded.shard_points(mc, r, world, owner=owner)[0])
+        c.map_set(mm.MAP_SURF_LOCAL, empty); c.map_set(mm.MAP_CORNER_LOCAL, empty)
+        # two ranks in ONE process on ONE device: a first-use allocation or graph instantiation on one context would
+        # wait for the other rank's kernel, which waits for this rank. Build everything up front with a one-rank
+        # exchange (the graph only bakes the descriptor's address); real deployments run one process per GPU.
+        c.shard_init(0, 1)
+        c.estimate_sharded(corner, surf, np.eye(4), T[:3, 3], q0)
+        c.shard_init(r, world)
+    ptrs = [c.shard_local_ptr() for c in ranks]
+    for c in ranks:
+        c.shard_connect_ptrs(ptrs, [0] * world)
+    out = [None] * world
+
+    def work(r):
+        try:
+            out[r] = ranks[r].estimate_sharded(corner, surf, np.eye(4), T[:3, 3], q0)
+        except Exception as e:  # noqa: BLE001
+            out[r] = e
+
+    for rep in range(2):                                     # twice: the exchange's sequence numbers carry over
+        th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(120)
+        for o in out:
+            assert not isinstance(o, Exception), o
+        (P0, q0_, s0), (P1, q1_, s1) = out
+        assert np.array_equal(P0, P1) and np.array_equal(q0_, q1_) and np.array_equal(s0[:7], s1[:7])
+        dP, dq = _pose_err(P0, q0_, P_ref, q_ref)
+        assert dP <= 1e-9 and dq <= 1e-9, (dP, dq)
+        assert s0[0] == st_ref[0] and s0[2] == st_ref[2] and s0[3] == st_ref[3]
+    # a shard context with a local map is refused: the fallback would match a query on every rank
+    ranks[0].map_set(mm.MAP_SURF_LOCAL, scene["map_surf"])
+    with pytest.raises(mm.MmlError):
+        ranks[0].estimate_sharded(corner, surf, np.eye(4), T[:3, 3], q0)
+    for c in ranks:
+        c.close()

@@ -236,6 +236,8 @@ def state_of(synth, T, v=0.5):
 
 
 MAP_UPDATE = 1  # set from --map-update
+# dram__bytes_read.sum + dram__bytes_write.sum of the S4 association kernels per sweep step (ncu --set full, profiles/)
+S4_ASSOC_TRAFFIC = None
 
 
 def cpu_window_loop(orc, synth, scans, Ts, imu, stamps, first, n, ms, mc, threads, window):
@@ -675,12 +677,31 @@ def main():
     dom_ms = ms_assoc_plane
     dom_bytes = int(surf.shape[0]) * BYTES_PER_QUERY_ASSOC
     achieved = dom_bytes / dom_ms / 1e6
-    roofline = {"bound": "hbm", "kernel": "k_associate_g<1,32> (plane association: hash-grid 5-NN + plane fit, one warp per query)",
+    scan_sized = {"kernel": "k_associate_g<1,32> (plane association of ONE scan: hash-grid 5-NN + plane fit, one warp per query)",
+                  "achieved": achieved, "frac": achieved / peak, "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
+                  "traffic": 975000,  # ncu --set full, profiles/r1h_ncu_full_summary.txt
+                  "note": "one-scan working set (~1.1 k queries, 0.1 MB): a dependent chain of memory round trips and float64 fits, "
+                          "not bandwidth; the headline step is bound by the latency of k_solve_window (DESIGN.md 5)"}
+    roof_kernel = scan_sized["kernel"]
+    roof_traffic = scan_sized["traffic"]
+    roof_note = scan_sized["note"]
+    if s4 and s4["sweep"]:
+        # the k-NN + fit kernels at the size north_star quotes the roofline on (BASELINE config 4: 1 M queries against a
+        # 1 M-point map), timed live above with CUDA events on the context's stream
+        big = s4["sweep"][-1]
+        dom_ms = big["associate_ms"]
+        dom_bytes = int(big["queries"]) * BYTES_PER_QUERY_ASSOC
+        achieved = dom_bytes / dom_ms / 1e6
+        roof_kernel = ("k_knn_walk + k_associate<KIND,true> (S4, BASELINE config 4: hash-grid 5-NN + line / plane fit + feature write of "
+                       f"{big['queries']} queries against a {s4['map_points']}-point map, line and plane kinds on two streams)")
+        roof_traffic = S4_ASSOC_TRAFFIC
+        roof_note = ("issue-bound under divergence, not bandwidth-bound (profiles/r2_s4_knn_experiments.txt); the residual / Jacobian "
+                     f"kernel of the same sweep: {big['accumulate_gbs']:.0f} GB/s = {100 * big['accumulate_frac']:.0f} % of the peak")
+    roofline = {"bound": "hbm", "kernel": roof_kernel,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": 975000,  # dram read + write bytes per launch, ncu --set full (profiles/r1h_ncu_full_summary.txt)
+                "traffic": roof_traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
-                "note": "one-scan working set (~1.1 k queries, 0.1 MB): a dependent chain of memory round trips and float64 "
-                        "fits, not bandwidth; the HBM-sized sweep is in s4 (there the kernels are issue / FP64-pipe bound)",
+                "note": roof_note, "scan_sized": scan_sized,
                 "stage_ms_per_scan": {"extract": stage_ms[0], "undistort_split_voxel": stage_ms[1], "estimate": stage_ms[2]},
                 "per_scan_avg": {"outer_iters": float(np.mean([i[0] for i in iters])), "dogleg_iters": float(np.mean([i[1] for i in iters])),
                                  "corner_queries": float(np.mean([i[2] for i in iters])), "surf_queries": float(np.mean([i[3] for i in iters]))},

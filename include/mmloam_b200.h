@@ -64,6 +64,18 @@ int mml_velo_ring_time(mml_ctx* ctx, const float* xyzi, int n, int16_t* line_out
 int mml_hori_filter(mml_ctx* ctx, const uint32_t* offset_time, const float* xyz3, const uint8_t* line, int n,
                     uint8_t* keep, float* reltime_out);
 
+/* ---- global feature map kept on the device: MAP_MANAGER::MapIncrement with MapMove, src/lio/Map_Manager.cpp:125-281,
+ * 288-581 (SURVEY.md 8 f, row F1, second half). The 21 x 11 x 21 grid of 50 m cubes lives in HBM, every populated cube
+ * in insertion order. One call = one update: the cubes as they are BEFORE the update become the global maps (kinds 0 / 1)
+ * the association searches (MM.cpp:133-146: the matcher lags the map by one update), MapMove re-centres the grid on
+ * T_wl16 (may be NULL), the new world-frame points are appended to their cubes and touched cubes above 300 points are
+ * voxel-filtered with leaf 0.4. n_from_map2 (may be NULL): sizes of laserCloudCornerFromMap / SurfFromMap.            */
+int mml_global_map_push(mml_ctx* ctx, const float* corner_world_xyzi, int n_corner, const float* surf_world_xyzi,
+                        int n_surf, const double* T_wl16, int* n_from_map2);
+/* which: 0 all cubes now, 1 the snapshot the matcher sees, 2 laserCloud*FromMap; cen3_out: (CenWidth, CenHeight, CenDepth) */
+int mml_global_map_get(mml_ctx* ctx, int kind, int which, float* out_xyzi, int cap, int* n_out, int* cen3_out);
+int mml_global_map_reset(mml_ctx* ctx);
+
 /* ---- F2: the message stages either side of the extractor, on the device (csrc/msgpack.cu).
  * livox_ros_driver/CustomMsg points (CustomPoint.msg:3-9 serialised: 19 packed bytes per point) -> xyzi, line and sweep
  * fraction behind the filter of getHoriFeatureExtract (FE.cpp:985-998: line <= used_line - 1, x >= 0.01), in message

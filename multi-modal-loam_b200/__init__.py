@@ -34,7 +34,7 @@ EXPORTS = [
     "mml_voxel_downsample", "mml_map_set", "mml_associate", "mml_accumulate", "mml_est_params_default",
     "mml_estimate", "mml_scan_to_pose", "mml_scan_to_pose_dev", "mml_frame_set", "mml_frame_associate",
     "mml_frame_accumulate", "mml_frame_associate_async", "mml_frame_associate_kind_async", "mml_frame_accumulate_async",
-    "mml_odom_run", "mml_local_map_push", "mml_local_map_push_dev", "mml_local_map_seed", "mml_unpack_custom_points", "mml_unpack_pointcloud2", "mml_pack_union_clouds", "mml_local_map_get", "mml_local_map_reset", "mml_timer_start",
+    "mml_odom_run", "mml_local_map_push", "mml_local_map_push_dev", "mml_local_map_seed", "mml_global_map_push", "mml_global_map_get", "mml_global_map_reset", "mml_unpack_custom_points", "mml_unpack_pointcloud2", "mml_pack_union_clouds", "mml_local_map_get", "mml_local_map_reset", "mml_timer_start",
     "mml_timer_stop_ms", "mml_frame_accumulate_partial_dev", "mml_stream_handle",
     "mml_imu_preintegrate", "mml_imu_factor", "mml_imu_predict", "mml_window_reset", "mml_window_size",
     "mml_window_push_frame", "mml_window_push_scan_dev", "mml_window_get_frame", "mml_estimate_window",
@@ -514,6 +514,28 @@ class Context:
                                               _p(so), _p(st), C.byref(ms)))
         return dict(poses_front=pf.reshape(n, 4, 4), poses_newest=pn.reshape(n, 4, 4), states=so, stats=st,
                     total_ms=float(ms.value))
+
+    # ---- global cube map on the device (MAP_MANAGER::MapIncrement + MapMove, MM.cpp:125-281, 288-581)
+    def global_map_push(self, corner_w, surf_w, T_wl=None):
+        corner_w = np.ascontiguousarray(corner_w, np.float32).reshape(-1, 4)
+        surf_w = np.ascontiguousarray(surf_w, np.float32).reshape(-1, 4)
+        T = _f64(T_wl).reshape(16) if T_wl is not None else None
+        n2 = np.zeros(2, np.int32)
+        self._ck(self.lib.mml_global_map_push(self.h, _p(corner_w), int(corner_w.shape[0]), _p(surf_w), int(surf_w.shape[0]),
+                                              _p(T) if T is not None else None, _p(n2)))
+        return int(n2[0]), int(n2[1])
+
+    def global_map_get(self, kind, which=0):
+        """which: 0 all cubes, 1 the matcher's snapshot, 2 laserCloud*FromMap. Returns (cloud [n,4], cen)."""
+        n = C.c_int(0)
+        cen = np.zeros(3, np.int32)
+        self._ck(self.lib.mml_global_map_get(self.h, int(kind), int(which), None, 0, C.byref(n), _p(cen)))
+        out = np.zeros((max(n.value, 1), 4), np.float32)
+        self._ck(self.lib.mml_global_map_get(self.h, int(kind), int(which), _p(out), int(out.shape[0]), C.byref(n), _p(cen)))
+        return out[:n.value], tuple(int(v) for v in cen)
+
+    def global_map_reset(self):
+        self._ck(self.lib.mml_global_map_reset(self.h))
 
     # ---- F2: message unpack / pack on the device (csrc/msgpack.cu)
     def unpack_custom_points(self, points19, used_line=6):

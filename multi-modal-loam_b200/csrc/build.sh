@@ -10,7 +10,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -Xcompiler -O3 ${MML_EXTRA_NVCC_FLAGS}"
 mkdir -p "$OBJ"
 pids=()
-for f in extract geometry splitvoxel framesort associate accumulate odometry localmap window windowsolve msgpack capi; do
+for f in extract geometry splitvoxel framesort associate accumulate odometry localmap globalmap window windowsolve msgpack capi; do
   if [ ! -f "$OBJ/$f.o" ] || [ -n "$(find "$HERE" -maxdepth 1 \( -name '*.cu' -o -name '*.cuh' \) -newer "$OBJ/$f.o" 2>/dev/null)" ] || [ "$HERE/../../include/mmloam_b200.h" -nt "$OBJ/$f.o" ]; then
     # accumulate.cu is pure float64 normal-equation arithmetic checked to 1e-9 relative (no bit-exact float32
     # thresholds inside): it may contract multiply-adds into DFMA
@@ -23,5 +23,5 @@ for f in extract geometry splitvoxel framesort associate accumulate odometry loc
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$OBJ"/{extract,geometry,splitvoxel,framesort,associate,accumulate,odometry,localmap,window,windowsolve,msgpack,capi}.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$OBJ"/{extract,geometry,splitvoxel,framesort,associate,accumulate,odometry,localmap,globalmap,window,windowsolve,msgpack,capi}.o -lcudart
 echo "built $OUT"

@@ -29,6 +29,7 @@ int mml_split_voxel_capacity();
 namespace mml { struct SvChain; }
 void mml_odom_destroy(mml_ctx* c);
 void mml_local_map_destroy(mml_ctx* c);
+void mml_global_map_destroy(mml_ctx* c);
 void mml_window_destroy(mml_ctx* c);
 int mml_split_voxel_device(mml_ctx* ctx, const float4* pts_d, const float* s_d, const uint8_t* label_d, int n,
                            const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, float4* corner_out,
@@ -83,6 +84,7 @@ int mml_ctx_destroy(mml_ctx* c) {
   if (c->chain_graph) cudaGraphExecDestroy(c->chain_graph);
   mml_odom_destroy(c);
   mml_local_map_destroy(c);
+  mml_global_map_destroy(c);
   mml_window_destroy(c);
   if (c->stream_fe) { cudaStreamSynchronize(c->stream_fe); cudaStreamDestroy(c->stream_fe); }
   mml::DevBuf* bufs[] = {&c->in_xyzi, &c->in_line, &c->in_s, &c->in_label, &c->srt_xyzi, &c->srt_src, &c->srt_line,

@@ -161,6 +161,7 @@ struct mml_ctx {
   std::vector<int> last_scan_off;  // scan offsets the resident chunk table was built for
   void* odom = nullptr;            // pipelined odometry runner state (odometry.cu)
   void* local_map = nullptr;       // device-side local feature map (localmap.cu)
+  void* global_map = nullptr;      // global cube map kept on the device (globalmap.cu)
   void* window = nullptr;          // sliding-window frame slots and solver scratch (window.cu)
   cudaStream_t stream_fe = nullptr;  // feature-extraction stream of the pipelined runner
   bool profile = false;

@@ -806,3 +806,47 @@ def test_sharded_estimate_through_peer_memory_matches_unsharded(mm, orc, synth, 
         ranks[0].estimate_sharded(corner, surf, np.eye(4), T[:3, 3], q0)
     for c in ranks:
         c.close()
+
+
+def test_global_map_increment_and_move_match_oracle(ctx, mm, orc, synth, scene):
+    """Device-side MAP_MANAGER::MapIncrement with MapMove (SURVEY 8 f, F1 second half) against oracle/map_maintenance.py
+    (itself pinned to the reference text): cubes, the matcher's snapshot, laserCloud*FromMap and the cube centre after
+    every update, bit for bit; then the association against the snapshot equals the oracle's."""
+    from oracle import map_maintenance as mmt
+    rng = np.random.default_rng(21)
+    cm = mmt.CubeMap()
+    ctx.global_map_reset()
+    surf_all, corner_all = scene["map_surf"], scene["map_corner"]
+    # the sensor drives along x: the scene is shifted with it, so points land in several cubes and MapMove re-centres
+    for k in range(6):
+        shift = np.array([18.0 * k, -7.0 * k, 0.0])
+        T = synth.make_T(synth.rot_z(0.02 * k), np.array([-3.0, -1.0, 0.2]) + shift)
+        s = surf_all[rng.choice(surf_all.shape[0], 5000, replace=False)].copy()
+        c = corner_all[rng.choice(corner_all.shape[0], 400, replace=False)].copy()
+        s[:, :3] += shift.astype(np.float32); c[:, :3] += shift.astype(np.float32)
+        if k == 3:
+            s[:7, 0] = 900.0                      # outside the 21 x 11 x 21 grid: dropped (MM.cpp:168-175)
+        oc, os_ = cm.increment(c, s, T)
+        nc, ns = ctx.global_map_push(c, s, T)
+        assert (nc, ns) == (oc.shape[0], os_.shape[0]), k
+        for kind in (0, 1):
+            cur, cen = ctx.global_map_get(kind, 0)
+            assert cen == tuple(cm.cen) and np.array_equal(cur, cm.cloud(kind)), (k, kind)
+            snap, cen_last = ctx.global_map_get(kind, 1)
+            assert cen_last == tuple(cm.cen_last) and np.array_equal(snap, cm.cloud(kind, matched=True)), (k, kind)
+            fm, _ = ctx.global_map_get(kind, 2)
+            assert np.array_equal(fm, cm.from_map[kind]), (k, kind)
+    assert len(cm.cubes[1]) >= 2 and any(v.shape[0] < 5000 for v in cm.cubes[1].values())   # several cubes, some filtered
+    # the association searches the snapshot (one update behind), with the centre of that moment
+    ctx.map_set(mm.MAP_SURF_LOCAL, np.zeros((0, 4), np.float32)); ctx.map_set(mm.MAP_CORNER_LOCAL, np.zeros((0, 4), np.float32))
+    om = orc.Map()
+    om.set(orc.SURF_GLOBAL, cm.cloud(1, matched=True), cm.cen_last)
+    om.set(orc.CORNER_GLOBAL, cm.cloud(0, matched=True), cm.cen_last)
+    corner_q, surf_q = _assoc_inputs(orc, scene)
+    Tq = scene["T_true"] @ synth.s1_offset_pose()
+    Tq = Tq.copy(); Tq[:3, 3] += np.array([18.0 * 4, -7.0 * 4, 0.0])
+    fp, np_, _, _ = ctx.associate(1, surf_q, Tq, 25.0)
+    rp, rnp, _, _ = om.associate_plane(surf_q, Tq, 25.0)
+    assert np_ == rnp and np_ > 50
+    _cmp_features(fp, rp, 1)
+    ctx.global_map_reset()

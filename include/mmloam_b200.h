@@ -161,7 +161,8 @@ typedef struct {
 } mml_est_params;
 void mml_est_params_default(mml_est_params* p);
 /* stats (may be NULL, 16 doubles): [outer_iters, inner_iters, n_line, n_plane, final_cost,
- * min_singular_value, is_degenerate, ...]                                              */
+ * min_singular_value, is_degenerate, ...]. corner_xyzi = surf_xyzi = NULL with n_corner = n_surf = -1: solve the frame
+ * mml_frame_set left in HBM (the same holds for mml_estimate_sharded).                    */
 int mml_estimate(mml_ctx* ctx, const float* corner_xyzi, int n_corner, const float* surf_xyzi, int n_surf,
                  const double* exTlb16, double* P3, double* q_wxyz4, const mml_est_params* prm, double* stats);
 

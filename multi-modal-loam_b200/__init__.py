@@ -333,6 +333,14 @@ class Context:
 
     # ---- A12
     def estimate(self, corner, surf, exTlb, P, q_wxyz, params=None):
+        if corner is None and surf is None:   # the frame frame_set() left in HBM
+            ex = _f64(exTlb).reshape(16)
+            P = _f64(P).copy()
+            q = _f64(q_wxyz).copy()
+            stats = np.zeros(16)
+            prm = params if params is not None else est_params()
+            self._ck(self.lib.mml_estimate(self.h, None, -1, None, -1, _p(ex), _p(P), _p(q), C.byref(prm), _p(stats)))
+            return P, q, stats
         corner = _f32(corner).reshape(-1, 4)
         surf = _f32(surf).reshape(-1, 4)
         ex = _f64(exTlb).reshape(16)
@@ -371,7 +379,16 @@ class Context:
         self._ck(self.lib.mml_shard_close(self.h))
 
     def estimate_sharded(self, corner, surf, exTlb, P, q_wxyz, params=None):
-        """mml_estimate_sharded: a collective over the ranks of shard_init (same queries and start pose on each)."""
+        """mml_estimate_sharded: a collective over the ranks of shard_init (same queries and start pose on each).
+        corner = surf = None: solve the frame frame_set() left in HBM."""
+        if corner is None and surf is None:
+            ex = _f64(exTlb).reshape(16)
+            P = _f64(P).copy()
+            q = _f64(q_wxyz).copy()
+            stats = np.zeros(16)
+            prm = params if params is not None else est_params()
+            self._ck(self.lib.mml_estimate_sharded(self.h, None, -1, None, -1, _p(ex), _p(P), _p(q), C.byref(prm), _p(stats)))
+            return P, q, stats
         corner = _f32(corner).reshape(-1, 4)
         surf = _f32(surf).reshape(-1, 4)
         ex = _f64(exTlb).reshape(16)

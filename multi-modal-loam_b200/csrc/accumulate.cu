@@ -20,6 +20,7 @@
 #include "eststate.cuh"
 #include "lidarfactor.cuh"
 #include <float.h>
+#include <time.h>
 #include <math.h>
 
 namespace mml {
@@ -827,6 +828,16 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
     MML_CUDA(ctx, cudaMemcpyAsync(h, S, sizeof(EstState), cudaMemcpyDeviceToHost, st));
     if (launched == 1) MML_CUDA(ctx, cudaMemcpyAsync(h_cnt, cnt_dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     MML_CUDA(ctx, cudaStreamSynchronize(st));
+    static const bool est_prof = getenv("MML_EST_PROF") != nullptr;  // debug aid: wall clock of every burst of outer iterations
+    if (est_prof) {
+      static thread_local double t_last = 0;
+      timespec ts;
+      clock_gettime(CLOCK_MONOTONIC, &ts);
+      const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+      fprintf(stderr, "[mml est prof] outer iterations launched %d (burst %d): %.3f ms since the previous mark, done %d, inner %d\n", launched, burst,
+              t_last > 0 ? now - t_last : 0.0, h->done_outer, h->total_inner);
+      t_last = now;
+    }
     if (h->done_outer) break;
   }
   // frames with more feature slots than one CTA turns over quickly go back to a launch per evaluation

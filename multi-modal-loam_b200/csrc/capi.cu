@@ -573,7 +573,12 @@ int mml_estimate(mml_ctx* c, const float* corner_xyzi, int n_corner, const float
   mml_est_params def;
   mml_est_params_default(&def);
   if (!prm) prm = &def;
-  MML_CHECK(mml_frame_set(c, corner_xyzi, n_corner, surf_xyzi, n_surf));
+  if (n_corner < 0 && n_surf < 0 && !corner_xyzi && !surf_xyzi) {
+    // the frame mml_frame_set left in HBM (queries uploaded and spatially sorted once, solved several times)
+    n_corner = c->n_corner; n_surf = c->n_surf;
+  } else {
+    MML_CHECK(mml_frame_set(c, corner_xyzi, n_corner, surf_xyzi, n_surf));
+  }
   return mml_estimate_device(c, c->frame_cnt.as<int>(), round_cap(n_corner), round_cap(n_surf), exTlb16, P3, q_wxyz4, prm,
                              stats);
 }

@@ -237,7 +237,7 @@ def state_of(synth, T, v=0.5):
 
 MAP_UPDATE = 1  # set from --map-update
 # dram__bytes_read.sum + dram__bytes_write.sum of the S4 association kernels per sweep step (ncu --set full, profiles/)
-S4_ASSOC_TRAFFIC = None
+S4_ASSOC_TRAFFIC = 162_400_000  # profiles/r2_ncu_s4_assoc.txt: both kinds, search + fit kernels
 
 
 def cpu_window_loop(orc, synth, scans, Ts, imu, stamps, first, n, ms, mc, threads, window):
@@ -623,10 +623,23 @@ def main():
         ctx4.map_set(mm.MAP_CORNER_LOCAL, hc)
         ctx4.sync()
         map_build_ms = 1e3 * (time.perf_counter() - t0)
+        # kernel-only map build (points resident in HBM): bounding box, cell counts, look-back scan, scatter, coarse level
+        hs_dev = ctx4.dev_upload(np.ascontiguousarray(hs, np.float32))
+        ctx4.map_set_dev(mm.MAP_SURF_LOCAL, hs_dev, hs.shape[0])
+        ctx4.sync()
+        ctx4.timer_start()
+        for _ in range(5):
+            ctx4.map_set_dev(mm.MAP_SURF_LOCAL, hs_dev, hs.shape[0])
+        build_ms = ctx4.timer_stop_ms() / 5
+        ctx4.dev_free(hs_dev)
         Tq = synth.s1_offset_pose()
         x6q = np.concatenate([Tq[:3, 3], synth.R_to_rotvec(Tq[:3, :3])])
         s4 = {"map_points": int(hs.shape[0] + hc.shape[0]), "map_cell_m": ctx4.map_info(mm.MAP_SURF_LOCAL)["cell"],
-              "map_build_ms_incl_h2d": map_build_ms, "sweep": []}
+              "map_build_ms_incl_h2d": map_build_ms,
+              "map_build_kernels": {"points": int(hs.shape[0]), "ms": build_ms, "gbs": hs.shape[0] * 36 / build_ms / 1e6,
+                                    "frac": hs.shape[0] * 36 / build_ms / 1e6 / peak,
+                                    "note": "36 B per point per rebuild (SURVEY 8 d); includes the host synchronisations that size the grid"},
+              "sweep": []}
         for Q in sorted({28_800, a.s4_queries, 1_000_000} if a.s4_queries >= 240_000 else {a.s4_queries}):
             qs = synth.queries_from_map(hs, Q, np.eye(4), seed=1004)
             qc = synth.queries_from_map(hc, max(Q // 20, 64), np.eye(4), seed=1005)

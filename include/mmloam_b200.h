@@ -112,6 +112,8 @@ int mml_voxel_downsample(mml_ctx* ctx, const float* xyzi, int n, float leaf, flo
 #define MML_MAP_CORNER_LOCAL 2
 #define MML_MAP_SURF_LOCAL 3
 int mml_map_set(mml_ctx* ctx, int kind, const float* xyzi, int m, const int* cube_centre3);
+/* the same with the points already resident in HBM (float4 xyzi)                       */
+int mml_map_set_dev(mml_ctx* ctx, int kind, const void* xyzi_dev, int m, const int* cube_centre3);
 /* Same with an explicit hash-cell edge in metres (0 = choose automatically).           */
 int mml_map_set_ex(mml_ctx* ctx, int kind, const float* xyzi, int m, const int* cube_centre3, float cell);
 /* info8 = [valid, points, cell edge, dim x, dim y, dim z, cells, cells per 50 m cube]  */

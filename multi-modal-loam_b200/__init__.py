@@ -31,7 +31,7 @@ ERRORS = {0: "ok", -1: "invalid argument", -2: "no CUDA device", -3: "CUDA error
 EXPORTS = [
     "mml_version", "mml_ctx_create", "mml_ctx_destroy", "mml_last_error", "mml_launch_count", "mml_sync",
     "mml_extract_features", "mml_extract_features_batch", "mml_velo_ring_time", "mml_hori_filter", "mml_undistort",
-    "mml_voxel_downsample", "mml_map_set", "mml_associate", "mml_accumulate", "mml_est_params_default",
+    "mml_voxel_downsample", "mml_map_set", "mml_map_set_dev", "mml_associate", "mml_accumulate", "mml_est_params_default",
     "mml_estimate", "mml_scan_to_pose", "mml_scan_to_pose_dev", "mml_frame_set", "mml_frame_associate",
     "mml_frame_accumulate", "mml_frame_associate_async", "mml_frame_associate_kind_async", "mml_frame_accumulate_async",
     "mml_odom_run", "mml_local_map_push", "mml_local_map_push_dev", "mml_local_map_seed", "mml_global_map_push", "mml_global_map_get", "mml_global_map_reset", "mml_unpack_custom_points", "mml_unpack_pointcloud2", "mml_pack_union_clouds", "mml_local_map_get", "mml_local_map_reset", "mml_timer_start",
@@ -617,6 +617,11 @@ class Context:
         self._ck(self.lib.mml_local_map_reset(self.h))
 
     # ---- device-resident scans (bench.py)
+    def map_set_dev(self, kind, xyzi_dev, m, cen=None):
+        """mml_map_set with the points already in HBM (pointer from dev_upload)."""
+        cen_a = np.asarray(cen, np.int32) if cen is not None else None
+        self._ck(self.lib.mml_map_set_dev(self.h, int(kind), xyzi_dev, int(m), _p(cen_a) if cen_a is not None else None))
+
     def dev_upload(self, arr):
         arr = np.ascontiguousarray(arr)
         ptr = C.c_void_p()

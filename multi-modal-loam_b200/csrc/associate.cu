@@ -99,7 +99,11 @@ __global__ void __launch_bounds__(256) k_map_count(const float4* __restrict__ pt
   const int cell = (c[2] * G.dim[1] + c[1]) * G.dim[0] + c[0];
   cell_of[i] = cell;
   atomicAdd(&cell_cnt[cell], 1);
-  if (G.global) atomicAdd(&cube_cnt[cube], 1);
+  if (G.global) {
+    // a map has a handful of populated cubes and millions of points: one atomic per (warp, cube) instead of one per point
+    const unsigned peers = __match_any_sync(__activemask(), cube);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&cube_cnt[cube], __popc(peers));
+  }
 }
 
 __global__ void __launch_bounds__(256) k_map_scatter(const float4* __restrict__ pts, int m, const int* __restrict__ cell_of,

@@ -284,6 +284,13 @@ int mml_map_set(mml_ctx* c, int kind, const float* xyzi, int m, const int* cube_
   return mml_map_set_device(c, kind, c->tmp_a.as<float4>(), m, cube_centre3, 0.f);
 }
 
+// the same with the points already resident in HBM (float4 xyzi): the kernel-only cost of a map build
+int mml_map_set_dev(mml_ctx* c, int kind, const void* xyzi_dev, int m, const int* cube_centre3) {
+  if (!c || m < 0 || (m && !xyzi_dev)) return MML_ERR_INVALID;
+  cudaSetDevice(c->device);
+  return mml_map_set_device(c, kind, static_cast<const float4*>(xyzi_dev), m, cube_centre3, 0.f);
+}
+
 // like mml_map_set with an explicit cell edge (0 = automatic); used by the roofline sweep
 int mml_map_set_ex(mml_ctx* c, int kind, const float* xyzi, int m, const int* cube_centre3, float cell) {
   if (!c || m < 0) return MML_ERR_INVALID;

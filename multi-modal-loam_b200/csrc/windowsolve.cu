@@ -75,7 +75,7 @@ struct WinShared {
   double cost_new, cost_imu, min_cost_out;
   int gidx[kMaxWindow - 1][30];           // factor column -> unknown (parameter order)
   int lidx[kMaxWindow - 1][kWinN];        // position -> factor column, or -1
-  int nnz;
+  int nnz, chol_ok;
   unsigned short nz[kWinN * (kWinN + 1) / 2];  // upper-triangle positions some factor touches: (row << 8) | column
   unsigned char tri[27 * 28 / 2][2];        // (row, column) of the idx-th entry of a lower triangle, row-major
   int pos[kWinN], unpos[kWinN];
@@ -135,45 +135,50 @@ __device__ __noinline__ bool cta_chol_solve(WinShared& s, int n, int B, int tid)
 #if defined(MML_WIN_DEVPROF) && MML_WIN_DEVPROF >= 2
   long long ct0 = clock64();
 #endif
+  if (tid == 0) s.chol_ok = 1;
+  int bj = 0, bnext = B;  // frame block of column c0 and the first column of the next block (no division in the loop)
 #pragma unroll 1
   for (int c0 = 0; c0 < n; c0 += 3) {
-    const int bj = c0 / B;
-    const int rend = min(n, B * (bj + 2));
+    if (c0 >= bnext) { bj++; bnext += B; }
+    const int rend = min(n, bnext + B);
     const int m = rend - (c0 + 3);  // panel rows below the diagonal block (band only); the right-hand side row is extra
-    const double* D0 = A + c0 * kWLD + c0;
     __syncthreads();  // the previous step's update is complete
     CTICK(0)
-    const double d00 = D0[0], d10 = D0[kWLD], d11 = D0[kWLD + 1], d20 = D0[2 * kWLD], d21 = D0[2 * kWLD + 1], d22 = D0[2 * kWLD + 2];
-    if (!(d00 > 0.0)) return false;
-    const double r0 = __drcp_rn(d00);
-    const double m10 = d10 * r0, m20 = d20 * r0;
-    const double p1 = d11 - m10 * d10;
-    if (!(p1 > 0.0)) return false;
-    const double e21 = d21 - m20 * d10;
-    const double m21 = e21 * __drcp_rn(p1);
-    const double p2 = d22 - m20 * d20 - m21 * e21;
-    if (!(p2 > 0.0)) return false;
-    const double i00 = rsqrt(d00), i11 = rsqrt(p1), i22 = rsqrt(p2);
-    const double l10 = d10 * i00, l20 = d20 * i00, l21 = e21 * i11;
-    CTICK(1)
-    if (tid <= m) {
-      const int r = tid < m ? c0 + 3 + tid : n;
-      double* Ar = A + r * kWLD + c0;
-      const double x0 = Ar[0] * i00;
-      const double x1 = (Ar[1] - x0 * l10) * i11;
-      const double x2 = (Ar[2] - x0 * l20 - x1 * l21) * i22;
-      Ar[0] = x0; Ar[1] = x1; Ar[2] = x2;
+    if (tid < 32) {
+      // warp 0: the 3 x 3 diagonal block in registers (every lane the same values), then one lane per panel row
+      double* D0 = A + c0 * kWLD + c0;
+      const double d00 = D0[0], d10 = D0[kWLD], d11 = D0[kWLD + 1], d20 = D0[2 * kWLD], d21 = D0[2 * kWLD + 1], d22 = D0[2 * kWLD + 2];
+      const double r0 = __drcp_rn(d00);
+      const double m10 = d10 * r0, m20 = d20 * r0;
+      const double p1 = d11 - m10 * d10;
+      const double e21 = d21 - m20 * d10;
+      const double m21 = e21 * __drcp_rn(p1);
+      const double p2 = d22 - m20 * d20 - m21 * e21;
+      const bool pd = d00 > 0.0 && p1 > 0.0 && p2 > 0.0;
+      const double i00 = rsqrt(d00), i11 = rsqrt(p1), i22 = rsqrt(p2);
+      const double l10 = d10 * i00, l20 = d20 * i00, l21 = e21 * i11;
+      CTICK(1)
+      if (pd && tid <= m) {
+        const int r = tid < m ? c0 + 3 + tid : n;
+        double* Ar = A + r * kWLD + c0;
+        const double x0 = Ar[0] * i00;
+        const double x1 = (Ar[1] - x0 * l10) * i11;
+        const double x2 = (Ar[2] - x0 * l20 - x1 * l21) * i22;
+        Ar[0] = x0; Ar[1] = x1; Ar[2] = x2;
+      }
+      __syncwarp();  // every lane has read the diagonal block
+      if (tid == 31) {
+        if (!pd) s.chol_ok = 0;
+        D0[0] = d00 * i00;
+        D0[kWLD] = l10; D0[kWLD + 1] = p1 * i11;
+        D0[2 * kWLD] = l20; D0[2 * kWLD + 1] = l21; D0[2 * kWLD + 2] = p2 * i22;
+        s.tv[c0] = i00; s.tv[c0 + 1] = i11; s.tv[c0 + 2] = i22;  // 1 / L[j][j] for the back substitution
+      }
     }
     CTICK(2)
-    __syncthreads();  // panel complete; every thread has read the diagonal block, which may now be overwritten
+    __syncthreads();  // panel complete
     CTICK(3)
-    if (tid == kWThreads - 1) {
-      double* Dw = A + c0 * kWLD + c0;
-      Dw[0] = d00 * i00;
-      Dw[kWLD] = l10; Dw[kWLD + 1] = p1 * i11;
-      Dw[2 * kWLD] = l20; Dw[2 * kWLD + 1] = l21; Dw[2 * kWLD + 2] = p2 * i22;
-      s.tv[c0] = i00; s.tv[c0 + 1] = i11; s.tv[c0 + 2] = i22;  // 1 / L[j][j] for the back substitution
-    }
+    if (!s.chol_ok) return false;  // not positive definite (uniform: the flag was written before the barrier)
     const int ntri = m * (m + 1) / 2;
 #pragma unroll 1
     for (int idx = tid; idx < ntri + m; idx += kWThreads) {
@@ -194,10 +199,12 @@ __device__ __noinline__ bool cta_chol_solve(WinShared& s, int n, int B, int tid)
     const int lane = tid;
     const double* yrow = A + n * kWLD;
     double y0 = lane < n ? yrow[lane] : 0.0, y1 = lane + 32 < n ? yrow[lane + 32] : 0.0;
+    int bstart = n;  // first column of the frame block of c0 (walked down without a division)
 #pragma unroll 1
     for (int c0 = n - 3; c0 >= 0; c0 -= 3) {
       const double* D0 = A + c0 * kWLD + c0;
-      const int bj = c0 / B, lo = bj > 0 ? B * (bj - 1) : 0;  // rows c0..c0+2 of the factor start at the previous block
+      while (c0 < bstart) bstart -= B;
+      const int lo = bstart >= B ? bstart - B : 0;  // rows c0..c0+2 of the factor start at the previous block
       // this lane's entries of those rows and the block's own entries: loads that do not wait for the chain below
       const bool u0 = lane >= lo && lane < c0, u1 = lane + 32 >= lo && lane + 32 < c0;
       const double a00 = u0 ? D0[lane - c0] : 0.0, a01 = u0 ? D0[kWLD + lane - c0] : 0.0, a02 = u0 ? D0[2 * kWLD + lane - c0] : 0.0;

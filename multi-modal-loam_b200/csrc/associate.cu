@@ -458,6 +458,27 @@ __global__ void __launch_bounds__(128) k_knn_walk(AssocArgs A) {
   A.pre_status[i] = status;
 }
 
+// Sum of the per-CTA moment partials by the last CTA (128 threads): every thread adds a strided share, then a fixed
+// shuffle / shared-memory tree - deterministic, and ~60 dependent loads per thread instead of thousands on seven.
+__device__ __forceinline__ void reduce_moment_partials(const double* __restrict__ partials, unsigned nblk, double (*sred)[7], double* out7) {
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (unsigned b = threadIdx.x; b < nblk; b += 128) {
+#pragma unroll
+    for (int k = 0; k < 7; k++) acc[k] += __ldcg(partials + (size_t)b * 8 + k);
+  }
+  __syncthreads();  // sred is reused
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+    double v = acc[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) out7[threadIdx.x] = ((sred[0][threadIdx.x] + sred[1][threadIdx.x]) + sred[2][threadIdx.x]) + sred[3][threadIdx.x];
+  __syncthreads();
+}
+
 // PRE: the neighbour search of map A.pre_map was done by k_knn_walk
 template <int KIND, bool PRE>
 __global__ void __launch_bounds__(128) k_associate(AssocArgs A) {
@@ -572,11 +593,12 @@ __global__ void __launch_bounds__(128) k_associate(AssocArgs A) {
   __syncthreads();
   if (threadIdx.x == 0) is_last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1);
   __syncthreads();
-  if (is_last) {
+  if (is_last) {  // block-uniform
     __threadfence();
+    __shared__ double tot7[7];
+    reduce_moment_partials(A.moment_partials, gridDim.x, sred, tot7);
     if (threadIdx.x < 7) {
-      double s = 0;
-      for (unsigned b = 0; b < gridDim.x; b++) s += __ldcg(A.moment_partials + (size_t)b * 8 + threadIdx.x);
+      const double s = tot7[threadIdx.x];
       A.moment_out[threadIdx.x] = s;
       if (threadIdx.x == 6) *A.n_feat_out = (int)s;
     }
@@ -962,11 +984,12 @@ __global__ void __launch_bounds__(128) k_associate_g(AssocArgs A) {
   __syncthreads();
   if (threadIdx.x == 0) is_last = (atomicAdd(A.ticket, 1u) == n_active - 1);
   __syncthreads();
-  if (is_last) {
+  if (is_last) {  // block-uniform
     __threadfence();
+    __shared__ double tot7[7];
+    reduce_moment_partials(A.moment_partials, n_active, sred, tot7);
     if (threadIdx.x < 7) {
-      double s = 0;
-      for (unsigned b = 0; b < n_active; b++) s += __ldcg(A.moment_partials + (size_t)b * 8 + threadIdx.x);
+      double s = tot7[threadIdx.x];
       if (A.accumulate_out) s += A.moment_out[threadIdx.x];
       A.moment_out[threadIdx.x] = s;
       if (threadIdx.x == 6) *A.n_feat_out = (int)s;

@@ -683,6 +683,32 @@ def main():
               "labelled_sharp_flat": [int(c2[0][0]), int(c2[0][1])], "queries_corner_surf": [int(c2[0][2]), int(c2[0][3])],
               "max_pos_err_m": float(max(np.abs(p2[k][:3, 3] - Ts2[2 + k][:3, 3]).max() for k in range(n2 - 1))),
               "path": "general (labelled points exceed the fused split/voxel kernel's 16384)"}
+        # the oracle beside it on the first two scans (its O(m^2) part sorts make a 240 k-point scan slow): time and parity
+        if rank == 0 and a.cpu_scans > 0:
+            orc.build()
+            om2 = orc.Map()
+            om2.set(orc.SURF_LOCAL, ms)
+            om2.set(orc.CORNER_LOCAL, mc)
+            prm_o = orc.est_params(threads=min(6, n_threads))
+            prm_o.max_outer = 10
+            odo2 = Odometry(Ts2[1], Ts2[0])
+            t0 = time.perf_counter()
+            d2p = 0.0
+            n_o = 2
+            for k in range(n_o):
+                hx, hl, hs = synth.horizon_scan(Ts2[k + 2], a.s2_pts, seed=2002 + k + 1, T_ws_start=Ts2[k + 1])
+                Tpr, delta = odo2.predict()
+                lab = orc.extract_scan(hx, hl.astype(np.uint16), 6, threads=min(6, n_threads))
+                und = orc.undistort(hx, hs.astype(np.float32), delta[:3, :3], delta[:3, 3])
+                cds = orc.voxel_downsample(und[lab == 1], LEAF_CORNER)
+                sds = orc.voxel_downsample(und[lab == 2], LEAF_SURF)
+                Po, qo, _ = om2.estimate(cds, sds, np.eye(4), Tpr[:3, 3], R_to_quat(Tpr[:3, :3]), prm_o)
+                Tn = T_from(Po, qo)
+                odo2.update(Tn)
+                d2p = max(d2p, float(np.abs(Tn[:3, 3] - p2[k][:3, 3]).max()))
+            s2["cpu_ms_per_scan"] = 1e3 * (time.perf_counter() - t0) / n_o
+            s2["cpu_cores"] = min(6, n_threads)
+            s2["parity_vs_oracle_max_dpos_m"] = d2p
         for d2 in sc2:
             for ptr in d2[:3]:
                 ctx.dev_free(ptr)

@@ -136,28 +136,34 @@ __device__ __noinline__ bool cta_chol_solve(WinShared& s, int n, int B, int tid)
   long long ct0 = clock64();
 #endif
   if (tid == 0) s.chol_ok = 1;
-  int bj = 0, bnext = B;  // frame block of column c0 and the first column of the next block (no division in the loop)
+  int bnext = B;  // first column of the frame block after the one c0 lies in (no division in the loop)
+  // the 3 x 3 diagonal block of the current step, factored one step AHEAD by warp 0 (registers, every lane the same
+  // values) while the other warps apply the previous step's rank-3 update: the dependent chain of the factor (two
+  // reciprocals, three reciprocal square roots) no longer sits between the two barriers of a step
+  double d00 = 0, d10 = 0, d20 = 0, p1 = 0, e21 = 0, p2 = 0, i00 = 0, i11 = 0, i22 = 0;
+  bool pd = true;
+  auto factor3 = [&](double a00, double a10, double a11, double a20, double a21, double a22) {
+    d00 = a00; d10 = a10; d20 = a20;
+    const double r0 = __drcp_rn(a00);
+    const double m10 = a10 * r0, m20 = a20 * r0;
+    p1 = a11 - m10 * a10;
+    e21 = a21 - m20 * a10;
+    const double m21 = e21 * __drcp_rn(p1);
+    p2 = a22 - m20 * a20 - m21 * e21;
+    pd = a00 > 0.0 && p1 > 0.0 && p2 > 0.0;
+    i00 = rsqrt(a00); i11 = rsqrt(p1); i22 = rsqrt(p2);
+  };
+  __syncthreads();  // the caller's A is complete
+  if (tid < 32) factor3(A[0], A[kWLD], A[kWLD + 1], A[2 * kWLD], A[2 * kWLD + 1], A[2 * kWLD + 2]);
 #pragma unroll 1
   for (int c0 = 0; c0 < n; c0 += 3) {
-    if (c0 >= bnext) { bj++; bnext += B; }
+    if (c0 >= bnext) bnext += B;
     const int rend = min(n, bnext + B);
     const int m = rend - (c0 + 3);  // panel rows below the diagonal block (band only); the right-hand side row is extra
-    __syncthreads();  // the previous step's update is complete
     CTICK(0)
     if (tid < 32) {
-      // warp 0: the 3 x 3 diagonal block in registers (every lane the same values), then one lane per panel row
-      double* D0 = A + c0 * kWLD + c0;
-      const double d00 = D0[0], d10 = D0[kWLD], d11 = D0[kWLD + 1], d20 = D0[2 * kWLD], d21 = D0[2 * kWLD + 1], d22 = D0[2 * kWLD + 2];
-      const double r0 = __drcp_rn(d00);
-      const double m10 = d10 * r0, m20 = d20 * r0;
-      const double p1 = d11 - m10 * d10;
-      const double e21 = d21 - m20 * d10;
-      const double m21 = e21 * __drcp_rn(p1);
-      const double p2 = d22 - m20 * d20 - m21 * e21;
-      const bool pd = d00 > 0.0 && p1 > 0.0 && p2 > 0.0;
-      const double i00 = rsqrt(d00), i11 = rsqrt(p1), i22 = rsqrt(p2);
+      // warp 0: one lane per panel row, then the factor's entries into the matrix
       const double l10 = d10 * i00, l20 = d20 * i00, l21 = e21 * i11;
-      CTICK(1)
       if (pd && tid <= m) {
         const int r = tid < m ? c0 + 3 + tid : n;
         double* Ar = A + r * kWLD + c0;
@@ -166,8 +172,8 @@ __device__ __noinline__ bool cta_chol_solve(WinShared& s, int n, int B, int tid)
         const double x2 = (Ar[2] - x0 * l20 - x1 * l21) * i22;
         Ar[0] = x0; Ar[1] = x1; Ar[2] = x2;
       }
-      __syncwarp();  // every lane has read the diagonal block
       if (tid == 31) {
+        double* D0 = A + c0 * kWLD + c0;
         if (!pd) s.chol_ok = 0;
         D0[0] = d00 * i00;
         D0[kWLD] = l10; D0[kWLD + 1] = p1 * i11;
@@ -179,17 +185,34 @@ __device__ __noinline__ bool cta_chol_solve(WinShared& s, int n, int B, int tid)
     __syncthreads();  // panel complete
     CTICK(3)
     if (!s.chol_ok) return false;  // not positive definite (uniform: the flag was written before the barrier)
-    const int ntri = m * (m + 1) / 2;
+    if (tid < 32) {
+      // warp 0: the next diagonal block (rows c0 + 3 .. c0 + 5, the first three panel rows) with this step's update, and its factor
+      if (c0 + 3 < n) {
+        const double* X = A + (c0 + 3) * kWLD + c0;        // panel rows of the next block: X[r][0..2]
+        const double* Dn = A + (c0 + 3) * kWLD + c0 + 3;   // its diagonal block before the update
+        const double x00 = X[0], x01 = X[1], x02 = X[2];
+        const double x10 = X[kWLD], x11 = X[kWLD + 1], x12 = X[kWLD + 2];
+        const double x20 = X[2 * kWLD], x21 = X[2 * kWLD + 1], x22 = X[2 * kWLD + 2];
+        factor3(Dn[0] - ((x00 * x00 + x01 * x01) + x02 * x02), Dn[kWLD] - ((x10 * x00 + x11 * x01) + x12 * x02),
+                Dn[kWLD + 1] - ((x10 * x10 + x11 * x11) + x12 * x12), Dn[2 * kWLD] - ((x20 * x00 + x21 * x01) + x22 * x02),
+                Dn[2 * kWLD + 1] - ((x20 * x10 + x21 * x11) + x22 * x12), Dn[2 * kWLD + 2] - ((x20 * x20 + x21 * x21) + x22 * x22));
+      }
+    } else {
+      // the other warps: rank-3 update of the band's trailing entries, the next diagonal block excepted (the first six
+      // entries of the triangle: warp 0 forms them in registers)
+      const int ntri = m * (m + 1) / 2;
 #pragma unroll 1
-    for (int idx = tid; idx < ntri + m; idx += kWThreads) {
-      int r, c;
-      if (idx < ntri) { r = c0 + 3 + s.tri[idx][0]; c = c0 + 3 + s.tri[idx][1]; }
-      else { r = n; c = c0 + 3 + idx - ntri; }
-      const double* Xr = A + r * kWLD + c0;
-      const double* Xc = A + c * kWLD + c0;
-      A[r * kWLD + c] -= (Xr[0] * Xc[0] + Xr[1] * Xc[1]) + Xr[2] * Xc[2];
+      for (int idx = 6 + tid - 32; idx < ntri + m; idx += kWThreads - 32) {
+        int r, c;
+        if (idx < ntri) { r = c0 + 3 + s.tri[idx][0]; c = c0 + 3 + s.tri[idx][1]; }
+        else { r = n; c = c0 + 3 + idx - ntri; }
+        const double* Xr = A + r * kWLD + c0;
+        const double* Xc = A + c * kWLD + c0;
+        A[r * kWLD + c] -= (Xr[0] * Xc[0] + Xr[1] * Xc[1]) + Xr[2] * Xc[2];
+      }
     }
     CTICK(4)
+    __syncthreads();  // update complete
   }
   __syncthreads();
   CTICK(5)
@@ -448,7 +471,7 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
   int first = 1, reuse = 0, it = 0, num_invalid = 0, evals = 0;
   int buf = 0;
 #ifdef MML_WIN_DEVPROF
-  long long wtp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, wt0 = clock64();
+  long long wtp[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, wt0 = clock64();
 #endif
 #pragma unroll 1
   for (;;) {
@@ -650,6 +673,7 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
       x_norm = sqrt(wdot2(s.x, s.x, n, lane));
       if (done_after) break;
     }
+    WTICK(8)
     if (!first && radius < 1e-32) break;
     first = 0;
     // ---- next step (with Ceres' handling of invalid steps)
@@ -677,7 +701,9 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
             if (tid < n) s.A[n * kWLD + tid] = s.gs[tid];
             mu_built = mu;
           }
+          WTICK(9)
           const bool solved = cta_chol_solve(s, n, B, tid);
+          WTICK(10)
           mu_built = -1.0;  // the working copy now holds the factor
           if (solved) break;
           mu *= 10.0;
@@ -734,8 +760,8 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
   }
 #endif
   if (rank == 0 && (tid == 0 || tid == kWLidarThreads))
-    printf("win solve tid %d: evals=%d pose=%lld eval=%lld wait=%lld weight=%lld assemble=%lld cluster=%lld totals=%lld feed=%lld cycles\n", tid,
-           evals, wtp[0], wtp[1], wtp[2], wtp[3], wtp[4], wtp[5], wtp[6], wtp[7]);
+    printf("win solve tid %d: evals=%d pose=%lld eval=%lld wait=%lld weight=%lld assemble=%lld cluster=%lld totals=%lld | feed: decide+accept=%lld pre-chol=%lld chol=%lld step+rest=%lld cycles\n", tid,
+           evals, wtp[0], wtp[1], wtp[2], wtp[3], wtp[4], wtp[5], wtp[6], wtp[8], wtp[9], wtp[10], wtp[7]);
 #endif
   // every remote store was completed by the last cluster barrier and all CTAs leave the loop in the same iteration
   if (rank != 0) return;

@@ -1137,6 +1137,8 @@ static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, floa
   };
 
   float cell = cell_hint;
+  if (!(cell > 0.f) && M.auto_cell > 0.f && (long long)m * 4 >= (long long)M.auto_m * 3 && (long long)m * 3 <= (long long)M.auto_m * 4)
+    cell = M.auto_cell;  // same map, a few frames later: the search result does not depend on the cell edge, only its speed
   if (!(cell > 0.f)) {
     // trial resolution from the volume per point, then rescale so that an occupied cell
     // holds ~3 points (feature maps are 1-D / 2-D manifolds: occupancy ~ cell^2)
@@ -1158,6 +1160,8 @@ static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, floa
     const double occ = (double)m / (double)nz;
     static const double target_occ = getenv("MML_CELL_OCC") ? atof(getenv("MML_CELL_OCC")) : 3.0;
     cell = (float)fmin(fmax((double)M.cell * sqrt(target_occ / occ), 0.05), 5.0);
+    M.auto_cell = cell;
+    M.auto_m = m;
   }
   while (!layout(cell)) cell *= 1.25f;
 

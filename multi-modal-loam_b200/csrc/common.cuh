@@ -91,6 +91,10 @@ struct GridMap {
   int dim2[3] = {0, 0, 0};
   DevBuf pts2, cell_start2;
   bool valid = false;
+  // cell edge the occupancy trial chose last time and the point count it chose it for: a rebuild of a map of similar
+  // size (the local map follows the trajectory update by update) skips the trial pass and its host synchronisation
+  float auto_cell = 0.f;
+  int auto_m = 0;
 };
 
 struct EstDev;  // device-side solver state (accumulate.cu)

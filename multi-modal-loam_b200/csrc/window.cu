@@ -26,9 +26,9 @@ int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres,
 int mml_extract_device(mml_ctx* ctx, const float4* xyzi_d, const uint16_t* line_d, const int* scan_off, int n_scans,
                        int n_lines, uint8_t* label_d, bool sequential);
 int mml_split_voxel_capacity();
+int mml_label_compact_device(mml_ctx* ctx, const uint8_t* label_d, int n, int* idx0, int* idx1, int* cnt_d);
 extern "C" int mml_local_map_push_dev(mml_ctx* c, const void* corner_dev, int n_corner, const void* surf_dev, int n_surf, const double* T_wl16,
                                       float leaf_corner, float leaf_surf, int clear_first, int* n_corner_map, int* n_surf_map);
-namespace mml { struct SvChain; }
 int mml_split_voxel_device(mml_ctx* ctx, const float4* pts_d, const float* s_d, const uint8_t* label_d, int n,
                            const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, float4* corner_out,
                            float4* surf_out, int* counts_d, const mml::SvChain* chain = nullptr);
@@ -152,7 +152,7 @@ void mml_window_destroy(mml_ctx* c) {
     cudaStreamDestroy(w->xstream);
     for (int k = 0; k < 2; k++) { cudaEventDestroy(w->xev[k]); cudaEventDestroy(w->xfree[k]); }
   }
-  for (int k = 0; k < 2; k++) { w->x_xyzi[k].release(); w->x_line[k].release(); w->x_s[k].release(); w->x_label[k].release(); w->x_counters[k].release(); }
+  for (int k = 0; k < 2; k++) { w->x_xyzi[k].release(); w->x_line[k].release(); w->x_s[k].release(); w->x_label[k].release(); w->x_counters[k].release(); w->x_idx[k].release(); }
   delete w;
   c->window = nullptr;
 }
@@ -363,7 +363,8 @@ int mml_window_push_frame(mml_ctx* c, const float* corner_xyzi, int n_corner, co
 // an asynchronous copy instead of a synchronisation (the loop reads them after the scan's solve has been awaited).
 static int window_push_scan(mml_ctx* c, const void* xyzi_dev, const void* line_id_dev, const void* s_dev, int n, int n_lines,
                             const double* dR9, const double* dt3, float leaf_corner, float leaf_surf, int max_frames,
-                            int* out_counts, const uint8_t* pre_label, const int* pre_counters, int* flags_async) {
+                            int* out_counts, const uint8_t* pre_label, const int* pre_counters, int* flags_async,
+                            const int* pre_idx = nullptr) {
   if (!c || n < 0) return MML_ERR_INVALID;
   cudaSetDevice(c->device);
   MML_CHECK(window_make_room(c, max_frames));
@@ -383,8 +384,20 @@ static int window_push_scan(mml_ctx* c, const void* xyzi_dev, const void* line_i
   }
   int* cnt = s.cnt.as<int>();  // [n_corner, n_surf, ., ., overflow]: the association and the solve read the counts here
   const bool undist = dR9 && dt3 && s_dev;
-  MML_CHECK(mml_split_voxel_device(c, (const float4*)xyzi_dev, undist ? (const float*)s_dev : nullptr, label_d, n,
-                                   dR9, dt3, leaf_corner, leaf_surf, s.q_corner.as<float4>(), s.q_surf.as<float4>(), cnt));
+  if (pre_idx) {
+    // the label split ran behind the extraction (k_label_compact): the cluster form of the fused undistortion + voxel
+    // filter starts from the compacted indices, eight CTAs per label sharing the float64 slerp
+    const int cap = mml_split_voxel_capacity();
+    mml::SvChain ch;
+    memset(&ch, 0, sizeof(ch));
+    ch.pre_idx[0] = pre_idx; ch.pre_idx[1] = pre_idx + cap; ch.pre_cnt = pre_idx + 2 * cap;
+    MML_CUDA(c, cudaMemsetAsync(cnt + 4, 0, sizeof(int), st));
+    MML_CHECK(mml_split_voxel_device(c, (const float4*)xyzi_dev, undist ? (const float*)s_dev : nullptr, label_d, n,
+                                     dR9, dt3, leaf_corner, leaf_surf, s.q_corner.as<float4>(), s.q_surf.as<float4>(), cnt, &ch));
+  } else {
+    MML_CHECK(mml_split_voxel_device(c, (const float4*)xyzi_dev, undist ? (const float*)s_dev : nullptr, label_d, n,
+                                     dR9, dt3, leaf_corner, leaf_surf, s.q_corner.as<float4>(), s.q_surf.as<float4>(), cnt));
+  }
   int* hf = flags_async ? flags_async : c->pin_flags.as<int>();
   MML_CUDA(c, cudaMemcpyAsync(hf, counters_d, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
   MML_CUDA(c, cudaMemcpyAsync(hf + 4, cnt, 5 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -588,8 +601,16 @@ int mml_odom_run_window(mml_ctx* c, const void* const* xyzi, const void* const* 
     c->counters_alt = w->x_counters[b].as<int>();
     const int rc = mml_extract_device(c, (const float4*)xdv[b], (const uint16_t*)ldv[b], off, 1, n_lines, w->x_label[b].as<uint8_t>(), false);
     c->counters_alt = nullptr;
+    int rc2 = MML_OK;
+    if (rc == MML_OK) {
+      const int cap = mml_split_voxel_capacity();
+      if (w->x_idx[b].reserve(sizeof(int) * (2 * (size_t)cap + 4)) != cudaSuccess) rc2 = MML_ERR_CUDA;
+      int* ix = w->x_idx[b].as<int>();
+      if (rc2 == MML_OK) rc2 = mml_label_compact_device(c, w->x_label[b].as<uint8_t>(), (int)n, ix, ix + cap, ix + 2 * cap);
+    }
     c->stream = keep;
     MML_CHECK(rc);
+    MML_CHECK(rc2);
     MML_CUDA(c, cudaEventRecord(w->xev[b], xs));
     return MML_OK;
   };
@@ -623,7 +644,7 @@ int mml_odom_run_window(mml_ctx* c, const void* const* xyzi, const void* const* 
     MML_CUDA(c, cudaStreamWaitEvent(st, w->xev[b], 0));
     int* flags = c->pin_flags.as<int>() + 16 * b;
     MML_CHECK(window_push_scan(c, xd, ld, sd, n_pts[k], n_lines, dR9, dt3, leaf_corner, leaf_surf, window, nullptr,
-                               w->x_label[b].as<uint8_t>(), w->x_counters[b].as<int>(), flags));
+                               w->x_label[b].as<uint8_t>(), w->x_counters[b].as<int>(), flags, w->x_idx[b].as<int>()));
     MML_CUDA(c, cudaEventRecord(w->xfree[b], st));  // raw scan, labels and counters of this buffer pair are consumed
     const int W = w->n_slots;
     memcpy(hp->state, next, sizeof(next));

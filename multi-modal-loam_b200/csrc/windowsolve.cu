@@ -354,16 +354,17 @@ __global__ void k_win_push(WinDev* wd, const WinPush* push, int* const* cnt_by_s
   __syncthreads();
   const int W_old = wd->W;
   if (drop) {
-    // shift frames 1.. to 0.. (sequential over frames, parallel inside a frame)
-    for (int f = 0; f + 1 < W_old; f++) {
-      for (int i = tid; i < 16; i += blockDim.x) wd->states[f][i] = wd->states[f + 1][i];
-      const unsigned* src = reinterpret_cast<const unsigned*>(&wd->pre[f + 1]);
-      unsigned* dst = reinterpret_cast<unsigned*>(&wd->pre[f]);
-      for (int i = tid; i < (int)(sizeof(mml_preint) / 4); i += blockDim.x) dst[i] = src[i];
-      __syncthreads();
-      if (tid == 0) wd->slot_of[f] = wd->slot_of[f + 1];
-      __syncthreads();
-    }
+    // frames 1.. move to 0..: thread i carries word i of every frame down in frame order, so no two threads touch the
+    // same word and the shift needs no barrier
+    constexpr int kPreWords = (int)(sizeof(mml_preint) / 4);
+    for (int i = tid; i < kPreWords; i += blockDim.x)
+      for (int f = 0; f + 1 < W_old; f++)
+        reinterpret_cast<unsigned*>(&wd->pre[f])[i] = reinterpret_cast<const unsigned*>(&wd->pre[f + 1])[i];
+    if (tid < 16)
+      for (int f = 0; f + 1 < W_old; f++) wd->states[f][tid] = wd->states[f + 1][tid];
+    if (tid == 32)
+      for (int f = 0; f + 1 < W_old; f++) wd->slot_of[f] = wd->slot_of[f + 1];
+    __syncthreads();
   }
   const int fn = W_new - 1;
   for (int i = tid; i < 16; i += blockDim.x) wd->states[fn][i] = push->state[i];
@@ -1025,7 +1026,7 @@ int mml_window_begin_launch(mml_ctx* c, WindowState* w) {
 }
 
 int mml_window_push_launch(mml_ctx* c, WindowState* w, const WinPush* push_dev) {
-  k_win_push<<<1, 128, 0, c->stream>>>(w->dev.as<WinDev>(), push_dev, slot_cnt_table(c, w));
+  k_win_push<<<1, 512, 0, c->stream>>>(w->dev.as<WinDev>(), push_dev, slot_cnt_table(c, w));
   MML_LAUNCHED(c);
   MML_CUDA(c, cudaGetLastError());
   return MML_OK;

@@ -71,6 +71,7 @@ struct WindowState {
   cudaStream_t xstream = nullptr;
   cudaEvent_t xev[2] = {nullptr, nullptr}, xfree[2] = {nullptr, nullptr};
   DevBuf x_xyzi[2], x_line[2], x_s[2], x_label[2], x_counters[2];
+  DevBuf x_idx[2];        // labelled indices compacted behind the extraction: [idx label 1 | idx label 2 | counts(2)]
   WinSlot& frame(int f) { return slot[order[f]]; }
 };
 

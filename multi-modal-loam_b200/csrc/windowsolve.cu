@@ -640,24 +640,16 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
         __syncthreads();
       }
       // the new linearisation: Jacobi-scaled copy, and the regularised copy + right-hand side the factorisation works on
+      // (the diagonal's square root and division are kept out of the row loop: one lane per row would stall its warp)
 #pragma unroll 1
       for (int i = warp; i < n; i += kWWarps) {
         const double si = s.scale[i];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           const int j = lane + 32 * h;
-          if (j < n) {
-            double v = s.Hn[i * kWLD + j] * si * s.scale[j];
+          if (j < n && j != i) {
+            const double v = s.Hn[i * kWLD + j] * si * s.scale[j];
             s.Hs[i * kWLD + j] = v;
-            if (i == j) {
-              const double dg = sqrt(fmin(fmax(v, 1e-6), 1e32));
-              const double g = s.gnew[i] * si;
-              s.diag[i] = dg;
-              s.gs[i] = g;
-              s.grad[i] = g / dg;
-              s.A[n * kWLD + i] = g;
-              v += mu * dg * dg;
-            }
             s.A[i * kWLD + j] = v;
           }
         }
@@ -665,6 +657,17 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
       mu_built = mu;
       const bool better = first || cost < min_cost;
       if (tid < n) {
+        const int i = tid;
+        const double si = s.scale[i];
+        const double v = s.Hn[i * kWLD + i] * si * si;
+        const double dg = sqrt(fmin(fmax(v, 1e-6), 1e32));
+        const double g = s.gnew[i] * si;
+        s.Hs[i * kWLD + i] = v;
+        s.diag[i] = dg;
+        s.gs[i] = g;
+        s.grad[i] = g / dg;
+        s.A[n * kWLD + i] = g;
+        s.A[i * kWLD + i] = v + mu * dg * dg;
         const double xv = first ? s.x[tid] : s.x_cand[tid];
         s.x[tid] = xv;
         if (better) s.x_best[tid] = xv;

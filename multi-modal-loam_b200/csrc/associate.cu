@@ -1032,10 +1032,12 @@ using namespace mml;
 
 // ---------------------------------------------------------------- host side
 constexpr int kCoarseFactor = 4;
-static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, float cell_hint);
+static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, float cell_hint, const float* bbox6);
 int mml_grid_table_sync(mml_ctx* ctx);
 
-int mml_map_set_device(mml_ctx* ctx, int kind, const float4* pts_d, int m, const int* cen3, float cell_hint) {
+// bbox6 (may be NULL): a bounding box of the points the caller already has (min xyz, max xyz; it may be loose): the
+// build then needs no pass over the points and no host synchronisation of its own to size the grid
+int mml_map_set_device(mml_ctx* ctx, int kind, const float4* pts_d, int m, const int* cen3, float cell_hint, const float* bbox6) {
   if (kind < 0 || kind > 3) return mml_fail(ctx, MML_ERR_INVALID, "map kind must be 0..3");
   GridMap& M = ctx->maps[kind];
   M.global = (kind == MML_MAP_CORNER_GLOBAL || kind == MML_MAP_SURF_GLOBAL);
@@ -1044,7 +1046,7 @@ int mml_map_set_device(mml_ctx* ctx, int kind, const float4* pts_d, int m, const
   M.m = m;
   ctx->grid_table_dirty = true;
   int rc = MML_OK;
-  if (m > 0) rc = build_grid(ctx, M, pts_d, m, cell_hint);
+  if (m > 0) rc = build_grid(ctx, M, pts_d, m, cell_hint, bbox6);
   // captured association launches read the descriptors from device memory: keep that copy current
   if (ctx->grid_table.p) { const int rc2 = mml_grid_table_sync(ctx); if (rc == MML_OK) rc = rc2; }
   return rc;
@@ -1074,10 +1076,14 @@ static GridDev grid_dev(const GridMap& M, int kind) {
   return G;
 }
 
-static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, float cell_hint) {
+static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, float cell_hint, const float* bbox6) {
   cudaStream_t st = ctx->stream;
   float mn[3], mx[3];
-  MML_CHECK(mml_bbox_device(ctx, pts_d, m, mn, mx));
+  if (bbox6) {
+    for (int a = 0; a < 3; a++) { mn[a] = bbox6[a]; mx[a] = bbox6[3 + a]; }
+  } else {
+    MML_CHECK(mml_bbox_device(ctx, pts_d, m, mn, mx));
+  }
   const long long kMaxCells = 1ll << 28;
 
   auto layout = [&](float cell) -> bool {  // fills M.{cell,org_d,dim,ncell,k_per_cube,cube_lo}

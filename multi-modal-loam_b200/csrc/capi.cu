@@ -17,7 +17,7 @@ int mml_velo_ring_time_device(mml_ctx* ctx, const float4* pts_d, int n, const fl
                               float* reltime_d);
 int mml_hori_filter_device(mml_ctx* ctx, const uint32_t* off_d, const float* xyz_d, const uint8_t* line_d, int n,
                            uint32_t last_offset, uint8_t* keep_d, float* reltime_d);
-int mml_map_set_device(mml_ctx* ctx, int kind, const float4* pts_d, int m, const int* cen3, float cell_hint);
+int mml_map_set_device(mml_ctx* ctx, int kind, const float4* pts_d, int m, const int* cen3, float cell_hint, const float* bbox6 = nullptr);
 int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres, const double* T_dev,
                          const float* thres_dev, const int* gate, const int* nq_dev, int cap);
 int mml_export_features(mml_ctx* ctx, int kind, int nq, double* out_dev);

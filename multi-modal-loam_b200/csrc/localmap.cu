@@ -8,7 +8,7 @@
 #include "common.cuh"
 
 int mml_voxel_device(mml_ctx* ctx, const float4* pts_d, const int* n_dev, int n_max, float leaf, float4* out_d, int* m_dev);
-int mml_map_set_device(mml_ctx* ctx, int kind, const float4* pts_d, int m, const int* cen3, float cell_hint);
+int mml_map_set_device(mml_ctx* ctx, int kind, const float4* pts_d, int m, const int* cen3, float cell_hint, const float* bbox6 = nullptr);
 
 namespace {
 
@@ -37,6 +37,7 @@ struct LocalMapDev {
   int from_n[2] = {0, 0};
   mml::DevBuf stage, concat, cnt;
   mml::DevBuf pending[2], result[2];  // an update is prepared here and committed only when both kinds succeeded
+  mml::PinBuf pin;                    // sizes and bounding boxes read back once per update
   long long id = 0;  // localMapID
   LocalMapDev() { memset(ring_n, 0, sizeof(ring_n)); }
 };
@@ -67,6 +68,9 @@ int local_map_push_impl(mml_ctx* c, const void* corner, int n_corner, const void
   Pose16 P;
   for (int i = 0; i < 16; i++) P.T[i] = T_wl16[i];
   MML_CUDA(c, L->cnt.reserve(64));
+  MML_CUDA(c, L->pin.reserve(sizeof(int) * 16));
+  int* hp = L->pin.as<int>();
+  bool have[2] = {false, false};
   int m_new[2] = {0, 0};
   for (int k = 0; k < 2; k++) {
     const void* src = k == 0 ? corner : surf;
@@ -89,7 +93,6 @@ int local_map_push_impl(mml_ctx* c, const void* corner, int n_corner, const void
     long long total = keep;
     for (int i = 0; i < kLocalWindow; i++) total += (i == slot) ? n : L->ring_n[k][i];
     if (total > 0x7fffffffLL / 32) return mml_fail(c, MML_ERR_CAPACITY, "local map too large");
-    int m = 0;
     if (total > 0) {
       MML_CUDA(c, L->concat.reserve(sizeof(float4) * (size_t)total));
       MML_CUDA(c, L->result[k].reserve(sizeof(float4) * (size_t)total));
@@ -111,10 +114,22 @@ int local_map_push_impl(mml_ctx* c, const void* corner, int n_corner, const void
       const int tot = (int)total;
       MML_CUDA(c, cudaMemcpyAsync(cnt, &tot, sizeof(int), cudaMemcpyHostToDevice, st));
       MML_CHECK(mml_voxel_device(c, dst, cnt, tot, leaf, L->result[k].as<float4>(), cnt + 1));
-      MML_CUDA(c, cudaMemcpyAsync(&m, cnt + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-      MML_CUDA(c, cudaStreamSynchronize(st));
+      // the size of the filtered map and the filter's bounding box of its input (the centroids lie inside it) come
+      // back together after both kinds have been enqueued: one host wait per update
+      MML_CUDA(c, cudaMemcpyAsync(hp + 8 * k, cnt + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+      MML_CUDA(c, cudaMemcpyAsync(hp + 8 * k + 1, c->vox_bbox.p, 6 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+      have[k] = true;
     }
-    m_new[k] = m;
+  }
+  MML_CUDA(c, cudaStreamSynchronize(st));
+  float bbox[2][6];
+  for (int k = 0; k < 2; k++) {
+    m_new[k] = have[k] ? hp[8 * k] : 0;
+    for (int a = 0; a < 6; a++) {  // order-preserving unsigned encoding of float (geometry.cu f2ord)
+      const unsigned u = (unsigned)hp[8 * k + 1 + a];
+      const unsigned b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+      memcpy(&bbox[k][a], &b, 4);
+    }
   }
   // ---- commit
   for (int k = 0; k < 2; k++) {
@@ -126,13 +141,13 @@ int local_map_push_impl(mml_ctx* c, const void* corner, int n_corner, const void
   L->id++;  // EST.cpp:1640
   // the association's search structures (replace the kd-tree rebuilds at EST.cpp:1159-1167)
   for (int k = 0; k < 2; k++) {
-    const int rc = mml_map_set_device(c, k == 0 ? MML_MAP_CORNER_LOCAL : MML_MAP_SURF_LOCAL, L->from_local[k].as<float4>(), L->from_n[k], nullptr, 0.f);
+    const int rc = mml_map_set_device(c, k == 0 ? MML_MAP_CORNER_LOCAL : MML_MAP_SURF_LOCAL, L->from_local[k].as<float4>(), L->from_n[k], nullptr, 0.f,
+                                      have[k] ? bbox[k] : nullptr);
     if (rc != MML_OK) { drop_local_maps(c); return rc; }  // never leave one kind new and the other stale
   }
   if (n_corner_map) *n_corner_map = m_new[0];
   if (n_surf_map) *n_surf_map = m_new[1];
-  MML_CUDA(c, cudaStreamSynchronize(st));
-  return MML_OK;
+  return MML_OK;  // what follows on the context's stream is ordered behind the update
 }
 
 }  // namespace
@@ -144,7 +159,7 @@ void mml_local_map_destroy(mml_ctx* c) {
     for (int i = 0; i < kLocalWindow; i++) L->ring[k][i].release();
     L->from_local[k].release(); L->pending[k].release(); L->result[k].release();
   }
-  L->stage.release(); L->concat.release(); L->cnt.release();
+  L->stage.release(); L->concat.release(); L->cnt.release(); L->pin.release();
   delete L;
   c->local_map = nullptr;
 }

@@ -75,6 +75,9 @@ struct WinShared {
   double cost_new, cost_imu, min_cost_out;
   int gidx[kMaxWindow - 1][30];           // factor column -> unknown (parameter order)
   int lidx[kMaxWindow - 1][kWinN];        // position -> factor column, or -1
+  double fac[2][8];                         // factor of a step's 3 x 3 diagonal block: 1 / L[j][j] (3), L[1][0], L[2][0], L[2][1], positive-definite flag
+                                            // (two copies by step parity: warp 0 publishes the next step's while the other warps still read this one's)
+  double X[28][3];                          // the step's solved panel rows (list order: band rows, then the right-hand side)
   int nnz, chol_ok;
   unsigned short nz[kWinN * (kWinN + 1) / 2];  // upper-triangle positions some factor touches: (row << 8) | column
   unsigned char tri[27 * 28 / 2][2];        // (row, column) of the idx-th entry of a lower triangle, row-major
@@ -130,28 +133,43 @@ __device__ long long g_cholprof[8];
 #else
 #define CTICK(k)
 #endif
+// 1 / sqrt(x) for a normal positive x: the hardware seed (rsqrt.approx.f64, relative error < 2^-22) and one third-order
+// correction, the sequence rsqrt() itself runs, without its branch to the special-case path: three calls in a row
+// overlap instead of queueing behind each other's branch. Non-positive input gives NaN / inf (callers test the sign).
+__device__ __forceinline__ double rsqrt_normal(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(x, -(y * y), 1.0);
+  return fma(fma(e, 0.375, 0.5), y * e, y);
+}
+
 __device__ __noinline__ bool cta_chol_solve(WinShared& s, int n, int B, int tid) {
   double* A = s.A;
 #if defined(MML_WIN_DEVPROF) && MML_WIN_DEVPROF >= 2
   long long ct0 = clock64();
 #endif
-  if (tid == 0) s.chol_ok = 1;
+  int par = 0;
   int bnext = B;  // first column of the frame block after the one c0 lies in (no division in the loop)
   // the 3 x 3 diagonal block of the current step, factored one step AHEAD by warp 0 (registers, every lane the same
   // values) while the other warps apply the previous step's rank-3 update: the dependent chain of the factor (two
   // reciprocals, three reciprocal square roots) no longer sits between the two barriers of a step
-  double d00 = 0, d10 = 0, d20 = 0, p1 = 0, e21 = 0, p2 = 0, i00 = 0, i11 = 0, i22 = 0;
+  double d10 = 0, d20 = 0, i00 = 0, i11 = 0, i22 = 0, l21 = 0;
+  double q[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   bool pd = true;
+  // Factor of a 3 x 3 block through its leading minors: pivots a00, det2 / a00, det3 / det2, so the three reciprocal
+  // square roots (of a00, det2, det3) are independent instead of waiting for each other through two reciprocals
   auto factor3 = [&](double a00, double a10, double a11, double a20, double a21, double a22) {
-    d00 = a00; d10 = a10; d20 = a20;
-    const double r0 = __drcp_rn(a00);
-    const double m10 = a10 * r0, m20 = a20 * r0;
-    p1 = a11 - m10 * a10;
-    e21 = a21 - m20 * a10;
-    const double m21 = e21 * __drcp_rn(p1);
-    p2 = a22 - m20 * a20 - m21 * e21;
-    pd = a00 > 0.0 && p1 > 0.0 && p2 > 0.0;
-    i00 = rsqrt(a00); i11 = rsqrt(p1); i22 = rsqrt(p2);
+    d10 = a10; d20 = a20;
+    const double c21 = a00 * a21 - a20 * a10;
+    const double c20 = a11 * a20 - a10 * a21;
+    const double det2 = a00 * a11 - a10 * a10;
+    const double det3 = a22 * det2 - (a21 * c21 + a20 * c20);
+    pd = a00 > 0.0 && det2 > 0.0 && det3 > 0.0;
+    const double r0 = rsqrt_normal(a00), r1 = rsqrt_normal(det2), r2 = rsqrt_normal(det3);
+    i00 = r0;                  // 1 / L00
+    i11 = (a00 * r0) * r1;     // 1 / L11 = sqrt(a00 / det2)
+    i22 = (det2 * r1) * r2;    // 1 / L22 = sqrt(det2 / det3)
+    l21 = c21 * (r0 * r1);     // L21 = (c21 / a00) / L11
   };
   __syncthreads();  // the caller's A is complete
   if (tid < 32) factor3(A[0], A[kWLD], A[kWLD + 1], A[2 * kWLD], A[2 * kWLD + 1], A[2 * kWLD + 2]);
@@ -161,58 +179,71 @@ __device__ __noinline__ bool cta_chol_solve(WinShared& s, int n, int B, int tid)
     const int rend = min(n, bnext + B);
     const int m = rend - (c0 + 3);  // panel rows below the diagonal block (band only); the right-hand side row is extra
     CTICK(0)
-    if (tid < 32) {
-      // warp 0: one lane per panel row, then the factor's entries into the matrix
-      const double l10 = d10 * i00, l20 = d20 * i00, l21 = e21 * i11;
-      if (pd && tid <= m) {
-        const int r = tid < m ? c0 + 3 + tid : n;
-        double* Ar = A + r * kWLD + c0;
-        const double x0 = Ar[0] * i00;
-        const double x1 = (Ar[1] - x0 * l10) * i11;
-        const double x2 = (Ar[2] - x0 * l20 - x1 * l21) * i22;
-        Ar[0] = x0; Ar[1] = x1; Ar[2] = x2;
-      }
-      if (tid == 31) {
-        double* D0 = A + c0 * kWLD + c0;
-        if (!pd) s.chol_ok = 0;
-        D0[0] = d00 * i00;
-        D0[kWLD] = l10; D0[kWLD + 1] = p1 * i11;
-        D0[2 * kWLD] = l20; D0[2 * kWLD + 1] = l21; D0[2 * kWLD + 2] = p2 * i22;
-        s.tv[c0] = i00; s.tv[c0 + 1] = i11; s.tv[c0 + 2] = i22;  // 1 / L[j][j] for the back substitution
-      }
+    const double l10 = d10 * i00, l20 = d20 * i00;  // (warp 0 only: the other warps hold zeros)
+    if (tid == 31) {
+      // warp 0 publishes the block's factor: into the matrix, and the six numbers a panel row needs
+      double* D0 = A + c0 * kWLD + c0;
+      double* fac = s.fac[par];
+      fac[0] = i00; fac[1] = i11; fac[2] = i22; fac[3] = l10; fac[4] = l20; fac[5] = l21; fac[6] = pd ? 1.0 : 0.0;
+      D0[kWLD] = l10; D0[2 * kWLD] = l20; D0[2 * kWLD + 1] = l21;  // (the diagonal of the factor lives in tv as reciprocals)
+      s.tv[c0] = i00; s.tv[c0 + 1] = i11; s.tv[c0 + 2] = i22;  // 1 / L[j][j] for the back substitution
     }
     CTICK(2)
-    __syncthreads();  // panel complete
+    __syncthreads();  // factor published, previous update complete
     CTICK(3)
-    if (!s.chol_ok) return false;  // not positive definite (uniform: the flag was written before the barrier)
+    const double* fac = s.fac[par];
+    if (fac[6] == 0.0) return false;  // not positive definite (uniform: the flag was written before the barrier)
+    par ^= 1;
     if (tid < 32) {
-      // warp 0: the next diagonal block (rows c0 + 3 .. c0 + 5, the first three panel rows) with this step's update, and its factor
+      // warp 0: the next diagonal block. Its three panel rows are solved here in registers (the other warps solve them
+      // too, into the side buffer), then the block takes this step's update and is factored: the chain a step waits for
+      if (tid == 0 && c0 > 0) {  // the previous step's solved rows of this block, in place (read by the back substitution only)
+        double* Xp = A + c0 * kWLD + c0 - 3;
+        Xp[0] = q[0]; Xp[1] = q[1]; Xp[2] = q[2];
+        Xp[kWLD] = q[3]; Xp[kWLD + 1] = q[4]; Xp[kWLD + 2] = q[5];
+        Xp[2 * kWLD] = q[6]; Xp[2 * kWLD + 1] = q[7]; Xp[2 * kWLD + 2] = q[8];
+      }
       if (c0 + 3 < n) {
-        const double* X = A + (c0 + 3) * kWLD + c0;        // panel rows of the next block: X[r][0..2]
+        const double* X = A + (c0 + 3) * kWLD + c0;        // rows of the next block in this step's columns, not yet solved
         const double* Dn = A + (c0 + 3) * kWLD + c0 + 3;   // its diagonal block before the update
-        const double x00 = X[0], x01 = X[1], x02 = X[2];
-        const double x10 = X[kWLD], x11 = X[kWLD + 1], x12 = X[kWLD + 2];
-        const double x20 = X[2 * kWLD], x21 = X[2 * kWLD + 1], x22 = X[2 * kWLD + 2];
+        const double x00 = X[0] * i00, x10 = X[kWLD] * i00, x20 = X[2 * kWLD] * i00;
+        const double x01 = (X[1] - x00 * l10) * i11, x11 = (X[kWLD + 1] - x10 * l10) * i11, x21 = (X[2 * kWLD + 1] - x20 * l10) * i11;
+        const double x02 = (X[2] - x00 * l20 - x01 * l21) * i22, x12 = (X[kWLD + 2] - x10 * l20 - x11 * l21) * i22,
+                     x22 = (X[2 * kWLD + 2] - x20 * l20 - x21 * l21) * i22;
         factor3(Dn[0] - ((x00 * x00 + x01 * x01) + x02 * x02), Dn[kWLD] - ((x10 * x00 + x11 * x01) + x12 * x02),
                 Dn[kWLD + 1] - ((x10 * x10 + x11 * x11) + x12 * x12), Dn[2 * kWLD] - ((x20 * x00 + x21 * x01) + x22 * x02),
                 Dn[2 * kWLD + 1] - ((x20 * x10 + x21 * x11) + x22 * x12), Dn[2 * kWLD + 2] - ((x20 * x20 + x21 * x21) + x22 * x22));
+        // those rows of the factor go into the matrix after the NEXT barrier: the panel threads are still reading them raw
+        q[0] = x00; q[1] = x01; q[2] = x02; q[3] = x10; q[4] = x11; q[5] = x12; q[6] = x20; q[7] = x21; q[8] = x22;
       }
     } else {
-      // the other warps: rank-3 update of the band's trailing entries, the next diagonal block excepted (the first six
-      // entries of the triangle: warp 0 forms them in registers)
+      // the other warps: one thread per panel row (forward substitution against the published block; solved rows into
+      // the side buffer, and in place except the three rows warp 0 is reading), then the rank-3 update of the band's
+      // trailing entries, the next diagonal block excepted (the first six entries of the triangle)
+      const int t = tid - 32;
+      if (t <= m) {
+        const int r = t < m ? c0 + 3 + t : n;
+        double* Ar = A + r * kWLD + c0;
+        const double f0 = fac[0], f1 = fac[1], f2 = fac[2], g10 = fac[3], g20 = fac[4], g21 = fac[5];
+        const double x0 = Ar[0] * f0;
+        const double x1 = (Ar[1] - x0 * g10) * f1;
+        const double x2 = (Ar[2] - x0 * g20 - x1 * g21) * f2;
+        s.X[t][0] = x0; s.X[t][1] = x1; s.X[t][2] = x2;
+        if (t >= 3 || t == m) { Ar[0] = x0; Ar[1] = x1; Ar[2] = x2; }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(kWThreads - 32) : "memory");  // panel complete (warps 1 .. 10)
       const int ntri = m * (m + 1) / 2;
 #pragma unroll 1
-      for (int idx = 6 + tid - 32; idx < ntri + m; idx += kWThreads - 32) {
-        int r, c;
-        if (idx < ntri) { r = c0 + 3 + s.tri[idx][0]; c = c0 + 3 + s.tri[idx][1]; }
-        else { r = n; c = c0 + 3 + idx - ntri; }
-        const double* Xr = A + r * kWLD + c0;
-        const double* Xc = A + c * kWLD + c0;
-        A[r * kWLD + c] -= (Xr[0] * Xc[0] + Xr[1] * Xc[1]) + Xr[2] * Xc[2];
+      for (int idx = 6 + t; idx < ntri + m; idx += kWThreads - 32) {
+        int i, j, r;
+        if (idx < ntri) { i = s.tri[idx][0]; j = s.tri[idx][1]; r = c0 + 3 + i; }
+        else { i = m; j = idx - ntri; r = n; }
+        const double* Xr = s.X[i];
+        const double* Xc = s.X[j];
+        A[r * kWLD + c0 + 3 + j] -= (Xr[0] * Xc[0] + Xr[1] * Xc[1]) + Xr[2] * Xc[2];
       }
     }
     CTICK(4)
-    __syncthreads();  // update complete
   }
   __syncthreads();
   CTICK(5)

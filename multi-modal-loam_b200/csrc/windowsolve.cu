@@ -78,8 +78,8 @@ struct WinShared {
   double fac[2][8];                         // factor of a step's 3 x 3 diagonal block: 1 / L[j][j] (3), L[1][0], L[2][0], L[2][1], positive-definite flag
                                             // (two copies by step parity: warp 0 publishes the next step's while the other warps still read this one's)
   double X[28][3];                          // the step's solved panel rows (list order: band rows, then the right-hand side)
-  int nnz, chol_ok;
-  unsigned short nz[kWinN * (kWinN + 1) / 2];  // upper-triangle positions some factor touches: (row << 8) | column
+  int chol_ok, ntile;
+  unsigned short tl[(kWinN / 3) * (kWinN / 3 + 1) / 2];  // 3 x 3 tiles of the upper triangle some factor touches: (tile row << 8) | tile column
   unsigned char tri[27 * 28 / 2][2];        // (row, column) of the idx-th entry of a lower triangle, row-major
   int pos[kWinN], unpos[kWinN];
   int total_inner_out, evals_out;
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
     s.pos[g] = ps;
     s.unpos[ps] = g;
   }
-  if (tid == 0) { s.cost_imu = 0.0; s.nnz = 0; }
+  if (tid == 0) { s.cost_imu = 0.0; s.ntile = 0; }
 #pragma unroll 1
   for (int i = tid; i < kWinN * kWLD; i += kWThreads) s.Hn[i] = 0.0;
   __syncthreads();
@@ -479,16 +479,21 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
     s.lidx[fi][s.pos[s.gidx[fi][col]]] = col;
   }
   __syncthreads();
-  // entries of the normal equations that are re-formed by every evaluation: those an IMU factor couples, and the
-  // pose blocks the lidar terms add to; everything else stays zero
+  // entries of the normal equations that are re-formed by every evaluation, as 3 x 3 tiles (the parameters come in
+  // triples: P, log Q, V, bg, ba of a frame occupy five consecutive tiles): those an IMU factor couples, and the pose
+  // tiles the lidar terms add to; everything else stays zero
+  {
+    const int nt = n / 3;
 #pragma unroll 1
-  for (int i = warp; i < n; i += kWWarps)
-#pragma unroll 1
-    for (int j = i + lane; j < n; j += 32) {
+    for (int t = tid; t < nt * nt; t += kWThreads) {
+      const int ti = t / nt, tj = t - nt * ti;
+      if (tj < ti) continue;
+      const int i = 3 * ti, j = 3 * tj;
       bool hit = i / B == j / B && i % B < 6 && j % B < 6;
       for (int fi = 0; fi < nf; fi++) hit = hit || (s.lidx[fi][i] >= 0 && s.lidx[fi][j] >= 0);
-      if (hit) s.nz[atomicAdd(&s.nnz, 1)] = (unsigned short)((i << 8) | j);
+      if (hit) s.tl[atomicAdd(&s.ntile, 1)] = (unsigned short)((ti << 8) | tj);
     }
+  }
   // the frame whose lidar terms this CTA evaluates
   const int fr = (int)rank % W, sub = (int)rank / W, ncta_f = (kWCluster - fr + W - 1) / W;
   const int slot = wd->slot_of[fr];
@@ -570,26 +575,38 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
     }
     __syncthreads();
     WTICK(3)
-    // the factors' J^T J and J^T r into the dense system (upper triangle formed, mirrored), frame-major positions
-#pragma unroll 1
-    for (int e = tid; e < s.nnz; e += kWThreads) {
-      const int gi = s.nz[e] >> 8, gj = s.nz[e] & 255;
-      double v = 0;
+    // the factors' J^T J and J^T r into the dense system, frame-major positions: one thread per 3 x 3 tile of the upper
+    // triangle (six columns of Jw read for nine entries), mirrored; J^T r and the IMU cost on threads from the other end
+    if (tid < s.ntile) {
+      const int ti = s.tl[tid] >> 8, tj = s.tl[tid] & 255;
+      double v00 = 0, v01 = 0, v02 = 0, v10 = 0, v11 = 0, v12 = 0, v20 = 0, v21 = 0, v22 = 0;
       for (int fi = 0; fi < nf; fi++) {
-        const int li = s.lidx[fi][gi], lj = s.lidx[fi][gj];
+        const int li = s.lidx[fi][3 * ti], lj = s.lidx[fi][3 * tj];
         if (li < 0 || lj < 0) continue;
         const double* a = s.Jw[fi][li];
         const double* b = s.Jw[fi][lj];
-        double t0 = 0, t1 = 0;
 #pragma unroll
-        for (int k = 0; k < 14; k += 2) { t0 += a[k] * b[k]; t1 += a[k + 1] * b[k + 1]; }
-        v += (t0 + a[14] * b[14]) + t1;
+        for (int k = 0; k < 15; k++) {
+          const double a0 = a[k], a1 = a[15 + k], a2 = a[30 + k], b0 = b[k], b1 = b[15 + k], b2 = b[30 + k];
+          v00 += a0 * b0; v01 += a0 * b1; v02 += a0 * b2;
+          v10 += a1 * b0; v11 += a1 * b1; v12 += a1 * b2;
+          v20 += a2 * b0; v21 += a2 * b1; v22 += a2 * b2;
+        }
       }
-      s.Hn[gi * kWLD + gj] = v;
-      s.Hn[gj * kWLD + gi] = v;
+      double* Hu = s.Hn + (3 * ti) * kWLD + 3 * tj;   // tile (ti, tj)
+      double* Hl = s.Hn + (3 * tj) * kWLD + 3 * ti;   // its mirror image
+      Hu[0] = v00; Hu[1] = v01; Hu[2] = v02;
+      Hu[kWLD] = v10; Hu[kWLD + 1] = v11; Hu[kWLD + 2] = v12;
+      Hu[2 * kWLD] = v20; Hu[2 * kWLD + 1] = v21; Hu[2 * kWLD + 2] = v22;
+      if (ti != tj) {
+        Hl[0] = v00; Hl[1] = v10; Hl[2] = v20;
+        Hl[kWLD] = v01; Hl[kWLD + 1] = v11; Hl[kWLD + 2] = v21;
+        Hl[2 * kWLD] = v02; Hl[2 * kWLD + 1] = v12; Hl[2 * kWLD + 2] = v22;
+      }
     }
-    if (tid < n) {
-      const int gi = tid;
+    const int gt = kWThreads - 2 - tid;
+    if (gt >= 0 && gt < n) {
+      const int gi = gt;
       double v = 0;
       for (int fi = 0; fi < nf; fi++) {
         const int li = s.lidx[fi][gi];

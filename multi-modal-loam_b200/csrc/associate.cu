@@ -325,6 +325,108 @@ __device__ bool knn5_grid_packed(const GridDev& G, float qx, float qy, float qz,
   return r.loc[4] >= 0 && knnp_d(r, 4) < thres;
 }
 
+__device__ __forceinline__ void scan_range_p2(const float4* __restrict__ pts, const int* __restrict__ cell_start, int c0, int c1, float qx,
+                                             float qy, float qz, KnnP& r) {
+  const int s = __ldg(cell_start + c0), e = __ldg(cell_start + c1 + 1);
+  for (int k = s; k < e; k++) {
+    const float4 p = __ldg(pts + k);
+    const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+    const float d = (dx * dx + dy * dy) + dz * dz;
+    knnp_push(r, d, __float_as_int(p.w), k);
+  }
+}
+
+// knn5_grid_packed for search radii that span many fine cells (MML_TWO_LEVEL_MIN_SHELLS shells or more; chosen by the
+// host, k_knn_walk<true>): two levels like the group search. The first
+// kFineShellsP shells on the fine cells; a query still open (displaced from the map, or with no neighbours in reach)
+// starts over on the coarse cells, whose shells cover `coarse` times the distance per row visited, bounded by the 5th
+// distance the fine level found. One copy of the shell walk in the instruction stream, run once per level.
+// Returns 0: no acceptable list, 1: the list in `r` indexes the fine copy of the points (G.pts), 3: the coarse copy
+// (G.pts2).
+#ifndef MML_FINE_SHELLS_P
+#define MML_FINE_SHELLS_P 2
+#endif
+#ifndef MML_TWO_LEVEL_MIN_SHELLS
+#define MML_TWO_LEVEL_MIN_SHELLS 12
+#endif
+__device__ int knn5_grid_packed2(const GridDev& G, float qx, float qy, float qz, float thres, KnnP& r) {
+  knnp_init(r);
+  int c[3], lo[3], hi[3], cube;
+  if (!locate(G, qx, qy, qz, c, lo, hi, cube)) return 0;
+  if (G.global) {
+    if (!(__ldg(G.cube_count + cube) > G.min_cube_pts)) return 0;
+  } else {
+    if (!(G.m > G.min_local_pts)) return 0;
+  }
+  const int rmax = (int)ceilf(sqrtf(thres) / G.cell) + 1;
+  const bool two_level = G.pts2 != nullptr && rmax >= MML_TWO_LEVEL_MIN_SHELLS;
+  float prune = INFINITY;
+  int lvl = 0;
+#pragma unroll 1
+  for (;; lvl++) {
+    const int f = lvl == 0 ? 1 : G.coarse;
+    const float4* __restrict__ pts = lvl == 0 ? G.pts : G.pts2;
+    const int* __restrict__ cell_start = lvl == 0 ? G.cell_start : G.cell_start2;
+    const int dim0 = lvl == 0 ? G.dim[0] : G.dim2[0], dim1 = lvl == 0 ? G.dim[1] : G.dim2[1];
+    const float cellf = G.cell * (float)f;
+    const float cell2 = cellf * cellf;
+    const int cx = c[0] / f, cy = c[1] / f, cz = c[2] / f;
+    const int lox = lo[0] / f, loy = lo[1] / f, loz = lo[2] / f, hix = hi[0] / f, hiy = hi[1] / f, hiz = hi[2] / f;
+    const int last = lvl == 0 ? (two_level ? MML_FINE_SHELLS_P : rmax) : (int)ceilf(sqrtf(thres) / cellf) + 1;
+    // position of the query inside its (possibly clamped) cell of this level, in cells
+    const double inv_l = G.inv_cell / (double)f;
+    const float fx = (float)(((double)qx - G.org[0]) * inv_l - (double)cx);
+    const float fy = (float)(((double)qy - G.org[1]) * inv_l - (double)cy);
+    const float fz = (float)(((double)qz - G.org[2]) * inv_l - (double)cz);
+    bool done = false;
+    for (int rr = 1; rr <= last; rr++) {
+      // ring order: |dz| + |dy| ascending puts the nearest rows first, so the bound tightens before the far rows are tested
+      for (int sum = 0; sum <= 2 * rr; sum++) {
+        for (int adz = 0; adz <= min(sum, rr); adz++) {
+          const int ady = sum - adz;
+          if (ady > rr) continue;
+          for (int sz = (adz ? -1 : 1); sz <= 1; sz += 2) {
+            for (int sy = (ady ? -1 : 1); sy <= 1; sy += 2) {
+              const int dz = sz * adz, dy = sy * ady;
+              const int z = cz + dz, y = cy + dy;
+              if (z < loz || z > hiz || y < loy || y > hiy) continue;
+              const float gy = axis_gap(fy, dy), gz = axis_gap(fz, dz);
+              const float row2 = (gy * gy + gz * gz) * cell2;
+              const float bound = fminf(knnp_d(r, 4), prune);  // +inf until five candidates have been seen
+              if (row2 > bound) continue;
+              const int row = (z * dim1 + y) * dim0;
+              const bool full = (rr == 1) || adz == rr || ady == rr;
+              if (full) {
+                const int x0 = max(cx - rr, lox), x1 = min(cx + rr, hix);
+                if (x0 <= x1) scan_range_p2(pts, cell_start, row + x0, row + x1, qx, qy, qz, r);
+              } else {
+                const int xa = cx - rr, xb = cx + rr;
+                const float ga = axis_gap(fx, -rr), gb = axis_gap(fx, rr);
+                if (xa >= lox && row2 + ga * ga * cell2 <= bound) scan_range_p2(pts, cell_start, row + xa, row + xa, qx, qy, qz, r);
+                if (xb <= hix && row2 + gb * gb * cell2 <= fminf(knnp_d(r, 4), prune))
+                  scan_range_p2(pts, cell_start, row + xb, row + xb, qx, qy, qz, r);
+              }
+            }
+          }
+        }
+      }
+      // nothing left inside the searchable block of cells
+      if (cx - rr < lox && cx + rr > hix && cy - rr < loy && cy + rr > hiy && cz - rr < loz && cz + rr > hiz) { done = true; break; }
+      const float reach = fmaxf((float)rr * cellf - 1e-3f, 0.f);
+      const float reach2 = reach * reach;
+      if (r.loc[4] >= 0 && knnp_d(r, 4) <= reach2) { done = true; break; }
+      if (reach2 >= thres) { done = true; break; }
+    }
+    if (done || !two_level || lvl == 1) break;
+    // the coarse level starts over (its list indexes another copy of the points); five points found on the fine level
+    // already bound the 5th distance
+    if (r.loc[4] >= 0) prune = knnp_d(r, 4);
+    knnp_init(r);
+  }
+  if (!(r.loc[4] >= 0 && knnp_d(r, 4) < thres)) return 0;
+  return lvl == 0 ? 1 : 3;
+}
+
 // checkLocalizability (EST.cpp:536-565) on the plane association's own statistics: the last CTA leaves the smallest
 // singular value of the stacked normals next to the moments (slot 7 of the plane block of assoc_stats), so the
 // solve does not spend its tail on a serial 3x3 eigen-solve. Called by one thread after the moments are final.
@@ -355,7 +457,7 @@ struct AssocArgs {
   // neighbours' positions in the cell-sorted point array and a status; the fit kernel (k_associate<KIND, true>)
   // picks them up. pre_map = index (0 global / 1 local) of the map that was searched.
   int* pre_loc;             // [nq][5]
-  int* pre_status;          // [nq]: -1 no search (query outside the grid / NaN), 0 no 5 neighbours inside thres,
+  int* pre_status;          // [nq]: -1 no search (query outside the grid / NaN), 0 no 5 neighbours inside thres, 1 / 3 found (pre_loc indexes the fine / coarse copy),
                             //        1 found, 2 undecided (the fit kernel searches itself)
   int pre_map;
   double T[16];
@@ -433,6 +535,7 @@ __device__ bool fit_plane(const float4* pts, const KnnT& r, float sx, float sy, 
 // Map-sized query sets (S4 / S5) run the neighbour search and the fit as two kernels: the search keeps 56 registers
 // (the fused kernel: 72 + 248 B of stack for the float64 QR), the fit runs with every lane busy, and the pair is
 // 12 % faster than the fused kernel at 1.05 M queries (0.685 vs 0.776 ms, profiles/r2_s4_knn_experiments.txt).
+template <bool TWO>
 __global__ void __launch_bounds__(128) k_knn_walk(AssocArgs A) {
   const int i = blockIdx.x * 128 + threadIdx.x;
   if (i >= A.nq) return;
@@ -449,8 +552,8 @@ __global__ void __launch_bounds__(128) k_knn_walk(AssocArgs A) {
   int status = -1;
   if (in_grid && finite) {
     KnnP r;
-    status = knn5_grid_packed(G, sel[0], sel[1], sel[2], A.thres, r) ? 1 : 0;
-    if (status == 1) {
+    status = TWO ? knn5_grid_packed2(G, sel[0], sel[1], sel[2], A.thres, r) : (knn5_grid_packed(G, sel[0], sel[1], sel[2], A.thres, r) ? 1 : 0);
+    if (status != 0) {
 #pragma unroll
       for (int k = 0; k < 5; k++) A.pre_loc[5 * (size_t)i + k] = r.loc[k];
     }
@@ -515,12 +618,13 @@ __global__ void __launch_bounds__(128) k_associate(AssocArgs A) {
         const GridDev& G = A.G[mp];
         if (!G.valid) continue;
         bool have;
-        int pre = 2;
+        int pre = 2;  // 2: not searched yet; else the walk's verdict (0 none, 1 fine copy, 3 coarse copy; -1 outside)
         if (PRE && mp == A.pre_map) pre = A.pre_status[i];
         if (pre == 2) {
           have = knn5_grid_packed(G, sel[0], sel[1], sel[2], thres, r);
+          pre = have ? 1 : 0;
         } else {
-          have = pre == 1;
+          have = pre == 1 || pre == 3;
           if (have) {
 #pragma unroll
             for (int k = 0; k < 5; k++) r.loc[k] = A.pre_loc[5 * (size_t)i + k];
@@ -529,7 +633,7 @@ __global__ void __launch_bounds__(128) k_associate(AssocArgs A) {
         if (!have) continue;
         if (KIND == 0) {
           float a[3], b[3];
-          if (!fit_line(G.pts, r, a, b)) continue;
+          if (!fit_line(pre == 3 ? G.pts2 : G.pts, r, a, b)) continue;
           f1 = make_float4(a[0], a[1], a[2], b[0]);
           f2 = make_float4(b[1], b[2], 0.f, 0.f);
           // Estimator.h:71-83 FeatureLine::ComputeError at the association pose
@@ -549,7 +653,7 @@ __global__ void __launch_bounds__(128) k_associate(AssocArgs A) {
           found = 1;
         } else {
           float nrm[3], dist;
-          if (!fit_plane(G.pts, r, sel[0], sel[1], sel[2], nrm, &dist)) continue;
+          if (!fit_plane(pre == 3 ? G.pts2 : G.pts, r, sel[0], sel[1], sel[2], nrm, &dist)) continue;
           f1 = make_float4(sel[0], sel[1], sel[2], dist);
           f2 = make_float4(nrm[0], nrm[1], nrm[2], 0.f);
           double e[3];
@@ -1274,7 +1378,12 @@ int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres,
     A.pre_status = pb.as<int>() + 5 * (size_t)nq;
     A.pre_map = A.G[0].valid ? 0 : 1;
     if (A.G[A.pre_map].valid) {
-      k_knn_walk<<<grid, 128, 0, ctx->stream>>>(A);
+      // search radii spanning many fine cells (the first outer iterations of a scan-to-map Estimate: thres 25, 10):
+      // the two-level walk, which sends displaced queries to the coarse cells after two fine shells
+      const GridDev& Gw = A.G[A.pre_map];
+      const bool two = Gw.pts2 != nullptr && (int)ceilf(sqrtf(thres) / Gw.cell) + 1 >= MML_TWO_LEVEL_MIN_SHELLS;
+      if (two) k_knn_walk<true><<<grid, 128, 0, ctx->stream>>>(A);
+      else k_knn_walk<false><<<grid, 128, 0, ctx->stream>>>(A);
       MML_LAUNCHED(ctx);
       if (kind == 0) k_associate<0, true><<<grid, 128, 0, ctx->stream>>>(A);
       else k_associate<1, true><<<grid, 128, 0, ctx->stream>>>(A);

@@ -632,8 +632,10 @@ def test_map_sized_association_240k_both_kinds(ctx, mm, orc, synth, kind, thres)
     _cmp_features(f, r, kind)
 
 
-def test_map_sized_association_global_cubes(ctx, mm, orc, synth):
-    """Global kinds (50 m cube rule) at map size: warps whose queries straddle two cubes take the per-thread search."""
+@pytest.mark.parametrize("thres", [1.0, 25.0])
+def test_map_sized_association_global_cubes(ctx, mm, orc, synth, thres):
+    """Global kinds (50 m cube rule) at map size, short and long search radii (the long one takes the two-level walk:
+    fine shells, then the coarse cells of the query's own cube block)."""
     so, co = synth.tiled_feature_map(600_000, 30_000, tiles=(2, 2, 1), seed=1005)
     ctx.map_set(mm.MAP_CORNER_LOCAL, np.zeros((0, 4), np.float32)); ctx.map_set(mm.MAP_SURF_LOCAL, np.zeros((0, 4), np.float32))
     ctx.map_set(mm.MAP_CORNER_GLOBAL, co); ctx.map_set(mm.MAP_SURF_GLOBAL, so)
@@ -641,8 +643,9 @@ def test_map_sized_association_global_cubes(ctx, mm, orc, synth):
     om.set(orc.SURF_GLOBAL, so)
     T = synth.s1_offset_pose()
     q = synth.queries_from_map(so, 100_000, np.eye(4), seed=77)
-    f, n, M, nn = ctx.associate(1, q, T, 1.0)
-    r, rn, rM, rnn = om.associate_plane(q, T, 1.0)
+    q[:3000, :3] += np.random.default_rng(6).normal(0, 0.8, (3000, 3)).astype(np.float32)  # off the surfaces
+    f, n, M, nn = ctx.associate(1, q, T, thres)
+    r, rn, rM, rnn = om.associate_plane(q, T, thres)
     assert n == rn and n > 50_000
     _cmp_features(f, r, 1)
     ctx.map_set(mm.MAP_CORNER_GLOBAL, np.zeros((0, 4), np.float32)); ctx.map_set(mm.MAP_SURF_GLOBAL, np.zeros((0, 4), np.float32))

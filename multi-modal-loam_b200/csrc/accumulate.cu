@@ -756,6 +756,9 @@ int mml_estimate_device(mml_ctx* ctx, const int* cnt_dev, int cap_corner, int ca
   MML_CUDA(ctx, ctx->assoc_stats.reserve(512));
   MML_CUDA(ctx, ctx->f_line.reserve(sizeof(float4) * 3 * (size_t)(cap_corner > 0 ? cap_corner : 1)));
   MML_CUDA(ctx, ctx->f_plane.reserve(sizeof(float4) * 3 * (size_t)(cap_surf > 0 ? cap_surf : 1)));
+  // map-sized frames take the search / fit split (mml_associate_launch): its hand-over buffers must exist before a capture
+  if (cap_corner > 32768) MML_CUDA(ctx, ctx->pre_knn[0].reserve(sizeof(int) * 6 * (size_t)cap_corner + 64));
+  if (cap_surf > 32768) MML_CUDA(ctx, ctx->pre_knn[1].reserve(sizeof(int) * 6 * (size_t)cap_surf + 64));
   MML_CUDA(ctx, ctx->assoc_part[0].reserve(sizeof(double) * 8 * (size_t)(div_up(cap_corner + 1, 4) + 1) + 64));
   MML_CUDA(ctx, ctx->assoc_part[1].reserve(sizeof(double) * 8 * (size_t)(div_up(cap_surf + 1, 4) + 1) + 64));
   EstState* S = ctx->est_state.as<EstState>();
@@ -862,6 +865,10 @@ int mml_chain_prepare(mml_ctx* ctx, int cap, mml::EstState** S_out) {
   MML_CUDA(ctx, ctx->assoc_stats.reserve(512));
   MML_CUDA(ctx, ctx->f_line.reserve(sizeof(float4) * 3 * (size_t)cap));
   MML_CUDA(ctx, ctx->f_plane.reserve(sizeof(float4) * 3 * (size_t)cap));
+  if (cap > 32768) {
+    MML_CUDA(ctx, ctx->pre_knn[0].reserve(sizeof(int) * 6 * (size_t)cap + 64));
+    MML_CUDA(ctx, ctx->pre_knn[1].reserve(sizeof(int) * 6 * (size_t)cap + 64));
+  }
   MML_CUDA(ctx, ctx->assoc_part[0].reserve(sizeof(double) * 8 * (size_t)(div_up(cap + 1, 4) + 1) + 64));
   MML_CUDA(ctx, ctx->assoc_part[1].reserve(sizeof(double) * 8 * (size_t)(div_up(cap + 1, 4) + 1) + 64));
   *S_out = ctx->est_state.as<EstState>();

@@ -537,22 +537,32 @@ __device__ bool fit_plane(const float4* pts, const KnnT& r, float sx, float sy, 
 // 12 % faster than the fused kernel at 1.05 M queries (0.685 vs 0.776 ms, profiles/r2_s4_knn_experiments.txt).
 template <bool TWO>
 __global__ void __launch_bounds__(128) k_knn_walk(AssocArgs A) {
+  if (A.gate && *A.gate) return;
   const int i = blockIdx.x * 128 + threadIdx.x;
-  if (i >= A.nq) return;
+  int nq = A.nq_dev ? *A.nq_dev : A.nq;
+  if (nq > A.nq) {  // more queries than this launch was sized for: flag it, the host re-launches
+    if (i == 0 && A.overflow) atomicExch(A.overflow, 1);
+    nq = A.nq;
+  }
+  if (i >= nq) return;
   const GridDev& G = A.G[A.pre_map];
+  const float thres = A.thres_dev ? *A.thres_dev : A.thres;
+  // both variants are launched when the radius is only known on the device: the one it does not call for leaves
+  if ((G.pts2 != nullptr && (int)ceilf(sqrtf(thres) / G.cell) + 1 >= MML_TWO_LEVEL_MIN_SHELLS) != TWO) return;
+  const double* __restrict__ Tq = A.T_dev ? A.T_dev : A.T;
   const float4 q = A.q[i];
   const double pin[3] = {(double)q.x, (double)q.y, (double)q.z};
   float sel[3];
 #pragma unroll
   for (int rr = 0; rr < 3; rr++)
-    sel[rr] = (float)(((A.T[4 * rr] * pin[0] + A.T[4 * rr + 1] * pin[1]) + A.T[4 * rr + 2] * pin[2]) + A.T[4 * rr + 3]);
+    sel[rr] = (float)(((Tq[4 * rr] * pin[0] + Tq[4 * rr + 1] * pin[1]) + Tq[4 * rr + 2] * pin[2]) + Tq[4 * rr + 3]);
   int cI, cJ, cK;
   const bool in_grid = cube_of(sel[0], sel[1], sel[2], A.G[0].cen, cI, cJ, cK);
   const bool finite = !(isnan(sel[0]) || isnan(sel[1]) || isnan(sel[2]));
   int status = -1;
   if (in_grid && finite) {
     KnnP r;
-    status = TWO ? knn5_grid_packed2(G, sel[0], sel[1], sel[2], A.thres, r) : (knn5_grid_packed(G, sel[0], sel[1], sel[2], A.thres, r) ? 1 : 0);
+    status = TWO ? knn5_grid_packed2(G, sel[0], sel[1], sel[2], thres, r) : (knn5_grid_packed(G, sel[0], sel[1], sel[2], thres, r) ? 1 : 0);
     if (status != 0) {
 #pragma unroll
       for (int k = 0; k < 5; k++) A.pre_loc[5 * (size_t)i + k] = r.loc[k];
@@ -599,7 +609,11 @@ __global__ void __launch_bounds__(128) k_associate(AssocArgs A) {
   }
   double mom[7] = {0, 0, 0, 0, 0, 0, 0};
   int found = 0;
-  const int nq = A.nq_dev ? *A.nq_dev : A.nq;
+  int nq = A.nq_dev ? *A.nq_dev : A.nq;
+  if (nq > A.nq) {  // more queries than this launch was sized for: flag it, the host re-launches
+    if (i == 0 && A.overflow) atomicExch(A.overflow, 1);
+    nq = A.nq;
+  }
   if (i < nq) {
     const float4 q = A.q[i];
     const double pin[3] = {(double)q.x, (double)q.y, (double)q.z};
@@ -1371,7 +1385,7 @@ int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres,
   A.perm = ctx->has_perm[kind] ? ctx->perm[kind].as<unsigned>() : nullptr;
   // map-sized, spatially sorted sets: search kernel, then fit kernel (MML_ASSOC_SPLIT=0: the fused kernel)
   static const int split_env = getenv("MML_ASSOC_SPLIT") ? atoi(getenv("MML_ASSOC_SPLIT")) : 1;
-  if (G == 1 && split_env && ctx->has_perm[kind] && !nq_dev && !T_dev && !gate && nq > 0) {
+  if (G == 1 && split_env && ctx->has_perm[kind] && nq > 0) {
     mml::DevBuf& pb = ctx->pre_knn[kind];  // [nq][5] positions + [nq] status
     MML_CUDA(ctx, pb.reserve(sizeof(int) * 6 * (size_t)nq + 64));
     A.pre_loc = pb.as<int>();
@@ -1382,9 +1396,10 @@ int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres,
       // the two-level walk, which sends displaced queries to the coarse cells after two fine shells
       const GridDev& Gw = A.G[A.pre_map];
       const bool two = Gw.pts2 != nullptr && (int)ceilf(sqrtf(thres) / Gw.cell) + 1 >= MML_TWO_LEVEL_MIN_SHELLS;
-      if (two) k_knn_walk<true><<<grid, 128, 0, ctx->stream>>>(A);
-      else k_knn_walk<false><<<grid, 128, 0, ctx->stream>>>(A);
-      MML_LAUNCHED(ctx);
+      // (a radius that lives on the device - the solve loop's schedule - is only known to the kernels: both are
+      // launched and the one that does not apply returns at once)
+      if (thres_dev || two) { k_knn_walk<true><<<grid, 128, 0, ctx->stream>>>(A); MML_LAUNCHED(ctx); }
+      if (thres_dev || !two) { k_knn_walk<false><<<grid, 128, 0, ctx->stream>>>(A); MML_LAUNCHED(ctx); }
       if (kind == 0) k_associate<0, true><<<grid, 128, 0, ctx->stream>>>(A);
       else k_associate<1, true><<<grid, 128, 0, ctx->stream>>>(A);
       MML_LAUNCHED(ctx);

@@ -118,13 +118,16 @@ __device__ __noinline__ void cta_matvec(const double* M, const double* v, double
 // Cholesky factorisation and solve of A y = b by the CTA. A holds the matrix (frame-major order) in rows 0..n-1 and
 // the right-hand side as row n. The factor has no entries outside the band of the block-tridiagonal system: a column
 // in frame block b only reaches the rows of blocks b and b + 1 and the right-hand side row.
-// Right-looking, three columns per step: every thread factors the 3 x 3 diagonal block in registers (same inputs,
-// same result, so the positive-definiteness test is uniform and nothing is broadcast; the pivots come out of an
-// LDL^T recurrence so that the three reciprocal square roots do not wait for each other), one thread per row solves
-// the panel below it, one barrier, the trailing entries of the band take their rank-3 update spread over all
-// threads, one barrier. What bounds a step is the dependent chain and the two barriers, not the flops. The back
-// substitution runs on warp 0 alone, three unknowns per step, the solution in registers (components lane and
-// lane + 32) and exchanged by shuffles: no barrier on the way.
+// Right-looking, three columns per step, two roles:
+//   warp 0 owns the dependent chain. It holds the factor of the step's 3 x 3 diagonal block in registers (every lane
+//     the same values), publishes it, and after the step's barrier forms the NEXT diagonal block - its three panel rows
+//     solved in registers, this step's update applied - and factors it through the leading minors (three independent
+//     reciprocal square roots), while
+//   warps 1-10 solve the panel rows against the published block (one thread per row, solved rows into a side buffer),
+//     meet at a named barrier of their own and apply the rank-3 update to the band's trailing entries.
+// One full barrier per step. What bounds a step is warp 0's chain (~25 dependent float64 operations), not the flops.
+// The back substitution runs on warp 0 alone, three unknowns per step through the inverted diagonal blocks, the
+// solution in registers (components lane and lane + 32) and exchanged by shuffles: no barrier on the way.
 // On success ysol = A^-1 b and the function returns true (uniform over the CTA).
 // Replaces chol_solve_n of the reference restatement, which factors the same matrix densely.
 #if defined(MML_WIN_DEVPROF) && MML_WIN_DEVPROF >= 2
@@ -150,9 +153,7 @@ __device__ __noinline__ bool cta_chol_solve(WinShared& s, int n, int B, int tid)
 #endif
   int par = 0;
   int bnext = B;  // first column of the frame block after the one c0 lies in (no division in the loop)
-  // the 3 x 3 diagonal block of the current step, factored one step AHEAD by warp 0 (registers, every lane the same
-  // values) while the other warps apply the previous step's rank-3 update: the dependent chain of the factor (two
-  // reciprocals, three reciprocal square roots) no longer sits between the two barriers of a step
+  // the 3 x 3 diagonal block of the current step, factored one step AHEAD by warp 0 (registers, every lane the same values)
   double d10 = 0, d20 = 0, i00 = 0, i11 = 0, i22 = 0, l21 = 0;
   double q[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   bool pd = true;

@@ -16,6 +16,8 @@ __host__ __device__ inline double dsin(double f) { return sin(f); }
 __host__ __device__ inline double dcos(double f) { return cos(f); }
 __host__ __device__ inline double datan(double f) { return atan(f); }
 __host__ __device__ inline double val(double x) { return x; }
+// sine and cosine of the same argument (the exponential map needs both): one call where the argument reduction can be shared
+__host__ __device__ inline void dsincos(double f, double& sn, double& cs) { sn = sin(f); cs = cos(f); }
 
 template <class T> struct Q4 { T w, x, y, z; };
 template <class T> __host__ __device__ inline Q4<T> qmul(const Q4<T>& a, const Q4<T>& b) {  // sophus/so3.hpp:326-340
@@ -39,8 +41,9 @@ template <class T> __host__ __device__ inline Q4<T> qexp(const T* om) {  // so3.
   } else {
     T theta = dsqrt(theta_sq);
     T half = T(0.5) * theta;
-    imag = dsin(half) / theta;
-    real = dcos(half);
+    T sn;
+    dsincos(half, sn, real);
+    imag = sn / theta;
   }
   return {real, imag * om[0], imag * om[1], imag * om[2]};
 }
@@ -116,6 +119,7 @@ __host__ __device__ inline Dual30 dsin(const Dual30& f) { return chain30(sin(f.a
 __host__ __device__ inline Dual30 dcos(const Dual30& f) { return chain30(cos(f.a), -sin(f.a), f); }
 __host__ __device__ inline Dual30 datan(const Dual30& f) { return chain30(atan(f.a), 1.0 / (1.0 + f.a * f.a), f); }
 __host__ __device__ inline double val(const Dual30& x) { return x.a; }
+__host__ __device__ inline void dsincos(const Dual30& f, Dual30& sn, Dual30& cs) { sn = dsin(f); cs = dcos(f); }
 
 // one derivative direction: the device evaluates column c of the 15 x 30 Jacobian on its own thread
 struct Dual1 {
@@ -134,5 +138,15 @@ __host__ __device__ inline Dual1 dsin(const Dual1& f) { return {sin(f.a), cos(f.
 __host__ __device__ inline Dual1 dcos(const Dual1& f) { return {cos(f.a), -sin(f.a) * f.v}; }
 __host__ __device__ inline Dual1 datan(const Dual1& f) { return {atan(f.a), (1.0 / (1.0 + f.a * f.a)) * f.v}; }
 __host__ __device__ inline double val(const Dual1& x) { return x.a; }
+__host__ __device__ inline void dsincos(const Dual1& f, Dual1& sn, Dual1& cs) {
+  double sv, cv;
+#ifdef __CUDA_ARCH__
+  sincos(f.a, &sv, &cv);  // one argument reduction for both
+#else
+  sv = sin(f.a); cv = cos(f.a);
+#endif
+  sn = {sv, cv * f.v};
+  cs = {cv, -sv * f.v};
+}
 
 }  // namespace mml

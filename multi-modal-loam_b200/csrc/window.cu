@@ -38,6 +38,9 @@ namespace {
 // MML_WIN_PROF=1: wall-clock split of the window loop (debug aid; printed by mml_odom_run_window)
 struct WinProf { double push = 0, assoc = 0, launch = 0, imu = 0, wait = 0, solve = 0, other = 0; long evals = 0, scans = 0; };
 WinProf g_prof;
+#ifdef MML_WIN_TIMELINE
+extern "C" int mml_debug_win_timeline(unsigned long long* out8);
+#endif
 const bool g_prof_on = getenv("MML_WIN_PROF") != nullptr;
 inline double now_us() {
   timespec ts;
@@ -713,6 +716,17 @@ int mml_odom_run_window(mml_ctx* c, const void* const* xyzi, const void* const* 
   } else {
     MML_CUDA(c, cudaStreamSynchronize(st));
   }
+#ifdef MML_WIN_TIMELINE
+  if (g_prof_on) {
+    unsigned long long t8[8];
+    if (mml_debug_win_timeline(t8) == 0 && t8[5]) {
+      const double ns = (double)t8[5];
+      fprintf(stderr, "[mml window timeline] per scan (device clock): solve kernels %.1f us (%.2f launches), k_win_push %.1f us, push end -> first solve %.1f us, "
+                      "solve -> next solve %.1f us, last solve end -> next push start %.1f us\n",
+              t8[0] / ns * 1e-3, t8[6] / ns, t8[1] / ns * 1e-3, t8[2] / ns * 1e-3, t8[3] / ns * 1e-3, t8[4] / ns * 1e-3);
+    }
+  }
+#endif
   if (g_prof_on && g_prof.scans) {
     const double ns = (double)g_prof.scans;
     fprintf(stderr, "[mml window prof] per scan: host pre-integration + prediction %.1f us, enqueue %.1f us, wait for the solve %.1f us, evaluations %.1f; map updates %ld\n",

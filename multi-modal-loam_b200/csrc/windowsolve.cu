@@ -363,6 +363,20 @@ __device__ inline void win_reset_control(WinDev* wd) {
 }
 
 // per-call API: the host has uploaded the head of WinDev
+// -DMML_WIN_TIMELINE: %globaltimer stamps of the odometry loop's critical stream, accumulated on the device
+// [0] solve kernels (busy), [1] k_win_push, [2] push end -> first solve start (graph launch + association),
+// [3] solve end -> next solve start (association), [4] last solve end -> next push start (host turn-around + scan kernels),
+// [5] scans, [6] solve launches that did work
+#ifdef MML_WIN_TIMELINE
+__device__ unsigned long long g_wtl[8], g_wtl_push_end, g_wtl_solve_end, g_wtl_t0;
+__device__ __forceinline__ unsigned long long wtl_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+extern "C" int mml_debug_win_timeline(unsigned long long* out8) {
+  const int rc = cudaMemcpyFromSymbol(out8, g_wtl, sizeof(unsigned long long) * 8) == cudaSuccess ? 0 : -3;
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaMemcpyToSymbol(g_wtl, z, sizeof(z));
+  return rc;
+}
+#endif
 __global__ void k_win_begin(WinDev* wd, int* const* cnt_by_slot) {
   if (threadIdx.x != 0) return;
   win_reset_control(wd);
@@ -379,6 +393,13 @@ __global__ void k_win_begin(WinDev* wd, int* const* cnt_by_slot) {
 __global__ void k_win_push(WinDev* wd, const WinPush* push, int* const* cnt_by_slot) {
   const int tid = threadIdx.x;
   __shared__ int W_new, drop;
+#ifdef MML_WIN_TIMELINE
+  if (tid == 0) {
+    g_wtl_t0 = wtl_now();
+    if (g_wtl_solve_end) g_wtl[4] += g_wtl_t0 - g_wtl_solve_end;
+    g_wtl[5]++;
+  }
+#endif
   if (tid == 0) {
     drop = wd->W >= push->window ? 1 : 0;
     W_new = wd->W - drop + 1;
@@ -416,6 +437,10 @@ __global__ void k_win_push(WinDev* wd, const WinPush* push, int* const* cnt_by_s
     for (int f = 0; f < W_new; f++) used[wd->slot_of[f]] = true;
     for (int p = 0; p < kMaxWindow; p++)
       if (!used[p]) { cnt_by_slot[p][0] = 0; cnt_by_slot[p][1] = 0; }
+#ifdef MML_WIN_TIMELINE
+    g_wtl_push_end = wtl_now();
+    g_wtl[1] += g_wtl_push_end - g_wtl_t0;
+#endif
   }
 }
 
@@ -428,6 +453,15 @@ __global__ void k_win_push(WinDev* wd, const WinPush* push, int* const* cnt_by_s
 __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
   WinDev* wd = A.wd;
   if (wd->done_outer) return;  // uniform over the cluster
+#ifdef MML_WIN_TIMELINE
+  unsigned long long wtl_start = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    wtl_start = wtl_now();
+    if (wd->outer_it == 0) g_wtl[2] += wtl_start - g_wtl_push_end;
+    else g_wtl[3] += wtl_start - g_wtl_solve_end;
+    g_wtl[6]++;
+  }
+#endif
   extern __shared__ __align__(16) unsigned char win_smem[];
   WinShared& s = *reinterpret_cast<WinShared*>(win_smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -864,6 +898,10 @@ __global__ void __launch_bounds__(kWThreads, 1) k_solve_window(WinSolveArgs A) {
     }
     wd->done_outer = done;
     if (A.use_cond) cudaGraphSetConditional(A.cond, done ? 0u : 1u);
+#ifdef MML_WIN_TIMELINE
+    g_wtl_solve_end = wtl_now();
+    g_wtl[0] += g_wtl_solve_end - wtl_start;
+#endif
   }
 }
 

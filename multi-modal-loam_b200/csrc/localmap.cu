@@ -30,6 +30,25 @@ __global__ void __launch_bounds__(256) k_point_to_map(const float4* __restrict__
   out[i] = o;
 }
 
+// The filtered map's input is the previous map (unless cleared) followed by the 50 ring entries in slot order: one
+// gather launch instead of up to 51 copy nodes per kind (the copies' launch overhead was most of an update's time).
+struct RingSrc {
+  const float4* p[kLocalWindow + 1];
+  int off[kLocalWindow + 2];  // off[j] = first output index of source j, off[n] = total
+  int n;
+};
+__global__ void __launch_bounds__(256) k_ring_concat(RingSrc R, float4* __restrict__ dst) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= R.off[R.n]) return;
+  int lo = 0, hi = R.n;  // the source j with off[j] <= i < off[j + 1]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (R.off[mid] <= i) lo = mid;
+    else hi = mid;
+  }
+  dst[i] = R.p[lo][i - R.off[lo]];
+}
+
 struct LocalMapDev {
   mml::DevBuf ring[2][kLocalWindow];
   int ring_n[2][kLocalWindow];
@@ -97,18 +116,21 @@ int local_map_push_impl(mml_ctx* c, const void* corner, int n_corner, const void
       MML_CUDA(c, L->concat.reserve(sizeof(float4) * (size_t)total));
       MML_CUDA(c, L->result[k].reserve(sizeof(float4) * (size_t)total));
       float4* dst = L->concat.as<float4>();
-      size_t at = 0;
-      if (keep) {
-        MML_CUDA(c, cudaMemcpyAsync(dst, L->from_local[k].p, sizeof(float4) * (size_t)keep, cudaMemcpyDeviceToDevice, st));
-        at += (size_t)keep;
-      }
-      for (int i = 0; i < kLocalWindow; i++) {
-        const int ni = (i == slot) ? n : L->ring_n[k][i];
-        if (!ni) continue;
-        const void* from = (i == slot) ? L->pending[k].p : L->ring[k][i].p;
-        MML_CUDA(c, cudaMemcpyAsync(dst + at, from, sizeof(float4) * (size_t)ni, cudaMemcpyDeviceToDevice, st));
-        at += (size_t)ni;
-      }
+      RingSrc R;
+      R.n = 0;
+      int at = 0;
+      auto add = [&](const void* from, int cnt_pts) {
+        if (!cnt_pts) return;
+        R.p[R.n] = static_cast<const float4*>(from);
+        R.off[R.n] = at;
+        R.n++;
+        at += cnt_pts;
+      };
+      if (keep) add(L->from_local[k].p, keep);
+      for (int i = 0; i < kLocalWindow; i++) add((i == slot) ? L->pending[k].p : L->ring[k][i].p, (i == slot) ? n : L->ring_n[k][i]);
+      R.off[R.n] = at;
+      k_ring_concat<<<div_up(at, 256), 256, 0, st>>>(R, dst);
+      MML_LAUNCHED(c);
       // voxel filter (EST.cpp:1630-1635)
       int* cnt = L->cnt.as<int>() + 4 * k;
       const int tot = (int)total;

@@ -700,8 +700,10 @@ int mml_odom_run_window(mml_ctx* c, const void* const* xyzi, const void* const* 
         const float dis = (float)(dx * dx + dy * dy + dz * dz);
         if (dis >= 0.5f) {
           WinSlot& f0 = w->frame(0);
+          const double tm0 = g_prof_on ? now_us() : 0;
           MML_CHECK(mml_local_map_push_dev(c, f0.q_corner.p, slot_counts[w->order[0]][0], f0.q_surf.p, slot_counts[w->order[0]][1], T_map,
                                            leaf_corner, leaf_surf, 1, nullptr, nullptr));
+          if (g_prof_on) g_prof.other += now_us() - tm0;
           last_update_pose[0] = T_map[3]; last_update_pose[1] = T_map[7]; last_update_pose[2] = T_map[11];
           map_updates++;
         }
@@ -731,6 +733,7 @@ int mml_odom_run_window(mml_ctx* c, const void* const* xyzi, const void* const* 
     const double ns = (double)g_prof.scans;
     fprintf(stderr, "[mml window prof] per scan: host pre-integration + prediction %.1f us, enqueue %.1f us, wait for the solve %.1f us, evaluations %.1f; map updates %ld\n",
             g_prof.imu / ns, g_prof.launch / ns, g_prof.wait / ns, g_prof.evals / ns, map_updates);
+    if (map_updates) fprintf(stderr, "[mml window prof] map update: %.1f us each on the host (enqueue + the one wait)\n", g_prof.other / (double)map_updates);
     g_prof = WinProf();
   }
   return MML_OK;

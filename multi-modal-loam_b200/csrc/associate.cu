@@ -258,11 +258,23 @@ __device__ __forceinline__ float knnp_d(const KnnP& r, int k) { return __uint_as
 
 __device__ __forceinline__ void scan_range_p(const GridDev& G, int c0, int c1, float qx, float qy, float qz, KnnP& r) {
   const int s = __ldg(G.cell_start + c0), e = __ldg(G.cell_start + c1 + 1);
-  for (int k = s; k < e; k++) {
+  // a candidate farther than the current 5th neighbour is dropped on one float compare (equal distances take the
+  // 64-bit key path: ties go to the lower index); two candidates per trip so that both loads are in flight together
+  int k = s;
+  for (; k + 1 < e; k += 2) {
+    const float4 p = __ldg(G.pts + k), p2 = __ldg(G.pts + k + 1);
+    const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+    const float d = (dx * dx + dy * dy) + dz * dz;
+    const float ex = qx - p2.x, ey = qy - p2.y, ez = qz - p2.z;
+    const float d2 = (ex * ex + ey * ey) + ez * ez;
+    if (!(d > knnp_d(r, 4))) knnp_push(r, d, __float_as_int(p.w), k);
+    if (!(d2 > knnp_d(r, 4))) knnp_push(r, d2, __float_as_int(p2.w), k + 1);
+  }
+  if (k < e) {
     const float4 p = __ldg(G.pts + k);
     const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
     const float d = (dx * dx + dy * dy) + dz * dz;
-    knnp_push(r, d, __float_as_int(p.w), k);
+    if (!(d > knnp_d(r, 4))) knnp_push(r, d, __float_as_int(p.w), k);
   }
 }
 
@@ -332,7 +344,7 @@ __device__ __forceinline__ void scan_range_p2(const float4* __restrict__ pts, co
     const float4 p = __ldg(pts + k);
     const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
     const float d = (dx * dx + dy * dy) + dz * dz;
-    knnp_push(r, d, __float_as_int(p.w), k);
+    if (!(d > knnp_d(r, 4))) knnp_push(r, d, __float_as_int(p.w), k);
   }
 }
 

@@ -1294,7 +1294,11 @@ static int build_grid(mml_ctx* ctx, GridMap& M, const float4* pts_d, int m, floa
     MML_CUDA(ctx, cudaStreamSynchronize(st));
     if (nz == 0) nz = 1;
     const double occ = (double)m / (double)nz;
-    static const double target_occ = getenv("MML_CELL_OCC") ? atof(getenv("MML_CELL_OCC")) : 3.0;
+    // points per non-empty cell the edge is sized for: 3 for scan-sized query sets (one warp per query: fewer candidates
+    // per dependent round trip), 6 for map-sized sweeps (thread per query: fewer rows of cells to walk; measured optimum
+    // of the S4 sweep, profiles/r2_s4_knn_experiments.txt)
+    static const double occ_env = getenv("MML_CELL_OCC") ? atof(getenv("MML_CELL_OCC")) : 0.0;
+    const double target_occ = occ_env > 0.0 ? occ_env : (m > 400000 ? 6.0 : 3.0);
     cell = (float)fmin(fmax((double)M.cell * sqrt(target_occ / occ), 0.05), 5.0);
     M.auto_cell = cell;
     M.auto_m = m;

@@ -237,7 +237,7 @@ def state_of(synth, T, v=0.5):
 
 MAP_UPDATE = 1  # set from --map-update
 # dram__bytes_read.sum + dram__bytes_write.sum of the S4 association kernels per sweep step (ncu --set full, profiles/)
-S4_ASSOC_TRAFFIC = 162_400_000  # profiles/r2_ncu_s4_assoc.txt: both kinds, search + fit kernels
+S4_ASSOC_TRAFFIC = 132_700_000  # profiles/r2_ncu_s4_assoc.txt: both kinds, search + fit kernels
 
 
 def cpu_window_loop(orc, synth, scans, Ts, imu, stamps, first, n, ms, mc, threads, window):

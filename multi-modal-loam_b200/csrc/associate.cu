@@ -359,7 +359,7 @@ __device__ __forceinline__ void scan_range_p2(const float4* __restrict__ pts, co
 #define MML_FINE_SHELLS_P 2
 #endif
 #ifndef MML_TWO_LEVEL_MIN_SHELLS
-#define MML_TWO_LEVEL_MIN_SHELLS 12
+#define MML_TWO_LEVEL_MIN_SHELLS 20
 #endif
 __device__ int knn5_grid_packed2(const GridDev& G, float qx, float qy, float qz, float thres, KnnP& r) {
   knnp_init(r);

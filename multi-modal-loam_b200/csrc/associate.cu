@@ -1362,9 +1362,8 @@ int mml_grid_table_sync(mml_ctx* ctx) {
 int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres, const double* T_dev,
                          const float* thres_dev, const int* gate, const int* nq_dev, int cap) {
   const int nq = cap;
-  // lanes per query: a whole warp for scan-sized query sets (latency), 8 lanes for map-sized sweeps
-  static const int g_env = getenv("MML_ASSOC_G") ? atoi(getenv("MML_ASSOC_G")) : 0;
-  const int G = g_env ? g_env : (cap <= 32768 ? 32 : 1);
+  // lanes per query: a whole warp for scan-sized query sets (latency), one thread per query for map-sized sweeps
+  const int G = cap <= 32768 ? 32 : 1;
   // group kernels stride over the queries: at most kAssocWave CTAs (4 per SM), however large the query buffer is
   const int kAssocWave = 4 * kNumSMs;
   int grid = G == 1 ? div_up(nq > 0 ? nq : 1, 128) : div_up(nq > 0 ? nq : 1, 128 / G);
@@ -1433,15 +1432,6 @@ int mml_associate_launch(mml_ctx* ctx, int kind, const double* T16, float thres,
   } else if (G == 32) {
     if (kind == 0) k_associate_g<0, 32><<<grid, 128, 0, ctx->stream>>>(A);
     else k_associate_g<1, 32><<<grid, 128, 0, ctx->stream>>>(A);
-  } else if (G == 8) {
-    if (kind == 0) k_associate_g<0, 8><<<grid, 128, 0, ctx->stream>>>(A);
-    else k_associate_g<1, 8><<<grid, 128, 0, ctx->stream>>>(A);
-  } else if (G == 16) {
-    if (kind == 0) k_associate_g<0, 16><<<grid, 128, 0, ctx->stream>>>(A);
-    else k_associate_g<1, 16><<<grid, 128, 0, ctx->stream>>>(A);
-  } else if (G == 4) {
-    if (kind == 0) k_associate_g<0, 4><<<grid, 128, 0, ctx->stream>>>(A);
-    else k_associate_g<1, 4><<<grid, 128, 0, ctx->stream>>>(A);
   } else {
     if (kind == 0) k_associate<0, false><<<grid, 128, 0, ctx->stream>>>(A);
     else k_associate<1, false><<<grid, 128, 0, ctx->stream>>>(A);

@@ -146,7 +146,7 @@ struct mml_ctx {
   mml::DevBuf q_corner, q_surf;   // float4
   mml::DevBuf perm[2];            // spatial sort permutation of large query sets (framesort.cu)
   bool has_perm[2] = {false, false};
-  mml::DevBuf pre_knn[2];         // map-sized sets: neighbour positions + status left by k_knn_box for the fit kernel
+  mml::DevBuf pre_knn[2];         // map-sized sets: neighbour positions + status left by k_knn_walk for the fit kernel
   int n_corner = 0, n_surf = 0;
   mml::DevBuf f_line, f_plane;    // compact features (see associate.cu)
   mml::DevBuf acc_partials, acc_out, est_state;

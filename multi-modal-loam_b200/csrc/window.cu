@@ -4,11 +4,12 @@
 // IMUIntegrator::PreIntegration, src/lio/IMUIntegrator.cpp:105-166; Cost_NavState_PRV_Bias,
 // include/utils/ceresfunc.h:321-393; pose prediction of process(), src/unionPoseEstimation.cpp:796-835.
 //
-// Split of the work (SURVEY.md §2 rows 11-12, §8 f F3): the per-point work of every frame — association against the
-// resident maps and the residual / Jacobian / Huber / 28-sum reduction — runs on the device, all frames of the
-// window in one launch per evaluation (k_accumulate_window). The IMU factors (W-1 blocks of 15 residuals), the
-// assembly of the (15 W)^2 normal equations and the dogleg step are a few thousand flops per iteration and stay on
-// the host, which reads W x 28 doubles per evaluation.
+// Split of the work (SURVEY.md §2 rows 11-12, §8 f F3): the whole solve of a window runs on the device
+// (csrc/windowsolve.cu: association of every frame against the resident maps, lidar residuals / Jacobians / Huber /
+// 28-sum reduction, the W - 1 IMU factors under forward-mode differentiation, the (15 W)-dim dogleg). This file is the
+// host side: IMU pre-integration, prediction and the factor as host API (mml_imu_*), the frame slots of the window,
+// the per-call entry points (mml_window_push_frame, mml_estimate_window) and the odometry loop (mml_odom_run_window:
+// per scan one pre-integration, one graph launch, one wait on the mapped result, the map update at its gate).
 #include "common.cuh"
 #include "smallmath.cuh"
 #include "eststate.cuh"

@@ -604,7 +604,7 @@ def test_large_query_set_is_sorted_but_slots_keep_caller_order(ctx, mm, orc, syn
     assert np.abs(f[ok, 3:6] - r[ok, 3:6]).max() <= 1e-9
 
 
-# ---- map-sized query sets (S4 / S5): box search per warp (k_knn_box) + fit kernel against the oracle ------------------
+# ---- map-sized query sets (S4 / S5): search kernel (k_knn_walk, one or two levels) + fit kernel against the oracle -------
 @pytest.mark.parametrize("kind", [0, 1])
 @pytest.mark.parametrize("thres", [1.0, 25.0])
 def test_map_sized_association_240k_both_kinds(ctx, mm, orc, synth, kind, thres):

@@ -233,6 +233,11 @@ typedef struct {
 /* t / gyr / acc: n samples in (last_time, t_frame]; acc in units of g (scaled by gnorm = 9.805, IMU.h:84). Host code. */
 int mml_imu_preintegrate(const double* t, const double* gyr, const double* acc, int n, double last_time,
                          const double* bg3, const double* ba3, mml_preint* out);
+/* The mean alone (dq, dp, dv, dt, bg, ba; cov / jac / sqrt_info are left untouched): the same arithmetic as
+ * mml_imu_preintegrate, bit for bit, at a fraction of its time. The odometry loop predicts the new frame's pose from it
+ * (PE.cpp:812-829) and forms the full pre-integration while the device already works on the scan. Host code.       */
+int mml_imu_preintegrate_mean(const double* t, const double* gyr, const double* acc, int n, double last_time,
+                              const double* bg3, const double* ba3, mml_preint* out);
 /* Cost_NavState_PRV_Bias (include/utils/ceresfunc.h:321-393) weighted by sqrt_info: r15 and, if J450 != NULL, the
  * Jacobian (15 x 30 row-major, columns [PR_i 6 | VBias_i 9 | PR_j 6 | VBias_j 9]) by forward-mode differentiation. */
 int mml_imu_factor(const mml_preint* pre, const double* gravity3, const double* pri6, const double* vbi9,

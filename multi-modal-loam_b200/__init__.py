@@ -36,7 +36,7 @@ EXPORTS = [
     "mml_frame_accumulate", "mml_frame_associate_async", "mml_frame_associate_kind_async", "mml_frame_accumulate_async",
     "mml_odom_run", "mml_local_map_push", "mml_local_map_push_dev", "mml_local_map_seed", "mml_global_map_push", "mml_global_map_get", "mml_global_map_reset", "mml_unpack_custom_points", "mml_unpack_pointcloud2", "mml_pack_union_clouds", "mml_local_map_get", "mml_local_map_reset", "mml_timer_start",
     "mml_timer_stop_ms", "mml_frame_accumulate_partial_dev", "mml_stream_handle",
-    "mml_imu_preintegrate", "mml_imu_factor", "mml_imu_predict", "mml_window_reset", "mml_window_size",
+    "mml_imu_preintegrate", "mml_imu_preintegrate_mean", "mml_imu_factor", "mml_imu_predict", "mml_window_reset", "mml_window_size",
     "mml_window_push_frame", "mml_window_push_scan_dev", "mml_window_get_frame", "mml_estimate_window",
     "mml_odom_run_window", "mml_shard_init", "mml_shard_local_ptr", "mml_shard_connect_ipc", "mml_shard_connect_ptrs",
     "mml_shard_close", "mml_estimate_sharded",
@@ -64,6 +64,19 @@ def imu_preintegrate(t, gyr, acc, last_time, bg=(0, 0, 0), ba=(0, 0, 0)):
                                              _p(_f64(ba)), C.byref(out))
     if rc != 0:
         raise MmlError(f"mml_imu_preintegrate: {ERRORS.get(rc, rc)}")
+    return out
+
+
+def imu_preintegrate_mean(t, gyr, acc, last_time, bg=(0, 0, 0), ba=(0, 0, 0)):
+    """The mean of the pre-integration alone (dq, dp, dv, dt): what the pose prediction needs (host code)."""
+    t = _f64(t)
+    gyr = _f64(gyr).reshape(-1, 3)
+    acc = _f64(acc).reshape(-1, 3)
+    out = Preint()
+    rc = load_library().mml_imu_preintegrate_mean(_p(t), _p(gyr), _p(acc), int(t.shape[0]), C.c_double(last_time), _p(_f64(bg)),
+                                                  _p(_f64(ba)), C.byref(out))
+    if rc != 0:
+        raise MmlError(f"mml_imu_preintegrate_mean: {ERRORS.get(rc, rc)}")
     return out
 
 

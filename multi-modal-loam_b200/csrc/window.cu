@@ -165,10 +165,48 @@ extern "C" {
 
 // IMUIntegrator::PreIntegration, IMU.cpp:105-166 (+ sqrt_information of EST.cpp:1240-1242). Host side: ~20 samples
 // of 15x15 algebra per scan.
-int mml_imu_preintegrate(const double* t, const double* gyr, const double* acc, int n, double last_time,
-                         const double* bg3, const double* ba3, mml_preint* out) {
+}  // extern "C" (helpers with internal linkage follow)
+
+// The mean of the pre-integration (dq, dp, dv, dt) does not depend on its covariance / Jacobian. The odometry loop
+// needs the mean first (it predicts the new frame's pose, which the undistortion of the scan waits for) and the rest
+// only when the window is pushed, so the mean can be formed alone (mean_only) and the full pre-integration afterwards,
+// while the device already works on the scan. Both run the SAME compiled code for the mean (the helpers below are
+// not inlined), so the two results are identical to the bit.
+namespace {
+__attribute__((noinline)) void imu_sample_terms(const double* gyr, const double* acc, const double* t, int s, double current_time,
+                                                const double* bg3, const double* ba3, double* g3, double* a3, double* dt_out,
+                                                double* gdt, double* dR) {
+  const double gnorm = 9.805;  // IMU.h:84
+  g3[0] = gyr[3 * s] - bg3[0]; g3[1] = gyr[3 * s + 1] - bg3[1]; g3[2] = gyr[3 * s + 2] - bg3[2];
+  a3[0] = acc[3 * s] * gnorm - ba3[0]; a3[1] = acc[3 * s + 1] * gnorm - ba3[1]; a3[2] = acc[3 * s + 2] * gnorm - ba3[2];
+  const double dt = t[s] - current_time;
+  *dt_out = dt;
+  gdt[0] = g3[0] * dt; gdt[1] = g3[1] * dt; gdt[2] = g3[2] * dt;
+  quat_to_R(so3_exp(gdt), dR);
+}
+__attribute__((noinline)) void imu_rotation_of(const Quat& dq, double* Rq) { quat_to_R(dq, Rq); }
+__attribute__((noinline)) void imu_mean_update(Quat& dq, double* dp, double* dv, const double* Rq, const double* a3, double dt,
+                                               const double* dR) {
+  const double dt2 = dt * dt;
+  const double Ra[3] = {Rq[0] * a3[0] + Rq[1] * a3[1] + Rq[2] * a3[2], Rq[3] * a3[0] + Rq[4] * a3[1] + Rq[5] * a3[2],
+                        Rq[6] * a3[0] + Rq[7] * a3[1] + Rq[8] * a3[2]};
+  for (int k = 0; k < 3; k++) dp[k] += dv[k] * dt + 0.5 * Ra[k] * dt2;
+  for (int k = 0; k < 3; k++) dv[k] += Ra[k] * dt;
+  double m3[9];
+  mat_mul(3, 3, 3, Rq, dR, m3);
+  Quat qt = quat_from_R9(m3);
+  if (qt.w < 0) { qt.w = -qt.w; qt.x = -qt.x; qt.y = -qt.y; qt.z = -qt.z; }
+  const double qn = sqrt(((qt.x * qt.x + qt.y * qt.y) + qt.z * qt.z) + qt.w * qt.w);
+  dq = {qt.w / qn, qt.x / qn, qt.y / qn, qt.z / qn};
+}
+}  // namespace
+
+extern "C" {
+
+static int imu_preintegrate_impl(const double* t, const double* gyr, const double* acc, int n, double last_time,
+                                 const double* bg3, const double* ba3, bool mean_only, mml_preint* out) {
   if (!out || n < 0 || (n && (!t || !gyr || !acc)) || !bg3 || !ba3) return MML_ERR_INVALID;
-  const double acc_n = 0.08, gyr_n = 0.004, acc_w = 2.0e-4, gyr_w = 2.0e-5, gnorm = 9.805;  // IMU.h:79-84
+  const double acc_n = 0.08, gyr_n = 0.004, acc_w = 2.0e-4, gyr_w = 2.0e-5;  // IMU.h:79-83
   Quat dq = {1, 0, 0, 0};
   double dp[3] = {0, 0, 0}, dv[3] = {0, 0, 0}, dtime = 0;
   std::vector<double> cov(225, 0.0), jac(225, 0.0), noise(144, 0.0), tmp(225), tmp2(225), AT(225), BNB(225);
@@ -179,12 +217,16 @@ int mml_imu_preintegrate(const double* t, const double* gyr, const double* acc, 
   }
   double current_time = last_time;
   for (int s = 0; s < n; s++) {
-    const double g3[3] = {gyr[3 * s] - bg3[0], gyr[3 * s + 1] - bg3[1], gyr[3 * s + 2] - bg3[2]};
-    const double a3[3] = {acc[3 * s] * gnorm - ba3[0], acc[3 * s + 1] * gnorm - ba3[1], acc[3 * s + 2] * gnorm - ba3[2]};
-    const double dt = t[s] - current_time, dt2 = dt * dt;
-    const double gdt[3] = {g3[0] * dt, g3[1] * dt, g3[2] * dt};
-    double dR[9];
-    quat_to_R(so3_exp(gdt), dR);
+    double g3[3], a3[3], dt, gdt[3], dR[9], Rq[9];
+    imu_sample_terms(gyr, acc, t, s, current_time, bg3, ba3, g3, a3, &dt, gdt, dR);
+    imu_rotation_of(dq, Rq);
+    if (mean_only) {
+      imu_mean_update(dq, dp, dv, Rq, a3, dt, dR);
+      dtime += dt;
+      current_time = t[s];
+      continue;
+    }
+    const double dt2 = dt * dt;
     double Jr[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     const double nrm = sqrt((gdt[0] * gdt[0] + gdt[1] * gdt[1]) + gdt[2] * gdt[2]);
     if (nrm > 0.00001) {
@@ -195,8 +237,7 @@ int mml_imu_preintegrate(const double* t, const double* gyr, const double* acc, 
       const double c1 = (1 - cos(nrm)) / nrm, c2 = 1 - sin(nrm) / nrm;
       for (int i = 0; i < 9; i++) Jr[i] = (i % 4 == 0 ? 1.0 : 0.0) - c1 * K[i] + c2 * KK[i];
     }
-    double Rq[9], Ha[9], RH[9];
-    quat_to_R(dq, Rq);
+    double Ha[9], RH[9];
     hat3(a3, Ha);
     mat_mul(3, 3, 3, Rq, Ha, RH);
     // A = d(state_{k+1}) / d(state_k) and B = d(state_{k+1}) / d(noise) (IMU.cpp:131-156) are identity plus a few
@@ -251,22 +292,14 @@ int mml_imu_preintegrate(const double* t, const double* gyr, const double* acc, 
     }
     for (int i = 0; i < 3; i++) { BNB[(9 + i) * 15 + 9 + i] = (dt * nwg) * dt; BNB[(12 + i) * 15 + 12 + i] = (dt * nwa) * dt; }
     for (int i = 0; i < 15; i++) for (int j = 0; j < 15; j++) cov[i * 15 + j] = tmp2[j * 15 + i] + BNB[i * 15 + j];
-    const double Ra[3] = {Rq[0] * a3[0] + Rq[1] * a3[1] + Rq[2] * a3[2], Rq[3] * a3[0] + Rq[4] * a3[1] + Rq[5] * a3[2],
-                          Rq[6] * a3[0] + Rq[7] * a3[1] + Rq[8] * a3[2]};
-    for (int k = 0; k < 3; k++) dp[k] += dv[k] * dt + 0.5 * Ra[k] * dt2;
-    for (int k = 0; k < 3; k++) dv[k] += Ra[k] * dt;
-    double m3[9];
-    mat_mul(3, 3, 3, Rq, dR, m3);
-    Quat qt = quat_from_R9(m3);
-    if (qt.w < 0) { qt.w = -qt.w; qt.x = -qt.x; qt.y = -qt.y; qt.z = -qt.z; }
-    const double qn = sqrt(((qt.x * qt.x + qt.y * qt.y) + qt.z * qt.z) + qt.w * qt.w);
-    dq = {qt.w / qn, qt.x / qn, qt.y / qn, qt.z / qn};
+    imu_mean_update(dq, dp, dv, Rq, a3, dt, dR);
     dtime += dt;
     current_time = t[s];
   }
   out->dq[0] = dq.w; out->dq[1] = dq.x; out->dq[2] = dq.y; out->dq[3] = dq.z;
   for (int k = 0; k < 3; k++) { out->dp[k] = dp[k]; out->dv[k] = dv[k]; out->bg[k] = bg3[k]; out->ba[k] = ba3[k]; }
   out->dt = dtime;
+  if (mean_only) return MML_OK;
   memcpy(out->cov, cov.data(), sizeof(out->cov));
   memcpy(out->jac, jac.data(), sizeof(out->jac));
   double inv[225], L[225];
@@ -291,6 +324,15 @@ int mml_imu_factor(const mml_preint* pre, const double* gravity3, const double* 
 }
 
 // PE.cpp:812-829. state = P(3) q_wxyz(4) V(3) bg(3) ba(3)
+int mml_imu_preintegrate(const double* t, const double* gyr, const double* acc, int n, double last_time,
+                         const double* bg3, const double* ba3, mml_preint* out) {
+  return imu_preintegrate_impl(t, gyr, acc, n, last_time, bg3, ba3, false, out);
+}
+int mml_imu_preintegrate_mean(const double* t, const double* gyr, const double* acc, int n, double last_time,
+                              const double* bg3, const double* ba3, mml_preint* out) {
+  return imu_preintegrate_impl(t, gyr, acc, n, last_time, bg3, ba3, true, out);
+}
+
 int mml_imu_predict(const double* prev16, const mml_preint* pre, double* next16) {
   if (!prev16 || !pre || !next16) return MML_ERR_INVALID;
   auto rot = [](const double* q, const double* v, double* o) {  // Eigen 3.3 _transformVector
@@ -628,8 +670,9 @@ int mml_odom_run_window(mml_ctx* c, const void* const* xyzi, const void* const* 
   for (int k = 0; k < n_scans; k++) {
     const double tq0 = g_prof_on ? now_us() : 0;
     WinPush* hp = ring + (k & 7);
-    MML_CHECK(mml_imu_preintegrate(imu_t + imu_off, imu_gyr + 3 * imu_off, imu_acc + 3 * imu_off, imu_n[k], t_prev, prev + 10, prev + 13, &hp->pre));
-    imu_off += imu_n[k];
+    // the mean of the pre-integration first: it gives the predicted pose the scan's undistortion waits for; covariance,
+    // Jacobian and sqrt-information (most of the host's time) follow below, while the device works on the scan
+    MML_CHECK(mml_imu_preintegrate_mean(imu_t + imu_off, imu_gyr + 3 * imu_off, imu_acc + 3 * imu_off, imu_n[k], t_prev, prev + 10, prev + 13, &hp->pre));
     double next[16];
     MML_CHECK(mml_imu_predict(prev, &hp->pre, next));
     // LiDAR motion over the sweep, PE.cpp:822-829: delta = T_wl(prev)^-1 T_wl(predicted)
@@ -650,6 +693,12 @@ int mml_odom_run_window(mml_ctx* c, const void* const* xyzi, const void* const* 
     MML_CHECK(window_push_scan(c, xd, ld, sd, n_pts[k], n_lines, dR9, dt3, leaf_corner, leaf_surf, window, nullptr,
                                w->x_label[b].as<uint8_t>(), w->x_counters[b].as<int>(), flags, w->x_idx[b].as<int>()));
     MML_CUDA(c, cudaEventRecord(w->xfree[b], st));  // raw scan, labels and counters of this buffer pair are consumed
+    {  // the full pre-integration (same mean, to the bit: shared code) for the window's IMU factor
+      const double dq_mean[4] = {hp->pre.dq[0], hp->pre.dq[1], hp->pre.dq[2], hp->pre.dq[3]};
+      MML_CHECK(mml_imu_preintegrate(imu_t + imu_off, imu_gyr + 3 * imu_off, imu_acc + 3 * imu_off, imu_n[k], t_prev, prev + 10, prev + 13, &hp->pre));
+      if (memcmp(dq_mean, hp->pre.dq, sizeof(dq_mean)) != 0) return mml_fail(c, MML_ERR_STATE, "pre-integration: the mean differs between its two passes");
+      imu_off += imu_n[k];
+    }
     const int W = w->n_slots;
     memcpy(hp->state, next, sizeof(next));
     hp->slot = w->order[W - 1];

@@ -26,6 +26,8 @@ def test_host_imu_code_matches_oracle(mm, orc, synth):
         P = mm.imu_preintegrate(*imu[k], stamps[k - 1], bg, ba)
         O = orc.Preint(*imu[k], stamps[k - 1], bg, ba)
         assert np.abs(np.array(P.dq) - O.dq).max() < 1e-15 and np.abs(np.array(P.dp) - O.dp).max() < 1e-15
+        Pm = mm.imu_preintegrate_mean(*imu[k], stamps[k - 1], bg, ba)  # the loop predicts from the mean alone: same bits
+        assert list(Pm.dq) == list(P.dq) and list(Pm.dp) == list(P.dp) and list(Pm.dv) == list(P.dv) and Pm.dt == P.dt
         assert np.abs(np.array(P.cov).reshape(15, 15) - O.cov).max() <= 1e-14 * np.abs(O.cov).max()
         assert np.abs(np.array(P.sqrt_info).reshape(15, 15) - O.sqrt_info).max() <= 1e-9 * np.abs(O.sqrt_info).max()
         pri = _x6(synth, Ts[k - 1]) + rng.normal(0, 0.01, 6)

@@ -15,7 +15,8 @@
 //     rows by sqrt_info and forms the factors' J^T J / J^T r straight into the dense system;
 //   * every CTA then takes the SAME dogleg step on its own copy of the solver state (identical inputs, identical
 //     code, fixed summation orders: identical steps, so nothing is broadcast): bulk vector / matrix work on all
-//     warps, the Cholesky factorisation (left-looking, the right-hand side carried as an extra row) on warp 0.
+//     warps; the banded Cholesky factorisation (right-looking, three columns per step, the right-hand side carried as
+//     an extra row) with warp 0 on the dependent chain and warps 1-10 on panel and update (cta_chol_solve).
 // The tail (CTA 0) writes the states back, runs the convergence test, prepares the next association's transforms
 // and, when the solve is over, publishes the result to mapped host memory and clears the WHILE condition.
 #include "windowstate.cuh"
@@ -78,7 +79,7 @@ struct WinShared {
   double fac[2][8];                         // factor of a step's 3 x 3 diagonal block: 1 / L[j][j] (3), L[1][0], L[2][0], L[2][1], positive-definite flag
                                             // (two copies by step parity: warp 0 publishes the next step's while the other warps still read this one's)
   double X[28][3];                          // the step's solved panel rows (list order: band rows, then the right-hand side)
-  int chol_ok, ntile;
+  int chol_ok, ntile;                       // (chol_ok: unused since the factor's flag travels with the published block)
   unsigned short tl[(kWinN / 3) * (kWinN / 3 + 1) / 2];  // 3 x 3 tiles of the upper triangle some factor touches: (tile row << 8) | tile column
   unsigned char tri[27 * 28 / 2][2];        // (row, column) of the idx-th entry of a lower triangle, row-major
   int pos[kWinN], unpos[kWinN];

@@ -474,7 +474,7 @@ def main():
         tl = torch.from_numpy(l.view(np.int16)).pin_memory()
         ts = torch.from_numpy(s).pin_memory()
         pinned.append((tx, tl, ts))
-        pinned_np.append((tx.numpy(), tl.numpy().view(np.uint16), ts.numpy(), x.shape[0]))
+        pinned_np.append((tx.data_ptr(), tl.data_ptr(), ts.data_ptr(), x.shape[0]))  # host addresses, as a C++ caller of the C-ABI passes them
 
     def max_over_ranks(v):
         t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local_rank}")

@@ -435,15 +435,17 @@ class Context:
     # ---- native odometry loop (pipelined extraction, constant-velocity prediction)
     def odom_run(self, scans, n_lines, T_init, T_prev, exTlb, host_buffers=False, leaf_corner=0.4, leaf_surf=0.2,
                  params=None):
-        """scans: list of (xyzi, line, s, n). Device pointers (ctypes.c_void_p) when host_buffers is False,
-        numpy arrays (ideally backed by pinned memory) otherwise. Returns (poses [k,4,4], total_ms, counts [k,4])."""
+        """scans: list of (xyzi, line, s, n). Device pointers (ctypes.c_void_p or int) when host_buffers is False,
+        numpy arrays or raw host addresses (ideally pinned memory) otherwise. Returns (poses [k,4,4], total_ms, counts [k,4])."""
         k = len(scans)
         PtrArr = C.c_void_p * max(k, 1)
 
         def ptr(v):
             if isinstance(v, C.c_void_p):
                 return v.value
-            return v.ctypes.data if v is not None else None
+            if isinstance(v, np.ndarray):
+                return v.ctypes.data
+            return int(v) if v is not None else None  # a raw address (device, or pinned host memory with host_buffers)
 
         xs = PtrArr(*[ptr(sc[0]) for sc in scans])
         ls = PtrArr(*[ptr(sc[1]) for sc in scans])
@@ -520,17 +522,24 @@ class Context:
                 return v.value
             if isinstance(v, np.ndarray):
                 keep.append(v)
-                return v.ctypes.data
+                return v.__array_interface__["data"][0]  # (.ctypes.data builds an object per access: this call is timed end to end)
             return int(v) if v is not None else None
+
+        def f64(v, cols):
+            if isinstance(v, np.ndarray) and v.dtype == np.float64:
+                return v.reshape(-1) if cols == 1 else v.reshape(-1, 3)
+            v = np.asarray(v, float)
+            return v.ravel() if cols == 1 else v.reshape(-1, 3)
 
         xs = (C.c_void_p * n)(*[ptr(sc[0]) for sc in scans])
         ls = (C.c_void_p * n)(*[ptr(sc[1]) for sc in scans])
         ss = (C.c_void_p * n)(*[ptr(sc[2]) for sc in scans])
-        npts = np.array([int(sc[3]) for sc in scans], np.int32)
-        it = _f64(np.concatenate([np.asarray(i[0], float).ravel() for i in imu]))
-        ig = _f64(np.concatenate([np.asarray(i[1], float).reshape(-1, 3) for i in imu]))
-        ia = _f64(np.concatenate([np.asarray(i[2], float).reshape(-1, 3) for i in imu]))
-        inn = np.array([len(np.asarray(i[0]).ravel()) for i in imu], np.int32)
+        npts = np.fromiter((sc[3] for sc in scans), np.int32, n)
+        ts = [f64(i[0], 1) for i in imu]
+        it = _f64(np.concatenate(ts))
+        ig = _f64(np.concatenate([f64(i[1], 3) for i in imu]))
+        ia = _f64(np.concatenate([f64(i[2], 3) for i in imu]))
+        inn = np.fromiter((t.shape[0] for t in ts), np.int32, len(ts))
         pf = np.zeros((n, 16))
         pn = np.zeros((n, 16))
         so = np.zeros((n, 16))

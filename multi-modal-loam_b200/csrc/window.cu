@@ -169,7 +169,7 @@ extern "C" {
 
 // The mean of the pre-integration (dq, dp, dv, dt) does not depend on its covariance / Jacobian. The odometry loop
 // needs the mean first (it predicts the new frame's pose, which the undistortion of the scan waits for) and the rest
-// only when the window is pushed, so the mean can be formed alone (mean_only) and the full pre-integration afterwards,
+// only when the window is pushed, so the mean can be formed alone (mml_imu_preintegrate_mean) and the full pre-integration afterwards,
 // while the device already works on the scan. Both run the SAME compiled code for the mean (the helpers below are
 // not inlined), so the two results are identical to the bit.
 namespace {
@@ -203,8 +203,8 @@ __attribute__((noinline)) void imu_mean_update(Quat& dq, double* dp, double* dv,
 
 extern "C" {
 
-static int imu_preintegrate_impl(const double* t, const double* gyr, const double* acc, int n, double last_time,
-                                 const double* bg3, const double* ba3, bool mean_only, mml_preint* out) {
+int mml_imu_preintegrate(const double* t, const double* gyr, const double* acc, int n, double last_time,
+                         const double* bg3, const double* ba3, mml_preint* out) {
   if (!out || n < 0 || (n && (!t || !gyr || !acc)) || !bg3 || !ba3) return MML_ERR_INVALID;
   const double acc_n = 0.08, gyr_n = 0.004, acc_w = 2.0e-4, gyr_w = 2.0e-5;  // IMU.h:79-83
   Quat dq = {1, 0, 0, 0};
@@ -220,12 +220,6 @@ static int imu_preintegrate_impl(const double* t, const double* gyr, const doubl
     double g3[3], a3[3], dt, gdt[3], dR[9], Rq[9];
     imu_sample_terms(gyr, acc, t, s, current_time, bg3, ba3, g3, a3, &dt, gdt, dR);
     imu_rotation_of(dq, Rq);
-    if (mean_only) {
-      imu_mean_update(dq, dp, dv, Rq, a3, dt, dR);
-      dtime += dt;
-      current_time = t[s];
-      continue;
-    }
     const double dt2 = dt * dt;
     double Jr[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     const double nrm = sqrt((gdt[0] * gdt[0] + gdt[1] * gdt[1]) + gdt[2] * gdt[2]);
@@ -299,7 +293,6 @@ static int imu_preintegrate_impl(const double* t, const double* gyr, const doubl
   out->dq[0] = dq.w; out->dq[1] = dq.x; out->dq[2] = dq.y; out->dq[3] = dq.z;
   for (int k = 0; k < 3; k++) { out->dp[k] = dp[k]; out->dv[k] = dv[k]; out->bg[k] = bg3[k]; out->ba[k] = ba3[k]; }
   out->dt = dtime;
-  if (mean_only) return MML_OK;
   memcpy(out->cov, cov.data(), sizeof(out->cov));
   memcpy(out->jac, jac.data(), sizeof(out->jac));
   double inv[225], L[225];
@@ -324,13 +317,24 @@ int mml_imu_factor(const mml_preint* pre, const double* gravity3, const double* 
 }
 
 // PE.cpp:812-829. state = P(3) q_wxyz(4) V(3) bg(3) ba(3)
-int mml_imu_preintegrate(const double* t, const double* gyr, const double* acc, int n, double last_time,
-                         const double* bg3, const double* ba3, mml_preint* out) {
-  return imu_preintegrate_impl(t, gyr, acc, n, last_time, bg3, ba3, false, out);
-}
 int mml_imu_preintegrate_mean(const double* t, const double* gyr, const double* acc, int n, double last_time,
                               const double* bg3, const double* ba3, mml_preint* out) {
-  return imu_preintegrate_impl(t, gyr, acc, n, last_time, bg3, ba3, true, out);
+  if (!out || n < 0 || (n && (!t || !gyr || !acc)) || !bg3 || !ba3) return MML_ERR_INVALID;
+  // the mean steps of mml_imu_preintegrate alone (the same non-inlined helpers: the same bits), without its work arrays
+  Quat dq = {1, 0, 0, 0};
+  double dp[3] = {0, 0, 0}, dv[3] = {0, 0, 0}, dtime = 0, current_time = last_time;
+  for (int s = 0; s < n; s++) {
+    double g3[3], a3[3], dt, gdt[3], dR[9], Rq[9];
+    imu_sample_terms(gyr, acc, t, s, current_time, bg3, ba3, g3, a3, &dt, gdt, dR);
+    imu_rotation_of(dq, Rq);
+    imu_mean_update(dq, dp, dv, Rq, a3, dt, dR);
+    dtime += dt;
+    current_time = t[s];
+  }
+  out->dq[0] = dq.w; out->dq[1] = dq.x; out->dq[2] = dq.y; out->dq[3] = dq.z;
+  for (int k = 0; k < 3; k++) { out->dp[k] = dp[k]; out->dv[k] = dv[k]; out->bg[k] = bg3[k]; out->ba[k] = ba3[k]; }
+  out->dt = dtime;
+  return MML_OK;
 }
 
 int mml_imu_predict(const double* prev16, const mml_preint* pre, double* next16) {
